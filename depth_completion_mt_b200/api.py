@@ -1,0 +1,271 @@
+"""Host-side mirror of the reference's call surface on top of the C ABI (include/dcmt.h).
+
+Function names, argument meaning and error behaviour follow the reference:
+
+    img_completion(sparse, extr, blur_type)                         src/DC_lidar_only/img_completion.cpp:17
+    interpolate_with_superpixels(labels, sparse, blur_type, use_superpixel)
+                                                                    src/DC_lidar_camera/img_completion_lc.cpp:34
+    calculateMeasuementDerivatives / get_initial_disparity / optimize_IG /
+    retrieve_optimized_depth / stereo_refine                        src/DC_stereo_lidar/main_sl.cpp:715-885,1165-1253
+
+Inputs may be ``torch`` CUDA tensors (device entry points, asynchronous on the current stream) or
+``numpy`` arrays (``*_host`` entry points: H2D, compute, D2H, synchronous).  A leading batch dimension
+is optional everywhere: (rows, cols) or (n, rows, cols).  Outputs are returned (the reference's
+``cv::Mat&`` out-parameter).  All compute happens in libdcmt.so on the GPU; nothing here falls back.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import BLUR, PATH, STATS_STRIDE, StereoParams
+
+try:
+    import torch
+except Exception:  # pragma: no cover - torch is part of the image
+    torch = None
+
+
+def _is_torch(x) -> bool:
+    return torch is not None and isinstance(x, torch.Tensor)
+
+
+def _batch3(x, what: str):
+    if x.ndim == 2:
+        return x[None], True
+    if x.ndim == 3:
+        return x, False
+    raise ValueError(f"{what} must be (rows, cols) or (n, rows, cols), got shape {tuple(x.shape)}")
+
+
+def _blur_code(blur_type) -> int:
+    # img_completion.cpp:172-189: exactly "bilateral" / "gaussian", anything else means no blur
+    return BLUR.get(blur_type, 0) if isinstance(blur_type, str) else int(blur_type)
+
+
+def _stream_ptr(stream) -> int:
+    if stream is None:
+        return int(torch.cuda.current_stream().cuda_stream)
+    return int(getattr(stream, "cuda_stream", stream))
+
+
+def _prep_torch(x, dtype, what: str):
+    if not x.is_cuda:
+        raise ValueError(f"{what}: torch tensors must live on a CUDA device (use numpy arrays for host data)")
+    if x.dtype != dtype:
+        raise TypeError(f"{what} must be {dtype}, got {x.dtype}")
+    return x.contiguous()
+
+
+def _prep_numpy(x, dtype, what: str):
+    if not isinstance(x, np.ndarray):
+        raise TypeError(f"{what} must be a numpy array or a torch CUDA tensor")
+    if x.dtype != dtype:
+        raise TypeError(f"{what} must be {np.dtype(dtype)}, got {x.dtype}")
+    return np.ascontiguousarray(x)
+
+
+def _np_ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def img_completion(sparse, extr: bool = False, blur_type="gaussian", *, path: str = "auto", return_stats: bool = False,
+                   stream=None, lib: _lib.Library | None = None):
+    """img_completion(sparse_r_img, dense_r_img, extr, blur_type) -- img_completion.cpp:17-204.
+
+    ``extr`` is accepted and ignored exactly like the reference (:103 ``int densify = true``).
+    Returns ``dense`` (and an int32 (n, 4) stats array when ``return_stats``)."""
+    del extr
+    lib = lib or _lib.load()
+    blur = _blur_code(blur_type)
+    if _is_torch(sparse):
+        s = _prep_torch(sparse, torch.float32, "sparse")
+        s3, squeeze = _batch3(s, "sparse")
+        n, rows, cols = s3.shape
+        out = torch.empty_like(s3)
+        stats = torch.zeros((n, STATS_STRIDE), dtype=torch.int32, device=s.device) if return_stats else None
+        with torch.cuda.device(s.device):
+            lib.check(lib.dcmt_img_completion_f32(s3.data_ptr(), out.data_ptr(), rows, cols, 0, 0, n, blur, PATH[path],
+                                                  stats.data_ptr() if return_stats else None, _stream_ptr(stream)))
+    else:
+        s = _prep_numpy(sparse, np.float32, "sparse")
+        s3, squeeze = _batch3(s, "sparse")
+        n, rows, cols = s3.shape
+        out = np.empty_like(s3)
+        stats = np.zeros((n, STATS_STRIDE), np.int32) if return_stats else None
+        lib.check(lib.dcmt_img_completion_f32_host(_np_ptr(s3), _np_ptr(out), rows, cols, 0, 0, n, blur, PATH[path],
+                                                   _np_ptr(stats) if return_stats else None))
+    out = out[0] if squeeze else out
+    return (out, stats) if return_stats else out
+
+
+def interpolate_with_superpixels(labels, sparse, blur_type="gaussian", use_superpixel: int = 1, *, n_clusters=None,
+                                 return_stats: bool = False, stream=None, lib: _lib.Library | None = None):
+    """interpolate_with_superpixels(slic, sparse, dense, blur_type, use_superpixel) -- img_completion_lc.cpp:34-203.
+
+    ``labels`` stands for ``slic.clusters`` as an int32 [row][col] map (the reference indexes [col][row], :83);
+    ``n_clusters`` for ``slic.centers.size()`` (default: max label + 1).  ``blur_type`` is ignored, as in the
+    reference (:183-192 blurs unconditionally)."""
+    del blur_type
+    lib = lib or _lib.load()
+    if _is_torch(sparse):
+        s = _prep_torch(sparse, torch.float32, "sparse")
+        s3, squeeze = _batch3(s, "sparse")
+        n, rows, cols = s3.shape
+        lab_ptr = None
+        if use_superpixel:
+            lab = _prep_torch(labels, torch.int32, "labels")
+            lab3, _ = _batch3(lab, "labels")
+            if lab3.shape != s3.shape:
+                raise ValueError("labels and sparse shapes differ")
+            if n_clusters is None:
+                n_clusters = int(lab3.max().item()) + 1
+            lab_ptr = lab3.data_ptr()
+        out = torch.empty_like(s3)
+        stats = torch.zeros((n, STATS_STRIDE), dtype=torch.int32, device=s.device) if return_stats else None
+        with torch.cuda.device(s.device):
+            lib.check(lib.dcmt_interpolate_with_superpixels_f32(
+                s3.data_ptr(), lab_ptr, int(n_clusters or 0), out.data_ptr(), rows, cols, 0, 0, n, int(use_superpixel),
+                stats.data_ptr() if return_stats else None, _stream_ptr(stream)))
+    else:
+        s = _prep_numpy(sparse, np.float32, "sparse")
+        s3, squeeze = _batch3(s, "sparse")
+        n, rows, cols = s3.shape
+        lab_ptr = None
+        if use_superpixel:
+            lab3, _ = _batch3(_prep_numpy(labels, np.int32, "labels"), "labels")
+            if lab3.shape != s3.shape:
+                raise ValueError("labels and sparse shapes differ")
+            if n_clusters is None:
+                n_clusters = int(lab3.max()) + 1
+            lab_ptr = _np_ptr(lab3)
+        out = np.empty_like(s3)
+        stats = np.zeros((n, STATS_STRIDE), np.int32) if return_stats else None
+        lib.check(lib.dcmt_interpolate_with_superpixels_f32_host(
+            _np_ptr(s3), lab_ptr, int(n_clusters or 0), _np_ptr(out), rows, cols, 0, 0, n, int(use_superpixel),
+            _np_ptr(stats) if return_stats else None))
+    out = out[0] if squeeze else out
+    return (out, stats) if return_stats else out
+
+
+def stereo_params(official: bool = False, num_iterations: int | None = None, lib: _lib.Library | None = None,
+                  **overrides) -> StereoParams:
+    """main_sl.cpp literals (baseline .54, focal 959.791, damp 500, clip 255/100, 4 iterations, final blur) or the
+    main_sl_OFFICIAL.cpp set (damp 1370, clip 221/80, caller-supplied iterations, no blur)."""
+    lib = lib or _lib.load()
+    p = StereoParams()
+    if official:
+        lib.dcmt_stereo_params_official(C.byref(p), int(num_iterations if num_iterations is not None else 4))
+    else:
+        lib.dcmt_stereo_params_default(C.byref(p))
+        if num_iterations is not None:
+            p.num_iterations = int(num_iterations)
+    for k, v in overrides.items():
+        if not hasattr(p, k):
+            raise TypeError(f"unknown stereo parameter {k!r}")
+        setattr(p, k, v)
+    return p
+
+
+def stereo_refine(depth_ig, left_gray, right_gray, params: StereoParams | None = None, *, return_disparity: bool = False,
+                  stream=None, lib: _lib.Library | None = None):
+    """main_sl.cpp:1165-1253: gray images + initial dense depth -> refined (and blurred) depth."""
+    lib = lib or _lib.load()
+    prm = params or stereo_params(lib=lib)
+    if _is_torch(depth_ig):
+        d3, squeeze = _batch3(_prep_torch(depth_ig, torch.float32, "depth_ig"), "depth_ig")
+        l3, _ = _batch3(_prep_torch(left_gray, torch.uint8, "left_gray"), "left_gray")
+        r3, _ = _batch3(_prep_torch(right_gray, torch.uint8, "right_gray"), "right_gray")
+        if l3.shape != d3.shape or r3.shape != d3.shape:
+            raise ValueError("depth_ig, left_gray and right_gray shapes differ")
+        n, rows, cols = d3.shape
+        out = torch.empty_like(d3)
+        disp = torch.empty_like(d3) if return_disparity else None
+        with torch.cuda.device(d3.device):
+            lib.check(lib.dcmt_stereo_refine_f32(d3.data_ptr(), l3.data_ptr(), r3.data_ptr(), out.data_ptr(),
+                                                 disp.data_ptr() if return_disparity else None, rows, cols, n,
+                                                 C.byref(prm), _stream_ptr(stream)))
+    else:
+        d3, squeeze = _batch3(_prep_numpy(depth_ig, np.float32, "depth_ig"), "depth_ig")
+        l3, _ = _batch3(_prep_numpy(left_gray, np.uint8, "left_gray"), "left_gray")
+        r3, _ = _batch3(_prep_numpy(right_gray, np.uint8, "right_gray"), "right_gray")
+        if l3.shape != d3.shape or r3.shape != d3.shape:
+            raise ValueError("depth_ig, left_gray and right_gray shapes differ")
+        n, rows, cols = d3.shape
+        out = np.empty_like(d3)
+        disp = np.empty_like(d3) if return_disparity else None
+        lib.check(lib.dcmt_stereo_refine_f32_host(_np_ptr(d3), _np_ptr(l3), _np_ptr(r3), _np_ptr(out),
+                                                  _np_ptr(disp) if return_disparity else None, rows, cols, n, C.byref(prm)))
+    if squeeze:
+        out = out[0]
+        disp = disp[0] if return_disparity else None
+    return (out, disp) if return_disparity else out
+
+
+def _device_planes(lib, fn_name, arrays, n_out, extra, stream, out_like=None):
+    """Helper for the per-function stereo entry points (device pointers only in the ABI): numpy inputs are
+    staged through torch."""
+    first = arrays[0]
+    host = not _is_torch(first)
+    if host:
+        if torch is None or not torch.cuda.is_available():
+            raise _lib.DcmtError(_lib.DCMT_E_CUDA, "no CUDA device available; depth_completion_mt_b200 has no CPU fallback")
+        tens = [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in arrays]
+    else:
+        tens = [a.contiguous() for a in arrays]
+    t3 = [_batch3(t, "plane")[0] for t in tens]
+    squeeze = tens[0].ndim == 2
+    n, rows, cols = t3[0].shape
+    outs = [torch.empty_like(t3[0]) for _ in range(n_out)]
+    with torch.cuda.device(t3[0].device):
+        fn = getattr(lib, fn_name)
+        lib.check(fn(*[t.data_ptr() for t in t3], *[o.data_ptr() for o in outs], rows, cols, n, *extra, _stream_ptr(stream)))
+    outs = [o[0] if squeeze else o for o in outs]
+    if host:
+        outs = [o.cpu().numpy() for o in outs]
+    return outs
+
+
+def calculateMeasuementDerivatives(value, *, stream=None, lib: _lib.Library | None = None):
+    """calculateMeasuementDerivatives (sic), main_sl.cpp:715-745: value plane -> (dx, dy)."""
+    lib = lib or _lib.load()
+    dx, dy = _device_planes(lib, "dcmt_measurement_derivatives_f32", [value], 2, (), stream)
+    return dx, dy
+
+
+def get_initial_disparity(depth, baseline: float = 0.54, focal: float = 9.597910e02, *, stream=None,
+                          lib: _lib.Library | None = None):
+    """get_initial_disparity, main_sl.cpp:846-861."""
+    lib = lib or _lib.load()
+    return _device_planes(lib, "dcmt_get_initial_disparity_f32", [depth], 1, (baseline, focal), stream)[0]
+
+
+def retrieve_optimized_depth(disp, baseline: float = 0.54, focal: float = 9.597910e02, depth_clip: float = 100.0, *,
+                             stream=None, lib: _lib.Library | None = None):
+    """retrieve_optimized_depth, main_sl.cpp:863-885."""
+    lib = lib or _lib.load()
+    return _device_planes(lib, "dcmt_retrieve_optimized_depth_f32", [disp], 1, (baseline, focal, depth_clip), stream)[0]
+
+
+def optimize_IG(value_left, value_right, disp, num_iterations: int = 4, damp_factor: float = 500.0,
+                err_clip: float = 255.0, *, stream=None, lib: _lib.Library | None = None):
+    """optimize_IG, main_sl.cpp:804-843.  Returns the refined disparity (the reference updates it in place)."""
+    lib = lib or _lib.load()
+    host = not _is_torch(disp)
+    if host:
+        if torch is None or not torch.cuda.is_available():
+            raise _lib.DcmtError(_lib.DCMT_E_CUDA, "no CUDA device available; depth_completion_mt_b200 has no CPU fallback")
+        vl, vr, d = (torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (value_left, value_right, disp))
+    else:
+        vl, vr, d = value_left.contiguous(), value_right.contiguous(), disp.clone()
+    d3, squeeze = _batch3(d, "disp")
+    vl3, _ = _batch3(vl, "value_left")
+    vr3, _ = _batch3(vr, "value_right")
+    n, rows, cols = d3.shape
+    with torch.cuda.device(d3.device):
+        lib.check(lib.dcmt_optimize_ig_f32(vl3.data_ptr(), vr3.data_ptr(), d3.data_ptr(), rows, cols, n, int(num_iterations),
+                                           float(damp_factor), float(err_clip), _stream_ptr(stream)))
+    out = d3[0] if squeeze else d3
+    return out.cpu().numpy() if host else out

@@ -1,0 +1,450 @@
+// api.cu -- the C ABI of libdcmt.so (include/dcmt.h): argument validation, workspace cache,
+// chunking, path selection.  No compute happens on the host and there is no CPU fallback.
+#include "../../include/dcmt.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <map>
+#include <mutex>
+#include <utility>
+
+#include "common.cuh"
+#include "generic.cuh"
+#include "stereo.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    return fail(DCMT_E_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+#define API_CUDA(x, what)                                  \
+    do {                                                   \
+        cudaError_t e__ = (x);                             \
+        if (e__ != cudaSuccess) return cuda_fail(e__, what); \
+    } while (0)
+
+// ---- workspace cache: one grow-only device arena per (device, stream) ----
+struct Arena {
+    char* base = nullptr;
+    size_t cap = 0, used = 0;
+};
+std::mutex g_mu;
+std::map<std::pair<int, cudaStream_t>, Arena> g_arenas;
+
+int arena_acquire(cudaStream_t st, size_t bytes, Arena** out) {
+    int dev = 0;
+    API_CUDA(cudaGetDevice(&dev), "cudaGetDevice");
+    std::lock_guard<std::mutex> lk(g_mu);
+    Arena& a = g_arenas[{dev, st}];
+    if (a.cap < bytes) {
+        if (a.base) {
+            // work enqueued earlier on this stream may still use the old block
+            API_CUDA(cudaStreamSynchronize(st), "cudaStreamSynchronize");
+            cudaFree(a.base);
+            a.base = nullptr;
+            a.cap = 0;
+        }
+        void* p = nullptr;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) return fail(DCMT_E_NOMEM, "workspace of %zu bytes: %s", bytes, cudaGetErrorString(e));
+        a.base = static_cast<char*>(p);
+        a.cap = bytes;
+    }
+    a.used = 0;
+    *out = &a;
+    return DCMT_OK;
+}
+
+template <class T>
+T* carve(Arena* a, size_t count) {
+    const size_t bytes = (count * sizeof(T) + 255) & ~size_t(255);
+    T* p = reinterpret_cast<T*>(a->base + a->used);
+    a->used += bytes;
+    return p;
+}
+size_t carve_bytes(size_t count, size_t elem) { return (count * elem + 255) & ~size_t(255); }
+
+// frames per generic chunk: intermediates of one chunk (2 planes) stay L2-resident (126 MB)
+int generic_chunk_frames(int rows, int cols, int n_frames) {
+    static const long env = [] {
+        const char* s = getenv("DCMT_GENERIC_CHUNK");
+        return s ? atol(s) : 0L;
+    }();
+    long c = env > 0 ? env : (long)((8u << 20) / ((size_t)rows * cols) + 1);  // ~32 MB per plane
+    if (c < 1) c = 1;
+    if (c > 65535) c = 65535;
+    if (c > n_frames) c = n_frames;
+    return (int)c;
+}
+
+size_t generic_ws_bytes(int rows, int cols, int chunk, bool bilateral) {
+    const size_t fpix = (size_t)rows * cols;
+    size_t b = 2 * carve_bytes(fpix * chunk, sizeof(float)) + carve_bytes(chunk, sizeof(dcmt::FrameCounters));
+    if (bilateral) b += carve_bytes(2 * (size_t)chunk, sizeof(unsigned)) + carve_bytes(dcmt::generic_lut_floats() * chunk, sizeof(float));
+    return b;
+}
+
+bool overlaps(const void* a, size_t an, const void* b, size_t bn) {
+    const char* pa = static_cast<const char*>(a);
+    const char* pb = static_cast<const char*>(b);
+    return pa < pb + bn && pb < pa + an;
+}
+
+struct Geometry {
+    size_t pitch, fstride;  // elements
+    size_t span_bytes;      // bytes touched by the whole batch
+};
+
+int check_geometry(int rows, int cols, size_t pitch_bytes, size_t frame_stride_bytes, int n_frames, Geometry* g) {
+    if (rows < 1 || cols < 1) return fail(DCMT_E_BADARG, "rows and cols must be >= 1 (got %d x %d)", rows, cols);
+    if (n_frames < 0) return fail(DCMT_E_BADARG, "n_frames must be >= 0 (got %d)", n_frames);
+    if ((size_t)rows * (size_t)cols > (size_t)1 << 30) return fail(DCMT_E_UNSUPPORTED, "frame larger than 2^30 pixels");
+    if (pitch_bytes == 0) pitch_bytes = (size_t)cols * sizeof(float);
+    if (pitch_bytes % sizeof(float) != 0 || pitch_bytes < (size_t)cols * sizeof(float))
+        return fail(DCMT_E_BADARG, "pitch_bytes %zu invalid for %d float columns", pitch_bytes, cols);
+    if (frame_stride_bytes == 0) frame_stride_bytes = pitch_bytes * rows;
+    if (frame_stride_bytes % sizeof(float) != 0 || frame_stride_bytes < pitch_bytes * (size_t)(rows - 1) + (size_t)cols * sizeof(float))
+        return fail(DCMT_E_BADARG, "frame_stride_bytes %zu invalid", frame_stride_bytes);
+    g->pitch = pitch_bytes / sizeof(float);
+    g->fstride = frame_stride_bytes / sizeof(float);
+    g->span_bytes = n_frames ? frame_stride_bytes * (size_t)(n_frames - 1) + pitch_bytes * (size_t)(rows - 1) + (size_t)cols * sizeof(float) : 0;
+    return DCMT_OK;
+}
+
+int check_device() {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n < 1)
+        return fail(DCMT_E_CUDA, "no CUDA device available (%s); libdcmt has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    return DCMT_OK;
+}
+
+// shared driver of (a1) and (a2)
+int run_completion(const float* sparse, const int32_t* labels, int n_clusters, bool guided, float* dense, int rows,
+                   int cols, size_t pitch_bytes, size_t frame_stride_bytes, int n_frames, int blur_type, int flags,
+                   int32_t* stats, float* stages, uint32_t* stage_mask, cudaStream_t st) {
+    if (!sparse || !dense) return fail(DCMT_E_BADARG, "null image pointer");
+    if (guided && !labels) return fail(DCMT_E_BADARG, "null label pointer");
+    if (blur_type < DCMT_BLUR_NONE || blur_type > DCMT_BLUR_BILATERAL) return fail(DCMT_E_BADARG, "blur_type %d", blur_type);
+    if (flags < DCMT_PATH_AUTO || flags > DCMT_PATH_FUSED) return fail(DCMT_E_BADARG, "flags %d", flags);
+    Geometry g;
+    int rc = check_geometry(rows, cols, pitch_bytes, frame_stride_bytes, n_frames, &g);
+    if (rc) return rc;
+    if (n_frames == 0) return DCMT_OK;
+    if (overlaps(sparse, g.span_bytes, dense, g.span_bytes)) return fail(DCMT_E_BADARG, "input and output overlap");
+    if ((rc = check_device())) return rc;
+    API_CUDA(dcmt::generic_configure(), "kernel attribute setup");
+
+    const int chunk = generic_chunk_frames(rows, cols, n_frames);
+    const bool bilateral = blur_type == DCMT_BLUR_BILATERAL;
+    Arena* ar = nullptr;
+    if ((rc = arena_acquire(st, generic_ws_bytes(rows, cols, chunk, bilateral), &ar))) return rc;
+    const size_t fpix = (size_t)rows * cols;
+    float* w1 = carve<float>(ar, fpix * chunk);
+    float* w2 = carve<float>(ar, fpix * chunk);
+    dcmt::FrameCounters* ctr = carve<dcmt::FrameCounters>(ar, chunk);
+    unsigned* mm = bilateral ? carve<unsigned>(ar, 2 * (size_t)chunk) : nullptr;
+    float* lut = bilateral ? carve<float>(ar, dcmt::generic_lut_floats() * chunk) : nullptr;
+
+    for (int f0 = 0; f0 < n_frames; f0 += chunk) {
+        const int nf = n_frames - f0 < chunk ? n_frames - f0 : chunk;
+        dcmt::GenericChunk c{};
+        c.in = sparse + (size_t)f0 * g.fstride;
+        c.in_pitch = g.pitch;
+        c.in_fstride = g.fstride;
+        c.labels = guided ? labels + (size_t)f0 * fpix : nullptr;
+        c.n_clusters = n_clusters;
+        c.guided = guided;
+        c.out = dense + (size_t)f0 * g.fstride;
+        c.out_pitch = g.pitch;
+        c.out_fstride = g.fstride;
+        c.rows = rows;
+        c.cols = cols;
+        c.n_frames = nf;
+        c.blur = blur_type;
+        c.w1 = w1;
+        c.w2 = w2;
+        c.ctr = ctr;
+        c.minmax = mm;
+        c.lut = lut;
+        c.stats = stats ? stats + (size_t)f0 * DCMT_STATS_STRIDE : nullptr;
+        c.stages = stages;
+        c.stage_mask = stage_mask;
+        c.skip_front = false;
+        API_CUDA(dcmt::generic_run_chunk(c, st), "generic pipeline launch");
+    }
+    return DCMT_OK;
+}
+
+// host-pointer wrapper: stage through the arena of the default stream
+template <class Fn>
+int with_device_copies(const float* h_in, float* h_out, size_t span_bytes, const int32_t* h_labels, size_t label_bytes,
+                       int32_t* h_stats, int n_frames, Fn&& fn) {
+    int rc = check_device();
+    if (rc) return rc;
+    float *d_in = nullptr, *d_out = nullptr;
+    int32_t *d_lab = nullptr, *d_stats = nullptr;
+    auto cleanup = [&] { cudaFree(d_in); cudaFree(d_out); cudaFree(d_lab); cudaFree(d_stats); };
+    cudaError_t e;
+    if ((e = cudaMalloc(&d_in, span_bytes)) != cudaSuccess || (e = cudaMalloc(&d_out, span_bytes)) != cudaSuccess ||
+        (label_bytes && (e = cudaMalloc(&d_lab, label_bytes)) != cudaSuccess) ||
+        (h_stats && (e = cudaMalloc(&d_stats, (size_t)n_frames * DCMT_STATS_STRIDE * sizeof(int32_t))) != cudaSuccess)) {
+        cleanup();
+        return fail(DCMT_E_NOMEM, "device staging buffers: %s", cudaGetErrorString(e));
+    }
+    if ((e = cudaMemcpy(d_in, h_in, span_bytes, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (label_bytes && (e = cudaMemcpy(d_lab, h_labels, label_bytes, cudaMemcpyHostToDevice)) != cudaSuccess)) {
+        cleanup();
+        return cuda_fail(e, "host to device copy");
+    }
+    // rows of `dense` beyond cols (pitch padding) are preserved: start from the caller's bytes
+    if ((e = cudaMemcpy(d_out, h_out, span_bytes, cudaMemcpyHostToDevice)) != cudaSuccess) { cleanup(); return cuda_fail(e, "host to device copy"); }
+    rc = fn(d_in, d_out, d_lab, d_stats);
+    if (rc == DCMT_OK) {
+        if ((e = cudaStreamSynchronize(nullptr)) != cudaSuccess) rc = cuda_fail(e, "kernel execution");
+        else if ((e = cudaMemcpy(h_out, d_out, span_bytes, cudaMemcpyDeviceToHost)) != cudaSuccess) rc = cuda_fail(e, "device to host copy");
+        else if (h_stats && (e = cudaMemcpy(h_stats, d_stats, (size_t)n_frames * DCMT_STATS_STRIDE * sizeof(int32_t), cudaMemcpyDeviceToHost)) != cudaSuccess)
+            rc = cuda_fail(e, "device to host copy");
+    }
+    cleanup();
+    return rc;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dcmt_version(void) { return DCMT_VERSION; }
+const char* dcmt_last_error(void) { return g_err; }
+
+const char* dcmt_status_string(int status) {
+    switch (status) {
+        case DCMT_OK: return "ok";
+        case DCMT_E_BADARG: return "bad argument";
+        case DCMT_E_UNSUPPORTED: return "unsupported";
+        case DCMT_E_CUDA: return "CUDA error";
+        case DCMT_E_NOMEM: return "out of device memory";
+        default: return "unknown status";
+    }
+}
+
+int dcmt_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceCount");
+    return n;
+}
+
+int dcmt_release_workspaces(void) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (auto& kv : g_arenas)
+        if (kv.second.base) cudaFree(kv.second.base);
+    g_arenas.clear();
+    return DCMT_OK;
+}
+
+size_t dcmt_workspace_bytes(int rows, int cols, int n_frames) {
+    if (rows < 1 || cols < 1 || n_frames < 1) return 0;
+    return generic_ws_bytes(rows, cols, generic_chunk_frames(rows, cols, n_frames), true);
+}
+
+int dcmt_img_completion_f32(const float* sparse, float* dense, int rows, int cols, size_t pitch_bytes,
+                            size_t frame_stride_bytes, int n_frames, int blur_type, int flags, int32_t* stats,
+                            void* cuda_stream) {
+    return run_completion(sparse, nullptr, 0, false, dense, rows, cols, pitch_bytes, frame_stride_bytes, n_frames, blur_type,
+                          flags, stats, nullptr, nullptr, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int dcmt_img_completion_f32_host(const float* sparse, float* dense, int rows, int cols, size_t pitch_bytes,
+                                 size_t frame_stride_bytes, int n_frames, int blur_type, int flags, int32_t* stats) {
+    if (!sparse || !dense) return fail(DCMT_E_BADARG, "null image pointer");
+    Geometry g;
+    int rc = check_geometry(rows, cols, pitch_bytes, frame_stride_bytes, n_frames, &g);
+    if (rc) return rc;
+    if (n_frames == 0) return DCMT_OK;
+    if (overlaps(sparse, g.span_bytes, dense, g.span_bytes)) return fail(DCMT_E_BADARG, "input and output overlap");
+    return with_device_copies(sparse, dense, g.span_bytes, nullptr, 0, stats, n_frames,
+                              [&](float* d_in, float* d_out, int32_t*, int32_t* d_stats) {
+                                  return dcmt_img_completion_f32(d_in, d_out, rows, cols, pitch_bytes, frame_stride_bytes,
+                                                                 n_frames, blur_type, flags, d_stats, nullptr);
+                              });
+}
+
+int dcmt_interpolate_with_superpixels_f32(const float* sparse, const int32_t* labels, int n_clusters, float* dense,
+                                          int rows, int cols, size_t pitch_bytes, size_t frame_stride_bytes, int n_frames,
+                                          int use_superpixel, int32_t* stats, void* cuda_stream) {
+    // blur is unconditionally Gaussian in the reference (img_completion_lc.cpp:183-192)
+    return run_completion(sparse, labels, n_clusters, use_superpixel != 0, dense, rows, cols, pitch_bytes,
+                          frame_stride_bytes, n_frames, DCMT_BLUR_GAUSSIAN, DCMT_PATH_GENERIC, stats, nullptr, nullptr,
+                          static_cast<cudaStream_t>(cuda_stream));
+}
+
+int dcmt_interpolate_with_superpixels_f32_host(const float* sparse, const int32_t* labels, int n_clusters, float* dense,
+                                               int rows, int cols, size_t pitch_bytes, size_t frame_stride_bytes,
+                                               int n_frames, int use_superpixel, int32_t* stats) {
+    if (!sparse || !dense) return fail(DCMT_E_BADARG, "null image pointer");
+    if (use_superpixel && !labels) return fail(DCMT_E_BADARG, "null label pointer");
+    Geometry g;
+    int rc = check_geometry(rows, cols, pitch_bytes, frame_stride_bytes, n_frames, &g);
+    if (rc) return rc;
+    if (n_frames == 0) return DCMT_OK;
+    if (overlaps(sparse, g.span_bytes, dense, g.span_bytes)) return fail(DCMT_E_BADARG, "input and output overlap");
+    const size_t label_bytes = use_superpixel ? (size_t)rows * cols * n_frames * sizeof(int32_t) : 0;
+    return with_device_copies(sparse, dense, g.span_bytes, labels, label_bytes, stats, n_frames,
+                              [&](float* d_in, float* d_out, int32_t* d_lab, int32_t* d_stats) {
+                                  return dcmt_interpolate_with_superpixels_f32(d_in, d_lab, n_clusters, d_out, rows, cols,
+                                                                               pitch_bytes, frame_stride_bytes, n_frames,
+                                                                               use_superpixel, d_stats, nullptr);
+                              });
+}
+
+int dcmt_img_completion_stages_f32(const float* sparse, float* dense, int rows, int cols, int blur_type, float* stages,
+                                   int n_stages, uint32_t* stage_mask_out, void* cuda_stream) {
+    if (!stages || n_stages < dcmt::kOracleStages) return fail(DCMT_E_BADARG, "stages buffer must hold %d planes", dcmt::kOracleStages);
+    uint32_t mask = 0;
+    int rc = run_completion(sparse, nullptr, 0, false, dense, rows, cols, 0, 0, 1, blur_type, DCMT_PATH_GENERIC, nullptr,
+                            stages, &mask, static_cast<cudaStream_t>(cuda_stream));
+    if (stage_mask_out) *stage_mask_out = mask;
+    return rc;
+}
+
+void dcmt_stereo_params_default(dcmt_stereo_params* p) {
+    if (!p) return;
+    p->baseline = 0.54f;
+    p->focal = 9.597910e+02f;
+    p->damp_factor = 500.0f;
+    p->err_clip = 255.0f;
+    p->depth_clip = 100.0f;
+    p->num_iterations = 4;
+    p->final_gauss = 1;
+}
+
+void dcmt_stereo_params_official(dcmt_stereo_params* p, int num_iterations) {
+    if (!p) return;
+    dcmt_stereo_params_default(p);
+    p->damp_factor = 1370.0f;
+    p->err_clip = 221.0f;
+    p->depth_clip = 80.0f;
+    p->num_iterations = num_iterations;
+    p->final_gauss = 0;
+}
+
+static int check_planes(int rows, int cols, int n_frames) {
+    if (rows < 1 || cols < 1) return fail(DCMT_E_BADARG, "rows and cols must be >= 1 (got %d x %d)", rows, cols);
+    if (n_frames < 0) return fail(DCMT_E_BADARG, "n_frames must be >= 0 (got %d)", n_frames);
+    return DCMT_OK;
+}
+
+int dcmt_stereo_refine_f32(const float* depth_ig, const uint8_t* left_gray, const uint8_t* right_gray, float* depth_out,
+                           float* disp_out, int rows, int cols, int n_frames, const dcmt_stereo_params* prm,
+                           void* cuda_stream) {
+    if (!depth_ig || !left_gray || !right_gray || !depth_out || !prm) return fail(DCMT_E_BADARG, "null pointer");
+    int rc = check_planes(rows, cols, n_frames);
+    if (rc) return rc;
+    if (prm->num_iterations < 0) return fail(DCMT_E_BADARG, "num_iterations %d", prm->num_iterations);
+    if (n_frames == 0) return DCMT_OK;
+    const size_t bytes = (size_t)rows * cols * n_frames * sizeof(float);
+    if (overlaps(depth_ig, bytes, depth_out, bytes)) return fail(DCMT_E_BADARG, "input and output overlap");
+    if ((rc = check_device())) return rc;
+    API_CUDA(dcmt::stereo_refine(depth_ig, left_gray, right_gray, depth_out, disp_out, rows, cols, n_frames, prm->baseline,
+                                 prm->focal, prm->damp_factor, prm->err_clip, prm->depth_clip, prm->num_iterations,
+                                 prm->final_gauss, static_cast<cudaStream_t>(cuda_stream)),
+             "stereo refine launch");
+    return DCMT_OK;
+}
+
+int dcmt_stereo_refine_f32_host(const float* depth_ig, const uint8_t* left_gray, const uint8_t* right_gray,
+                                float* depth_out, float* disp_out, int rows, int cols, int n_frames,
+                                const dcmt_stereo_params* prm) {
+    if (!depth_ig || !left_gray || !right_gray || !depth_out || !prm) return fail(DCMT_E_BADARG, "null pointer");
+    int rc = check_planes(rows, cols, n_frames);
+    if (rc) return rc;
+    if (n_frames == 0) return DCMT_OK;
+    if ((rc = check_device())) return rc;
+    const size_t n = (size_t)rows * cols * n_frames;
+    float *d_ig = nullptr, *d_out = nullptr, *d_disp = nullptr;
+    uint8_t *d_l = nullptr, *d_r = nullptr;
+    auto cleanup = [&] { cudaFree(d_ig); cudaFree(d_out); cudaFree(d_disp); cudaFree(d_l); cudaFree(d_r); };
+    cudaError_t e;
+    if ((e = cudaMalloc(&d_ig, n * 4)) != cudaSuccess || (e = cudaMalloc(&d_out, n * 4)) != cudaSuccess ||
+        (disp_out && (e = cudaMalloc(&d_disp, n * 4)) != cudaSuccess) || (e = cudaMalloc(&d_l, n)) != cudaSuccess ||
+        (e = cudaMalloc(&d_r, n)) != cudaSuccess) {
+        cleanup();
+        return fail(DCMT_E_NOMEM, "device staging buffers: %s", cudaGetErrorString(e));
+    }
+    if ((e = cudaMemcpy(d_ig, depth_ig, n * 4, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMemcpy(d_l, left_gray, n, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMemcpy(d_r, right_gray, n, cudaMemcpyHostToDevice)) != cudaSuccess) {
+        cleanup();
+        return cuda_fail(e, "host to device copy");
+    }
+    rc = dcmt_stereo_refine_f32(d_ig, d_l, d_r, d_out, d_disp, rows, cols, n_frames, prm, nullptr);
+    if (rc == DCMT_OK) {
+        if ((e = cudaStreamSynchronize(nullptr)) != cudaSuccess) rc = cuda_fail(e, "kernel execution");
+        else if ((e = cudaMemcpy(depth_out, d_out, n * 4, cudaMemcpyDeviceToHost)) != cudaSuccess) rc = cuda_fail(e, "device to host copy");
+        else if (disp_out && (e = cudaMemcpy(disp_out, d_disp, n * 4, cudaMemcpyDeviceToHost)) != cudaSuccess) rc = cuda_fail(e, "device to host copy");
+    }
+    cleanup();
+    return rc;
+}
+
+int dcmt_measurement_derivatives_f32(const float* value, float* dx, float* dy, int rows, int cols, int n_frames,
+                                     void* cuda_stream) {
+    if (!value || !dx) return fail(DCMT_E_BADARG, "null pointer");
+    int rc = check_planes(rows, cols, n_frames);
+    if (rc) return rc;
+    if ((rc = check_device())) return rc;
+    API_CUDA(dcmt::stereo_measurement_derivatives(value, dx, dy, rows, cols, n_frames, static_cast<cudaStream_t>(cuda_stream)),
+             "measurement derivatives launch");
+    return DCMT_OK;
+}
+
+int dcmt_get_initial_disparity_f32(const float* depth, float* disp, int rows, int cols, int n_frames, float baseline,
+                                   float focal, void* cuda_stream) {
+    if (!depth || !disp) return fail(DCMT_E_BADARG, "null pointer");
+    int rc = check_planes(rows, cols, n_frames);
+    if (rc) return rc;
+    if ((rc = check_device())) return rc;
+    API_CUDA(dcmt::stereo_get_initial_disparity(depth, disp, rows, cols, n_frames, baseline, focal, static_cast<cudaStream_t>(cuda_stream)),
+             "initial disparity launch");
+    return DCMT_OK;
+}
+
+int dcmt_optimize_ig_f32(const float* value_left, const float* value_right, float* disp, int rows, int cols, int n_frames,
+                         int num_iterations, float damp_factor, float err_clip, void* cuda_stream) {
+    if (!value_left || !value_right || !disp) return fail(DCMT_E_BADARG, "null pointer");
+    int rc = check_planes(rows, cols, n_frames);
+    if (rc) return rc;
+    if (num_iterations < 0) return fail(DCMT_E_BADARG, "num_iterations %d", num_iterations);
+    if ((rc = check_device())) return rc;
+    API_CUDA(dcmt::stereo_optimize_ig(value_left, value_right, disp, rows, cols, n_frames, num_iterations, damp_factor,
+                                      err_clip, static_cast<cudaStream_t>(cuda_stream)),
+             "optimize_IG launch");
+    return DCMT_OK;
+}
+
+int dcmt_retrieve_optimized_depth_f32(const float* disp, float* depth, int rows, int cols, int n_frames, float baseline,
+                                      float focal, float depth_clip, void* cuda_stream) {
+    if (!disp || !depth) return fail(DCMT_E_BADARG, "null pointer");
+    int rc = check_planes(rows, cols, n_frames);
+    if (rc) return rc;
+    if ((rc = check_device())) return rc;
+    API_CUDA(dcmt::stereo_retrieve_depth(disp, depth, rows, cols, n_frames, baseline, focal, depth_clip, static_cast<cudaStream_t>(cuda_stream)),
+             "retrieve depth launch");
+    return DCMT_OK;
+}
+
+}  // extern "C"

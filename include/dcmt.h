@@ -1,0 +1,158 @@
+/*
+ * dcmt.h -- C ABI of libdcmt.so: the B200 (sm_100a) replacement for the depth-completion hot path of
+ * PatrizioPerugini/depth_completion_MT.
+ *
+ * The reference has no FFI layer: its hot path is three groups of free C++ functions on cv::Mat
+ *   (a1) img_completion                    src/DC_lidar_only/img_completion.cpp:17-20
+ *   (a2) interpolate_with_superpixels      src/DC_lidar_camera/img_completion_lc.cpp:34-38
+ *   (a4-a9) calculateMeasuementDerivatives / get_initial_disparity / optimize_IG /
+ *           retrieve_optimized_depth / final GaussianBlur
+ *                                          src/DC_stereo_lidar/main_sl.cpp:715,747,804,846,863,1253
+ * Each entry point below names the reference function it replaces.  include/img_completion.h is
+ * the C++ shim that keeps the reference's own signatures on top of this ABI.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch/OpenCV types cross this boundary;
+ *   - every function returns DCMT_OK (0) or a negative DCMT_E_* code, never throws, never prints;
+ *     dcmt_last_error() returns a thread-local description of the last failure;
+ *   - un-suffixed entry points take DEVICE pointers, enqueue all work on `cuda_stream`
+ *     (a cudaStream_t passed as void*, NULL = legacy default stream) and return without
+ *     synchronising; `*_host` variants take HOST pointers, copy in/out and synchronise;
+ *   - images are row-major float32 (CV_32FC1), `pitch_bytes` between rows (0 = cols*4),
+ *     `frame_stride_bytes` between consecutive frames of a batch (0 = rows*pitch);
+ *   - input and output must not alias; the library keeps a cached per-(device,stream) workspace,
+ *     nothing else is retained after return;
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     DCMT_E_CUDA.
+ */
+#ifndef DCMT_H_
+#define DCMT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define DCMT_API
+#else
+#define DCMT_API __attribute__((visibility("default")))
+#endif
+
+#define DCMT_VERSION 100 /* 0.1.0 */
+
+enum {
+    DCMT_OK = 0,
+    DCMT_E_BADARG = -1,      /* null pointer, non-positive size, bad pitch, aliasing in/out */
+    DCMT_E_UNSUPPORTED = -2, /* valid request this build cannot serve */
+    DCMT_E_CUDA = -3,        /* CUDA runtime error (see dcmt_last_error) */
+    DCMT_E_NOMEM = -4        /* workspace allocation failed */
+};
+
+/* blur_type of img_completion (img_completion.cpp:172-189): any string other than "gaussian" /
+ * "bilateral" means no blur. */
+enum { DCMT_BLUR_NONE = 0, DCMT_BLUR_GAUSSIAN = 1, DCMT_BLUR_BILATERAL = 2 };
+
+/* kernel path selection (flags argument) */
+enum {
+    DCMT_PATH_AUTO = 0,    /* fused q8 strip kernel when the frame qualifies, generic otherwise */
+    DCMT_PATH_GENERIC = 1, /* force the generic float32 multi-kernel pipeline */
+    DCMT_PATH_FUSED = 2    /* force the fused kernel (frames that do not qualify are still redone generically) */
+};
+
+/* per-frame statistics, DCMT_STATS_STRIDE int32 per frame (device memory for the async entry
+ * points, host memory for *_host), all optional (NULL):
+ *   [0] passes the reference's `while` loop executes (img_completion.cpp:146-166), >= 1
+ *   [1] holes counted by the first loop pass (= holes left after the first 31x31 fill)
+ *   [2] holes counted by the first 31x31 fill (= holes left after column extrapolation)
+ *   [3] path that produced the frame: 0 generic, 1 fused q8 */
+#define DCMT_STATS_STRIDE 4
+
+DCMT_API int dcmt_version(void);
+DCMT_API const char *dcmt_last_error(void);
+DCMT_API const char *dcmt_status_string(int status);
+/* number of visible CUDA devices, or a negative DCMT_E_CUDA */
+DCMT_API int dcmt_device_count(void);
+/* frees every cached workspace of the calling process (all devices) */
+DCMT_API int dcmt_release_workspaces(void);
+/* bytes of device workspace the library caches for a call of this shape */
+DCMT_API size_t dcmt_workspace_bytes(int rows, int cols, int n_frames);
+
+/* (a1) replaces img_completion(const cv::Mat&, cv::Mat&, const bool& extr, const std::string&)
+ * -- src/DC_lidar_only/img_completion.cpp:17-204.  `extr` is ignored by the reference (:103) and
+ * has no counterpart here. */
+DCMT_API int dcmt_img_completion_f32(const float *sparse, float *dense, int rows, int cols, size_t pitch_bytes,
+                                     size_t frame_stride_bytes, int n_frames, int blur_type, int flags,
+                                     int32_t *stats_or_null, void *cuda_stream);
+DCMT_API int dcmt_img_completion_f32_host(const float *sparse, float *dense, int rows, int cols, size_t pitch_bytes,
+                                          size_t frame_stride_bytes, int n_frames, int blur_type, int flags,
+                                          int32_t *stats_or_null);
+
+/* (a2) replaces interpolate_with_superpixels(Slic&, const cv::Mat&, cv::Mat&, const std::string&, int)
+ * -- src/DC_lidar_camera/img_completion_lc.cpp:34-203.  `labels` is the Slic::clusters label map as
+ * row-major int32 [row][col] (the reference stores [col][row], :83; the C++ shim transposes),
+ * `n_clusters` = slic.centers.size(); labels outside [0, n_clusters) are never selected.  The
+ * reference ignores blur_type here (Gaussian is unconditional, :183-192). */
+DCMT_API int dcmt_interpolate_with_superpixels_f32(const float *sparse, const int32_t *labels, int n_clusters,
+                                                   float *dense, int rows, int cols, size_t pitch_bytes,
+                                                   size_t frame_stride_bytes, int n_frames, int use_superpixel,
+                                                   int32_t *stats_or_null, void *cuda_stream);
+DCMT_API int dcmt_interpolate_with_superpixels_f32_host(const float *sparse, const int32_t *labels, int n_clusters,
+                                                        float *dense, int rows, int cols, size_t pitch_bytes,
+                                                        size_t frame_stride_bytes, int n_frames, int use_superpixel,
+                                                        int32_t *stats_or_null);
+
+/* parameters of the stereo refinement; dcmt_stereo_params_default() fills the values hard-coded in
+ * main_sl.cpp, dcmt_stereo_params_official() those of main_sl_OFFICIAL.cpp:832-918. */
+typedef struct dcmt_stereo_params {
+    float baseline;         /* 0.54        main_sl.cpp:848,866 */
+    float focal;            /* 959.791     main_sl.cpp:849,867 */
+    float damp_factor;      /* 500   (OFFICIAL 1370)   :808 */
+    float err_clip;         /* 255   (OFFICIAL 221)    :820-825 */
+    float depth_clip;       /* 100   (OFFICIAL 80)     :875 */
+    int32_t num_iterations; /* 4                       :805 */
+    int32_t final_gauss;    /* 1     (OFFICIAL 0)      :1253 */
+} dcmt_stereo_params;
+DCMT_API void dcmt_stereo_params_default(dcmt_stereo_params *p);
+DCMT_API void dcmt_stereo_params_official(dcmt_stereo_params *p, int num_iterations);
+
+/* (a3-a9) replaces the sequence main_sl.cpp:1165-1253: EntryType fill from the two gray images,
+ * calculateMeasuementDerivatives (:715), get_initial_disparity (:846), optimize_IG (:804, with
+ * calculateObservationDerivatives :747 inlined), retrieve_optimized_depth (:863), GaussianBlur (:1253).
+ * gray planes are uint8 row-major with pitch = cols; depth planes float32 with pitch = cols*4.
+ * disp_out_or_null receives the refined disparity (the reference's disparity_IG after :1240). */
+DCMT_API int dcmt_stereo_refine_f32(const float *depth_ig, const uint8_t *left_gray, const uint8_t *right_gray,
+                                    float *depth_out, float *disp_out_or_null, int rows, int cols, int n_frames,
+                                    const dcmt_stereo_params *params, void *cuda_stream);
+DCMT_API int dcmt_stereo_refine_f32_host(const float *depth_ig, const uint8_t *left_gray, const uint8_t *right_gray,
+                                         float *depth_out, float *disp_out_or_null, int rows, int cols, int n_frames,
+                                         const dcmt_stereo_params *params);
+
+/* the individual stereo functions, for callers that use them one by one (device pointers) */
+/* (a4) calculateMeasuementDerivatives, main_sl.cpp:715-745: value plane -> dx, dy planes */
+DCMT_API int dcmt_measurement_derivatives_f32(const float *value, float *dx, float *dy, int rows, int cols,
+                                              int n_frames, void *cuda_stream);
+/* (a5) get_initial_disparity, main_sl.cpp:846-861 (output pre-zeroed as at :1191) */
+DCMT_API int dcmt_get_initial_disparity_f32(const float *depth, float *disp, int rows, int cols, int n_frames,
+                                            float baseline, float focal, void *cuda_stream);
+/* (a6+a7) optimize_IG, main_sl.cpp:804-843: value planes of both images, disparity in place */
+DCMT_API int dcmt_optimize_ig_f32(const float *value_left, const float *value_right, float *disp, int rows, int cols,
+                                  int n_frames, int num_iterations, float damp_factor, float err_clip,
+                                  void *cuda_stream);
+/* (a8) retrieve_optimized_depth, main_sl.cpp:863-885 (output pre-zeroed as at :1244) */
+DCMT_API int dcmt_retrieve_optimized_depth_f32(const float *disp, float *depth, int rows, int cols, int n_frames,
+                                               float baseline, float focal, float depth_clip, void *cuda_stream);
+
+/* debugging aid: runs the generic pipeline on ONE frame and snapshots intermediate images
+ * (device memory, n_stages * rows * cols floats, stage order of oracle/dcmt_oracle.c; stages the
+ * kernels never materialise are left untouched).  `stage_mask_out` (host) gets a bit per stage written. */
+DCMT_API int dcmt_img_completion_stages_f32(const float *sparse, float *dense, int rows, int cols, int blur_type,
+                                            float *stages, int n_stages, uint32_t *stage_mask_out,
+                                            void *cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DCMT_H_ */

@@ -1,0 +1,96 @@
+"""The C-ABI boundary (include/dcmt.h): the library loads, exports every declared symbol, validates
+arguments with the documented codes and -- on a machine without a GPU -- refuses to compute instead
+of falling back to the CPU."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from depth_completion_mt_b200 import _lib, build
+from tests.conftest import ROOT
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "dcmt.h")).read()
+    return sorted(set(re.findall(r"DCMT_API\s+[\w\s\*]+?\b(dcmt_\w+)\s*\(", text)))
+
+
+@pytest.fixture(scope="module")
+def product_lib():
+    return _lib.bind(build.build_library())
+
+
+def test_header_symbols_match_binding():
+    assert declared_symbols() == sorted(_lib.EXPORTED_SYMBOLS)
+
+
+def test_library_exports_every_declared_symbol(product_lib):
+    out = subprocess.run(["nm", "-D", "--defined-only", product_lib.path], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r"\bT (dcmt_\w+)", out))
+    assert set(declared_symbols()) <= exported
+    assert not [s for s in exported if "oracle" in s], "the product must not link the oracle"
+    assert product_lib.dcmt_version() == 100
+
+
+def test_product_is_sm100a_cuda_and_does_not_link_oracle(product_lib):
+    sass = subprocess.run(["cuobjdump", "-lelf", product_lib.path], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass, sass
+    ldd = subprocess.run(["ldd", product_lib.path], capture_output=True, text=True).stdout
+    assert "oracle" not in ldd and "opencv" not in ldd.lower()
+
+
+def test_no_cpu_fallback_without_gpu(product_lib):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    s = np.zeros((8, 8), np.float32)
+    out = np.empty_like(s)
+    rc = product_lib.dcmt_img_completion_f32_host(s.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), 8, 8, 0, 0, 1, 1, 0, None)
+    assert rc == _lib.DCMT_E_CUDA
+    assert b"no CPU fallback" in product_lib.dcmt_last_error()
+    with pytest.raises(_lib.DcmtError):
+        from depth_completion_mt_b200 import api
+
+        api.img_completion(s, lib=product_lib)
+
+
+def test_argument_validation(emu_lib):
+    """error behaviour of the ABI (validated before any device work; exercised on the emulator build)."""
+    lib = emu_lib
+    s = np.zeros((8, 8), np.float32)
+    o = np.empty_like(s)
+    sp, op = s.ctypes.data_as(C.c_void_p), o.ctypes.data_as(C.c_void_p)
+    call = lib.dcmt_img_completion_f32_host
+    assert call(None, op, 8, 8, 0, 0, 1, 1, 0, None) == _lib.DCMT_E_BADARG
+    assert call(sp, op, 0, 8, 0, 0, 1, 1, 0, None) == _lib.DCMT_E_BADARG
+    assert call(sp, op, 8, 8, 0, 0, -1, 1, 0, None) == _lib.DCMT_E_BADARG
+    assert call(sp, op, 8, 8, 30, 0, 1, 1, 0, None) == _lib.DCMT_E_BADARG  # pitch not a multiple of 4
+    assert call(sp, op, 8, 8, 16, 0, 1, 1, 0, None) == _lib.DCMT_E_BADARG  # pitch < cols*4
+    assert call(sp, op, 8, 8, 0, 0, 1, 7, 0, None) == _lib.DCMT_E_BADARG   # blur type
+    assert call(sp, op, 8, 8, 0, 0, 1, 1, 9, None) == _lib.DCMT_E_BADARG   # flags
+    assert call(sp, sp, 8, 8, 0, 0, 1, 1, 0, None) == _lib.DCMT_E_BADARG   # aliasing
+    assert b"overlap" in lib.dcmt_last_error()
+    assert call(sp, op, 8, 8, 0, 0, 0, 1, 0, None) == _lib.DCMT_OK          # empty batch is a no-op
+    assert lib.dcmt_interpolate_with_superpixels_f32_host(sp, None, 4, op, 8, 8, 0, 0, 1, 1, None) == _lib.DCMT_E_BADARG
+    assert lib.dcmt_stereo_refine_f32_host(sp, None, None, op, None, 8, 8, 1, None) == _lib.DCMT_E_BADARG
+    assert lib.dcmt_status_string(_lib.DCMT_E_CUDA) == b"CUDA error"
+    assert lib.dcmt_workspace_bytes(352, 1216, 1024) > 0
+
+
+def test_python_api_rejects_wrong_types(emu_lib):
+    from depth_completion_mt_b200 import api
+
+    with pytest.raises(TypeError):
+        api.img_completion(np.zeros((4, 4), np.float64), lib=emu_lib)
+    with pytest.raises(ValueError):
+        api.img_completion(np.zeros((4,), np.float32), lib=emu_lib)
+    # any blur string other than gaussian/bilateral means "no blur" (img_completion.cpp:172-189)
+    s = np.zeros((6, 6), np.float32)
+    s[2, 3] = 5.0
+    assert np.array_equal(api.img_completion(s, False, "whatever", lib=emu_lib), api.img_completion(s, False, "none", lib=emu_lib))
