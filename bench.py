@@ -1,0 +1,420 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the img_completion hot path (BASELINE.json metric: frames/s at 1216x352).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload lidar_only|guided|stereo]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+A step is one pass of the hot path over one batch of synthetic frames (default: BASELINE configs[1],
+DC_lidar_only, 1024 frames of 352x1216 at 5 % valid pixels, 64 unique frames x 16).  Per-GPU work is
+fixed as N grows (weak scaling): frames are independent and sharded frame-wise, no collective on the
+hot path; NCCL only gathers timings / checksums (depth_completion_mt_b200/sharding.py).
+
+  value     frames/s, device-resident inputs, CUDA events on the launch stream, max over ranks
+  e2e       the same through the C ABI host entry point: pinned HOST buffers in and out, H2D + D2H inside
+            the timed region
+  roofline  algorithmic bytes (8 B/px lidar-only, 12 guided, 10 stereo) / time vs the measured
+            HBM copy bandwidth (MEASURED_PEAKS.json)
+  cpu_baseline  the reference CPU path (oracle port: cv2 transliteration, one process per host core)
+            timed on a bounded sample of the same workload, rank 0 at N=1 only
+`--impl reference` prints the reference-CPU arm alone in the same JSON shape.
+"""
+from __future__ import annotations
+
+import argparse
+import hashlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+BYTES_PER_PX = {"lidar_only": 8, "guided": 12, "stereo": 10}
+METRIC = "frames/sec @1216x352 sparse depth"
+UNIQUE = 64
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="lidar_only", choices=list(BYTES_PER_PX))
+    ap.add_argument("--frames", type=int, default=1024, help="frames per GPU per step")
+    ap.add_argument("--rows", type=int, default=352)
+    ap.add_argument("--cols", type=int, default=1216)
+    ap.add_argument("--density", type=float, default=0.05)
+    ap.add_argument("--path", default="auto", choices=["auto", "generic", "fused"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-frames-per-core", type=int, default=4, help="reference arm: frames per host core per step")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------- reference (CPU) arm
+_W = {}
+
+
+def _ref_worker_init(workload, rows, cols, density):
+    sys.path.insert(0, ROOT)
+    from depth_completion_mt_b200 import synth
+    try:
+        from oracle import cv2_oracle as cvo
+        have_cv2 = cvo.HAVE_CV2
+    except Exception:
+        have_cv2 = False
+    if have_cv2:
+        import cv2
+
+        cv2.setNumThreads(1)
+        _W["impl"] = cvo
+        _W["kind"] = "cv2"
+    else:
+        from oracle import c_oracle as co
+
+        _W["impl"] = co
+        _W["kind"] = "c"
+    _W.update(workload=workload, rows=rows, cols=cols, density=density, synth=synth, cache={})
+
+
+def _ref_inputs(f):
+    c = _W["cache"]
+    if f not in c:
+        synth, rows, cols = _W["synth"], _W["rows"], _W["cols"]
+        if _W["workload"] == "lidar_only":
+            c[f] = (synth.sparse_depth(f, rows, cols, _W["density"]),)
+        elif _W["workload"] == "guided":
+            lab, k = synth.superpixel_labels(f, rows, cols)
+            c[f] = (synth.sparse_depth(f, rows, cols, _W["density"]), lab, k)
+        else:
+            c[f] = synth.stereo_pair(f, rows, cols)
+    return c[f]
+
+
+def _ref_task(f):
+    impl, args = _W["impl"], _ref_inputs(f % UNIQUE)
+    if _W["workload"] == "lidar_only":
+        out = impl.img_completion(args[0], "gaussian")
+    elif _W["workload"] == "guided":
+        out = impl.interpolate_with_superpixels(args[0], args[1], args[2])
+    else:
+        out = impl.stereo_refine(*args)
+    return float(out[0, 0])
+
+
+def run_reference(args, quiet=False):
+    """Reference CPU arm: oracle port of the reference's own CPU implementation on all host cores."""
+    import multiprocessing as mp
+
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    per_step = max(1, args.ref_frames_per_core) * cores
+    if args.workload == "guided":
+        per_step = cores  # ~2 s per frame per core
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores, initializer=_ref_worker_init, initargs=(args.workload, args.rows, args.cols, args.density)) as pool:
+        kind = pool.apply(_kind)
+        frames = list(range(per_step))
+        chunk = max(1, per_step // (cores * 2))
+        for _ in range(max(1, args.warmup)):
+            pool.map(_ref_task, frames, chunksize=chunk)  # also fills the per-worker input caches
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            pool.map(_ref_task, frames, chunksize=chunk)
+        dt = time.perf_counter() - t0
+    fps = per_step * args.steps / dt
+    sample = (f"{per_step} frames/step x {args.steps} steps of the {args.workload} workload "
+              f"({args.rows}x{args.cols}, {args.density:.0%} valid), {kind} oracle port, one single-threaded process per core")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, per_step),
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    if not quiet:
+        print(json.dumps(line), flush=True)
+    return line
+
+
+def _kind():
+    return "cv2 (OpenCV %s)" % _W["impl"].cv2.__version__ if _W["kind"] == "cv2" else "plain-C"
+
+
+def workload_config(args, frames_per_step_per_gpu):
+    names = {"lidar_only": "DC_lidar_only img_completion, fused dilate/erode/fill/blur (BASELINE configs[1])",
+             "guided": "DC_lidar_camera interpolate_with_superpixels (BASELINE configs[2])",
+             "stereo": "DC_stereo_lidar disparity refinement (BASELINE configs[3])"}
+    return {"workload": names[args.workload], "rows": args.rows, "cols": args.cols, "valid_density": args.density,
+            "frames_per_gpu_per_step": frames_per_step_per_gpu, "global_batch": frames_per_step_per_gpu * max(1, args.gpus),
+            "unique_frames": UNIQUE, "blur": "gaussian", "parallelism": f"frame-sharded dp{max(1, args.gpus)}, no collective on the hot path",
+            "l2_policy": "inputs larger than L2 (batch >> 126 MB), no flush needed"}
+
+
+# --------------------------------------------------------------------------- GPU arm
+class ClockSampler:
+    """nvidia-smi sampling during the timed regions (B200_PROFILING.md clocks line)."""
+
+    FIELDS = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.proc = None
+        self.path = f"/tmp/dcmt_clocks_{os.getpid()}.csv"
+        try:
+            self.fh = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "50",
+                                          "-i", str(index)], stdout=self.fh, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+        self.windows = []
+
+    def mark(self, t0, t1):
+        self.windows.append((t0, t1))
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "note": "nvidia-smi unavailable"}
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.fh.close()
+        import datetime
+
+        rows = []
+        for line in open(self.path):
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                ts = datetime.datetime.strptime(p[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(p[2]), float(p[3]), p[5:9]))
+            except Exception:
+                continue
+        try:
+            os.unlink(self.path)
+        except OSError:
+            pass
+        inwin = [r for r in rows if any(a <= r[0] <= b for a, b in self.windows)]
+        used = inwin or rows
+        if not used:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "note": "no samples"}
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in used for n, v in zip(names, r[3]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(r[1] for r in used), "sm_max_mhz": max(r[2] for r in used), "reasons": reasons,
+                "samples": len(used), "samples_in_timed_regions": len(inwin)}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(workload):
+    """dram bytes per frame from the committed ncu capture, if one exists (profiles/traffic.json)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            return json.load(fh).get(workload)
+    except Exception:
+        return None
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+
+    from depth_completion_mt_b200 import _lib, api, sharding, synth
+
+    rank, local_rank, world = sharding.init_process_group()
+    assert torch.cuda.is_available(), "bench.py --impl ours needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    lib = _lib.load()
+    rows, cols, n = args.rows, args.cols, args.frames
+    reps = (n + UNIQUE - 1) // UNIQUE
+    fpix = rows * cols
+
+    # ---- synthetic inputs, device resident before timing
+    if args.workload == "lidar_only":
+        uniq = np.stack([synth.sparse_depth(f, rows, cols, args.density) for f in range(UNIQUE)])
+        d_in = torch.from_numpy(uniq).to(dev).repeat(reps, 1, 1)[:n].contiguous()
+        d_out = torch.empty_like(d_in)
+
+        def step():
+            api.img_completion(d_in, False, "gaussian", path=args.path, out=d_out, lib=lib)
+        h2d = d2h = n * fpix * 4
+    elif args.workload == "guided":
+        uniq = np.stack([synth.sparse_depth(f, rows, cols, args.density) for f in range(UNIQUE)])
+        labs = [synth.superpixel_labels(f, rows, cols) for f in range(UNIQUE)]
+        k = labs[0][1]
+        d_in = torch.from_numpy(uniq).to(dev).repeat(reps, 1, 1)[:n].contiguous()
+        d_lab = torch.from_numpy(np.stack([l[0] for l in labs])).to(dev).repeat(reps, 1, 1)[:n].contiguous()
+        holder = {}
+
+        def step():
+            holder["out"] = api.interpolate_with_superpixels(d_lab, d_in, "gaussian", 1, n_clusters=k, lib=lib)
+        h2d, d2h = n * fpix * 8, n * fpix * 4
+    else:
+        trip = [synth.stereo_pair(f, rows, cols) for f in range(UNIQUE)]
+        d_ig, d_l, d_r = (torch.from_numpy(np.stack([t[i] for t in trip])).to(dev).repeat(reps, 1, 1)[:n].contiguous() for i in range(3))
+        prm = api.stereo_params(lib=lib)
+        holder = {}
+
+        def step():
+            holder["out"] = api.stereo_refine(d_ig, d_l, d_r, prm, lib=lib)
+        h2d, d2h = n * fpix * 6, n * fpix * 4
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    for _ in range(max(3, args.warmup)):
+        step()
+    torch.cuda.synchronize()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = lib.dcmt_launch_count()
+    torch.cuda.synchronize()
+    w0 = time.time()
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    torch.cuda.synchronize()
+    w1 = time.time()
+    barrier()
+    launches = lib.dcmt_launch_count() - launches0
+    if sampler:
+        sampler.mark(w0, w1)
+    elapsed_ms = ev0.elapsed_time(ev1)
+
+    # ---- validation payload: checksums of the unique outputs (+ digests vs the committed golden file)
+    out_t = d_out if args.workload == "lidar_only" else holder["out"]
+    sums = sharding.frame_checksums(out_t[: min(n, UNIQUE)])
+    replicas_equal = all(bool(torch.equal(out_t[UNIQUE * k_:UNIQUE * (k_ + 1)], out_t[:UNIQUE][: max(0, min(UNIQUE, n - UNIQUE * k_))]))
+                         for k_ in range(1, reps) if n - UNIQUE * k_ > 0)
+    golden_ok = None
+    if args.workload == "lidar_only" and (rows, cols, args.density) == (352, 1216, 0.05):
+        golden_ok = True
+        for l in open(os.path.join(ROOT, "tests", "golden", "lidar_only_352x1216.sha256")):
+            p = l.split()
+            if l.startswith("#") or len(p) != 5 or p[1] != "0" or p[2] != "gaussian":
+                continue
+            golden_ok &= hashlib.sha256(out_t[int(p[0])].cpu().numpy().tobytes()).hexdigest() == p[4]
+
+    # ---- end to end through the host entry point: pinned host buffers, H2D + D2H inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        if args.workload == "lidar_only":
+            h_in = torch.empty((n, rows, cols), dtype=torch.float32, pin_memory=True)
+            h_in.copy_(d_in)
+            h_out = torch.empty_like(h_in, pin_memory=True)
+            np_in, np_out = h_in.numpy(), h_out.numpy()
+
+            def host_step():
+                api.img_completion(np_in, False, "gaussian", path=args.path, out=np_out, lib=lib)
+        elif args.workload == "guided":
+            h_in = torch.empty((n, rows, cols), dtype=torch.float32, pin_memory=True)
+            h_in.copy_(d_in)
+            h_lab = torch.empty((n, rows, cols), dtype=torch.int32, pin_memory=True)
+            h_lab.copy_(d_lab)
+            np_in, np_lab = h_in.numpy(), h_lab.numpy()
+
+            def host_step():
+                holder["h"] = api.interpolate_with_superpixels(np_lab, np_in, "gaussian", 1, n_clusters=k, lib=lib)
+        else:
+            hs = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in (d_ig, d_l, d_r)]
+            for a, b in zip(hs, (d_ig, d_l, d_r)):
+                a.copy_(b)
+            nps = [a.numpy() for a in hs]
+
+            def host_step():
+                holder["h"] = api.stereo_refine(nps[0], nps[1], nps[2], prm, lib=lib)
+        for _ in range(2):
+            host_step()
+        torch.cuda.synchronize()
+        barrier()
+        t0w = time.time()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            host_step()
+        torch.cuda.synchronize()
+        e2e_ms = 1e3 * (time.perf_counter() - t0)
+        t1w = time.time()
+        barrier()
+        if sampler:
+            sampler.mark(t0w, t1w)
+        if args.workload == "lidar_only":
+            assert bool(torch.equal(h_out[:UNIQUE].to(dev), out_t[:UNIQUE])), "host path and device path disagree"
+    else:
+        e2e_ms = 0.0
+
+    res = sharding.gather_validation(elapsed_ms, n * args.steps, sums, device=dev)
+    res_e2e = sharding.gather_validation(e2e_ms, n * args.steps, sums, device=dev)
+    clocks = sampler.stop() if sampler else None
+    if rank != 0:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
+    total_frames = res["total_frames"]
+    secs = res["max_ms"] / 1e3
+    fps = total_frames / secs
+    bytes_per_frame = BYTES_PER_PX[args.workload] * fpix
+    peak, peak_src = measured_peak()
+    achieved = fps * bytes_per_frame / 1e9 / world  # per GPU
+    traffic = ncu_traffic(args.workload)
+    line = {
+        "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": res["max_ms"] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": workload_config(args, n),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                     "peak_source": peak_src,
+                     "note": f"whole hot path, {BYTES_PER_PX[args.workload]} algorithmic B/px x {fpix} px x frames / CUDA-event time, per GPU"},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "validation": {"ranks": world, "checksums_equal_across_ranks": all(bool(torch.equal(c, res["checksums"][0])) for c in res["checksums"]),
+                       "replicas_equal": bool(replicas_equal), "golden_sha256_match": golden_ok, "ms_per_rank": res["ms_per_rank"]},
+    }
+    if not args.no_e2e:
+        line["e2e"] = {"value": res_e2e["total_frames"] / (res_e2e["max_ms"] / 1e3), "unit": "frames/s",
+                       "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                       "api": "dcmt_*_f32_host via depth_completion_mt_b200.api with numpy views of pinned host buffers"}
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "3", "--warmup", "1", "--workload", args.workload,
+                   "--rows", str(rows), "--cols", str(cols), "--density", str(args.density)]
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+            ref = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+            line["cpu_baseline"] = ref["cpu_baseline"]
+        except Exception as exc:  # never lose the GPU numbers because the CPU leg failed
+            line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": None, "kind": "port", "sample": f"failed: {exc!r}"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) != 0:
+            return 0  # rank 0 alone runs the CPU arm
+        run_reference(args)
+        return 0
+    run_ours(args)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -43,6 +43,7 @@ _SIGNATURES = {
     "dcmt_device_count": (C.c_int, []),
     "dcmt_release_workspaces": (C.c_int, []),
     "dcmt_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "dcmt_launch_count": (C.c_longlong, []),
     "dcmt_img_completion_f32": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int, _P, _P]),
     "dcmt_img_completion_f32_host": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int, _P]),
     "dcmt_interpolate_with_superpixels_f32": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_int, C.c_int, _P, _P]),

@@ -13,6 +13,13 @@
 #include "generic.cuh"
 #include "stereo.cuh"
 
+#include <atomic>
+
+namespace dcmt {
+static std::atomic<long long> g_launches{0};
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+}  // namespace dcmt
+
 namespace {
 
 thread_local char g_err[512] = "";
@@ -132,49 +139,47 @@ int check_device() {
     return DCMT_OK;
 }
 
-// shared driver of (a1) and (a2)
-int run_completion(const float* sparse, const int32_t* labels, int n_clusters, bool guided, float* dense, int rows,
-                   int cols, size_t pitch_bytes, size_t frame_stride_bytes, int n_frames, int blur_type, int flags,
-                   int32_t* stats, float* stages, uint32_t* stage_mask, cudaStream_t st) {
-    if (!sparse || !dense) return fail(DCMT_E_BADARG, "null image pointer");
-    if (guided && !labels) return fail(DCMT_E_BADARG, "null label pointer");
-    if (blur_type < DCMT_BLUR_NONE || blur_type > DCMT_BLUR_BILATERAL) return fail(DCMT_E_BADARG, "blur_type %d", blur_type);
-    if (flags < DCMT_PATH_AUTO || flags > DCMT_PATH_FUSED) return fail(DCMT_E_BADARG, "flags %d", flags);
-    Geometry g;
-    int rc = check_geometry(rows, cols, pitch_bytes, frame_stride_bytes, n_frames, &g);
-    if (rc) return rc;
-    if (n_frames == 0) return DCMT_OK;
-    if (overlaps(sparse, g.span_bytes, dense, g.span_bytes)) return fail(DCMT_E_BADARG, "input and output overlap");
-    if ((rc = check_device())) return rc;
-    API_CUDA(dcmt::generic_configure(), "kernel attribute setup");
+// validated description of one completion call
+struct CompletionCall {
+    const int32_t* labels;
+    int n_clusters;
+    bool guided;
+    int rows, cols, blur, flags;
+};
 
+size_t completion_ws_bytes(int rows, int cols, int n_frames, bool bilateral) {
+    return generic_ws_bytes(rows, cols, generic_chunk_frames(rows, cols, n_frames), bilateral);
+}
+
+// Enqueue n_frames through the pipeline; every pointer is a device pointer, the workspace is carved from `ar`.
+int enqueue_completion(const CompletionCall& cc, const float* sparse, const int32_t* labels, float* dense, size_t pitch,
+                       size_t fstride, int n_frames, int32_t* stats, float* stages, uint32_t* stage_mask, Arena* ar,
+                       cudaStream_t st) {
+    const int rows = cc.rows, cols = cc.cols;
     const int chunk = generic_chunk_frames(rows, cols, n_frames);
-    const bool bilateral = blur_type == DCMT_BLUR_BILATERAL;
-    Arena* ar = nullptr;
-    if ((rc = arena_acquire(st, generic_ws_bytes(rows, cols, chunk, bilateral), &ar))) return rc;
+    const bool bilateral = cc.blur == DCMT_BLUR_BILATERAL;
     const size_t fpix = (size_t)rows * cols;
     float* w1 = carve<float>(ar, fpix * chunk);
     float* w2 = carve<float>(ar, fpix * chunk);
     dcmt::FrameCounters* ctr = carve<dcmt::FrameCounters>(ar, chunk);
     unsigned* mm = bilateral ? carve<unsigned>(ar, 2 * (size_t)chunk) : nullptr;
     float* lut = bilateral ? carve<float>(ar, dcmt::generic_lut_floats() * chunk) : nullptr;
-
     for (int f0 = 0; f0 < n_frames; f0 += chunk) {
         const int nf = n_frames - f0 < chunk ? n_frames - f0 : chunk;
         dcmt::GenericChunk c{};
-        c.in = sparse + (size_t)f0 * g.fstride;
-        c.in_pitch = g.pitch;
-        c.in_fstride = g.fstride;
-        c.labels = guided ? labels + (size_t)f0 * fpix : nullptr;
-        c.n_clusters = n_clusters;
-        c.guided = guided;
-        c.out = dense + (size_t)f0 * g.fstride;
-        c.out_pitch = g.pitch;
-        c.out_fstride = g.fstride;
+        c.in = sparse + (size_t)f0 * fstride;
+        c.in_pitch = pitch;
+        c.in_fstride = fstride;
+        c.labels = cc.guided ? labels + (size_t)f0 * fpix : nullptr;
+        c.n_clusters = cc.n_clusters;
+        c.guided = cc.guided;
+        c.out = dense + (size_t)f0 * fstride;
+        c.out_pitch = pitch;
+        c.out_fstride = fstride;
         c.rows = rows;
         c.cols = cols;
         c.n_frames = nf;
-        c.blur = blur_type;
+        c.blur = cc.blur;
         c.w1 = w1;
         c.w2 = w2;
         c.ctr = ctr;
@@ -189,38 +194,125 @@ int run_completion(const float* sparse, const int32_t* labels, int n_clusters, b
     return DCMT_OK;
 }
 
-// host-pointer wrapper: stage through the arena of the default stream
-template <class Fn>
-int with_device_copies(const float* h_in, float* h_out, size_t span_bytes, const int32_t* h_labels, size_t label_bytes,
-                       int32_t* h_stats, int n_frames, Fn&& fn) {
-    int rc = check_device();
+int validate_completion(const float* sparse, const int32_t* labels, bool guided, float* dense, int rows, int cols,
+                        size_t pitch_bytes, size_t frame_stride_bytes, int n_frames, int blur_type, int flags, Geometry* g) {
+    if (!sparse || !dense) return fail(DCMT_E_BADARG, "null image pointer");
+    if (guided && !labels) return fail(DCMT_E_BADARG, "null label pointer");
+    if (blur_type < DCMT_BLUR_NONE || blur_type > DCMT_BLUR_BILATERAL) return fail(DCMT_E_BADARG, "blur_type %d", blur_type);
+    if (flags < DCMT_PATH_AUTO || flags > DCMT_PATH_FUSED) return fail(DCMT_E_BADARG, "flags %d", flags);
+    int rc = check_geometry(rows, cols, pitch_bytes, frame_stride_bytes, n_frames, g);
     if (rc) return rc;
-    float *d_in = nullptr, *d_out = nullptr;
-    int32_t *d_lab = nullptr, *d_stats = nullptr;
-    auto cleanup = [&] { cudaFree(d_in); cudaFree(d_out); cudaFree(d_lab); cudaFree(d_stats); };
-    cudaError_t e;
-    if ((e = cudaMalloc(&d_in, span_bytes)) != cudaSuccess || (e = cudaMalloc(&d_out, span_bytes)) != cudaSuccess ||
-        (label_bytes && (e = cudaMalloc(&d_lab, label_bytes)) != cudaSuccess) ||
-        (h_stats && (e = cudaMalloc(&d_stats, (size_t)n_frames * DCMT_STATS_STRIDE * sizeof(int32_t))) != cudaSuccess)) {
-        cleanup();
-        return fail(DCMT_E_NOMEM, "device staging buffers: %s", cudaGetErrorString(e));
+    if (n_frames && overlaps(sparse, g->span_bytes, dense, g->span_bytes)) return fail(DCMT_E_BADARG, "input and output overlap");
+    return DCMT_OK;
+}
+
+// device-pointer driver of (a1) and (a2)
+int run_completion(const float* sparse, const int32_t* labels, int n_clusters, bool guided, float* dense, int rows,
+                   int cols, size_t pitch_bytes, size_t frame_stride_bytes, int n_frames, int blur_type, int flags,
+                   int32_t* stats, float* stages, uint32_t* stage_mask, cudaStream_t st) {
+    Geometry g;
+    int rc = validate_completion(sparse, labels, guided, dense, rows, cols, pitch_bytes, frame_stride_bytes, n_frames,
+                                 blur_type, flags, &g);
+    if (rc) return rc;
+    if (n_frames == 0) return DCMT_OK;
+    if ((rc = check_device())) return rc;
+    API_CUDA(dcmt::generic_configure(), "kernel attribute setup");
+    Arena* ar = nullptr;
+    if ((rc = arena_acquire(st, completion_ws_bytes(rows, cols, n_frames, blur_type == DCMT_BLUR_BILATERAL), &ar))) return rc;
+    const CompletionCall cc{labels, n_clusters, guided, rows, cols, blur_type, flags};
+    return enqueue_completion(cc, sparse, labels, dense, g.pitch, g.fstride, n_frames, stats, stages, stage_mask, ar, st);
+}
+
+// ---- host-pointer driver: chunks of frames flow H2D -> kernels -> D2H round-robin over three internal
+// streams, so the copies of one chunk overlap the kernels of another.  Copies are asynchronous when the
+// caller's buffers are page-locked (e.g. torch pinned memory); pageable buffers work, just slower.
+constexpr int kHostStreams = 3;
+struct HostStreams {
+    cudaStream_t s[kHostStreams];
+};
+std::map<int, HostStreams> g_host_streams;
+
+int host_streams(HostStreams** out) {
+    int dev = 0;
+    API_CUDA(cudaGetDevice(&dev), "cudaGetDevice");
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_host_streams.find(dev);
+    if (it == g_host_streams.end()) {
+        HostStreams hs{};
+        for (int i = 0; i < kHostStreams; ++i) API_CUDA(cudaStreamCreateWithFlags(&hs.s[i], cudaStreamNonBlocking), "cudaStreamCreate");
+        it = g_host_streams.emplace(dev, hs).first;
     }
-    if ((e = cudaMemcpy(d_in, h_in, span_bytes, cudaMemcpyHostToDevice)) != cudaSuccess ||
-        (label_bytes && (e = cudaMemcpy(d_lab, h_labels, label_bytes, cudaMemcpyHostToDevice)) != cudaSuccess)) {
-        cleanup();
-        return cuda_fail(e, "host to device copy");
+    *out = &it->second;
+    return DCMT_OK;
+}
+
+int host_chunk_frames(int rows, int cols, int n_frames) {
+    long c = (long)((16u << 20) / ((size_t)rows * cols) + 1);  // ~64 MB of float pixels per chunk
+    if (c > n_frames) c = n_frames;
+    if (c > 65535) c = 65535;
+    return (int)(c < 1 ? 1 : c);
+}
+
+int run_completion_host(const float* sparse, const int32_t* labels, int n_clusters, bool guided, float* dense, int rows,
+                        int cols, size_t pitch_bytes, size_t frame_stride_bytes, int n_frames, int blur_type, int flags,
+                        int32_t* stats) {
+    Geometry g;
+    int rc = validate_completion(sparse, labels, guided, dense, rows, cols, pitch_bytes, frame_stride_bytes, n_frames,
+                                 blur_type, flags, &g);
+    if (rc) return rc;
+    if (n_frames == 0) return DCMT_OK;
+    if ((rc = check_device())) return rc;
+    API_CUDA(dcmt::generic_configure(), "kernel attribute setup");
+    HostStreams* hs = nullptr;
+    if ((rc = host_streams(&hs))) return rc;
+    const size_t fpix = (size_t)rows * cols;
+    const int hc = host_chunk_frames(rows, cols, n_frames);
+    const bool bilateral = blur_type == DCMT_BLUR_BILATERAL;
+    const size_t row_bytes = (size_t)cols * sizeof(float);
+    const bool dense_rows = g.pitch == (size_t)cols;
+    const CompletionCall cc{labels, n_clusters, guided, rows, cols, blur_type, flags};
+    const size_t bytes = 2 * carve_bytes(fpix * hc, sizeof(float)) + (guided ? carve_bytes(fpix * hc, sizeof(int32_t)) : 0) +
+                         carve_bytes((size_t)hc * DCMT_STATS_STRIDE, sizeof(int32_t)) + completion_ws_bytes(rows, cols, hc, bilateral);
+    int slot = 0;
+    for (int f0 = 0; f0 < n_frames; f0 += hc, slot = (slot + 1) % kHostStreams) {
+        const int nf = n_frames - f0 < hc ? n_frames - f0 : hc;
+        cudaStream_t st = hs->s[slot];
+        Arena* ar = nullptr;
+        if ((rc = arena_acquire(st, bytes, &ar))) return rc;  // stream order protects reuse by the chunk 3 steps later
+        float* d_in = carve<float>(ar, fpix * hc);
+        float* d_out = carve<float>(ar, fpix * hc);
+        int32_t* d_lab = guided ? carve<int32_t>(ar, fpix * hc) : nullptr;
+        int32_t* d_stats = carve<int32_t>(ar, (size_t)hc * DCMT_STATS_STRIDE);
+        const float* h_in = sparse + (size_t)f0 * g.fstride;
+        float* h_out = dense + (size_t)f0 * g.fstride;
+        if (dense_rows && g.fstride == fpix) {
+            API_CUDA(cudaMemcpyAsync(d_in, h_in, fpix * nf * sizeof(float), cudaMemcpyHostToDevice, st), "host to device copy");
+        } else {
+            for (int f = 0; f < nf; ++f)
+                API_CUDA(cudaMemcpy2DAsync(d_in + (size_t)f * fpix, row_bytes, h_in + (size_t)f * g.fstride,
+                                           g.pitch * sizeof(float), row_bytes, rows, cudaMemcpyHostToDevice, st),
+                         "host to device copy");
+        }
+        if (guided)
+            API_CUDA(cudaMemcpyAsync(d_lab, labels + (size_t)f0 * fpix, fpix * nf * sizeof(int32_t), cudaMemcpyHostToDevice, st),
+                     "host to device copy");
+        if ((rc = enqueue_completion(cc, d_in, d_lab, d_out, cols, fpix, nf, stats ? d_stats : nullptr, nullptr, nullptr, ar, st)))
+            return rc;
+        if (dense_rows && g.fstride == fpix) {
+            API_CUDA(cudaMemcpyAsync(h_out, d_out, fpix * nf * sizeof(float), cudaMemcpyDeviceToHost, st), "device to host copy");
+        } else {
+            for (int f = 0; f < nf; ++f)
+                API_CUDA(cudaMemcpy2DAsync(h_out + (size_t)f * g.fstride, g.pitch * sizeof(float), d_out + (size_t)f * fpix,
+                                           row_bytes, row_bytes, rows, cudaMemcpyDeviceToHost, st),
+                         "device to host copy");
+        }
+        if (stats)
+            API_CUDA(cudaMemcpyAsync(stats + (size_t)f0 * DCMT_STATS_STRIDE, d_stats, (size_t)nf * DCMT_STATS_STRIDE * sizeof(int32_t),
+                                     cudaMemcpyDeviceToHost, st),
+                     "device to host copy");
     }
-    // rows of `dense` beyond cols (pitch padding) are preserved: start from the caller's bytes
-    if ((e = cudaMemcpy(d_out, h_out, span_bytes, cudaMemcpyHostToDevice)) != cudaSuccess) { cleanup(); return cuda_fail(e, "host to device copy"); }
-    rc = fn(d_in, d_out, d_lab, d_stats);
-    if (rc == DCMT_OK) {
-        if ((e = cudaStreamSynchronize(nullptr)) != cudaSuccess) rc = cuda_fail(e, "kernel execution");
-        else if ((e = cudaMemcpy(h_out, d_out, span_bytes, cudaMemcpyDeviceToHost)) != cudaSuccess) rc = cuda_fail(e, "device to host copy");
-        else if (h_stats && (e = cudaMemcpy(h_stats, d_stats, (size_t)n_frames * DCMT_STATS_STRIDE * sizeof(int32_t), cudaMemcpyDeviceToHost)) != cudaSuccess)
-            rc = cuda_fail(e, "device to host copy");
-    }
-    cleanup();
-    return rc;
+    for (int i = 0; i < kHostStreams; ++i) API_CUDA(cudaStreamSynchronize(hs->s[i]), "kernel execution");
+    return DCMT_OK;
 }
 
 }  // namespace
@@ -250,6 +342,7 @@ int dcmt_device_count(void) {
 
 int dcmt_release_workspaces(void) {
     std::lock_guard<std::mutex> lk(g_mu);
+    cudaDeviceSynchronize();
     for (auto& kv : g_arenas)
         if (kv.second.base) cudaFree(kv.second.base);
     g_arenas.clear();
@@ -258,8 +351,10 @@ int dcmt_release_workspaces(void) {
 
 size_t dcmt_workspace_bytes(int rows, int cols, int n_frames) {
     if (rows < 1 || cols < 1 || n_frames < 1) return 0;
-    return generic_ws_bytes(rows, cols, generic_chunk_frames(rows, cols, n_frames), true);
+    return completion_ws_bytes(rows, cols, n_frames, true);
 }
+
+long long dcmt_launch_count(void) { return dcmt::g_launches.load(std::memory_order_relaxed); }
 
 int dcmt_img_completion_f32(const float* sparse, float* dense, int rows, int cols, size_t pitch_bytes,
                             size_t frame_stride_bytes, int n_frames, int blur_type, int flags, int32_t* stats,
@@ -270,17 +365,8 @@ int dcmt_img_completion_f32(const float* sparse, float* dense, int rows, int col
 
 int dcmt_img_completion_f32_host(const float* sparse, float* dense, int rows, int cols, size_t pitch_bytes,
                                  size_t frame_stride_bytes, int n_frames, int blur_type, int flags, int32_t* stats) {
-    if (!sparse || !dense) return fail(DCMT_E_BADARG, "null image pointer");
-    Geometry g;
-    int rc = check_geometry(rows, cols, pitch_bytes, frame_stride_bytes, n_frames, &g);
-    if (rc) return rc;
-    if (n_frames == 0) return DCMT_OK;
-    if (overlaps(sparse, g.span_bytes, dense, g.span_bytes)) return fail(DCMT_E_BADARG, "input and output overlap");
-    return with_device_copies(sparse, dense, g.span_bytes, nullptr, 0, stats, n_frames,
-                              [&](float* d_in, float* d_out, int32_t*, int32_t* d_stats) {
-                                  return dcmt_img_completion_f32(d_in, d_out, rows, cols, pitch_bytes, frame_stride_bytes,
-                                                                 n_frames, blur_type, flags, d_stats, nullptr);
-                              });
+    return run_completion_host(sparse, nullptr, 0, false, dense, rows, cols, pitch_bytes, frame_stride_bytes, n_frames,
+                               blur_type, flags, stats);
 }
 
 int dcmt_interpolate_with_superpixels_f32(const float* sparse, const int32_t* labels, int n_clusters, float* dense,
@@ -295,20 +381,8 @@ int dcmt_interpolate_with_superpixels_f32(const float* sparse, const int32_t* la
 int dcmt_interpolate_with_superpixels_f32_host(const float* sparse, const int32_t* labels, int n_clusters, float* dense,
                                                int rows, int cols, size_t pitch_bytes, size_t frame_stride_bytes,
                                                int n_frames, int use_superpixel, int32_t* stats) {
-    if (!sparse || !dense) return fail(DCMT_E_BADARG, "null image pointer");
-    if (use_superpixel && !labels) return fail(DCMT_E_BADARG, "null label pointer");
-    Geometry g;
-    int rc = check_geometry(rows, cols, pitch_bytes, frame_stride_bytes, n_frames, &g);
-    if (rc) return rc;
-    if (n_frames == 0) return DCMT_OK;
-    if (overlaps(sparse, g.span_bytes, dense, g.span_bytes)) return fail(DCMT_E_BADARG, "input and output overlap");
-    const size_t label_bytes = use_superpixel ? (size_t)rows * cols * n_frames * sizeof(int32_t) : 0;
-    return with_device_copies(sparse, dense, g.span_bytes, labels, label_bytes, stats, n_frames,
-                              [&](float* d_in, float* d_out, int32_t* d_lab, int32_t* d_stats) {
-                                  return dcmt_interpolate_with_superpixels_f32(d_in, d_lab, n_clusters, d_out, rows, cols,
-                                                                               pitch_bytes, frame_stride_bytes, n_frames,
-                                                                               use_superpixel, d_stats, nullptr);
-                              });
+    return run_completion_host(sparse, labels, n_clusters, use_superpixel != 0, dense, rows, cols, pitch_bytes,
+                               frame_stride_bytes, n_frames, DCMT_BLUR_GAUSSIAN, DCMT_PATH_GENERIC, stats);
 }
 
 int dcmt_img_completion_stages_f32(const float* sparse, float* dense, int rows, int cols, int blur_type, float* stages,

@@ -11,7 +11,9 @@
 #define DCMT_DYN_SMEM(type, name)                                         \
     extern __shared__ __align__(16) unsigned char dcmt_dyn_smem_raw[];    \
     type* name = reinterpret_cast<type*>(dcmt_dyn_smem_raw)
-#define DCMT_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+namespace dcmt { void note_launch(); }  // launch counter behind dcmt_launch_count() (api.cu)
+#define DCMT_LAUNCH(kernel, grid, block, smem, stream, ...) \
+    (dcmt::note_launch(), kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__))
 #endif
 
 namespace dcmt {

@@ -77,6 +77,9 @@ DCMT_API const char *dcmt_status_string(int status);
 DCMT_API int dcmt_device_count(void);
 /* frees every cached workspace of the calling process (all devices) */
 DCMT_API int dcmt_release_workspaces(void);
+/* number of CUDA kernels this library has launched in the calling process (monotonic; bench.py reports the
+ * difference across its timed region as `gpu_launches`) */
+DCMT_API long long dcmt_launch_count(void);
 /* bytes of device workspace the library caches for a call of this shape */
 DCMT_API size_t dcmt_workspace_bytes(int rows, int cols, int n_frames);
 

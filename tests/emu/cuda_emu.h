@@ -62,8 +62,9 @@ long launches();
 }  // namespace dcmt_emu
 
 #define DCMT_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(dcmt_emu::dyn_smem())
+namespace dcmt { void note_launch(); }
 #define DCMT_LAUNCH(kernel, grid, block, smem, stream, ...) \
-    dcmt_emu::launch((grid), (block), (smem), [=]() { kernel(__VA_ARGS__); })
+    (dcmt::note_launch(), dcmt_emu::launch((grid), (block), (smem), [=]() { kernel(__VA_ARGS__); }))
 
 // ---- runtime shims (device memory == host memory) ----
 static inline const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "emulated CUDA error"; }
@@ -82,6 +83,9 @@ static inline cudaError_t cudaMemcpy2DAsync(void* d, size_t dp, const void* s, s
 }
 static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = nullptr) { std::memset(d, v, n); return cudaSuccess; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+enum { cudaStreamNonBlocking = 1 };
+static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { static char tok[8]; static int n = 0; *s = &tok[(n++) & 7]; return cudaSuccess; }
+static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
 static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
 template <class F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
 
