@@ -8,8 +8,11 @@
 #include <map>
 #include <mutex>
 #include <utility>
+#include <vector>
+#include <algorithm>
 
 #include "common.cuh"
+#include "fused_q8.cuh"
 #include "generic.cuh"
 #include "stereo.cuh"
 
@@ -147,23 +150,67 @@ struct CompletionCall {
     int rows, cols, blur, flags;
 };
 
-size_t completion_ws_bytes(int rows, int cols, int n_frames, bool bilateral) {
-    return generic_ws_bytes(rows, cols, generic_chunk_frames(rows, cols, n_frames), bilateral);
+// the strict-q8 fused path serves plain img_completion with blur none/gaussian on frames of a sane size
+bool fused_applies(const CompletionCall& cc) {
+    if (cc.flags == DCMT_PATH_GENERIC || cc.guided || cc.blur == DCMT_BLUR_BILATERAL) return false;
+    if (cc.rows < dcmt::kQ8MinRows || cc.cols < dcmt::kQ8MinCols || cc.rows > dcmt::kQ8MaxRows) return false;
+    int th, tw;
+    dcmt::q8_choose_tile(cc.rows, cc.cols, &th, &tw);
+    return dcmt::q8_tail_smem(th, tw) <= 200 * 1024 && dcmt::q8_front_smem(th, tw) <= 200 * 1024;
+}
+
+size_t completion_ws_bytes(int rows, int cols, int n_frames, bool bilateral, bool fused) {
+    const int chunk = generic_chunk_frames(rows, cols, n_frames);
+    size_t b = generic_ws_bytes(rows, cols, chunk, bilateral);
+    if (fused) {
+        const size_t mid_pitch = ((size_t)cols + 7) / 8 * 8;
+        b += carve_bytes((size_t)rows * mid_pitch * chunk, sizeof(uint16_t)) + 2 * carve_bytes(mid_pitch * chunk, sizeof(uint32_t));
+    }
+    return b;
 }
 
 // Enqueue n_frames through the pipeline; every pointer is a device pointer, the workspace is carved from `ar`.
+// Never synchronises.  On the fused path `redo_flags` (device, one int32 per frame, optional) receives 1 for
+// frames that turned out not to be strict q8: their output is NOT valid and the caller must redo them with
+// DCMT_PATH_GENERIC.  *used_fused tells the caller which path ran.
 int enqueue_completion(const CompletionCall& cc, const float* sparse, const int32_t* labels, float* dense, size_t pitch,
-                       size_t fstride, int n_frames, int32_t* stats, float* stages, uint32_t* stage_mask, Arena* ar,
-                       cudaStream_t st) {
+                       size_t fstride, int n_frames, int32_t* stats, int32_t* redo_flags, float* stages,
+                       uint32_t* stage_mask, Arena* ar, cudaStream_t st, bool* used_fused) {
     const int rows = cc.rows, cols = cc.cols;
     const int chunk = generic_chunk_frames(rows, cols, n_frames);
     const bool bilateral = cc.blur == DCMT_BLUR_BILATERAL;
+    const bool fused = fused_applies(cc) && !stages;
+    if (used_fused) *used_fused = fused;
     const size_t fpix = (size_t)rows * cols;
     float* w1 = carve<float>(ar, fpix * chunk);
     float* w2 = carve<float>(ar, fpix * chunk);
     dcmt::FrameCounters* ctr = carve<dcmt::FrameCounters>(ar, chunk);
     unsigned* mm = bilateral ? carve<unsigned>(ar, 2 * (size_t)chunk) : nullptr;
     float* lut = bilateral ? carve<float>(ar, dcmt::generic_lut_floats() * chunk) : nullptr;
+    if (fused) {
+        dcmt::Q8Plan p{};
+        p.rows = rows;
+        p.cols = cols;
+        dcmt::q8_choose_tile(rows, cols, &p.th, &p.tw);
+        p.mid_pitch = (cols + 7) / 8 * 8;
+        p.max_frames = chunk;
+        p.mid = carve<uint16_t>(ar, (size_t)rows * p.mid_pitch * chunk);
+        p.col_first = carve<uint32_t>(ar, (size_t)p.mid_pitch * chunk);
+        p.col_last = carve<uint32_t>(ar, (size_t)p.mid_pitch * chunk);
+        p.ctr = ctr;
+        p.w1 = w1;
+        p.w2 = w2;
+        for (int f0 = 0; f0 < n_frames; f0 += chunk) {
+            const int nf = n_frames - f0 < chunk ? n_frames - f0 : chunk;
+            API_CUDA(dcmt::q8_run_front(p, sparse + (size_t)f0 * fstride, pitch, fstride, nf, st), "fused front launch");
+            API_CUDA(dcmt::q8_run_tail(p, dense + (size_t)f0 * fstride, pitch, fstride, nf, cc.blur, st), "fused tail launch");
+            if (stats || redo_flags)
+                API_CUDA(dcmt::q8_write_stats(p, stats ? stats + (size_t)f0 * DCMT_STATS_STRIDE : nullptr,
+                                              redo_flags ? redo_flags + f0 : nullptr, nf, st),
+                         "stats launch");
+        }
+        return DCMT_OK;
+    }
     for (int f0 = 0; f0 < n_frames; f0 += chunk) {
         const int nf = n_frames - f0 < chunk ? n_frames - f0 : chunk;
         dcmt::GenericChunk c{};
@@ -194,6 +241,32 @@ int enqueue_completion(const CompletionCall& cc, const float* sparse, const int3
     return DCMT_OK;
 }
 
+// pinned host scratch for the redo flags (one per device, grow-only)
+struct PinnedFlags {
+    int32_t* p = nullptr;
+    size_t cap = 0;
+};
+std::map<int, PinnedFlags> g_pinned;
+
+int pinned_flags(size_t n, int32_t** out) {
+    int dev = 0;
+    API_CUDA(cudaGetDevice(&dev), "cudaGetDevice");
+    std::lock_guard<std::mutex> lk(g_mu);
+    PinnedFlags& pf = g_pinned[dev];
+    if (pf.cap < n) {
+        if (pf.p) cudaFreeHost(pf.p);
+        pf.p = nullptr;
+        pf.cap = 0;
+        void* q = nullptr;
+        cudaError_t e = cudaMallocHost(&q, n * sizeof(int32_t));
+        if (e != cudaSuccess) return fail(DCMT_E_NOMEM, "pinned flag buffer: %s", cudaGetErrorString(e));
+        pf.p = static_cast<int32_t*>(q);
+        pf.cap = n;
+    }
+    *out = pf.p;
+    return DCMT_OK;
+}
+
 int validate_completion(const float* sparse, const int32_t* labels, bool guided, float* dense, int rows, int cols,
                         size_t pitch_bytes, size_t frame_stride_bytes, int n_frames, int blur_type, int flags, Geometry* g) {
     if (!sparse || !dense) return fail(DCMT_E_BADARG, "null image pointer");
@@ -217,10 +290,37 @@ int run_completion(const float* sparse, const int32_t* labels, int n_clusters, b
     if (n_frames == 0) return DCMT_OK;
     if ((rc = check_device())) return rc;
     API_CUDA(dcmt::generic_configure(), "kernel attribute setup");
+    API_CUDA(dcmt::q8_configure(), "kernel attribute setup");
+    CompletionCall cc{labels, n_clusters, guided, rows, cols, blur_type, flags};
+    const bool fused = fused_applies(cc) && !stages;
+    const bool bilateral = blur_type == DCMT_BLUR_BILATERAL;
     Arena* ar = nullptr;
-    if ((rc = arena_acquire(st, completion_ws_bytes(rows, cols, n_frames, blur_type == DCMT_BLUR_BILATERAL), &ar))) return rc;
-    const CompletionCall cc{labels, n_clusters, guided, rows, cols, blur_type, flags};
-    return enqueue_completion(cc, sparse, labels, dense, g.pitch, g.fstride, n_frames, stats, stages, stage_mask, ar, st);
+    const size_t flag_bytes = fused ? carve_bytes((size_t)n_frames, sizeof(int32_t)) : 0;
+    if ((rc = arena_acquire(st, completion_ws_bytes(rows, cols, n_frames, bilateral, fused) + flag_bytes, &ar))) return rc;
+    int32_t* d_flags = fused ? carve<int32_t>(ar, (size_t)n_frames) : nullptr;
+    bool used = false;
+    if ((rc = enqueue_completion(cc, sparse, labels, dense, g.pitch, g.fstride, n_frames, stats, d_flags, stages, stage_mask, ar,
+                                 st, &used)))
+        return rc;
+    if (!used || flags != DCMT_PATH_AUTO) return DCMT_OK;  // DCMT_PATH_FUSED: fully asynchronous, stats[3] = -1 marks bad frames
+    // DCMT_PATH_AUTO: one readback of the per-frame "not strict q8" flags, then the generic pipeline for those frames
+    int32_t* h_flags = nullptr;
+    if ((rc = pinned_flags((size_t)n_frames, &h_flags))) return rc;
+    API_CUDA(cudaMemcpyAsync(h_flags, d_flags, (size_t)n_frames * sizeof(int32_t), cudaMemcpyDeviceToHost, st), "flag readback");
+    API_CUDA(cudaStreamSynchronize(st), "kernel execution");
+    cc.flags = DCMT_PATH_GENERIC;
+    for (int f = 0; f < n_frames;) {
+        if (!h_flags[f]) { ++f; continue; }
+        int e = f;
+        while (e < n_frames && h_flags[e]) ++e;
+        ar->used = 0;  // the fused work has completed: the arena is free again
+        if ((rc = enqueue_completion(cc, sparse + (size_t)f * g.fstride, nullptr, dense + (size_t)f * g.fstride, g.pitch, g.fstride,
+                                     e - f, stats ? stats + (size_t)f * DCMT_STATS_STRIDE : nullptr, nullptr, nullptr, nullptr, ar,
+                                     st, nullptr)))
+            return rc;
+        f = e;
+    }
+    return DCMT_OK;
 }
 
 // ---- host-pointer driver: chunks of frames flow H2D -> kernels -> D2H round-robin over three internal
@@ -263,6 +363,7 @@ int run_completion_host(const float* sparse, const int32_t* labels, int n_cluste
     if (n_frames == 0) return DCMT_OK;
     if ((rc = check_device())) return rc;
     API_CUDA(dcmt::generic_configure(), "kernel attribute setup");
+    API_CUDA(dcmt::q8_configure(), "kernel attribute setup");
     HostStreams* hs = nullptr;
     if ((rc = host_streams(&hs))) return rc;
     const size_t fpix = (size_t)rows * cols;
@@ -271,8 +372,12 @@ int run_completion_host(const float* sparse, const int32_t* labels, int n_cluste
     const size_t row_bytes = (size_t)cols * sizeof(float);
     const bool dense_rows = g.pitch == (size_t)cols;
     const CompletionCall cc{labels, n_clusters, guided, rows, cols, blur_type, flags};
+    const bool fused = fused_applies(cc);
     const size_t bytes = 2 * carve_bytes(fpix * hc, sizeof(float)) + (guided ? carve_bytes(fpix * hc, sizeof(int32_t)) : 0) +
-                         carve_bytes((size_t)hc * DCMT_STATS_STRIDE, sizeof(int32_t)) + completion_ws_bytes(rows, cols, hc, bilateral);
+                         carve_bytes((size_t)hc * DCMT_STATS_STRIDE, sizeof(int32_t)) + carve_bytes((size_t)hc, sizeof(int32_t)) +
+                         completion_ws_bytes(rows, cols, hc, bilateral, fused);
+    int32_t* h_flags = nullptr;
+    if (fused && (rc = pinned_flags((size_t)n_frames, &h_flags))) return rc;
     int slot = 0;
     for (int f0 = 0; f0 < n_frames; f0 += hc, slot = (slot + 1) % kHostStreams) {
         const int nf = n_frames - f0 < hc ? n_frames - f0 : hc;
@@ -283,6 +388,7 @@ int run_completion_host(const float* sparse, const int32_t* labels, int n_cluste
         float* d_out = carve<float>(ar, fpix * hc);
         int32_t* d_lab = guided ? carve<int32_t>(ar, fpix * hc) : nullptr;
         int32_t* d_stats = carve<int32_t>(ar, (size_t)hc * DCMT_STATS_STRIDE);
+        int32_t* d_flags = carve<int32_t>(ar, (size_t)hc);
         const float* h_in = sparse + (size_t)f0 * g.fstride;
         float* h_out = dense + (size_t)f0 * g.fstride;
         if (dense_rows && g.fstride == fpix) {
@@ -296,8 +402,11 @@ int run_completion_host(const float* sparse, const int32_t* labels, int n_cluste
         if (guided)
             API_CUDA(cudaMemcpyAsync(d_lab, labels + (size_t)f0 * fpix, fpix * nf * sizeof(int32_t), cudaMemcpyHostToDevice, st),
                      "host to device copy");
-        if ((rc = enqueue_completion(cc, d_in, d_lab, d_out, cols, fpix, nf, stats ? d_stats : nullptr, nullptr, nullptr, ar, st)))
+        if ((rc = enqueue_completion(cc, d_in, d_lab, d_out, cols, fpix, nf, stats ? d_stats : nullptr, fused ? d_flags : nullptr,
+                                     nullptr, nullptr, ar, st, nullptr)))
             return rc;
+        if (fused)
+            API_CUDA(cudaMemcpyAsync(h_flags + f0, d_flags, (size_t)nf * sizeof(int32_t), cudaMemcpyDeviceToHost, st), "flag readback");
         if (dense_rows && g.fstride == fpix) {
             API_CUDA(cudaMemcpyAsync(h_out, d_out, fpix * nf * sizeof(float), cudaMemcpyDeviceToHost, st), "device to host copy");
         } else {
@@ -312,6 +421,21 @@ int run_completion_host(const float* sparse, const int32_t* labels, int n_cluste
                      "device to host copy");
     }
     for (int i = 0; i < kHostStreams; ++i) API_CUDA(cudaStreamSynchronize(hs->s[i]), "kernel execution");
+    if (fused && flags == DCMT_PATH_AUTO) {
+        // frames that turned out not to be strict q8 go through the generic pipeline (runs of consecutive frames)
+        for (int f = 0; f < n_frames;) {
+            if (!h_flags[f]) { ++f; continue; }
+            int e = f;
+            while (e < n_frames && h_flags[e]) ++e;
+            std::vector<int32_t> keep(h_flags + e, h_flags + n_frames);  // the nested call reuses the pinned buffer
+            rc = run_completion_host(sparse + (size_t)f * g.fstride, nullptr, 0, false, dense + (size_t)f * g.fstride, rows, cols,
+                                     pitch_bytes, frame_stride_bytes, e - f, blur_type, DCMT_PATH_GENERIC,
+                                     stats ? stats + (size_t)f * DCMT_STATS_STRIDE : nullptr);
+            if (rc) return rc;
+            std::copy(keep.begin(), keep.end(), h_flags + e);
+            f = e;
+        }
+    }
     return DCMT_OK;
 }
 
@@ -351,7 +475,7 @@ int dcmt_release_workspaces(void) {
 
 size_t dcmt_workspace_bytes(int rows, int cols, int n_frames) {
     if (rows < 1 || cols < 1 || n_frames < 1) return 0;
-    return completion_ws_bytes(rows, cols, n_frames, true);
+    return completion_ws_bytes(rows, cols, n_frames, true, true);
 }
 
 long long dcmt_launch_count(void) { return dcmt::g_launches.load(std::memory_order_relaxed); }

@@ -1,0 +1,800 @@
+// fused_q8.cu -- the fast path of img_completion (/root/reference/src/DC_lidar_only/img_completion.cpp:17-204)
+// for KITTI-style input: depth = uint16 / 256 (main.cpp:75-82), i.e. every pixel is 0 or k/256 with
+// 26 <= k <= 25574 ("strict q8").  For such frames every stage up to and including the 5x5 Gaussian is exact
+// integer arithmetic, so the whole pipeline runs on packed uint16x2 words:
+//
+//   encoding   e = 0                absent / -FLT_MAX (OpenCV's dilate border value)
+//              e = q + 1            depth q/256 in inverted space;  hole <=> e == 1,  valid <=> e >= 27
+//   k_q8_front   (A1..A4, :55-100)   invert, 2-tap dilate, close5, dilate7 + hole fill on a 2-D tile held in
+//                                    shared memory; 7 passes fused, 128-bit shared-memory accesses, VIMNMX.U16x2 /
+//                                    VIMNMX3.U16x2 / PRMT; writes a uint16 plane + per-column first/last keys
+//   k_q8_tail    (A5..A10, :103-202) column extrapolation applied on load, 31x31 fill (vertical log-doubling +
+//                                    ballot/popc-compacted horizontal pass over hole words only), median5 by
+//                                    shared sorted columns + a 54-comparator selection network, Gaussian in
+//                                    integer q16, final inversion, float32 store
+//   k_q8_fixup   one CTA per frame, runs only for frames the tiles could not finish (a second fill pass needed)
+// Frames that are not strict q8 are detected (k_q8_classify or in-kernel validation) and go through generic.cu.
+// No tensor cores: nothing here is a contraction.
+#include "fused_q8.cuh"
+
+#include "median_f32.cuh"
+#include "median_net.cuh"
+
+namespace dcmt {
+namespace {
+
+constexpr int QT = 512;  // threads per CTA
+
+#define SPLAT16(x) ((uint32_t)(x) | ((uint32_t)(x) << 16))
+constexpr uint32_t E_VALID_MIN = 27;   // e >= 27  <=>  depth >= 0.1f  (26/256 = 0.1015625 is the smallest q8 value >= 0.1f)
+constexpr uint32_t E_HUNDRED = 25601;  // encoding of 100.0 (empty-column fill, img_completion.cpp:110)
+constexpr uint32_t kAbsMax = 0u;           // identity of max in the encoding (two lanes)
+constexpr uint32_t kAbsMin = 0xffffffffu;  // identity of min
+
+__device__ __forceinline__ uint32_t pmax(uint32_t a, uint32_t b) { return __vmaxu2(a, b); }
+__device__ __forceinline__ uint32_t pmin(uint32_t a, uint32_t b) { return __vminu2(a, b); }
+__device__ __forceinline__ uint32_t pmax3(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_u16x2(a, b, c); }
+__device__ __forceinline__ uint32_t pmin3(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_u16x2(a, b, c); }
+// (lo.hi16, hi.lo16): the pixel pair that starts one pixel to the right of `lo`
+__device__ __forceinline__ uint32_t odd_pair(uint32_t lo, uint32_t hi) { return __byte_perm(lo, hi, 0x5432); }
+
+template <bool kIsMax>
+__device__ __forceinline__ uint32_t pext3(uint32_t a, uint32_t b, uint32_t c) {
+    return kIsMax ? pmax3(a, b, c) : pmin3(a, b, c);
+}
+template <bool kIsMax>
+__device__ __forceinline__ uint32_t pext(uint32_t a, uint32_t b) {
+    return kIsMax ? pmax(a, b) : pmin(a, b);
+}
+
+__device__ __forceinline__ uint4 lds4(const uint32_t* p) { return *reinterpret_cast<const uint4*>(p); }
+__device__ __forceinline__ void sts4(uint32_t* p, uint4 v) { *reinterpret_cast<uint4*>(p) = v; }
+__device__ __forceinline__ uint4 splat4(uint32_t v) { return make_uint4(v, v, v, v); }
+
+// Blend the lanes of a quad (8 pixels starting at image column gx) that lie outside [0, cols) with `ident`.
+__device__ __forceinline__ uint4 mask_columns(uint4 v, int gx, int cols, uint32_t ident) {
+    uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int x0 = gx + 2 * j, x1 = x0 + 1;
+        const uint32_t m = ((x0 >= 0 && x0 < cols) ? 0x0000ffffu : 0u) | ((x1 >= 0 && x1 < cols) ? 0xffff0000u : 0u);
+        w[j] = (w[j] & m) | (ident & ~m);
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// Encode one input pixel (metres, float) into inverted q8 (+1).  img_completion.cpp:55-67.
+// strict q8 input: v == 0 (hole -> e = 1) or v = k/256 with 26 <= k <= 25574 (e = 25601 - k in [27, 25575]).
+__device__ __forceinline__ uint32_t encode_px(float v, int& bad) {
+    const float t = fmaf(v, -256.0f, 25601.0f);  // 25601 - k, exact for q8 input
+    const bool valid = v >= 0.1f;
+    const float ef = valid ? t : 1.0f;
+    const float m = ef + 8388608.0f;  // 2^23: integer lands in the low mantissa bits
+    // validation: holes must be exactly 0, valid pixels integral and inside [27, 25575]
+    bad |= valid ? !(m - 8388608.0f == t && t >= 27.0f && t <= 25575.0f) : (v != 0.0f);
+    return __float_as_uint(m) & 0xffffu;
+}
+
+struct FrontArgs {
+    const float* in;
+    size_t in_pitch, in_fstride;  // elements
+    uint16_t* mid;                // rows x mid_pitch uint16 per frame
+    size_t mid_pitch, mid_fstride;
+    uint32_t* col_first;          // mid_pitch keys per frame: (row << 16) | e of the first valid row, atomicMin
+    uint32_t* col_last;           // ... last valid row, atomicMax
+    FrameCounters* ctr;
+    int rows, cols, th, tw;
+    int vec_ok;                   // input rows are 16-byte aligned: float4 loads
+};
+
+// ------------------------------------------------------------------------------------------------
+// k_q8_front.  Region = core (th x tw) + {up 8, down 9} rows, {left 8, right 16} columns (the dependency cone is
+// up 8 / down 9 / left 7 / right 9; widths are rounded to 8-pixel quads).  Every pass handles (row, quad) items,
+// reads neighbours from one shared-memory plane with 128-bit loads and writes the other plane; cells outside the
+// image always hold the identity of the operator that reads them next.
+// ------------------------------------------------------------------------------------------------
+constexpr int FU = 8, FD = 9, FLQ = 1, FRQ = 2;  // rows up/down, quads left/right
+
+template <int R, bool kIsMax>
+__device__ __forceinline__ void v_pass(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int RH, int RQ, int gy0,
+                                       int gx0, int rows, int cols, uint32_t ident_next) {
+    const int pitchw = RQ * 4;
+    for (int it = threadIdx.x; it < RH * RQ; it += QT) {
+        const int r = it / RQ, q = it - r * RQ;
+        const int gy = gy0 + r, gx = gx0 + q * 8;
+        uint4 acc;
+        if (gy < 0 || gy >= rows) {
+            acc = splat4(ident_next);
+        } else {
+            acc = lds4(src + it * 4);
+#pragma unroll
+            for (int d = 1; d <= R; ++d) {
+                const uint4 up = lds4(src + max(r - d, 0) * pitchw + q * 4);
+                const uint4 dn = lds4(src + min(r + d, RH - 1) * pitchw + q * 4);
+                acc.x = pext3<kIsMax>(acc.x, up.x, dn.x);
+                acc.y = pext3<kIsMax>(acc.y, up.y, dn.y);
+                acc.z = pext3<kIsMax>(acc.z, up.z, dn.z);
+                acc.w = pext3<kIsMax>(acc.w, up.w, dn.w);
+            }
+            if (gx < 0 || gx + 8 > cols) acc = mask_columns(acc, gx, cols, ident_next);
+        }
+        sts4(dst + it * 4, acc);
+    }
+}
+
+// horizontal 5-window: out_j = ext(P_{j-1}, R_j, P_j, R_{j+1}, P_{j+1}),  R_j = (c_{2j-1}, c_{2j})
+template <bool kIsMax>
+__device__ __forceinline__ void h5_pass(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int RH, int RQ, int gy0,
+                                        int gx0, int rows, int cols, uint32_t ident_next) {
+    const int pitchw = RQ * 4;
+    for (int it = threadIdx.x; it < RH * RQ; it += QT) {
+        const int r = it / RQ, q = it - r * RQ;
+        const int gy = gy0 + r, gx = gx0 + q * 8;
+        uint4 o;
+        if (gy < 0 || gy >= rows) {
+            o = splat4(ident_next);
+        } else {
+            const uint32_t* row = src + r * pitchw;
+            const uint4 c = lds4(row + q * 4);
+            const uint32_t wl = row[max(q * 4 - 1, 0)], wr = row[min(q * 4 + 4, pitchw - 1)];
+            const uint32_t r0 = odd_pair(wl, c.x), r1 = odd_pair(c.x, c.y), r2 = odd_pair(c.y, c.z), r3 = odd_pair(c.z, c.w),
+                           r4 = odd_pair(c.w, wr);
+            o.x = pext3<kIsMax>(pext3<kIsMax>(wl, r0, c.x), r1, c.y);
+            o.y = pext3<kIsMax>(pext3<kIsMax>(c.x, r1, c.y), r2, c.z);
+            o.z = pext3<kIsMax>(pext3<kIsMax>(c.y, r2, c.z), r3, c.w);
+            o.w = pext3<kIsMax>(pext3<kIsMax>(c.z, r3, c.w), r4, wr);
+            if (gx < 0 || gx + 8 > cols) o = mask_columns(o, gx, cols, ident_next);
+        }
+        sts4(dst + it * 4, o);
+    }
+}
+
+// horizontal 7-window max of one quad: out_j = max(R_{j-1}, R_j, R_{j+1}, R_{j+2}, P_{j-1}, P_j, P_{j+1})
+__device__ __forceinline__ uint4 h7_max_quad(const uint32_t* __restrict__ row, int q, int pitchw) {
+    const uint4 c = lds4(row + q * 4);
+    const int il = max(q * 4 - 2, 0), ir = min(q * 4 + 4, pitchw - 2);
+    const uint2 l = *reinterpret_cast<const uint2*>(row + il);
+    const uint2 rr = *reinterpret_cast<const uint2*>(row + ir);
+    // words w[-2..5]
+    const uint32_t wm2 = l.x, wm1 = l.y, w0 = c.x, w1 = c.y, w2 = c.z, w3 = c.w, w4 = rr.x, w5 = rr.y;
+    const uint32_t rm1 = odd_pair(wm2, wm1), r0 = odd_pair(wm1, w0), r1 = odd_pair(w0, w1), r2 = odd_pair(w1, w2),
+                   r3 = odd_pair(w2, w3), r4 = odd_pair(w3, w4), r5 = odd_pair(w4, w5);
+    uint4 o;
+    o.x = pmax3(pmax3(rm1, r0, r1), pmax3(r2, wm1, w0), w1);
+    o.y = pmax3(pmax3(r0, r1, r2), pmax3(r3, w0, w1), w2);
+    o.z = pmax3(pmax3(r1, r2, r3), pmax3(r4, w1, w2), w3);
+    o.w = pmax3(pmax3(r2, r3, r4), pmax3(r5, w2, w3), w4);
+    return o;
+}
+
+// d = hole(d) ? t : d for two packed lanes, given t >= d >= 1 and holes == 1 exactly (img_completion.cpp:92-99):
+//   a = d - 27 (mod 2^16) is huge for holes, small otherwise;  min(t - 27, a) + 27 picks t for holes, d otherwise.
+__device__ __forceinline__ uint32_t fill_holes(uint32_t d, uint32_t t) {
+    const uint32_t k = SPLAT16(65536 - 27);
+    return __vadd2(pmin(__vadd2(t, k), __vadd2(d, k)), SPLAT16(27));
+}
+
+__global__ void __launch_bounds__(QT) k_q8_front(FrontArgs a) {
+    DCMT_DYN_SMEM(uint32_t, smem);
+    const int th = a.th, tw = a.tw, rows = a.rows, cols = a.cols;
+    const int RH = th + FU + FD, RQ = tw / 8 + FLQ + FRQ, pitchw = RQ * 4;
+    uint32_t* A = smem;
+    uint32_t* B = smem + RH * pitchw;
+    const int frame = blockIdx.z;  // slot == frame offset inside the chunk
+    const int y0 = blockIdx.y * th, x0 = blockIdx.x * tw;
+    const int gy0 = y0 - FU, gx0 = x0 - FLQ * 8;
+    const float* in = a.in + (size_t)frame * a.in_fstride;
+    const bool interior = gy0 >= 0 && gy0 + RH <= rows && gx0 >= 0 && gx0 + RQ * 8 <= cols;
+
+    // ---- pass 0: load, validate, invert, encode (:55-67)
+    int bad = 0;
+    if (interior && a.vec_ok) {
+        for (int it = threadIdx.x; it < RH * RQ; it += QT) {
+            const int r = it / RQ, q = it - r * RQ;
+            const float4* p = reinterpret_cast<const float4*>(in + (size_t)(gy0 + r) * a.in_pitch + gx0 + q * 8);
+            const float4 f0 = __ldg(p), f1 = __ldg(p + 1);
+            uint4 o;
+            o.x = encode_px(f0.x, bad) | (encode_px(f0.y, bad) << 16);
+            o.y = encode_px(f0.z, bad) | (encode_px(f0.w, bad) << 16);
+            o.z = encode_px(f1.x, bad) | (encode_px(f1.y, bad) << 16);
+            o.w = encode_px(f1.z, bad) | (encode_px(f1.w, bad) << 16);
+            sts4(A + it * 4, o);
+        }
+    } else {
+        for (int it = threadIdx.x; it < RH * RQ; it += QT) {
+            const int r = it / RQ, q = it - r * RQ;
+            const int gy = gy0 + r, gx = gx0 + q * 8;
+            uint32_t e[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int x = gx + j;
+                e[j] = 0u;  // outside the image: absent
+                if (gy >= 0 && gy < rows && x >= 0 && x < cols) e[j] = encode_px(__ldg(in + (size_t)gy * a.in_pitch + x), bad);
+            }
+            sts4(A + it * 4, make_uint4(e[0] | (e[1] << 16), e[2] | (e[3] << 16), e[4] | (e[5] << 16), e[6] | (e[7] << 16)));
+        }
+    }
+    if (__syncthreads_or(bad)) {  // not strict q8: this frame is redone by the generic pipeline
+        if (threadIdx.x == 0) a.ctr[frame].needs_generic = 1;
+        return;
+    }
+
+    // ---- pass 1: 2-tap dilate (:71-80)  out(y,x) = max(in(y-1,x+1), in(y+2,x+2)), absent taps = -FLT_MAX (e = 0)
+    for (int it = threadIdx.x; it < RH * RQ; it += QT) {
+        const int r = it / RQ, q = it - r * RQ;
+        const int gy = gy0 + r, gx = gx0 + q * 8;
+        uint4 o = splat4(kAbsMax);
+        if (gy >= 0 && gy < rows) {
+            const uint32_t* ra = A + max(r - 1, 0) * pitchw;
+            const uint32_t* rb = A + min(r + 2, RH - 1) * pitchw;
+            const uint4 ca = lds4(ra + q * 4), cb = lds4(rb + q * 4);
+            const int inext = min(q * 4 + 4, pitchw - 1);
+            const uint32_t na = ra[inext], nb = rb[inext];
+            // tap 1: pixels (x+1, x+2) of row y-1; tap 2: pixels (x+2, x+3) of row y+2
+            o.x = pmax(odd_pair(ca.x, ca.y), cb.y);
+            o.y = pmax(odd_pair(ca.y, ca.z), cb.z);
+            o.z = pmax(odd_pair(ca.z, ca.w), cb.w);
+            o.w = pmax(odd_pair(ca.w, na), nb);
+            if (gx < 0 || gx + 8 > cols) o = mask_columns(o, gx, cols, kAbsMax);
+        }
+        sts4(B + it * 4, o);
+    }
+    __syncthreads();
+    // ---- passes 2-5: close5 (:84-85) = dilate5 (V, H) then erode5 (H, V)
+    v_pass<2, true>(B, A, RH, RQ, gy0, gx0, rows, cols, kAbsMax);
+    __syncthreads();
+    h5_pass<true>(A, B, RH, RQ, gy0, gx0, rows, cols, kAbsMin);
+    __syncthreads();
+    h5_pass<false>(B, A, RH, RQ, gy0, gx0, rows, cols, kAbsMin);
+    __syncthreads();
+    v_pass<2, false>(A, B, RH, RQ, gy0, gx0, rows, cols, kAbsMax);  // B = D, the closed image
+    __syncthreads();
+    // ---- pass 6: vertical half of dilate7 (:88-90)
+    v_pass<3, true>(B, A, RH, RQ, gy0, gx0, rows, cols, kAbsMax);
+    __syncthreads();
+    // ---- pass 7: horizontal half of dilate7, hole fill (:92-100), store the core
+    const int CQ = tw / 8;
+    uint16_t* mid = a.mid + (size_t)frame * a.mid_fstride;
+    for (int it = threadIdx.x; it < th * CQ; it += QT) {
+        const int cy = it / CQ, cq = it - cy * CQ;
+        const int r = cy + FU, q = cq + FLQ;
+        const int gy = y0 + cy, gx = x0 + cq * 8;
+        if (gy >= rows || gx >= cols) continue;
+        const uint4 t = h7_max_quad(A + r * pitchw, q, pitchw);
+        uint4 d = lds4(B + r * pitchw + q * 4);
+        d.x = fill_holes(d.x, t.x);
+        d.y = fill_holes(d.y, t.y);
+        d.z = fill_holes(d.z, t.z);
+        d.w = fill_holes(d.w, t.w);
+        sts4(B + r * pitchw + q * 4, d);  // only this thread reads this quad of B in this pass
+        *reinterpret_cast<uint4*>(mid + (size_t)gy * a.mid_pitch + gx) = d;
+    }
+    __syncthreads();
+    // ---- per-column first / last valid row inside this tile (feeds :103-129), merged across tiles by atomics
+    const uint16_t* Bh = reinterpret_cast<const uint16_t*>(B);
+    for (int c = threadIdx.x; c < tw; c += QT) {
+        const int gx = x0 + c;
+        if (gx >= cols) continue;
+        const int hrows = min(th, rows - y0);
+        const int col = (FLQ * 8 + c);
+        int first = -1, last = -1;
+        uint32_t ef = 0, el = 0;
+        for (int cy = 0; cy < hrows; ++cy) {
+            const uint32_t e = Bh[(size_t)(cy + FU) * pitchw * 2 + col];
+            if (e >= E_VALID_MIN) { first = cy; ef = e; break; }
+        }
+        if (first < 0) continue;
+        for (int cy = hrows - 1; cy >= 0; --cy) {
+            const uint32_t e = Bh[(size_t)(cy + FU) * pitchw * 2 + col];
+            if (e >= E_VALID_MIN) { last = cy; el = e; break; }
+        }
+        atomicMin(a.col_first + (size_t)frame * a.mid_pitch + gx, ((uint32_t)(y0 + first) << 16) | ef);
+        atomicMax(a.col_last + (size_t)frame * a.mid_pitch + gx, ((uint32_t)(y0 + last) << 16) | el);
+    }
+}
+
+__global__ void k_q8_init_cols(uint32_t* first, uint32_t* last, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { first[i] = 0xffffffffu; last[i] = 0u; }
+}
+
+// debugging / test aid: decode a uint16 plane back to float metres in inverted space
+__global__ void k_q8_decode(const uint16_t* __restrict__ mid, size_t mid_pitch, float* __restrict__ out, int rows, int cols) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= cols || y >= rows) return;
+    const uint32_t e = mid[(size_t)y * mid_pitch + x];
+    out[(size_t)y * cols + x] = e == 0 ? -FLT_MAX : (float)(e - 1) * (1.0f / 256.0f);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// k_q8_tail.  Region = core + 19 rows up/down and 24 columns (3 quads) left/right: 15 (one effective 31x31
+// fill) + 2 (median) + 2 (Gaussian) = 19.  Two shared-memory planes: A = image, B = vertical 16-row maxima,
+// later the median image.
+// ------------------------------------------------------------------------------------------------
+constexpr int TV = 19, TQ = 3;  // rows up/down, quads left/right
+constexpr int KIPT = 8;         // register-resident quads per thread in the in-place doubling steps
+
+struct TailArgs {
+    const uint16_t* mid;
+    size_t mid_pitch, mid_fstride;
+    const uint32_t* col_first;
+    const uint32_t* col_last;
+    FrameCounters* ctr;
+    float* out;
+    size_t out_pitch, out_fstride;
+    int rows, cols, th, tw, blur, vec2_ok;
+};
+
+struct PackedOps {
+    static __device__ __forceinline__ uint32_t mn(uint32_t a, uint32_t b) { return pmin(a, b); }
+    static __device__ __forceinline__ uint32_t mx(uint32_t a, uint32_t b) { return pmax(a, b); }
+    static __device__ __forceinline__ uint32_t mn3(uint32_t a, uint32_t b, uint32_t c) { return pmin3(a, b, c); }
+    static __device__ __forceinline__ uint32_t mx3(uint32_t a, uint32_t b, uint32_t c) { return pmax3(a, b, c); }
+};
+
+__device__ __forceinline__ void pcswap(uint32_t& a, uint32_t& b) {
+    const uint32_t lo = pmin(a, b);
+    b = pmax(a, b);
+    a = lo;
+}
+// optimal 9-comparator sort of five packed words (both lanes independently)
+__device__ __forceinline__ void sort5(uint32_t (&v)[5]) {
+    pcswap(v[0], v[1]); pcswap(v[3], v[4]); pcswap(v[2], v[4]); pcswap(v[2], v[3]); pcswap(v[0], v[3]);
+    pcswap(v[0], v[2]); pcswap(v[1], v[4]); pcswap(v[1], v[3]); pcswap(v[1], v[2]);
+}
+
+// lanes equal to 1 (holes) -> 0xffff mask per lane
+__device__ __forceinline__ uint32_t hole_mask(uint32_t w) {
+    return (((w & 0xffffu) == 1u) ? 0x0000ffffu : 0u) | (((w >> 16) == 1u) ? 0xffff0000u : 0u);
+}
+
+// q16 inverted-space value -> output float: img_completion.cpp:191-202 (d >= 0.1f <=> d16 >= 6554), exact
+__device__ __forceinline__ float finish_px(uint32_t d16) {
+    const uint32_t o = d16 >= 6554u ? 6553600u - d16 : d16;
+    return fmaf(__uint_as_float(0x4b000000u + o), 1.0f / 65536.0f, -128.0f);  // (2^23 + o) / 2^16 - 128
+}
+
+__global__ void __launch_bounds__(QT) k_q8_tail(TailArgs a) {
+    DCMT_DYN_SMEM(uint32_t, smem);
+    const int th = a.th, tw = a.tw, rows = a.rows, cols = a.cols;
+    const int RH = th + 2 * TV, RQ = tw / 8 + 2 * TQ, pitchw = RQ * 4;
+    uint32_t* A = smem;
+    uint32_t* B = smem + RH * pitchw;
+    uint16_t* list = reinterpret_cast<uint16_t*>(B + RH * pitchw);
+    uint16_t* Ah = reinterpret_cast<uint16_t*>(A);
+    uint16_t* Bh = reinterpret_cast<uint16_t*>(B);
+    __shared__ int s_count, s_remaining, s_holes_core, s_left_core;
+    const int slot = blockIdx.z;
+    if (a.ctr[slot].needs_generic) return;  // not strict q8: the generic pipeline redoes this frame
+    const int y0 = blockIdx.y * th, x0 = blockIdx.x * tw;
+    const int gy0 = y0 - TV, gx0 = x0 - TQ * 8;
+    const uint16_t* mid = a.mid + (size_t)slot * a.mid_fstride;
+    const bool border = gy0 < 0 || gy0 + RH > rows || gx0 < 0 || gx0 + RQ * 8 > cols;
+    if (threadIdx.x == 0) { s_count = 0; s_remaining = 0; s_holes_core = 0; s_left_core = 0; }
+
+    // ---- load the A4 plane (outside the image: absent)
+    for (int it = threadIdx.x; it < RH * RQ; it += QT) {
+        const int r = it / RQ, q = it - r * RQ;
+        const int gy = gy0 + r, gx = gx0 + q * 8;
+        uint4 v = splat4(kAbsMax);
+        if (gy >= 0 && gy < rows && gx >= 0 && gx < cols) {
+            v = __ldg(reinterpret_cast<const uint4*>(mid + (size_t)gy * a.mid_pitch + gx));
+            if (gx + 8 > cols) v = mask_columns(v, gx, cols, kAbsMax);
+        }
+        sts4(A + it * 4, v);
+    }
+    __syncthreads();
+    // ---- A5 column extrapolation (:103-129) from the per-column keys: rows >= last <- value(last), then
+    //      rows <= first <- value(first) (second write wins); empty column <- 100
+    {
+        const int RW = RQ * 8, chunks = (RH + 15) / 16;
+        for (int it = threadIdx.x; it < RW * chunks; it += QT) {
+            const int ch = it / RW, c = it - ch * RW;
+            const int gx = gx0 + c;
+            if (gx < 0 || gx >= cols) continue;
+            const uint32_t kf = __ldg(a.col_first + (size_t)slot * a.mid_pitch + gx);
+            const uint32_t kl = __ldg(a.col_last + (size_t)slot * a.mid_pitch + gx);
+            const bool empty = kf == 0xffffffffu;
+            const int first = empty ? rows - 1 : (int)(kf >> 16), last = empty ? 0 : (int)(kl >> 16);
+            const uint16_t nv = empty ? (uint16_t)E_HUNDRED : (uint16_t)(kf & 0xffffu);
+            const uint16_t mv = empty ? (uint16_t)E_HUNDRED : (uint16_t)(kl & 0xffffu);
+            const int r_lo = ch * 16, r_hi = min(RH, r_lo + 16);
+            for (int r = r_lo; r < r_hi; ++r) {
+                const int gy = gy0 + r;
+                if (gy < 0 || gy >= rows) continue;
+                if (gy <= first) Ah[(size_t)r * pitchw * 2 + c] = nv;
+                else if (gy >= last) Ah[(size_t)r * pitchw * 2 + c] = mv;
+            }
+        }
+    }
+    __syncthreads();
+    // ---- A6 vertical part: B(r) = max of A over rows r .. r+15 by log-doubling; steps 2..4 run in place with
+    //      the thread's quads held in registers
+    for (int it = threadIdx.x; it < RH * RQ; it += QT) {
+        const int r = it / RQ;
+        const uint4 x = lds4(A + it * 4), y = lds4(A + (min(r + 1, RH - 1) * RQ + (it - r * RQ)) * 4);
+        sts4(B + it * 4, make_uint4(pmax(x.x, y.x), pmax(x.y, y.y), pmax(x.z, y.z), pmax(x.w, y.w)));
+    }
+    __syncthreads();
+    {
+        uint4 v[KIPT];
+#pragma unroll
+        for (int k = 0; k < KIPT; ++k) {
+            const int it = threadIdx.x + k * QT;
+            if (it < RH * RQ) v[k] = lds4(B + it * 4);
+        }
+#pragma unroll
+        for (int step = 2; step <= 8; step *= 2) {
+#pragma unroll
+            for (int k = 0; k < KIPT; ++k) {
+                const int it = threadIdx.x + k * QT;
+                if (it < RH * RQ) {
+                    const int r = it / RQ, q = it - r * RQ;
+                    const uint4 y = lds4(B + (min(r + step, RH - 1) * RQ + q) * 4);
+                    v[k] = make_uint4(pmax(v[k].x, y.x), pmax(v[k].y, y.y), pmax(v[k].z, y.z), pmax(v[k].w, y.w));
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < KIPT; ++k) {
+                const int it = threadIdx.x + k * QT;
+                if (it < RH * RQ) sts4(B + it * 4, v[k]);
+            }
+            __syncthreads();
+        }
+    }
+    // ---- A6 horizontal part on hole words only: ballot/popc compaction of the words that hold a hole, then
+    //      a 31-wide max of the vertical maxima for those words (:131-144)
+    const int SH = th + 8, SW = tw / 2 + 4;          // scan region: core +- 4 rows, +- 2 words
+    const int sr0 = TV - 4, sw0 = TQ * 4 - 2;
+    int holes_core = 0;
+    for (int base = 0; base < SH * SW; base += QT) {
+        const int idx = base + threadIdx.x;
+        bool has = false;
+        int widx = 0;
+        if (idx < SH * SW) {
+            const int sr = idx / SW, sw = idx - sr * SW;
+            widx = (sr0 + sr) * pitchw + sw0 + sw;
+            const uint32_t hm = hole_mask(A[widx]);
+            has = hm != 0u;
+            if (has && sr >= 4 && sr < 4 + th && sw >= 2 && sw < 2 + tw / 2) holes_core += __popc(hm) >> 4;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, has);
+        int basepos = 0;
+        if ((threadIdx.x & 31) == 0 && bal) basepos = atomicAdd(&s_count, __popc(bal));
+        basepos = __shfl_sync(0xffffffffu, basepos, 0);
+        if (has) list[basepos + __popc(bal & ((1u << (threadIdx.x & 31)) - 1u))] = (uint16_t)widx;
+    }
+    __syncthreads();
+    int left_core = 0, left_any = 0;
+    for (int k = threadIdx.x; k < s_count; k += QT) {
+        const int widx = list[k];
+        const int r = widx / pitchw, w = widx - r * pitchw;
+        const uint32_t* b0 = B + max(r - 15, 0) * pitchw;  // rows r-15 .. r
+        const uint32_t* b1 = B + r * pitchw;               // rows r .. r+15
+        uint32_t m = 0u;
+#pragma unroll
+        for (int j = -7; j <= 7; ++j) m = pmax3(m, b0[w + j], b1[w + j]);
+        // m.lo / m.hi hold the maxima over the even / odd columns of words w-7 .. w+7; both output lanes need
+        // both (lane swap), plus column 2w-15 for the low lane only and column 2w+16 for the high lane only
+        m = pmax3(m, __byte_perm(m, m, 0x1032), odd_pair(pmax(b0[w - 8], b1[w - 8]), pmax(b0[w + 8], b1[w + 8])));
+        const uint32_t d = A[widx], hm = hole_mask(d);
+        const uint32_t nd = (m & hm) | (d & ~hm);
+        A[widx] = nd;
+        const uint32_t still = hole_mask(nd);
+        if (still) {
+            left_any = 1;
+            const int sr = r - sr0, sw = w - sw0;
+            if (sr >= 4 && sr < 4 + th && sw >= 2 && sw < 2 + tw / 2) left_core += __popc(still) >> 4;
+        }
+    }
+    if (holes_core) atomicAdd(&s_holes_core, holes_core);
+    if (left_core) atomicAdd(&s_left_core, left_core);
+    if (left_any) s_remaining = 1;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_holes_core) atomicAdd(&a.ctr[slot].holes_after_extrapolation, s_holes_core);
+        if (s_left_core) atomicAdd(&a.ctr[slot].holes_after_first_fill, s_left_core);
+        if (s_remaining) a.ctr[slot].holes_remaining = 1;  // a second pass is needed: k_q8_fixup redoes the frame
+    }
+    // ---- BORDER_REPLICATE for the median (:170): copy the nearest image pixel into cells outside the image
+    if (border) {
+        for (int it = threadIdx.x; it < SH * (tw + 8); it += QT) {
+            const int sr = it / (tw + 8), sc = it - sr * (tw + 8);
+            const int r = sr0 + sr, c = TQ * 8 - 4 + sc;
+            const int gy = gy0 + r, gx = gx0 + c;
+            if (gy >= 0 && gy < rows && gx >= 0 && gx < cols) continue;
+            const int cr = clampi(gy, 0, rows - 1) - gy0, cc = clampi(gx, 0, cols - 1) - gx0;
+            if (cr >= 0 && cr < RH && cc >= 0 && cc < RQ * 8) Ah[(size_t)r * pitchw * 2 + c] = Ah[(size_t)cr * pitchw * 2 + cc];
+        }
+        __syncthreads();
+    }
+    // ---- A8 median 5x5: sorted columns shared by the two output words of an item + selection network
+    {
+        const int MH = th + 4, MI = tw / 4 + 1;  // rows core +- 2; items of two words covering core +- 1 word
+        const int mr0 = TV - 2, mw0 = TQ * 4 - 1;
+        for (int it = threadIdx.x; it < MH * MI; it += QT) {
+            const int mr = it / MI, mi = it - mr * MI;
+            const int r = mr0 + mr, w = mw0 + 2 * mi;  // output words w, w+1; columns w-1 .. w+2
+            uint32_t col[4][5];
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                const uint32_t* row = A + (r - 2 + k) * pitchw + (w - 1);
+                const uint2 p0 = *reinterpret_cast<const uint2*>(row), p1 = *reinterpret_cast<const uint2*>(row + 2);
+                col[0][k] = p0.x; col[1][k] = p0.y; col[2][k] = p1.x; col[3][k] = p1.y;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) sort5(col[j]);
+            uint32_t odd[3][5];  // sorted columns of the odd-aligned pixel pairs between the words
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+#pragma unroll
+                for (int k = 0; k < 5; ++k) odd[j][k] = odd_pair(col[j][k], col[j + 1][k]);
+#pragma unroll
+            for (int o = 0; o < 2; ++o) {
+                uint32_t c[25];
+#pragma unroll
+                for (int k = 0; k < 5; ++k) {
+                    c[k] = col[o][k];
+                    c[5 + k] = odd[o][k];
+                    c[10 + k] = col[o + 1][k];
+                    c[15 + k] = odd[o + 1][k];
+                    c[20 + k] = col[o + 2][k];
+                }
+                B[r * pitchw + w + o] = median25_sorted_columns<PackedOps>(c);
+            }
+        }
+    }
+    __syncthreads();
+    float* out = a.out + (size_t)slot * a.out_fstride;
+    if (a.blur == 0) {
+        // no blur: final inversion only (:191-202)
+        for (int it = threadIdx.x; it < th * (tw / 2); it += QT) {
+            const int cy = it / (tw / 2), cw = it - cy * (tw / 2);
+            const int gy = y0 + cy, gx = x0 + 2 * cw;
+            if (gy >= rows || gx >= cols) continue;
+            const uint32_t m = B[(TV + cy) * pitchw + TQ * 4 + cw];
+            const float f0 = finish_px(((m & 0xffffu) - 1u) << 8), f1 = finish_px(((m >> 16) - 1u) << 8);
+            float* o = out + (size_t)gy * a.out_pitch + gx;
+            if (gx + 1 < cols && a.vec2_ok) *reinterpret_cast<float2*>(o) = make_float2(f0, f1);
+            else { o[0] = f0; if (gx + 1 < cols) o[1] = f1; }
+        }
+        return;
+    }
+    // ---- BORDER_REFLECT_101 for the Gaussian (:179): mirror the median image into the 2 cells beyond each edge
+    if (border) {
+        for (int it = threadIdx.x; it < (th + 4) * (tw + 4); it += QT) {
+            const int sr = it / (tw + 4), sc = it - sr * (tw + 4);
+            const int r = TV - 2 + sr, c = TQ * 8 - 2 + sc;
+            const int gy = gy0 + r, gx = gx0 + c;
+            if (gy >= 0 && gy < rows && gx >= 0 && gx < cols) continue;
+            if (gy < -2 || gy > rows + 1 || gx < -2 || gx > cols + 1) continue;
+            const int cr = reflect101(gy, rows) - gy0, cc = reflect101(gx, cols) - gx0;
+            if (cr >= TV - 2 && cr < TV + th + 2 && cc >= TQ * 8 - 2 && cc < TQ * 8 + tw + 2)
+                Bh[(size_t)r * pitchw * 2 + c] = Bh[(size_t)cr * pitchw * 2 + cc];
+        }
+        __syncthreads();
+    }
+    // ---- A9 + A10: 5x5 Gaussian [1 4 6 4 1]^2 / 256 in integer q16 where the median is valid (:176-189), final
+    //      inversion (:191-202), float32 store.  One thread walks a word column over a segment of rows with the
+    //      horizontal sums of the last five rows in registers.
+    {
+        const int CW = tw / 2;
+        const int nseg = 8, seg = (th + nseg - 1) / nseg;
+        for (int it = threadIdx.x; it < nseg * CW; it += QT) {
+            const int s = it / CW, cw = it - s * CW;
+            const int cy0 = s * seg, cy1 = min(th, cy0 + seg);
+            const int gx = x0 + 2 * cw;
+            if (cy0 >= cy1 || gx >= cols || y0 + cy0 >= rows) continue;
+            const int w = TQ * 4 + cw;
+            uint32_t hl[5], hh[5], mc[3];
+#pragma unroll
+            for (int k = 0; k < 5; ++k) hl[k] = hh[k] = 0u;
+            mc[0] = mc[1] = mc[2] = 0u;
+            for (int cy = cy0 - 2; cy < cy1 + 2; ++cy) {
+                const uint32_t* row = B + (TV + cy) * pitchw + w;
+                const uint32_t pa = row[-1], pb = row[0], pc = row[1];
+                const uint32_t a0 = pa & 0xffffu, a1 = pa >> 16, b0 = pb & 0xffffu, b1 = pb >> 16, c0 = pc & 0xffffu, c1 = pc >> 16;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { hl[k] = hl[k + 1]; hh[k] = hh[k + 1]; }
+                mc[0] = mc[1]; mc[1] = mc[2]; mc[2] = pb;
+                hl[4] = (a0 + c0) + 4u * (a1 + b1) + 6u * b0;  // pixel 2w:   columns 2w-2 .. 2w+2
+                hh[4] = (a1 + c1) + 4u * (b0 + c0) + 6u * b1;  // pixel 2w+1: columns 2w-1 .. 2w+3
+                const int oy = cy - 2;  // the window is centred two rows back
+                if (oy < cy0) continue;
+                const int gy = y0 + oy;
+                if (gy >= rows) break;
+                const uint32_t gl = (hl[0] + hl[4]) + 4u * (hl[1] + hl[3]) + 6u * hl[2];
+                const uint32_t gh = (hh[0] + hh[4]) + 4u * (hh[1] + hh[3]) + 6u * hh[2];
+                const uint32_t ml = mc[0] & 0xffffu, mh = mc[0] >> 16;
+                // e = q + 1: the weights sum to 256, so the blurred q16 value is g - 256
+                const float f0 = finish_px(ml >= E_VALID_MIN ? gl - 256u : (ml - 1u) << 8);
+                const float f1 = finish_px(mh >= E_VALID_MIN ? gh - 256u : (mh - 1u) << 8);
+                float* o = out + (size_t)gy * a.out_pitch + gx;
+                if (gx + 1 < cols && a.vec2_ok) *reinterpret_cast<float2*>(o) = make_float2(f0, f1);
+                else { o[0] = f0; if (gx + 1 < cols) o[1] = f1; }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_q8_fixup: one CTA per slot; returns at once unless the tiles found holes left after the first 31x31 fill
+// (the reference's while loop then runs more than one effective pass, :146-166).  Redoes A5..A10 for the whole
+// frame in float, in global memory (L2 resident).  Rare and slow by design.
+// ------------------------------------------------------------------------------------------------
+struct FixupArgs {
+    const uint16_t* mid;
+    size_t mid_pitch, mid_fstride;
+    const uint32_t* col_first;
+    const uint32_t* col_last;
+    FrameCounters* ctr;
+    float* w1;
+    float* w2;
+    float* out;
+    size_t out_pitch, out_fstride;
+    int rows, cols, blur, max_passes;
+};
+
+__global__ void __launch_bounds__(1024) k_q8_fixup(FixupArgs a) {
+    const int slot = blockIdx.x;
+    if (a.ctr[slot].needs_generic || !a.ctr[slot].holes_remaining) return;
+    const int rows = a.rows, cols = a.cols;
+    const size_t fpix = (size_t)rows * cols;
+    const uint16_t* mid = a.mid + (size_t)slot * a.mid_fstride;
+    float* D = a.w1 + (size_t)slot * fpix;
+    float* T = a.w2 + (size_t)slot * fpix;
+    float* out = a.out + (size_t)slot * a.out_fstride;
+    // decode + A5
+    for (size_t i = threadIdx.x; i < fpix; i += blockDim.x) {
+        const int y = (int)(i / cols), x = (int)(i - (size_t)y * cols);
+        const uint32_t kf = a.col_first[(size_t)slot * a.mid_pitch + x], kl = a.col_last[(size_t)slot * a.mid_pitch + x];
+        const bool empty = kf == 0xffffffffu;
+        const int first = empty ? rows - 1 : (int)(kf >> 16), last = empty ? 0 : (int)(kl >> 16);
+        uint32_t e = mid[(size_t)y * a.mid_pitch + x];
+        if (y <= first) e = empty ? E_HUNDRED : (kf & 0xffffu);
+        else if (y >= last) e = empty ? E_HUNDRED : (kl & 0xffffu);
+        D[i] = (float)(e - 1u) * (1.0f / 256.0f);
+    }
+    __syncthreads();
+    int passes = 0, any = 1;
+    while (any && passes < a.max_passes) {  // A6 + A7
+        for (size_t i = threadIdx.x; i < fpix; i += blockDim.x) {
+            const int y = (int)(i / cols), x = (int)(i - (size_t)y * cols);
+            const int lo = max(x - 15, 0), hi = min(x + 15, cols - 1);
+            const float* row = D + (size_t)y * cols;
+            float m = row[lo];
+            for (int k = lo + 1; k <= hi; ++k) m = fmaxf(m, row[k]);
+            T[i] = m;
+        }
+        __syncthreads();
+        int remaining = 0;
+        for (size_t i = threadIdx.x; i < fpix; i += blockDim.x) {
+            if (!is_hole(D[i])) continue;
+            const int y = (int)(i / cols), x = (int)(i - (size_t)y * cols);
+            const int lo = max(y - 15, 0), hi = min(y + 15, rows - 1);
+            float m = T[(size_t)lo * cols + x];
+            for (int k = lo + 1; k <= hi; ++k) m = fmaxf(m, T[(size_t)k * cols + x]);
+            D[i] = m;
+            if (is_hole(m)) ++remaining;
+        }
+        ++passes;
+        any = __syncthreads_count(remaining > 0);
+    }
+    // A8 median (BORDER_REPLICATE) -> T
+    for (size_t i = threadIdx.x; i < fpix; i += blockDim.x) {
+        const int y = (int)(i / cols), x = (int)(i - (size_t)y * cols);
+        float w[25];
+#pragma unroll
+        for (int dy = 0; dy < 5; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 5; ++dx)
+                w[dy * 5 + dx] = D[(size_t)clampi(y + dy - 2, 0, rows - 1) * cols + clampi(x + dx - 2, 0, cols - 1)];
+        T[i] = median25(w, 5);
+    }
+    __syncthreads();
+    if (a.blur == 1) {  // A9 Gaussian rows -> D, then columns + mask + A10
+        const float k0 = 0.375f, k1 = 0.25f, k2 = 0.0625f;
+        for (size_t i = threadIdx.x; i < fpix; i += blockDim.x) {
+            const int y = (int)(i / cols), x = (int)(i - (size_t)y * cols);
+            const float* row = T + (size_t)y * cols;
+            D[i] = __fadd_rn(__fadd_rn(__fmul_rn(row[x], k0), __fmul_rn(__fadd_rn(row[reflect101(x - 1, cols)], row[reflect101(x + 1, cols)]), k1)),
+                             __fmul_rn(__fadd_rn(row[reflect101(x - 2, cols)], row[reflect101(x + 2, cols)]), k2));
+        }
+        __syncthreads();
+        for (size_t i = threadIdx.x; i < fpix; i += blockDim.x) {
+            const int y = (int)(i / cols), x = (int)(i - (size_t)y * cols);
+            float d = T[i];
+            if (is_valid(d)) {
+                const float c0 = D[i];
+                const float m1 = D[(size_t)reflect101(y - 1, rows) * cols + x], p1 = D[(size_t)reflect101(y + 1, rows) * cols + x];
+                const float m2 = D[(size_t)reflect101(y - 2, rows) * cols + x], p2 = D[(size_t)reflect101(y + 2, rows) * cols + x];
+                d = __fadd_rn(__fadd_rn(__fmul_rn(c0, k0), __fmul_rn(__fadd_rn(m1, p1), k1)), __fmul_rn(__fadd_rn(m2, p2), k2));
+            }
+            out[(size_t)y * a.out_pitch + x] = invert_valid(d);
+        }
+    } else {
+        for (size_t i = threadIdx.x; i < fpix; i += blockDim.x) {
+            const int y = (int)(i / cols), x = (int)(i - (size_t)y * cols);
+            out[(size_t)y * a.out_pitch + x] = invert_valid(T[i]);
+        }
+    }
+    if (threadIdx.x == 0) a.ctr[slot].extra_passes = passes - 1;
+}
+
+__global__ void k_q8_zero_counters(FrameCounters* c, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { c[i] = FrameCounters{}; c[i].path = 1; }
+}
+
+__global__ void k_q8_write_stats(const FrameCounters* __restrict__ c, int32_t* __restrict__ stats, int32_t* __restrict__ flags, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (stats) {
+        stats[4 * i + 0] = c[i].extra_passes + 1;
+        stats[4 * i + 1] = c[i].holes_after_first_fill;
+        stats[4 * i + 2] = c[i].holes_after_extrapolation;
+        stats[4 * i + 3] = c[i].needs_generic ? -1 : 1;
+    }
+    if (flags) flags[i] = c[i].needs_generic;
+}
+
+}  // namespace
+
+size_t q8_front_smem(int th, int tw) { return (size_t)2 * (th + FU + FD) * (tw / 8 + FLQ + FRQ) * 4 * sizeof(uint32_t); }
+
+size_t q8_tail_smem(int th, int tw) {
+    const size_t plane = (size_t)(th + 2 * TV) * (tw / 8 + 2 * TQ) * 4 * sizeof(uint32_t);
+    const size_t list = (size_t)(th + 8) * (tw / 2 + 4) * sizeof(uint16_t);
+    return 2 * plane + ((list + 15) & ~size_t(15));
+}
+
+void q8_choose_tile(int rows, int cols, int* th, int* tw) {
+    // tiles of about 96 x 160 that divide the frame evenly (KITTI 352 x 1216 -> 88 x 152, 4 x 8 tiles)
+    const int ny = (rows + 95) / 96, nx = (cols + 159) / 160;
+    *th = (rows + ny - 1) / ny;
+    *tw = (((cols + nx - 1) / nx) + 7) / 8 * 8;
+}
+
+cudaError_t q8_configure() {
+    cudaError_t e = cudaFuncSetAttribute(k_q8_front, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_q8_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+}
+
+cudaError_t q8_run_front(const Q8Plan& p, const float* in, size_t in_pitch, size_t in_fstride, int n_frames, cudaStream_t st) {
+    const size_t ncol = (size_t)p.mid_pitch * n_frames;
+    DCMT_LAUNCH(k_q8_zero_counters, dim3((n_frames + 127) / 128), dim3(128), 0, st, p.ctr, n_frames);
+    DCMT_LAUNCH(k_q8_init_cols, dim3((unsigned)((ncol + 255) / 256)), dim3(256), 0, st, p.col_first, p.col_last, ncol);
+    FrontArgs a{in, in_pitch, in_fstride, p.mid, (size_t)p.mid_pitch, (size_t)p.mid_pitch * p.rows, p.col_first, p.col_last,
+                p.ctr, p.rows, p.cols, p.th, p.tw,
+                (int)(in_pitch % 4 == 0 && in_fstride % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0)};
+    const dim3 grid((p.cols + p.tw - 1) / p.tw, (p.rows + p.th - 1) / p.th, n_frames);
+    DCMT_LAUNCH(k_q8_front, grid, dim3(QT), q8_front_smem(p.th, p.tw), st, a);
+    return cudaGetLastError();
+}
+
+cudaError_t q8_run_tail(const Q8Plan& p, float* out, size_t out_pitch, size_t out_fstride, int n_frames, int blur, cudaStream_t st) {
+    const int vec2 = out_pitch % 2 == 0 && out_fstride % 2 == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0;
+    TailArgs a{p.mid, (size_t)p.mid_pitch, (size_t)p.mid_pitch * p.rows, p.col_first, p.col_last, p.ctr, out, out_pitch,
+               out_fstride, p.rows, p.cols, p.th, p.tw, blur, vec2};
+    const dim3 grid((p.cols + p.tw - 1) / p.tw, (p.rows + p.th - 1) / p.th, n_frames);
+    DCMT_LAUNCH(k_q8_tail, grid, dim3(QT), q8_tail_smem(p.th, p.tw), st, a);
+    FixupArgs f{p.mid, (size_t)p.mid_pitch, (size_t)p.mid_pitch * p.rows, p.col_first, p.col_last, p.ctr, p.w1, p.w2, out,
+                out_pitch, out_fstride, p.rows, p.cols, blur, (p.rows > p.cols ? p.rows : p.cols) / 15 + 2};
+    DCMT_LAUNCH(k_q8_fixup, dim3(n_frames), dim3(1024), 0, st, f);
+    return cudaGetLastError();
+}
+
+cudaError_t q8_write_stats(const Q8Plan& p, int32_t* stats, int32_t* flags, int n_frames, cudaStream_t st) {
+    DCMT_LAUNCH(k_q8_write_stats, dim3((n_frames + 127) / 128), dim3(128), 0, st, p.ctr, stats, flags, n_frames);
+    return cudaGetLastError();
+}
+
+cudaError_t q8_decode_plane(const uint16_t* mid, size_t mid_pitch, float* out, int rows, int cols, cudaStream_t st) {
+    DCMT_LAUNCH(k_q8_decode, dim3((cols + 127) / 128, rows), dim3(128), 0, st, mid, mid_pitch, out, rows, cols);
+    return cudaGetLastError();
+}
+
+}  // namespace dcmt

@@ -1,0 +1,39 @@
+// fused_q8.cuh -- host-side interface of the strict-q8 fast path (fused_q8.cu).
+#pragma once
+#include "common.cuh"
+
+namespace dcmt {
+
+// Workspace + geometry of one chunk of frames on the fused path.  Buffers are indexed by SLOT
+// (position inside the chunk); the frame a slot maps to is slot (+ pointer offset applied by the caller).
+struct Q8Plan {
+    int rows, cols;
+    int th, tw;          // tile core (tw % 8 == 0)
+    int mid_pitch;       // uint16 per row of the intermediate plane (cols rounded up to 8)
+    int max_frames;      // slots
+    uint16_t* mid;       // max_frames * rows * mid_pitch
+    uint32_t* col_first; // max_frames * mid_pitch   (row << 16 | e) of the first valid row per column
+    uint32_t* col_last;  // max_frames * mid_pitch
+    FrameCounters* ctr;  // max_frames
+    float* w1;           // max_frames * rows * cols, fix-up scratch
+    float* w2;
+};
+
+// fused path applies to frames of at least this size (smaller ones use the generic pipeline)
+constexpr int kQ8MinRows = 32, kQ8MinCols = 32, kQ8MaxRows = 65535;
+
+void q8_choose_tile(int rows, int cols, int* th, int* tw);
+size_t q8_front_smem(int th, int tw);
+size_t q8_tail_smem(int th, int tw);
+cudaError_t q8_configure();
+// A1..A4 for n_frames slots: in -> plan.mid (+ column keys, counters zeroed)
+cudaError_t q8_run_front(const Q8Plan& p, const float* in, size_t in_pitch, size_t in_fstride, int n_frames, cudaStream_t st);
+// A5..A10: plan.mid -> out (float32), blur in {none, gaussian}; then the fix-up kernel
+cudaError_t q8_run_tail(const Q8Plan& p, float* out, size_t out_pitch, size_t out_fstride, int n_frames, int blur,
+                        cudaStream_t st);
+// counters -> stats[4*n] (optional) and flags[n] (1 = frame must be redone by the generic pipeline)
+cudaError_t q8_write_stats(const Q8Plan& p, int32_t* stats, int32_t* flags, int n_frames, cudaStream_t st);
+// test aid: decode a uint16 plane (inverted space) into float
+cudaError_t q8_decode_plane(const uint16_t* mid, size_t mid_pitch, float* out, int rows, int cols, cudaStream_t st);
+
+}  // namespace dcmt

@@ -12,6 +12,7 @@
 //     k_minmax/k_bilateral_lut/k_tail_bilateral  :172-175 bilateral variant (intended out-of-place call)
 // All min/max/select work is exact, so every stage up to the blur is bit-identical to OpenCV's.
 #include "generic.cuh"
+#include "median_f32.cuh"
 
 #include <cmath>
 
@@ -366,36 +367,6 @@ __global__ void __launch_bounds__(1024) k_fill31_loop(float* __restrict__ img, f
 // ------------------------------------------------------------------------------------------------
 constexpr int T_RH = TH + 8, T_RW = TW + 8;  // input region (halo 4)
 constexpr int T_MH = TH + 4, T_MW = TW + 4;  // median region (halo 2)
-
-__device__ __forceinline__ void cswap(float& a, float& b) {
-    const float lo = fminf(a, b);
-    b = fmaxf(a, b);
-    a = lo;
-}
-
-// exact median of 25 by forgetful selection: keep 14, drop min and max, add one, ... down to 3.
-__device__ __forceinline__ float median25(const float* __restrict__ p, int stride) {
-    float w[25];
-#pragma unroll
-    for (int dy = 0; dy < 5; ++dy)
-#pragma unroll
-        for (int dx = 0; dx < 5; ++dx) w[dy * 5 + dx] = p[dy * stride + dx];
-    float v[14];
-#pragma unroll
-    for (int i = 0; i < 14; ++i) v[i] = w[i];
-#pragma unroll
-    for (int n = 14; n >= 3; --n) {
-        // min of v[0..n) to v[0], max to v[n-1]
-#pragma unroll
-        for (int i = 0; i < n / 2; ++i) cswap(v[i], v[n - 1 - i]);
-#pragma unroll
-        for (int i = 1; i < (n + 1) / 2; ++i) cswap(v[0], v[i]);
-#pragma unroll
-        for (int i = n / 2; i < n - 1; ++i) cswap(v[i], v[n - 1]);
-        if (n > 3) v[0] = w[14 + (14 - n)];  // drop min (slot 0) and max (slot n-1), add the next sample
-    }
-    return v[1];
-}
 
 struct TailArgs {
     const float* src;  // contiguous

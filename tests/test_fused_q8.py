@@ -1,0 +1,147 @@
+"""The strict-q8 fused path (fused_q8.cu) against the oracle: bit-exact end to end (none / gaussian), for odd
+sizes, tile-edge cases, boundary q8 values, pitched input, multi-pass frames (fix-up kernel) and the routing
+of non-q8 frames to the generic pipeline.  Same bodies on the CPU emulator build and on the B200."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from depth_completion_mt_b200 import api, synth
+from oracle import c_oracle as co
+from oracle.make_golden import multipass_frame
+from tests.conftest import assert_bit_equal
+from tests.helpers import Backend
+
+
+def check(be, s, name, blur="gaussian", path="auto", want_path=1):
+    out, st = be.img_completion(s, blur, path=path, return_stats=True)
+    ref_st = {}
+    assert_bit_equal(out, co.img_completion(s, blur, ref_st), f"{name} blur={blur} path={path}")
+    assert int(st[0, 0]) == ref_st["loop_passes"], name
+    assert int(st[0, 1]) == ref_st["holes_before_loop"], name
+    assert int(st[0, 2]) == ref_st["holes_after_extrapolation"], name
+    if want_path is not None:
+        assert int(st[0, 3]) == want_path, f"{name}: path {st[0, 3]}"
+
+
+def body_shapes(be, shapes):
+    for i, (rows, cols, p) in enumerate(shapes):
+        s = synth.sparse_depth(90 + i, rows, cols, p, kitti_like=bool(i & 1))
+        check(be, s, f"{rows}x{cols}")
+        check(be, s, f"{rows}x{cols}", blur="none", path="fused")
+
+
+def body_boundary_values(be):
+    """q8 codes around the thresholds: 26/256 is the smallest valid depth; 25574/256 inverts to 26/256 (still
+    valid); 25575/256 inverts to 25/256 < 0.1 and becomes a hole again -> not strict q8 -> generic pipeline."""
+    rng = np.random.default_rng(3)
+    base = synth.sparse_depth_q8(5, 48, 72, 0.08)
+    for codes, strict in (((26, 27, 25574, 25573, 300), True), ((25,), False), ((25575,), False), ((25600,), False), ((1,), False)):
+        d16 = base.copy()
+        ys, xs = rng.integers(0, 48, 20), rng.integers(0, 72, 20)
+        d16[ys, xs] = rng.choice(codes, 20)
+        s = d16.astype(np.float32) / np.float32(256)
+        check(be, s, f"codes {codes}", want_path=1 if strict else 0)
+
+
+def body_routing(be):
+    s = synth.sparse_depth(6, 64, 96, 0.05)
+    check(be, s, "forced generic", path="generic", want_path=0)
+    f = synth.sparse_depth_float(6, 64, 96, 0.05)
+    check(be, f, "float frame via auto", want_path=0)
+    # DCMT_PATH_FUSED never synchronises: a frame that is not strict q8 is reported with stats[3] == -1
+    _, st = be.img_completion(f, "gaussian", path="fused", return_stats=True)
+    assert int(st[0, 3]) == -1
+    # bilateral and tiny frames are served by the generic pipeline whatever the flag says
+    out, st = be.img_completion(s, "bilateral", path="fused", return_stats=True)
+    assert int(st[0, 3]) == 0 and np.abs(out - co.img_completion(s, "bilateral")).max() <= 2e-4
+    t = synth.sparse_depth(6, 20, 24, 0.2)
+    check(be, t, "tiny frame", path="fused", want_path=0)
+    # mixed batch: only the non-q8 frame is redone
+    b = np.stack([synth.sparse_depth(7, 64, 96, 0.05), f, synth.sparse_depth(8, 64, 96, 0.02)])
+    out, st = be.img_completion(b, "gaussian", return_stats=True)
+    assert [int(v) for v in st[:, 3]] == [1, 0, 1]
+    for i in (0, 2):
+        assert_bit_equal(out[i], co.img_completion(b[i], "gaussian"), f"mixed batch frame {i}")
+    assert np.abs(out[1] - co.img_completion(b[1], "gaussian")).max() <= 1e-4
+
+
+def body_multipass(be):
+    check(be, multipass_frame(), "multipass 120x64 (fix-up kernel)")
+    check(be, multipass_frame(150, 200), "multipass 150x200", blur="none")
+    b = np.stack([synth.sparse_depth(9, 120, 64, 0.05), multipass_frame(), synth.sparse_depth(10, 120, 64, 0.05)])
+    out, st = be.img_completion(b, "gaussian", return_stats=True)
+    assert [int(v) for v in st[:, 0]] == [1, 4, 1]
+    for i in range(3):
+        assert_bit_equal(out[i], co.img_completion(b[i], "gaussian"), f"frame {i}")
+
+
+# ------------------------------------------------------------------ CPU: emulator build
+def test_emu_shapes(emu_lib):
+    body_shapes(Backend(emu_lib, "emu"), [(32, 32, 0.1), (33, 47, 0.05), (97, 171, 0.03), (100, 321, 0.02), (193, 40, 0.05), (96, 160, 0.2)])
+
+
+def test_emu_boundary_values(emu_lib):
+    body_boundary_values(Backend(emu_lib, "emu"))
+
+
+def test_emu_routing(emu_lib):
+    body_routing(Backend(emu_lib, "emu"))
+
+
+def test_emu_multipass(emu_lib):
+    body_multipass(Backend(emu_lib, "emu"))
+
+
+def test_emu_kitti_frame(emu_lib):
+    check(Backend(emu_lib, "emu"), synth.sparse_depth(1, kitti_like=True), "352x1216")
+
+
+def test_emu_pitched_input_takes_scalar_loads(emu_lib):
+    rows, cols, pitch = 40, 70, 75  # odd pitch: rows are not 16-byte aligned
+    s = synth.sparse_depth(11, rows, cols, 0.06)
+    src = np.zeros((rows, pitch), np.float32)
+    src[:, :cols] = s
+    dst = np.full((rows, pitch), -3.0, np.float32)
+    st = np.zeros((1, 4), np.int32)
+    rc = emu_lib.dcmt_img_completion_f32_host(src.ctypes.data_as(C.c_void_p), dst.ctypes.data_as(C.c_void_p), rows, cols, pitch * 4, 0, 1, 1,
+                                              0, st.ctypes.data_as(C.c_void_p))
+    assert rc == 0, emu_lib.dcmt_last_error()
+    assert int(st[0, 3]) == 1
+    assert_bit_equal(dst[:, :cols].copy(), co.img_completion(s, "gaussian"), "pitched")
+    assert (dst[:, cols:] == -3.0).all()
+
+
+# ------------------------------------------------------------------ GPU: the product
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["gpu_host", "gpu_device"])
+def test_gpu_shapes(gpu_lib, mode):
+    body_shapes(Backend(gpu_lib, mode), [(32, 32, 0.1), (33, 47, 0.05), (97, 171, 0.03), (100, 321, 0.02), (193, 40, 0.05), (96, 160, 0.2),
+                                         (352, 1216, 0.05), (375, 1242, 0.05), (512, 1760, 0.02)])
+
+
+@pytest.mark.gpu
+def test_gpu_boundary_routing_multipass(gpu_lib):
+    be = Backend(gpu_lib, "gpu_device")
+    body_boundary_values(be)
+    body_routing(be)
+    body_multipass(be)
+    body_routing(Backend(gpu_lib, "gpu_host"))
+
+
+@pytest.mark.gpu
+def test_gpu_fused_equals_generic_on_a_large_batch(gpu_lib):
+    """256 distinct frames at KITTI size, densities 1-20 %: the fused and the generic pipeline give the same bytes."""
+    import torch
+
+    dens = (0.01, 0.02, 0.05, 0.1, 0.2)
+    batch = np.stack([synth.sparse_depth(200 + f, density=dens[f % 5], kitti_like=bool(f & 1)) for f in range(256)])
+    dev = torch.from_numpy(batch).cuda()
+    a, sa = api.img_completion(dev, False, "gaussian", path="fused", return_stats=True, lib=gpu_lib)
+    b, sb = api.img_completion(dev, False, "gaussian", path="generic", return_stats=True, lib=gpu_lib)
+    assert torch.equal(a, b)
+    assert torch.equal(sa[:, :3], sb[:, :3]) and bool((sa[:, 3] == 1).all()) and bool((sb[:, 3] == 0).all())
+    for f in (0, 101, 255):
+        assert_bit_equal(a[f].cpu().numpy(), co.img_completion(batch[f], "gaussian"), f"frame {f}")
