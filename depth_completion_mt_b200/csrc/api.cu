@@ -99,6 +99,20 @@ int generic_chunk_frames(int rows, int cols, int n_frames) {
     return (int)c;
 }
 
+// frames per fused chunk: the uint16 intermediate plane of a chunk (~64 MB) stays L2 resident between the two
+// kernels, and the grids are large enough (thousands of CTAs) to hide wave quantisation and launch latency
+int fused_chunk_frames(int rows, int cols, int n_frames) {
+    static const long env = [] {
+        const char* s = getenv("DCMT_FUSED_CHUNK");
+        return s ? atol(s) : 0L;
+    }();
+    long c = env > 0 ? env : (long)((32u << 20) / ((size_t)rows * cols) + 1);
+    if (c < 1) c = 1;
+    if (c > 65535) c = 65535;
+    if (c > n_frames) c = n_frames;
+    return (int)c;
+}
+
 size_t generic_ws_bytes(int rows, int cols, int chunk, bool bilateral) {
     const size_t fpix = (size_t)rows * cols;
     size_t b = 2 * carve_bytes(fpix * chunk, sizeof(float)) + carve_bytes(chunk, sizeof(dcmt::FrameCounters));
@@ -160,7 +174,7 @@ bool fused_applies(const CompletionCall& cc) {
 }
 
 size_t completion_ws_bytes(int rows, int cols, int n_frames, bool bilateral, bool fused) {
-    const int chunk = generic_chunk_frames(rows, cols, n_frames);
+    const int chunk = fused ? fused_chunk_frames(rows, cols, n_frames) : generic_chunk_frames(rows, cols, n_frames);
     size_t b = generic_ws_bytes(rows, cols, chunk, bilateral);
     if (fused) {
         const size_t mid_pitch = ((size_t)cols + 7) / 8 * 8;
@@ -177,9 +191,9 @@ int enqueue_completion(const CompletionCall& cc, const float* sparse, const int3
                        size_t fstride, int n_frames, int32_t* stats, int32_t* redo_flags, float* stages,
                        uint32_t* stage_mask, Arena* ar, cudaStream_t st, bool* used_fused) {
     const int rows = cc.rows, cols = cc.cols;
-    const int chunk = generic_chunk_frames(rows, cols, n_frames);
     const bool bilateral = cc.blur == DCMT_BLUR_BILATERAL;
     const bool fused = fused_applies(cc) && !stages;
+    const int chunk = fused ? fused_chunk_frames(rows, cols, n_frames) : generic_chunk_frames(rows, cols, n_frames);
     if (used_fused) *used_fused = fused;
     const size_t fpix = (size_t)rows * cols;
     float* w1 = carve<float>(ar, fpix * chunk);
@@ -202,7 +216,8 @@ int enqueue_completion(const CompletionCall& cc, const float* sparse, const int3
         p.w2 = w2;
         for (int f0 = 0; f0 < n_frames; f0 += chunk) {
             const int nf = n_frames - f0 < chunk ? n_frames - f0 : chunk;
-            API_CUDA(dcmt::q8_run_front(p, sparse + (size_t)f0 * fstride, pitch, fstride, nf, st), "fused front launch");
+            API_CUDA(dcmt::q8_run_front(p, sparse + (size_t)f0 * fstride, pitch, fstride, nf, cc.flags != DCMT_PATH_FUSED, st),
+                     "fused front launch");
             API_CUDA(dcmt::q8_run_tail(p, dense + (size_t)f0 * fstride, pitch, fstride, nf, cc.blur, st), "fused tail launch");
             if (stats || redo_flags)
                 API_CUDA(dcmt::q8_write_stats(p, stats ? stats + (size_t)f0 * DCMT_STATS_STRIDE : nullptr,

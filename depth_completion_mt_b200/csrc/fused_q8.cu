@@ -63,16 +63,37 @@ __device__ __forceinline__ uint4 mask_columns(uint4 v, int gx, int cols, uint32_
     return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
+// Iterates item = threadIdx.x, threadIdx.x + QT, ... over an (nr x nq) grid as (r, q) without a division per item.
+struct Items {
+    int r, q, dr, dq, nq;
+    __device__ __forceinline__ explicit Items(int nq_) : nq(nq_) {
+        r = threadIdx.x / nq_;
+        q = threadIdx.x - r * nq_;
+        dr = QT / nq_;
+        dq = QT - dr * nq_;
+    }
+    __device__ __forceinline__ void next() {
+        q += dq;
+        r += dr;
+        if (q >= nq) { q -= nq; ++r; }
+    }
+};
+
 // Encode one input pixel (metres, float) into inverted q8 (+1).  img_completion.cpp:55-67.
 // strict q8 input: v == 0 (hole -> e = 1) or v = k/256 with 26 <= k <= 25574 (e = 25601 - k in [27, 25575]).
-__device__ __forceinline__ uint32_t encode_px(float v, int& bad) {
+template <bool kValidate>
+__device__ __forceinline__ uint32_t encode_bits(float v, int& bad) {
     const float t = fmaf(v, -256.0f, 25601.0f);  // 25601 - k, exact for q8 input
     const bool valid = v >= 0.1f;
     const float ef = valid ? t : 1.0f;
-    const float m = ef + 8388608.0f;  // 2^23: integer lands in the low mantissa bits
-    // validation: holes must be exactly 0, valid pixels integral and inside [27, 25575]
-    bad |= valid ? !(m - 8388608.0f == t && t >= 27.0f && t <= 25575.0f) : (v != 0.0f);
-    return __float_as_uint(m) & 0xffffu;
+    const float m = ef + 8388608.0f;  // 2^23: the integer lands in the low mantissa bits
+    if (kValidate)  // holes must be exactly 0; valid pixels integral (no rounding in the add) and >= 27 (<= 25575 follows)
+        bad |= valid ? !(m - 8388608.0f == t && t >= 27.0f) : (v != 0.0f);
+    return __float_as_uint(m);
+}
+template <bool kValidate>
+__device__ __forceinline__ uint32_t encode_pair(float v0, float v1, int& bad) {
+    return __byte_perm(encode_bits<kValidate>(v0, bad), encode_bits<kValidate>(v1, bad), 0x5410);
 }
 
 struct FrontArgs {
@@ -85,77 +106,87 @@ struct FrontArgs {
     FrameCounters* ctr;
     int rows, cols, th, tw;
     int vec_ok;                   // input rows are 16-byte aligned: float4 loads
+    int validate;                 // check strict q8-ness of the core pixels (DCMT_PATH_AUTO)
 };
 
 // ------------------------------------------------------------------------------------------------
 // k_q8_front.  Region = core (th x tw) + {up 8, down 9} rows, {left 8, right 16} columns (the dependency cone is
 // up 8 / down 9 / left 7 / right 9; widths are rounded to 8-pixel quads).  Every pass handles (row, quad) items,
-// reads neighbours from one shared-memory plane with 128-bit loads and writes the other plane; cells outside the
-// image always hold the identity of the operator that reads them next.
+// reads neighbours from one shared-memory plane with 128-bit loads and writes the other plane.  Planes carry FG
+// guard rows above and below so that neighbour reads need no clamping (what is read there only reaches cells
+// outside the dependency cone of the core).  Cells outside the image always hold the identity of the operator
+// that reads them next; tiles whose region lies inside the image (kBorder = false) skip those tests.
 // ------------------------------------------------------------------------------------------------
 constexpr int FU = 8, FD = 9, FLQ = 1, FRQ = 2;  // rows up/down, quads left/right
+constexpr int FG = 3;                            // guard rows
 
-template <int R, bool kIsMax>
-__device__ __forceinline__ void v_pass(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int RH, int RQ, int gy0,
-                                       int gx0, int rows, int cols, uint32_t ident_next) {
-    const int pitchw = RQ * 4;
-    for (int it = threadIdx.x; it < RH * RQ; it += QT) {
-        const int r = it / RQ, q = it - r * RQ;
-        const int gy = gy0 + r, gx = gx0 + q * 8;
+struct Tile {
+    int RH, RQ, pitchw;
+    int rlo, rhi;   // region rows inside the image: [rlo, rhi)
+    int gx0, cols;  // image column of region column 0
+};
+
+template <int R, bool kIsMax, bool kBorder>
+__device__ __forceinline__ void v_pass(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, const Tile& t,
+                                       uint32_t ident_next) {
+    for (Items i(t.RQ); i.r < t.RH; i.next()) {
+        const int off = (i.r * t.RQ + i.q) * 4;
         uint4 acc;
-        if (gy < 0 || gy >= rows) {
+        if (kBorder && (i.r < t.rlo || i.r >= t.rhi)) {
             acc = splat4(ident_next);
         } else {
-            acc = lds4(src + it * 4);
+            const uint32_t* p = src + off;
+            acc = lds4(p);
 #pragma unroll
             for (int d = 1; d <= R; ++d) {
-                const uint4 up = lds4(src + max(r - d, 0) * pitchw + q * 4);
-                const uint4 dn = lds4(src + min(r + d, RH - 1) * pitchw + q * 4);
+                const uint4 up = lds4(p - d * t.pitchw), dn = lds4(p + d * t.pitchw);
                 acc.x = pext3<kIsMax>(acc.x, up.x, dn.x);
                 acc.y = pext3<kIsMax>(acc.y, up.y, dn.y);
                 acc.z = pext3<kIsMax>(acc.z, up.z, dn.z);
                 acc.w = pext3<kIsMax>(acc.w, up.w, dn.w);
             }
-            if (gx < 0 || gx + 8 > cols) acc = mask_columns(acc, gx, cols, ident_next);
+            if (kBorder) {
+                const int gx = t.gx0 + i.q * 8;
+                if (gx < 0 || gx + 8 > t.cols) acc = mask_columns(acc, gx, t.cols, ident_next);
+            }
         }
-        sts4(dst + it * 4, acc);
+        sts4(dst + off, acc);
     }
 }
 
 // horizontal 5-window: out_j = ext(P_{j-1}, R_j, P_j, R_{j+1}, P_{j+1}),  R_j = (c_{2j-1}, c_{2j})
-template <bool kIsMax>
-__device__ __forceinline__ void h5_pass(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int RH, int RQ, int gy0,
-                                        int gx0, int rows, int cols, uint32_t ident_next) {
-    const int pitchw = RQ * 4;
-    for (int it = threadIdx.x; it < RH * RQ; it += QT) {
-        const int r = it / RQ, q = it - r * RQ;
-        const int gy = gy0 + r, gx = gx0 + q * 8;
+template <bool kIsMax, bool kBorder>
+__device__ __forceinline__ void h5_pass(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, const Tile& t,
+                                        uint32_t ident_next) {
+    for (Items i(t.RQ); i.r < t.RH; i.next()) {
+        const int off = (i.r * t.RQ + i.q) * 4;
         uint4 o;
-        if (gy < 0 || gy >= rows) {
+        if (kBorder && (i.r < t.rlo || i.r >= t.rhi)) {
             o = splat4(ident_next);
         } else {
-            const uint32_t* row = src + r * pitchw;
-            const uint4 c = lds4(row + q * 4);
-            const uint32_t wl = row[max(q * 4 - 1, 0)], wr = row[min(q * 4 + 4, pitchw - 1)];
+            const uint32_t* p = src + off;
+            const uint4 c = lds4(p);
+            const uint32_t wl = p[-1], wr = p[4];
             const uint32_t r0 = odd_pair(wl, c.x), r1 = odd_pair(c.x, c.y), r2 = odd_pair(c.y, c.z), r3 = odd_pair(c.z, c.w),
                            r4 = odd_pair(c.w, wr);
             o.x = pext3<kIsMax>(pext3<kIsMax>(wl, r0, c.x), r1, c.y);
             o.y = pext3<kIsMax>(pext3<kIsMax>(c.x, r1, c.y), r2, c.z);
             o.z = pext3<kIsMax>(pext3<kIsMax>(c.y, r2, c.z), r3, c.w);
             o.w = pext3<kIsMax>(pext3<kIsMax>(c.z, r3, c.w), r4, wr);
-            if (gx < 0 || gx + 8 > cols) o = mask_columns(o, gx, cols, ident_next);
+            if (kBorder) {
+                const int gx = t.gx0 + i.q * 8;
+                if (gx < 0 || gx + 8 > t.cols) o = mask_columns(o, gx, t.cols, ident_next);
+            }
         }
-        sts4(dst + it * 4, o);
+        sts4(dst + off, o);
     }
 }
 
 // horizontal 7-window max of one quad: out_j = max(R_{j-1}, R_j, R_{j+1}, R_{j+2}, P_{j-1}, P_j, P_{j+1})
-__device__ __forceinline__ uint4 h7_max_quad(const uint32_t* __restrict__ row, int q, int pitchw) {
-    const uint4 c = lds4(row + q * 4);
-    const int il = max(q * 4 - 2, 0), ir = min(q * 4 + 4, pitchw - 2);
-    const uint2 l = *reinterpret_cast<const uint2*>(row + il);
-    const uint2 rr = *reinterpret_cast<const uint2*>(row + ir);
-    // words w[-2..5]
+__device__ __forceinline__ uint4 h7_max_quad(const uint32_t* __restrict__ p) {
+    const uint4 c = lds4(p);
+    const uint2 l = *reinterpret_cast<const uint2*>(p - 2);
+    const uint2 rr = *reinterpret_cast<const uint2*>(p + 4);
     const uint32_t wm2 = l.x, wm1 = l.y, w0 = c.x, w1 = c.y, w2 = c.z, w3 = c.w, w4 = rr.x, w5 = rr.y;
     const uint32_t rm1 = odd_pair(wm2, wm1), r0 = odd_pair(wm1, w0), r1 = odd_pair(w0, w1), r2 = odd_pair(w1, w2),
                    r3 = odd_pair(w2, w3), r4 = odd_pair(w3, w4), r5 = odd_pair(w4, w5);
@@ -174,122 +205,159 @@ __device__ __forceinline__ uint32_t fill_holes(uint32_t d, uint32_t t) {
     return __vadd2(pmin(__vadd2(t, k), __vadd2(d, k)), SPLAT16(27));
 }
 
-__global__ void __launch_bounds__(QT) k_q8_front(FrontArgs a) {
-    DCMT_DYN_SMEM(uint32_t, smem);
-    const int th = a.th, tw = a.tw, rows = a.rows, cols = a.cols;
-    const int RH = th + FU + FD, RQ = tw / 8 + FLQ + FRQ, pitchw = RQ * 4;
-    uint32_t* A = smem;
-    uint32_t* B = smem + RH * pitchw;
-    const int frame = blockIdx.z;  // slot == frame offset inside the chunk
-    const int y0 = blockIdx.y * th, x0 = blockIdx.x * tw;
-    const int gy0 = y0 - FU, gx0 = x0 - FLQ * 8;
-    const float* in = a.in + (size_t)frame * a.in_fstride;
-    const bool interior = gy0 >= 0 && gy0 + RH <= rows && gx0 >= 0 && gx0 + RQ * 8 <= cols;
-
-    // ---- pass 0: load, validate, invert, encode (:55-67)
-    int bad = 0;
-    if (interior && a.vec_ok) {
-        for (int it = threadIdx.x; it < RH * RQ; it += QT) {
-            const int r = it / RQ, q = it - r * RQ;
-            const float4* p = reinterpret_cast<const float4*>(in + (size_t)(gy0 + r) * a.in_pitch + gx0 + q * 8);
-            const float4 f0 = __ldg(p), f1 = __ldg(p + 1);
-            uint4 o;
-            o.x = encode_px(f0.x, bad) | (encode_px(f0.y, bad) << 16);
-            o.y = encode_px(f0.z, bad) | (encode_px(f0.w, bad) << 16);
-            o.z = encode_px(f1.x, bad) | (encode_px(f1.y, bad) << 16);
-            o.w = encode_px(f1.z, bad) | (encode_px(f1.w, bad) << 16);
-            sts4(A + it * 4, o);
-        }
-    } else {
-        for (int it = threadIdx.x; it < RH * RQ; it += QT) {
-            const int r = it / RQ, q = it - r * RQ;
-            const int gy = gy0 + r, gx = gx0 + q * 8;
-            uint32_t e[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int x = gx + j;
-                e[j] = 0u;  // outside the image: absent
-                if (gy >= 0 && gy < rows && x >= 0 && x < cols) e[j] = encode_px(__ldg(in + (size_t)gy * a.in_pitch + x), bad);
-            }
-            sts4(A + it * 4, make_uint4(e[0] | (e[1] << 16), e[2] | (e[3] << 16), e[4] | (e[5] << 16), e[6] | (e[7] << 16)));
-        }
-    }
-    if (__syncthreads_or(bad)) {  // not strict q8: this frame is redone by the generic pipeline
-        if (threadIdx.x == 0) a.ctr[frame].needs_generic = 1;
-        return;
-    }
-
+template <bool kBorder>
+__device__ __forceinline__ void front_passes(uint32_t* A, uint32_t* B, const Tile& t) {
     // ---- pass 1: 2-tap dilate (:71-80)  out(y,x) = max(in(y-1,x+1), in(y+2,x+2)), absent taps = -FLT_MAX (e = 0)
-    for (int it = threadIdx.x; it < RH * RQ; it += QT) {
-        const int r = it / RQ, q = it - r * RQ;
-        const int gy = gy0 + r, gx = gx0 + q * 8;
-        uint4 o = splat4(kAbsMax);
-        if (gy >= 0 && gy < rows) {
-            const uint32_t* ra = A + max(r - 1, 0) * pitchw;
-            const uint32_t* rb = A + min(r + 2, RH - 1) * pitchw;
-            const uint4 ca = lds4(ra + q * 4), cb = lds4(rb + q * 4);
-            const int inext = min(q * 4 + 4, pitchw - 1);
-            const uint32_t na = ra[inext], nb = rb[inext];
+    for (Items i(t.RQ); i.r < t.RH; i.next()) {
+        const int off = (i.r * t.RQ + i.q) * 4;
+        uint4 o;
+        if (kBorder && (i.r < t.rlo || i.r >= t.rhi)) {
+            o = splat4(kAbsMax);
+        } else {
+            const uint32_t* pa = A + off - t.pitchw;      // row y-1
+            const uint32_t* pb = A + off + 2 * t.pitchw;  // row y+2
+            const uint4 ca = lds4(pa), cb = lds4(pb);
+            const uint32_t na = pa[4], nb = pb[4];
             // tap 1: pixels (x+1, x+2) of row y-1; tap 2: pixels (x+2, x+3) of row y+2
             o.x = pmax(odd_pair(ca.x, ca.y), cb.y);
             o.y = pmax(odd_pair(ca.y, ca.z), cb.z);
             o.z = pmax(odd_pair(ca.z, ca.w), cb.w);
             o.w = pmax(odd_pair(ca.w, na), nb);
-            if (gx < 0 || gx + 8 > cols) o = mask_columns(o, gx, cols, kAbsMax);
+            if (kBorder) {
+                const int gx = t.gx0 + i.q * 8;
+                if (gx < 0 || gx + 8 > t.cols) o = mask_columns(o, gx, t.cols, kAbsMax);
+            }
         }
-        sts4(B + it * 4, o);
+        sts4(B + off, o);
     }
     __syncthreads();
     // ---- passes 2-5: close5 (:84-85) = dilate5 (V, H) then erode5 (H, V)
-    v_pass<2, true>(B, A, RH, RQ, gy0, gx0, rows, cols, kAbsMax);
+    v_pass<2, true, kBorder>(B, A, t, kAbsMax);
     __syncthreads();
-    h5_pass<true>(A, B, RH, RQ, gy0, gx0, rows, cols, kAbsMin);
+    h5_pass<true, kBorder>(A, B, t, kAbsMin);
     __syncthreads();
-    h5_pass<false>(B, A, RH, RQ, gy0, gx0, rows, cols, kAbsMin);
+    h5_pass<false, kBorder>(B, A, t, kAbsMin);
     __syncthreads();
-    v_pass<2, false>(A, B, RH, RQ, gy0, gx0, rows, cols, kAbsMax);  // B = D, the closed image
+    v_pass<2, false, kBorder>(A, B, t, kAbsMax);  // B = D, the closed image
     __syncthreads();
     // ---- pass 6: vertical half of dilate7 (:88-90)
-    v_pass<3, true>(B, A, RH, RQ, gy0, gx0, rows, cols, kAbsMax);
+    v_pass<3, true, kBorder>(B, A, t, kAbsMax);
     __syncthreads();
+}
+
+template <bool kValidate>
+__device__ __forceinline__ void front_load(const FrontArgs& a, const float* in, uint32_t* A, const Tile& t, int gy0, int& bad) {
+    const int rows = a.rows, cols = a.cols;
+    for (Items i(t.RQ); i.r < t.RH; i.next()) {
+        const int gy = gy0 + i.r, gx = t.gx0 + i.q * 8;
+        // only the core is validated: every pixel is in the core of exactly one tile
+        const bool core = kValidate && i.r >= FU && i.r < FU + a.th && i.q >= FLQ && i.q < t.RQ - FRQ;
+        uint4 o = splat4(kAbsMax);  // outside the image: absent
+        int b = 0;
+        if (gy >= 0 && gy < rows) {
+            const float* p = in + (size_t)gy * a.in_pitch + gx;
+            if (gx >= 0 && gx + 8 <= cols && a.vec_ok) {
+                const float4 f0 = __ldg(reinterpret_cast<const float4*>(p)), f1 = __ldg(reinterpret_cast<const float4*>(p) + 1);
+                if (core) {
+                    o.x = encode_pair<true>(f0.x, f0.y, b); o.y = encode_pair<true>(f0.z, f0.w, b);
+                    o.z = encode_pair<true>(f1.x, f1.y, b); o.w = encode_pair<true>(f1.z, f1.w, b);
+                } else {
+                    o.x = encode_pair<false>(f0.x, f0.y, b); o.y = encode_pair<false>(f0.z, f0.w, b);
+                    o.z = encode_pair<false>(f1.x, f1.y, b); o.w = encode_pair<false>(f1.z, f1.w, b);
+                }
+            } else {
+                uint32_t e[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int x = gx + j;
+                    e[j] = 0u;
+                    if (x >= 0 && x < cols) {
+                        int bb = 0;
+                        e[j] = encode_bits<true>(__ldg(p + j), bb) & 0xffffu;
+                        if (core) b |= bb;
+                    }
+                }
+                o = make_uint4(e[0] | (e[1] << 16), e[2] | (e[3] << 16), e[4] | (e[5] << 16), e[6] | (e[7] << 16));
+            }
+        }
+        bad |= b;
+        sts4(A + (i.r * t.RQ + i.q) * 4, o);
+    }
+}
+
+__global__ void __launch_bounds__(QT) k_q8_front(FrontArgs a) {
+    DCMT_DYN_SMEM(uint32_t, smem);
+    const int th = a.th, tw = a.tw, rows = a.rows, cols = a.cols;
+    Tile t;
+    t.RH = th + FU + FD;
+    t.RQ = tw / 8 + FLQ + FRQ;
+    t.pitchw = t.RQ * 4;
+    uint32_t* A = smem + FG * t.pitchw;
+    uint32_t* B = A + (t.RH + 2 * FG) * t.pitchw;
+    const int frame = blockIdx.z;  // slot == frame offset inside the chunk
+    const int y0 = blockIdx.y * th, x0 = blockIdx.x * tw;
+    const int gy0 = y0 - FU;
+    t.gx0 = x0 - FLQ * 8;
+    t.cols = cols;
+    t.rlo = max(0, -gy0);
+    t.rhi = min(t.RH, rows - gy0);
+    const float* in = a.in + (size_t)frame * a.in_fstride;
+    const bool border = gy0 < 0 || gy0 + t.RH > rows || t.gx0 < 0 || t.gx0 + t.RQ * 8 > cols;
+
+    // ---- pass 0: load, validate, invert, encode (:55-67)
+    int bad = 0;
+    if (a.validate) front_load<true>(a, in, A, t, gy0, bad);
+    else front_load<false>(a, in, A, t, gy0, bad);
+    if (__syncthreads_or(bad)) {  // not strict q8: this frame is redone by the generic pipeline
+        if (threadIdx.x == 0) a.ctr[frame].needs_generic = 1;
+        return;
+    }
+    if (border) front_passes<true>(A, B, t);
+    else front_passes<false>(A, B, t);
+
     // ---- pass 7: horizontal half of dilate7, hole fill (:92-100), store the core
     const int CQ = tw / 8;
     uint16_t* mid = a.mid + (size_t)frame * a.mid_fstride;
-    for (int it = threadIdx.x; it < th * CQ; it += QT) {
-        const int cy = it / CQ, cq = it - cy * CQ;
-        const int r = cy + FU, q = cq + FLQ;
-        const int gy = y0 + cy, gx = x0 + cq * 8;
+    for (Items i(CQ); i.r < th; i.next()) {
+        const int gy = y0 + i.r, gx = x0 + i.q * 8;
         if (gy >= rows || gx >= cols) continue;
-        const uint4 t = h7_max_quad(A + r * pitchw, q, pitchw);
-        uint4 d = lds4(B + r * pitchw + q * 4);
-        d.x = fill_holes(d.x, t.x);
-        d.y = fill_holes(d.y, t.y);
-        d.z = fill_holes(d.z, t.z);
-        d.w = fill_holes(d.w, t.w);
-        sts4(B + r * pitchw + q * 4, d);  // only this thread reads this quad of B in this pass
+        const int off = ((i.r + FU) * t.RQ + i.q + FLQ) * 4;
+        const uint4 tt = h7_max_quad(A + off);
+        uint4 d = lds4(B + off);
+        d.x = fill_holes(d.x, tt.x);
+        d.y = fill_holes(d.y, tt.y);
+        d.z = fill_holes(d.z, tt.z);
+        d.w = fill_holes(d.w, tt.w);
+        sts4(B + off, d);  // only this thread touches this quad of B in this pass
         *reinterpret_cast<uint4*>(mid + (size_t)gy * a.mid_pitch + gx) = d;
     }
     __syncthreads();
-    // ---- per-column first / last valid row inside this tile (feeds :103-129), merged across tiles by atomics
+    // ---- per-column first / last valid row inside this tile (feeds :103-129), merged across tiles by atomics.
+    //      Two threads per column: one searches from the top, one from the bottom.
     const uint16_t* Bh = reinterpret_cast<const uint16_t*>(B);
-    for (int c = threadIdx.x; c < tw; c += QT) {
-        const int gx = x0 + c;
+    const int hrows = min(th, rows - y0);
+    for (int c = threadIdx.x; c < 2 * tw; c += QT) {
+        const int col = c >> 1, from_bottom = c & 1;
+        const int gx = x0 + col;
         if (gx >= cols) continue;
-        const int hrows = min(th, rows - y0);
-        const int col = (FLQ * 8 + c);
-        int first = -1, last = -1;
-        uint32_t ef = 0, el = 0;
-        for (int cy = 0; cy < hrows; ++cy) {
-            const uint32_t e = Bh[(size_t)(cy + FU) * pitchw * 2 + col];
-            if (e >= E_VALID_MIN) { first = cy; ef = e; break; }
+        const uint16_t* p = Bh + (size_t)FU * t.pitchw * 2 + FLQ * 8 + col;
+        if (!from_bottom) {
+            for (int cy = 0; cy < hrows; ++cy) {
+                const uint32_t e = p[(size_t)cy * t.pitchw * 2];
+                if (e >= E_VALID_MIN) {
+                    atomicMin(a.col_first + (size_t)frame * a.mid_pitch + gx, ((uint32_t)(y0 + cy) << 16) | e);
+                    break;
+                }
+            }
+        } else {
+            for (int cy = hrows - 1; cy >= 0; --cy) {
+                const uint32_t e = p[(size_t)cy * t.pitchw * 2];
+                if (e >= E_VALID_MIN) {
+                    atomicMax(a.col_last + (size_t)frame * a.mid_pitch + gx, ((uint32_t)(y0 + cy) << 16) | e);
+                    break;
+                }
+            }
         }
-        if (first < 0) continue;
-        for (int cy = hrows - 1; cy >= 0; --cy) {
-            const uint32_t e = Bh[(size_t)(cy + FU) * pitchw * 2 + col];
-            if (e >= E_VALID_MIN) { last = cy; el = e; break; }
-        }
-        atomicMin(a.col_first + (size_t)frame * a.mid_pitch + gx, ((uint32_t)(y0 + first) << 16) | ef);
-        atomicMax(a.col_last + (size_t)frame * a.mid_pitch + gx, ((uint32_t)(y0 + last) << 16) | el);
     }
 }
 
@@ -306,14 +374,15 @@ __global__ void k_q8_decode(const uint16_t* __restrict__ mid, size_t mid_pitch, 
     out[(size_t)y * cols + x] = e == 0 ? -FLT_MAX : (float)(e - 1) * (1.0f / 256.0f);
 }
 
-
 // ------------------------------------------------------------------------------------------------
 // k_q8_tail.  Region = core + 19 rows up/down and 24 columns (3 quads) left/right: 15 (one effective 31x31
 // fill) + 2 (median) + 2 (Gaussian) = 19.  Two shared-memory planes: A = image, B = vertical 16-row maxima,
-// later the median image.
+// later the median image; B carries 8 guard rows below for the doubling steps.
 // ------------------------------------------------------------------------------------------------
-constexpr int TV = 19, TQ = 3;  // rows up/down, quads left/right
-constexpr int KIPT = 8;         // register-resident quads per thread in the in-place doubling steps
+constexpr int TV = 19, TQ = 3;   // rows up/down, quads left/right
+constexpr int TG = 8;            // guard rows below plane B
+constexpr int KIPT = 8;          // register-resident quads per thread in the in-place doubling steps
+constexpr int kListCap = 3072;   // hole words kept for the lazy horizontal fill; more than that: all words are processed
 
 struct TailArgs {
     const uint16_t* mid;
@@ -323,7 +392,7 @@ struct TailArgs {
     FrameCounters* ctr;
     float* out;
     size_t out_pitch, out_fstride;
-    int rows, cols, th, tw, blur, vec2_ok;
+    int rows, cols, th, tw, blur, vec_ok;
 };
 
 struct PackedOps {
@@ -355,13 +424,25 @@ __device__ __forceinline__ float finish_px(uint32_t d16) {
     return fmaf(__uint_as_float(0x4b000000u + o), 1.0f / 65536.0f, -128.0f);  // (2^23 + o) / 2^16 - 128
 }
 
-__global__ void __launch_bounds__(QT) k_q8_tail(TailArgs a) {
+// 31-wide horizontal max of the vertical maxima for word w of row r (B holds 16-row maxima: rows r-15..r and r..r+15)
+__device__ __forceinline__ uint32_t hmax31(const uint32_t* __restrict__ B, int pitchw, int r, int w) {
+    const uint32_t* b0 = B + (r - 15) * pitchw + w;
+    const uint32_t* b1 = B + r * pitchw + w;
+    uint32_t m = 0u;
+#pragma unroll
+    for (int j = -7; j <= 7; ++j) m = pmax3(m, b0[j], b1[j]);
+    // m.lo / m.hi hold the maxima over the even / odd columns of words w-7 .. w+7; both output lanes need both
+    // (lane swap), plus column 2w-15 for the low lane only and column 2w+16 for the high lane only
+    return pmax3(m, __byte_perm(m, m, 0x1032), odd_pair(pmax(b0[-8], b1[-8]), pmax(b0[8], b1[8])));
+}
+
+__global__ void __launch_bounds__(QT, 2) k_q8_tail(TailArgs a) {
     DCMT_DYN_SMEM(uint32_t, smem);
     const int th = a.th, tw = a.tw, rows = a.rows, cols = a.cols;
     const int RH = th + 2 * TV, RQ = tw / 8 + 2 * TQ, pitchw = RQ * 4;
     uint32_t* A = smem;
     uint32_t* B = smem + RH * pitchw;
-    uint16_t* list = reinterpret_cast<uint16_t*>(B + RH * pitchw);
+    uint16_t* list = reinterpret_cast<uint16_t*>(B + (RH + TG) * pitchw);
     uint16_t* Ah = reinterpret_cast<uint16_t*>(A);
     uint16_t* Bh = reinterpret_cast<uint16_t*>(B);
     __shared__ int s_count, s_remaining, s_holes_core, s_left_core;
@@ -374,64 +455,66 @@ __global__ void __launch_bounds__(QT) k_q8_tail(TailArgs a) {
     if (threadIdx.x == 0) { s_count = 0; s_remaining = 0; s_holes_core = 0; s_left_core = 0; }
 
     // ---- load the A4 plane (outside the image: absent)
-    for (int it = threadIdx.x; it < RH * RQ; it += QT) {
-        const int r = it / RQ, q = it - r * RQ;
-        const int gy = gy0 + r, gx = gx0 + q * 8;
-        uint4 v = splat4(kAbsMax);
-        if (gy >= 0 && gy < rows && gx >= 0 && gx < cols) {
-            v = __ldg(reinterpret_cast<const uint4*>(mid + (size_t)gy * a.mid_pitch + gx));
-            if (gx + 8 > cols) v = mask_columns(v, gx, cols, kAbsMax);
-        }
-        sts4(A + it * 4, v);
-    }
-    __syncthreads();
-    // ---- A5 column extrapolation (:103-129) from the per-column keys: rows >= last <- value(last), then
-    //      rows <= first <- value(first) (second write wins); empty column <- 100
-    {
-        const int RW = RQ * 8, chunks = (RH + 15) / 16;
-        for (int it = threadIdx.x; it < RW * chunks; it += QT) {
-            const int ch = it / RW, c = it - ch * RW;
-            const int gx = gx0 + c;
-            if (gx < 0 || gx >= cols) continue;
-            const uint32_t kf = __ldg(a.col_first + (size_t)slot * a.mid_pitch + gx);
-            const uint32_t kl = __ldg(a.col_last + (size_t)slot * a.mid_pitch + gx);
-            const bool empty = kf == 0xffffffffu;
-            const int first = empty ? rows - 1 : (int)(kf >> 16), last = empty ? 0 : (int)(kl >> 16);
-            const uint16_t nv = empty ? (uint16_t)E_HUNDRED : (uint16_t)(kf & 0xffffu);
-            const uint16_t mv = empty ? (uint16_t)E_HUNDRED : (uint16_t)(kl & 0xffffu);
-            const int r_lo = ch * 16, r_hi = min(RH, r_lo + 16);
-            for (int r = r_lo; r < r_hi; ++r) {
-                const int gy = gy0 + r;
-                if (gy < 0 || gy >= rows) continue;
-                if (gy <= first) Ah[(size_t)r * pitchw * 2 + c] = nv;
-                else if (gy >= last) Ah[(size_t)r * pitchw * 2 + c] = mv;
+    if (!border) {
+        for (Items i(RQ); i.r < RH; i.next())
+            sts4(A + (i.r * RQ + i.q) * 4,
+                 __ldg(reinterpret_cast<const uint4*>(mid + (size_t)(gy0 + i.r) * a.mid_pitch + gx0 + i.q * 8)));
+    } else {
+        for (Items i(RQ); i.r < RH; i.next()) {
+            const int gy = gy0 + i.r, gx = gx0 + i.q * 8;
+            uint4 v = splat4(kAbsMax);
+            if (gy >= 0 && gy < rows && gx >= 0 && gx < cols) {
+                v = __ldg(reinterpret_cast<const uint4*>(mid + (size_t)gy * a.mid_pitch + gx));
+                if (gx + 8 > cols) v = mask_columns(v, gx, cols, kAbsMax);
             }
+            sts4(A + (i.r * RQ + i.q) * 4, v);
         }
     }
     __syncthreads();
-    // ---- A6 vertical part: B(r) = max of A over rows r .. r+15 by log-doubling; steps 2..4 run in place with
-    //      the thread's quads held in registers
-    for (int it = threadIdx.x; it < RH * RQ; it += QT) {
-        const int r = it / RQ;
-        const uint4 x = lds4(A + it * 4), y = lds4(A + (min(r + 1, RH - 1) * RQ + (it - r * RQ)) * 4);
-        sts4(B + it * 4, make_uint4(pmax(x.x, y.x), pmax(x.y, y.y), pmax(x.z, y.z), pmax(x.w, y.w)));
+    // ---- A5 column extrapolation (:103-129) from the per-column keys: rows >= last <- value(last), rows <= first
+    //      <- value(first) (the second write wins); empty column <- 100.  Two threads per column, one per zone.
+    for (int it = threadIdx.x; it < 2 * RQ * 8; it += QT) {
+        const int c = it >> 1, bottom = it & 1;
+        const int gx = gx0 + c;
+        if (gx < 0 || gx >= cols) continue;
+        const uint32_t kf = __ldg(a.col_first + (size_t)slot * a.mid_pitch + gx);
+        const uint32_t kl = __ldg(a.col_last + (size_t)slot * a.mid_pitch + gx);
+        const bool empty = kf == 0xffffffffu;
+        const int first = empty ? rows - 1 : (int)(kf >> 16), last = empty ? 0 : (int)(kl >> 16);
+        uint16_t* p = Ah + c;
+        if (!bottom) {  // rows <= first
+            const uint16_t nv = empty ? (uint16_t)E_HUNDRED : (uint16_t)(kf & 0xffffu);
+            const int r1 = min(RH - 1, first - gy0);
+            for (int r = max(0, -gy0); r <= r1; ++r) p[(size_t)r * pitchw * 2] = nv;
+        } else {  // rows >= last that are not <= first
+            const uint16_t mv = empty ? (uint16_t)E_HUNDRED : (uint16_t)(kl & 0xffffu);
+            const int r1 = min(RH - 1, rows - 1 - gy0);
+            for (int r = max(max(0, -gy0), max(last, first + 1) - gy0); r <= r1; ++r) p[(size_t)r * pitchw * 2] = mv;
+        }
     }
     __syncthreads();
+    // ---- A6 vertical part: B(r) = max of A over rows r .. r+15 by log-doubling.  Step 1 goes from A to B, steps
+    //      2..4 run in place with the thread's quads held in registers (reads below the plane hit guard rows
+    //      whose content only reaches rows outside the dependency cone).
     {
         uint4 v[KIPT];
 #pragma unroll
         for (int k = 0; k < KIPT; ++k) {
             const int it = threadIdx.x + k * QT;
-            if (it < RH * RQ) v[k] = lds4(B + it * 4);
+            if (it < RH * RQ) {
+                const uint4 x = lds4(A + it * 4), y = lds4(A + (it + RQ < RH * RQ ? it + RQ : it) * 4);  // last row: itself
+                v[k] = make_uint4(pmax(x.x, y.x), pmax(x.y, y.y), pmax(x.z, y.z), pmax(x.w, y.w));
+                sts4(B + it * 4, v[k]);
+            }
         }
+        __syncthreads();
 #pragma unroll
         for (int step = 2; step <= 8; step *= 2) {
 #pragma unroll
             for (int k = 0; k < KIPT; ++k) {
                 const int it = threadIdx.x + k * QT;
                 if (it < RH * RQ) {
-                    const int r = it / RQ, q = it - r * RQ;
-                    const uint4 y = lds4(B + (min(r + step, RH - 1) * RQ + q) * 4);
+                    const uint4 y = lds4(B + (it + step * RQ) * 4);
                     v[k] = make_uint4(pmax(v[k].x, y.x), pmax(v[k].y, y.y), pmax(v[k].z, y.z), pmax(v[k].w, y.w));
                 }
             }
@@ -444,50 +527,63 @@ __global__ void __launch_bounds__(QT) k_q8_tail(TailArgs a) {
             __syncthreads();
         }
     }
-    // ---- A6 horizontal part on hole words only: ballot/popc compaction of the words that hold a hole, then
-    //      a 31-wide max of the vertical maxima for those words (:131-144)
-    const int SH = th + 8, SW = tw / 2 + 4;          // scan region: core +- 4 rows, +- 2 words
-    const int sr0 = TV - 4, sw0 = TQ * 4 - 2;
+    // ---- A6 horizontal part on hole words only (:131-144): scan quads for lanes == 1, ballot/popc-compact the
+    //      words that hold a hole into a list, then a 31-wide max of the vertical maxima for those words.
+    //      Scan region: rows core +- 4, quads covering columns core +- 8 (a superset of the +- 4 the median needs).
+    const int SH = th + 8, SQ = tw / 8 + 2;
+    const int sr0 = TV - 4, sq0 = TQ - 1;
     int holes_core = 0;
-    for (int base = 0; base < SH * SW; base += QT) {
-        const int idx = base + threadIdx.x;
-        bool has = false;
-        int widx = 0;
-        if (idx < SH * SW) {
-            const int sr = idx / SW, sw = idx - sr * SW;
-            widx = (sr0 + sr) * pitchw + sw0 + sw;
-            const uint32_t hm = hole_mask(A[widx]);
-            has = hm != 0u;
-            if (has && sr >= 4 && sr < 4 + th && sw >= 2 && sw < 2 + tw / 2) holes_core += __popc(hm) >> 4;
+    {
+        const int n = SH * SQ;
+        Items i(SQ);
+        for (int base = 0; base < n; base += QT, i.next()) {
+            const bool active = base + (int)threadIdx.x < n;
+            uint32_t w[4] = {2u, 2u, 2u, 2u};
+            int wbase = 0;
+            bool cand = false;
+            if (active) {
+                wbase = ((sr0 + i.r) * RQ + sq0 + i.q) * 4;
+                const uint4 v = lds4(A + wbase);
+                w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+                // some lane <= 1 (a hole, or absent outside the image)?
+                cand = pmin(pmin(pmin(v.x, v.y), pmin(v.z, v.w)), SPLAT16(2)) != SPLAT16(2);
+            }
+            if (!__any_sync(0xffffffffu, cand)) continue;
+            const bool core_row = i.r >= 4 && i.r < 4 + th;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t hm = cand ? hole_mask(w[j]) : 0u;
+                const bool has = hm != 0u;
+                if (has && core_row && i.q >= 1 && i.q < SQ - 1) holes_core += __popc(hm) >> 4;
+                const unsigned bal = __ballot_sync(0xffffffffu, has);
+                if (bal == 0u) continue;
+                int pos = 0;
+                if ((threadIdx.x & 31) == 0) pos = atomicAdd(&s_count, __popc(bal));
+                pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(bal & ((1u << (threadIdx.x & 31)) - 1u));
+                if (has && pos < kListCap) list[pos] = (uint16_t)(wbase + j);
+            }
         }
-        const unsigned bal = __ballot_sync(0xffffffffu, has);
-        int basepos = 0;
-        if ((threadIdx.x & 31) == 0 && bal) basepos = atomicAdd(&s_count, __popc(bal));
-        basepos = __shfl_sync(0xffffffffu, basepos, 0);
-        if (has) list[basepos + __popc(bal & ((1u << (threadIdx.x & 31)) - 1u))] = (uint16_t)widx;
     }
     __syncthreads();
     int left_core = 0, left_any = 0;
-    for (int k = threadIdx.x; k < s_count; k += QT) {
-        const int widx = list[k];
-        const int r = widx / pitchw, w = widx - r * pitchw;
-        const uint32_t* b0 = B + max(r - 15, 0) * pitchw;  // rows r-15 .. r
-        const uint32_t* b1 = B + r * pitchw;               // rows r .. r+15
-        uint32_t m = 0u;
-#pragma unroll
-        for (int j = -7; j <= 7; ++j) m = pmax3(m, b0[w + j], b1[w + j]);
-        // m.lo / m.hi hold the maxima over the even / odd columns of words w-7 .. w+7; both output lanes need
-        // both (lane swap), plus column 2w-15 for the low lane only and column 2w+16 for the high lane only
-        m = pmax3(m, __byte_perm(m, m, 0x1032), odd_pair(pmax(b0[w - 8], b1[w - 8]), pmax(b0[w + 8], b1[w + 8])));
+    const int n_holes = s_count;
+    auto fill_word = [&](int widx) {
         const uint32_t d = A[widx], hm = hole_mask(d);
-        const uint32_t nd = (m & hm) | (d & ~hm);
+        if (hm == 0u) return;
+        const int r = widx / pitchw, w = widx - r * pitchw;
+        const uint32_t nd = (hmax31(B, pitchw, r, w) & hm) | (d & ~hm);
         A[widx] = nd;
         const uint32_t still = hole_mask(nd);
         if (still) {
             left_any = 1;
-            const int sr = r - sr0, sw = w - sw0;
-            if (sr >= 4 && sr < 4 + th && sw >= 2 && sw < 2 + tw / 2) left_core += __popc(still) >> 4;
+            const int sr = r - sr0, sw = w - TQ * 4;
+            if (sr >= 4 && sr < 4 + th && sw >= 0 && sw < tw / 2) left_core += __popc(still) >> 4;
         }
+    };
+    if (n_holes <= kListCap) {
+        for (int k = threadIdx.x; k < n_holes; k += QT) fill_word(list[k]);
+    } else {  // very sparse input: most words hold holes, process the whole scan region
+        for (Items i(SQ * 4); i.r < SH; i.next()) fill_word((sr0 + i.r) * pitchw + sq0 * 4 + i.q);
     }
     if (holes_core) atomicAdd(&s_holes_core, holes_core);
     if (left_core) atomicAdd(&s_left_core, left_core);
@@ -499,10 +595,12 @@ __global__ void __launch_bounds__(QT) k_q8_tail(TailArgs a) {
         if (s_remaining) a.ctr[slot].holes_remaining = 1;  // a second pass is needed: k_q8_fixup redoes the frame
     }
     // ---- BORDER_REPLICATE for the median (:170): copy the nearest image pixel into cells outside the image
+    //      (rows / columns core +- 4)
     if (border) {
-        for (int it = threadIdx.x; it < SH * (tw + 8); it += QT) {
-            const int sr = it / (tw + 8), sc = it - sr * (tw + 8);
-            const int r = sr0 + sr, c = TQ * 8 - 4 + sc;
+        const int c_lo = TQ * 8 - 4, c_n = tw + 8;
+        for (int it = threadIdx.x; it < SH * c_n; it += QT) {
+            const int sr = it / c_n, sc = it - sr * c_n;
+            const int r = sr0 + sr, c = c_lo + sc;
             const int gy = gy0 + r, gx = gx0 + c;
             if (gy >= 0 && gy < rows && gx >= 0 && gx < cols) continue;
             const int cr = clampi(gy, 0, rows - 1) - gy0, cc = clampi(gx, 0, cols - 1) - gx0;
@@ -514,14 +612,13 @@ __global__ void __launch_bounds__(QT) k_q8_tail(TailArgs a) {
     {
         const int MH = th + 4, MI = tw / 4 + 1;  // rows core +- 2; items of two words covering core +- 1 word
         const int mr0 = TV - 2, mw0 = TQ * 4 - 1;
-        for (int it = threadIdx.x; it < MH * MI; it += QT) {
-            const int mr = it / MI, mi = it - mr * MI;
-            const int r = mr0 + mr, w = mw0 + 2 * mi;  // output words w, w+1; columns w-1 .. w+2
+        for (Items i(MI); i.r < MH; i.next()) {
+            const int r = mr0 + i.r, w = mw0 + 2 * i.q;  // output words w, w+1; columns w-1 .. w+2
             uint32_t col[4][5];
+            const uint32_t* p = A + (r - 2) * pitchw + (w - 1);
 #pragma unroll
             for (int k = 0; k < 5; ++k) {
-                const uint32_t* row = A + (r - 2 + k) * pitchw + (w - 1);
-                const uint2 p0 = *reinterpret_cast<const uint2*>(row), p1 = *reinterpret_cast<const uint2*>(row + 2);
+                const uint2 p0 = *reinterpret_cast<const uint2*>(p + k * pitchw), p1 = *reinterpret_cast<const uint2*>(p + k * pitchw + 2);
                 col[0][k] = p0.x; col[1][k] = p0.y; col[2][k] = p1.x; col[3][k] = p1.y;
             }
 #pragma unroll
@@ -548,73 +645,63 @@ __global__ void __launch_bounds__(QT) k_q8_tail(TailArgs a) {
     }
     __syncthreads();
     float* out = a.out + (size_t)slot * a.out_fstride;
-    if (a.blur == 0) {
-        // no blur: final inversion only (:191-202)
-        for (int it = threadIdx.x; it < th * (tw / 2); it += QT) {
-            const int cy = it / (tw / 2), cw = it - cy * (tw / 2);
-            const int gy = y0 + cy, gx = x0 + 2 * cw;
-            if (gy >= rows || gx >= cols) continue;
-            const uint32_t m = B[(TV + cy) * pitchw + TQ * 4 + cw];
-            const float f0 = finish_px(((m & 0xffffu) - 1u) << 8), f1 = finish_px(((m >> 16) - 1u) << 8);
-            float* o = out + (size_t)gy * a.out_pitch + gx;
-            if (gx + 1 < cols && a.vec2_ok) *reinterpret_cast<float2*>(o) = make_float2(f0, f1);
-            else { o[0] = f0; if (gx + 1 < cols) o[1] = f1; }
-        }
-        return;
-    }
     // ---- BORDER_REFLECT_101 for the Gaussian (:179): mirror the median image into the 2 cells beyond each edge
-    if (border) {
-        for (int it = threadIdx.x; it < (th + 4) * (tw + 4); it += QT) {
-            const int sr = it / (tw + 4), sc = it - sr * (tw + 4);
-            const int r = TV - 2 + sr, c = TQ * 8 - 2 + sc;
+    if (border && a.blur == 1) {
+        const int c_lo = TQ * 8 - 2, c_n = tw + 4;
+        for (int it = threadIdx.x; it < (th + 4) * c_n; it += QT) {
+            const int sr = it / c_n, sc = it - sr * c_n;
+            const int r = TV - 2 + sr, c = c_lo + sc;
             const int gy = gy0 + r, gx = gx0 + c;
             if (gy >= 0 && gy < rows && gx >= 0 && gx < cols) continue;
             if (gy < -2 || gy > rows + 1 || gx < -2 || gx > cols + 1) continue;
             const int cr = reflect101(gy, rows) - gy0, cc = reflect101(gx, cols) - gx0;
-            if (cr >= TV - 2 && cr < TV + th + 2 && cc >= TQ * 8 - 2 && cc < TQ * 8 + tw + 2)
+            if (cr >= TV - 2 && cr < TV + th + 2 && cc >= c_lo && cc < c_lo + c_n)
                 Bh[(size_t)r * pitchw * 2 + c] = Bh[(size_t)cr * pitchw * 2 + cc];
         }
         __syncthreads();
     }
     // ---- A9 + A10: 5x5 Gaussian [1 4 6 4 1]^2 / 256 in integer q16 where the median is valid (:176-189), final
-    //      inversion (:191-202), float32 store.  One thread walks a word column over a segment of rows with the
-    //      horizontal sums of the last five rows in registers.
-    {
-        const int CW = tw / 2;
-        const int nseg = 8, seg = (th + nseg - 1) / nseg;
-        for (int it = threadIdx.x; it < nseg * CW; it += QT) {
-            const int s = it / CW, cw = it - s * CW;
-            const int cy0 = s * seg, cy1 = min(th, cy0 + seg);
-            const int gx = x0 + 2 * cw;
-            if (cy0 >= cy1 || gx >= cols || y0 + cy0 >= rows) continue;
-            const int w = TQ * 4 + cw;
-            uint32_t hl[5], hh[5], mc[3];
+    //      inversion (:191-202), float32 store.  One item = one quad (8 pixels) of one row: vertical sums of the
+    //      12 columns it touches, then the horizontal combination in registers.
+    const int CQ = tw / 8;
+    for (Items i(CQ); i.r < th; i.next()) {
+        const int gy = y0 + i.r, gx = x0 + i.q * 8;
+        if (gy >= rows || gx >= cols) continue;
+        const uint32_t* p = B + (TV + i.r) * pitchw + (TQ + i.q) * 4;  // centre row, first word of the quad
+        uint32_t f[8];
+        if (a.blur == 1) {
+            uint32_t g[12];  // vertical [1 4 6 4 1] sums of columns gx-2 .. gx+9 (words -1 .. 4)
 #pragma unroll
-            for (int k = 0; k < 5; ++k) hl[k] = hh[k] = 0u;
-            mc[0] = mc[1] = mc[2] = 0u;
-            for (int cy = cy0 - 2; cy < cy1 + 2; ++cy) {
-                const uint32_t* row = B + (TV + cy) * pitchw + w;
-                const uint32_t pa = row[-1], pb = row[0], pc = row[1];
-                const uint32_t a0 = pa & 0xffffu, a1 = pa >> 16, b0 = pb & 0xffffu, b1 = pb >> 16, c0 = pc & 0xffffu, c1 = pc >> 16;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) { hl[k] = hl[k + 1]; hh[k] = hh[k + 1]; }
-                mc[0] = mc[1]; mc[1] = mc[2]; mc[2] = pb;
-                hl[4] = (a0 + c0) + 4u * (a1 + b1) + 6u * b0;  // pixel 2w:   columns 2w-2 .. 2w+2
-                hh[4] = (a1 + c1) + 4u * (b0 + c0) + 6u * b1;  // pixel 2w+1: columns 2w-1 .. 2w+3
-                const int oy = cy - 2;  // the window is centred two rows back
-                if (oy < cy0) continue;
-                const int gy = y0 + oy;
-                if (gy >= rows) break;
-                const uint32_t gl = (hl[0] + hl[4]) + 4u * (hl[1] + hl[3]) + 6u * hl[2];
-                const uint32_t gh = (hh[0] + hh[4]) + 4u * (hh[1] + hh[3]) + 6u * hh[2];
-                const uint32_t ml = mc[0] & 0xffffu, mh = mc[0] >> 16;
-                // e = q + 1: the weights sum to 256, so the blurred q16 value is g - 256
-                const float f0 = finish_px(ml >= E_VALID_MIN ? gl - 256u : (ml - 1u) << 8);
-                const float f1 = finish_px(mh >= E_VALID_MIN ? gh - 256u : (mh - 1u) << 8);
-                float* o = out + (size_t)gy * a.out_pitch + gx;
-                if (gx + 1 < cols && a.vec2_ok) *reinterpret_cast<float2*>(o) = make_float2(f0, f1);
-                else { o[0] = f0; if (gx + 1 < cols) o[1] = f1; }
+            for (int j = 0; j < 6; ++j) {
+                const uint32_t* c = p + (j - 1);
+                const uint32_t m2 = c[-2 * pitchw], m1 = c[-pitchw], c0 = c[0], p1 = c[pitchw], p2 = c[2 * pitchw];
+                const uint32_t so = __vadd2(m2, p2), si = __vadd2(m1, p1);  // <= 51202 per lane: no overflow
+                g[2 * j] = (so & 0xffffu) + 4u * (si & 0xffffu) + 6u * (c0 & 0xffffu);
+                g[2 * j + 1] = (so >> 16) + 4u * (si >> 16) + 6u * (c0 >> 16);
             }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t gg = (g[k] + g[k + 4]) + 4u * (g[k + 1] + g[k + 3]) + 6u * g[k + 2];  // centre column gx + k
+                const uint32_t word = p[k >> 1];
+                const uint32_t m = (k & 1) ? (word >> 16) : (word & 0xffffu);
+                // e = q + 1 and the weights sum to 256: the blurred q16 value is gg - 256
+                f[k] = m >= E_VALID_MIN ? gg - 256u : (m - 1u) << 8;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t word = p[k >> 1];
+                f[k] = (((k & 1) ? (word >> 16) : (word & 0xffffu)) - 1u) << 8;
+            }
+        }
+        float* o = out + (size_t)gy * a.out_pitch + gx;
+        if (gx + 8 <= cols && a.vec_ok) {
+            reinterpret_cast<float4*>(o)[0] = make_float4(finish_px(f[0]), finish_px(f[1]), finish_px(f[2]), finish_px(f[3]));
+            reinterpret_cast<float4*>(o)[1] = make_float4(finish_px(f[4]), finish_px(f[5]), finish_px(f[6]), finish_px(f[7]));
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (gx + k < cols) o[k] = finish_px(f[k]);
         }
     }
 }
@@ -742,12 +829,13 @@ __global__ void k_q8_write_stats(const FrameCounters* __restrict__ c, int32_t* _
 
 }  // namespace
 
-size_t q8_front_smem(int th, int tw) { return (size_t)2 * (th + FU + FD) * (tw / 8 + FLQ + FRQ) * 4 * sizeof(uint32_t); }
+size_t q8_front_smem(int th, int tw) {
+    return (size_t)2 * (th + FU + FD + 2 * FG) * (tw / 8 + FLQ + FRQ) * 4 * sizeof(uint32_t);
+}
 
 size_t q8_tail_smem(int th, int tw) {
-    const size_t plane = (size_t)(th + 2 * TV) * (tw / 8 + 2 * TQ) * 4 * sizeof(uint32_t);
-    const size_t list = (size_t)(th + 8) * (tw / 2 + 4) * sizeof(uint16_t);
-    return 2 * plane + ((list + 15) & ~size_t(15));
+    const size_t rowb = (size_t)(tw / 8 + 2 * TQ) * 4 * sizeof(uint32_t);
+    return (size_t)(2 * (th + 2 * TV) + TG) * rowb + (size_t)kListCap * sizeof(uint16_t);
 }
 
 void q8_choose_tile(int rows, int cols, int* th, int* tw) {
@@ -763,20 +851,21 @@ cudaError_t q8_configure() {
     return cudaFuncSetAttribute(k_q8_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 }
 
-cudaError_t q8_run_front(const Q8Plan& p, const float* in, size_t in_pitch, size_t in_fstride, int n_frames, cudaStream_t st) {
+cudaError_t q8_run_front(const Q8Plan& p, const float* in, size_t in_pitch, size_t in_fstride, int n_frames, int validate,
+                         cudaStream_t st) {
     const size_t ncol = (size_t)p.mid_pitch * n_frames;
     DCMT_LAUNCH(k_q8_zero_counters, dim3((n_frames + 127) / 128), dim3(128), 0, st, p.ctr, n_frames);
     DCMT_LAUNCH(k_q8_init_cols, dim3((unsigned)((ncol + 255) / 256)), dim3(256), 0, st, p.col_first, p.col_last, ncol);
     FrontArgs a{in, in_pitch, in_fstride, p.mid, (size_t)p.mid_pitch, (size_t)p.mid_pitch * p.rows, p.col_first, p.col_last,
                 p.ctr, p.rows, p.cols, p.th, p.tw,
-                (int)(in_pitch % 4 == 0 && in_fstride % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0)};
+                (int)(in_pitch % 4 == 0 && in_fstride % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0), validate};
     const dim3 grid((p.cols + p.tw - 1) / p.tw, (p.rows + p.th - 1) / p.th, n_frames);
     DCMT_LAUNCH(k_q8_front, grid, dim3(QT), q8_front_smem(p.th, p.tw), st, a);
     return cudaGetLastError();
 }
 
 cudaError_t q8_run_tail(const Q8Plan& p, float* out, size_t out_pitch, size_t out_fstride, int n_frames, int blur, cudaStream_t st) {
-    const int vec2 = out_pitch % 2 == 0 && out_fstride % 2 == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0;
+    const int vec2 = out_pitch % 4 == 0 && out_fstride % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
     TailArgs a{p.mid, (size_t)p.mid_pitch, (size_t)p.mid_pitch * p.rows, p.col_first, p.col_last, p.ctr, out, out_pitch,
                out_fstride, p.rows, p.cols, p.th, p.tw, blur, vec2};
     const dim3 grid((p.cols + p.tw - 1) / p.tw, (p.rows + p.th - 1) / p.th, n_frames);

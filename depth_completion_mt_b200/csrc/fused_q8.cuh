@@ -27,7 +27,9 @@ size_t q8_front_smem(int th, int tw);
 size_t q8_tail_smem(int th, int tw);
 cudaError_t q8_configure();
 // A1..A4 for n_frames slots: in -> plan.mid (+ column keys, counters zeroed)
-cudaError_t q8_run_front(const Q8Plan& p, const float* in, size_t in_pitch, size_t in_fstride, int n_frames, cudaStream_t st);
+// `validate` != 0: check strict q8-ness of every pixel (frames that fail are flagged for the generic pipeline)
+cudaError_t q8_run_front(const Q8Plan& p, const float* in, size_t in_pitch, size_t in_fstride, int n_frames, int validate,
+                         cudaStream_t st);
 // A5..A10: plan.mid -> out (float32), blur in {none, gaussian}; then the fix-up kernel
 cudaError_t q8_run_tail(const Q8Plan& p, float* out, size_t out_pitch, size_t out_fstride, int n_frames, int blur,
                         cudaStream_t st);

@@ -57,9 +57,16 @@ enum { DCMT_BLUR_NONE = 0, DCMT_BLUR_GAUSSIAN = 1, DCMT_BLUR_BILATERAL = 2 };
 
 /* kernel path selection (flags argument) */
 enum {
-    DCMT_PATH_AUTO = 0,    /* fused q8 strip kernel when the frame qualifies, generic otherwise */
-    DCMT_PATH_GENERIC = 1, /* force the generic float32 multi-kernel pipeline */
-    DCMT_PATH_FUSED = 2    /* force the fused kernel (frames that do not qualify are still redone generically) */
+    /* fused strict-q8 kernels with in-kernel validation; frames that turn out not to be strict q8 (any pixel that is
+     * neither 0 nor k/256 with 26 <= k <= 25574) are redone by the generic pipeline.  Always correct; reads one
+     * int32 per frame back at the end of the call, i.e. synchronises the stream once. */
+    DCMT_PATH_AUTO = 0,
+    /* generic float32 multi-kernel pipeline: any finite input, fully asynchronous */
+    DCMT_PATH_GENERIC = 1,
+    /* fused kernels without validation, fully asynchronous (CUDA-graph capturable): the CALLER guarantees strict q8
+     * input (e.g. KITTI uint16 PNG / 256, main.cpp:75-82); other input gives undefined output.  Shapes / blur
+     * types the fused kernels do not serve (bilateral, frames under 32x32) still use the generic pipeline. */
+    DCMT_PATH_FUSED = 2
 };
 
 /* per-frame statistics, DCMT_STATS_STRIDE int32 per frame (device memory for the async entry
@@ -67,7 +74,7 @@ enum {
  *   [0] passes the reference's `while` loop executes (img_completion.cpp:146-166), >= 1
  *   [1] holes counted by the first loop pass (= holes left after the first 31x31 fill)
  *   [2] holes counted by the first 31x31 fill (= holes left after column extrapolation)
- *   [3] path that produced the frame: 0 generic, 1 fused q8 */
+ *   [3] path that produced the frame: 0 generic, 1 fused strict-q8 */
 #define DCMT_STATS_STRIDE 4
 
 DCMT_API int dcmt_version(void);

@@ -51,9 +51,8 @@ def body_routing(be):
     check(be, s, "forced generic", path="generic", want_path=0)
     f = synth.sparse_depth_float(6, 64, 96, 0.05)
     check(be, f, "float frame via auto", want_path=0)
-    # DCMT_PATH_FUSED never synchronises: a frame that is not strict q8 is reported with stats[3] == -1
-    _, st = be.img_completion(f, "gaussian", path="fused", return_stats=True)
-    assert int(st[0, 3]) == -1
+    # DCMT_PATH_FUSED trusts the caller (no validation, no synchronisation): only meaningful for strict q8 frames
+    check(be, s, "forced fused", path="fused", want_path=1)
     # bilateral and tiny frames are served by the generic pipeline whatever the flag says
     out, st = be.img_completion(s, "bilateral", path="fused", return_stats=True)
     assert int(st[0, 3]) == 0 and np.abs(out - co.img_completion(s, "bilateral")).max() <= 2e-4
