@@ -80,15 +80,20 @@ struct Items {
 };
 
 // Encode one input pixel (metres, float) into inverted q8 (+1).  img_completion.cpp:55-67.
-// strict q8 input: v == 0 (hole -> e = 1) or v = k/256 with 26 <= k <= 25574 (e = 25601 - k in [27, 25575]).
+//   v in [0.1f, 25574/256]  ->  e = 25601 - 256 v  in [27, 25575]   (valid, inverted: 100 - v)
+//   anything else           ->  e = 1                                (a hole)
+// "Anything else" covers 0, negatives, values below 0.1f and values whose inversion 100 - v falls below 0.1f:
+// all of them are holes for every later stage (each stage only asks `< 0.1f`, takes max/min with valid values
+// or overwrites them), so their exact value never reaches the output.  What must hold for the integer pipeline to
+// be exact is that every VALID pixel is a multiple of 1/256: kValidate checks it (the add of 2^23 must not round).
 template <bool kValidate>
 __device__ __forceinline__ uint32_t encode_bits(float v, int& bad) {
     const float t = fmaf(v, -256.0f, 25601.0f);  // 25601 - k, exact for q8 input
-    const bool valid = v >= 0.1f;
+    // positive floats order like their bit patterns: one unsigned compare tests 0.1f <= v <= 99.8984375f
+    const bool valid = __float_as_uint(v) - 0x3dcccccdu <= 0x42c7cc00u - 0x3dcccccdu;
     const float ef = valid ? t : 1.0f;
     const float m = ef + 8388608.0f;  // 2^23: the integer lands in the low mantissa bits
-    if (kValidate)  // holes must be exactly 0; valid pixels integral (no rounding in the add) and >= 27 (<= 25575 follows)
-        bad |= valid ? !(m - 8388608.0f == t && t >= 27.0f) : (v != 0.0f);
+    if (kValidate) bad |= (m - 8388608.0f != ef);
     return __float_as_uint(m);
 }
 template <bool kValidate>
@@ -122,9 +127,33 @@ constexpr int FG = 3;                            // guard rows
 
 struct Tile {
     int RH, RQ, pitchw;
-    int rlo, rhi;   // region rows inside the image: [rlo, rhi)
-    int gx0, cols;  // image column of region column 0
+    int rlo, rhi;  // region rows inside the image: [rlo, rhi)
+    int qlo, qhi;  // region quads with at least one pixel inside the image: [qlo, qhi)
+    int qs;        // the quad straddling the right image edge (cols % 8 != 0), or -1
+    uint4 smask;   // its in-image lanes
 };
+
+__device__ __forceinline__ void tile_columns(Tile& t, int gx0, int cols) {
+    t.qlo = gx0 < 0 ? (-gx0) / 8 : 0;  // gx0 is a multiple of 8
+    t.qhi = min(t.RQ, (cols - gx0 + 7) / 8);
+    t.qs = -1;
+    t.smask = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+    if (cols % 8 != 0) {
+        const int q = (cols - gx0) / 8;
+        if (q >= 0 && q < t.RQ) {
+            t.qs = q;
+            const int n = cols - (gx0 + q * 8);  // 1..7 pixels inside
+            uint32_t m[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) m[j] = (2 * j < n ? 0x0000ffffu : 0u) | (2 * j + 1 < n ? 0xffff0000u : 0u);
+            t.smask = make_uint4(m[0], m[1], m[2], m[3]);
+        }
+    }
+}
+__device__ __forceinline__ bool outside(const Tile& t, int r, int q) { return r < t.rlo || r >= t.rhi || q < t.qlo || q >= t.qhi; }
+__device__ __forceinline__ uint4 blend(uint4 v, uint4 m, uint32_t ident) {
+    return make_uint4((v.x & m.x) | (ident & ~m.x), (v.y & m.y) | (ident & ~m.y), (v.z & m.z) | (ident & ~m.z), (v.w & m.w) | (ident & ~m.w));
+}
 
 template <int R, bool kIsMax, bool kBorder>
 __device__ __forceinline__ void v_pass(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, const Tile& t,
@@ -132,7 +161,7 @@ __device__ __forceinline__ void v_pass(const uint32_t* __restrict__ src, uint32_
     for (Items i(t.RQ); i.r < t.RH; i.next()) {
         const int off = (i.r * t.RQ + i.q) * 4;
         uint4 acc;
-        if (kBorder && (i.r < t.rlo || i.r >= t.rhi)) {
+        if (kBorder && outside(t, i.r, i.q)) {
             acc = splat4(ident_next);
         } else {
             const uint32_t* p = src + off;
@@ -145,10 +174,7 @@ __device__ __forceinline__ void v_pass(const uint32_t* __restrict__ src, uint32_
                 acc.z = pext3<kIsMax>(acc.z, up.z, dn.z);
                 acc.w = pext3<kIsMax>(acc.w, up.w, dn.w);
             }
-            if (kBorder) {
-                const int gx = t.gx0 + i.q * 8;
-                if (gx < 0 || gx + 8 > t.cols) acc = mask_columns(acc, gx, t.cols, ident_next);
-            }
+            if (kBorder && i.q == t.qs) acc = blend(acc, t.smask, ident_next);
         }
         sts4(dst + off, acc);
     }
@@ -161,7 +187,7 @@ __device__ __forceinline__ void h5_pass(const uint32_t* __restrict__ src, uint32
     for (Items i(t.RQ); i.r < t.RH; i.next()) {
         const int off = (i.r * t.RQ + i.q) * 4;
         uint4 o;
-        if (kBorder && (i.r < t.rlo || i.r >= t.rhi)) {
+        if (kBorder && outside(t, i.r, i.q)) {
             o = splat4(ident_next);
         } else {
             const uint32_t* p = src + off;
@@ -173,10 +199,7 @@ __device__ __forceinline__ void h5_pass(const uint32_t* __restrict__ src, uint32
             o.y = pext3<kIsMax>(pext3<kIsMax>(c.x, r1, c.y), r2, c.z);
             o.z = pext3<kIsMax>(pext3<kIsMax>(c.y, r2, c.z), r3, c.w);
             o.w = pext3<kIsMax>(pext3<kIsMax>(c.z, r3, c.w), r4, wr);
-            if (kBorder) {
-                const int gx = t.gx0 + i.q * 8;
-                if (gx < 0 || gx + 8 > t.cols) o = mask_columns(o, gx, t.cols, ident_next);
-            }
+            if (kBorder && i.q == t.qs) o = blend(o, t.smask, ident_next);
         }
         sts4(dst + off, o);
     }
@@ -211,7 +234,7 @@ __device__ __forceinline__ void front_passes(uint32_t* A, uint32_t* B, const Til
     for (Items i(t.RQ); i.r < t.RH; i.next()) {
         const int off = (i.r * t.RQ + i.q) * 4;
         uint4 o;
-        if (kBorder && (i.r < t.rlo || i.r >= t.rhi)) {
+        if (kBorder && outside(t, i.r, i.q)) {
             o = splat4(kAbsMax);
         } else {
             const uint32_t* pa = A + off - t.pitchw;      // row y-1
@@ -223,10 +246,7 @@ __device__ __forceinline__ void front_passes(uint32_t* A, uint32_t* B, const Til
             o.y = pmax(odd_pair(ca.y, ca.z), cb.z);
             o.z = pmax(odd_pair(ca.z, ca.w), cb.w);
             o.w = pmax(odd_pair(ca.w, na), nb);
-            if (kBorder) {
-                const int gx = t.gx0 + i.q * 8;
-                if (gx < 0 || gx + 8 > t.cols) o = mask_columns(o, gx, t.cols, kAbsMax);
-            }
+            if (kBorder && i.q == t.qs) o = blend(o, t.smask, kAbsMax);
         }
         sts4(B + off, o);
     }
@@ -246,41 +266,26 @@ __device__ __forceinline__ void front_passes(uint32_t* A, uint32_t* B, const Til
 }
 
 template <bool kValidate>
-__device__ __forceinline__ void front_load(const FrontArgs& a, const float* in, uint32_t* A, const Tile& t, int gy0, int& bad) {
-    const int rows = a.rows, cols = a.cols;
+__device__ __forceinline__ void front_load(const FrontArgs& a, const float* in, uint32_t* A, const Tile& t, int gy0, int gx0,
+                                           int& bad) {
     for (Items i(t.RQ); i.r < t.RH; i.next()) {
-        const int gy = gy0 + i.r, gx = t.gx0 + i.q * 8;
-        // only the core is validated: every pixel is in the core of exactly one tile
-        const bool core = kValidate && i.r >= FU && i.r < FU + a.th && i.q >= FLQ && i.q < t.RQ - FRQ;
         uint4 o = splat4(kAbsMax);  // outside the image: absent
-        int b = 0;
-        if (gy >= 0 && gy < rows) {
-            const float* p = in + (size_t)gy * a.in_pitch + gx;
-            if (gx >= 0 && gx + 8 <= cols && a.vec_ok) {
+        if (!outside(t, i.r, i.q)) {
+            const int gx = gx0 + i.q * 8;
+            const float* p = in + (size_t)(gy0 + i.r) * a.in_pitch + gx;
+            if (i.q != t.qs && a.vec_ok) {
                 const float4 f0 = __ldg(reinterpret_cast<const float4*>(p)), f1 = __ldg(reinterpret_cast<const float4*>(p) + 1);
-                if (core) {
-                    o.x = encode_pair<true>(f0.x, f0.y, b); o.y = encode_pair<true>(f0.z, f0.w, b);
-                    o.z = encode_pair<true>(f1.x, f1.y, b); o.w = encode_pair<true>(f1.z, f1.w, b);
-                } else {
-                    o.x = encode_pair<false>(f0.x, f0.y, b); o.y = encode_pair<false>(f0.z, f0.w, b);
-                    o.z = encode_pair<false>(f1.x, f1.y, b); o.w = encode_pair<false>(f1.z, f1.w, b);
-                }
+                o.x = encode_pair<kValidate>(f0.x, f0.y, bad);
+                o.y = encode_pair<kValidate>(f0.z, f0.w, bad);
+                o.z = encode_pair<kValidate>(f1.x, f1.y, bad);
+                o.w = encode_pair<kValidate>(f1.z, f1.w, bad);
             } else {
                 uint32_t e[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int x = gx + j;
-                    e[j] = 0u;
-                    if (x >= 0 && x < cols) {
-                        int bb = 0;
-                        e[j] = encode_bits<true>(__ldg(p + j), bb) & 0xffffu;
-                        if (core) b |= bb;
-                    }
-                }
+                for (int j = 0; j < 8; ++j) e[j] = gx + j < a.cols ? (encode_bits<kValidate>(__ldg(p + j), bad) & 0xffffu) : 0u;
                 o = make_uint4(e[0] | (e[1] << 16), e[2] | (e[3] << 16), e[4] | (e[5] << 16), e[6] | (e[7] << 16));
             }
         }
-        bad |= b;
         sts4(A + (i.r * t.RQ + i.q) * 4, o);
     }
 }
@@ -297,17 +302,17 @@ __global__ void __launch_bounds__(QT) k_q8_front(FrontArgs a) {
     const int frame = blockIdx.z;  // slot == frame offset inside the chunk
     const int y0 = blockIdx.y * th, x0 = blockIdx.x * tw;
     const int gy0 = y0 - FU;
-    t.gx0 = x0 - FLQ * 8;
-    t.cols = cols;
+    const int gx0 = x0 - FLQ * 8;
     t.rlo = max(0, -gy0);
     t.rhi = min(t.RH, rows - gy0);
+    tile_columns(t, gx0, cols);
     const float* in = a.in + (size_t)frame * a.in_fstride;
-    const bool border = gy0 < 0 || gy0 + t.RH > rows || t.gx0 < 0 || t.gx0 + t.RQ * 8 > cols;
+    const bool border = gy0 < 0 || gy0 + t.RH > rows || gx0 < 0 || gx0 + t.RQ * 8 > cols;
 
     // ---- pass 0: load, validate, invert, encode (:55-67)
     int bad = 0;
-    if (a.validate) front_load<true>(a, in, A, t, gy0, bad);
-    else front_load<false>(a, in, A, t, gy0, bad);
+    if (a.validate) front_load<true>(a, in, A, t, gy0, gx0, bad);
+    else front_load<false>(a, in, A, t, gy0, gx0, bad);
     if (__syncthreads_or(bad)) {  // not strict q8: this frame is redone by the generic pipeline
         if (threadIdx.x == 0) a.ctr[frame].needs_generic = 1;
         return;
@@ -418,10 +423,9 @@ __device__ __forceinline__ uint32_t hole_mask(uint32_t w) {
     return (((w & 0xffffu) == 1u) ? 0x0000ffffu : 0u) | (((w >> 16) == 1u) ? 0xffff0000u : 0u);
 }
 
-// q16 inverted-space value -> output float: img_completion.cpp:191-202 (d >= 0.1f <=> d16 >= 6554), exact
-__device__ __forceinline__ float finish_px(uint32_t d16) {
-    const uint32_t o = d16 >= 6554u ? 6553600u - d16 : d16;
-    return fmaf(__uint_as_float(0x4b000000u + o), 1.0f / 65536.0f, -128.0f);  // (2^23 + o) / 2^16 - 128
+// q16 output value (already inverted, < 2^23) -> float, exact: (2^23 + o) / 2^16 - 128
+__device__ __forceinline__ float finish_px(uint32_t o) {
+    return fmaf(__uint_as_float(0x4b000000u + o), 1.0f / 65536.0f, -128.0f);
 }
 
 // 31-wide horizontal max of the vertical maxima for word w of row r (B holds 16-row maxima: rows r-15..r and r..r+15)
@@ -455,19 +459,27 @@ __global__ void __launch_bounds__(QT, 2) k_q8_tail(TailArgs a) {
     if (threadIdx.x == 0) { s_count = 0; s_remaining = 0; s_holes_core = 0; s_left_core = 0; }
 
     // ---- load the A4 plane (outside the image: absent)
-    if (!border) {
-        for (Items i(RQ); i.r < RH; i.next())
-            sts4(A + (i.r * RQ + i.q) * 4,
-                 __ldg(reinterpret_cast<const uint4*>(mid + (size_t)(gy0 + i.r) * a.mid_pitch + gx0 + i.q * 8)));
-    } else {
-        for (Items i(RQ); i.r < RH; i.next()) {
-            const int gy = gy0 + i.r, gx = gx0 + i.q * 8;
-            uint4 v = splat4(kAbsMax);
-            if (gy >= 0 && gy < rows && gx >= 0 && gx < cols) {
-                v = __ldg(reinterpret_cast<const uint4*>(mid + (size_t)gy * a.mid_pitch + gx));
-                if (gx + 8 > cols) v = mask_columns(v, gx, cols, kAbsMax);
+    Tile t;
+    t.RH = RH;
+    t.RQ = RQ;
+    t.pitchw = pitchw;
+    t.rlo = max(0, -gy0);
+    t.rhi = min(RH, rows - gy0);
+    tile_columns(t, gx0, cols);
+    {
+        const uint16_t* mp = mid + (ptrdiff_t)gy0 * (ptrdiff_t)a.mid_pitch + gx0;
+        if (!border) {
+            for (Items i(RQ); i.r < RH; i.next())
+                sts4(A + (i.r * RQ + i.q) * 4, __ldg(reinterpret_cast<const uint4*>(mp + (size_t)i.r * a.mid_pitch + i.q * 8)));
+        } else {
+            for (Items i(RQ); i.r < RH; i.next()) {
+                uint4 v = splat4(kAbsMax);
+                if (!outside(t, i.r, i.q)) {
+                    v = __ldg(reinterpret_cast<const uint4*>(mp + (ptrdiff_t)i.r * (ptrdiff_t)a.mid_pitch + i.q * 8));
+                    if (i.q == t.qs) v = blend(v, t.smask, kAbsMax);
+                }
+                sts4(A + (i.r * RQ + i.q) * 4, v);
             }
-            sts4(A + (i.r * RQ + i.q) * 4, v);
         }
     }
     __syncthreads();
@@ -532,57 +544,47 @@ __global__ void __launch_bounds__(QT, 2) k_q8_tail(TailArgs a) {
     //      Scan region: rows core +- 4, quads covering columns core +- 8 (a superset of the +- 4 the median needs).
     const int SH = th + 8, SQ = tw / 8 + 2;
     const int sr0 = TV - 4, sq0 = TQ - 1;
-    int holes_core = 0;
     {
         const int n = SH * SQ;
         Items i(SQ);
         for (int base = 0; base < n; base += QT, i.next()) {
-            const bool active = base + (int)threadIdx.x < n;
-            uint32_t w[4] = {2u, 2u, 2u, 2u};
-            int wbase = 0;
             bool cand = false;
-            if (active) {
-                wbase = ((sr0 + i.r) * RQ + sq0 + i.q) * 4;
-                const uint4 v = lds4(A + wbase);
-                w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+            int qidx = 0;
+            if (base + (int)threadIdx.x < n) {
+                qidx = (sr0 + i.r) * RQ + sq0 + i.q;
+                const uint4 v = lds4(A + qidx * 4);
                 // some lane <= 1 (a hole, or absent outside the image)?
                 cand = pmin(pmin(pmin(v.x, v.y), pmin(v.z, v.w)), SPLAT16(2)) != SPLAT16(2);
             }
-            if (!__any_sync(0xffffffffu, cand)) continue;
-            const bool core_row = i.r >= 4 && i.r < 4 + th;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const uint32_t hm = cand ? hole_mask(w[j]) : 0u;
-                const bool has = hm != 0u;
-                if (has && core_row && i.q >= 1 && i.q < SQ - 1) holes_core += __popc(hm) >> 4;
-                const unsigned bal = __ballot_sync(0xffffffffu, has);
-                if (bal == 0u) continue;
-                int pos = 0;
-                if ((threadIdx.x & 31) == 0) pos = atomicAdd(&s_count, __popc(bal));
-                pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(bal & ((1u << (threadIdx.x & 31)) - 1u));
-                if (has && pos < kListCap) list[pos] = (uint16_t)(wbase + j);
-            }
+            const unsigned bal = __ballot_sync(0xffffffffu, cand);
+            if (bal == 0u) continue;
+            int pos = 0;
+            if ((threadIdx.x & 31) == 0) pos = atomicAdd(&s_count, __popc(bal));
+            pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(bal & ((1u << (threadIdx.x & 31)) - 1u));
+            if (cand && pos < kListCap) list[pos] = (uint16_t)qidx;
         }
     }
     __syncthreads();
-    int left_core = 0, left_any = 0;
-    const int n_holes = s_count;
+    int holes_core = 0, left_core = 0, left_any = 0;
+    const int n_quads = s_count;
     auto fill_word = [&](int widx) {
         const uint32_t d = A[widx], hm = hole_mask(d);
         if (hm == 0u) return;
         const int r = widx / pitchw, w = widx - r * pitchw;
+        const int sr = r - sr0, sw = w - TQ * 4;
+        const bool core = sr >= 4 && sr < 4 + th && sw >= 0 && sw < tw / 2;
+        if (core) holes_core += __popc(hm) >> 4;
         const uint32_t nd = (hmax31(B, pitchw, r, w) & hm) | (d & ~hm);
         A[widx] = nd;
         const uint32_t still = hole_mask(nd);
         if (still) {
             left_any = 1;
-            const int sr = r - sr0, sw = w - TQ * 4;
-            if (sr >= 4 && sr < 4 + th && sw >= 0 && sw < tw / 2) left_core += __popc(still) >> 4;
+            if (core) left_core += __popc(still) >> 4;
         }
     };
-    if (n_holes <= kListCap) {
-        for (int k = threadIdx.x; k < n_holes; k += QT) fill_word(list[k]);
-    } else {  // very sparse input: most words hold holes, process the whole scan region
+    if (n_quads <= kListCap) {
+        for (int k = threadIdx.x; k < 4 * n_quads; k += QT) fill_word(list[k >> 2] * 4 + (k & 3));
+    } else {  // cannot happen for tiles up to 96 x 160 (2184 scan quads); kept for larger tiles
         for (Items i(SQ * 4); i.r < SH; i.next()) fill_word((sr0 + i.r) * pitchw + sq0 * 4 + i.q);
     }
     if (holes_core) atomicAdd(&s_holes_core, holes_core);
@@ -594,17 +596,27 @@ __global__ void __launch_bounds__(QT, 2) k_q8_tail(TailArgs a) {
         if (s_left_core) atomicAdd(&a.ctr[slot].holes_after_first_fill, s_left_core);
         if (s_remaining) a.ctr[slot].holes_remaining = 1;  // a second pass is needed: k_q8_fixup redoes the frame
     }
-    // ---- BORDER_REPLICATE for the median (:170): copy the nearest image pixel into cells outside the image
-    //      (rows / columns core +- 4)
+    // ---- BORDER_REPLICATE for the median (:170): copy the nearest image pixel into the cells outside the image
+    //      (rows / columns core +- 4).  Only the strips that are outside are visited.
     if (border) {
         const int c_lo = TQ * 8 - 4, c_n = tw + 8;
-        for (int it = threadIdx.x; it < SH * c_n; it += QT) {
-            const int sr = it / c_n, sc = it - sr * c_n;
-            const int r = sr0 + sr, c = c_lo + sc;
-            const int gy = gy0 + r, gx = gx0 + c;
-            if (gy >= 0 && gy < rows && gx >= 0 && gx < cols) continue;
-            const int cr = clampi(gy, 0, rows - 1) - gy0, cc = clampi(gx, 0, cols - 1) - gx0;
-            if (cr >= 0 && cr < RH && cc >= 0 && cc < RQ * 8) Ah[(size_t)r * pitchw * 2 + c] = Ah[(size_t)cr * pitchw * 2 + cc];
+        const int r_in0 = max(sr0, -gy0), r_in1 = min(sr0 + SH, rows - gy0);          // in-image scan rows [r_in0, r_in1)
+        const int c_in0 = max(c_lo, -gx0), c_in1 = min(c_lo + c_n, cols - gx0);        // in-image scan columns
+        const int n_rows_out = SH - max(0, r_in1 - r_in0), n_cols_out = c_n - max(0, c_in1 - c_in0);
+        // (1) columns outside, rows inside   (2) rows outside, all columns (after (1): sources are final)
+        for (int it = threadIdx.x; it < max(0, r_in1 - r_in0) * n_cols_out; it += QT) {
+            const int rr = it / n_cols_out, k = it - rr * n_cols_out;
+            const int r = r_in0 + rr;
+            const int c = k < c_in0 - c_lo ? c_lo + k : c_in1 + (k - (c_in0 - c_lo));
+            const int cc = clampi(c, c_in0, c_in1 - 1);
+            Ah[(size_t)r * pitchw * 2 + c] = Ah[(size_t)r * pitchw * 2 + cc];
+        }
+        __syncthreads();
+        for (int it = threadIdx.x; it < n_rows_out * c_n; it += QT) {
+            const int k = it / c_n, c = c_lo + (it - k * c_n);
+            const int r = k < r_in0 - sr0 ? sr0 + k : r_in1 + (k - (r_in0 - sr0));
+            const int cr = clampi(r, r_in0, r_in1 - 1);
+            if (cr >= 0 && cr < RH) Ah[(size_t)r * pitchw * 2 + c] = Ah[(size_t)cr * pitchw * 2 + c];
         }
         __syncthreads();
     }
@@ -645,18 +657,25 @@ __global__ void __launch_bounds__(QT, 2) k_q8_tail(TailArgs a) {
     }
     __syncthreads();
     float* out = a.out + (size_t)slot * a.out_fstride;
-    // ---- BORDER_REFLECT_101 for the Gaussian (:179): mirror the median image into the 2 cells beyond each edge
+    // ---- BORDER_REFLECT_101 for the Gaussian (:179): mirror the median image into the 2 cells beyond each edge.
+    //      Columns first (rows inside), then whole rows (their sources then include the mirrored columns).
     if (border && a.blur == 1) {
-        const int c_lo = TQ * 8 - 2, c_n = tw + 4;
-        for (int it = threadIdx.x; it < (th + 4) * c_n; it += QT) {
-            const int sr = it / c_n, sc = it - sr * c_n;
-            const int r = TV - 2 + sr, c = c_lo + sc;
-            const int gy = gy0 + r, gx = gx0 + c;
-            if (gy >= 0 && gy < rows && gx >= 0 && gx < cols) continue;
-            if (gy < -2 || gy > rows + 1 || gx < -2 || gx > cols + 1) continue;
-            const int cr = reflect101(gy, rows) - gy0, cc = reflect101(gx, cols) - gx0;
-            if (cr >= TV - 2 && cr < TV + th + 2 && cc >= c_lo && cc < c_lo + c_n)
-                Bh[(size_t)r * pitchw * 2 + c] = Bh[(size_t)cr * pitchw * 2 + cc];
+        const int c_lo = TQ * 8 - 2, c_n = tw + 4, r_lo = TV - 2, r_n = th + 4;
+        const int r_in0 = max(r_lo, -gy0), r_in1 = min(r_lo + r_n, rows - gy0);
+        const int c_in0 = max(c_lo, -gx0), c_in1 = min(c_lo + c_n, cols - gx0);
+        // at most 2 columns on each side matter: region columns -gx0-2, -gx0-1 and cols-gx0, cols-gx0+1
+        for (int it = threadIdx.x; it < max(0, r_in1 - r_in0) * 4; it += QT) {
+            const int r = r_in0 + (it >> 2), k = it & 3;
+            const int gx = k < 2 ? k - 2 : cols + (k - 2);
+            const int c = gx - gx0, cc = reflect101(gx, cols) - gx0;
+            if (c >= c_lo && c < c_lo + c_n && cc >= c_in0 && cc < c_in1) Bh[(size_t)r * pitchw * 2 + c] = Bh[(size_t)r * pitchw * 2 + cc];
+        }
+        __syncthreads();
+        for (int it = threadIdx.x; it < 4 * c_n; it += QT) {
+            const int k = it / c_n, c = c_lo + (it - k * c_n);
+            const int gy = k < 2 ? k - 2 : rows + (k - 2);
+            const int r = gy - gy0, cr = reflect101(gy, rows) - gy0;
+            if (r >= r_lo && r < r_lo + r_n && cr >= r_in0 && cr < r_in1) Bh[(size_t)r * pitchw * 2 + c] = Bh[(size_t)cr * pitchw * 2 + c];
         }
         __syncthreads();
     }
@@ -679,19 +698,17 @@ __global__ void __launch_bounds__(QT, 2) k_q8_tail(TailArgs a) {
                 g[2 * j] = (so & 0xffffu) + 4u * (si & 0xffffu) + 6u * (c0 & 0xffffu);
                 g[2 * j + 1] = (so >> 16) + 4u * (si >> 16) + 6u * (c0 >> 16);
             }
+            // Every pixel is valid here (a frame with holes left is redone by k_q8_fixup), so the masked copy
+            // (:181-188) always takes the blurred value and the final inversion (:191-202) always applies:
+            // out16 = 6553600 - (gg - 256) with e = q + 1 and weights summing to 256.
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const uint32_t gg = (g[k] + g[k + 4]) + 4u * (g[k + 1] + g[k + 3]) + 6u * g[k + 2];  // centre column gx + k
-                const uint32_t word = p[k >> 1];
-                const uint32_t m = (k & 1) ? (word >> 16) : (word & 0xffffu);
-                // e = q + 1 and the weights sum to 256: the blurred q16 value is gg - 256
-                f[k] = m >= E_VALID_MIN ? gg - 256u : (m - 1u) << 8;
-            }
+            for (int k = 0; k < 8; ++k)
+                f[k] = 6553856u - ((g[k] + g[k + 4]) + 4u * (g[k + 1] + g[k + 3]) + 6u * g[k + 2]);  // centre column gx + k
         } else {
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 const uint32_t word = p[k >> 1];
-                f[k] = (((k & 1) ? (word >> 16) : (word & 0xffffu)) - 1u) << 8;
+                f[k] = 6553856u - (((k & 1) ? (word >> 16) : (word & 0xffffu)) << 8);  // 6553600 - ((e - 1) << 8)
             }
         }
         float* o = out + (size_t)gy * a.out_pitch + gx;

@@ -34,16 +34,26 @@ def body_shapes(be, shapes):
 
 
 def body_boundary_values(be):
-    """q8 codes around the thresholds: 26/256 is the smallest valid depth; 25574/256 inverts to 26/256 (still
-    valid); 25575/256 inverts to 25/256 < 0.1 and becomes a hole again -> not strict q8 -> generic pipeline."""
+    """q8 codes around the thresholds: 26/256 is the smallest valid depth; 25574/256 inverts to 26/256 (still valid);
+    25575/256 .. 25600/256 invert to < 0.1 and become holes again; 1/256 .. 25/256 are holes from the start.  Hole
+    VALUES never reach the output (every stage only tests `< 0.1f`), so all of these stay on the fused path and
+    must still match the oracle bit for bit.  Negative and > 100 m pixels are holes too."""
     rng = np.random.default_rng(3)
     base = synth.sparse_depth_q8(5, 48, 72, 0.08)
-    for codes, strict in (((26, 27, 25574, 25573, 300), True), ((25,), False), ((25575,), False), ((25600,), False), ((1,), False)):
+    for codes in ((26, 27, 25574, 25573, 300), (25,), (25575,), (25600,), (1,), (1, 25, 26, 25574, 25575, 25599, 25600, 30000, 65535)):
         d16 = base.copy()
-        ys, xs = rng.integers(0, 48, 20), rng.integers(0, 72, 20)
-        d16[ys, xs] = rng.choice(codes, 20)
+        ys, xs = rng.integers(0, 48, 30), rng.integers(0, 72, 30)
+        d16[ys, xs] = rng.choice(codes, 30)
         s = d16.astype(np.float32) / np.float32(256)
-        check(be, s, f"codes {codes}", want_path=1 if strict else 0)
+        check(be, s, f"codes {codes}", want_path=1)
+    s = base.astype(np.float32) / np.float32(256)
+    s[rng.integers(0, 48, 10), rng.integers(0, 72, 10)] = np.float32(-3.25)
+    s[rng.integers(0, 48, 10), rng.integers(0, 72, 10)] = np.float32(0.05)
+    s[rng.integers(0, 48, 10), rng.integers(0, 72, 10)] = np.float32(1e-30)
+    check(be, s, "negative / tiny / sub-threshold values are holes", want_path=1)
+    s2 = s.copy()
+    s2[7, 9] = np.float32(12.3)  # a valid pixel that is not a multiple of 1/256: generic pipeline
+    check(be, s2, "one non-q8 valid pixel", want_path=0)
 
 
 def body_routing(be):
