@@ -64,36 +64,49 @@ __device__ __forceinline__ uint4 mask_columns(uint4 v, int gx, int cols, uint32_
 }
 
 // Iterates item = threadIdx.x, threadIdx.x + QT, ... over an (nr x nq) grid as (r, q) without a division per item.
+// Built once per kernel for each row length it is used with (the constructor divides), then copied per loop;
+// `lin` is the linear item index r * nq + q.
 struct Items {
-    int r, q, dr, dq, nq;
+    int r, q, lin, dr, dq, nq;
     __device__ __forceinline__ explicit Items(int nq_) : nq(nq_) {
         r = threadIdx.x / nq_;
         q = threadIdx.x - r * nq_;
+        lin = threadIdx.x;
         dr = QT / nq_;
         dq = QT - dr * nq_;
     }
     __device__ __forceinline__ void next() {
         q += dq;
         r += dr;
+        lin += QT;
         if (q >= nq) { q -= nq; ++r; }
     }
 };
 
 // Encode one input pixel (metres, float) into inverted q8 (+1).  img_completion.cpp:55-67.
-//   v in [0.1f, 25574/256]  ->  e = 25601 - 256 v  in [27, 25575]   (valid, inverted: 100 - v)
-//   anything else           ->  e = 1                                (a hole)
+//   v = k/256, 26 <= k <= 25574  ->  e = 25601 - k  in [27, 25575]   (valid, inverted: 100 - v)
+//   anything else a hole        ->  e = 1
 // "Anything else" covers 0, negatives, values below 0.1f and values whose inversion 100 - v falls below 0.1f:
 // all of them are holes for every later stage (each stage only asks `< 0.1f`, takes max/min with valid values
 // or overwrites them), so their exact value never reaches the output.  What must hold for the integer pipeline to
 // be exact is that every VALID pixel is a multiple of 1/256: kValidate checks it (the add of 2^23 must not round).
 template <bool kValidate>
 __device__ __forceinline__ uint32_t encode_bits(float v, int& bad) {
-    const float t = fmaf(v, -256.0f, 25601.0f);  // 25601 - k, exact for q8 input
-    // positive floats order like their bit patterns: one unsigned compare tests 0.1f <= v <= 99.8984375f
-    const bool valid = __float_as_uint(v) - 0x3dcccccdu <= 0x42c7cc00u - 0x3dcccccdu;
+    const float t = fmaf(v, -256.0f, 25601.0f);  // 25601 - 256 v, exact for q8 input
+    // valid <=> 26.5 <= t <= 25575.5 in ONE unsigned compare (positive floats order like their bit patterns; smaller,
+    // negative and NaN t wrap to huge values).  For q8 input t is an integer, so this is exactly 27 <= t <= 25575,
+    // i.e. 0.1f <= v and 0.1f <= 100 - v.  For other input the band is slightly wider than the reference's `>= 0.1f`
+    // on purpose: every pixel the reference would treat as valid lands inside it with a non-integral t and trips
+    // the validation, and everything outside it is a hole for the reference as well.
+    const bool valid = __float_as_uint(t) - 0x41d40000u <= 0x46c7cf00u - 0x41d40000u;
     const float ef = valid ? t : 1.0f;
     const float m = ef + 8388608.0f;  // 2^23: the integer lands in the low mantissa bits
-    if (kValidate) bad |= (m - 8388608.0f != ef);
+    if (kValidate) {
+        // exact test that 256 v is an integer: K = round(256 v) via the 2^23 trick, residual 256 v - K by one FMA
+        // (t itself may round a near-grid value onto the grid, so it cannot be used for this)
+        const float K = fmaf(v, 256.0f, 8388608.0f) - 8388608.0f;
+        bad |= valid & (fmaf(v, 256.0f, -K) != 0.0f);
+    }
     return __float_as_uint(m);
 }
 template <bool kValidate>
@@ -156,10 +169,10 @@ __device__ __forceinline__ uint4 blend(uint4 v, uint4 m, uint32_t ident) {
 }
 
 template <int R, bool kIsMax, bool kBorder>
-__device__ __forceinline__ void v_pass(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, const Tile& t,
+__device__ __forceinline__ void v_pass(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, const Tile& t, Items i,
                                        uint32_t ident_next) {
-    for (Items i(t.RQ); i.r < t.RH; i.next()) {
-        const int off = (i.r * t.RQ + i.q) * 4;
+    for (; i.r < t.RH; i.next()) {
+        const int off = i.lin * 4;
         uint4 acc;
         if (kBorder && outside(t, i.r, i.q)) {
             acc = splat4(ident_next);
@@ -182,10 +195,10 @@ __device__ __forceinline__ void v_pass(const uint32_t* __restrict__ src, uint32_
 
 // horizontal 5-window: out_j = ext(P_{j-1}, R_j, P_j, R_{j+1}, P_{j+1}),  R_j = (c_{2j-1}, c_{2j})
 template <bool kIsMax, bool kBorder>
-__device__ __forceinline__ void h5_pass(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, const Tile& t,
+__device__ __forceinline__ void h5_pass(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, const Tile& t, Items i,
                                         uint32_t ident_next) {
-    for (Items i(t.RQ); i.r < t.RH; i.next()) {
-        const int off = (i.r * t.RQ + i.q) * 4;
+    for (; i.r < t.RH; i.next()) {
+        const int off = i.lin * 4;
         uint4 o;
         if (kBorder && outside(t, i.r, i.q)) {
             o = splat4(ident_next);
@@ -229,10 +242,10 @@ __device__ __forceinline__ uint32_t fill_holes(uint32_t d, uint32_t t) {
 }
 
 template <bool kBorder>
-__device__ __forceinline__ void front_passes(uint32_t* A, uint32_t* B, const Tile& t) {
+__device__ __forceinline__ void front_passes(uint32_t* A, uint32_t* B, const Tile& t, const Items& it0) {
     // ---- pass 1: 2-tap dilate (:71-80)  out(y,x) = max(in(y-1,x+1), in(y+2,x+2)), absent taps = -FLT_MAX (e = 0)
-    for (Items i(t.RQ); i.r < t.RH; i.next()) {
-        const int off = (i.r * t.RQ + i.q) * 4;
+    for (Items i = it0; i.r < t.RH; i.next()) {
+        const int off = i.lin * 4;
         uint4 o;
         if (kBorder && outside(t, i.r, i.q)) {
             o = splat4(kAbsMax);
@@ -252,27 +265,28 @@ __device__ __forceinline__ void front_passes(uint32_t* A, uint32_t* B, const Til
     }
     __syncthreads();
     // ---- passes 2-5: close5 (:84-85) = dilate5 (V, H) then erode5 (H, V)
-    v_pass<2, true, kBorder>(B, A, t, kAbsMax);
+    v_pass<2, true, kBorder>(B, A, t, it0, kAbsMax);
     __syncthreads();
-    h5_pass<true, kBorder>(A, B, t, kAbsMin);
+    h5_pass<true, kBorder>(A, B, t, it0, kAbsMin);
     __syncthreads();
-    h5_pass<false, kBorder>(B, A, t, kAbsMin);
+    h5_pass<false, kBorder>(B, A, t, it0, kAbsMin);
     __syncthreads();
-    v_pass<2, false, kBorder>(A, B, t, kAbsMax);  // B = D, the closed image
+    v_pass<2, false, kBorder>(A, B, t, it0, kAbsMax);  // B = D, the closed image
     __syncthreads();
     // ---- pass 6: vertical half of dilate7 (:88-90)
-    v_pass<3, true, kBorder>(B, A, t, kAbsMax);
+    v_pass<3, true, kBorder>(B, A, t, it0, kAbsMax);
     __syncthreads();
 }
 
 template <bool kValidate>
-__device__ __forceinline__ void front_load(const FrontArgs& a, const float* in, uint32_t* A, const Tile& t, int gy0, int gx0,
+__device__ __forceinline__ void front_load(const FrontArgs& a, const float* in0, uint32_t* A, const Tile& t, Items i, int gx0,
                                            int& bad) {
-    for (Items i(t.RQ); i.r < t.RH; i.next()) {
+    // in0 points at region cell (0, 0) of the frame (possibly outside the buffer: only in-image cells are read)
+    const int pitch = (int)a.in_pitch;
+    for (; i.r < t.RH; i.next()) {
         uint4 o = splat4(kAbsMax);  // outside the image: absent
         if (!outside(t, i.r, i.q)) {
-            const int gx = gx0 + i.q * 8;
-            const float* p = in + (size_t)(gy0 + i.r) * a.in_pitch + gx;
+            const float* p = in0 + (i.r * pitch + i.q * 8);
             if (i.q != t.qs && a.vec_ok) {
                 const float4 f0 = __ldg(reinterpret_cast<const float4*>(p)), f1 = __ldg(reinterpret_cast<const float4*>(p) + 1);
                 o.x = encode_pair<kValidate>(f0.x, f0.y, bad);
@@ -280,17 +294,18 @@ __device__ __forceinline__ void front_load(const FrontArgs& a, const float* in, 
                 o.z = encode_pair<kValidate>(f1.x, f1.y, bad);
                 o.w = encode_pair<kValidate>(f1.z, f1.w, bad);
             } else {
+                const int gx = gx0 + i.q * 8;
                 uint32_t e[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) e[j] = gx + j < a.cols ? (encode_bits<kValidate>(__ldg(p + j), bad) & 0xffffu) : 0u;
                 o = make_uint4(e[0] | (e[1] << 16), e[2] | (e[3] << 16), e[4] | (e[5] << 16), e[6] | (e[7] << 16));
             }
         }
-        sts4(A + (i.r * t.RQ + i.q) * 4, o);
+        sts4(A + i.lin * 4, o);
     }
 }
 
-__global__ void __launch_bounds__(QT) k_q8_front(FrontArgs a) {
+__global__ void __launch_bounds__(QT, 3) k_q8_front(FrontArgs a) {
     DCMT_DYN_SMEM(uint32_t, smem);
     const int th = a.th, tw = a.tw, rows = a.rows, cols = a.cols;
     Tile t;
@@ -306,19 +321,20 @@ __global__ void __launch_bounds__(QT) k_q8_front(FrontArgs a) {
     t.rlo = max(0, -gy0);
     t.rhi = min(t.RH, rows - gy0);
     tile_columns(t, gx0, cols);
-    const float* in = a.in + (size_t)frame * a.in_fstride;
+    const float* in0 = a.in + (size_t)frame * a.in_fstride + ((ptrdiff_t)gy0 * (ptrdiff_t)a.in_pitch + gx0);
     const bool border = gy0 < 0 || gy0 + t.RH > rows || gx0 < 0 || gx0 + t.RQ * 8 > cols;
+    const Items it_rq(t.RQ);
 
     // ---- pass 0: load, validate, invert, encode (:55-67)
     int bad = 0;
-    if (a.validate) front_load<true>(a, in, A, t, gy0, gx0, bad);
-    else front_load<false>(a, in, A, t, gy0, gx0, bad);
+    if (a.validate) front_load<true>(a, in0, A, t, it_rq, gx0, bad);
+    else front_load<false>(a, in0, A, t, it_rq, gx0, bad);
     if (__syncthreads_or(bad)) {  // not strict q8: this frame is redone by the generic pipeline
         if (threadIdx.x == 0) a.ctr[frame].needs_generic = 1;
         return;
     }
-    if (border) front_passes<true>(A, B, t);
-    else front_passes<false>(A, B, t);
+    if (border) front_passes<true>(A, B, t, it_rq);
+    else front_passes<false>(A, B, t, it_rq);
 
     // ---- pass 7: horizontal half of dilate7, hole fill (:92-100), store the core
     const int CQ = tw / 8;
@@ -467,18 +483,19 @@ __global__ void __launch_bounds__(QT, 2) k_q8_tail(TailArgs a) {
     t.rhi = min(RH, rows - gy0);
     tile_columns(t, gx0, cols);
     {
-        const uint16_t* mp = mid + (ptrdiff_t)gy0 * (ptrdiff_t)a.mid_pitch + gx0;
+        const uint16_t* mp = mid + ((ptrdiff_t)gy0 * (ptrdiff_t)a.mid_pitch + gx0);
+        const int mpitch = (int)a.mid_pitch;
         if (!border) {
             for (Items i(RQ); i.r < RH; i.next())
-                sts4(A + (i.r * RQ + i.q) * 4, __ldg(reinterpret_cast<const uint4*>(mp + (size_t)i.r * a.mid_pitch + i.q * 8)));
+                sts4(A + i.lin * 4, __ldg(reinterpret_cast<const uint4*>(mp + (i.r * mpitch + i.q * 8))));
         } else {
             for (Items i(RQ); i.r < RH; i.next()) {
                 uint4 v = splat4(kAbsMax);
                 if (!outside(t, i.r, i.q)) {
-                    v = __ldg(reinterpret_cast<const uint4*>(mp + (ptrdiff_t)i.r * (ptrdiff_t)a.mid_pitch + i.q * 8));
+                    v = __ldg(reinterpret_cast<const uint4*>(mp + (i.r * mpitch + i.q * 8)));
                     if (i.q == t.qs) v = blend(v, t.smask, kAbsMax);
                 }
-                sts4(A + (i.r * RQ + i.q) * 4, v);
+                sts4(A + i.lin * 4, v);
             }
         }
     }
@@ -679,46 +696,58 @@ __global__ void __launch_bounds__(QT, 2) k_q8_tail(TailArgs a) {
         }
         __syncthreads();
     }
-    // ---- A9 + A10: 5x5 Gaussian [1 4 6 4 1]^2 / 256 in integer q16 where the median is valid (:176-189), final
-    //      inversion (:191-202), float32 store.  One item = one quad (8 pixels) of one row: vertical sums of the
-    //      12 columns it touches, then the horizontal combination in registers.
-    const int CQ = tw / 8;
-    for (Items i(CQ); i.r < th; i.next()) {
-        const int gy = y0 + i.r, gx = x0 + i.q * 8;
-        if (gy >= rows || gx >= cols) continue;
-        const uint32_t* p = B + (TV + i.r) * pitchw + (TQ + i.q) * 4;  // centre row, first word of the quad
-        uint32_t f[8];
-        if (a.blur == 1) {
-            uint32_t g[12];  // vertical [1 4 6 4 1] sums of columns gx-2 .. gx+9 (words -1 .. 4)
+    // ---- A9 + A10: 5x5 Gaussian [1 4 6 4 1]^2 / 256 in integer q16 (:176-189), final inversion (:191-202), float32
+    //      store.  One item = 4 pixels (two words) x 4 rows: the horizontal [1 4 6 4 1] sums of the 8 rows it touches
+    //      come straight from the packed words with 16-bit x 8-bit dot products (IDP.2A), the vertical combination
+    //      runs on those 32-bit sums in registers.  Every pixel is valid here (a frame with holes left is redone by
+    //      k_q8_fixup), so the masked copy (:181-188) always takes the blurred value and the inversion always
+    //      applies:  out16 = 6553600 - (g - 256)  with e = q + 1 and weights summing to 256.
+    {
+        const int NP = tw / 4, NGR = (th + 3) / 4;
+        for (Items i(NP); i.r < NGR; i.next()) {
+            const int cy0 = i.r * 4, gx = x0 + i.q * 4;
+            if (y0 + cy0 >= rows || gx >= cols) continue;
+            const uint32_t* p = B + (TV + cy0) * pitchw + TQ * 4 + 2 * i.q;  // row cy0, first word of the pair
+            float* o = out + (size_t)(y0 + cy0) * a.out_pitch + gx;
+            uint32_t f[4][4];
+            if (a.blur == 1) {
+                uint32_t h[8][4];
 #pragma unroll
-            for (int j = 0; j < 6; ++j) {
-                const uint32_t* c = p + (j - 1);
-                const uint32_t m2 = c[-2 * pitchw], m1 = c[-pitchw], c0 = c[0], p1 = c[pitchw], p2 = c[2 * pitchw];
-                const uint32_t so = __vadd2(m2, p2), si = __vadd2(m1, p1);  // <= 51202 per lane: no overflow
-                g[2 * j] = (so & 0xffffu) + 4u * (si & 0xffffu) + 6u * (c0 & 0xffffu);
-                g[2 * j + 1] = (so >> 16) + 4u * (si >> 16) + 6u * (c0 >> 16);
+                for (int k = 0; k < 8; ++k) {  // input rows cy0-2 .. cy0+5
+                    const uint32_t* q = p + (k - 2) * pitchw;
+                    const uint32_t wa = q[-1], wb = q[0], wc = q[1], wd = q[2];
+                    h[k][0] = __dp2a_lo(wa, 0x0401u, __dp2a_lo(wb, 0x0406u, __dp2a_lo(wc, 0x0001u, 0u)));
+                    h[k][1] = __dp2a_lo(wa, 0x0100u, __dp2a_lo(wb, 0x0604u, __dp2a_lo(wc, 0x0104u, 0u)));
+                    h[k][2] = __dp2a_lo(wb, 0x0401u, __dp2a_lo(wc, 0x0406u, __dp2a_lo(wd, 0x0001u, 0u)));
+                    h[k][3] = __dp2a_lo(wb, 0x0100u, __dp2a_lo(wc, 0x0604u, __dp2a_lo(wd, 0x0104u, 0u)));
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        f[j][c] = 6553856u - ((h[j][c] + h[j + 4][c]) + 4u * (h[j + 1][c] + h[j + 3][c]) + 6u * h[j + 2][c]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t w0 = p[j * pitchw], w1 = p[j * pitchw + 1];
+                    f[j][0] = 6553856u - ((w0 & 0xffffu) << 8);  // 6553600 - ((e - 1) << 8)
+                    f[j][1] = 6553856u - ((w0 >> 16) << 8);
+                    f[j][2] = 6553856u - ((w1 & 0xffffu) << 8);
+                    f[j][3] = 6553856u - ((w1 >> 16) << 8);
+                }
             }
-            // Every pixel is valid here (a frame with holes left is redone by k_q8_fixup), so the masked copy
-            // (:181-188) always takes the blurred value and the final inversion (:191-202) always applies:
-            // out16 = 6553600 - (gg - 256) with e = q + 1 and weights summing to 256.
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
-                f[k] = 6553856u - ((g[k] + g[k + 4]) + 4u * (g[k + 1] + g[k + 3]) + 6u * g[k + 2]);  // centre column gx + k
-        } else {
+            for (int j = 0; j < 4; ++j) {
+                if (y0 + cy0 + j >= rows) break;
+                float* oj = o + (size_t)j * a.out_pitch;
+                if (gx + 4 <= cols && a.vec_ok) {
+                    *reinterpret_cast<float4*>(oj) = make_float4(finish_px(f[j][0]), finish_px(f[j][1]), finish_px(f[j][2]), finish_px(f[j][3]));
+                } else {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const uint32_t word = p[k >> 1];
-                f[k] = 6553856u - (((k & 1) ? (word >> 16) : (word & 0xffffu)) << 8);  // 6553600 - ((e - 1) << 8)
+                    for (int c = 0; c < 4; ++c)
+                        if (gx + c < cols) oj[c] = finish_px(f[j][c]);
+                }
             }
-        }
-        float* o = out + (size_t)gy * a.out_pitch + gx;
-        if (gx + 8 <= cols && a.vec_ok) {
-            reinterpret_cast<float4*>(o)[0] = make_float4(finish_px(f[0]), finish_px(f[1]), finish_px(f[2]), finish_px(f[3]));
-            reinterpret_cast<float4*>(o)[1] = make_float4(finish_px(f[4]), finish_px(f[5]), finish_px(f[6]), finish_px(f[7]));
-        } else {
-#pragma unroll
-            for (int k = 0; k < 8; ++k)
-                if (gx + k < cols) o[k] = finish_px(f[k]);
         }
     }
 }

@@ -165,6 +165,8 @@ static inline unsigned __vcmpgeu2(unsigned a, unsigned b) { return ~__vcmpltu2(a
 static inline unsigned __vcmpeq2(unsigned a, unsigned b) {
     return (((a & 0xffffu) == (b & 0xffffu)) ? 0xffffu : 0u) | (((a >> 16) == (b >> 16)) ? 0xffff0000u : 0u);
 }
+static inline unsigned __dp2a_lo(unsigned a, unsigned b, unsigned c) { return c + (a & 0xffffu) * (b & 0xffu) + (a >> 16) * ((b >> 8) & 0xffu); }
+static inline unsigned __dp2a_hi(unsigned a, unsigned b, unsigned c) { return c + (a & 0xffffu) * ((b >> 16) & 0xffu) + (a >> 16) * (b >> 24); }
 static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned s) {
     unsigned long long v = ((unsigned long long)b << 32) | a;
     unsigned r = 0;

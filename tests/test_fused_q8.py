@@ -54,6 +54,17 @@ def body_boundary_values(be):
     s2 = s.copy()
     s2[7, 9] = np.float32(12.3)  # a valid pixel that is not a multiple of 1/256: generic pipeline
     check(be, s2, "one non-q8 valid pixel", want_path=0)
+    # slivers next to the thresholds where a non-q8 value is valid for the reference: must be caught, not mapped to a hole
+    for v in (0.1, np.nextafter(np.float32(0.1015625), np.float32(0)), 99.899, 99.8999, np.nextafter(np.float32(99.9), np.float32(0)),
+              np.nextafter(np.float32(36.00390625), np.float32(0)), np.nextafter(np.float32(12.5), np.float32(100))):
+        s3 = base.astype(np.float32) / np.float32(256)
+        s3[11, 13] = np.float32(v)
+        check(be, s3, f"sliver value {v!r}", want_path=0)
+    # ... and just outside them the pixel is a hole for the reference too (either path is fine, the bytes must match)
+    for v in (0.0999, 99.9, 99.95, 100.0, 250.0):
+        s3 = base.astype(np.float32) / np.float32(256)
+        s3[11, 13] = np.float32(v)
+        check(be, s3, f"hole-class value {v!r}", want_path=None)
 
 
 def body_routing(be):

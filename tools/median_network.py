@@ -86,6 +86,40 @@ def initial_network():
     return net, cand[6]
 
 
+def oddeven_merge_lists(a, b):
+    """Batcher odd-even merge of two sorted wire lists (any lengths); returns (comparators, merged wire order)."""
+    if not a:
+        return [], list(b)
+    if not b:
+        return [], list(a)
+    if len(a) == 1 and len(b) == 1:
+        return [(a[0], b[0])], [a[0], b[0]]
+    ce, ev = oddeven_merge_lists(a[0::2], b[0::2])
+    co, od = oddeven_merge_lists(a[1::2], b[1::2])
+    net = ce + co
+    out = [ev[0]]
+    i = 1
+    j = 0
+    # interleave: compare od[j] with ev[i]
+    while i < len(ev) and j < len(od):
+        net.append((od[j], ev[i]))
+        out += [od[j], ev[i]]
+        i += 1
+        j += 1
+    out += ev[i:] + od[j:]
+    return net, out
+
+
+def merge_tree_network():
+    """merge the five sorted columns pairwise with odd-even merges, take rank 12 of the final order"""
+    cols = [[5 * c + r for r in range(5)] for c in range(5)]
+    n1, s01 = oddeven_merge_lists(cols[0], cols[1])
+    n2, s23 = oddeven_merge_lists(cols[2], cols[3])
+    n3, s0123 = oddeven_merge_lists(s01, s23)
+    n4, sall = oddeven_merge_lists(s0123, cols[4])
+    return n1 + n2 + n3 + n4, sall[12]
+
+
 def prune(net, out, rng):
     """remove comparators (random order) while the network stays correct"""
     net = list(net)
@@ -151,7 +185,7 @@ def search(seconds, seed):
     import time
 
     rng = random.Random(seed)
-    net, out = initial_network()
+    net, out = merge_tree_network() if seed % 2 else initial_network()
     assert run(net, out), "initial network wrong"
     best = prune(net, out, rng)
     best_cost = count_ops(best, out)
