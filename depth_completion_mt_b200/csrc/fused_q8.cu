@@ -91,7 +91,7 @@ struct Items {
 // or overwrites them), so their exact value never reaches the output.  What must hold for the integer pipeline to
 // be exact is that every VALID pixel is a multiple of 1/256: kValidate checks it (the add of 2^23 must not round).
 template <bool kValidate>
-__device__ __forceinline__ uint32_t encode_bits(float v, int& bad) {
+__device__ __forceinline__ uint32_t encode_bits(float v, float& bad) {
     const float t = fmaf(v, -256.0f, 25601.0f);  // 25601 - 256 v, exact for q8 input
     // valid <=> 26.5 <= t <= 25575.5 in ONE unsigned compare (positive floats order like their bit patterns; smaller,
     // negative and NaN t wrap to huge values).  For q8 input t is an integer, so this is exactly 27 <= t <= 25575,
@@ -105,12 +105,13 @@ __device__ __forceinline__ uint32_t encode_bits(float v, int& bad) {
         // exact test that 256 v is an integer: K = round(256 v) via the 2^23 trick, residual 256 v - K by one FMA
         // (t itself may round a near-grid value onto the grid, so it cannot be used for this)
         const float K = fmaf(v, 256.0f, 8388608.0f) - 8388608.0f;
-        bad |= valid & (fmaf(v, 256.0f, -K) != 0.0f);
+        const float res = valid ? fmaf(v, 256.0f, -K) : 0.0f;
+        bad = fmaf(res, res, bad);  // stays 0 iff every valid pixel seen so far is on the grid
     }
     return __float_as_uint(m);
 }
 template <bool kValidate>
-__device__ __forceinline__ uint32_t encode_pair(float v0, float v1, int& bad) {
+__device__ __forceinline__ uint32_t encode_pair(float v0, float v1, float& bad) {
     return __byte_perm(encode_bits<kValidate>(v0, bad), encode_bits<kValidate>(v1, bad), 0x5410);
 }
 
@@ -168,52 +169,62 @@ __device__ __forceinline__ uint4 blend(uint4 v, uint4 m, uint32_t ident) {
     return make_uint4((v.x & m.x) | (ident & ~m.x), (v.y & m.y) | (ident & ~m.y), (v.z & m.z) | (ident & ~m.z), (v.w & m.w) | (ident & ~m.w));
 }
 
-template <int R, bool kIsMax, bool kBorder>
-__device__ __forceinline__ void v_pass(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, const Tile& t, Items i,
-                                       uint32_t ident_next) {
-    for (; i.r < t.RH; i.next()) {
-        const int off = i.lin * 4;
-        uint4 acc;
-        if (kBorder && outside(t, i.r, i.q)) {
-            acc = splat4(ident_next);
-        } else {
-            const uint32_t* p = src + off;
-            acc = lds4(p);
+// Cells outside the image must hold the identity of the operator that reads them next.  The passes below compute
+// every cell of the region without testing; tiles that touch the image border then patch the outside strips
+// (whole rows, whole quads, and the lanes of the quad straddling the right edge) -- a few hundred cells.
+__device__ __forceinline__ void patch_outside(uint32_t* __restrict__ P, const Tile& t, uint32_t ident) {
+    const uint4 id4 = splat4(ident);
+    const int nro = t.rlo + (t.RH - t.rhi), nri = t.rhi - t.rlo, nco = t.qlo + (t.RQ - t.qhi);
+    for (int it = threadIdx.x; it < nro * t.RQ; it += QT) {
+        const int k = it / t.RQ, q = it - k * t.RQ;
+        const int r = k < t.rlo ? k : t.rhi + (k - t.rlo);
+        sts4(P + (r * t.RQ + q) * 4, id4);
+    }
+    for (int it = threadIdx.x; it < nri * nco; it += QT) {
+        const int rr = it / nco, k = it - rr * nco;
+        const int q = k < t.qlo ? k : t.qhi + (k - t.qlo);
+        sts4(P + ((t.rlo + rr) * t.RQ + q) * 4, id4);
+    }
+    if (t.qs >= 0)
+        for (int rr = threadIdx.x; rr < nri; rr += QT) {
+            uint32_t* p = P + ((t.rlo + rr) * t.RQ + t.qs) * 4;
+            sts4(p, blend(lds4(p), t.smask, ident));
+        }
+}
+
+template <int R, bool kIsMax>
+__device__ __forceinline__ void v_pass(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, const Tile& t) {
+    const int n4 = t.RH * t.RQ * 4;
+    for (int off = threadIdx.x * 4; off < n4; off += QT * 4) {
+        const uint32_t* p = src + off;
+        uint4 acc = lds4(p);
 #pragma unroll
-            for (int d = 1; d <= R; ++d) {
-                const uint4 up = lds4(p - d * t.pitchw), dn = lds4(p + d * t.pitchw);
-                acc.x = pext3<kIsMax>(acc.x, up.x, dn.x);
-                acc.y = pext3<kIsMax>(acc.y, up.y, dn.y);
-                acc.z = pext3<kIsMax>(acc.z, up.z, dn.z);
-                acc.w = pext3<kIsMax>(acc.w, up.w, dn.w);
-            }
-            if (kBorder && i.q == t.qs) acc = blend(acc, t.smask, ident_next);
+        for (int d = 1; d <= R; ++d) {
+            const uint4 up = lds4(p - d * t.pitchw), dn = lds4(p + d * t.pitchw);
+            acc.x = pext3<kIsMax>(acc.x, up.x, dn.x);
+            acc.y = pext3<kIsMax>(acc.y, up.y, dn.y);
+            acc.z = pext3<kIsMax>(acc.z, up.z, dn.z);
+            acc.w = pext3<kIsMax>(acc.w, up.w, dn.w);
         }
         sts4(dst + off, acc);
     }
 }
 
 // horizontal 5-window: out_j = ext(P_{j-1}, R_j, P_j, R_{j+1}, P_{j+1}),  R_j = (c_{2j-1}, c_{2j})
-template <bool kIsMax, bool kBorder>
-__device__ __forceinline__ void h5_pass(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, const Tile& t, Items i,
-                                        uint32_t ident_next) {
-    for (; i.r < t.RH; i.next()) {
-        const int off = i.lin * 4;
+template <bool kIsMax>
+__device__ __forceinline__ void h5_pass(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, const Tile& t) {
+    const int n4 = t.RH * t.RQ * 4;
+    for (int off = threadIdx.x * 4; off < n4; off += QT * 4) {
+        const uint32_t* p = src + off;
+        const uint4 c = lds4(p);
+        const uint32_t wl = p[-1], wr = p[4];
+        const uint32_t r0 = odd_pair(wl, c.x), r1 = odd_pair(c.x, c.y), r2 = odd_pair(c.y, c.z), r3 = odd_pair(c.z, c.w),
+                       r4 = odd_pair(c.w, wr);
         uint4 o;
-        if (kBorder && outside(t, i.r, i.q)) {
-            o = splat4(ident_next);
-        } else {
-            const uint32_t* p = src + off;
-            const uint4 c = lds4(p);
-            const uint32_t wl = p[-1], wr = p[4];
-            const uint32_t r0 = odd_pair(wl, c.x), r1 = odd_pair(c.x, c.y), r2 = odd_pair(c.y, c.z), r3 = odd_pair(c.z, c.w),
-                           r4 = odd_pair(c.w, wr);
-            o.x = pext3<kIsMax>(pext3<kIsMax>(wl, r0, c.x), r1, c.y);
-            o.y = pext3<kIsMax>(pext3<kIsMax>(c.x, r1, c.y), r2, c.z);
-            o.z = pext3<kIsMax>(pext3<kIsMax>(c.y, r2, c.z), r3, c.w);
-            o.w = pext3<kIsMax>(pext3<kIsMax>(c.z, r3, c.w), r4, wr);
-            if (kBorder && i.q == t.qs) o = blend(o, t.smask, ident_next);
-        }
+        o.x = pext3<kIsMax>(pext3<kIsMax>(wl, r0, c.x), r1, c.y);
+        o.y = pext3<kIsMax>(pext3<kIsMax>(c.x, r1, c.y), r2, c.z);
+        o.z = pext3<kIsMax>(pext3<kIsMax>(c.y, r2, c.z), r3, c.w);
+        o.w = pext3<kIsMax>(pext3<kIsMax>(c.z, r3, c.w), r4, wr);
         sts4(dst + off, o);
     }
 }
@@ -241,46 +252,48 @@ __device__ __forceinline__ uint32_t fill_holes(uint32_t d, uint32_t t) {
     return __vadd2(pmin(__vadd2(t, k), __vadd2(d, k)), SPLAT16(27));
 }
 
-template <bool kBorder>
-__device__ __forceinline__ void front_passes(uint32_t* A, uint32_t* B, const Tile& t, const Items& it0) {
+// barrier, and for border tiles the patch of the plane just written + another barrier
+__device__ __forceinline__ void pass_end(uint32_t* written, const Tile& t, bool border, uint32_t ident_next) {
+    __syncthreads();
+    if (border) {
+        patch_outside(written, t, ident_next);
+        __syncthreads();
+    }
+}
+
+__device__ __forceinline__ void front_passes(uint32_t* A, uint32_t* B, const Tile& t, bool border) {
     // ---- pass 1: 2-tap dilate (:71-80)  out(y,x) = max(in(y-1,x+1), in(y+2,x+2)), absent taps = -FLT_MAX (e = 0)
-    for (Items i = it0; i.r < t.RH; i.next()) {
-        const int off = i.lin * 4;
-        uint4 o;
-        if (kBorder && outside(t, i.r, i.q)) {
-            o = splat4(kAbsMax);
-        } else {
-            const uint32_t* pa = A + off - t.pitchw;      // row y-1
-            const uint32_t* pb = A + off + 2 * t.pitchw;  // row y+2
-            const uint4 ca = lds4(pa), cb = lds4(pb);
-            const uint32_t na = pa[4], nb = pb[4];
-            // tap 1: pixels (x+1, x+2) of row y-1; tap 2: pixels (x+2, x+3) of row y+2
-            o.x = pmax(odd_pair(ca.x, ca.y), cb.y);
-            o.y = pmax(odd_pair(ca.y, ca.z), cb.z);
-            o.z = pmax(odd_pair(ca.z, ca.w), cb.w);
-            o.w = pmax(odd_pair(ca.w, na), nb);
-            if (kBorder && i.q == t.qs) o = blend(o, t.smask, kAbsMax);
-        }
+    const int n4 = t.RH * t.RQ * 4;
+    for (int off = threadIdx.x * 4; off < n4; off += QT * 4) {
+        const uint32_t* pa = A + off - t.pitchw;      // row y-1
+        const uint32_t* pb = A + off + 2 * t.pitchw;  // row y+2
+        const uint4 ca = lds4(pa), cb = lds4(pb);
+        const uint32_t na = pa[4], nb = pb[4];
+        uint4 o;  // tap 1: pixels (x+1, x+2) of row y-1; tap 2: pixels (x+2, x+3) of row y+2
+        o.x = pmax(odd_pair(ca.x, ca.y), cb.y);
+        o.y = pmax(odd_pair(ca.y, ca.z), cb.z);
+        o.z = pmax(odd_pair(ca.z, ca.w), cb.w);
+        o.w = pmax(odd_pair(ca.w, na), nb);
         sts4(B + off, o);
     }
-    __syncthreads();
+    pass_end(B, t, border, kAbsMax);
     // ---- passes 2-5: close5 (:84-85) = dilate5 (V, H) then erode5 (H, V)
-    v_pass<2, true, kBorder>(B, A, t, it0, kAbsMax);
-    __syncthreads();
-    h5_pass<true, kBorder>(A, B, t, it0, kAbsMin);
-    __syncthreads();
-    h5_pass<false, kBorder>(B, A, t, it0, kAbsMin);
-    __syncthreads();
-    v_pass<2, false, kBorder>(A, B, t, it0, kAbsMax);  // B = D, the closed image
-    __syncthreads();
+    v_pass<2, true>(B, A, t);
+    pass_end(A, t, border, kAbsMax);
+    h5_pass<true>(A, B, t);
+    pass_end(B, t, border, kAbsMin);
+    h5_pass<false>(B, A, t);
+    pass_end(A, t, border, kAbsMin);
+    v_pass<2, false>(A, B, t);  // B = D, the closed image
+    pass_end(B, t, border, kAbsMax);
     // ---- pass 6: vertical half of dilate7 (:88-90)
-    v_pass<3, true, kBorder>(B, A, t, it0, kAbsMax);
-    __syncthreads();
+    v_pass<3, true>(B, A, t);
+    pass_end(A, t, border, kAbsMax);
 }
 
 template <bool kValidate>
 __device__ __forceinline__ void front_load(const FrontArgs& a, const float* in0, uint32_t* A, const Tile& t, Items i, int gx0,
-                                           int& bad) {
+                                           float& bad) {
     // in0 points at region cell (0, 0) of the frame (possibly outside the buffer: only in-image cells are read)
     const int pitch = (int)a.in_pitch;
     for (; i.r < t.RH; i.next()) {
@@ -326,15 +339,14 @@ __global__ void __launch_bounds__(QT, 3) k_q8_front(FrontArgs a) {
     const Items it_rq(t.RQ);
 
     // ---- pass 0: load, validate, invert, encode (:55-67)
-    int bad = 0;
+    float bad = 0.0f;
     if (a.validate) front_load<true>(a, in0, A, t, it_rq, gx0, bad);
     else front_load<false>(a, in0, A, t, it_rq, gx0, bad);
-    if (__syncthreads_or(bad)) {  // not strict q8: this frame is redone by the generic pipeline
+    if (__syncthreads_or(bad != 0.0f)) {  // not strict q8: this frame is redone by the generic pipeline
         if (threadIdx.x == 0) a.ctr[frame].needs_generic = 1;
         return;
     }
-    if (border) front_passes<true>(A, B, t, it_rq);
-    else front_passes<false>(A, B, t, it_rq);
+    front_passes(A, B, t, border);
 
     // ---- pass 7: horizontal half of dilate7, hole fill (:92-100), store the core
     const int CQ = tw / 8;
@@ -637,39 +649,51 @@ __global__ void __launch_bounds__(QT, 2) k_q8_tail(TailArgs a) {
         }
         __syncthreads();
     }
-    // ---- A8 median 5x5: sorted columns shared by the two output words of an item + selection network
+    // ---- A8 median 5x5 (:170): one item = four output words of one row.  The six word columns it touches are sorted
+    //      once (9 compare-exchanges each, both lanes at once), the odd-aligned pixel pairs between them come from
+    //      PRMTs of the sorted columns, and each output is the 54-comparator selection network of median_net.cuh on
+    //      its five sorted columns.
     {
-        const int MH = th + 4, MI = tw / 4 + 1;  // rows core +- 2; items of two words covering core +- 1 word
+        const int MH = th + 4, MI = (tw / 2 + 2 + 3) / 4;  // rows core +- 2; items of four words covering core +- 1 word
         const int mr0 = TV - 2, mw0 = TQ * 4 - 1;
         for (Items i(MI); i.r < MH; i.next()) {
-            const int r = mr0 + i.r, w = mw0 + 2 * i.q;  // output words w, w+1; columns w-1 .. w+2
-            uint32_t col[4][5];
-            const uint32_t* p = A + (r - 2) * pitchw + (w - 1);
+            const int r = mr0 + i.r, w = mw0 + 4 * i.q;  // output words w .. w+3; columns w-1 .. w+4
+            uint32_t col[6][5];
+            const uint32_t* p = A + (r - 2) * pitchw + (w - 1);  // w - 1 is even: 8-byte aligned
 #pragma unroll
             for (int k = 0; k < 5; ++k) {
-                const uint2 p0 = *reinterpret_cast<const uint2*>(p + k * pitchw), p1 = *reinterpret_cast<const uint2*>(p + k * pitchw + 2);
-                col[0][k] = p0.x; col[1][k] = p0.y; col[2][k] = p1.x; col[3][k] = p1.y;
+                const uint2 p0 = *reinterpret_cast<const uint2*>(p + k * pitchw), p1 = *reinterpret_cast<const uint2*>(p + k * pitchw + 2),
+                            p2 = *reinterpret_cast<const uint2*>(p + k * pitchw + 4);
+                col[0][k] = p0.x; col[1][k] = p0.y; col[2][k] = p1.x; col[3][k] = p1.y; col[4][k] = p2.x; col[5][k] = p2.y;
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) sort5(col[j]);
-            uint32_t odd[3][5];  // sorted columns of the odd-aligned pixel pairs between the words
+            for (int j = 0; j < 6; ++j) sort5(col[j]);
+            uint32_t res[4];
+            uint32_t oddl[5];  // sorted column of the odd-aligned pair left of the current output word
 #pragma unroll
-            for (int j = 0; j < 3; ++j)
+            for (int k = 0; k < 5; ++k) oddl[k] = odd_pair(col[0][k], col[1][k]);
 #pragma unroll
-                for (int k = 0; k < 5; ++k) odd[j][k] = odd_pair(col[j][k], col[j + 1][k]);
+            for (int o = 0; o < 4; ++o) {
+                uint32_t oddr[5];
 #pragma unroll
-            for (int o = 0; o < 2; ++o) {
+                for (int k = 0; k < 5; ++k) oddr[k] = odd_pair(col[o + 1][k], col[o + 2][k]);
                 uint32_t c[25];
 #pragma unroll
                 for (int k = 0; k < 5; ++k) {
                     c[k] = col[o][k];
-                    c[5 + k] = odd[o][k];
+                    c[5 + k] = oddl[k];
                     c[10 + k] = col[o + 1][k];
-                    c[15 + k] = odd[o + 1][k];
+                    c[15 + k] = oddr[k];
                     c[20 + k] = col[o + 2][k];
                 }
-                B[r * pitchw + w + o] = median25_sorted_columns<PackedOps>(c);
+                res[o] = median25_sorted_columns<PackedOps>(c);
+#pragma unroll
+                for (int k = 0; k < 5; ++k) oddl[k] = oddr[k];
             }
+            uint32_t* q = B + r * pitchw + w;  // w is odd: store as 1 + 2 + 1 words
+            q[0] = res[0];
+            *reinterpret_cast<uint2*>(q + 1) = make_uint2(res[1], res[2]);
+            q[3] = res[3];
         }
     }
     __syncthreads();
@@ -738,7 +762,7 @@ __global__ void __launch_bounds__(QT, 2) k_q8_tail(TailArgs a) {
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                if (y0 + cy0 + j >= rows) break;
+                if (cy0 + j >= th || y0 + cy0 + j >= rows) break;  // rows past the core belong to the next tile
                 float* oj = o + (size_t)j * a.out_pitch;
                 if (gx + 4 <= cols && a.vec_ok) {
                     *reinterpret_cast<float4*>(oj) = make_float4(finish_px(f[j][0]), finish_px(f[j][1]), finish_px(f[j][2]), finish_px(f[j][3]));

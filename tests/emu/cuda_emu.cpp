@@ -120,9 +120,14 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()
     g_body = &body;
     gridDim = grid;
     blockDim = block;
-    for (unsigned bz = 0; bz < grid.z; ++bz)
-        for (unsigned by = 0; by < grid.y; ++by)
-            for (unsigned bx = 0; bx < grid.x; ++bx) {
+    // DCMT_EMU_ORDER=reverse runs the blocks of a grid and the threads of a block in reverse order: results that
+    // depend on block order (two tiles writing one cell) or on thread order (a missing barrier) then change.
+    static const bool reverse = [] { const char* e = std::getenv("DCMT_EMU_ORDER"); return e && e[0] == 'r'; }();
+    const unsigned nblocks = grid.x * grid.y * grid.z;
+    for (unsigned bi = 0; bi < nblocks; ++bi) {
+            {
+                const unsigned b = reverse ? nblocks - 1 - bi : bi;
+                const unsigned bx = b % grid.x, by = (b / grid.x) % grid.y, bz = b / (grid.x * grid.y);
                 blockIdx = uint3{bx, by, bz};
                 std::memset(g_smem, 0xCD, smem_bytes);  // poison: uninitialised shared memory reads show up
                 g_bar_count = g_bar_gen = g_bar_acc = g_bar_result = 0;
@@ -141,7 +146,8 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()
                 g_alive = nthreads;
                 while (alive) {
                     alive = 0;
-                    for (int t = 0; t < nthreads; ++t) {
+                    for (int tt = 0; tt < nthreads; ++tt) {
+                        const int t = reverse ? nthreads - 1 - tt : tt;
                         if (g_done[t]) continue;
                         g_cur = t;
                         threadIdx = uint3{(unsigned)t % block.x, ((unsigned)t / block.x) % block.y,
@@ -151,6 +157,7 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()
                     }
                 }
             }
+    }
     g_body = nullptr;
 }
 }  // namespace dcmt_emu

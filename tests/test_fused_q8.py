@@ -4,6 +4,7 @@ of non-q8 frames to the generic pipeline.  Same bodies on the CPU emulator build
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -117,6 +118,36 @@ def test_emu_multipass(emu_lib):
 
 def test_emu_kitti_frame(emu_lib):
     check(Backend(emu_lib, "emu"), synth.sparse_depth(1, kitti_like=True), "352x1216")
+
+
+def test_emu_reverse_block_and_thread_order():
+    """The emulator normally runs blocks and threads in ascending order, which hides write conflicts between tiles
+    and missing barriers.  Re-run a multi-tile frame whose tile height is not a multiple of the 4-row Gaussian
+    items with both orders reversed (separate process: the order is read once)."""
+    import subprocess
+    import sys
+
+    from tests.conftest import ROOT
+
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "import numpy as np\n"
+        "from depth_completion_mt_b200 import _lib, api, synth\n"
+        "from oracle import c_oracle as co\n"
+        "from tests.emu import build_emu\n"
+        "lib = _lib.bind(build_emu.build())\n"
+        "for (r, c, p, k) in ((200, 333, 0.01, True), (97, 171, 0.05, False), (120, 64, 0.03, False)):\n"
+        "    s = synth.sparse_depth(43, r, c, p, kitti_like=k)\n"
+        "    for blur in ('gaussian', 'none'):\n"
+        "        out = api.img_completion(s, False, blur, lib=lib)\n"
+        "        assert np.array_equal(out.view(np.uint32), co.img_completion(s, blur).view(np.uint32)), (r, c, blur)\n"
+        "    g = api.img_completion(s, False, 'gaussian', path='generic', lib=lib)\n"
+        "    assert np.array_equal(g.view(np.uint32), co.img_completion(s, 'gaussian').view(np.uint32)), (r, c, 'generic')\n"
+        "print('REVERSE_OK')\n" % ROOT
+    )
+    env = dict(os.environ, DCMT_EMU_ORDER="reverse")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900, env=env)
+    assert r.returncode == 0 and "REVERSE_OK" in r.stdout, r.stdout + r.stderr
 
 
 def test_emu_pitched_input_takes_scalar_loads(emu_lib):
