@@ -534,6 +534,42 @@ int dcmt_img_completion_stages_f32(const float* sparse, float* dense, int rows, 
     return rc;
 }
 
+int dcmt_debug_q8_phase_cycles(const float* sparse, float* dense, int rows, int cols, int n_frames, long long* front_stamps,
+                               long long* tail_stamps, int* tiles_per_frame, void* cuda_stream) {
+    // debugging aid: the fused kernels on one chunk with per-CTA clock64() stamps at the phase boundaries
+    if (!sparse || !dense || rows < dcmt::kQ8MinRows || cols < dcmt::kQ8MinCols || n_frames < 1) return fail(DCMT_E_BADARG, "bad argument");
+    int rc = check_device();
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    API_CUDA(dcmt::q8_configure(), "kernel attribute setup");
+    CompletionCall cc{nullptr, 0, false, rows, cols, DCMT_BLUR_GAUSSIAN, DCMT_PATH_AUTO};
+    if (!fused_applies(cc)) return fail(DCMT_E_UNSUPPORTED, "shape not served by the fused kernels");
+    Arena* ar = nullptr;
+    const size_t fpix = (size_t)rows * cols;
+    const size_t mid_pitch = ((size_t)cols + 7) / 8 * 8;
+    const size_t bytes = 2 * carve_bytes(fpix * n_frames, 4) + carve_bytes(n_frames, sizeof(dcmt::FrameCounters)) +
+                         carve_bytes((size_t)rows * mid_pitch * n_frames, 2) + 2 * carve_bytes(mid_pitch * n_frames, 4);
+    if ((rc = arena_acquire(st, bytes, &ar))) return rc;
+    dcmt::Q8Plan p{};
+    p.rows = rows;
+    p.cols = cols;
+    dcmt::q8_choose_tile(rows, cols, &p.th, &p.tw);
+    p.mid_pitch = (int)mid_pitch;
+    p.max_frames = n_frames;
+    p.w1 = carve<float>(ar, fpix * n_frames);
+    p.w2 = carve<float>(ar, fpix * n_frames);
+    p.ctr = carve<dcmt::FrameCounters>(ar, n_frames);
+    p.mid = carve<uint16_t>(ar, (size_t)rows * mid_pitch * n_frames);
+    p.col_first = carve<uint32_t>(ar, mid_pitch * n_frames);
+    p.col_last = carve<uint32_t>(ar, mid_pitch * n_frames);
+    p.prof_front = front_stamps;
+    p.prof_tail = tail_stamps;
+    if (tiles_per_frame) *tiles_per_frame = ((cols + p.tw - 1) / p.tw) * ((rows + p.th - 1) / p.th);
+    API_CUDA(dcmt::q8_run_front(p, sparse, cols, fpix, n_frames, 1, st), "fused front launch");
+    API_CUDA(dcmt::q8_run_tail(p, dense, cols, fpix, n_frames, DCMT_BLUR_GAUSSIAN, st), "fused tail launch");
+    return DCMT_OK;
+}
+
 void dcmt_stereo_params_default(dcmt_stereo_params* p) {
     if (!p) return;
     p->baseline = 0.54f;

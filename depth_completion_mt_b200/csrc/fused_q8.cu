@@ -125,19 +125,24 @@ struct FrontArgs {
     FrameCounters* ctr;
     int rows, cols, th, tw;
     int vec_ok;                   // input rows are 16-byte aligned: float4 loads
-    int validate;                 // check strict q8-ness of the core pixels (DCMT_PATH_AUTO)
+    int validate;                 // check strict q8-ness of every loaded pixel (DCMT_PATH_AUTO)
+    long long* prof;              // optional: 16 clock64() stamps per CTA (debugging aid)
 };
 
 // ------------------------------------------------------------------------------------------------
 // k_q8_front.  Region = core (th x tw) + {up 8, down 9} rows, {left 8, right 16} columns (the dependency cone is
 // up 8 / down 9 / left 7 / right 9; widths are rounded to 8-pixel quads).  Every pass handles (row, quad) items,
-// reads neighbours from one shared-memory plane with 128-bit loads and writes the other plane.  Planes carry FG
-// guard rows above and below so that neighbour reads need no clamping (what is read there only reaches cells
-// outside the dependency cone of the core).  Cells outside the image always hold the identity of the operator
-// that reads them next; tiles whose region lies inside the image (kBorder = false) skip those tests.
+// reads neighbours from one shared-memory plane with 128-bit loads and writes the other plane.  The rows at the
+// region edge that lie outside every dependency cone are simply not computed, so no clamping is needed.  Cells
+// outside the image always hold the identity of the operator that reads them next (per-thread bit masks).
 // ------------------------------------------------------------------------------------------------
 constexpr int FU = 8, FD = 9, FLQ = 1, FRQ = 2;  // rows up/down, quads left/right
-constexpr int FG = 3;                            // guard rows
+
+#define DCMT_STAMP(a, k)                                                                                         \
+    do {                                                                                                         \
+        if ((a).prof && threadIdx.x == 0)                                                                        \
+            (a).prof[((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + (k)] = clock64(); \
+    } while (0)
 
 struct Tile {
     int RH, RQ, pitchw;
@@ -169,64 +174,70 @@ __device__ __forceinline__ uint4 blend(uint4 v, uint4 m, uint32_t ident) {
     return make_uint4((v.x & m.x) | (ident & ~m.x), (v.y & m.y) | (ident & ~m.y), (v.z & m.z) | (ident & ~m.z), (v.w & m.w) | (ident & ~m.w));
 }
 
-// Cells outside the image must hold the identity of the operator that reads them next.  The passes below compute
-// every cell of the region without testing; tiles that touch the image border then patch the outside strips
-// (whole rows, whole quads, and the lanes of the quad straddling the right edge) -- a few hundred cells.
-__device__ __forceinline__ void patch_outside(uint32_t* __restrict__ P, const Tile& t, uint32_t ident) {
-    const uint4 id4 = splat4(ident);
-    const int nro = t.rlo + (t.RH - t.rhi), nri = t.rhi - t.rlo, nco = t.qlo + (t.RQ - t.qhi);
-    for (int it = threadIdx.x; it < nro * t.RQ; it += QT) {
-        const int k = it / t.RQ, q = it - k * t.RQ;
-        const int r = k < t.rlo ? k : t.rhi + (k - t.rlo);
-        sts4(P + (r * t.RQ + q) * 4, id4);
-    }
-    for (int it = threadIdx.x; it < nri * nco; it += QT) {
-        const int rr = it / nco, k = it - rr * nco;
-        const int q = k < t.qlo ? k : t.qhi + (k - t.qlo);
-        sts4(P + ((t.rlo + rr) * t.RQ + q) * 4, id4);
-    }
-    if (t.qs >= 0)
-        for (int rr = threadIdx.x; rr < nri; rr += QT) {
-            uint32_t* p = P + ((t.rlo + rr) * t.RQ + t.qs) * 4;
-            sts4(p, blend(lds4(p), t.smask, ident));
+// Cells outside the image must hold the identity of the operator that reads them next.  Every full-region pass
+// visits the same items per thread (item k of a thread is cell threadIdx.x + k * QT), so each thread computes once
+// which of its items lie outside the image (`out`) or straddle the right edge (`str`) -- one bit per item -- and
+// every pass just tests the bit.  Interior tiles have both masks zero: one code path, no extra barriers.
+struct BorderMasks {
+    uint32_t out, str;
+};
+constexpr int KF = 6;  // items per thread upper bound: region quads <= KF * QT
+
+__device__ __forceinline__ BorderMasks border_masks(const Tile& t, Items i, bool border) {
+    BorderMasks m{0u, 0u};
+    if (border) {
+#pragma unroll
+        for (int k = 0; k < KF; ++k, i.next()) {
+            if (i.r >= t.RH) break;
+            if (outside(t, i.r, i.q)) m.out |= 1u << k;
+            else if (i.q == t.qs) m.str |= 1u << k;
         }
+    }
+    return m;
+}
+
+// One pass over the region: item offsets [lo, hi) are computed by f(off), the edge rows outside every dependency
+// cone are skipped (no clamping, no guard rows: f may read up to the distance those rows provide).
+template <class F>
+__device__ __forceinline__ void region_pass(uint32_t* __restrict__ dst, int n4, int lo, int hi, BorderMasks bm, const Tile& t,
+                                            uint32_t ident_next, F f) {
+    uint32_t mo = bm.out, ms = bm.str;
+#pragma unroll 2
+    for (int off = threadIdx.x * 4; off < n4; off += QT * 4, mo >>= 1, ms >>= 1) {
+        if (off < lo || off >= hi) continue;
+        uint4 v = f(off);
+        if ((mo | ms) & 1u) v = (mo & 1u) ? splat4(ident_next) : blend(v, t.smask, ident_next);
+        sts4(dst + off, v);
+    }
 }
 
 template <int R, bool kIsMax>
-__device__ __forceinline__ void v_pass(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, const Tile& t) {
-    const int n4 = t.RH * t.RQ * 4;
-    for (int off = threadIdx.x * 4; off < n4; off += QT * 4) {
-        const uint32_t* p = src + off;
-        uint4 acc = lds4(p);
+__device__ __forceinline__ uint4 v_window(const uint32_t* __restrict__ p, int pitchw) {
+    uint4 acc = lds4(p);
 #pragma unroll
-        for (int d = 1; d <= R; ++d) {
-            const uint4 up = lds4(p - d * t.pitchw), dn = lds4(p + d * t.pitchw);
-            acc.x = pext3<kIsMax>(acc.x, up.x, dn.x);
-            acc.y = pext3<kIsMax>(acc.y, up.y, dn.y);
-            acc.z = pext3<kIsMax>(acc.z, up.z, dn.z);
-            acc.w = pext3<kIsMax>(acc.w, up.w, dn.w);
-        }
-        sts4(dst + off, acc);
+    for (int d = 1; d <= R; ++d) {
+        const uint4 up = lds4(p - d * pitchw), dn = lds4(p + d * pitchw);
+        acc.x = pext3<kIsMax>(acc.x, up.x, dn.x);
+        acc.y = pext3<kIsMax>(acc.y, up.y, dn.y);
+        acc.z = pext3<kIsMax>(acc.z, up.z, dn.z);
+        acc.w = pext3<kIsMax>(acc.w, up.w, dn.w);
     }
+    return acc;
 }
 
 // horizontal 5-window: out_j = ext(P_{j-1}, R_j, P_j, R_{j+1}, P_{j+1}),  R_j = (c_{2j-1}, c_{2j})
 template <bool kIsMax>
-__device__ __forceinline__ void h5_pass(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, const Tile& t) {
-    const int n4 = t.RH * t.RQ * 4;
-    for (int off = threadIdx.x * 4; off < n4; off += QT * 4) {
-        const uint32_t* p = src + off;
-        const uint4 c = lds4(p);
-        const uint32_t wl = p[-1], wr = p[4];
-        const uint32_t r0 = odd_pair(wl, c.x), r1 = odd_pair(c.x, c.y), r2 = odd_pair(c.y, c.z), r3 = odd_pair(c.z, c.w),
-                       r4 = odd_pair(c.w, wr);
-        uint4 o;
-        o.x = pext3<kIsMax>(pext3<kIsMax>(wl, r0, c.x), r1, c.y);
-        o.y = pext3<kIsMax>(pext3<kIsMax>(c.x, r1, c.y), r2, c.z);
-        o.z = pext3<kIsMax>(pext3<kIsMax>(c.y, r2, c.z), r3, c.w);
-        o.w = pext3<kIsMax>(pext3<kIsMax>(c.z, r3, c.w), r4, wr);
-        sts4(dst + off, o);
-    }
+__device__ __forceinline__ uint4 h5_window(const uint32_t* __restrict__ p) {
+    const uint4 c = lds4(p);
+    const uint32_t wl = p[-1], wr = p[4];
+    const uint32_t r0 = odd_pair(wl, c.x), r1 = odd_pair(c.x, c.y), r2 = odd_pair(c.y, c.z), r3 = odd_pair(c.z, c.w),
+                   r4 = odd_pair(c.w, wr);
+    uint4 o;
+    o.x = pext3<kIsMax>(pext3<kIsMax>(wl, r0, c.x), r1, c.y);
+    o.y = pext3<kIsMax>(pext3<kIsMax>(c.x, r1, c.y), r2, c.z);
+    o.z = pext3<kIsMax>(pext3<kIsMax>(c.y, r2, c.z), r3, c.w);
+    o.w = pext3<kIsMax>(pext3<kIsMax>(c.z, r3, c.w), r4, wr);
+    return o;
 }
 
 // horizontal 7-window max of one quad: out_j = max(R_{j-1}, R_j, R_{j+1}, R_{j+2}, P_{j-1}, P_j, P_{j+1})
@@ -252,81 +263,94 @@ __device__ __forceinline__ uint32_t fill_holes(uint32_t d, uint32_t t) {
     return __vadd2(pmin(__vadd2(t, k), __vadd2(d, k)), SPLAT16(27));
 }
 
-// barrier, and for border tiles the patch of the plane just written + another barrier
-__device__ __forceinline__ void pass_end(uint32_t* written, const Tile& t, bool border, uint32_t ident_next) {
-    __syncthreads();
-    if (border) {
-        patch_outside(written, t, ident_next);
-        __syncthreads();
-    }
-}
-
-__device__ __forceinline__ void front_passes(uint32_t* A, uint32_t* B, const Tile& t, bool border) {
+__device__ __forceinline__ void front_passes(uint32_t* A, uint32_t* B, const Tile& t, BorderMasks bm) {
+    const int n4 = t.RH * t.RQ * 4, pw = t.pitchw;
     // ---- pass 1: 2-tap dilate (:71-80)  out(y,x) = max(in(y-1,x+1), in(y+2,x+2)), absent taps = -FLT_MAX (e = 0)
-    const int n4 = t.RH * t.RQ * 4;
-    for (int off = threadIdx.x * 4; off < n4; off += QT * 4) {
-        const uint32_t* pa = A + off - t.pitchw;      // row y-1
-        const uint32_t* pb = A + off + 2 * t.pitchw;  // row y+2
+    region_pass(B, n4, pw, n4 - 2 * pw, bm, t, kAbsMax, [&](int off) {
+        const uint32_t* pa = A + off - pw;      // row y-1
+        const uint32_t* pb = A + off + 2 * pw;  // row y+2
         const uint4 ca = lds4(pa), cb = lds4(pb);
         const uint32_t na = pa[4], nb = pb[4];
-        uint4 o;  // tap 1: pixels (x+1, x+2) of row y-1; tap 2: pixels (x+2, x+3) of row y+2
-        o.x = pmax(odd_pair(ca.x, ca.y), cb.y);
-        o.y = pmax(odd_pair(ca.y, ca.z), cb.z);
-        o.z = pmax(odd_pair(ca.z, ca.w), cb.w);
-        o.w = pmax(odd_pair(ca.w, na), nb);
-        sts4(B + off, o);
-    }
-    pass_end(B, t, border, kAbsMax);
+        // tap 1: pixels (x+1, x+2) of row y-1; tap 2: pixels (x+2, x+3) of row y+2
+        return make_uint4(pmax(odd_pair(ca.x, ca.y), cb.y), pmax(odd_pair(ca.y, ca.z), cb.z), pmax(odd_pair(ca.z, ca.w), cb.w),
+                          pmax(odd_pair(ca.w, na), nb));
+    });
+    __syncthreads();
     // ---- passes 2-5: close5 (:84-85) = dilate5 (V, H) then erode5 (H, V)
-    v_pass<2, true>(B, A, t);
-    pass_end(A, t, border, kAbsMax);
-    h5_pass<true>(A, B, t);
-    pass_end(B, t, border, kAbsMin);
-    h5_pass<false>(B, A, t);
-    pass_end(A, t, border, kAbsMin);
-    v_pass<2, false>(A, B, t);  // B = D, the closed image
-    pass_end(B, t, border, kAbsMax);
+    region_pass(A, n4, 2 * pw, n4 - 2 * pw, bm, t, kAbsMax, [&](int off) { return v_window<2, true>(B + off, pw); });
+    __syncthreads();
+    region_pass(B, n4, 4, n4 - 4, bm, t, kAbsMin, [&](int off) { return h5_window<true>(A + off); });
+    __syncthreads();
+    region_pass(A, n4, 4, n4 - 4, bm, t, kAbsMin, [&](int off) { return h5_window<false>(B + off); });
+    __syncthreads();
+    region_pass(B, n4, 2 * pw, n4 - 2 * pw, bm, t, kAbsMax, [&](int off) { return v_window<2, false>(A + off, pw); });  // B = D
+    __syncthreads();
     // ---- pass 6: vertical half of dilate7 (:88-90)
-    v_pass<3, true>(B, A, t);
-    pass_end(A, t, border, kAbsMax);
+    region_pass(A, n4, 3 * pw, n4 - 3 * pw, bm, t, kAbsMax, [&](int off) { return v_window<3, true>(B + off, pw); });
+    __syncthreads();
 }
 
+// pass 0: load, validate, invert, encode (:55-67).  Items go in batches of three so that six 16-byte global loads
+// per thread are in flight before the first one is consumed.
 template <bool kValidate>
-__device__ __forceinline__ void front_load(const FrontArgs& a, const float* in0, uint32_t* A, const Tile& t, Items i, int gx0,
-                                           float& bad) {
+__device__ __forceinline__ void front_load(const FrontArgs& a, const float* in0, uint32_t* A, const Tile& t, Items i, BorderMasks bm,
+                                           int gx0, float& bad) {
     // in0 points at region cell (0, 0) of the frame (possibly outside the buffer: only in-image cells are read)
     const int pitch = (int)a.in_pitch;
-    for (; i.r < t.RH; i.next()) {
-        uint4 o = splat4(kAbsMax);  // outside the image: absent
-        if (!outside(t, i.r, i.q)) {
-            const float* p = in0 + (i.r * pitch + i.q * 8);
-            if (i.q != t.qs && a.vec_ok) {
-                const float4 f0 = __ldg(reinterpret_cast<const float4*>(p)), f1 = __ldg(reinterpret_cast<const float4*>(p) + 1);
-                o.x = encode_pair<kValidate>(f0.x, f0.y, bad);
-                o.y = encode_pair<kValidate>(f0.z, f0.w, bad);
-                o.z = encode_pair<kValidate>(f1.x, f1.y, bad);
-                o.w = encode_pair<kValidate>(f1.z, f1.w, bad);
-            } else {
-                const int gx = gx0 + i.q * 8;
+    uint32_t mo = bm.out, ms = bm.str;
+#pragma unroll 1
+    for (int k0 = 0; k0 < KF; k0 += 3) {
+        float4 f0[3], f1[3];
+        const float* ptr[3];
+        int lin[3], gx[3];
+        bool live[3], vec[3], sca[3];
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+            lin[u] = i.lin;
+            live[u] = i.r < t.RH;
+            const bool inside = live[u] && !(mo & 1u);
+            vec[u] = inside && !(ms & 1u) && a.vec_ok;
+            sca[u] = inside && !vec[u];
+            ptr[u] = in0 + (i.r * pitch + i.q * 8);
+            gx[u] = gx0 + i.q * 8;
+            f0[u] = f1[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (vec[u]) {
+                f0[u] = __ldg(reinterpret_cast<const float4*>(ptr[u]));
+                f1[u] = __ldg(reinterpret_cast<const float4*>(ptr[u]) + 1);
+            }
+            i.next();
+            mo >>= 1;
+            ms >>= 1;
+        }
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+            if (!live[u]) continue;
+            uint4 o = splat4(kAbsMax);  // outside the image: absent
+            if (vec[u]) {
+                o.x = encode_pair<kValidate>(f0[u].x, f0[u].y, bad);
+                o.y = encode_pair<kValidate>(f0[u].z, f0[u].w, bad);
+                o.z = encode_pair<kValidate>(f1[u].x, f1[u].y, bad);
+                o.w = encode_pair<kValidate>(f1[u].z, f1[u].w, bad);
+            } else if (sca[u]) {
                 uint32_t e[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) e[j] = gx + j < a.cols ? (encode_bits<kValidate>(__ldg(p + j), bad) & 0xffffu) : 0u;
+                for (int j = 0; j < 8; ++j) e[j] = gx[u] + j < a.cols ? (encode_bits<kValidate>(__ldg(ptr[u] + j), bad) & 0xffffu) : 0u;
                 o = make_uint4(e[0] | (e[1] << 16), e[2] | (e[3] << 16), e[4] | (e[5] << 16), e[6] | (e[7] << 16));
             }
+            sts4(A + lin[u] * 4, o);
         }
-        sts4(A + i.lin * 4, o);
     }
 }
 
-__global__ void __launch_bounds__(QT, 3) k_q8_front(FrontArgs a) {
+__global__ void __launch_bounds__(QT, 2) k_q8_front(FrontArgs a) {
     DCMT_DYN_SMEM(uint32_t, smem);
     const int th = a.th, tw = a.tw, rows = a.rows, cols = a.cols;
     Tile t;
     t.RH = th + FU + FD;
     t.RQ = tw / 8 + FLQ + FRQ;
     t.pitchw = t.RQ * 4;
-    uint32_t* A = smem + FG * t.pitchw;
-    uint32_t* B = A + (t.RH + 2 * FG) * t.pitchw;
+    uint32_t* A = smem;
+    uint32_t* B = A + t.RH * t.pitchw;
     const int frame = blockIdx.z;  // slot == frame offset inside the chunk
     const int y0 = blockIdx.y * th, x0 = blockIdx.x * tw;
     const int gy0 = y0 - FU;
@@ -337,16 +361,19 @@ __global__ void __launch_bounds__(QT, 3) k_q8_front(FrontArgs a) {
     const float* in0 = a.in + (size_t)frame * a.in_fstride + ((ptrdiff_t)gy0 * (ptrdiff_t)a.in_pitch + gx0);
     const bool border = gy0 < 0 || gy0 + t.RH > rows || gx0 < 0 || gx0 + t.RQ * 8 > cols;
     const Items it_rq(t.RQ);
+    const BorderMasks bm = border_masks(t, it_rq, border);
 
-    // ---- pass 0: load, validate, invert, encode (:55-67)
+    DCMT_STAMP(a, 0);
     float bad = 0.0f;
-    if (a.validate) front_load<true>(a, in0, A, t, it_rq, gx0, bad);
-    else front_load<false>(a, in0, A, t, it_rq, gx0, bad);
+    if (a.validate) front_load<true>(a, in0, A, t, it_rq, bm, gx0, bad);
+    else front_load<false>(a, in0, A, t, it_rq, bm, gx0, bad);
     if (__syncthreads_or(bad != 0.0f)) {  // not strict q8: this frame is redone by the generic pipeline
         if (threadIdx.x == 0) a.ctr[frame].needs_generic = 1;
         return;
     }
-    front_passes(A, B, t, border);
+    DCMT_STAMP(a, 1);
+    front_passes(A, B, t, bm);
+    DCMT_STAMP(a, 2);
 
     // ---- pass 7: horizontal half of dilate7, hole fill (:92-100), store the core
     const int CQ = tw / 8;
@@ -365,6 +392,7 @@ __global__ void __launch_bounds__(QT, 3) k_q8_front(FrontArgs a) {
         *reinterpret_cast<uint4*>(mid + (size_t)gy * a.mid_pitch + gx) = d;
     }
     __syncthreads();
+    DCMT_STAMP(a, 3);
     // ---- per-column first / last valid row inside this tile (feeds :103-129), merged across tiles by atomics.
     //      Two threads per column: one searches from the top, one from the bottom.
     const uint16_t* Bh = reinterpret_cast<const uint16_t*>(B);
@@ -392,6 +420,7 @@ __global__ void __launch_bounds__(QT, 3) k_q8_front(FrontArgs a) {
             }
         }
     }
+    DCMT_STAMP(a, 4);
 }
 
 __global__ void k_q8_init_cols(uint32_t* first, uint32_t* last, size_t n) {
@@ -410,11 +439,9 @@ __global__ void k_q8_decode(const uint16_t* __restrict__ mid, size_t mid_pitch, 
 // ------------------------------------------------------------------------------------------------
 // k_q8_tail.  Region = core + 19 rows up/down and 24 columns (3 quads) left/right: 15 (one effective 31x31
 // fill) + 2 (median) + 2 (Gaussian) = 19.  Two shared-memory planes: A = image, B = vertical 16-row maxima,
-// later the median image; B carries 8 guard rows below for the doubling steps.
+// later the median image.
 // ------------------------------------------------------------------------------------------------
 constexpr int TV = 19, TQ = 3;   // rows up/down, quads left/right
-constexpr int TG = 8;            // guard rows below plane B
-constexpr int KIPT = 8;          // register-resident quads per thread in the in-place doubling steps
 constexpr int kListCap = 3072;   // hole words kept for the lazy horizontal fill; more than that: all words are processed
 
 struct TailArgs {
@@ -426,6 +453,7 @@ struct TailArgs {
     float* out;
     size_t out_pitch, out_fstride;
     int rows, cols, th, tw, blur, vec_ok;
+    long long* prof;  // optional: 16 clock64() stamps per CTA (debugging aid)
 };
 
 struct PackedOps {
@@ -474,7 +502,7 @@ __global__ void __launch_bounds__(QT, 2) k_q8_tail(TailArgs a) {
     const int RH = th + 2 * TV, RQ = tw / 8 + 2 * TQ, pitchw = RQ * 4;
     uint32_t* A = smem;
     uint32_t* B = smem + RH * pitchw;
-    uint16_t* list = reinterpret_cast<uint16_t*>(B + (RH + TG) * pitchw);
+    uint16_t* list = reinterpret_cast<uint16_t*>(B + RH * pitchw);
     uint16_t* Ah = reinterpret_cast<uint16_t*>(A);
     uint16_t* Bh = reinterpret_cast<uint16_t*>(B);
     __shared__ int s_count, s_remaining, s_holes_core, s_left_core;
@@ -486,7 +514,9 @@ __global__ void __launch_bounds__(QT, 2) k_q8_tail(TailArgs a) {
     const bool border = gy0 < 0 || gy0 + RH > rows || gx0 < 0 || gx0 + RQ * 8 > cols;
     if (threadIdx.x == 0) { s_count = 0; s_remaining = 0; s_holes_core = 0; s_left_core = 0; }
 
-    // ---- load the A4 plane (outside the image: absent)
+    DCMT_STAMP(a, 0);
+    // ---- load the A4 plane with 16-byte asynchronous copies (outside the image: absent); the per-column keys of
+    //      the A5 step are fetched while the copies are in flight
     Tile t;
     t.RH = RH;
     t.RQ = RQ;
@@ -498,76 +528,68 @@ __global__ void __launch_bounds__(QT, 2) k_q8_tail(TailArgs a) {
         const uint16_t* mp = mid + ((ptrdiff_t)gy0 * (ptrdiff_t)a.mid_pitch + gx0);
         const int mpitch = (int)a.mid_pitch;
         if (!border) {
-            for (Items i(RQ); i.r < RH; i.next())
-                sts4(A + i.lin * 4, __ldg(reinterpret_cast<const uint4*>(mp + (i.r * mpitch + i.q * 8))));
+            for (Items i(RQ); i.r < RH; i.next()) DCMT_CP_ASYNC_16(A + i.lin * 4, mp + (i.r * mpitch + i.q * 8));
         } else {
             for (Items i(RQ); i.r < RH; i.next()) {
-                uint4 v = splat4(kAbsMax);
-                if (!outside(t, i.r, i.q)) {
-                    v = __ldg(reinterpret_cast<const uint4*>(mp + (i.r * mpitch + i.q * 8)));
-                    if (i.q == t.qs) v = blend(v, t.smask, kAbsMax);
-                }
-                sts4(A + i.lin * 4, v);
+                if (outside(t, i.r, i.q)) sts4(A + i.lin * 4, splat4(kAbsMax));
+                else if (i.q == t.qs) sts4(A + i.lin * 4, blend(__ldg(reinterpret_cast<const uint4*>(mp + (i.r * mpitch + i.q * 8))), t.smask, kAbsMax));
+                else DCMT_CP_ASYNC_16(A + i.lin * 4, mp + (i.r * mpitch + i.q * 8));
             }
         }
     }
+    // A5 (:103-129): two threads per region column, one per zone (rows <= first, rows >= last)
+    const int a5_item = threadIdx.x, a5_c = a5_item >> 1, a5_bottom = a5_item & 1;
+    const int a5_gx = gx0 + a5_c;
+    const bool a5_live = a5_item < 2 * RQ * 8 && a5_gx >= 0 && a5_gx < cols;
+    uint32_t a5_kf = 0xffffffffu, a5_kl = 0u;
+    if (a5_live) {
+        a5_kf = __ldg(a.col_first + (size_t)slot * a.mid_pitch + a5_gx);
+        a5_kl = __ldg(a.col_last + (size_t)slot * a.mid_pitch + a5_gx);
+    }
+    DCMT_CP_ASYNC_WAIT_ALL();
     __syncthreads();
-    // ---- A5 column extrapolation (:103-129) from the per-column keys: rows >= last <- value(last), rows <= first
-    //      <- value(first) (the second write wins); empty column <- 100.  Two threads per column, one per zone.
-    for (int it = threadIdx.x; it < 2 * RQ * 8; it += QT) {
-        const int c = it >> 1, bottom = it & 1;
-        const int gx = gx0 + c;
-        if (gx < 0 || gx >= cols) continue;
-        const uint32_t kf = __ldg(a.col_first + (size_t)slot * a.mid_pitch + gx);
-        const uint32_t kl = __ldg(a.col_last + (size_t)slot * a.mid_pitch + gx);
-        const bool empty = kf == 0xffffffffu;
-        const int first = empty ? rows - 1 : (int)(kf >> 16), last = empty ? 0 : (int)(kl >> 16);
-        uint16_t* p = Ah + c;
-        if (!bottom) {  // rows <= first
-            const uint16_t nv = empty ? (uint16_t)E_HUNDRED : (uint16_t)(kf & 0xffffu);
+    DCMT_STAMP(a, 1);
+    // rows >= last <- value(last), rows <= first <- value(first) (the second write wins); empty column <- 100
+    if (a5_live) {
+        const bool empty = a5_kf == 0xffffffffu;
+        const int first = empty ? rows - 1 : (int)(a5_kf >> 16), last = empty ? 0 : (int)(a5_kl >> 16);
+        uint16_t* p = Ah + a5_c;
+        if (!a5_bottom) {
+            const uint16_t nv = empty ? (uint16_t)E_HUNDRED : (uint16_t)(a5_kf & 0xffffu);
             const int r1 = min(RH - 1, first - gy0);
             for (int r = max(0, -gy0); r <= r1; ++r) p[(size_t)r * pitchw * 2] = nv;
-        } else {  // rows >= last that are not <= first
-            const uint16_t mv = empty ? (uint16_t)E_HUNDRED : (uint16_t)(kl & 0xffffu);
+        } else {
+            const uint16_t mv = empty ? (uint16_t)E_HUNDRED : (uint16_t)(a5_kl & 0xffffu);
             const int r1 = min(RH - 1, rows - 1 - gy0);
             for (int r = max(max(0, -gy0), max(last, first + 1) - gy0); r <= r1; ++r) p[(size_t)r * pitchw * 2] = mv;
         }
     }
     __syncthreads();
-    // ---- A6 vertical part: B(r) = max of A over rows r .. r+15 by log-doubling.  Step 1 goes from A to B, steps
-    //      2..4 run in place with the thread's quads held in registers (reads below the plane hit guard rows
-    //      whose content only reaches rows outside the dependency cone).
+    DCMT_STAMP(a, 2);
+    // ---- A6 vertical part: B(r) = max of A over rows r .. r+15 (van Herk / Gil-Werman with blocks of 16 rows).
+    //      One item = one word column x one block: suffix maxima of the block's 16 rows stay in registers, the
+    //      running prefix maximum of the next 15 rows completes every window.  No intermediate planes, one barrier.
     {
-        uint4 v[KIPT];
+        const int NB = (TV + th + 4 + 15) / 16;  // vertical maxima are needed for rows [0, TV + th + 4)
+        for (Items i(pitchw); i.r < NB; i.next()) {
+            const int r0 = 16 * i.r;
+            const uint32_t* p = A + r0 * pitchw + i.q;
+            uint32_t* o = B + r0 * pitchw + i.q;
+            uint32_t sfx[16];
+            sfx[15] = p[15 * pitchw];
 #pragma unroll
-        for (int k = 0; k < KIPT; ++k) {
-            const int it = threadIdx.x + k * QT;
-            if (it < RH * RQ) {
-                const uint4 x = lds4(A + it * 4), y = lds4(A + (it + RQ < RH * RQ ? it + RQ : it) * 4);  // last row: itself
-                v[k] = make_uint4(pmax(x.x, y.x), pmax(x.y, y.y), pmax(x.z, y.z), pmax(x.w, y.w));
-                sts4(B + it * 4, v[k]);
+            for (int k = 14; k >= 0; --k) sfx[k] = pmax(p[k * pitchw], sfx[k + 1]);
+            o[0] = sfx[0];
+            uint32_t m = 0u;
+#pragma unroll
+            for (int j = 1; j < 16; ++j) {
+                if (r0 + 15 + j < RH) m = pmax(m, p[(15 + j) * pitchw]);  // rows past the region are absent
+                o[j * pitchw] = pmax(sfx[j], m);
             }
-        }
-        __syncthreads();
-#pragma unroll
-        for (int step = 2; step <= 8; step *= 2) {
-#pragma unroll
-            for (int k = 0; k < KIPT; ++k) {
-                const int it = threadIdx.x + k * QT;
-                if (it < RH * RQ) {
-                    const uint4 y = lds4(B + (it + step * RQ) * 4);
-                    v[k] = make_uint4(pmax(v[k].x, y.x), pmax(v[k].y, y.y), pmax(v[k].z, y.z), pmax(v[k].w, y.w));
-                }
-            }
-            __syncthreads();
-#pragma unroll
-            for (int k = 0; k < KIPT; ++k) {
-                const int it = threadIdx.x + k * QT;
-                if (it < RH * RQ) sts4(B + it * 4, v[k]);
-            }
-            __syncthreads();
         }
     }
+    __syncthreads();
+    DCMT_STAMP(a, 3);
     // ---- A6 horizontal part on hole words only (:131-144): scan quads for lanes == 1, ballot/popc-compact the
     //      words that hold a hole into a list, then a 31-wide max of the vertical maxima for those words.
     //      Scan region: rows core +- 4, quads covering columns core +- 8 (a superset of the +- 4 the median needs).
@@ -594,6 +616,7 @@ __global__ void __launch_bounds__(QT, 2) k_q8_tail(TailArgs a) {
         }
     }
     __syncthreads();
+    DCMT_STAMP(a, 4);
     int holes_core = 0, left_core = 0, left_any = 0;
     const int n_quads = s_count;
     auto fill_word = [&](int widx) {
@@ -625,6 +648,7 @@ __global__ void __launch_bounds__(QT, 2) k_q8_tail(TailArgs a) {
         if (s_left_core) atomicAdd(&a.ctr[slot].holes_after_first_fill, s_left_core);
         if (s_remaining) a.ctr[slot].holes_remaining = 1;  // a second pass is needed: k_q8_fixup redoes the frame
     }
+    DCMT_STAMP(a, 5);
     // ---- BORDER_REPLICATE for the median (:170): copy the nearest image pixel into the cells outside the image
     //      (rows / columns core +- 4).  Only the strips that are outside are visited.
     if (border) {
@@ -649,6 +673,7 @@ __global__ void __launch_bounds__(QT, 2) k_q8_tail(TailArgs a) {
         }
         __syncthreads();
     }
+    DCMT_STAMP(a, 6);
     // ---- A8 median 5x5 (:170): one item = four output words of one row.  The six word columns it touches are sorted
     //      once (9 compare-exchanges each, both lanes at once), the odd-aligned pixel pairs between them come from
     //      PRMTs of the sorted columns, and each output is the 54-comparator selection network of median_net.cuh on
@@ -697,6 +722,7 @@ __global__ void __launch_bounds__(QT, 2) k_q8_tail(TailArgs a) {
         }
     }
     __syncthreads();
+    DCMT_STAMP(a, 7);
     float* out = a.out + (size_t)slot * a.out_fstride;
     // ---- BORDER_REFLECT_101 for the Gaussian (:179): mirror the median image into the 2 cells beyond each edge.
     //      Columns first (rows inside), then whole rows (their sources then include the mirrored columns).
@@ -720,6 +746,7 @@ __global__ void __launch_bounds__(QT, 2) k_q8_tail(TailArgs a) {
         }
         __syncthreads();
     }
+    DCMT_STAMP(a, 8);
     // ---- A9 + A10: 5x5 Gaussian [1 4 6 4 1]^2 / 256 in integer q16 (:176-189), final inversion (:191-202), float32
     //      store.  One item = 4 pixels (two words) x 4 rows: the horizontal [1 4 6 4 1] sums of the 8 rows it touches
     //      come straight from the packed words with 16-bit x 8-bit dot products (IDP.2A), the vertical combination
@@ -774,6 +801,7 @@ __global__ void __launch_bounds__(QT, 2) k_q8_tail(TailArgs a) {
             }
         }
     }
+    DCMT_STAMP(a, 9);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -899,13 +927,11 @@ __global__ void k_q8_write_stats(const FrameCounters* __restrict__ c, int32_t* _
 
 }  // namespace
 
-size_t q8_front_smem(int th, int tw) {
-    return (size_t)2 * (th + FU + FD + 2 * FG) * (tw / 8 + FLQ + FRQ) * 4 * sizeof(uint32_t);
-}
+size_t q8_front_smem(int th, int tw) { return (size_t)2 * (th + FU + FD) * (tw / 8 + FLQ + FRQ) * 4 * sizeof(uint32_t); }
 
 size_t q8_tail_smem(int th, int tw) {
     const size_t rowb = (size_t)(tw / 8 + 2 * TQ) * 4 * sizeof(uint32_t);
-    return (size_t)(2 * (th + 2 * TV) + TG) * rowb + (size_t)kListCap * sizeof(uint16_t);
+    return (size_t)2 * (th + 2 * TV) * rowb + (size_t)kListCap * sizeof(uint16_t);
 }
 
 void q8_choose_tile(int rows, int cols, int* th, int* tw) {
@@ -928,7 +954,7 @@ cudaError_t q8_run_front(const Q8Plan& p, const float* in, size_t in_pitch, size
     DCMT_LAUNCH(k_q8_init_cols, dim3((unsigned)((ncol + 255) / 256)), dim3(256), 0, st, p.col_first, p.col_last, ncol);
     FrontArgs a{in, in_pitch, in_fstride, p.mid, (size_t)p.mid_pitch, (size_t)p.mid_pitch * p.rows, p.col_first, p.col_last,
                 p.ctr, p.rows, p.cols, p.th, p.tw,
-                (int)(in_pitch % 4 == 0 && in_fstride % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0), validate};
+                (int)(in_pitch % 4 == 0 && in_fstride % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0), validate, p.prof_front};
     const dim3 grid((p.cols + p.tw - 1) / p.tw, (p.rows + p.th - 1) / p.th, n_frames);
     DCMT_LAUNCH(k_q8_front, grid, dim3(QT), q8_front_smem(p.th, p.tw), st, a);
     return cudaGetLastError();
@@ -937,7 +963,7 @@ cudaError_t q8_run_front(const Q8Plan& p, const float* in, size_t in_pitch, size
 cudaError_t q8_run_tail(const Q8Plan& p, float* out, size_t out_pitch, size_t out_fstride, int n_frames, int blur, cudaStream_t st) {
     const int vec2 = out_pitch % 4 == 0 && out_fstride % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
     TailArgs a{p.mid, (size_t)p.mid_pitch, (size_t)p.mid_pitch * p.rows, p.col_first, p.col_last, p.ctr, out, out_pitch,
-               out_fstride, p.rows, p.cols, p.th, p.tw, blur, vec2};
+               out_fstride, p.rows, p.cols, p.th, p.tw, blur, vec2, p.prof_tail};
     const dim3 grid((p.cols + p.tw - 1) / p.tw, (p.rows + p.th - 1) / p.th, n_frames);
     DCMT_LAUNCH(k_q8_tail, grid, dim3(QT), q8_tail_smem(p.th, p.tw), st, a);
     FixupArgs f{p.mid, (size_t)p.mid_pitch, (size_t)p.mid_pitch * p.rows, p.col_first, p.col_last, p.ctr, p.w1, p.w2, out,

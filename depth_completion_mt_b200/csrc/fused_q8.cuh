@@ -17,6 +17,8 @@ struct Q8Plan {
     FrameCounters* ctr;  // max_frames
     float* w1;           // max_frames * rows * cols, fix-up scratch
     float* w2;
+    long long* prof_front;  // optional debugging aid: 16 clock64() stamps per CTA of k_q8_front / k_q8_tail
+    long long* prof_tail;
 };
 
 // fused path applies to frames of at least this size (smaller ones use the generic pipeline)

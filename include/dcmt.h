@@ -162,6 +162,13 @@ DCMT_API int dcmt_img_completion_stages_f32(const float *sparse, float *dense, i
                                             float *stages, int n_stages, uint32_t *stage_mask_out,
                                             void *cuda_stream);
 
+/* debugging aid: runs the fused strict-q8 kernels on one chunk of frames (device pointers, contiguous) and records
+ * 16 clock64() stamps per CTA at the phase boundaries of k_q8_front / k_q8_tail (device arrays of
+ * tiles_per_frame * n_frames * 16 int64 each; use ceil(rows/32)*ceil(cols/32) tiles as an upper bound). */
+DCMT_API int dcmt_debug_q8_phase_cycles(const float *sparse, float *dense, int rows, int cols, int n_frames,
+                                        long long *front_stamps, long long *tail_stamps, int *tiles_per_frame,
+                                        void *cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

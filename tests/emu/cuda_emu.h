@@ -62,6 +62,8 @@ long launches();
 }  // namespace dcmt_emu
 
 #define DCMT_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(dcmt_emu::dyn_smem())
+#define DCMT_CP_ASYNC_16(smem_ptr, gmem_ptr) std::memcpy((smem_ptr), (gmem_ptr), 16)
+#define DCMT_CP_ASYNC_WAIT_ALL() ((void)0)
 namespace dcmt { void note_launch(); }
 #define DCMT_LAUNCH(kernel, grid, block, smem, stream, ...) \
     (dcmt::note_launch(), dcmt_emu::launch((grid), (block), (smem), [=]() { kernel(__VA_ARGS__); }))
@@ -110,6 +112,7 @@ template <class T> static inline T __shfl_xor_sync(unsigned, T v, int m) { retur
 static inline unsigned __ballot_sync(unsigned, int p) { return dcmt_emu::warp_ballot(p); }
 static inline int __any_sync(unsigned, int p) { return dcmt_emu::warp_ballot(p) != 0; }
 static inline int __all_sync(unsigned, int p) { return dcmt_emu::warp_ballot(!p) == 0; }
+static inline long long clock64() { static long long c = 0; return ++c; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __clz(int v) { return v == 0 ? 32 : __builtin_clz((unsigned)v); }
 static inline int __ffs(int v) { return __builtin_ffs(v); }
