@@ -23,7 +23,8 @@
 namespace dcmt {
 namespace {
 
-constexpr int QT = 512;  // threads per CTA
+constexpr int QT = 512;    // threads per CTA of k_q8_front (2 CTAs per SM)
+constexpr int QTT = 512;   // threads per CTA of k_q8_tail (2 CTAs per SM: their phases overlap)
 
 #define SPLAT16(x) ((uint32_t)(x) | ((uint32_t)(x) << 16))
 constexpr uint32_t E_VALID_MIN = 27;   // e >= 27  <=>  depth >= 0.1f  (26/256 = 0.1015625 is the smallest q8 value >= 0.1f)
@@ -67,18 +68,18 @@ __device__ __forceinline__ uint4 mask_columns(uint4 v, int gx, int cols, uint32_
 // Built once per kernel for each row length it is used with (the constructor divides), then copied per loop;
 // `lin` is the linear item index r * nq + q.
 struct Items {
-    int r, q, lin, dr, dq, nq;
-    __device__ __forceinline__ explicit Items(int nq_) : nq(nq_) {
+    int r, q, lin, dr, dq, nq, nt;
+    __device__ __forceinline__ explicit Items(int nq_, int nt_ = QT) : nq(nq_), nt(nt_) {
         r = threadIdx.x / nq_;
         q = threadIdx.x - r * nq_;
         lin = threadIdx.x;
-        dr = QT / nq_;
-        dq = QT - dr * nq_;
+        dr = nt_ / nq_;
+        dq = nt_ - dr * nq_;
     }
     __device__ __forceinline__ void next() {
         q += dq;
         r += dr;
-        lin += QT;
+        lin += nt;
         if (q >= nq) { q -= nq; ++r; }
     }
 };
@@ -453,25 +454,37 @@ struct TailArgs {
     float* out;
     size_t out_pitch, out_fstride;
     int rows, cols, th, tw, blur, vec_ok;
+    int one;          // the constant 1, opaque to the compiler (see other_of_pair)
     long long* prof;  // optional: 16 clock64() stamps per CTA (debugging aid)
 };
 
+// The element of {a, b} that is not lo = min(a, b), for both packed lanes at once: a + b - lo as ONE 32-bit
+// expression is exact (the lane results fit 16 bits, so the carries between the lanes cancel).  Min/max of every
+// flavour runs on the ALU pipe at 64 lanes/clk/SM (tools/pipe_bench.cu); integer multiply-add runs on the FMA
+// pipe in parallel, so a compare-exchange written this way costs one ALU-pipe slot instead of two.  The multiplier
+// is an opaque 1 so that the additions are emitted as IMAD (FMA pipe) and not folded into an ALU-pipe IADD3.
+__device__ __forceinline__ uint32_t other_of_pair(uint32_t a, uint32_t b, uint32_t lo, uint32_t one) {
+    return a * one + (b * one - lo);
+}
+
 struct PackedOps {
+    uint32_t one;
+    __device__ __forceinline__ uint32_t other(uint32_t a, uint32_t b, uint32_t lo) const { return other_of_pair(a, b, lo, one); }
     static __device__ __forceinline__ uint32_t mn(uint32_t a, uint32_t b) { return pmin(a, b); }
     static __device__ __forceinline__ uint32_t mx(uint32_t a, uint32_t b) { return pmax(a, b); }
     static __device__ __forceinline__ uint32_t mn3(uint32_t a, uint32_t b, uint32_t c) { return pmin3(a, b, c); }
     static __device__ __forceinline__ uint32_t mx3(uint32_t a, uint32_t b, uint32_t c) { return pmax3(a, b, c); }
 };
 
-__device__ __forceinline__ void pcswap(uint32_t& a, uint32_t& b) {
+__device__ __forceinline__ void pcswap(uint32_t& a, uint32_t& b, uint32_t one) {
     const uint32_t lo = pmin(a, b);
-    b = pmax(a, b);
+    b = other_of_pair(a, b, lo, one);
     a = lo;
 }
 // optimal 9-comparator sort of five packed words (both lanes independently)
-__device__ __forceinline__ void sort5(uint32_t (&v)[5]) {
-    pcswap(v[0], v[1]); pcswap(v[3], v[4]); pcswap(v[2], v[4]); pcswap(v[2], v[3]); pcswap(v[0], v[3]);
-    pcswap(v[0], v[2]); pcswap(v[1], v[4]); pcswap(v[1], v[3]); pcswap(v[1], v[2]);
+__device__ __forceinline__ void sort5(uint32_t (&v)[5], uint32_t one) {
+    pcswap(v[0], v[1], one); pcswap(v[3], v[4], one); pcswap(v[2], v[4], one); pcswap(v[2], v[3], one); pcswap(v[0], v[3], one);
+    pcswap(v[0], v[2], one); pcswap(v[1], v[4], one); pcswap(v[1], v[3], one); pcswap(v[1], v[2], one);
 }
 
 // lanes equal to 1 (holes) -> 0xffff mask per lane
@@ -496,7 +509,7 @@ __device__ __forceinline__ uint32_t hmax31(const uint32_t* __restrict__ B, int p
     return pmax3(m, __byte_perm(m, m, 0x1032), odd_pair(pmax(b0[-8], b1[-8]), pmax(b0[8], b1[8])));
 }
 
-__global__ void __launch_bounds__(QT, 2) k_q8_tail(TailArgs a) {
+__global__ void __launch_bounds__(QTT, 2) k_q8_tail(TailArgs a) {
     DCMT_DYN_SMEM(uint32_t, smem);
     const int th = a.th, tw = a.tw, rows = a.rows, cols = a.cols;
     const int RH = th + 2 * TV, RQ = tw / 8 + 2 * TQ, pitchw = RQ * 4;
@@ -528,9 +541,9 @@ __global__ void __launch_bounds__(QT, 2) k_q8_tail(TailArgs a) {
         const uint16_t* mp = mid + ((ptrdiff_t)gy0 * (ptrdiff_t)a.mid_pitch + gx0);
         const int mpitch = (int)a.mid_pitch;
         if (!border) {
-            for (Items i(RQ); i.r < RH; i.next()) DCMT_CP_ASYNC_16(A + i.lin * 4, mp + (i.r * mpitch + i.q * 8));
+            for (Items i(RQ, QTT); i.r < RH; i.next()) DCMT_CP_ASYNC_16(A + i.lin * 4, mp + (i.r * mpitch + i.q * 8));
         } else {
-            for (Items i(RQ); i.r < RH; i.next()) {
+            for (Items i(RQ, QTT); i.r < RH; i.next()) {
                 if (outside(t, i.r, i.q)) sts4(A + i.lin * 4, splat4(kAbsMax));
                 else if (i.q == t.qs) sts4(A + i.lin * 4, blend(__ldg(reinterpret_cast<const uint4*>(mp + (i.r * mpitch + i.q * 8))), t.smask, kAbsMax));
                 else DCMT_CP_ASYNC_16(A + i.lin * 4, mp + (i.r * mpitch + i.q * 8));
@@ -571,7 +584,7 @@ __global__ void __launch_bounds__(QT, 2) k_q8_tail(TailArgs a) {
     //      running prefix maximum of the next 15 rows completes every window.  No intermediate planes, one barrier.
     {
         const int NB = (TV + th + 4 + 15) / 16;  // vertical maxima are needed for rows [0, TV + th + 4)
-        for (Items i(pitchw); i.r < NB; i.next()) {
+        for (Items i(pitchw, QTT); i.r < NB; i.next()) {
             const int r0 = 16 * i.r;
             const uint32_t* p = A + r0 * pitchw + i.q;
             uint32_t* o = B + r0 * pitchw + i.q;
@@ -597,8 +610,8 @@ __global__ void __launch_bounds__(QT, 2) k_q8_tail(TailArgs a) {
     const int sr0 = TV - 4, sq0 = TQ - 1;
     {
         const int n = SH * SQ;
-        Items i(SQ);
-        for (int base = 0; base < n; base += QT, i.next()) {
+        Items i(SQ, QTT);
+        for (int base = 0; base < n; base += QTT, i.next()) {
             bool cand = false;
             int qidx = 0;
             if (base + (int)threadIdx.x < n) {
@@ -635,9 +648,9 @@ __global__ void __launch_bounds__(QT, 2) k_q8_tail(TailArgs a) {
         }
     };
     if (n_quads <= kListCap) {
-        for (int k = threadIdx.x; k < 4 * n_quads; k += QT) fill_word(list[k >> 2] * 4 + (k & 3));
+        for (int k = threadIdx.x; k < 4 * n_quads; k += QTT) fill_word(list[k >> 2] * 4 + (k & 3));
     } else {  // cannot happen for tiles up to 96 x 160 (2184 scan quads); kept for larger tiles
-        for (Items i(SQ * 4); i.r < SH; i.next()) fill_word((sr0 + i.r) * pitchw + sq0 * 4 + i.q);
+        for (Items i(SQ * 4, QTT); i.r < SH; i.next()) fill_word((sr0 + i.r) * pitchw + sq0 * 4 + i.q);
     }
     if (holes_core) atomicAdd(&s_holes_core, holes_core);
     if (left_core) atomicAdd(&s_left_core, left_core);
@@ -657,7 +670,7 @@ __global__ void __launch_bounds__(QT, 2) k_q8_tail(TailArgs a) {
         const int c_in0 = max(c_lo, -gx0), c_in1 = min(c_lo + c_n, cols - gx0);        // in-image scan columns
         const int n_rows_out = SH - max(0, r_in1 - r_in0), n_cols_out = c_n - max(0, c_in1 - c_in0);
         // (1) columns outside, rows inside   (2) rows outside, all columns (after (1): sources are final)
-        for (int it = threadIdx.x; it < max(0, r_in1 - r_in0) * n_cols_out; it += QT) {
+        for (int it = threadIdx.x; it < max(0, r_in1 - r_in0) * n_cols_out; it += QTT) {
             const int rr = it / n_cols_out, k = it - rr * n_cols_out;
             const int r = r_in0 + rr;
             const int c = k < c_in0 - c_lo ? c_lo + k : c_in1 + (k - (c_in0 - c_lo));
@@ -665,7 +678,7 @@ __global__ void __launch_bounds__(QT, 2) k_q8_tail(TailArgs a) {
             Ah[(size_t)r * pitchw * 2 + c] = Ah[(size_t)r * pitchw * 2 + cc];
         }
         __syncthreads();
-        for (int it = threadIdx.x; it < n_rows_out * c_n; it += QT) {
+        for (int it = threadIdx.x; it < n_rows_out * c_n; it += QTT) {
             const int k = it / c_n, c = c_lo + (it - k * c_n);
             const int r = k < r_in0 - sr0 ? sr0 + k : r_in1 + (k - (r_in0 - sr0));
             const int cr = clampi(r, r_in0, r_in1 - 1);
@@ -681,7 +694,8 @@ __global__ void __launch_bounds__(QT, 2) k_q8_tail(TailArgs a) {
     {
         const int MH = th + 4, MI = (tw / 2 + 2 + 3) / 4;  // rows core +- 2; items of four words covering core +- 1 word
         const int mr0 = TV - 2, mw0 = TQ * 4 - 1;
-        for (Items i(MI); i.r < MH; i.next()) {
+        const PackedOps ops{(uint32_t)a.one};
+        for (Items i(MI, QTT); i.r < MH; i.next()) {
             const int r = mr0 + i.r, w = mw0 + 4 * i.q;  // output words w .. w+3; columns w-1 .. w+4
             uint32_t col[6][5];
             const uint32_t* p = A + (r - 2) * pitchw + (w - 1);  // w - 1 is even: 8-byte aligned
@@ -692,7 +706,7 @@ __global__ void __launch_bounds__(QT, 2) k_q8_tail(TailArgs a) {
                 col[0][k] = p0.x; col[1][k] = p0.y; col[2][k] = p1.x; col[3][k] = p1.y; col[4][k] = p2.x; col[5][k] = p2.y;
             }
 #pragma unroll
-            for (int j = 0; j < 6; ++j) sort5(col[j]);
+            for (int j = 0; j < 6; ++j) sort5(col[j], ops.one);
             uint32_t res[4];
             uint32_t oddl[5];  // sorted column of the odd-aligned pair left of the current output word
 #pragma unroll
@@ -711,7 +725,7 @@ __global__ void __launch_bounds__(QT, 2) k_q8_tail(TailArgs a) {
                     c[15 + k] = oddr[k];
                     c[20 + k] = col[o + 2][k];
                 }
-                res[o] = median25_sorted_columns<PackedOps>(c);
+                res[o] = median25_sorted_columns(ops, c);
 #pragma unroll
                 for (int k = 0; k < 5; ++k) oddl[k] = oddr[k];
             }
@@ -731,14 +745,14 @@ __global__ void __launch_bounds__(QT, 2) k_q8_tail(TailArgs a) {
         const int r_in0 = max(r_lo, -gy0), r_in1 = min(r_lo + r_n, rows - gy0);
         const int c_in0 = max(c_lo, -gx0), c_in1 = min(c_lo + c_n, cols - gx0);
         // at most 2 columns on each side matter: region columns -gx0-2, -gx0-1 and cols-gx0, cols-gx0+1
-        for (int it = threadIdx.x; it < max(0, r_in1 - r_in0) * 4; it += QT) {
+        for (int it = threadIdx.x; it < max(0, r_in1 - r_in0) * 4; it += QTT) {
             const int r = r_in0 + (it >> 2), k = it & 3;
             const int gx = k < 2 ? k - 2 : cols + (k - 2);
             const int c = gx - gx0, cc = reflect101(gx, cols) - gx0;
             if (c >= c_lo && c < c_lo + c_n && cc >= c_in0 && cc < c_in1) Bh[(size_t)r * pitchw * 2 + c] = Bh[(size_t)r * pitchw * 2 + cc];
         }
         __syncthreads();
-        for (int it = threadIdx.x; it < 4 * c_n; it += QT) {
+        for (int it = threadIdx.x; it < 4 * c_n; it += QTT) {
             const int k = it / c_n, c = c_lo + (it - k * c_n);
             const int gy = k < 2 ? k - 2 : rows + (k - 2);
             const int r = gy - gy0, cr = reflect101(gy, rows) - gy0;
@@ -755,7 +769,7 @@ __global__ void __launch_bounds__(QT, 2) k_q8_tail(TailArgs a) {
     //      applies:  out16 = 6553600 - (g - 256)  with e = q + 1 and weights summing to 256.
     {
         const int NP = tw / 4, NGR = (th + 3) / 4;
-        for (Items i(NP); i.r < NGR; i.next()) {
+        for (Items i(NP, QTT); i.r < NGR; i.next()) {
             const int cy0 = i.r * 4, gx = x0 + i.q * 4;
             if (y0 + cy0 >= rows || gx >= cols) continue;
             const uint32_t* p = B + (TV + cy0) * pitchw + TQ * 4 + 2 * i.q;  // row cy0, first word of the pair
@@ -963,9 +977,9 @@ cudaError_t q8_run_front(const Q8Plan& p, const float* in, size_t in_pitch, size
 cudaError_t q8_run_tail(const Q8Plan& p, float* out, size_t out_pitch, size_t out_fstride, int n_frames, int blur, cudaStream_t st) {
     const int vec2 = out_pitch % 4 == 0 && out_fstride % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
     TailArgs a{p.mid, (size_t)p.mid_pitch, (size_t)p.mid_pitch * p.rows, p.col_first, p.col_last, p.ctr, out, out_pitch,
-               out_fstride, p.rows, p.cols, p.th, p.tw, blur, vec2, p.prof_tail};
+               out_fstride, p.rows, p.cols, p.th, p.tw, blur, vec2, 1, p.prof_tail};
     const dim3 grid((p.cols + p.tw - 1) / p.tw, (p.rows + p.th - 1) / p.th, n_frames);
-    DCMT_LAUNCH(k_q8_tail, grid, dim3(QT), q8_tail_smem(p.th, p.tw), st, a);
+    DCMT_LAUNCH(k_q8_tail, grid, dim3(QTT), q8_tail_smem(p.th, p.tw), st, a);
     FixupArgs f{p.mid, (size_t)p.mid_pitch, (size_t)p.mid_pitch * p.rows, p.col_first, p.col_last, p.ctr, p.w1, p.w2, out,
                 out_pitch, out_fstride, p.rows, p.cols, blur, (p.rows > p.cols ? p.rows : p.cols) / 15 + 2};
     DCMT_LAUNCH(k_q8_fixup, dim3(n_frames), dim3(1024), 0, st, f);

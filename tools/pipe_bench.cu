@@ -37,6 +37,26 @@ __global__ void __launch_bounds__(1024) k(unsigned* out, unsigned seed, long lon
             if (MODE == 10) a[i] = __shfl_xor_sync(0xffffffffu, a[i], 1);  // SHFL
             if (MODE == 11) a[i] = fmaxf(__uint_as_float(a[i]), __uint_as_float(b)) > 0 ? a[i] : b;  // FMNMX-ish
             if (MODE == 12) { if (i & 1) a[i] = __vmaxu2(a[i], b); else a[i] = __byte_perm(a[i], b, 0x5432); }  // VIMNMX+PRMT
+            if (MODE == 13) a[i] = __vmaxu2(a[i], a[(i + 3) & 7]);          // VIMNMX, two distinct varying registers
+            if (MODE == 15) a[i] = __dp2a_lo(a[i], 0x0401u, b);             // IDP.2A
+            if (MODE == 16) { __half2 x = *reinterpret_cast<__half2*>(&a[i]), y = *reinterpret_cast<__half2*>(&a[(i + 3) & 7]);
+                              x = __hmax2(x, y); a[i] = *reinterpret_cast<unsigned*>(&x); }  // HMNMX2 two varying regs
+            if (MODE == 17) { if (i & 1) a[i] = __vmaxu2(a[i], a[(i + 3) & 7]);
+                              else { __half2 x = *reinterpret_cast<__half2*>(&a[i]), y = *reinterpret_cast<__half2*>(&a[(i + 3) & 7]);
+                                     x = __hmin2(x, y); a[i] = *reinterpret_cast<unsigned*>(&x); } }  // VIMNMX / HMNMX2 alternating
+            if (MODE == 18) a[i] = max((int)a[i], (int)a[(i + 3) & 7]);     // 32-bit IMNMX two varying regs
+            if (MODE == 19) a[i] = __float_as_uint(fmaxf(__uint_as_float(a[i]), __uint_as_float(a[(i + 3) & 7])));  // FMNMX
+            if (MODE == 20) { if (i & 1) a[i] = __vmaxu2(a[i], a[(i + 3) & 7]); else a[i] = a[i] * 5 + a[(i + 3) & 7]; }  // VIMNMX / IMAD varying
+        }
+        if (MODE == 14) {  // compare-exchange network (odd-even transposition) on 8 registers: min + max of the same pair
+#pragma unroll
+            for (int rep = 0; rep < 4; ++rep) {
+#pragma unroll
+                for (int i = 0; i + 1 < UNROLL; i += 2) { unsigned lo = __vminu2(a[i], a[i + 1]), hi = __vmaxu2(a[i], a[i + 1]); a[i] = lo; a[i + 1] = hi; }
+#pragma unroll
+                for (int i = 1; i + 1 < UNROLL; i += 2) { unsigned lo = __vminu2(a[i], a[i + 1]), hi = __vmaxu2(a[i], a[i + 1]); a[i] = lo; a[i + 1] = hi; }
+            }
+            a[0] ^= b; a[7] += b;
         }
         b += 0x00010001u;
     }
@@ -65,6 +85,14 @@ __global__ void __launch_bounds__(1024) k_lds(unsigned* out, long long* cycles) 
     long long t1 = clock64();
     out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
     if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
+__global__ void k_hcheck(const unsigned* a, const unsigned* b, unsigned* mx, unsigned* mn) {
+    const int i = threadIdx.x;
+    __half2 x = *reinterpret_cast<const __half2*>(&a[i]), y = *reinterpret_cast<const __half2*>(&b[i]);
+    __half2 hi = __hmax2(x, y), lo = __hmin2(x, y);
+    mx[i] = *reinterpret_cast<unsigned*>(&hi);
+    mn[i] = *reinterpret_cast<unsigned*>(&lo);
 }
 
 template <int MODE>
@@ -114,6 +142,30 @@ int main() {
     run<10>("SHFL", d_out, d_cyc);
     run<11>("FMNMX + SEL", d_out, d_cyc);
     run<12>("VIMNMX + PRMT (1:1)", d_out, d_cyc);
+    run<13>("VIMNMX two varying regs", d_out, d_cyc);
+    run<14>("compare-exchange x56/iter (8/iter counted)", d_out, d_cyc);
+    run<15>("IDP.2A", d_out, d_cyc);
+    run<16>("HMNMX2 two varying regs", d_out, d_cyc);
+    run<17>("VIMNMX / HMNMX2 alternating", d_out, d_cyc);
+    run<18>("IMNMX 32-bit two varying", d_out, d_cyc);
+    run<19>("FMNMX two varying", d_out, d_cyc);
+    run<20>("VIMNMX / IMAD alternating", d_out, d_cyc);
+    {   // does HMNMX2 order small (denormal-pattern) and large u16 codes like integers?
+        unsigned h_a[8] = {0x00010000u, 0x00010002u, 0x03ff0400u, 0x64010001u, 0x00000001u, 0x7bff6401u, 0x00016401u, 0x00020001u};
+        unsigned h_b[8] = {0x00000001u, 0x00020001u, 0x04000001u, 0x00016401u, 0x00010000u, 0x64017bffu, 0x64010001u, 0x00010002u};
+        unsigned *da, *db, *dmx, *dmn, hmx[8], hmn[8];
+        cudaMalloc(&da, 32); cudaMalloc(&db, 32); cudaMalloc(&dmx, 32); cudaMalloc(&dmn, 32);
+        cudaMemcpy(da, h_a, 32, cudaMemcpyHostToDevice); cudaMemcpy(db, h_b, 32, cudaMemcpyHostToDevice);
+        k_hcheck<<<1, 8>>>(da, db, dmx, dmn);
+        cudaMemcpy(hmx, dmx, 32, cudaMemcpyDeviceToHost); cudaMemcpy(hmn, dmn, 32, cudaMemcpyDeviceToHost);
+        int ok = 1;
+        for (int i = 0; i < 8; ++i) {
+            unsigned alo = h_a[i] & 0xffff, ahi = h_a[i] >> 16, blo = h_b[i] & 0xffff, bhi = h_b[i] >> 16;
+            unsigned emx = (alo > blo ? alo : blo) | ((ahi > bhi ? ahi : bhi) << 16), emn = (alo < blo ? alo : blo) | ((ahi < bhi ? ahi : bhi) << 16);
+            if (emx != hmx[i] || emn != hmn[i]) { ok = 0; printf("HMNMX2 mismatch %08x %08x -> max %08x (want %08x) min %08x (want %08x)\n", h_a[i], h_b[i], hmx[i], emx, hmn[i], emn); }
+        }
+        printf("HMNMX2 orders u16 codes below 0x7c00 like integers (incl. denormal patterns): %s\n", ok ? "yes" : "NO");
+    }
     run_lds<4>("LDS.32 stream", d_out, d_cyc);
     run_lds<8>("LDS.64 stream", d_out, d_cyc);
     run_lds<16>("LDS.128 stream", d_out, d_cyc);
