@@ -362,6 +362,26 @@ def run_ours(args):
     else:
         e2e_ms = 0.0
 
+    # ---- per-kernel split of the fused path (CUDA events around each kernel, a few extra untimed steps)
+    kernels = None
+    if args.workload == "lidar_only":
+        import ctypes as C
+
+        lib.check(lib.dcmt_profile_begin())
+        for _ in range(3):
+            step()
+        fm, tm, ch = C.c_double(0), C.c_double(0), C.c_longlong(0)
+        lib.check(lib.dcmt_profile_end(C.byref(fm), C.byref(tm), C.byref(ch)))
+        if ch.value:
+            peak_, _src = measured_peak()
+            px = 3 * n * fpix
+            kernels = {
+                "k_q8_front": {"ms_per_step": fm.value / 3, "alg_bytes_per_px": 6, "achieved_GBps": 6 * px / (fm.value * 1e6),
+                               "frac": 6 * px / (fm.value * 1e6) / peak_, "note": "float32 in, uint16 intermediate out"},
+                "k_q8_tail": {"ms_per_step": tm.value / 3, "alg_bytes_per_px": 6, "achieved_GBps": 6 * px / (tm.value * 1e6),
+                              "frac": 6 * px / (tm.value * 1e6) / peak_, "note": "uint16 intermediate in, float32 out; dominant kernel"},
+                "chunks_per_step": ch.value // 3,
+            }
     res = sharding.gather_validation(elapsed_ms, n * args.steps, sums, device=dev)
     res_e2e = sharding.gather_validation(e2e_ms, n * args.steps, sums, device=dev)
     clocks = sampler.stop() if sampler else None
@@ -381,7 +401,7 @@ def run_ours(args):
         "ms_per_step": res["max_ms"] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": workload_config(args, n),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                     "peak_source": peak_src,
+                     "peak_source": peak_src, "kernels": kernels,
                      "note": f"whole hot path, {BYTES_PER_PX[args.workload]} algorithmic B/px x {fpix} px x frames / CUDA-event time, per GPU"},
         "gpu_launches": int(launches), "clocks": clocks,
         "validation": {"ranks": world, "checksums_equal_across_ranks": all(bool(torch.equal(c, res["checksums"][0])) for c in res["checksums"]),

@@ -156,6 +156,21 @@ int check_device() {
     return DCMT_OK;
 }
 
+// ---- optional per-kernel timing of the fused path (dcmt_profile_begin / dcmt_profile_end): CUDA events recorded on
+// the launch stream around k_q8_front and k_q8_tail of every chunk, read back when profiling ends
+struct ProfEvents {
+    cudaEvent_t e[3];
+};
+bool g_prof_on = false;
+std::vector<ProfEvents> g_prof_events;
+
+cudaError_t prof_mark(cudaStream_t st, int which, ProfEvents* pe) {
+    if (!g_prof_on) return cudaSuccess;
+    cudaError_t e = cudaEventCreate(&pe->e[which]);
+    if (e != cudaSuccess) return e;
+    return cudaEventRecord(pe->e[which], st);
+}
+
 // validated description of one completion call
 struct CompletionCall {
     const int32_t* labels;
@@ -216,9 +231,17 @@ int enqueue_completion(const CompletionCall& cc, const float* sparse, const int3
         p.w2 = w2;
         for (int f0 = 0; f0 < n_frames; f0 += chunk) {
             const int nf = n_frames - f0 < chunk ? n_frames - f0 : chunk;
+            ProfEvents pe{};
+            API_CUDA(prof_mark(st, 0, &pe), "profiling event");
             API_CUDA(dcmt::q8_run_front(p, sparse + (size_t)f0 * fstride, pitch, fstride, nf, cc.flags != DCMT_PATH_FUSED, st),
                      "fused front launch");
+            API_CUDA(prof_mark(st, 1, &pe), "profiling event");
             API_CUDA(dcmt::q8_run_tail(p, dense + (size_t)f0 * fstride, pitch, fstride, nf, cc.blur, st), "fused tail launch");
+            API_CUDA(prof_mark(st, 2, &pe), "profiling event");
+            if (g_prof_on) {
+                std::lock_guard<std::mutex> lk(g_mu);
+                g_prof_events.push_back(pe);
+            }
             if (stats || redo_flags)
                 API_CUDA(dcmt::q8_write_stats(p, stats ? stats + (size_t)f0 * DCMT_STATS_STRIDE : nullptr,
                                               redo_flags ? redo_flags + f0 : nullptr, nf, st),
@@ -491,6 +514,36 @@ int dcmt_release_workspaces(void) {
 size_t dcmt_workspace_bytes(int rows, int cols, int n_frames) {
     if (rows < 1 || cols < 1 || n_frames < 1) return 0;
     return completion_ws_bytes(rows, cols, n_frames, true, true);
+}
+
+int dcmt_profile_begin(void) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_prof_events.clear();
+    g_prof_on = true;
+    return DCMT_OK;
+}
+
+int dcmt_profile_end(double* front_ms, double* tail_ms, long long* chunks) {
+    std::vector<ProfEvents> ev;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        g_prof_on = false;
+        ev.swap(g_prof_events);
+    }
+    double f = 0.0, t = 0.0;
+    for (auto& pe : ev) {
+        API_CUDA(cudaEventSynchronize(pe.e[2]), "profiling event");
+        float a = 0.f, b = 0.f;
+        API_CUDA(cudaEventElapsedTime(&a, pe.e[0], pe.e[1]), "profiling event");
+        API_CUDA(cudaEventElapsedTime(&b, pe.e[1], pe.e[2]), "profiling event");
+        f += a;
+        t += b;
+        for (int i = 0; i < 3; ++i) cudaEventDestroy(pe.e[i]);
+    }
+    if (front_ms) *front_ms = f;
+    if (tail_ms) *tail_ms = t;
+    if (chunks) *chunks = (long long)ev.size();
+    return DCMT_OK;
 }
 
 long long dcmt_launch_count(void) { return dcmt::g_launches.load(std::memory_order_relaxed); }

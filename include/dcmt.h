@@ -87,6 +87,11 @@ DCMT_API int dcmt_release_workspaces(void);
 /* number of CUDA kernels this library has launched in the calling process (monotonic; bench.py reports the
  * difference across its timed region as `gpu_launches`) */
 DCMT_API long long dcmt_launch_count(void);
+/* per-kernel timing of the fused path: between begin and end every chunk's k_q8_front (with its two set-up kernels)
+ * and k_q8_tail (with fix-up and stats kernels) are bracketed by CUDA events on the launch stream; end waits for
+ * them and returns the summed milliseconds and the number of chunks.  Not thread-safe with concurrent callers. */
+DCMT_API int dcmt_profile_begin(void);
+DCMT_API int dcmt_profile_end(double *front_ms, double *tail_ms, long long *chunks);
 /* bytes of device workspace the library caches for a call of this shape */
 DCMT_API size_t dcmt_workspace_bytes(int rows, int cols, int n_frames);
 

@@ -91,6 +91,12 @@ enum { cudaStreamNonBlocking = 1 };
 static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { static char tok[8]; static int n = 0; *s = &tok[(n++) & 7]; return cudaSuccess; }
 static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
 static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+typedef int* cudaEvent_t;
+static inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new int(0); return cudaSuccess; }
+static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = nullptr) { return cudaSuccess; }
+static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return cudaSuccess; }
+static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
 template <class F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
 
 // ---- device intrinsics ----
