@@ -50,6 +50,8 @@ def parse_args():
     ap.add_argument("--cols", type=int, default=1216)
     ap.add_argument("--density", type=float, default=0.05)
     ap.add_argument("--path", default="auto", choices=["auto", "generic", "fused"])
+    ap.add_argument("--input", default="f32", choices=["f32", "u16"],
+                    help="lidar_only: float32 metres (the reference's cv::Mat, default) or KITTI uint16 = metres * 256 (main.cpp:75-82)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-frames-per-core", type=int, default=4, help="reference arm: frames per host core per step")
@@ -153,7 +155,7 @@ def workload_config(args, frames_per_step_per_gpu):
              "stereo": "DC_stereo_lidar disparity refinement (BASELINE configs[3])"}
     return {"workload": names[args.workload], "rows": args.rows, "cols": args.cols, "valid_density": args.density,
             "frames_per_gpu_per_step": frames_per_step_per_gpu, "global_batch": frames_per_step_per_gpu * max(1, args.gpus),
-            "unique_frames": UNIQUE, "blur": "gaussian", "parallelism": f"frame-sharded dp{max(1, args.gpus)}, no collective on the hot path",
+            "unique_frames": UNIQUE, "blur": "gaussian", "input": getattr(args, "input", "f32") if args.workload == "lidar_only" else "f32", "parallelism": f"frame-sharded dp{max(1, args.gpus)}, no collective on the hot path",
             "l2_policy": "inputs larger than L2 (batch >> 126 MB), no flush needed"}
 
 
@@ -237,6 +239,7 @@ def run_ours(args):
 
     from depth_completion_mt_b200 import _lib, api, sharding, synth
 
+    os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: rank 0 prints one JSON line
     rank, local_rank, world = sharding.init_process_group()
     assert torch.cuda.is_available(), "bench.py --impl ours needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
@@ -248,13 +251,14 @@ def run_ours(args):
 
     # ---- synthetic inputs, device resident before timing
     if args.workload == "lidar_only":
-        uniq = np.stack([synth.sparse_depth(f, rows, cols, args.density) for f in range(UNIQUE)])
-        d_in = torch.from_numpy(uniq).to(dev).repeat(reps, 1, 1)[:n].contiguous()
-        d_out = torch.empty_like(d_in)
+        uniq16 = np.stack([synth.sparse_depth_q8(f, rows, cols, args.density) for f in range(UNIQUE)])
+        d_in16 = torch.from_numpy(uniq16).to(dev).repeat(reps, 1, 1)[:n].contiguous()
+        d_in = d_in16 if args.input == "u16" else (d_in16.to(torch.float32) / 256.0).contiguous()  # exact: convertTo(CV_32F, 1/256)
+        d_out = torch.empty((n, rows, cols), dtype=torch.float32, device=dev)
 
         def step():
             api.img_completion(d_in, False, "gaussian", path=args.path, out=d_out, lib=lib)
-        h2d = d2h = n * fpix * 4
+        h2d, d2h = n * fpix * (2 if args.input == "u16" else 4), n * fpix * 4
     elif args.workload == "guided":
         uniq = np.stack([synth.sparse_depth(f, rows, cols, args.density) for f in range(UNIQUE)])
         labs = [synth.superpixel_labels(f, rows, cols) for f in range(UNIQUE)]
@@ -319,9 +323,9 @@ def run_ours(args):
     e2e = None
     if not args.no_e2e:
         if args.workload == "lidar_only":
-            h_in = torch.empty((n, rows, cols), dtype=torch.float32, pin_memory=True)
+            h_in = torch.empty((n, rows, cols), dtype=d_in.dtype, pin_memory=True)
             h_in.copy_(d_in)
-            h_out = torch.empty_like(h_in, pin_memory=True)
+            h_out = torch.empty((n, rows, cols), dtype=torch.float32, pin_memory=True)
             np_in, np_out = h_in.numpy(), h_out.numpy()
 
             def host_step():
@@ -359,8 +363,31 @@ def run_ours(args):
             sampler.mark(t0w, t1w)
         if args.workload == "lidar_only":
             assert bool(torch.equal(h_out[:UNIQUE].to(dev), out_t[:UNIQUE])), "host path and device path disagree"
+        # the same frames as the KITTI uint16 payload (dcmt_img_completion_u16_host): half the host-to-device bytes
+        e2e16_ms = None
+        if args.workload == "lidar_only" and args.input == "f32":
+            h_in16 = torch.empty((n, rows, cols), dtype=torch.uint16, pin_memory=True)
+            h_in16.copy_(d_in16)
+            np_in16 = h_in16.numpy()
+            h_out.zero_()
+            for _ in range(2):
+                api.img_completion(np_in16, False, "gaussian", out=np_out, lib=lib)
+            torch.cuda.synchronize()
+            barrier()
+            t0w = time.time()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                api.img_completion(np_in16, False, "gaussian", out=np_out, lib=lib)
+            torch.cuda.synchronize()
+            e2e16_ms = 1e3 * (time.perf_counter() - t0)
+            t1w = time.time()
+            barrier()
+            if sampler:
+                sampler.mark(t0w, t1w)
+            assert bool(torch.equal(h_out[:UNIQUE].to(dev), out_t[:UNIQUE])), "uint16 host path and device path disagree"
     else:
         e2e_ms = 0.0
+        e2e16_ms = None
 
     # ---- per-kernel split of the fused path (CUDA events around each kernel, a few extra untimed steps)
     kernels = None
@@ -375,15 +402,17 @@ def run_ours(args):
         if ch.value:
             peak_, _src = measured_peak()
             px = 3 * n * fpix
+            fb = 4 if args.input == "u16" else 6
             kernels = {
-                "k_q8_front": {"ms_per_step": fm.value / 3, "alg_bytes_per_px": 6, "achieved_GBps": 6 * px / (fm.value * 1e6),
-                               "frac": 6 * px / (fm.value * 1e6) / peak_, "note": "float32 in, uint16 intermediate out"},
+                "k_q8_front": {"ms_per_step": fm.value / 3, "alg_bytes_per_px": fb, "achieved_GBps": fb * px / (fm.value * 1e6),
+                               "frac": fb * px / (fm.value * 1e6) / peak_, "note": f"{args.input} in, uint16 intermediate out"},
                 "k_q8_tail": {"ms_per_step": tm.value / 3, "alg_bytes_per_px": 6, "achieved_GBps": 6 * px / (tm.value * 1e6),
                               "frac": 6 * px / (tm.value * 1e6) / peak_, "note": "uint16 intermediate in, float32 out; dominant kernel"},
                 "chunks_per_step": ch.value // 3,
             }
     res = sharding.gather_validation(elapsed_ms, n * args.steps, sums, device=dev)
     res_e2e = sharding.gather_validation(e2e_ms, n * args.steps, sums, device=dev)
+    res_e2e16 = sharding.gather_validation(e2e16_ms, n * args.steps, sums, device=dev) if e2e16_ms is not None else None
     clocks = sampler.stop() if sampler else None
     if rank != 0:
         if world > 1:
@@ -392,7 +421,8 @@ def run_ours(args):
     total_frames = res["total_frames"]
     secs = res["max_ms"] / 1e3
     fps = total_frames / secs
-    bytes_per_frame = BYTES_PER_PX[args.workload] * fpix
+    bpp = 6 if (args.workload == "lidar_only" and args.input == "u16") else BYTES_PER_PX[args.workload]  # uint16 in + float32 out
+    bytes_per_frame = bpp * fpix
     peak, peak_src = measured_peak()
     achieved = fps * bytes_per_frame / 1e9 / world  # per GPU
     traffic = ncu_traffic(args.workload)
@@ -402,7 +432,7 @@ def run_ours(args):
         "dtype": "f32", "data": "synthetic", "config": workload_config(args, n),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "peak_source": peak_src, "kernels": kernels,
-                     "note": f"whole hot path, {BYTES_PER_PX[args.workload]} algorithmic B/px x {fpix} px x frames / CUDA-event time, per GPU"},
+                     "note": f"whole hot path, {bpp} algorithmic B/px x {fpix} px x frames / CUDA-event time, per GPU"},
         "gpu_launches": int(launches), "clocks": clocks,
         "validation": {"ranks": world, "checksums_equal_across_ranks": all(bool(torch.equal(c, res["checksums"][0])) for c in res["checksums"]),
                        "replicas_equal": bool(replicas_equal), "golden_sha256_match": golden_ok, "ms_per_rank": res["ms_per_rank"]},
@@ -410,7 +440,11 @@ def run_ours(args):
     if not args.no_e2e:
         line["e2e"] = {"value": res_e2e["total_frames"] / (res_e2e["max_ms"] / 1e3), "unit": "frames/s",
                        "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                       "api": "dcmt_*_f32_host via depth_completion_mt_b200.api with numpy views of pinned host buffers"}
+                       "api": "dcmt_*_host via depth_completion_mt_b200.api with numpy views of pinned host buffers"}
+        if res_e2e16 is not None:
+            line["e2e_u16_input"] = {"value": res_e2e16["total_frames"] / (res_e2e16["max_ms"] / 1e3), "unit": "frames/s",
+                                     "h2d_bytes_per_step": int(n * fpix * 2), "d2h_bytes_per_step": int(d2h),
+                                     "api": "dcmt_img_completion_u16_host: KITTI uint16 payload in (main.cpp:75-82), float32 out"}
     if world == 1 and not args.no_cpu_baseline:
         try:
             cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "3", "--warmup", "1", "--workload", args.workload,

@@ -76,38 +76,50 @@ def img_completion(sparse, extr: bool = False, blur_type="gaussian", *, path: st
     """img_completion(sparse_r_img, dense_r_img, extr, blur_type) -- img_completion.cpp:17-204.
 
     ``extr`` is accepted and ignored exactly like the reference (:103 ``int densify = true``).
+    ``sparse`` is float32 metres, or uint16 = metres * 256 -- the payload of a KITTI depth PNG, in which case the call
+    also stands for the ``convertTo(CV_32F, 1.0 / 256.0)`` of main.cpp:79 in front of it (``dcmt_img_completion_u16``).
     Returns ``dense`` (and an int32 (n, 4) stats array when ``return_stats``).  ``out`` optionally supplies the
     output buffer (same type/shape as ``sparse``, contiguous) so that steady-state callers allocate nothing."""
     del extr
     lib = lib or _lib.load()
     blur = _blur_code(blur_type)
     if _is_torch(sparse):
-        s = _prep_torch(sparse, torch.float32, "sparse")
+        u16 = sparse.dtype == torch.uint16
+        s = _prep_torch(sparse, torch.uint16 if u16 else torch.float32, "sparse")
         s3, squeeze = _batch3(s, "sparse")
         n, rows, cols = s3.shape
         if out is None:
-            out = torch.empty_like(s3)
+            out = torch.empty(s3.shape, dtype=torch.float32, device=s.device)
         else:
             if not (_is_torch(out) and out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and out.numel() == s3.numel()):
                 raise ValueError("out must be a contiguous float32 CUDA tensor of the input's size")
             out = out.view(s3.shape)
         stats = torch.zeros((n, STATS_STRIDE), dtype=torch.int32, device=s.device) if return_stats else None
+        st_ptr = stats.data_ptr() if return_stats else None
         with torch.cuda.device(s.device):
-            lib.check(lib.dcmt_img_completion_f32(s3.data_ptr(), out.data_ptr(), rows, cols, 0, 0, n, blur, PATH[path],
-                                                  stats.data_ptr() if return_stats else None, _stream_ptr(stream)))
+            if u16:
+                lib.check(lib.dcmt_img_completion_u16(s3.data_ptr(), out.data_ptr(), rows, cols, 0, 0, 0, 0, n, blur, PATH[path],
+                                                      st_ptr, _stream_ptr(stream)))
+            else:
+                lib.check(lib.dcmt_img_completion_f32(s3.data_ptr(), out.data_ptr(), rows, cols, 0, 0, n, blur, PATH[path],
+                                                      st_ptr, _stream_ptr(stream)))
     else:
-        s = _prep_numpy(sparse, np.float32, "sparse")
+        u16 = isinstance(sparse, np.ndarray) and sparse.dtype == np.uint16
+        s = _prep_numpy(sparse, np.uint16 if u16 else np.float32, "sparse")
         s3, squeeze = _batch3(s, "sparse")
         n, rows, cols = s3.shape
         if out is None:
-            out = np.empty_like(s3)
+            out = np.empty(s3.shape, np.float32)
         else:
             if not (isinstance(out, np.ndarray) and out.dtype == np.float32 and out.flags.c_contiguous and out.size == s3.size):
                 raise ValueError("out must be a C-contiguous float32 array of the input's size")
             out = out.reshape(s3.shape)
         stats = np.zeros((n, STATS_STRIDE), np.int32) if return_stats else None
-        lib.check(lib.dcmt_img_completion_f32_host(_np_ptr(s3), _np_ptr(out), rows, cols, 0, 0, n, blur, PATH[path],
-                                                   _np_ptr(stats) if return_stats else None))
+        st_ptr = _np_ptr(stats) if return_stats else None
+        if u16:
+            lib.check(lib.dcmt_img_completion_u16_host(_np_ptr(s3), _np_ptr(out), rows, cols, 0, 0, 0, 0, n, blur, PATH[path], st_ptr))
+        else:
+            lib.check(lib.dcmt_img_completion_f32_host(_np_ptr(s3), _np_ptr(out), rows, cols, 0, 0, n, blur, PATH[path], st_ptr))
     out = out[0] if squeeze else out
     return (out, stats) if return_stats else out
 

@@ -131,19 +131,20 @@ struct Geometry {
     size_t span_bytes;      // bytes touched by the whole batch
 };
 
-int check_geometry(int rows, int cols, size_t pitch_bytes, size_t frame_stride_bytes, int n_frames, Geometry* g) {
+int check_geometry(int rows, int cols, size_t pitch_bytes, size_t frame_stride_bytes, int n_frames, Geometry* g,
+                   size_t elem = sizeof(float)) {
     if (rows < 1 || cols < 1) return fail(DCMT_E_BADARG, "rows and cols must be >= 1 (got %d x %d)", rows, cols);
     if (n_frames < 0) return fail(DCMT_E_BADARG, "n_frames must be >= 0 (got %d)", n_frames);
     if ((size_t)rows * (size_t)cols > (size_t)1 << 30) return fail(DCMT_E_UNSUPPORTED, "frame larger than 2^30 pixels");
-    if (pitch_bytes == 0) pitch_bytes = (size_t)cols * sizeof(float);
-    if (pitch_bytes % sizeof(float) != 0 || pitch_bytes < (size_t)cols * sizeof(float))
-        return fail(DCMT_E_BADARG, "pitch_bytes %zu invalid for %d float columns", pitch_bytes, cols);
+    if (pitch_bytes == 0) pitch_bytes = (size_t)cols * elem;
+    if (pitch_bytes % elem != 0 || pitch_bytes < (size_t)cols * elem)
+        return fail(DCMT_E_BADARG, "pitch_bytes %zu invalid for %d columns of %zu bytes", pitch_bytes, cols, elem);
     if (frame_stride_bytes == 0) frame_stride_bytes = pitch_bytes * rows;
-    if (frame_stride_bytes % sizeof(float) != 0 || frame_stride_bytes < pitch_bytes * (size_t)(rows - 1) + (size_t)cols * sizeof(float))
+    if (frame_stride_bytes % elem != 0 || frame_stride_bytes < pitch_bytes * (size_t)(rows - 1) + (size_t)cols * elem)
         return fail(DCMT_E_BADARG, "frame_stride_bytes %zu invalid", frame_stride_bytes);
-    g->pitch = pitch_bytes / sizeof(float);
-    g->fstride = frame_stride_bytes / sizeof(float);
-    g->span_bytes = n_frames ? frame_stride_bytes * (size_t)(n_frames - 1) + pitch_bytes * (size_t)(rows - 1) + (size_t)cols * sizeof(float) : 0;
+    g->pitch = pitch_bytes / elem;
+    g->fstride = frame_stride_bytes / elem;
+    g->span_bytes = n_frames ? frame_stride_bytes * (size_t)(n_frames - 1) + pitch_bytes * (size_t)(rows - 1) + (size_t)cols * elem : 0;
     return DCMT_OK;
 }
 
@@ -188,9 +189,10 @@ bool fused_applies(const CompletionCall& cc) {
     return dcmt::q8_tail_smem(th, tw) <= 200 * 1024 && dcmt::q8_front_smem(th, tw) <= 200 * 1024;
 }
 
-size_t completion_ws_bytes(int rows, int cols, int n_frames, bool bilateral, bool fused) {
+size_t completion_ws_bytes(int rows, int cols, int n_frames, bool bilateral, bool fused, bool u16_in = false) {
     const int chunk = fused ? fused_chunk_frames(rows, cols, n_frames) : generic_chunk_frames(rows, cols, n_frames);
     size_t b = generic_ws_bytes(rows, cols, chunk, bilateral);
+    if (u16_in && !fused) b += carve_bytes((size_t)rows * cols * chunk, sizeof(float));
     if (fused) {
         const size_t mid_pitch = ((size_t)cols + 7) / 8 * 8;
         b += carve_bytes((size_t)rows * mid_pitch * chunk, sizeof(uint16_t)) + 2 * carve_bytes(mid_pitch * chunk, sizeof(uint32_t));
@@ -202,9 +204,19 @@ size_t completion_ws_bytes(int rows, int cols, int n_frames, bool bilateral, boo
 // Never synchronises.  On the fused path `redo_flags` (device, one int32 per frame, optional) receives 1 for
 // frames that turned out not to be strict q8: their output is NOT valid and the caller must redo them with
 // DCMT_PATH_GENERIC.  *used_fused tells the caller which path ran.
+//
+// Input is either float32 metres (`sparse`, sharing pitch / fstride with the output) or -- `in16.p` non-null -- KITTI
+// uint16 (metres * 256, main.cpp:75-82) with its own pitch / frame stride in elements.  uint16 input is strict q8 by
+// construction: the fused kernels read it directly and nothing is validated or redone; shapes the fused kernels do
+// not serve get a convertTo(CV_32F, 1/256) (main.cpp:79) into a workspace plane in front of the generic pipeline.
+struct U16Input {
+    const uint16_t* p = nullptr;
+    size_t pitch = 0, fstride = 0;  // elements
+};
+
 int enqueue_completion(const CompletionCall& cc, const float* sparse, const int32_t* labels, float* dense, size_t pitch,
                        size_t fstride, int n_frames, int32_t* stats, int32_t* redo_flags, float* stages,
-                       uint32_t* stage_mask, Arena* ar, cudaStream_t st, bool* used_fused) {
+                       uint32_t* stage_mask, Arena* ar, cudaStream_t st, bool* used_fused, U16Input in16 = U16Input{}) {
     const int rows = cc.rows, cols = cc.cols;
     const bool bilateral = cc.blur == DCMT_BLUR_BILATERAL;
     const bool fused = fused_applies(cc) && !stages;
@@ -233,8 +245,13 @@ int enqueue_completion(const CompletionCall& cc, const float* sparse, const int3
             const int nf = n_frames - f0 < chunk ? n_frames - f0 : chunk;
             ProfEvents pe{};
             API_CUDA(prof_mark(st, 0, &pe), "profiling event");
-            API_CUDA(dcmt::q8_run_front(p, sparse + (size_t)f0 * fstride, pitch, fstride, nf, cc.flags != DCMT_PATH_FUSED, st),
-                     "fused front launch");
+            if (in16.p)
+                API_CUDA(dcmt::q8_run_front(p, nullptr, in16.p + (size_t)f0 * in16.fstride, in16.pitch, in16.fstride, nf, 0, st),
+                         "fused front launch");
+            else
+                API_CUDA(dcmt::q8_run_front(p, sparse + (size_t)f0 * fstride, nullptr, pitch, fstride, nf,
+                                            cc.flags != DCMT_PATH_FUSED, st),
+                         "fused front launch");
             API_CUDA(prof_mark(st, 1, &pe), "profiling event");
             API_CUDA(dcmt::q8_run_tail(p, dense + (size_t)f0 * fstride, pitch, fstride, nf, cc.blur, st), "fused tail launch");
             API_CUDA(prof_mark(st, 2, &pe), "profiling event");
@@ -249,12 +266,21 @@ int enqueue_completion(const CompletionCall& cc, const float* sparse, const int3
         }
         return DCMT_OK;
     }
+    float* conv = in16.p ? carve<float>(ar, fpix * chunk) : nullptr;
     for (int f0 = 0; f0 < n_frames; f0 += chunk) {
         const int nf = n_frames - f0 < chunk ? n_frames - f0 : chunk;
         dcmt::GenericChunk c{};
-        c.in = sparse + (size_t)f0 * fstride;
-        c.in_pitch = pitch;
-        c.in_fstride = fstride;
+        if (in16.p) {
+            API_CUDA(dcmt::q8_convert_u16(in16.p + (size_t)f0 * in16.fstride, in16.pitch, in16.fstride, conv, rows, cols, nf, st),
+                     "uint16 conversion launch");
+            c.in = conv;
+            c.in_pitch = (size_t)cols;
+            c.in_fstride = fpix;
+        } else {
+            c.in = sparse + (size_t)f0 * fstride;
+            c.in_pitch = pitch;
+            c.in_fstride = fstride;
+        }
         c.labels = cc.guided ? labels + (size_t)f0 * fpix : nullptr;
         c.n_clusters = cc.n_clusters;
         c.guided = cc.guided;
@@ -477,6 +503,104 @@ int run_completion_host(const float* sparse, const int32_t* labels, int n_cluste
     return DCMT_OK;
 }
 
+// ---- KITTI uint16 input (main.cpp:75-82: imread(IMREAD_ANYDEPTH) + convertTo(CV_32F, 1/256) + img_completion) ----
+int validate_completion_u16(const uint16_t* sparse, float* dense, int rows, int cols, size_t in_pitch_bytes,
+                            size_t in_frame_stride_bytes, size_t out_pitch_bytes, size_t out_frame_stride_bytes, int n_frames,
+                            int blur_type, int flags, Geometry* gi, Geometry* go) {
+    if (!sparse || !dense) return fail(DCMT_E_BADARG, "null image pointer");
+    if (blur_type < DCMT_BLUR_NONE || blur_type > DCMT_BLUR_BILATERAL) return fail(DCMT_E_BADARG, "blur_type %d", blur_type);
+    if (flags < DCMT_PATH_AUTO || flags > DCMT_PATH_FUSED) return fail(DCMT_E_BADARG, "flags %d", flags);
+    int rc = check_geometry(rows, cols, in_pitch_bytes, in_frame_stride_bytes, n_frames, gi, sizeof(uint16_t));
+    if (rc) return rc;
+    if ((rc = check_geometry(rows, cols, out_pitch_bytes, out_frame_stride_bytes, n_frames, go, sizeof(float)))) return rc;
+    if (n_frames && overlaps(sparse, gi->span_bytes, dense, go->span_bytes)) return fail(DCMT_E_BADARG, "input and output overlap");
+    return DCMT_OK;
+}
+
+int run_completion_u16(const uint16_t* sparse, float* dense, int rows, int cols, size_t in_pitch_bytes,
+                       size_t in_frame_stride_bytes, size_t out_pitch_bytes, size_t out_frame_stride_bytes, int n_frames,
+                       int blur_type, int flags, int32_t* stats, cudaStream_t st) {
+    Geometry gi, go;
+    int rc = validate_completion_u16(sparse, dense, rows, cols, in_pitch_bytes, in_frame_stride_bytes, out_pitch_bytes,
+                                     out_frame_stride_bytes, n_frames, blur_type, flags, &gi, &go);
+    if (rc) return rc;
+    if (n_frames == 0) return DCMT_OK;
+    if ((rc = check_device())) return rc;
+    API_CUDA(dcmt::generic_configure(), "kernel attribute setup");
+    API_CUDA(dcmt::q8_configure(), "kernel attribute setup");
+    // uint16 input needs no validation: AUTO and FUSED are the same thing here
+    CompletionCall cc{nullptr, 0, false, rows, cols, blur_type, flags == DCMT_PATH_GENERIC ? DCMT_PATH_GENERIC : DCMT_PATH_FUSED};
+    const bool fused = fused_applies(cc);
+    Arena* ar = nullptr;
+    if ((rc = arena_acquire(st, completion_ws_bytes(rows, cols, n_frames, blur_type == DCMT_BLUR_BILATERAL, fused, true), &ar))) return rc;
+    return enqueue_completion(cc, nullptr, nullptr, dense, go.pitch, go.fstride, n_frames, stats, nullptr, nullptr, nullptr, ar, st,
+                              nullptr, U16Input{sparse, gi.pitch, gi.fstride});
+}
+
+int run_completion_u16_host(const uint16_t* sparse, float* dense, int rows, int cols, size_t in_pitch_bytes,
+                            size_t in_frame_stride_bytes, size_t out_pitch_bytes, size_t out_frame_stride_bytes, int n_frames,
+                            int blur_type, int flags, int32_t* stats) {
+    Geometry gi, go;
+    int rc = validate_completion_u16(sparse, dense, rows, cols, in_pitch_bytes, in_frame_stride_bytes, out_pitch_bytes,
+                                     out_frame_stride_bytes, n_frames, blur_type, flags, &gi, &go);
+    if (rc) return rc;
+    if (n_frames == 0) return DCMT_OK;
+    if ((rc = check_device())) return rc;
+    API_CUDA(dcmt::generic_configure(), "kernel attribute setup");
+    API_CUDA(dcmt::q8_configure(), "kernel attribute setup");
+    HostStreams* hs = nullptr;
+    if ((rc = host_streams(&hs))) return rc;
+    const size_t fpix = (size_t)rows * cols;
+    const size_t in_pitch = ((size_t)cols + 7) / 8 * 8;  // device rows 16-byte aligned: vector loads in k_q8_front
+    const int hc = host_chunk_frames(rows, cols, n_frames);
+    CompletionCall cc{nullptr, 0, false, rows, cols, blur_type, flags == DCMT_PATH_GENERIC ? DCMT_PATH_GENERIC : DCMT_PATH_FUSED};
+    const bool fused = fused_applies(cc);
+    const size_t bytes = carve_bytes((size_t)rows * in_pitch * hc, sizeof(uint16_t)) + carve_bytes(fpix * hc, sizeof(float)) +
+                         carve_bytes((size_t)hc * DCMT_STATS_STRIDE, sizeof(int32_t)) +
+                         completion_ws_bytes(rows, cols, hc, blur_type == DCMT_BLUR_BILATERAL, fused, true);
+    int slot = 0;
+    for (int f0 = 0; f0 < n_frames; f0 += hc, slot = (slot + 1) % kHostStreams) {
+        const int nf = n_frames - f0 < hc ? n_frames - f0 : hc;
+        cudaStream_t st = hs->s[slot];
+        Arena* ar = nullptr;
+        if ((rc = arena_acquire(st, bytes, &ar))) return rc;
+        uint16_t* d_in = carve<uint16_t>(ar, (size_t)rows * in_pitch * hc);
+        float* d_out = carve<float>(ar, fpix * hc);
+        int32_t* d_stats = carve<int32_t>(ar, (size_t)hc * DCMT_STATS_STRIDE);
+        const uint16_t* h_in = sparse + (size_t)f0 * gi.fstride;
+        float* h_out = dense + (size_t)f0 * go.fstride;
+        if (in_pitch == (size_t)cols && gi.pitch == (size_t)cols && gi.fstride == fpix) {
+            API_CUDA(cudaMemcpyAsync(d_in, h_in, fpix * nf * sizeof(uint16_t), cudaMemcpyHostToDevice, st), "host to device copy");
+        } else if (gi.fstride == gi.pitch * (size_t)rows) {  // frames back to back: one 2-D copy for the whole chunk
+            API_CUDA(cudaMemcpy2DAsync(d_in, in_pitch * sizeof(uint16_t), h_in, gi.pitch * sizeof(uint16_t),
+                                       (size_t)cols * sizeof(uint16_t), (size_t)rows * nf, cudaMemcpyHostToDevice, st),
+                     "host to device copy");
+        } else {
+            for (int f = 0; f < nf; ++f)
+                API_CUDA(cudaMemcpy2DAsync(d_in + (size_t)f * rows * in_pitch, in_pitch * sizeof(uint16_t), h_in + (size_t)f * gi.fstride,
+                                           gi.pitch * sizeof(uint16_t), (size_t)cols * sizeof(uint16_t), rows, cudaMemcpyHostToDevice, st),
+                         "host to device copy");
+        }
+        if ((rc = enqueue_completion(cc, nullptr, nullptr, d_out, cols, fpix, nf, stats ? d_stats : nullptr, nullptr, nullptr, nullptr,
+                                     ar, st, nullptr, U16Input{d_in, in_pitch, (size_t)rows * in_pitch})))
+            return rc;
+        if (go.pitch == (size_t)cols && go.fstride == fpix) {
+            API_CUDA(cudaMemcpyAsync(h_out, d_out, fpix * nf * sizeof(float), cudaMemcpyDeviceToHost, st), "device to host copy");
+        } else {
+            for (int f = 0; f < nf; ++f)
+                API_CUDA(cudaMemcpy2DAsync(h_out + (size_t)f * go.fstride, go.pitch * sizeof(float), d_out + (size_t)f * fpix,
+                                           (size_t)cols * sizeof(float), (size_t)cols * sizeof(float), rows, cudaMemcpyDeviceToHost, st),
+                         "device to host copy");
+        }
+        if (stats)
+            API_CUDA(cudaMemcpyAsync(stats + (size_t)f0 * DCMT_STATS_STRIDE, d_stats, (size_t)nf * DCMT_STATS_STRIDE * sizeof(int32_t),
+                                     cudaMemcpyDeviceToHost, st),
+                     "device to host copy");
+    }
+    for (int i = 0; i < kHostStreams; ++i) API_CUDA(cudaStreamSynchronize(hs->s[i]), "kernel execution");
+    return DCMT_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -561,6 +685,20 @@ int dcmt_img_completion_f32_host(const float* sparse, float* dense, int rows, in
                                blur_type, flags, stats);
 }
 
+int dcmt_img_completion_u16(const uint16_t* sparse_u16, float* dense, int rows, int cols, size_t in_pitch_bytes,
+                            size_t in_frame_stride_bytes, size_t out_pitch_bytes, size_t out_frame_stride_bytes, int n_frames,
+                            int blur_type, int flags, int32_t* stats, void* cuda_stream) {
+    return run_completion_u16(sparse_u16, dense, rows, cols, in_pitch_bytes, in_frame_stride_bytes, out_pitch_bytes,
+                              out_frame_stride_bytes, n_frames, blur_type, flags, stats, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int dcmt_img_completion_u16_host(const uint16_t* sparse_u16, float* dense, int rows, int cols, size_t in_pitch_bytes,
+                                 size_t in_frame_stride_bytes, size_t out_pitch_bytes, size_t out_frame_stride_bytes,
+                                 int n_frames, int blur_type, int flags, int32_t* stats) {
+    return run_completion_u16_host(sparse_u16, dense, rows, cols, in_pitch_bytes, in_frame_stride_bytes, out_pitch_bytes,
+                                   out_frame_stride_bytes, n_frames, blur_type, flags, stats);
+}
+
 int dcmt_interpolate_with_superpixels_f32(const float* sparse, const int32_t* labels, int n_clusters, float* dense,
                                           int rows, int cols, size_t pitch_bytes, size_t frame_stride_bytes, int n_frames,
                                           int use_superpixel, int32_t* stats, void* cuda_stream) {
@@ -618,7 +756,7 @@ int dcmt_debug_q8_phase_cycles(const float* sparse, float* dense, int rows, int 
     p.prof_front = front_stamps;
     p.prof_tail = tail_stamps;
     if (tiles_per_frame) *tiles_per_frame = ((cols + p.tw - 1) / p.tw) * ((rows + p.th - 1) / p.th);
-    API_CUDA(dcmt::q8_run_front(p, sparse, cols, fpix, n_frames, 1, st), "fused front launch");
+    API_CUDA(dcmt::q8_run_front(p, sparse, nullptr, cols, fpix, n_frames, 1, st), "fused front launch");
     API_CUDA(dcmt::q8_run_tail(p, dense, cols, fpix, n_frames, DCMT_BLUR_GAUSSIAN, st), "fused tail launch");
     return DCMT_OK;
 }

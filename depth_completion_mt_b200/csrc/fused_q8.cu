@@ -117,7 +117,8 @@ __device__ __forceinline__ uint32_t encode_pair(float v0, float v1, float& bad) 
 }
 
 struct FrontArgs {
-    const float* in;
+    const float* in;              // float32 metres ...
+    const uint16_t* in16;         // ... or KITTI uint16 (metres * 256), exactly one of the two
     size_t in_pitch, in_fstride;  // elements
     uint16_t* mid;                // rows x mid_pitch uint16 per frame
     size_t mid_pitch, mid_fstride;
@@ -291,6 +292,66 @@ __device__ __forceinline__ void front_passes(uint32_t* A, uint32_t* B, const Til
     __syncthreads();
 }
 
+// Encode two KITTI uint16 pixels (k = metres * 256, main.cpp:75-82) packed in one word: the convertTo(CV_32F, 1/256)
+// of main.cpp:79 and the inversion of img_completion.cpp:55-67 in integer form.  Per lane: t = 25601 - k (mod 2^16);
+// the pixel is valid iff 27 <= t <= 25575 (<=> 26 <= k <= 25574), otherwise it is a hole (e = 1).
+__device__ __forceinline__ uint32_t encode_u16_pair(uint32_t w) {
+    const uint32_t t = __vsub2(SPLAT16(25601), w);
+    const uint32_t u = __vsub2(t, SPLAT16(27));              // valid lanes: 0 .. 25548
+    const uint32_t c = pmin(u, SPLAT16(25549)) ^ SPLAT16(25549);  // zero lane <=> invalid; both operands < 0x8000
+    const uint32_t nz = ((c + SPLAT16(0x7fff)) >> 15) & 0x00010001u;  // 1 per valid lane (no carry between lanes)
+    const uint32_t m = nz * 0xffffu;                          // 0xffff per valid lane
+    return (t & m) | (SPLAT16(1) & ~m);
+}
+
+// pass 0 for uint16 input: one 16-byte load per quad, batches of three items
+__device__ __forceinline__ void front_load16(const FrontArgs& a, const uint16_t* in0, uint32_t* A, const Tile& t, Items i, BorderMasks bm,
+                                             int gx0) {
+    const int pitch = (int)a.in_pitch;
+    uint32_t mo = bm.out, ms = bm.str;
+#pragma unroll 1
+    for (int k0 = 0; k0 < KF; k0 += 3) {
+        uint4 v[3];
+        const uint16_t* ptr[3];
+        int lin[3], gx[3];
+        bool live[3], vec[3], sca[3];
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+            lin[u] = i.lin;
+            live[u] = i.r < t.RH;
+            const bool inside = live[u] && !(mo & 1u);
+            vec[u] = inside && !(ms & 1u) && a.vec_ok;
+            sca[u] = inside && !vec[u];
+            ptr[u] = in0 + (i.r * pitch + i.q * 8);
+            gx[u] = gx0 + i.q * 8;
+            v[u] = make_uint4(0u, 0u, 0u, 0u);
+            if (vec[u]) v[u] = __ldg(reinterpret_cast<const uint4*>(ptr[u]));
+            i.next();
+            mo >>= 1;
+            ms >>= 1;
+        }
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+            if (!live[u]) continue;
+            uint4 o = splat4(kAbsMax);  // outside the image: absent
+            if (vec[u]) {
+                o = make_uint4(encode_u16_pair(v[u].x), encode_u16_pair(v[u].y), encode_u16_pair(v[u].z), encode_u16_pair(v[u].w));
+            } else if (sca[u]) {
+                uint32_t w[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t k0_ = gx[u] + 2 * j < a.cols ? (uint32_t)__ldg(ptr[u] + 2 * j) : 0u;
+                    const uint32_t k1_ = gx[u] + 2 * j + 1 < a.cols ? (uint32_t)__ldg(ptr[u] + 2 * j + 1) : 0u;
+                    const uint32_t e = encode_u16_pair(k0_ | (k1_ << 16));
+                    w[j] = (gx[u] + 2 * j < a.cols ? (e & 0xffffu) : 0u) | (gx[u] + 2 * j + 1 < a.cols ? (e & 0xffff0000u) : 0u);
+                }
+                o = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+            sts4(A + lin[u] * 4, o);
+        }
+    }
+}
+
 // pass 0: load, validate, invert, encode (:55-67).  Items go in batches of three so that six 16-byte global loads
 // per thread are in flight before the first one is consumed.
 template <bool kValidate>
@@ -359,15 +420,16 @@ __global__ void __launch_bounds__(QT, 2) k_q8_front(FrontArgs a) {
     t.rlo = max(0, -gy0);
     t.rhi = min(t.RH, rows - gy0);
     tile_columns(t, gx0, cols);
-    const float* in0 = a.in + (size_t)frame * a.in_fstride + ((ptrdiff_t)gy0 * (ptrdiff_t)a.in_pitch + gx0);
+    const ptrdiff_t origin = (ptrdiff_t)frame * (ptrdiff_t)a.in_fstride + ((ptrdiff_t)gy0 * (ptrdiff_t)a.in_pitch + gx0);
     const bool border = gy0 < 0 || gy0 + t.RH > rows || gx0 < 0 || gx0 + t.RQ * 8 > cols;
     const Items it_rq(t.RQ);
     const BorderMasks bm = border_masks(t, it_rq, border);
 
     DCMT_STAMP(a, 0);
     float bad = 0.0f;
-    if (a.validate) front_load<true>(a, in0, A, t, it_rq, bm, gx0, bad);
-    else front_load<false>(a, in0, A, t, it_rq, bm, gx0, bad);
+    if (a.in16) front_load16(a, a.in16 + origin, A, t, it_rq, bm, gx0);  // uint16 input is q8 by construction
+    else if (a.validate) front_load<true>(a, a.in + origin, A, t, it_rq, bm, gx0, bad);
+    else front_load<false>(a, a.in + origin, A, t, it_rq, bm, gx0, bad);
     if (__syncthreads_or(bad != 0.0f)) {  // not strict q8: this frame is redone by the generic pipeline
         if (threadIdx.x == 0) a.ctr[frame].needs_generic = 1;
         return;
@@ -476,15 +538,18 @@ struct PackedOps {
     static __device__ __forceinline__ uint32_t mx3(uint32_t a, uint32_t b, uint32_t c) { return pmax3(a, b, c); }
 };
 
+template <bool kOnFma>
 __device__ __forceinline__ void pcswap(uint32_t& a, uint32_t& b, uint32_t one) {
     const uint32_t lo = pmin(a, b);
-    b = other_of_pair(a, b, lo, one);
+    b = kOnFma ? other_of_pair(a, b, lo, one) : pmax(a, b);
     a = lo;
 }
-// optimal 9-comparator sort of five packed words (both lanes independently)
+// optimal 9-comparator sort of five packed words (both lanes independently).  Five of the nine maxima are computed
+// on the FMA pipe, four on the ALU pipe: with the selection network's own mix this loads both pipes equally.
 __device__ __forceinline__ void sort5(uint32_t (&v)[5], uint32_t one) {
-    pcswap(v[0], v[1], one); pcswap(v[3], v[4], one); pcswap(v[2], v[4], one); pcswap(v[2], v[3], one); pcswap(v[0], v[3], one);
-    pcswap(v[0], v[2], one); pcswap(v[1], v[4], one); pcswap(v[1], v[3], one); pcswap(v[1], v[2], one);
+    pcswap<true>(v[0], v[1], one); pcswap<false>(v[3], v[4], one); pcswap<true>(v[2], v[4], one);
+    pcswap<false>(v[2], v[3], one); pcswap<true>(v[0], v[3], one); pcswap<false>(v[0], v[2], one);
+    pcswap<true>(v[1], v[4], one); pcswap<false>(v[1], v[3], one); pcswap<true>(v[1], v[2], one);
 }
 
 // lanes equal to 1 (holes) -> 0xffff mask per lane
@@ -922,6 +987,12 @@ __global__ void __launch_bounds__(1024) k_q8_fixup(FixupArgs a) {
     if (threadIdx.x == 0) a.ctr[slot].extra_passes = passes - 1;
 }
 
+// main.cpp:79 `convertTo(CV_32F, 1.0 / 256.0)` for frames the fused kernels do not serve (generic pipeline input)
+__global__ void k_u16_to_f32(const uint16_t* __restrict__ in, size_t in_pitch, size_t in_fstride, float* __restrict__ out, int rows, int cols) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, f = blockIdx.z;
+    if (x < cols) out[((size_t)f * rows + y) * cols + x] = (float)in[(size_t)f * in_fstride + (size_t)y * in_pitch + x] * (1.0f / 256.0f);
+}
+
 __global__ void k_q8_zero_counters(FrameCounters* c, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { c[i] = FrameCounters{}; c[i].path = 1; }
@@ -961,14 +1032,17 @@ cudaError_t q8_configure() {
     return cudaFuncSetAttribute(k_q8_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 }
 
-cudaError_t q8_run_front(const Q8Plan& p, const float* in, size_t in_pitch, size_t in_fstride, int n_frames, int validate,
-                         cudaStream_t st) {
+cudaError_t q8_run_front(const Q8Plan& p, const float* in, const uint16_t* in16, size_t in_pitch, size_t in_fstride, int n_frames,
+                         int validate, cudaStream_t st) {
     const size_t ncol = (size_t)p.mid_pitch * n_frames;
     DCMT_LAUNCH(k_q8_zero_counters, dim3((n_frames + 127) / 128), dim3(128), 0, st, p.ctr, n_frames);
     DCMT_LAUNCH(k_q8_init_cols, dim3((unsigned)((ncol + 255) / 256)), dim3(256), 0, st, p.col_first, p.col_last, ncol);
-    FrontArgs a{in, in_pitch, in_fstride, p.mid, (size_t)p.mid_pitch, (size_t)p.mid_pitch * p.rows, p.col_first, p.col_last,
-                p.ctr, p.rows, p.cols, p.th, p.tw,
-                (int)(in_pitch % 4 == 0 && in_fstride % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0), validate, p.prof_front};
+    // 16-byte vector loads need 16-byte aligned rows: 4 floats or 8 uint16 per unit
+    const size_t unit = in16 ? 8 : 4;
+    const uintptr_t base = in16 ? reinterpret_cast<uintptr_t>(in16) : reinterpret_cast<uintptr_t>(in);
+    FrontArgs a{in, in16, in_pitch, in_fstride, p.mid, (size_t)p.mid_pitch, (size_t)p.mid_pitch * p.rows, p.col_first, p.col_last,
+                p.ctr, p.rows, p.cols, p.th, p.tw, (int)(in_pitch % unit == 0 && in_fstride % unit == 0 && (base & 15) == 0), validate,
+                p.prof_front};
     const dim3 grid((p.cols + p.tw - 1) / p.tw, (p.rows + p.th - 1) / p.th, n_frames);
     DCMT_LAUNCH(k_q8_front, grid, dim3(QT), q8_front_smem(p.th, p.tw), st, a);
     return cudaGetLastError();
@@ -988,6 +1062,12 @@ cudaError_t q8_run_tail(const Q8Plan& p, float* out, size_t out_pitch, size_t ou
 
 cudaError_t q8_write_stats(const Q8Plan& p, int32_t* stats, int32_t* flags, int n_frames, cudaStream_t st) {
     DCMT_LAUNCH(k_q8_write_stats, dim3((n_frames + 127) / 128), dim3(128), 0, st, p.ctr, stats, flags, n_frames);
+    return cudaGetLastError();
+}
+
+cudaError_t q8_convert_u16(const uint16_t* in, size_t in_pitch, size_t in_fstride, float* out, int rows, int cols, int n_frames,
+                           cudaStream_t st) {
+    DCMT_LAUNCH(k_u16_to_f32, dim3((cols + 255) / 256, rows, n_frames), dim3(256), 0, st, in, in_pitch, in_fstride, out, rows, cols);
     return cudaGetLastError();
 }
 

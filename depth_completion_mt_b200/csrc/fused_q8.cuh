@@ -28,10 +28,14 @@ void q8_choose_tile(int rows, int cols, int* th, int* tw);
 size_t q8_front_smem(int th, int tw);
 size_t q8_tail_smem(int th, int tw);
 cudaError_t q8_configure();
-// A1..A4 for n_frames slots: in -> plan.mid (+ column keys, counters zeroed)
-// `validate` != 0: check strict q8-ness of every pixel (frames that fail are flagged for the generic pipeline)
-cudaError_t q8_run_front(const Q8Plan& p, const float* in, size_t in_pitch, size_t in_fstride, int n_frames, int validate,
-                         cudaStream_t st);
+// A1..A4 for n_frames slots: in (float32) or in16 (KITTI uint16 = metres * 256; exactly one is non-null) -> plan.mid
+// (+ column keys, counters zeroed).  `validate` != 0: check strict q8-ness of every float pixel (frames that fail are
+// flagged for the generic pipeline); uint16 input needs no check.  Pitches in elements of the input type.
+cudaError_t q8_run_front(const Q8Plan& p, const float* in, const uint16_t* in16, size_t in_pitch, size_t in_fstride, int n_frames,
+                         int validate, cudaStream_t st);
+// uint16 -> float32 metres (main.cpp:79) into a contiguous buffer, for frames served by the generic pipeline
+cudaError_t q8_convert_u16(const uint16_t* in, size_t in_pitch, size_t in_fstride, float* out, int rows, int cols, int n_frames,
+                           cudaStream_t st);
 // A5..A10: plan.mid -> out (float32), blur in {none, gaussian}; then the fix-up kernel
 cudaError_t q8_run_tail(const Q8Plan& p, float* out, size_t out_pitch, size_t out_fstride, int n_frames, int blur,
                         cudaStream_t st);

@@ -105,6 +105,20 @@ DCMT_API int dcmt_img_completion_f32_host(const float *sparse, float *dense, int
                                           size_t frame_stride_bytes, int n_frames, int blur_type, int flags,
                                           int32_t *stats_or_null);
 
+/* (a1, KITTI on-disk format) replaces the caller's sequence main.cpp:75-93: the uint16 payload of a KITTI depth PNG
+ * (cv::imread(..., IMREAD_ANYDEPTH)), convertTo(CV_32F, 1.0 / 256.0) (main.cpp:79) and img_completion (:93) in one
+ * call.  Input pixels are uint16 = metres * 256 (0 = empty), output is float32 metres as above.  Input and output have
+ * their own pitches / frame strides in bytes (0 = dense).  uint16 input is strict q8 by construction, so the fused
+ * kernels serve it without validation and the call never synchronises (DCMT_PATH_AUTO == DCMT_PATH_FUSED here);
+ * it moves 6 instead of 8 bytes per pixel through HBM and halves the host-to-device copy of the *_host variant. */
+DCMT_API int dcmt_img_completion_u16(const uint16_t *sparse_u16, float *dense, int rows, int cols, size_t in_pitch_bytes,
+                                     size_t in_frame_stride_bytes, size_t out_pitch_bytes, size_t out_frame_stride_bytes,
+                                     int n_frames, int blur_type, int flags, int32_t *stats_or_null, void *cuda_stream);
+DCMT_API int dcmt_img_completion_u16_host(const uint16_t *sparse_u16, float *dense, int rows, int cols,
+                                          size_t in_pitch_bytes, size_t in_frame_stride_bytes, size_t out_pitch_bytes,
+                                          size_t out_frame_stride_bytes, int n_frames, int blur_type, int flags,
+                                          int32_t *stats_or_null);
+
 /* (a2) replaces interpolate_with_superpixels(Slic&, const cv::Mat&, cv::Mat&, const std::string&, int)
  * -- src/DC_lidar_camera/img_completion_lc.cpp:34-203.  `labels` is the Slic::clusters label map as
  * row-major int32 [row][col] (the reference stores [col][row], :83; the C++ shim transposes),

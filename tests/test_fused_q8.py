@@ -99,7 +99,62 @@ def body_multipass(be):
         assert_bit_equal(out[i], co.img_completion(b[i], "gaussian"), f"frame {i}")
 
 
+def body_u16(be, shapes):
+    """KITTI uint16 input (main.cpp:75-82: PNG payload, convertTo(CV_32F, 1/256), img_completion): same bytes as the
+    float32 call on d16 / 256, for every uint16 code, aligned and unaligned widths, fused and generic routing."""
+    for i, (rows, cols, p) in enumerate(shapes):
+        d16 = synth.sparse_depth_q8(300 + i, rows, cols, p, kitti_like=bool(i & 1))
+        s = d16.astype(np.float32) / np.float32(256)
+        for blur in ("gaussian", "none"):
+            out, st = be.img_completion(d16, blur, return_stats=True)
+            ref_st = {}
+            assert_bit_equal(out, co.img_completion(s, blur, ref_st), f"u16 {rows}x{cols} {blur}")
+            assert int(st[0, 0]) == ref_st["loop_passes"] and int(st[0, 2]) == ref_st["holes_after_extrapolation"]
+            assert int(st[0, 3]) == (1 if rows >= 32 and cols >= 32 else 0)
+    # every uint16 code once (256 x 256), then sparsified so that the pipeline has holes to fill
+    codes = np.arange(65536, dtype=np.uint16).reshape(256, 256)
+    rng = np.random.default_rng(12)
+    codes = np.where(rng.random(codes.shape) < 0.15, rng.permutation(codes.ravel()).reshape(256, 256), 0).astype(np.uint16)
+    s = codes.astype(np.float32) / np.float32(256)
+    assert_bit_equal(be.img_completion(codes, "gaussian"), co.img_completion(s, "gaussian"), "all uint16 codes")
+    assert_bit_equal(be.img_completion(codes, "gaussian", path="generic"), co.img_completion(s, "gaussian"), "all codes, generic")
+    # bilateral is served by the generic pipeline behind the conversion kernel
+    d16 = synth.sparse_depth_q8(17, 64, 96, 0.05)
+    out = be.img_completion(d16, "bilateral")
+    assert np.abs(out - co.img_completion(d16.astype(np.float32) / np.float32(256), "bilateral")).max() <= 2e-4
+    # batch
+    b16 = np.stack([synth.sparse_depth_q8(400 + f, 64, 96, 0.05) for f in range(5)])
+    outb = be.img_completion(b16, "gaussian")
+    for f in range(5):
+        assert_bit_equal(outb[f], co.img_completion(b16[f].astype(np.float32) / np.float32(256), "gaussian"), f"u16 batch frame {f}")
+
+
+def body_u16_pitched(lib):
+    rows, cols, ipitch, opitch = 40, 70, 77, 75  # odd pitches: neither side is 16-byte aligned
+    d16 = synth.sparse_depth_q8(21, rows, cols, 0.06)
+    src = np.full((2, rows + 1, ipitch), 7, np.uint16)
+    src[0, :rows, :cols] = d16
+    src[1, :rows, :cols] = d16[::-1]
+    dst = np.full((2, rows + 2, opitch), -3.0, np.float32)
+    rc = lib.dcmt_img_completion_u16_host(src.ctypes.data_as(C.c_void_p), dst.ctypes.data_as(C.c_void_p), rows, cols, ipitch * 2,
+                                          (rows + 1) * ipitch * 2, opitch * 4, (rows + 2) * opitch * 4, 2, 1, 0, None)
+    assert rc == 0, lib.dcmt_last_error()
+    assert_bit_equal(dst[0, :rows, :cols].copy(), co.img_completion(d16.astype(np.float32) / np.float32(256), "gaussian"), "pitched u16 f0")
+    assert_bit_equal(dst[1, :rows, :cols].copy(), co.img_completion(d16[::-1].astype(np.float32) / np.float32(256), "gaussian"), "pitched u16 f1")
+    assert (dst[:, :, cols:] == -3.0).all() and (dst[:, rows:] == -3.0).all()
+    # argument errors: pitch too small for uint16 columns, aliasing
+    assert lib.dcmt_img_completion_u16_host(src.ctypes.data_as(C.c_void_p), dst.ctypes.data_as(C.c_void_p), rows, cols, cols * 2 - 2, 0,
+                                            0, 0, 1, 1, 0, None) == -1
+    assert lib.dcmt_img_completion_u16_host(dst.ctypes.data_as(C.c_void_p), dst.ctypes.data_as(C.c_void_p), rows, cols, 0, 0, 0, 0, 1, 1,
+                                            0, None) == -1
+
+
 # ------------------------------------------------------------------ CPU: emulator build
+def test_emu_u16(emu_lib):
+    body_u16(Backend(emu_lib, "emu"), [(32, 32, 0.1), (33, 47, 0.05), (97, 171, 0.03), (20, 24, 0.2), (96, 160, 0.2)])
+    body_u16_pitched(emu_lib)
+
+
 def test_emu_shapes(emu_lib):
     body_shapes(Backend(emu_lib, "emu"), [(32, 32, 0.1), (33, 47, 0.05), (97, 171, 0.03), (100, 321, 0.02), (193, 40, 0.05), (96, 160, 0.2)])
 
@@ -171,6 +226,13 @@ def test_emu_pitched_input_takes_scalar_loads(emu_lib):
 def test_gpu_shapes(gpu_lib, mode):
     body_shapes(Backend(gpu_lib, mode), [(32, 32, 0.1), (33, 47, 0.05), (97, 171, 0.03), (100, 321, 0.02), (193, 40, 0.05), (96, 160, 0.2),
                                          (352, 1216, 0.05), (375, 1242, 0.05), (512, 1760, 0.02)])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["gpu_host", "gpu_device"])
+def test_gpu_u16(gpu_lib, mode):
+    body_u16(Backend(gpu_lib, mode), [(32, 32, 0.1), (33, 47, 0.05), (97, 171, 0.03), (20, 24, 0.2), (352, 1216, 0.05), (375, 1242, 0.05)])
+    body_u16_pitched(gpu_lib)
 
 
 @pytest.mark.gpu
