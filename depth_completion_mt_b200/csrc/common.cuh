@@ -7,9 +7,10 @@
 // CPU emulation of the CUDA execution model, tests only (tests/emu/cuda_emu.h); never defined for libdcmt.so
 #include "cuda_emu.h"
 #else
+#include <cuda.h>  // CUtensorMap and its enums only; the encoder is fetched with cudaGetDriverEntryPoint (no -lcuda)
 #include <cuda_runtime.h>
 #define DCMT_DYN_SMEM(type, name)                                         \
-    extern __shared__ __align__(16) unsigned char dcmt_dyn_smem_raw[];    \
+    extern __shared__ __align__(128) unsigned char dcmt_dyn_smem_raw[];   \
     type* name = reinterpret_cast<type*>(dcmt_dyn_smem_raw)
 // 16-byte asynchronous global -> shared copy (LDGSTS): no registers, many copies in flight per thread
 #define DCMT_CP_ASYNC_16(smem_ptr, gmem_ptr)                                                                        \
@@ -23,6 +24,69 @@ namespace dcmt { void note_launch(); }  // launch counter behind dcmt_launch_cou
 #endif
 
 namespace dcmt {
+
+// ---- TMA (cp.async.bulk.tensor) tile load of a uint16 plane: one thread issues one 3-D box copy (columns, rows,
+// frame) global -> shared; elements of the box outside the tensor are ZERO-filled by the hardware, the copy signals an
+// mbarrier with its byte count.  The emulator build replaces the map by a plain description and copies in place.
+#ifdef DCMT_EMU
+struct TensorMap3D {
+    const uint16_t* base;
+    int dim[3];         // elements: columns, rows, frames
+    size_t stride[2];   // bytes between rows, between frames
+    int box[2];         // columns, rows of the box (one frame)
+};
+inline cudaError_t tma_encode_u16_3d(TensorMap3D* m, const uint16_t* base, int cols, int rows, int frames, size_t row_bytes,
+                                     size_t frame_bytes, int box_cols, int box_rows) {
+    *m = TensorMap3D{base, {cols, rows, frames}, {row_bytes, frame_bytes}, {box_cols, box_rows}};
+    return cudaSuccess;
+}
+inline void tma_bar_init(uint64_t*) {}
+inline void tma_load_3d(void* smem_dst, const TensorMap3D* m, int c0, int c1, int c2, uint64_t*, uint32_t) {
+    uint16_t* d = static_cast<uint16_t*>(smem_dst);
+    for (int r = 0; r < m->box[1]; ++r)
+        for (int c = 0; c < m->box[0]; ++c) {
+            const int x = c0 + c, y = c1 + r;
+            const bool in = x >= 0 && x < m->dim[0] && y >= 0 && y < m->dim[1] && c2 >= 0 && c2 < m->dim[2];
+            d[(size_t)r * m->box[0] + c] =
+                in ? *reinterpret_cast<const uint16_t*>(reinterpret_cast<const char*>(m->base) + (size_t)c2 * m->stride[1] + (size_t)y * m->stride[0] + (size_t)x * 2)
+                   : (uint16_t)0;
+        }
+}
+inline void tma_bar_wait(uint64_t*, uint32_t) {}
+#else
+typedef CUtensorMap TensorMap3D;
+cudaError_t tma_encode_u16_3d(TensorMap3D* m, const uint16_t* base, int cols, int rows, int frames, size_t row_bytes,
+                              size_t frame_bytes, int box_cols, int box_rows);  // fused_q8.cu
+__device__ __forceinline__ void tma_bar_init(uint64_t* bar) {  // one thread; follow with __syncthreads()
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const TensorMap3D* m, int c0, int c1, int c2, uint64_t* bar, uint32_t bytes) {
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar), d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(d),
+                 "l"(reinterpret_cast<uint64_t>(m)), "r"(b), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_bar_wait(uint64_t* bar, uint32_t parity) {
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "DCMT_TMA_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DCMT_TMA_DONE;\n"
+        "bra DCMT_TMA_WAIT;\n"
+        "DCMT_TMA_DONE:\n"
+        "}" ::"r"(b),
+        "r"(parity)
+        : "memory");
+}
+#endif
+
+// x / n for x * n < 2^32 with magic = floor(2^32 / n) + 1 (computed on the host): one IMAD.HI instead of a division
+__device__ __forceinline__ int fast_div(int x, uint32_t magic) { return (int)__umulhi((uint32_t)x, magic); }
 
 // img_completion.cpp:59,96,113,140,154,184,194 compare float against the double literal 0.1:
 //   (double)d > 0.1  <=>  d >= 0.1f      (valid pixel)

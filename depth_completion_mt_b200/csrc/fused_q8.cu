@@ -17,6 +17,8 @@
 // No tensor cores: nothing here is a contraction.
 #include "fused_q8.cuh"
 
+#include <cstdlib>
+
 #include "median_f32.cuh"
 #include "median_net.cuh"
 
@@ -64,17 +66,20 @@ __device__ __forceinline__ uint4 mask_columns(uint4 v, int gx, int cols, uint32_
     return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-// Iterates item = threadIdx.x, threadIdx.x + QT, ... over an (nr x nq) grid as (r, q) without a division per item.
-// Built once per kernel for each row length it is used with (the constructor divides), then copied per loop;
-// `lin` is the linear item index r * nq + q.
+// Iterates item = threadIdx.x, threadIdx.x + nt, ... over an (nr x nq) grid as (r, q) without a division: the
+// descriptor (row length, per-step increments, magic reciprocal) is computed on the host for every row length a
+// kernel uses; `lin` is the linear item index r * nq + q.
+struct ItemsDesc {
+    int nq, dr, dq, nt;
+    uint32_t magic;  // floor(2^32 / nq) + 1
+};
+static ItemsDesc make_items(int nq, int nt) { return ItemsDesc{nq, nt / nq, nt % nq, nt, (uint32_t)((1ull << 32) / (unsigned)nq) + 1u}; }
 struct Items {
     int r, q, lin, dr, dq, nq, nt;
-    __device__ __forceinline__ explicit Items(int nq_, int nt_ = QT) : nq(nq_), nt(nt_) {
-        r = threadIdx.x / nq_;
-        q = threadIdx.x - r * nq_;
+    __device__ __forceinline__ explicit Items(const ItemsDesc& d) : dr(d.dr), dq(d.dq), nq(d.nq), nt(d.nt) {
+        r = fast_div((int)threadIdx.x, d.magic);
+        q = (int)threadIdx.x - r * d.nq;
         lin = threadIdx.x;
-        dr = nt_ / nq_;
-        dq = nt_ - dr * nq_;
     }
     __device__ __forceinline__ void next() {
         q += dq;
@@ -116,6 +121,14 @@ __device__ __forceinline__ uint32_t encode_pair(float v0, float v1, float& bad) 
     return __byte_perm(encode_bits<kValidate>(v0, bad), encode_bits<kValidate>(v1, bad), 0x5410);
 }
 
+// thread -> (row r0, quad q) of a grid that is nq quads wide: q is fixed per thread, rows advance by nrt = QT / nq per
+// sweep (threads with r0 >= nrt idle).  magic = floor(2^32 / nq) + 1 comes from the host: no division in the kernel.
+struct ColMap {
+    int nq, nrt;
+    uint32_t magic;
+};
+static ColMap make_colmap(int nq, int nthreads) { return ColMap{nq, nthreads / nq, (uint32_t)((1ull << 32) / (unsigned)nq) + 1u}; }
+
 struct FrontArgs {
     const float* in;              // float32 metres ...
     const uint16_t* in16;         // ... or KITTI uint16 (metres * 256), exactly one of the two
@@ -128,15 +141,25 @@ struct FrontArgs {
     int rows, cols, th, tw;
     int vec_ok;                   // input rows are 16-byte aligned: float4 loads
     int validate;                 // check strict q8-ness of every loaded pixel (DCMT_PATH_AUTO)
+    ColMap m_load, m_pass, m_core;  // region (RQ quads), computed quads (RQ - 1), core quads (tw / 8)
     long long* prof;              // optional: 16 clock64() stamps per CTA (debugging aid)
 };
 
 // ------------------------------------------------------------------------------------------------
 // k_q8_front.  Region = core (th x tw) + {up 8, down 9} rows, {left 8, right 16} columns (the dependency cone is
-// up 8 / down 9 / left 7 / right 9; widths are rounded to 8-pixel quads).  Every pass handles (row, quad) items,
-// reads neighbours from one shared-memory plane with 128-bit loads and writes the other plane.  The rows at the
-// region edge that lie outside every dependency cone are simply not computed, so no clamping is needed.  Cells
-// outside the image always hold the identity of the operator that reads them next (per-thread bit masks).
+// up 8 / down 9 / left 7 / right 9; widths are rounded to 8-pixel quads).  Two shared-memory planes; every pass reads
+// neighbours from one with 128-bit loads and writes the other.
+//
+// Border handling costs nothing inside the passes:
+//   * a thread owns one quad COLUMN for the whole kernel and walks down the rows, so "this quad is outside the image"
+//     is a per-thread constant (such threads idle) and the in-image row range is a loop bound uniform over the CTA;
+//   * cells outside the image are zeroed once in both planes and never written again, and every pass is a MAX:
+//     the erosion half of close5 runs on complemented values (min(a, b) = ~max(~a, ~b)), so 0 is the identity the
+//     next reader needs in every pass (absent tap, -FLT_MAX for the dilations, +FLT_MAX for the erosions);
+//   * each pass computes exactly the rows / quads later passes need (the rest of the region holds stale values no
+//     core pixel depends on), so nothing is clamped.
+// A frame width that is not a multiple of 8 leaves one quad straddling the right edge: its outside lanes are masked
+// in the kStraddle instantiation only.
 // ------------------------------------------------------------------------------------------------
 constexpr int FU = 8, FD = 9, FLQ = 1, FRQ = 2;  // rows up/down, quads left/right
 
@@ -175,40 +198,37 @@ __device__ __forceinline__ bool outside(const Tile& t, int r, int q) { return r 
 __device__ __forceinline__ uint4 blend(uint4 v, uint4 m, uint32_t ident) {
     return make_uint4((v.x & m.x) | (ident & ~m.x), (v.y & m.y) | (ident & ~m.y), (v.z & m.z) | (ident & ~m.z), (v.w & m.w) | (ident & ~m.w));
 }
+__device__ __forceinline__ uint4 and4(uint4 v, uint4 m) { return make_uint4(v.x & m.x, v.y & m.y, v.z & m.z, v.w & m.w); }
+__device__ __forceinline__ uint4 not4(uint4 v) { return make_uint4(~v.x, ~v.y, ~v.z, ~v.w); }
 
-// Cells outside the image must hold the identity of the operator that reads them next.  Every full-region pass
-// visits the same items per thread (item k of a thread is cell threadIdx.x + k * QT), so each thread computes once
-// which of its items lie outside the image (`out`) or straddle the right edge (`str`) -- one bit per item -- and
-// every pass just tests the bit.  Interior tiles have both masks zero: one code path, no extra barriers.
-struct BorderMasks {
-    uint32_t out, str;
+// what a thread needs to walk its quad column: first row, word offset of (r0, q), strides, activity, lane mask
+struct ColThread {
+    int r0, off0, nrt, dstep;
+    bool act;     // the thread owns a quad with at least one pixel inside the image
+    uint4 cmask;  // in-image lanes of that quad (all ones unless it straddles the right edge)
 };
-constexpr int KF = 6;  // items per thread upper bound: region quads <= KF * QT
-
-__device__ __forceinline__ BorderMasks border_masks(const Tile& t, Items i, bool border) {
-    BorderMasks m{0u, 0u};
-    if (border) {
-#pragma unroll
-        for (int k = 0; k < KF; ++k, i.next()) {
-            if (i.r >= t.RH) break;
-            if (outside(t, i.r, i.q)) m.out |= 1u << k;
-            else if (i.q == t.qs) m.str |= 1u << k;
-        }
-    }
-    return m;
+__device__ __forceinline__ ColThread col_thread(const ColMap& m, const Tile& t, int q_first) {
+    ColThread c;
+    c.r0 = fast_div((int)threadIdx.x, m.magic);
+    const int q = (int)threadIdx.x - c.r0 * m.nq + q_first;
+    c.off0 = (c.r0 * t.RQ + q) * 4;
+    c.nrt = m.nrt;
+    c.dstep = m.nrt * t.RQ * 4;
+    c.act = c.r0 < m.nrt && q >= t.qlo && q < t.qhi;
+    c.cmask = q == t.qs ? t.smask : make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+    return c;
 }
 
-// One pass over the region: item offsets [lo, hi) are computed by f(off), the edge rows outside every dependency
-// cone are skipped (no clamping, no guard rows: f may read up to the distance those rows provide).
-template <class F>
-__device__ __forceinline__ void region_pass(uint32_t* __restrict__ dst, int n4, int lo, int hi, BorderMasks bm, const Tile& t,
-                                            uint32_t ident_next, F f) {
-    uint32_t mo = bm.out, ms = bm.str;
+// One pass: rows [rb, re) of the thread's quad column, v = f(word offset).  rb <= 8 < nrt: at most one sweep is skipped.
+template <bool kStraddle, class F>
+__device__ __forceinline__ void col_pass(uint32_t* __restrict__ dst, const ColThread& c, int rb, int re, F f) {
+    if (!c.act) return;
+    int r = c.r0, off = c.off0;
+    if (r < rb) { r += c.nrt; off += c.dstep; }
 #pragma unroll 2
-    for (int off = threadIdx.x * 4; off < n4; off += QT * 4, mo >>= 1, ms >>= 1) {
-        if (off < lo || off >= hi) continue;
+    for (; r < re; r += c.nrt, off += c.dstep) {
         uint4 v = f(off);
-        if ((mo | ms) & 1u) v = (mo & 1u) ? splat4(ident_next) : blend(v, t.smask, ident_next);
+        if (kStraddle) v = and4(v, c.cmask);
         sts4(dst + off, v);
     }
 }
@@ -265,10 +285,15 @@ __device__ __forceinline__ uint32_t fill_holes(uint32_t d, uint32_t t) {
     return __vadd2(pmin(__vadd2(t, k), __vadd2(d, k)), SPLAT16(27));
 }
 
-__device__ __forceinline__ void front_passes(uint32_t* A, uint32_t* B, const Tile& t, BorderMasks bm) {
-    const int n4 = t.RH * t.RQ * 4, pw = t.pitchw;
+// Passes 1-6 on region rows (core rows are [FU, FU + th)); each pass covers the rows the later ones read:
+//   pass 7 needs V7 on the core rows <- D on core +- 3 <- H5 on core +- 5 (<- V5max on the same rows) <- 2-tap on core +- 7.
+template <bool kStraddle>
+__device__ __forceinline__ void front_passes(uint32_t* A, uint32_t* B, const Tile& t, const ColThread& c, int th) {
+    const int pw = t.pitchw;
+    auto rb = [&](int lo) { return max(lo, t.rlo); };
+    auto re = [&](int hi) { return min(hi, t.rhi); };
     // ---- pass 1: 2-tap dilate (:71-80)  out(y,x) = max(in(y-1,x+1), in(y+2,x+2)), absent taps = -FLT_MAX (e = 0)
-    region_pass(B, n4, pw, n4 - 2 * pw, bm, t, kAbsMax, [&](int off) {
+    col_pass<kStraddle>(B, c, rb(FU - 7), re(FU + th + 7), [&](int off) {
         const uint32_t* pa = A + off - pw;      // row y-1
         const uint32_t* pb = A + off + 2 * pw;  // row y+2
         const uint4 ca = lds4(pa), cb = lds4(pb);
@@ -278,17 +303,17 @@ __device__ __forceinline__ void front_passes(uint32_t* A, uint32_t* B, const Til
                           pmax(odd_pair(ca.w, na), nb));
     });
     __syncthreads();
-    // ---- passes 2-5: close5 (:84-85) = dilate5 (V, H) then erode5 (H, V)
-    region_pass(A, n4, 2 * pw, n4 - 2 * pw, bm, t, kAbsMax, [&](int off) { return v_window<2, true>(B + off, pw); });
+    // ---- passes 2-5: close5 (:84-85) = dilate5 (V, H) then erode5 (H, V); the erosions run on complemented values
+    col_pass<kStraddle>(A, c, rb(FU - 5), re(FU + th + 5), [&](int off) { return v_window<2, true>(B + off, pw); });
     __syncthreads();
-    region_pass(B, n4, 4, n4 - 4, bm, t, kAbsMin, [&](int off) { return h5_window<true>(A + off); });
+    col_pass<kStraddle>(B, c, rb(FU - 5), re(FU + th + 5), [&](int off) { return not4(h5_window<true>(A + off)); });
     __syncthreads();
-    region_pass(A, n4, 4, n4 - 4, bm, t, kAbsMin, [&](int off) { return h5_window<false>(B + off); });
+    col_pass<kStraddle>(A, c, rb(FU - 5), re(FU + th + 5), [&](int off) { return h5_window<true>(B + off); });
     __syncthreads();
-    region_pass(B, n4, 2 * pw, n4 - 2 * pw, bm, t, kAbsMax, [&](int off) { return v_window<2, false>(A + off, pw); });  // B = D
+    col_pass<kStraddle>(B, c, rb(FU - 3), re(FU + th + 3), [&](int off) { return not4(v_window<2, true>(A + off, pw)); });  // B = D
     __syncthreads();
     // ---- pass 6: vertical half of dilate7 (:88-90)
-    region_pass(A, n4, 3 * pw, n4 - 3 * pw, bm, t, kAbsMax, [&](int off) { return v_window<3, true>(B + off, pw); });
+    col_pass<kStraddle>(A, c, rb(FU), re(FU + th), [&](int off) { return v_window<3, true>(B + off, pw); });
     __syncthreads();
 }
 
@@ -304,106 +329,85 @@ __device__ __forceinline__ uint32_t encode_u16_pair(uint32_t w) {
     return (t & m) | (SPLAT16(1) & ~m);
 }
 
-// pass 0 for uint16 input: one 16-byte load per quad, batches of three items
-__device__ __forceinline__ void front_load16(const FrontArgs& a, const uint16_t* in0, uint32_t* A, const Tile& t, Items i, BorderMasks bm,
-                                             int gx0) {
-    const int pitch = (int)a.in_pitch;
-    uint32_t mo = bm.out, ms = bm.str;
-#pragma unroll 1
-    for (int k0 = 0; k0 < KF; k0 += 3) {
-        uint4 v[3];
-        const uint16_t* ptr[3];
-        int lin[3], gx[3];
-        bool live[3], vec[3], sca[3];
-#pragma unroll
-        for (int u = 0; u < 3; ++u) {
-            lin[u] = i.lin;
-            live[u] = i.r < t.RH;
-            const bool inside = live[u] && !(mo & 1u);
-            vec[u] = inside && !(ms & 1u) && a.vec_ok;
-            sca[u] = inside && !vec[u];
-            ptr[u] = in0 + (i.r * pitch + i.q * 8);
-            gx[u] = gx0 + i.q * 8;
-            v[u] = make_uint4(0u, 0u, 0u, 0u);
-            if (vec[u]) v[u] = __ldg(reinterpret_cast<const uint4*>(ptr[u]));
-            i.next();
-            mo >>= 1;
-            ms >>= 1;
-        }
-#pragma unroll
-        for (int u = 0; u < 3; ++u) {
-            if (!live[u]) continue;
-            uint4 o = splat4(kAbsMax);  // outside the image: absent
-            if (vec[u]) {
-                o = make_uint4(encode_u16_pair(v[u].x), encode_u16_pair(v[u].y), encode_u16_pair(v[u].z), encode_u16_pair(v[u].w));
-            } else if (sca[u]) {
-                uint32_t w[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const uint32_t k0_ = gx[u] + 2 * j < a.cols ? (uint32_t)__ldg(ptr[u] + 2 * j) : 0u;
-                    const uint32_t k1_ = gx[u] + 2 * j + 1 < a.cols ? (uint32_t)__ldg(ptr[u] + 2 * j + 1) : 0u;
-                    const uint32_t e = encode_u16_pair(k0_ | (k1_ << 16));
-                    w[j] = (gx[u] + 2 * j < a.cols ? (e & 0xffffu) : 0u) | (gx[u] + 2 * j + 1 < a.cols ? (e & 0xffff0000u) : 0u);
-                }
-                o = make_uint4(w[0], w[1], w[2], w[3]);
-            }
-            sts4(A + lin[u] * 4, o);
-        }
-    }
-}
-
-// pass 0: load, validate, invert, encode (:55-67).  Items go in batches of three so that six 16-byte global loads
-// per thread are in flight before the first one is consumed.
-template <bool kValidate>
-__device__ __forceinline__ void front_load(const FrontArgs& a, const float* in0, uint32_t* A, const Tile& t, Items i, BorderMasks bm,
-                                           int gx0, float& bad) {
+// pass 0: load, validate, invert, encode (:55-67) into plane A; cells outside the image are zeroed in BOTH planes.
+// Sweeps go in batches of three so that up to six 16-byte global loads per thread are in flight before the first
+// one is consumed.  kIn16: KITTI uint16 input (one 16-byte load per quad, no validation needed).
+template <bool kIn16, bool kValidate>
+__device__ __forceinline__ void front_load(const FrontArgs& a, const void* in0v, uint32_t* A, uint32_t* B, const Tile& t, int gx0,
+                                           float& bad) {
     // in0 points at region cell (0, 0) of the frame (possibly outside the buffer: only in-image cells are read)
-    const int pitch = (int)a.in_pitch;
-    uint32_t mo = bm.out, ms = bm.str;
+    const float* in0 = static_cast<const float*>(in0v);
+    const uint16_t* in0h = static_cast<const uint16_t*>(in0v);
+    const ColMap& m = a.m_load;
+    const int r0 = fast_div((int)threadIdx.x, m.magic), q = (int)threadIdx.x - r0 * m.nq;
+    if (r0 >= m.nrt) return;
+    const int pitch = (int)a.in_pitch, gx = gx0 + q * 8;
+    const bool q_in = q >= t.qlo && q < t.qhi;
+    const bool vec = q_in && q != t.qs && a.vec_ok;
+    const int dstep = m.nrt * t.pitchw;
+    int r = r0, off = (r0 * t.RQ + q) * 4;
 #pragma unroll 1
-    for (int k0 = 0; k0 < KF; k0 += 3) {
+    while (r < t.RH) {
         float4 f0[3], f1[3];
-        const float* ptr[3];
-        int lin[3], gx[3];
-        bool live[3], vec[3], sca[3];
+        uint4 h[3];
+        int offs[3], rr[3];
+        bool live[3], in[3];
 #pragma unroll
         for (int u = 0; u < 3; ++u) {
-            lin[u] = i.lin;
-            live[u] = i.r < t.RH;
-            const bool inside = live[u] && !(mo & 1u);
-            vec[u] = inside && !(ms & 1u) && a.vec_ok;
-            sca[u] = inside && !vec[u];
-            ptr[u] = in0 + (i.r * pitch + i.q * 8);
-            gx[u] = gx0 + i.q * 8;
+            offs[u] = off;
+            rr[u] = r;
+            live[u] = r < t.RH;
+            in[u] = live[u] && q_in && r >= t.rlo && r < t.rhi;
             f0[u] = f1[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (vec[u]) {
-                f0[u] = __ldg(reinterpret_cast<const float4*>(ptr[u]));
-                f1[u] = __ldg(reinterpret_cast<const float4*>(ptr[u]) + 1);
+            h[u] = make_uint4(0u, 0u, 0u, 0u);
+            if (in[u] && vec) {
+                if (kIn16) {
+                    h[u] = __ldg(reinterpret_cast<const uint4*>(in0h + (r * pitch + q * 8)));
+                } else {
+                    const float4* p = reinterpret_cast<const float4*>(in0 + (r * pitch + q * 8));
+                    f0[u] = __ldg(p);
+                    f1[u] = __ldg(p + 1);
+                }
             }
-            i.next();
-            mo >>= 1;
-            ms >>= 1;
+            r += m.nrt;
+            off += dstep;
         }
 #pragma unroll
         for (int u = 0; u < 3; ++u) {
             if (!live[u]) continue;
-            uint4 o = splat4(kAbsMax);  // outside the image: absent
-            if (vec[u]) {
-                o.x = encode_pair<kValidate>(f0[u].x, f0[u].y, bad);
-                o.y = encode_pair<kValidate>(f0[u].z, f0[u].w, bad);
-                o.z = encode_pair<kValidate>(f1[u].x, f1[u].y, bad);
-                o.w = encode_pair<kValidate>(f1[u].z, f1[u].w, bad);
-            } else if (sca[u]) {
+            if (!in[u]) {  // outside the image: absent, in both planes, for good
+                sts4(A + offs[u], splat4(0u));
+                sts4(B + offs[u], splat4(0u));
+                continue;
+            }
+            uint4 o;
+            if (vec) {
+                if (kIn16) {
+                    o = make_uint4(encode_u16_pair(h[u].x), encode_u16_pair(h[u].y), encode_u16_pair(h[u].z), encode_u16_pair(h[u].w));
+                } else {
+                    o.x = encode_pair<kValidate>(f0[u].x, f0[u].y, bad);
+                    o.y = encode_pair<kValidate>(f0[u].z, f0[u].w, bad);
+                    o.z = encode_pair<kValidate>(f1[u].x, f1[u].y, bad);
+                    o.w = encode_pair<kValidate>(f1[u].z, f1[u].w, bad);
+                }
+            } else {  // unaligned rows or the quad straddling the right edge: scalar loads, outside lanes absent
                 uint32_t e[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) e[j] = gx[u] + j < a.cols ? (encode_bits<kValidate>(__ldg(ptr[u] + j), bad) & 0xffffu) : 0u;
+                for (int j = 0; j < 8; ++j) {
+                    e[j] = 0u;
+                    if (gx + j < a.cols) {
+                        if (kIn16) e[j] = encode_u16_pair((uint32_t)__ldg(in0h + (rr[u] * pitch + q * 8 + j))) & 0xffffu;
+                        else e[j] = encode_bits<kValidate>(__ldg(in0 + (rr[u] * pitch + q * 8 + j)), bad) & 0xffffu;
+                    }
+                }
                 o = make_uint4(e[0] | (e[1] << 16), e[2] | (e[3] << 16), e[4] | (e[5] << 16), e[6] | (e[7] << 16));
             }
-            sts4(A + lin[u] * 4, o);
+            sts4(A + offs[u], o);
         }
     }
 }
 
+template <bool kStraddle>
 __global__ void __launch_bounds__(QT, 2) k_q8_front(FrontArgs a) {
     DCMT_DYN_SMEM(uint32_t, smem);
     const int th = a.th, tw = a.tw, rows = a.rows, cols = a.cols;
@@ -411,7 +415,9 @@ __global__ void __launch_bounds__(QT, 2) k_q8_front(FrontArgs a) {
     t.RH = th + FU + FD;
     t.RQ = tw / 8 + FLQ + FRQ;
     t.pitchw = t.RQ * 4;
-    uint32_t* A = smem;
+    // one quad of padding in front of plane A and behind plane B: the horizontal passes read one word beyond the
+    // ends of a row (values no needed cell depends on, but the addresses must exist)
+    uint32_t* A = smem + 4;
     uint32_t* B = A + t.RH * t.pitchw;
     const int frame = blockIdx.z;  // slot == frame offset inside the chunk
     const int y0 = blockIdx.y * th, x0 = blockIdx.x * tw;
@@ -421,38 +427,45 @@ __global__ void __launch_bounds__(QT, 2) k_q8_front(FrontArgs a) {
     t.rhi = min(t.RH, rows - gy0);
     tile_columns(t, gx0, cols);
     const ptrdiff_t origin = (ptrdiff_t)frame * (ptrdiff_t)a.in_fstride + ((ptrdiff_t)gy0 * (ptrdiff_t)a.in_pitch + gx0);
-    const bool border = gy0 < 0 || gy0 + t.RH > rows || gx0 < 0 || gx0 + t.RQ * 8 > cols;
-    const Items it_rq(t.RQ);
-    const BorderMasks bm = border_masks(t, it_rq, border);
 
     DCMT_STAMP(a, 0);
     float bad = 0.0f;
-    if (a.in16) front_load16(a, a.in16 + origin, A, t, it_rq, bm, gx0);  // uint16 input is q8 by construction
-    else if (a.validate) front_load<true>(a, a.in + origin, A, t, it_rq, bm, gx0, bad);
-    else front_load<false>(a, a.in + origin, A, t, it_rq, bm, gx0, bad);
+    if (a.in16) front_load<true, false>(a, a.in16 + origin, A, B, t, gx0, bad);  // uint16 input is q8 by construction
+    else if (a.validate) front_load<false, true>(a, a.in + origin, A, B, t, gx0, bad);
+    else front_load<false, false>(a, a.in + origin, A, B, t, gx0, bad);
     if (__syncthreads_or(bad != 0.0f)) {  // not strict q8: this frame is redone by the generic pipeline
         if (threadIdx.x == 0) a.ctr[frame].needs_generic = 1;
         return;
     }
     DCMT_STAMP(a, 1);
-    front_passes(A, B, t, bm);
+    const ColThread c = col_thread(a.m_pass, t, 0);  // quads 0 .. RQ-2: the last halo quad is only ever read
+    front_passes<kStraddle>(A, B, t, c, th);
     DCMT_STAMP(a, 2);
 
     // ---- pass 7: horizontal half of dilate7, hole fill (:92-100), store the core
-    const int CQ = tw / 8;
     uint16_t* mid = a.mid + (size_t)frame * a.mid_fstride;
-    for (Items i(CQ); i.r < th; i.next()) {
-        const int gy = y0 + i.r, gx = x0 + i.q * 8;
-        if (gy >= rows || gx >= cols) continue;
-        const int off = ((i.r + FU) * t.RQ + i.q + FLQ) * 4;
-        const uint4 tt = h7_max_quad(A + off);
-        uint4 d = lds4(B + off);
-        d.x = fill_holes(d.x, tt.x);
-        d.y = fill_holes(d.y, tt.y);
-        d.z = fill_holes(d.z, tt.z);
-        d.w = fill_holes(d.w, tt.w);
-        sts4(B + off, d);  // only this thread touches this quad of B in this pass
-        *reinterpret_cast<uint4*>(mid + (size_t)gy * a.mid_pitch + gx) = d;
+    {
+        const ColMap& m = a.m_core;
+        const int r0 = fast_div((int)threadIdx.x, m.magic), q = (int)threadIdx.x - r0 * m.nq;
+        const int gx = x0 + q * 8;
+        const int rend = min(th, rows - y0);
+        if (r0 < m.nrt && gx < cols) {
+            const int dstep = m.nrt * t.pitchw;
+            int off = ((r0 + FU) * t.RQ + q + FLQ) * 4;
+            uint16_t* mp = mid + (size_t)(y0 + r0) * a.mid_pitch + gx;
+            const size_t mstep = (size_t)m.nrt * a.mid_pitch;
+#pragma unroll 2
+            for (int r = r0; r < rend; r += m.nrt, off += dstep, mp += mstep) {
+                const uint4 tt = h7_max_quad(A + off);
+                uint4 d = lds4(B + off);
+                d.x = fill_holes(d.x, tt.x);
+                d.y = fill_holes(d.y, tt.y);
+                d.z = fill_holes(d.z, tt.z);
+                d.w = fill_holes(d.w, tt.w);
+                sts4(B + off, d);  // only this thread touches this quad of B in this pass
+                *reinterpret_cast<uint4*>(mp) = d;
+            }
+        }
     }
     __syncthreads();
     DCMT_STAMP(a, 3);
@@ -460,8 +473,8 @@ __global__ void __launch_bounds__(QT, 2) k_q8_front(FrontArgs a) {
     //      Two threads per column: one searches from the top, one from the bottom.
     const uint16_t* Bh = reinterpret_cast<const uint16_t*>(B);
     const int hrows = min(th, rows - y0);
-    for (int c = threadIdx.x; c < 2 * tw; c += QT) {
-        const int col = c >> 1, from_bottom = c & 1;
+    for (int c2 = threadIdx.x; c2 < 2 * tw; c2 += QT) {
+        const int col = c2 >> 1, from_bottom = c2 & 1;
         const int gx = x0 + col;
         if (gx >= cols) continue;
         const uint16_t* p = Bh + (size_t)FU * t.pitchw * 2 + FLQ * 8 + col;
@@ -517,6 +530,8 @@ struct TailArgs {
     size_t out_pitch, out_fstride;
     int rows, cols, th, tw, blur, vec_ok;
     int one;          // the constant 1, opaque to the compiler (see other_of_pair)
+    int use_tma;      // tile load by one TMA box copy (else 16-byte cp.async per thread)
+    ItemsDesc i_load, i_vert, i_scan, i_scanw, i_med, i_gauss;  // row lengths RQ, pitchw, SQ, 4 SQ, MI, NP
     long long* prof;  // optional: 16 clock64() stamps per CTA (debugging aid)
 };
 
@@ -574,7 +589,7 @@ __device__ __forceinline__ uint32_t hmax31(const uint32_t* __restrict__ B, int p
     return pmax3(m, __byte_perm(m, m, 0x1032), odd_pair(pmax(b0[-8], b1[-8]), pmax(b0[8], b1[8])));
 }
 
-__global__ void __launch_bounds__(QTT, 2) k_q8_tail(TailArgs a) {
+__global__ void __launch_bounds__(QTT, 2) k_q8_tail(TailArgs a, const __grid_constant__ TensorMap3D tmap) {
     DCMT_DYN_SMEM(uint32_t, smem);
     const int th = a.th, tw = a.tw, rows = a.rows, cols = a.cols;
     const int RH = th + 2 * TV, RQ = tw / 8 + 2 * TQ, pitchw = RQ * 4;
@@ -584,6 +599,7 @@ __global__ void __launch_bounds__(QTT, 2) k_q8_tail(TailArgs a) {
     uint16_t* Ah = reinterpret_cast<uint16_t*>(A);
     uint16_t* Bh = reinterpret_cast<uint16_t*>(B);
     __shared__ int s_count, s_remaining, s_holes_core, s_left_core;
+    __shared__ __align__(8) uint64_t s_bar;  // mbarrier the TMA tile load signals
     const int slot = blockIdx.z;
     if (a.ctr[slot].needs_generic) return;  // not strict q8: the generic pipeline redoes this frame
     const int y0 = blockIdx.y * th, x0 = blockIdx.x * tw;
@@ -593,22 +609,28 @@ __global__ void __launch_bounds__(QTT, 2) k_q8_tail(TailArgs a) {
     if (threadIdx.x == 0) { s_count = 0; s_remaining = 0; s_holes_core = 0; s_left_core = 0; }
 
     DCMT_STAMP(a, 0);
-    // ---- load the A4 plane with 16-byte asynchronous copies (outside the image: absent); the per-column keys of
-    //      the A5 step are fetched while the copies are in flight
+    // ---- load the A4 plane: ONE TMA box copy (200 x 126 uint16 for the KITTI tiles) issued by one thread; the hardware
+    //      zero-fills everything outside the image (0 = absent, exactly what the border cells must hold) and signals
+    //      an mbarrier.  The per-column keys of the A5 step are fetched while the copy is in flight.  Fallback (no
+    //      tensor map): 16-byte cp.async copies by all threads with the border handled in software.
     Tile t;
     t.RH = RH;
     t.RQ = RQ;
     t.pitchw = pitchw;
     t.rlo = max(0, -gy0);
     t.rhi = min(RH, rows - gy0);
-    tile_columns(t, gx0, cols);
-    {
+    if (a.use_tma) {
+        if (threadIdx.x == 0) tma_bar_init(&s_bar);
+        __syncthreads();
+        if (threadIdx.x == 0) tma_load_3d(A, &tmap, gx0, gy0, slot, &s_bar, (uint32_t)(RH * pitchw * 4));
+    } else {
+        tile_columns(t, gx0, cols);
         const uint16_t* mp = mid + ((ptrdiff_t)gy0 * (ptrdiff_t)a.mid_pitch + gx0);
         const int mpitch = (int)a.mid_pitch;
         if (!border) {
-            for (Items i(RQ, QTT); i.r < RH; i.next()) DCMT_CP_ASYNC_16(A + i.lin * 4, mp + (i.r * mpitch + i.q * 8));
+            for (Items i(a.i_load); i.r < RH; i.next()) DCMT_CP_ASYNC_16(A + i.lin * 4, mp + (i.r * mpitch + i.q * 8));
         } else {
-            for (Items i(RQ, QTT); i.r < RH; i.next()) {
+            for (Items i(a.i_load); i.r < RH; i.next()) {
                 if (outside(t, i.r, i.q)) sts4(A + i.lin * 4, splat4(kAbsMax));
                 else if (i.q == t.qs) sts4(A + i.lin * 4, blend(__ldg(reinterpret_cast<const uint4*>(mp + (i.r * mpitch + i.q * 8))), t.smask, kAbsMax));
                 else DCMT_CP_ASYNC_16(A + i.lin * 4, mp + (i.r * mpitch + i.q * 8));
@@ -624,7 +646,8 @@ __global__ void __launch_bounds__(QTT, 2) k_q8_tail(TailArgs a) {
         a5_kf = __ldg(a.col_first + (size_t)slot * a.mid_pitch + a5_gx);
         a5_kl = __ldg(a.col_last + (size_t)slot * a.mid_pitch + a5_gx);
     }
-    DCMT_CP_ASYNC_WAIT_ALL();
+    if (a.use_tma) tma_bar_wait(&s_bar, 0);
+    else DCMT_CP_ASYNC_WAIT_ALL();
     __syncthreads();
     DCMT_STAMP(a, 1);
     // rows >= last <- value(last), rows <= first <- value(first) (the second write wins); empty column <- 100
@@ -649,7 +672,7 @@ __global__ void __launch_bounds__(QTT, 2) k_q8_tail(TailArgs a) {
     //      running prefix maximum of the next 15 rows completes every window.  No intermediate planes, one barrier.
     {
         const int NB = (TV + th + 4 + 15) / 16;  // vertical maxima are needed for rows [0, TV + th + 4)
-        for (Items i(pitchw, QTT); i.r < NB; i.next()) {
+        for (Items i(a.i_vert); i.r < NB; i.next()) {
             const int r0 = 16 * i.r;
             const uint32_t* p = A + r0 * pitchw + i.q;
             uint32_t* o = B + r0 * pitchw + i.q;
@@ -675,7 +698,7 @@ __global__ void __launch_bounds__(QTT, 2) k_q8_tail(TailArgs a) {
     const int sr0 = TV - 4, sq0 = TQ - 1;
     {
         const int n = SH * SQ;
-        Items i(SQ, QTT);
+        Items i(a.i_scan);
         for (int base = 0; base < n; base += QTT, i.next()) {
             bool cand = false;
             int qidx = 0;
@@ -700,7 +723,7 @@ __global__ void __launch_bounds__(QTT, 2) k_q8_tail(TailArgs a) {
     auto fill_word = [&](int widx) {
         const uint32_t d = A[widx], hm = hole_mask(d);
         if (hm == 0u) return;
-        const int r = widx / pitchw, w = widx - r * pitchw;
+        const int r = fast_div(widx, a.i_vert.magic), w = widx - r * pitchw;
         const int sr = r - sr0, sw = w - TQ * 4;
         const bool core = sr >= 4 && sr < 4 + th && sw >= 0 && sw < tw / 2;
         if (core) holes_core += __popc(hm) >> 4;
@@ -715,7 +738,7 @@ __global__ void __launch_bounds__(QTT, 2) k_q8_tail(TailArgs a) {
     if (n_quads <= kListCap) {
         for (int k = threadIdx.x; k < 4 * n_quads; k += QTT) fill_word(list[k >> 2] * 4 + (k & 3));
     } else {  // cannot happen for tiles up to 96 x 160 (2184 scan quads); kept for larger tiles
-        for (Items i(SQ * 4, QTT); i.r < SH; i.next()) fill_word((sr0 + i.r) * pitchw + sq0 * 4 + i.q);
+        for (Items i(a.i_scanw); i.r < SH; i.next()) fill_word((sr0 + i.r) * pitchw + sq0 * 4 + i.q);
     }
     if (holes_core) atomicAdd(&s_holes_core, holes_core);
     if (left_core) atomicAdd(&s_left_core, left_core);
@@ -760,7 +783,7 @@ __global__ void __launch_bounds__(QTT, 2) k_q8_tail(TailArgs a) {
         const int MH = th + 4, MI = (tw / 2 + 2 + 3) / 4;  // rows core +- 2; items of four words covering core +- 1 word
         const int mr0 = TV - 2, mw0 = TQ * 4 - 1;
         const PackedOps ops{(uint32_t)a.one};
-        for (Items i(MI, QTT); i.r < MH; i.next()) {
+        for (Items i(a.i_med); i.r < MH; i.next()) {
             const int r = mr0 + i.r, w = mw0 + 4 * i.q;  // output words w .. w+3; columns w-1 .. w+4
             uint32_t col[6][5];
             const uint32_t* p = A + (r - 2) * pitchw + (w - 1);  // w - 1 is even: 8-byte aligned
@@ -834,7 +857,7 @@ __global__ void __launch_bounds__(QTT, 2) k_q8_tail(TailArgs a) {
     //      applies:  out16 = 6553600 - (g - 256)  with e = q + 1 and weights summing to 256.
     {
         const int NP = tw / 4, NGR = (th + 3) / 4;
-        for (Items i(NP, QTT); i.r < NGR; i.next()) {
+        for (Items i(a.i_gauss); i.r < NGR; i.next()) {
             const int cy0 = i.r * 4, gx = x0 + i.q * 4;
             if (y0 + cy0 >= rows || gx >= cols) continue;
             const uint32_t* p = B + (TV + cy0) * pitchw + TQ * 4 + 2 * i.q;  // row cy0, first word of the pair
@@ -1012,7 +1035,32 @@ __global__ void k_q8_write_stats(const FrameCounters* __restrict__ c, int32_t* _
 
 }  // namespace
 
-size_t q8_front_smem(int th, int tw) { return (size_t)2 * (th + FU + FD) * (tw / 8 + FLQ + FRQ) * 4 * sizeof(uint32_t); }
+#ifndef DCMT_EMU
+cudaError_t tma_encode_u16_3d(TensorMap3D* m, const uint16_t* base, int cols, int rows, int frames, size_t row_bytes,
+                              size_t frame_bytes, int box_cols, int box_rows) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static const EncodeFn fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) f = nullptr;
+        return reinterpret_cast<EncodeFn>(f);
+    }();
+    if (!fn || box_cols > 256 || box_rows > 256 || (row_bytes & 15) || (frame_bytes & 15) || (reinterpret_cast<uintptr_t>(base) & 15))
+        return cudaErrorNotSupported;
+    const cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)frames};
+    const cuuint64_t strides[2] = {(cuuint64_t)row_bytes, (cuuint64_t)frame_bytes};
+    const cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<uint16_t*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+#endif
+
+size_t q8_front_smem(int th, int tw) { return ((size_t)2 * (th + FU + FD) * (tw / 8 + FLQ + FRQ) * 4 + 8) * sizeof(uint32_t); }
 
 size_t q8_tail_smem(int th, int tw) {
     const size_t rowb = (size_t)(tw / 8 + 2 * TQ) * 4 * sizeof(uint32_t);
@@ -1027,7 +1075,9 @@ void q8_choose_tile(int rows, int cols, int* th, int* tw) {
 }
 
 cudaError_t q8_configure() {
-    cudaError_t e = cudaFuncSetAttribute(k_q8_front, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(k_q8_front<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_q8_front<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_q8_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 }
@@ -1042,18 +1092,28 @@ cudaError_t q8_run_front(const Q8Plan& p, const float* in, const uint16_t* in16,
     const uintptr_t base = in16 ? reinterpret_cast<uintptr_t>(in16) : reinterpret_cast<uintptr_t>(in);
     FrontArgs a{in, in16, in_pitch, in_fstride, p.mid, (size_t)p.mid_pitch, (size_t)p.mid_pitch * p.rows, p.col_first, p.col_last,
                 p.ctr, p.rows, p.cols, p.th, p.tw, (int)(in_pitch % unit == 0 && in_fstride % unit == 0 && (base & 15) == 0), validate,
-                p.prof_front};
+                make_colmap(p.tw / 8 + FLQ + FRQ, QT), make_colmap(p.tw / 8 + FLQ + FRQ - 1, QT), make_colmap(p.tw / 8, QT), p.prof_front};
     const dim3 grid((p.cols + p.tw - 1) / p.tw, (p.rows + p.th - 1) / p.th, n_frames);
-    DCMT_LAUNCH(k_q8_front, grid, dim3(QT), q8_front_smem(p.th, p.tw), st, a);
+    if (p.cols % 8 != 0) DCMT_LAUNCH(k_q8_front<true>, grid, dim3(QT), q8_front_smem(p.th, p.tw), st, a);
+    else DCMT_LAUNCH(k_q8_front<false>, grid, dim3(QT), q8_front_smem(p.th, p.tw), st, a);
     return cudaGetLastError();
 }
 
 cudaError_t q8_run_tail(const Q8Plan& p, float* out, size_t out_pitch, size_t out_fstride, int n_frames, int blur, cudaStream_t st) {
     const int vec2 = out_pitch % 4 == 0 && out_fstride % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    const int RQ = p.tw / 8 + 2 * TQ, RH = p.th + 2 * TV, SQ = p.tw / 8 + 2, MI = (p.tw / 2 + 2 + 3) / 4, NP = p.tw / 4;
+    // tile load by TMA: a 3-D map (columns, rows, slots) of the intermediate plane whose column extent is the true
+    // image width, so that the padding columns of the plane read as absent like everything else outside the image
+    TensorMap3D tmap{};
+    static const bool no_tma = [] { const char* e = getenv("DCMT_NO_TMA"); return e && e[0] == '1'; }();
+    const int use_tma = !no_tma && tma_encode_u16_3d(&tmap, p.mid, p.cols, p.rows, p.max_frames, (size_t)p.mid_pitch * 2,
+                                                     (size_t)p.mid_pitch * p.rows * 2, RQ * 8, RH) == cudaSuccess;
     TailArgs a{p.mid, (size_t)p.mid_pitch, (size_t)p.mid_pitch * p.rows, p.col_first, p.col_last, p.ctr, out, out_pitch,
-               out_fstride, p.rows, p.cols, p.th, p.tw, blur, vec2, 1, p.prof_tail};
+               out_fstride, p.rows, p.cols, p.th, p.tw, blur, vec2, 1, use_tma,
+               make_items(RQ, QTT), make_items(RQ * 4, QTT), make_items(SQ, QTT), make_items(SQ * 4, QTT), make_items(MI, QTT),
+               make_items(NP, QTT), p.prof_tail};
     const dim3 grid((p.cols + p.tw - 1) / p.tw, (p.rows + p.th - 1) / p.th, n_frames);
-    DCMT_LAUNCH(k_q8_tail, grid, dim3(QTT), q8_tail_smem(p.th, p.tw), st, a);
+    DCMT_LAUNCH(k_q8_tail, grid, dim3(QTT), q8_tail_smem(p.th, p.tw), st, a, tmap);
     FixupArgs f{p.mid, (size_t)p.mid_pitch, (size_t)p.mid_pitch * p.rows, p.col_first, p.col_last, p.ctr, p.w1, p.w2, out,
                 out_pitch, out_fstride, p.rows, p.cols, blur, (p.rows > p.cols ? p.rows : p.cols) / 15 + 2};
     DCMT_LAUNCH(k_q8_fixup, dim3(n_frames), dim3(1024), 0, st, f);
