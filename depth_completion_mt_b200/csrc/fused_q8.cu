@@ -52,6 +52,8 @@ __device__ __forceinline__ uint32_t pext(uint32_t a, uint32_t b) {
 
 __device__ __forceinline__ uint4 lds4(const uint32_t* p) { return *reinterpret_cast<const uint4*>(p); }
 __device__ __forceinline__ void sts4(uint32_t* p, uint4 v) { *reinterpret_cast<uint4*>(p) = v; }
+__device__ __forceinline__ uint2 lds2(const uint32_t* p) { return *reinterpret_cast<const uint2*>(p); }
+__device__ __forceinline__ void sts2(uint32_t* p, uint2 v) { *reinterpret_cast<uint2*>(p) = v; }
 __device__ __forceinline__ uint4 splat4(uint32_t v) { return make_uint4(v, v, v, v); }
 
 // Blend the lanes of a quad (8 pixels starting at image column gx) that lie outside [0, cols) with `ident`.
@@ -142,6 +144,7 @@ struct FrontArgs {
     int vec_ok;                   // input rows are 16-byte aligned: float4 loads
     int validate;                 // check strict q8-ness of every loaded pixel (DCMT_PATH_AUTO)
     ColMap m_load, m_pass, m_core;  // region (RQ quads), computed quads (RQ - 1), core quads (tw / 8)
+    ItemsDesc i_half;               // half-quad columns of the computed quads: 2 (RQ - 1) per row of items
     long long* prof;              // optional: 16 clock64() stamps per CTA (debugging aid)
 };
 
@@ -285,10 +288,129 @@ __device__ __forceinline__ uint32_t fill_holes(uint32_t d, uint32_t t) {
     return __vadd2(pmin(__vadd2(t, k), __vadd2(d, k)), SPLAT16(27));
 }
 
+// ---- vertical passes: one item = one half-quad column (2 words, 4 pixels) x a run of L consecutive rows.  The rows
+// a window needs are loaded once and slide through registers, so a 5-row window costs (L + 4) / L loads per output
+// instead of 5 -- the front kernel is bound by shared-memory bandwidth, not by instruction issue.
+__device__ __forceinline__ uint2 half_mask(const Tile& t, int h) {
+    if ((h >> 1) != t.qs) return make_uint2(0xffffffffu, 0xffffffffu);
+    return (h & 1) ? make_uint2(t.smask.z, t.smask.w) : make_uint2(t.smask.x, t.smask.y);
+}
+
+// dst(r) = max of src over rows r-2 .. r+2, rows [rb, re)
+template <bool kStraddle, int L>
+__device__ __forceinline__ void v5max_runs(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, const Tile& t, const ItemsDesc& d,
+                                           int rb, int re) {
+    const int pw = t.pitchw, nseg = (re - rb + L - 1) / L;
+    for (Items i(d); i.r < nseg; i.next()) {
+        const int h = i.q, q = h >> 1;
+        if (q < t.qlo || q >= t.qhi) continue;
+        const int rf = rb + i.r * L, n = min(L, re - rf);
+        const uint32_t* p = src + (rf - 2) * pw + 2 * h;
+        uint32_t* o = dst + rf * pw + 2 * h;
+        const uint2 m = half_mask(t, h);
+        uint2 w0 = lds2(p), w1 = lds2(p + pw), w2 = lds2(p + 2 * pw), w3 = lds2(p + 3 * pw);
+        auto step = [&](int k) {
+            const uint2 w4 = lds2(p + (k + 4) * pw);
+            uint2 v = make_uint2(pmax3(pmax3(w0.x, w1.x, w2.x), w3.x, w4.x), pmax3(pmax3(w0.y, w1.y, w2.y), w3.y, w4.y));
+            if (kStraddle) { v.x &= m.x; v.y &= m.y; }
+            sts2(o + k * pw, v);
+            w0 = w1; w1 = w2; w2 = w3; w3 = w4;
+        };
+        if (n == L) {  // full run: no guards
+#pragma unroll
+            for (int k = 0; k < L; ++k) step(k);
+        } else {
+#pragma unroll
+            for (int k = 0; k < L; ++k)
+                if (k < n) step(k);
+        }
+    }
+}
+
+// The vertical erosion of close5 and the vertical half of dilate7 in one sweep (:85, :88-90), for core rows [rb, re):
+//   D(r)  = ~max(Y'(r-2 .. r+2))   Y' = complemented horizontal erosion; rows outside the image give D = 0 (absent)
+//   V7(r) =  max(D(r-3 .. r+3))
+// D goes to the core-sized plane C (core quads only: pass 7 reads nothing else of it), V7 to plane V.
+template <bool kStraddle, int L>
+__device__ __forceinline__ void v_close_dilate_runs(const uint32_t* __restrict__ Y, uint32_t* __restrict__ V, uint32_t* __restrict__ C,
+                                                    const Tile& t, const ItemsDesc& d, int rb, int re, int cq) {
+    const int pw = t.pitchw, cpw = cq * 4, nseg = (re - rb + L - 1) / L;
+    for (Items i(d); i.r < nseg; i.next()) {
+        const int h = i.q, q = h >> 1;
+        if (q < t.qlo || q >= t.qhi) continue;
+        const int rf = rb + i.r * L, n = min(L, re - rf);
+        const uint32_t* p = Y + (rf - 5) * pw + 2 * h;
+        uint32_t* ov = V + rf * pw + 2 * h;
+        const bool core = q >= FLQ && q < FLQ + cq;
+        uint32_t* od = C + (rf - FU) * cpw + (2 * h - FLQ * 4);
+        const uint2 m = half_mask(t, h);
+        uint2 y0 = lds2(p), y1 = lds2(p + pw), y2 = lds2(p + 2 * pw), y3 = lds2(p + 3 * pw);
+        uint2 dw[7];
+        auto step = [&](int e, bool check_rows) {  // D row rf - 3 + e, V7 row rf + e - 6
+            const uint2 y4 = lds2(p + (e + 4) * pw);
+            uint2 dn = make_uint2(~pmax3(pmax3(y0.x, y1.x, y2.x), y3.x, y4.x), ~pmax3(pmax3(y0.y, y1.y, y2.y), y3.y, y4.y));
+            if (kStraddle) { dn.x &= m.x; dn.y &= m.y; }
+            if (check_rows) {
+                const int row = rf - 3 + e;
+                if (row < t.rlo || row >= t.rhi) dn = make_uint2(0u, 0u);
+            }
+            y0 = y1; y1 = y2; y2 = y3; y3 = y4;
+            dw[e % 7] = dn;
+            if (e >= 3 && e < 3 + L && e - 3 < n && core) sts2(od + (e - 3) * cpw, dn);
+            if (e >= 6) {
+                const uint2 v = make_uint2(pmax3(pmax3(dw[0].x, dw[1].x, dw[2].x), pmax3(dw[3].x, dw[4].x, dw[5].x), dw[6].x),
+                                           pmax3(pmax3(dw[0].y, dw[1].y, dw[2].y), pmax3(dw[3].y, dw[4].y, dw[5].y), dw[6].y));
+                sts2(ov + (e - 6) * pw, v);
+            }
+        };
+        if (n == L && rf - 3 >= t.rlo && rf + L + 3 <= t.rhi) {  // full run, every D row inside the image: no guards
+#pragma unroll
+            for (int e = 0; e < L + 6; ++e) step(e, false);
+        } else {
+#pragma unroll
+            for (int e = 0; e < L + 6; ++e)
+                if (e < n + 6) step(e, true);
+        }
+    }
+}
+
+// The two horizontal passes of close5 (:84-85) on one quad in registers: dilate5 on words -1 .. 4, complement (0 where
+// the word lies outside the image: absent for the erosion), erode5 as a max of complements on words 0 .. 3.  The result
+// stays complemented (Y') for the vertical erosion.  ml / mr: in-image lanes of words -1 / 4, mc: of the quad itself.
+__device__ __forceinline__ uint4 h5_close_quad(const uint32_t* __restrict__ p, uint32_t ml, uint4 mc, uint32_t mr) {
+    const uint2 l = lds2(p - 2), r = lds2(p + 4);
+    const uint4 c = lds4(p);
+    const uint32_t P[8] = {l.x, l.y, c.x, c.y, c.z, c.w, r.x, r.y};  // P[j + 2] = word j
+    uint32_t R[7];                                                     // R[j + 1] = odd pair (word j-1, word j), j = -1 .. 5
+#pragma unroll
+    for (int j = 0; j < 7; ++j) R[j] = odd_pair(P[j], P[j + 1]);
+    uint32_t m[6];  // m[j + 1] = dilate5 at word j, j = -1 .. 4
+#pragma unroll
+    for (int j = 0; j < 6; ++j) m[j] = pmax3(pmax3(P[j], R[j], P[j + 1]), R[j + 1], P[j + 2]);
+    m[0] = ~m[0] & ml;
+    m[1] = ~m[1] & mc.x;
+    m[2] = ~m[2] & mc.y;
+    m[3] = ~m[3] & mc.z;
+    m[4] = ~m[4] & mc.w;
+    m[5] = ~m[5] & mr;
+    uint32_t S[5];  // S[j] = odd pair (m word j-1, m word j), j = 0 .. 4
+#pragma unroll
+    for (int j = 0; j < 5; ++j) S[j] = odd_pair(m[j], m[j + 1]);
+    uint4 o;
+    o.x = pmax3(pmax3(m[0], S[0], m[1]), S[1], m[2]);
+    o.y = pmax3(pmax3(m[1], S[1], m[2]), S[2], m[3]);
+    o.z = pmax3(pmax3(m[2], S[2], m[3]), S[3], m[4]);
+    o.w = pmax3(pmax3(m[3], S[3], m[4]), S[4], m[5]);
+    return o;
+}
+
 // Passes 1-6 on region rows (core rows are [FU, FU + th)); each pass covers the rows the later ones read:
 //   pass 7 needs V7 on the core rows <- D on core +- 3 <- H5 on core +- 5 (<- V5max on the same rows) <- 2-tap on core +- 7.
+// Four trips through shared memory: 2-tap, V5max (vertical runs), H5max + H5min (fused per quad), V5min + V7max (fused
+// vertical runs).
 template <bool kStraddle>
-__device__ __forceinline__ void front_passes(uint32_t* A, uint32_t* B, const Tile& t, const ColThread& c, int th) {
+__device__ __forceinline__ void front_passes(uint32_t* A, uint32_t* B, uint32_t* C, const Tile& t, const ColThread& c, const ItemsDesc& halves,
+                                             int th, int cq) {
     const int pw = t.pitchw;
     auto rb = [&](int lo) { return max(lo, t.rlo); };
     auto re = [&](int hi) { return min(hi, t.rhi); };
@@ -303,17 +425,19 @@ __device__ __forceinline__ void front_passes(uint32_t* A, uint32_t* B, const Til
                           pmax(odd_pair(ca.w, na), nb));
     });
     __syncthreads();
-    // ---- passes 2-5: close5 (:84-85) = dilate5 (V, H) then erode5 (H, V); the erosions run on complemented values
-    col_pass<kStraddle>(A, c, rb(FU - 5), re(FU + th + 5), [&](int off) { return v_window<2, true>(B + off, pw); });
+    // ---- pass 2: vertical half of dilate5 (:84)
+    v5max_runs<kStraddle, 9>(B, A, t, halves, rb(FU - 5), re(FU + th + 5));
     __syncthreads();
-    col_pass<kStraddle>(B, c, rb(FU - 5), re(FU + th + 5), [&](int off) { return not4(h5_window<true>(A + off)); });
+    // ---- passes 3 + 4: horizontal dilate5 and horizontal erode5, fused per quad; output complemented
+    {
+        const int q = (c.off0 >> 2) - c.r0 * t.RQ;  // the thread's quad column
+        const uint32_t ml = (q - 1 >= t.qlo && q - 1 < t.qhi) ? (q - 1 == t.qs ? t.smask.w : 0xffffffffu) : 0u;
+        const uint32_t mr = (q + 1 >= t.qlo && q + 1 < t.qhi) ? (q + 1 == t.qs ? t.smask.x : 0xffffffffu) : 0u;
+        col_pass<kStraddle>(B, c, rb(FU - 5), re(FU + th + 5), [&](int off) { return h5_close_quad(A + off, ml, c.cmask, mr); });
+    }
     __syncthreads();
-    col_pass<kStraddle>(A, c, rb(FU - 5), re(FU + th + 5), [&](int off) { return h5_window<true>(B + off); });
-    __syncthreads();
-    col_pass<kStraddle>(B, c, rb(FU - 3), re(FU + th + 3), [&](int off) { return not4(v_window<2, true>(A + off, pw)); });  // B = D
-    __syncthreads();
-    // ---- pass 6: vertical half of dilate7 (:88-90)
-    col_pass<kStraddle>(A, c, rb(FU), re(FU + th), [&](int off) { return v_window<3, true>(B + off, pw); });
+    // ---- passes 5 + 6: vertical erode5 -> D (plane C, core quads) and vertical half of dilate7 (:88-90) -> A
+    v_close_dilate_runs<kStraddle, 8>(B, A, C, t, halves, rb(FU), re(FU + th), cq);
     __syncthreads();
 }
 
@@ -419,6 +543,7 @@ __global__ void __launch_bounds__(QT, 2) k_q8_front(FrontArgs a) {
     // ends of a row (values no needed cell depends on, but the addresses must exist)
     uint32_t* A = smem + 4;
     uint32_t* B = A + t.RH * t.pitchw;
+    uint32_t* C = B + t.RH * t.pitchw + 4;  // D = close5 result on the core: th rows x tw / 8 quads
     const int frame = blockIdx.z;  // slot == frame offset inside the chunk
     const int y0 = blockIdx.y * th, x0 = blockIdx.x * tw;
     const int gy0 = y0 - FU;
@@ -439,7 +564,7 @@ __global__ void __launch_bounds__(QT, 2) k_q8_front(FrontArgs a) {
     }
     DCMT_STAMP(a, 1);
     const ColThread c = col_thread(a.m_pass, t, 0);  // quads 0 .. RQ-2: the last halo quad is only ever read
-    front_passes<kStraddle>(A, B, t, c, th);
+    front_passes<kStraddle>(A, B, C, t, c, a.i_half, th, tw / 8);
     DCMT_STAMP(a, 2);
 
     // ---- pass 7: horizontal half of dilate7, hole fill (:92-100), store the core
@@ -452,17 +577,19 @@ __global__ void __launch_bounds__(QT, 2) k_q8_front(FrontArgs a) {
         if (r0 < m.nrt && gx < cols) {
             const int dstep = m.nrt * t.pitchw;
             int off = ((r0 + FU) * t.RQ + q + FLQ) * 4;
+            const int cstep = m.nrt * m.nq * 4;
+            uint32_t* pc = C + (r0 * m.nq + q) * 4;
             uint16_t* mp = mid + (size_t)(y0 + r0) * a.mid_pitch + gx;
             const size_t mstep = (size_t)m.nrt * a.mid_pitch;
 #pragma unroll 2
-            for (int r = r0; r < rend; r += m.nrt, off += dstep, mp += mstep) {
+            for (int r = r0; r < rend; r += m.nrt, off += dstep, pc += cstep, mp += mstep) {
                 const uint4 tt = h7_max_quad(A + off);
-                uint4 d = lds4(B + off);
+                uint4 d = lds4(pc);
                 d.x = fill_holes(d.x, tt.x);
                 d.y = fill_holes(d.y, tt.y);
                 d.z = fill_holes(d.z, tt.z);
                 d.w = fill_holes(d.w, tt.w);
-                sts4(B + off, d);  // only this thread touches this quad of B in this pass
+                sts4(pc, d);  // only this thread touches this quad of C in this pass
                 *reinterpret_cast<uint4*>(mp) = d;
             }
         }
@@ -471,16 +598,16 @@ __global__ void __launch_bounds__(QT, 2) k_q8_front(FrontArgs a) {
     DCMT_STAMP(a, 3);
     // ---- per-column first / last valid row inside this tile (feeds :103-129), merged across tiles by atomics.
     //      Two threads per column: one searches from the top, one from the bottom.
-    const uint16_t* Bh = reinterpret_cast<const uint16_t*>(B);
+    const uint16_t* Ch = reinterpret_cast<const uint16_t*>(C);
     const int hrows = min(th, rows - y0);
     for (int c2 = threadIdx.x; c2 < 2 * tw; c2 += QT) {
         const int col = c2 >> 1, from_bottom = c2 & 1;
         const int gx = x0 + col;
         if (gx >= cols) continue;
-        const uint16_t* p = Bh + (size_t)FU * t.pitchw * 2 + FLQ * 8 + col;
+        const uint16_t* p = Ch + col;
         if (!from_bottom) {
             for (int cy = 0; cy < hrows; ++cy) {
-                const uint32_t e = p[(size_t)cy * t.pitchw * 2];
+                const uint32_t e = p[(size_t)cy * tw];
                 if (e >= E_VALID_MIN) {
                     atomicMin(a.col_first + (size_t)frame * a.mid_pitch + gx, ((uint32_t)(y0 + cy) << 16) | e);
                     break;
@@ -488,7 +615,7 @@ __global__ void __launch_bounds__(QT, 2) k_q8_front(FrontArgs a) {
             }
         } else {
             for (int cy = hrows - 1; cy >= 0; --cy) {
-                const uint32_t e = p[(size_t)cy * t.pitchw * 2];
+                const uint32_t e = p[(size_t)cy * tw];
                 if (e >= E_VALID_MIN) {
                     atomicMax(a.col_last + (size_t)frame * a.mid_pitch + gx, ((uint32_t)(y0 + cy) << 16) | e);
                     break;
@@ -1060,7 +1187,10 @@ cudaError_t tma_encode_u16_3d(TensorMap3D* m, const uint16_t* base, int cols, in
 }
 #endif
 
-size_t q8_front_smem(int th, int tw) { return ((size_t)2 * (th + FU + FD) * (tw / 8 + FLQ + FRQ) * 4 + 8) * sizeof(uint32_t); }
+size_t q8_front_smem(int th, int tw) {
+    // two region planes, the core-sized D plane, one quad of padding in front of / behind the region planes
+    return ((size_t)2 * (th + FU + FD) * (tw / 8 + FLQ + FRQ) * 4 + (size_t)th * (tw / 8) * 4 + 8) * sizeof(uint32_t);
+}
 
 size_t q8_tail_smem(int th, int tw) {
     const size_t rowb = (size_t)(tw / 8 + 2 * TQ) * 4 * sizeof(uint32_t);
@@ -1092,7 +1222,8 @@ cudaError_t q8_run_front(const Q8Plan& p, const float* in, const uint16_t* in16,
     const uintptr_t base = in16 ? reinterpret_cast<uintptr_t>(in16) : reinterpret_cast<uintptr_t>(in);
     FrontArgs a{in, in16, in_pitch, in_fstride, p.mid, (size_t)p.mid_pitch, (size_t)p.mid_pitch * p.rows, p.col_first, p.col_last,
                 p.ctr, p.rows, p.cols, p.th, p.tw, (int)(in_pitch % unit == 0 && in_fstride % unit == 0 && (base & 15) == 0), validate,
-                make_colmap(p.tw / 8 + FLQ + FRQ, QT), make_colmap(p.tw / 8 + FLQ + FRQ - 1, QT), make_colmap(p.tw / 8, QT), p.prof_front};
+                make_colmap(p.tw / 8 + FLQ + FRQ, QT), make_colmap(p.tw / 8 + FLQ + FRQ - 1, QT), make_colmap(p.tw / 8, QT),
+                make_items(2 * (p.tw / 8 + FLQ + FRQ - 1), QT), p.prof_front};
     const dim3 grid((p.cols + p.tw - 1) / p.tw, (p.rows + p.th - 1) / p.th, n_frames);
     if (p.cols % 8 != 0) DCMT_LAUNCH(k_q8_front<true>, grid, dim3(QT), q8_front_smem(p.th, p.tw), st, a);
     else DCMT_LAUNCH(k_q8_front<false>, grid, dim3(QT), q8_front_smem(p.th, p.tw), st, a);
