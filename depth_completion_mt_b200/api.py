@@ -292,3 +292,60 @@ def optimize_IG(value_left, value_right, disp, num_iterations: int = 4, damp_fac
                                            float(damp_factor), float(err_clip), _stream_ptr(stream)))
     out = d3[0] if squeeze else d3
     return out.cpu().numpy() if host else out
+
+
+# ---------------------------------------------------------------------------------------------- evaluation (8f #3)
+EVAL_VARIANTS = {
+    # variant: (mode, tolerance)   mode 0: mask gt > tol, mode 1: mask gt > tol and r > tol
+    "lidar_only": (0, 0.0),    # src/DC_lidar_only/main.cpp:16-34       `int tolerance = 0`
+    "lidar_camera": (1, 0.0),  # src/DC_lidar_camera/main_lc.cpp:85-116 `int tolerance = 0.1` truncates to 0
+    "stereo_lidar": (1, 2.0),  # src/DC_stereo_lidar/main_sl.cpp:1031-1061 `int tolerance = 2`
+}
+
+
+def evaluate(gt, dense, variant: str = "lidar_camera", *, stream=None, lib: _lib.Library | None = None):
+    """The masked error sums behind the reference's evaluation functions, one record per frame.
+
+    Returns a numpy structured array with fields count, sum_err, sum_abs, sum_sq (float64) and mean_err, mae, rmse
+    (float32).  ``gt`` / ``dense`` are float32 (rows, cols) or (n, rows, cols), numpy (host entry point) or torch CUDA
+    tensors (device entry point; the records are read back, which synchronises the stream)."""
+    lib = lib or _lib.load()
+    mode, tol = EVAL_VARIANTS[variant]
+    dt = np.dtype([("count", "f8"), ("sum_err", "f8"), ("sum_abs", "f8"), ("sum_sq", "f8"), ("mean_err", "f4"), ("mae", "f4"),
+                   ("rmse", "f4"), ("pad", "i4")])
+    if _is_torch(gt):
+        g3, _ = _batch3(_prep_torch(gt, torch.float32, "gt"), "gt")
+        r3, _ = _batch3(_prep_torch(dense, torch.float32, "dense"), "dense")
+        if g3.shape != r3.shape:
+            raise ValueError("gt and dense shapes differ")
+        n, rows, cols = g3.shape
+        res = torch.empty((n, dt.itemsize), dtype=torch.uint8, device=g3.device)
+        with torch.cuda.device(g3.device):
+            lib.check(lib.dcmt_evaluate_f32(g3.data_ptr(), r3.data_ptr(), rows, cols, 0, 0, n, float(tol), mode, res.data_ptr(),
+                                            _stream_ptr(stream)))
+        return res.cpu().numpy().view(dt).reshape(n)
+    g3, _ = _batch3(_prep_numpy(gt, np.float32, "gt"), "gt")
+    r3, _ = _batch3(_prep_numpy(dense, np.float32, "dense"), "dense")
+    if g3.shape != r3.shape:
+        raise ValueError("gt and dense shapes differ")
+    n, rows, cols = g3.shape
+    res = np.zeros(n, dt)
+    lib.check(lib.dcmt_evaluate_f32_host(_np_ptr(g3), _np_ptr(r3), rows, cols, 0, 0, n, float(tol), mode, _np_ptr(res)))
+    return res
+
+
+def evaluate_performance(GT_img, r_img, variant: str = "lidar_camera", **kw):
+    """evaluate_performance(GT_img, r_img, mse[, mae]) of the reference, for ONE frame.
+
+    variant "lidar_only"   (main.cpp:16-34)      -> mse            (= mean of gt - r over gt > 0: a signed mean, sic)
+    variant "lidar_camera" (main_lc.cpp:85-116)  -> (mse, mae)     (mse = sqrt(sum d^2 / count), sic)"""
+    rec = evaluate(GT_img, r_img, variant, **kw)[0]
+    if variant == "lidar_only":
+        return float(rec["mean_err"])
+    return float(rec["rmse"]), float(rec["mae"])
+
+
+def evaluate_performances(GT_img, r_img, **kw):
+    """evaluate_performances(GT_img, r_img, mae, rmse), main_sl.cpp:1031-1061 (tolerance 2) -> (mae, rmse)."""
+    rec = evaluate(GT_img, r_img, "stereo_lidar", **kw)[0]
+    return float(rec["mae"]), float(rec["rmse"])

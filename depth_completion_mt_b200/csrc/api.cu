@@ -12,6 +12,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "evaluate.cuh"
 #include "fused_q8.cuh"
 #include "generic.cuh"
 #include "stereo.cuh"
@@ -763,6 +764,60 @@ int dcmt_debug_q8_phase_cycles(const float* sparse, float* dense, int rows, int 
     API_CUDA(dcmt::q8_run_front(p, sparse, nullptr, cols, fpix, n_frames, 1, st), "fused front launch");
     API_CUDA(dcmt::q8_run_tail(p, dense, cols, fpix, n_frames, DCMT_BLUR_GAUSSIAN, st), "fused tail launch");
     return DCMT_OK;
+}
+
+static_assert(sizeof(dcmt_eval_result) == sizeof(dcmt::EvalResult), "dcmt_eval_result and dcmt::EvalResult must match");
+
+int dcmt_evaluate_f32(const float* gt, const float* dense, int rows, int cols, size_t pitch_bytes, size_t frame_stride_bytes,
+                      int n_frames, float tolerance, int mode, dcmt_eval_result* results, void* cuda_stream) {
+    if (!gt || !dense || !results) return fail(DCMT_E_BADARG, "null pointer");
+    if (mode != DCMT_EVAL_GT_VALID && mode != DCMT_EVAL_BOTH_VALID) return fail(DCMT_E_BADARG, "mode %d", mode);
+    Geometry g;
+    int rc = check_geometry(rows, cols, pitch_bytes, frame_stride_bytes, n_frames, &g);
+    if (rc) return rc;
+    if (n_frames == 0) return DCMT_OK;
+    if ((rc = check_device())) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    Arena* ar = nullptr;
+    if ((rc = arena_acquire(st, carve_bytes(dcmt::eval_partial_doubles(n_frames), sizeof(double)), &ar))) return rc;
+    double* partials = carve<double>(ar, dcmt::eval_partial_doubles(n_frames));
+    API_CUDA(dcmt::eval_run(gt, dense, rows, cols, g.pitch, g.fstride, n_frames, tolerance, mode, partials,
+                            reinterpret_cast<dcmt::EvalResult*>(results), st),
+             "evaluation launch");
+    return DCMT_OK;
+}
+
+int dcmt_evaluate_f32_host(const float* gt, const float* dense, int rows, int cols, size_t pitch_bytes, size_t frame_stride_bytes,
+                           int n_frames, float tolerance, int mode, dcmt_eval_result* results) {
+    if (!gt || !dense || !results) return fail(DCMT_E_BADARG, "null pointer");
+    if (mode != DCMT_EVAL_GT_VALID && mode != DCMT_EVAL_BOTH_VALID) return fail(DCMT_E_BADARG, "mode %d", mode);
+    Geometry g;
+    int rc = check_geometry(rows, cols, pitch_bytes, frame_stride_bytes, n_frames, &g);
+    if (rc) return rc;
+    if (n_frames == 0) return DCMT_OK;
+    if ((rc = check_device())) return rc;
+    float *d_gt = nullptr, *d_r = nullptr;
+    dcmt_eval_result* d_res = nullptr;
+    auto cleanup = [&] { cudaFree(d_gt); cudaFree(d_r); cudaFree(d_res); };
+    cudaError_t e;
+    if ((e = cudaMalloc(&d_gt, g.span_bytes)) != cudaSuccess || (e = cudaMalloc(&d_r, g.span_bytes)) != cudaSuccess ||
+        (e = cudaMalloc(&d_res, (size_t)n_frames * sizeof(dcmt_eval_result))) != cudaSuccess) {
+        cleanup();
+        return fail(DCMT_E_NOMEM, "device staging buffers: %s", cudaGetErrorString(e));
+    }
+    if ((e = cudaMemcpy(d_gt, gt, g.span_bytes, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMemcpy(d_r, dense, g.span_bytes, cudaMemcpyHostToDevice)) != cudaSuccess) {
+        cleanup();
+        return cuda_fail(e, "host to device copy");
+    }
+    rc = dcmt_evaluate_f32(d_gt, d_r, rows, cols, pitch_bytes, frame_stride_bytes, n_frames, tolerance, mode, d_res, nullptr);
+    if (rc == DCMT_OK) {
+        if ((e = cudaStreamSynchronize(nullptr)) != cudaSuccess) rc = cuda_fail(e, "kernel execution");
+        else if ((e = cudaMemcpy(results, d_res, (size_t)n_frames * sizeof(dcmt_eval_result), cudaMemcpyDeviceToHost)) != cudaSuccess)
+            rc = cuda_fail(e, "device to host copy");
+    }
+    cleanup();
+    return rc;
 }
 
 void dcmt_stereo_params_default(dcmt_stereo_params* p) {

@@ -174,6 +174,28 @@ DCMT_API int dcmt_optimize_ig_f32(const float *value_left, const float *value_ri
 DCMT_API int dcmt_retrieve_optimized_depth_f32(const float *disp, float *depth, int rows, int cols, int n_frames,
                                                float baseline, float focal, float depth_clip, void *cuda_stream);
 
+/* (8f #3) evaluation reductions: replace evaluate_performance (src/DC_lidar_only/main.cpp:16-34, mode
+ * DCMT_EVAL_GT_VALID: pixels with gt > tolerance, result mean_err = sum(gt - r) / count, which that program calls
+ * "mse"), evaluate_performance (src/DC_lidar_camera/main_lc.cpp:85-116) and evaluate_performances
+ * (src/DC_stereo_lidar/main_sl.cpp:1031-1061) (mode DCMT_EVAL_BOTH_VALID: pixels with gt > tolerance and
+ * r > tolerance; rmse = sqrt(sum d^2 / count), mae = sum |d| / count).  `tolerance` is the reference's `int tolerance`
+ * converted to float: 0 for main.cpp (`= 0`) and main_lc.cpp (`= 0.1` truncates), 2 for main_sl.cpp.  One result per
+ * frame.  Sums are accumulated in double in a fixed order (deterministic; the reference accumulates in float32 in
+ * raster order, so its own figures differ from the exact sums in the 4th-5th digit).  An empty mask gives NaN like
+ * the reference's 0 / 0. */
+enum { DCMT_EVAL_GT_VALID = 0, DCMT_EVAL_BOTH_VALID = 1 };
+typedef struct dcmt_eval_result {
+    double count, sum_err, sum_abs, sum_sq;
+    float mean_err, mae, rmse;
+    int32_t pad;
+} dcmt_eval_result;
+DCMT_API int dcmt_evaluate_f32(const float *gt, const float *dense, int rows, int cols, size_t pitch_bytes,
+                               size_t frame_stride_bytes, int n_frames, float tolerance, int mode,
+                               dcmt_eval_result *results /* device, n_frames */, void *cuda_stream);
+DCMT_API int dcmt_evaluate_f32_host(const float *gt, const float *dense, int rows, int cols, size_t pitch_bytes,
+                                    size_t frame_stride_bytes, int n_frames, float tolerance, int mode,
+                                    dcmt_eval_result *results /* host, n_frames */);
+
 /* debugging aid: runs the generic pipeline on ONE frame and snapshots intermediate images
  * (device memory, n_stages * rows * cols floats, stage order of oracle/dcmt_oracle.c; stages the
  * kernels never materialise are left untouched).  `stage_mask_out` (host) gets a bit per stage written. */

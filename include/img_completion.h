@@ -59,6 +59,39 @@ inline void img_completion(const MatView& sparse, MatView& dense, const bool& /*
     // stride of input and output must agree in the ABI; MatViews with different steps are handled by the cv::Mat overload
 }
 
+// main.cpp:75-93 in one call: the uint16 payload of a KITTI depth PNG (CV_16UC1 view, metres * 256) -> dense float32 metres;
+// stands for image_r.convertTo(projected_depths, CV_32F, 1.0 / 256.0) (:79) followed by img_completion (:93)
+inline void img_completion_u16(const MatView& sparse_u16, MatView& dense, const std::string& blur_type, int path = DCMT_PATH_AUTO) {
+    if (dense.rows != sparse_u16.rows || dense.cols != sparse_u16.cols || !dense.data) throw std::invalid_argument("dcmt: dense view not allocated");
+    check(dcmt_img_completion_u16_host(static_cast<const uint16_t*>(sparse_u16.data), static_cast<float*>(dense.data), sparse_u16.rows,
+                                       sparse_u16.cols, sparse_u16.step, 0, dense.step, 0, 1, blur_code(blur_type), path, nullptr));
+}
+
+// The evaluation loops of the three programs; GT and result must share one step.
+inline dcmt_eval_result evaluate(const MatView& GT_img, const MatView& r_img, float tolerance, int mode) {
+    if (GT_img.rows != r_img.rows || GT_img.cols != r_img.cols || GT_img.step != r_img.step) throw std::invalid_argument("dcmt: evaluate needs same-shaped Mats");
+    dcmt_eval_result res;
+    check(dcmt_evaluate_f32_host(static_cast<const float*>(GT_img.data), static_cast<const float*>(r_img.data), GT_img.rows, GT_img.cols,
+                                 GT_img.step, 0, 1, tolerance, mode, &res));
+    return res;
+}
+// src/DC_lidar_only/main.cpp:16-34: "mse" = mean of (gt - r) over gt > 0 (a signed mean, sic)
+inline void evaluate_performance(const MatView& GT_img, const MatView& r_img, float& mse) {
+    mse = evaluate(GT_img, r_img, 0.0f, DCMT_EVAL_GT_VALID).mean_err;
+}
+// src/DC_lidar_camera/main_lc.cpp:85-116: `int tolerance = 0.1` is 0; "mse" = sqrt(sum d^2 / count) (sic), mae
+inline void evaluate_performance(const MatView& GT_img, const MatView& r_img, float& mse, float& mae) {
+    const dcmt_eval_result r = evaluate(GT_img, r_img, 0.0f, DCMT_EVAL_BOTH_VALID);
+    mse = r.rmse;
+    mae = r.mae;
+}
+// src/DC_stereo_lidar/main_sl.cpp:1031-1061: tolerance 2
+inline void evaluate_performances(const MatView& GT_img, const MatView& r_img, float& mae, float& rmse) {
+    const dcmt_eval_result r = evaluate(GT_img, r_img, 2.0f, DCMT_EVAL_BOTH_VALID);
+    mae = r.mae;
+    rmse = r.rmse;
+}
+
 // img_completion_lc.cpp:34-203.  `clusters_col_major` is Slic::clusters, indexed [col][row] (:83); it is transposed
 // into the row-major int32 label map of the ABI here.  `n_centers` is slic.centers.size().
 inline void interpolate_with_superpixels(const std::vector<std::vector<int>>& clusters_col_major, size_t n_centers,
@@ -100,8 +133,15 @@ namespace dcmt {
 inline MatView view_of(const cv::Mat& m) { return MatView{m.rows, m.cols, (size_t)m.step, m.data}; }
 }  // namespace dcmt
 
-// img_completion.cpp:17-20
+// img_completion.cpp:17-20.  A CV_16UC1 Mat (the KITTI PNG as read by cv::imread(..., IMREAD_ANYDEPTH), main.cpp:75) is
+// accepted as well and stands for convertTo(CV_32F, 1.0 / 256.0) + img_completion.
 inline void img_completion(const cv::Mat& sparse_r_img, cv::Mat& dense_r_img, const bool& extr, const std::string& blur_type) {
+    if (sparse_r_img.type() == CV_16UC1) {
+        dense_r_img.create(sparse_r_img.rows, sparse_r_img.cols, CV_32FC1);
+        dcmt::MatView s16 = dcmt::view_of(sparse_r_img), d16 = dcmt::view_of(dense_r_img);
+        dcmt::img_completion_u16(s16, d16, blur_type);
+        return;
+    }
     CV_Assert(sparse_r_img.type() == CV_32FC1);
     cv::Mat in = sparse_r_img.isContinuous() ? sparse_r_img : sparse_r_img.clone();
     dense_r_img.create(in.rows, in.cols, CV_32FC1);  // the reference's `dense = sparse.clone()` (:27)
@@ -130,6 +170,20 @@ inline void stereo_refine(const cv::Mat& dense_range_img, const cv::Mat& left_gr
     optimized_depth.create(ig.rows, ig.cols, CV_32FC1);
     dcmt::MatView vi = dcmt::view_of(ig), vl = dcmt::view_of(l), vr = dcmt::view_of(r), vo = dcmt::view_of(optimized_depth);
     dcmt::stereo_refine(vi, vl, vr, vo, params);
+}
+
+// the evaluation functions of main.cpp:16 / main_lc.cpp:85 / main_sl.cpp:1031 (CV_32FC1 Mats)
+inline void evaluate_performance(const cv::Mat& GT_img, const cv::Mat& r_img, float& mse) {
+    cv::Mat g = GT_img.isContinuous() ? GT_img : GT_img.clone(), r = r_img.isContinuous() ? r_img : r_img.clone();
+    dcmt::evaluate_performance(dcmt::view_of(g), dcmt::view_of(r), mse);
+}
+inline void evaluate_performance(const cv::Mat& GT_img, const cv::Mat& r_img, float& mse, float& mae) {
+    cv::Mat g = GT_img.isContinuous() ? GT_img : GT_img.clone(), r = r_img.isContinuous() ? r_img : r_img.clone();
+    dcmt::evaluate_performance(dcmt::view_of(g), dcmt::view_of(r), mse, mae);
+}
+inline void evaluate_performances(cv::Mat& GT_img, cv::Mat& r_img, float& mae, float& rmse) {
+    cv::Mat g = GT_img.isContinuous() ? GT_img : GT_img.clone(), r = r_img.isContinuous() ? r_img : r_img.clone();
+    dcmt::evaluate_performances(dcmt::view_of(g), dcmt::view_of(r), mae, rmse);
 }
 #endif  // DCMT_HAVE_OPENCV
 

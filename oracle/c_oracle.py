@@ -148,3 +148,13 @@ def op_column_extrapolation(src):
     s = np.array(src, dtype=np.float32, order="C", copy=True)
     lib().dcmt_oracle_op_column_extrapolation(s.ctypes.data_as(C.POINTER(C.c_float)), s.shape[0], s.shape[1])
     return s
+
+
+def evaluate(gt, r, tolerance: int = 0, mode: int = 1):
+    """Literal float32 raster-order evaluation loop (main.cpp:16-34 mode 0; main_lc.cpp:85-116 / main_sl.cpp:1031-1061
+    mode 1).  Returns dict(mean_err, mae, rmse, count)."""
+    g, gp = _f32(gt)
+    v, vp = _f32(r)
+    out = np.zeros(4, np.float32)
+    lib().dcmt_oracle_evaluate(gp, vp, g.shape[0], g.shape[1], int(tolerance), int(mode), out.ctypes.data_as(C.POINTER(C.c_float)))
+    return {"mean_err": float(out[0]), "mae": float(out[1]), "rmse": float(out[2]), "count": int(out[3])}

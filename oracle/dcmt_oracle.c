@@ -508,3 +508,30 @@ DCMT_ORACLE_API void dcmt_oracle_op_gaussian5(const float *s, float *d, int rows
 DCMT_ORACLE_API void dcmt_oracle_op_bilateral5(const float *s, float *d, int rows, int cols) { bilateral5(s, d, rows, cols); }
 DCMT_ORACLE_API void dcmt_oracle_op_column_extrapolation(float *d, int rows, int cols) { column_extrapolation(d, rows, cols); }
 DCMT_ORACLE_API int dcmt_oracle_n_stages(void) { return DCMT_ORACLE_N_STAGES; }
+
+/* ---------------------------------------------------------------- evaluation
+ * Literal restatement of the three evaluation loops: float32 accumulators, raster order.
+ *   mode 0  src/DC_lidar_only/main.cpp:16-34        mask gt > tol             out[0] = sum(gt - r) / count
+ *   mode 1  src/DC_lidar_camera/main_lc.cpp:85-116  mask gt > tol && r > tol  out[1] = sum|d| / count, out[2] = sqrt(sum d^2 / count)
+ *           src/DC_stereo_lidar/main_sl.cpp:1031-1061 (tolerance 2)
+ * `tolerance` is the reference's int (0, (int)0.1 = 0, 2).  out[3] = count. */
+DCMT_ORACLE_API void dcmt_oracle_evaluate(const float *gt, const float *r, int rows, int cols, int tolerance, int mode, float *out) {
+    float sum_err = 0, sum_mse = 0, sum_mae = 0;
+    int count = 0;
+    for (int i = 0; i < rows; i++)
+        for (int j = 0; j < cols; j++) {
+            const float g = gt[(size_t)i * cols + j], v = r[(size_t)i * cols + j];
+            if (mode == 0) {
+                if (g > tolerance) { sum_err += (g - v); count++; }
+            } else if (g > tolerance && v > tolerance) {
+                const float d = fabsf(g - v);
+                sum_mse += d * d;
+                sum_mae += d;
+                count++;
+            }
+        }
+    out[0] = sum_err / count;
+    out[1] = sum_mae / count;
+    out[2] = sqrtf(sum_mse / count);
+    out[3] = (float)count;
+}

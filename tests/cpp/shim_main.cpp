@@ -23,6 +23,17 @@ int main(int argc, char** argv) {
         std::fprintf(stderr, "%s\n", e.what());
         return 4;
     }
+    // the caller's evaluation against its own input as "ground truth" (main.cpp:101, main_lc.cpp:224, main_sl.cpp:1232)
+    try {
+        float mse = 0, rmse = 0, mae = 0, mae2 = 0, rmse2 = 0;
+        dcmt::evaluate_performance(sparse, dense, mse);
+        dcmt::evaluate_performance(sparse, dense, rmse, mae);
+        dcmt::evaluate_performances(sparse, dense, mae2, rmse2);
+        std::printf("%.9g %.9g %.9g %.9g %.9g\n", mse, rmse, mae, mae2, rmse2);
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "%s\n", e.what());
+        return 4;
+    }
     f = std::fopen(argv[4], "wb");
     std::fwrite(out.data(), sizeof(float), out.size(), f);
     std::fclose(f);

@@ -119,6 +119,8 @@ static inline unsigned __ballot_sync(unsigned, int p) { return dcmt_emu::warp_ba
 static inline int __any_sync(unsigned, int p) { return dcmt_emu::warp_ballot(p) != 0; }
 static inline int __all_sync(unsigned, int p) { return dcmt_emu::warp_ballot(!p) == 0; }
 static inline long long clock64() { static long long c = 0; return ++c; }
+static inline long long __double_as_longlong(double d) { long long u; std::memcpy(&u, &d, 8); return u; }
+static inline double __longlong_as_double(long long u) { double d; std::memcpy(&d, &u, 8); return d; }
 static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __clz(int v) { return v == 0 ? 32 : __builtin_clz((unsigned)v); }

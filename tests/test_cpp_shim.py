@@ -31,6 +31,16 @@ def run_shim(exe, tmp_path, s, blur):
     return r, (np.fromfile(fout, np.float32).reshape(s.shape) if r.returncode == 0 else None)
 
 
+def check_eval(stdout, gt, dense):
+    """the shim's evaluate_performance / evaluate_performances against the literal float32 loops"""
+    mse, rmse, mae, mae2, rmse2 = (float(v) for v in stdout.split())
+    assert abs(mse - co.evaluate(gt, dense, 0, 0)["mean_err"]) < 1e-4
+    ref = co.evaluate(gt, dense, 0, 1)
+    assert abs(rmse - ref["rmse"]) < 1e-3 and abs(mae - ref["mae"]) < 1e-3
+    ref = co.evaluate(gt, dense, 2, 1)
+    assert abs(rmse2 - ref["rmse"]) < 1e-3 and abs(mae2 - ref["mae"]) < 1e-3
+
+
 def test_shim_on_emulator_matches_oracle(tmp_path, emu_lib):
     exe = compile_shim(tmp_path, emu_lib.path)
     for blur in ("gaussian", "none", "something else"):
@@ -38,6 +48,7 @@ def test_shim_on_emulator_matches_oracle(tmp_path, emu_lib):
         r, out = run_shim(exe, tmp_path, s, blur)
         assert r.returncode == 0, r.stderr
         assert_bit_equal(out, co.img_completion(s, blur if blur in ("gaussian", "none") else "none"), f"shim {blur}")
+        check_eval(r.stdout, s, out)
 
 
 def test_shim_with_product_library_fails_loudly_without_gpu(tmp_path):
@@ -57,3 +68,4 @@ def test_shim_with_product_library_on_gpu(tmp_path, gpu_lib):
     r, out = run_shim(exe, tmp_path, s, "gaussian")
     assert r.returncode == 0, r.stderr
     assert_bit_equal(out, co.img_completion(s, "gaussian"), "shim on the GPU")
+    check_eval(r.stdout, s, out)
