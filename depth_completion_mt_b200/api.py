@@ -349,3 +349,37 @@ def evaluate_performances(GT_img, r_img, **kw):
     """evaluate_performances(GT_img, r_img, mae, rmse), main_sl.cpp:1031-1061 (tolerance 2) -> (mae, rmse)."""
     rec = evaluate(GT_img, r_img, "stereo_lidar", **kw)[0]
     return float(rec["mae"]), float(rec["rmse"])
+
+
+# ---------------------------------------------------------------------------------------------- LiDAR projection (8f #2)
+def lidar_project(points, T, P, rows: int, cols: int, norm=(0.0, 80.0), *, return_count: bool = False, stream=None,
+                  lib: _lib.Library | None = None):
+    """main_sl.cpp:478-523: Velodyne points (n, 4) float32 -> (projected_depths, normalized_depths).
+
+    ``T`` is the 4x4 velodyne-to-camera transform, ``P`` the 3x4 projection matrix (numpy, row-major like the maths;
+    the reference holds them as Eigen matrices).  Last point in file order wins a pixel (:515);
+    ``normalized = cv::normalize(projected, norm[0], norm[1], NORM_MINMAX)`` (:521)."""
+    lib = lib or _lib.load()
+    Tm = np.ascontiguousarray(np.asarray(T, np.float32).reshape(4, 4))
+    Pm = np.ascontiguousarray(np.asarray(P, np.float32).reshape(3, 4))
+    if _is_torch(points):
+        pts = _prep_torch(points, torch.float32, "points")
+        if pts.ndim != 2 or pts.shape[1] != 4:
+            raise ValueError("points must be (n, 4)")
+        proj = torch.empty((rows, cols), dtype=torch.float32, device=pts.device)
+        nrm = torch.empty_like(proj)
+        cnt = torch.zeros(1, dtype=torch.int32, device=pts.device)
+        with torch.cuda.device(pts.device):
+            lib.check(lib.dcmt_lidar_project_f32(pts.data_ptr() if pts.numel() else None, pts.shape[0], _np_ptr(Tm), _np_ptr(Pm), rows, cols,
+                                                 proj.data_ptr(), nrm.data_ptr(), float(norm[0]), float(norm[1]), cnt.data_ptr(),
+                                                 _stream_ptr(stream)))
+        return (proj, nrm, int(cnt.item())) if return_count else (proj, nrm)
+    pts = _prep_numpy(points, np.float32, "points")
+    if pts.ndim != 2 or pts.shape[1] != 4:
+        raise ValueError("points must be (n, 4)")
+    proj = np.empty((rows, cols), np.float32)
+    nrm = np.empty_like(proj)
+    cnt = np.zeros(1, np.int32)
+    lib.check(lib.dcmt_lidar_project_f32_host(_np_ptr(pts) if pts.size else None, pts.shape[0], _np_ptr(Tm), _np_ptr(Pm), rows, cols,
+                                              _np_ptr(proj), _np_ptr(nrm), float(norm[0]), float(norm[1]), _np_ptr(cnt)))
+    return (proj, nrm, int(cnt[0])) if return_count else (proj, nrm)

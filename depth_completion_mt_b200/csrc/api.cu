@@ -15,6 +15,7 @@
 #include "evaluate.cuh"
 #include "fused_q8.cuh"
 #include "generic.cuh"
+#include "project.cuh"
 #include "stereo.cuh"
 
 #include <atomic>
@@ -610,6 +611,8 @@ int run_completion_u16_host(const uint16_t* sparse, float* dense, int rows, int 
 
 extern "C" {
 
+static int check_planes(int rows, int cols, int n_frames);
+
 int dcmt_version(void) { return DCMT_VERSION; }
 const char* dcmt_last_error(void) { return g_err; }
 
@@ -764,6 +767,57 @@ int dcmt_debug_q8_phase_cycles(const float* sparse, float* dense, int rows, int 
     API_CUDA(dcmt::q8_run_front(p, sparse, nullptr, cols, fpix, n_frames, 1, st), "fused front launch");
     API_CUDA(dcmt::q8_run_tail(p, dense, cols, fpix, n_frames, DCMT_BLUR_GAUSSIAN, st), "fused tail launch");
     return DCMT_OK;
+}
+
+int dcmt_lidar_project_f32(const float* points, int n_points, const float* T_host, const float* P_host, int rows, int cols,
+                           float* projected, float* normalized, float norm_a, float norm_b, int32_t* n_projected, void* cuda_stream) {
+    if ((!points && n_points > 0) || !T_host || !P_host) return fail(DCMT_E_BADARG, "null pointer");
+    if (n_points < 0) return fail(DCMT_E_BADARG, "n_points must be >= 0 (got %d)", n_points);
+    int rc = check_planes(rows, cols, 1);
+    if (rc) return rc;
+    if ((size_t)rows * (size_t)cols > (size_t)1 << 30) return fail(DCMT_E_UNSUPPORTED, "frame larger than 2^30 pixels");
+    if (points && (reinterpret_cast<uintptr_t>(points) & 15)) return fail(DCMT_E_BADARG, "points must be 16-byte aligned");
+    if ((rc = check_device())) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    Arena* ar = nullptr;
+    const size_t nk = dcmt::project_key_count(rows, cols);
+    if ((rc = arena_acquire(st, carve_bytes(nk, sizeof(unsigned long long)) + carve_bytes(8, sizeof(unsigned)), &ar))) return rc;
+    dcmt::ProjectWork w{carve<unsigned long long>(ar, nk), carve<unsigned>(ar, 8)};
+    API_CUDA(dcmt::project_run(points, n_points, T_host, P_host, rows, cols, projected, normalized, norm_a, norm_b, n_projected, w, st),
+             "projection launch");
+    return DCMT_OK;
+}
+
+int dcmt_lidar_project_f32_host(const float* points, int n_points, const float* T_host, const float* P_host, int rows, int cols,
+                                float* projected, float* normalized, float norm_a, float norm_b, int32_t* n_projected) {
+    if ((!points && n_points > 0) || !T_host || !P_host) return fail(DCMT_E_BADARG, "null pointer");
+    if (n_points < 0) return fail(DCMT_E_BADARG, "n_points must be >= 0 (got %d)", n_points);
+    int rc = check_planes(rows, cols, 1);
+    if (rc) return rc;
+    if ((rc = check_device())) return rc;
+    const size_t n = (size_t)rows * cols;
+    float *d_pts = nullptr, *d_proj = nullptr, *d_norm = nullptr;
+    int32_t* d_cnt = nullptr;
+    auto cleanup = [&] { cudaFree(d_pts); cudaFree(d_proj); cudaFree(d_norm); cudaFree(d_cnt); };
+    cudaError_t e;
+    if ((e = cudaMalloc(&d_pts, (size_t)(n_points > 0 ? n_points : 1) * 16)) != cudaSuccess || (e = cudaMalloc(&d_proj, n * 4)) != cudaSuccess ||
+        (e = cudaMalloc(&d_norm, n * 4)) != cudaSuccess || (e = cudaMalloc(&d_cnt, 4)) != cudaSuccess) {
+        cleanup();
+        return fail(DCMT_E_NOMEM, "device staging buffers: %s", cudaGetErrorString(e));
+    }
+    if (n_points > 0 && (e = cudaMemcpy(d_pts, points, (size_t)n_points * 16, cudaMemcpyHostToDevice)) != cudaSuccess) {
+        cleanup();
+        return cuda_fail(e, "host to device copy");
+    }
+    rc = dcmt_lidar_project_f32(d_pts, n_points, T_host, P_host, rows, cols, d_proj, d_norm, norm_a, norm_b, d_cnt, nullptr);
+    if (rc == DCMT_OK) {
+        if ((e = cudaStreamSynchronize(nullptr)) != cudaSuccess) rc = cuda_fail(e, "kernel execution");
+        else if (projected && (e = cudaMemcpy(projected, d_proj, n * 4, cudaMemcpyDeviceToHost)) != cudaSuccess) rc = cuda_fail(e, "device to host copy");
+        else if (normalized && (e = cudaMemcpy(normalized, d_norm, n * 4, cudaMemcpyDeviceToHost)) != cudaSuccess) rc = cuda_fail(e, "device to host copy");
+        else if (n_projected && (e = cudaMemcpy(n_projected, d_cnt, 4, cudaMemcpyDeviceToHost)) != cudaSuccess) rc = cuda_fail(e, "device to host copy");
+    }
+    cleanup();
+    return rc;
 }
 
 static_assert(sizeof(dcmt_eval_result) == sizeof(dcmt::EvalResult), "dcmt_eval_result and dcmt::EvalResult must match");

@@ -88,3 +88,27 @@ def stereo_pair(frame: int, rows: int = KITTI_ROWS, cols: int = KITTI_COLS, dens
     holes = rng.random((rows, cols)) < 0.01  # a few zero pixels: disparity stays 0 there
     depth_ig[holes] = 0.0
     return depth_ig, left, right
+
+
+# KITTI raw calibration, drive 2011_09_26 (public calib_velo_to_cam.txt / calib_cam_to_cam.txt values): velodyne -> camera 0,
+# rectification, projection of camera 2.  Used for synthetic LiDAR clouds only.
+KITTI_T_VELO_TO_CAM = np.array([
+    [7.533745e-03, -9.999714e-01, -6.166020e-04, -4.069766e-03],
+    [1.480249e-02, 7.280733e-04, -9.998902e-01, -7.631618e-02],
+    [9.998621e-01, 7.523790e-03, 1.480755e-02, -2.717806e-01],
+    [0.0, 0.0, 0.0, 1.0]], np.float32)
+KITTI_P_RECT_02 = np.array([
+    [7.215377e+02, 0.0, 6.095593e+02, 4.485728e+01],
+    [0.0, 7.215377e+02, 1.728540e+02, 2.163791e-01],
+    [0.0, 0.0, 1.0, 2.745884e-03]], np.float32)
+
+
+def velodyne_cloud(frame: int, n_points: int = 120000) -> np.ndarray:
+    """Synthetic Velodyne HDL-64 sweep as the (n, 4) float32 payload of a KITTI .bin: 64 elevation rings over the full
+    azimuth, ranges from a random piecewise-smooth scene (3 .. 80 m), intensity in [0, 1)."""
+    rng = np.random.default_rng(BASE_SEED + 300007 + frame)
+    az = rng.uniform(-np.pi, np.pi, n_points)
+    el = np.deg2rad(rng.integers(0, 64, n_points) * (26.8 / 63.0) - 24.8)
+    rg = 3.0 + 77.0 * np.abs(np.sin(3.0 * az + rng.uniform(0, 6.28))) * rng.uniform(0.3, 1.0, n_points)
+    x, y, z = rg * np.cos(el) * np.cos(az), rg * np.cos(el) * np.sin(az), rg * np.sin(el)
+    return np.stack([x, y, z, rng.random(n_points)], axis=1).astype(np.float32)

@@ -196,6 +196,22 @@ DCMT_API int dcmt_evaluate_f32_host(const float *gt, const float *dense, int row
                                     size_t frame_stride_bytes, int n_frames, float tolerance, int mode,
                                     dcmt_eval_result *results /* host, n_frames */);
 
+/* (8f #2) LiDAR projection + normalisation: replaces the loops of src/DC_stereo_lidar/main_sl.cpp:478-523 (withSuperPixels;
+ * the same code in vedi_pc :340-385): Velodyne points (n_points x 4 float32: x, y, z, intensity -- the .bin payload)
+ * -> T (4x4, velodyne to camera; rows 0..2 used) -> keep z > 0 -> P (3x4) -> perspective division -> bounds test ->
+ * (int) truncation -> depth scatter where the LAST point in file order wins -> cv::normalize(NORM_MINMAX, norm_a,
+ * norm_b) (the reference uses 0, 80).  T and P are HOST pointers, row-major (Eigen's default storage is column-major:
+ * pass the transpose or use the C++ shim).  `projected` receives the sparse depth image (main_sl.cpp's
+ * projected_depths, 0 = empty), `normalized` the normalised one (the input of interpolate_with_superpixels); either may
+ * be NULL.  `n_projected` (int32, optional) counts the points that landed in the image (:508).  Float arithmetic
+ * follows the source order without FMA contraction; the result is deterministic. */
+DCMT_API int dcmt_lidar_project_f32(const float *points, int n_points, const float *T_host, const float *P_host, int rows,
+                                    int cols, float *projected_or_null, float *normalized_or_null, float norm_a,
+                                    float norm_b, int32_t *n_projected_or_null, void *cuda_stream);
+DCMT_API int dcmt_lidar_project_f32_host(const float *points, int n_points, const float *T_host, const float *P_host,
+                                         int rows, int cols, float *projected_or_null, float *normalized_or_null,
+                                         float norm_a, float norm_b, int32_t *n_projected_or_null);
+
 /* debugging aid: runs the generic pipeline on ONE frame and snapshots intermediate images
  * (device memory, n_stages * rows * cols floats, stage order of oracle/dcmt_oracle.c; stages the
  * kernels never materialise are left untouched).  `stage_mask_out` (host) gets a bit per stage written. */

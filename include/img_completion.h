@@ -92,6 +92,20 @@ inline void evaluate_performances(const MatView& GT_img, const MatView& r_img, f
     rmse = r.rmse;
 }
 
+// main_sl.cpp:478-523: the Velodyne .bin payload (n_points x 4 floats) -> projected_depths and its cv::normalize(0, 80).
+// T (4x4) and P (3x4) are row-major here; from Eigen pass `Eigen::Matrix<float, 4, 4, Eigen::RowMajor>(T).data()`.
+inline int project_lidar(const float* points, int n_points, const float* T_row_major, const float* P_row_major, MatView& projected_depths,
+                         MatView& normalized_depths, float norm_a = 0.0f, float norm_b = 80.0f) {
+    const int rows = projected_depths.rows, cols = projected_depths.cols;
+    if (normalized_depths.rows != rows || normalized_depths.cols != cols || projected_depths.step != (size_t)cols * 4 ||
+        normalized_depths.step != (size_t)cols * 4)
+        throw std::invalid_argument("dcmt: project_lidar needs continuous same-shaped Mats");
+    int32_t n = 0;
+    check(dcmt_lidar_project_f32_host(points, n_points, T_row_major, P_row_major, rows, cols, static_cast<float*>(projected_depths.data),
+                                      static_cast<float*>(normalized_depths.data), norm_a, norm_b, &n));
+    return n;
+}
+
 // img_completion_lc.cpp:34-203.  `clusters_col_major` is Slic::clusters, indexed [col][row] (:83); it is transposed
 // into the row-major int32 label map of the ABI here.  `n_centers` is slic.centers.size().
 inline void interpolate_with_superpixels(const std::vector<std::vector<int>>& clusters_col_major, size_t n_centers,

@@ -158,3 +158,19 @@ def evaluate(gt, r, tolerance: int = 0, mode: int = 1):
     out = np.zeros(4, np.float32)
     lib().dcmt_oracle_evaluate(gp, vp, g.shape[0], g.shape[1], int(tolerance), int(mode), out.ctypes.data_as(C.POINTER(C.c_float)))
     return {"mean_err": float(out[0]), "mae": float(out[1]), "rmse": float(out[2]), "count": int(out[3])}
+
+
+def lidar_project(points, T, P, rows, cols, norm=(0.0, 80.0)):
+    """Literal main_sl.cpp:478-523 + cv::normalize: returns (projected, normalized, count)."""
+    pts, pp = _f32(np.asarray(points, np.float32).reshape(-1, 4))
+    Tm, tp = _f32(np.asarray(T, np.float32).reshape(4, 4))
+    Pm, ppm = _f32(np.asarray(P, np.float32).reshape(3, 4))
+    proj = np.empty((rows, cols), np.float32)
+    nrm = np.empty((rows, cols), np.float32)
+    fn = lib().dcmt_oracle_lidar_project
+    fn.restype = C.c_int
+    fn.argtypes = [C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.c_int, C.POINTER(C.c_float),
+                   C.POINTER(C.c_float), C.c_float, C.c_float]
+    cnt = fn(pp, pts.shape[0], tp, ppm, rows, cols, proj.ctypes.data_as(C.POINTER(C.c_float)), nrm.ctypes.data_as(C.POINTER(C.c_float)),
+             float(norm[0]), float(norm[1]))
+    return proj, nrm, int(cnt)
