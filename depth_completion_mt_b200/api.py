@@ -383,3 +383,37 @@ def lidar_project(points, T, P, rows: int, cols: int, norm=(0.0, 80.0), *, retur
     lib.check(lib.dcmt_lidar_project_f32_host(_np_ptr(pts) if pts.size else None, pts.shape[0], _np_ptr(Tm), _np_ptr(Pm), rows, cols,
                                               _np_ptr(proj), _np_ptr(nrm), float(norm[0]), float(norm[1]), _np_ptr(cnt)))
     return (proj, nrm, int(cnt[0])) if return_count else (proj, nrm)
+
+
+# ---------------------------------------------------------------------------------------------- SLIC (8f #1)
+def generate_superpixels(lab_image, step, nc: int, *, iterations: int = 10, return_centers: bool = False, stream=None,
+                         lib: _lib.Library | None = None):
+    """Slic::generate_superpixels(lab_image, step, nc), slic.cpp:101-182.
+
+    ``lab_image`` is (rows, cols, 3) uint8 after COLOR_BGR2Lab; ``step`` is truncated to int like the reference's int
+    parameter (main_lc.cpp:197-201 passes a double).  Returns the label map ``Slic::clusters`` as int32 [row][col]
+    (-1 = never assigned) and, optionally, ``Slic::centers`` (K, 5) float64.  ``K = len(centers)`` is the ``n_clusters``
+    argument of interpolate_with_superpixels."""
+    lib = lib or _lib.load()
+    step = int(step)
+    if _is_torch(lab_image):
+        lab = _prep_torch(lab_image, torch.uint8, "lab_image")
+        if lab.ndim != 3 or lab.shape[2] != 3:
+            raise ValueError("lab_image must be (rows, cols, 3)")
+        rows, cols = int(lab.shape[0]), int(lab.shape[1])
+        k = lib.dcmt_slic_center_count(rows, cols, step)
+        labels = torch.empty((rows, cols), dtype=torch.int32, device=lab.device)
+        centers = torch.empty((max(k, 1), 5), dtype=torch.float64, device=lab.device)
+        with torch.cuda.device(lab.device):
+            lib.check(lib.dcmt_slic_u8c3(lab.data_ptr(), rows, cols, step, int(nc), int(iterations), labels.data_ptr(), centers.data_ptr(),
+                                         _stream_ptr(stream)))
+        return (labels, centers[:k]) if return_centers else labels
+    lab = _prep_numpy(lab_image, np.uint8, "lab_image")
+    if lab.ndim != 3 or lab.shape[2] != 3:
+        raise ValueError("lab_image must be (rows, cols, 3)")
+    rows, cols = lab.shape[:2]
+    k = lib.dcmt_slic_center_count(rows, cols, step)
+    labels = np.empty((rows, cols), np.int32)
+    centers = np.empty((max(k, 1), 5), np.float64)
+    lib.check(lib.dcmt_slic_u8c3_host(_np_ptr(lab), rows, cols, step, int(nc), int(iterations), _np_ptr(labels), _np_ptr(centers)))
+    return (labels, centers[:k]) if return_centers else labels

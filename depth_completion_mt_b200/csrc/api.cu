@@ -16,6 +16,7 @@
 #include "fused_q8.cuh"
 #include "generic.cuh"
 #include "project.cuh"
+#include "slic.cuh"
 #include "stereo.cuh"
 
 #include <atomic>
@@ -767,6 +768,73 @@ int dcmt_debug_q8_phase_cycles(const float* sparse, float* dense, int rows, int 
     API_CUDA(dcmt::q8_run_front(p, sparse, nullptr, cols, fpix, n_frames, 1, st), "fused front launch");
     API_CUDA(dcmt::q8_run_tail(p, dense, cols, fpix, n_frames, DCMT_BLUR_GAUSSIAN, st), "fused tail launch");
     return DCMT_OK;
+}
+
+int dcmt_slic_center_count(int rows, int cols, int step) {
+    if (rows < 1 || cols < 1 || step < 1) return 0;
+    return dcmt::slic_center_count(rows, cols, step);
+}
+
+int dcmt_slic_u8c3(const uint8_t* lab, int rows, int cols, int step, int nc, int iterations, int32_t* labels, double* centers,
+                   void* cuda_stream) {
+    if (!lab || !labels) return fail(DCMT_E_BADARG, "null pointer");
+    int rc = check_planes(rows, cols, 1);
+    if (rc) return rc;
+    if (nc == 0 || iterations < 0) return fail(DCMT_E_BADARG, "nc %d, iterations %d", nc, iterations);
+    if (step < 4) return fail(DCMT_E_UNSUPPORTED, "step %d: find_local_minimum (slic.cpp:72-99) reads outside the image below 4", step);
+    if ((size_t)rows * (size_t)cols > (size_t)1 << 30) return fail(DCMT_E_UNSUPPORTED, "frame larger than 2^30 pixels");
+    if ((rc = check_device())) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    const int k = dcmt::slic_center_count(rows, cols, step);
+    dcmt::SlicWork w{};
+    const size_t nbins = dcmt::slic_bins(rows, cols, step, &w.bins_x, &w.bins_y);
+    const size_t kk = k > 0 ? (size_t)k : 1;
+    Arena* ar = nullptr;
+    if ((rc = arena_acquire(st, carve_bytes(kk * 5, sizeof(double)) + carve_bytes(kk * 6, sizeof(unsigned long long)) +
+                                    carve_bytes(nbins + 1, sizeof(int)) + carve_bytes(nbins, sizeof(int)) + carve_bytes(kk, sizeof(int)),
+                            &ar)))
+        return rc;
+    w.centers = carve<double>(ar, kk * 5);
+    w.sums = carve<unsigned long long>(ar, kk * 6);
+    w.bin_count = carve<int>(ar, nbins + 1);
+    w.bin_fill = carve<int>(ar, nbins);
+    w.bin_items = carve<int>(ar, kk);
+    API_CUDA(dcmt::slic_run(lab, rows, cols, step, nc, iterations, labels, k, w, st), "SLIC launch");
+    if (centers && k > 0)
+        API_CUDA(cudaMemcpyAsync(centers, w.centers, (size_t)k * 5 * sizeof(double), cudaMemcpyDeviceToDevice, st), "centre copy");
+    return DCMT_OK;
+}
+
+int dcmt_slic_u8c3_host(const uint8_t* lab, int rows, int cols, int step, int nc, int iterations, int32_t* labels, double* centers) {
+    if (!lab || !labels) return fail(DCMT_E_BADARG, "null pointer");
+    int rc = check_planes(rows, cols, 1);
+    if (rc) return rc;
+    if ((rc = check_device())) return rc;
+    const size_t n = (size_t)rows * cols;
+    const int k = step >= 1 ? dcmt::slic_center_count(rows, cols, step) : 0;
+    uint8_t* d_lab = nullptr;
+    int32_t* d_labels = nullptr;
+    double* d_centers = nullptr;
+    auto cleanup = [&] { cudaFree(d_lab); cudaFree(d_labels); cudaFree(d_centers); };
+    cudaError_t e;
+    if ((e = cudaMalloc(&d_lab, n * 3)) != cudaSuccess || (e = cudaMalloc(&d_labels, n * 4)) != cudaSuccess ||
+        (e = cudaMalloc(&d_centers, (size_t)(k > 0 ? k : 1) * 5 * sizeof(double))) != cudaSuccess) {
+        cleanup();
+        return fail(DCMT_E_NOMEM, "device staging buffers: %s", cudaGetErrorString(e));
+    }
+    if ((e = cudaMemcpy(d_lab, lab, n * 3, cudaMemcpyHostToDevice)) != cudaSuccess) {
+        cleanup();
+        return cuda_fail(e, "host to device copy");
+    }
+    rc = dcmt_slic_u8c3(d_lab, rows, cols, step, nc, iterations, d_labels, centers ? d_centers : nullptr, nullptr);
+    if (rc == DCMT_OK) {
+        if ((e = cudaStreamSynchronize(nullptr)) != cudaSuccess) rc = cuda_fail(e, "kernel execution");
+        else if ((e = cudaMemcpy(labels, d_labels, n * 4, cudaMemcpyDeviceToHost)) != cudaSuccess) rc = cuda_fail(e, "device to host copy");
+        else if (centers && k > 0 && (e = cudaMemcpy(centers, d_centers, (size_t)k * 5 * sizeof(double), cudaMemcpyDeviceToHost)) != cudaSuccess)
+            rc = cuda_fail(e, "device to host copy");
+    }
+    cleanup();
+    return rc;
 }
 
 int dcmt_lidar_project_f32(const float* points, int n_points, const float* T_host, const float* P_host, int rows, int cols,

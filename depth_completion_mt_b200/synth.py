@@ -112,3 +112,17 @@ def velodyne_cloud(frame: int, n_points: int = 120000) -> np.ndarray:
     rg = 3.0 + 77.0 * np.abs(np.sin(3.0 * az + rng.uniform(0, 6.28))) * rng.uniform(0.3, 1.0, n_points)
     x, y, z = rg * np.cos(el) * np.cos(az), rg * np.cos(el) * np.sin(az), rg * np.sin(el)
     return np.stack([x, y, z, rng.random(n_points)], axis=1).astype(np.float32)
+
+
+def lab_image(frame: int, rows: int = KITTI_ROWS, cols: int = KITTI_COLS) -> np.ndarray:
+    """Synthetic CV_8UC3 Lab image (what cv::cvtColor(COLOR_BGR2Lab) hands to Slic::generate_superpixels): smooth colour
+    regions with edges and noise, so that superpixels have something to follow."""
+    rng = np.random.default_rng(BASE_SEED + 500009 + frame)
+    yy, xx = np.mgrid[0:rows, 0:cols].astype(np.float64)
+    img = np.empty((rows, cols, 3), np.float64)
+    for c in range(3):
+        f = rng.uniform(0.005, 0.03, 4)
+        ph = rng.uniform(0, 6.28, 4)
+        base = 128 + 60 * np.sin(f[0] * xx + ph[0]) * np.cos(f[1] * yy + ph[1]) + 30 * np.sign(np.sin(f[2] * xx + f[3] * yy + ph[2]))
+        img[:, :, c] = base + rng.normal(0, 4, (rows, cols))
+    return np.clip(np.rint(img), 0, 255).astype(np.uint8)

@@ -212,6 +212,23 @@ DCMT_API int dcmt_lidar_project_f32_host(const float *points, int n_points, cons
                                          int rows, int cols, float *projected_or_null, float *normalized_or_null,
                                          float norm_a, float norm_b, int32_t *n_projected_or_null);
 
+/* (8f #1) SLIC superpixels: replaces Slic::generate_superpixels(cv::Mat& lab_image, int step, int nc)
+ * (src/DC_lidar_camera/slic.cpp:101-182, with init_data :19-59, find_local_minimum :72-99, compute_dist :61-69), the
+ * producer of the label map of interpolate_with_superpixels.  `lab` is the CV_8UC3 image after
+ * cv::cvtColor(COLOR_BGR2Lab) (main_lc.cpp:184, rows x cols x 3 bytes, continuous); `step` the already truncated int
+ * (the reference passes a double into an int parameter, main_lc.cpp:197-201), `nc` the colour weight, `iterations` the
+ * reference's NR_ITERATIONS = 10 (slic.h:20).  `labels` receives Slic::clusters as row-major int32 [row][col] (the
+ * layout dcmt_interpolate_with_superpixels_f32 takes; -1 = never assigned), `centers_or_null` the final
+ * Slic::centers (n_centers x 5 doubles: L, a, b, x, y; NaN for an empty cluster like the reference's 0 / 0).
+ * dcmt_slic_center_count gives slic.centers.size() for a shape.  Labels are bit-identical to a scalar build of the
+ * reference (same double arithmetic, ties to the lowest centre index, stale labels kept).  Needs step >= 4 (below
+ * that the reference itself reads outside the image in find_local_minimum). */
+DCMT_API int dcmt_slic_center_count(int rows, int cols, int step);
+DCMT_API int dcmt_slic_u8c3(const uint8_t *lab, int rows, int cols, int step, int nc, int iterations, int32_t *labels,
+                            double *centers_or_null, void *cuda_stream);
+DCMT_API int dcmt_slic_u8c3_host(const uint8_t *lab, int rows, int cols, int step, int nc, int iterations, int32_t *labels,
+                                 double *centers_or_null);
+
 /* debugging aid: runs the generic pipeline on ONE frame and snapshots intermediate images
  * (device memory, n_stages * rows * cols floats, stage order of oracle/dcmt_oracle.c; stages the
  * kernels never materialise are left untouched).  `stage_mask_out` (host) gets a bit per stage written. */

@@ -174,3 +174,16 @@ def lidar_project(points, T, P, rows, cols, norm=(0.0, 80.0)):
     cnt = fn(pp, pts.shape[0], tp, ppm, rows, cols, proj.ctypes.data_as(C.POINTER(C.c_float)), nrm.ctypes.data_as(C.POINTER(C.c_float)),
              float(norm[0]), float(norm[1]))
     return proj, nrm, int(cnt)
+
+
+def slic(lab, step, nc, iterations=10):
+    """Literal Slic::generate_superpixels (slic.cpp:101-182): returns (labels int32 [row][col], centers (K, 5) float64)."""
+    lab = np.ascontiguousarray(lab, np.uint8)
+    rows, cols = lab.shape[:2]
+    labels = np.empty((rows, cols), np.int32)
+    centers = np.empty((max(1, (rows // max(int(step), 1) + 2) * (cols // max(int(step), 1) + 2)), 5), np.float64)
+    fn = lib().dcmt_oracle_slic
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    k = fn(lab.ctypes.data, rows, cols, int(step), int(nc), int(iterations), labels.ctypes.data, centers.ctypes.data)
+    return labels, centers[:k].copy()

@@ -573,3 +573,76 @@ DCMT_ORACLE_API int dcmt_oracle_lidar_project(const float *pts, int n, const flo
     }
     return count;
 }
+
+/* ---------------------------------------------------------------- SLIC
+ * Literal restatement of Slic::generate_superpixels (src/DC_lidar_camera/slic.cpp:101-182) with init_data (:19-59),
+ * find_local_minimum (:72-99) and compute_dist (:61-69): same loops, same double arithmetic, clusters / distances
+ * indexed [col][row].  lab: rows x cols x 3 bytes.  labels_out is written row-major [row][col]; centers_out K x 5.
+ * Returns K = centers.size(). */
+DCMT_ORACLE_API int dcmt_oracle_slic(const uint8_t *lab, int rows, int cols, int step, int nc, int iterations, int32_t *labels_out,
+                                     double *centers_out) {
+    const int ns = step;
+    int K = 0;
+    for (int i = step; i < cols - step / 2; i += step)
+        for (int j = step; j < rows - step / 2; j += step) ++K;
+    int *clusters = (int *)malloc((size_t)rows * cols * sizeof(int));        /* [col][row] */
+    double *distances = (double *)malloc((size_t)rows * cols * sizeof(double));
+    double *centers = (double *)malloc((size_t)(K ? K : 1) * 5 * sizeof(double));
+    int *counts = (int *)malloc((size_t)(K ? K : 1) * sizeof(int));
+    for (size_t i = 0; i < (size_t)rows * cols; ++i) { clusters[i] = -1; distances[i] = FLT_MAX; }
+#define LAB(y, x, c) lab[((size_t)(y) * cols + (x)) * 3 + (c)]
+    int n = 0;
+    for (int i = step; i < cols - step / 2; i += step)
+        for (int j = step; j < rows - step / 2; j += step) {
+            double min_grad = FLT_MAX;
+            int lx = i, ly = j;
+            for (int a = i - 1; a < i + 2; a++)
+                for (int b = j - 1; b < j + 2; b++) {
+                    const double i1 = LAB(b + 1, a, 0), i2 = LAB(b, a + 1, 0), i3 = LAB(b, a, 0);
+                    if (sqrt(pow(i1 - i3, 2)) + sqrt(pow(i2 - i3, 2)) < min_grad) {
+                        min_grad = fabs(i1 - i3) + fabs(i2 - i3);
+                        lx = a;
+                        ly = b;
+                    }
+                }
+            double *c = centers + (size_t)n * 5;
+            c[0] = LAB(ly, lx, 0); c[1] = LAB(ly, lx, 1); c[2] = LAB(ly, lx, 2); c[3] = lx; c[4] = ly;
+            counts[n++] = 0;
+        }
+    for (int it = 0; it < iterations; it++) {
+        for (size_t i = 0; i < (size_t)rows * cols; ++i) distances[i] = FLT_MAX;
+        for (int j = 0; j < K; j++) {
+            const double *c = centers + (size_t)j * 5;
+            if (c[3] != c[3] || c[4] != c[4]) continue; /* NaN centre: `int k = NaN` is undefined; x86 gives INT_MIN and the loop body never runs */
+            for (int k = c[3] - step; k < c[3] + step; k++)
+                for (int l = c[4] - step; l < c[4] + step; l++)
+                    if (k >= 0 && k < cols && l >= 0 && l < rows) {
+                        const double dc = sqrt(pow(c[0] - LAB(l, k, 0), 2) + pow(c[1] - LAB(l, k, 1), 2) + pow(c[2] - LAB(l, k, 2), 2));
+                        const double ds = sqrt(pow(c[3] - k, 2) + pow(c[4] - l, 2));
+                        const double d = sqrt(pow(dc / nc, 2) + pow(ds / ns, 2));
+                        if (d < distances[(size_t)k * rows + l]) {
+                            distances[(size_t)k * rows + l] = d;
+                            clusters[(size_t)k * rows + l] = j;
+                        }
+                    }
+        }
+        for (int j = 0; j < K; j++) { for (int q = 0; q < 5; q++) centers[(size_t)j * 5 + q] = 0; counts[j] = 0; }
+        for (int j = 0; j < cols; j++)
+            for (int k = 0; k < rows; k++) {
+                const int id = clusters[(size_t)j * rows + k];
+                if (id != -1) {
+                    double *c = centers + (size_t)id * 5;
+                    c[0] += LAB(k, j, 0); c[1] += LAB(k, j, 1); c[2] += LAB(k, j, 2); c[3] += j; c[4] += k;
+                    counts[id] += 1;
+                }
+            }
+        for (int j = 0; j < K; j++)
+            for (int q = 0; q < 5; q++) centers[(size_t)j * 5 + q] /= counts[j];
+    }
+#undef LAB
+    for (int y = 0; y < rows; ++y)
+        for (int x = 0; x < cols; ++x) labels_out[(size_t)y * cols + x] = clusters[(size_t)x * rows + y];
+    if (centers_out) memcpy(centers_out, centers, (size_t)K * 5 * sizeof(double));
+    free(clusters); free(distances); free(centers); free(counts);
+    return K;
+}

@@ -135,6 +135,9 @@ static inline float __fmul_rn(float a, float b) { volatile float r = a * b; retu
 static inline float __fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
 static inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
 static inline double __dsub_rn(double a, double b) { volatile double r = a - b; return r; }
+static inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
+static inline double __ddiv_rn(double a, double b) { volatile double r = a / b; return r; }
+static inline double __dsqrt_rn(double a) { volatile double r = std::sqrt(a); return r; }
 static inline float __double2float_rn(double a) { return (float)a; }
 static inline int __double2int_rz(double a) {
     if (a != a) return 0;
@@ -154,6 +157,7 @@ static inline int atomicMin(int* p, int v) { int o = *p; *p = std::min(o, v); re
 static inline int atomicMax(int* p, int v) { int o = *p; *p = std::max(o, v); return o; }
 static inline unsigned atomicMin(unsigned* p, unsigned v) { unsigned o = *p; *p = std::min(o, v); return o; }
 static inline unsigned atomicMax(unsigned* p, unsigned v) { unsigned o = *p; *p = std::max(o, v); return o; }
+static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; *p += v; return o; }
 static inline unsigned long long atomicMax(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; *p = std::max(o, v); return o; }
 static inline int atomicOr(int* p, int v) { int o = *p; *p |= v; return o; }
 static inline unsigned atomicOr(unsigned* p, unsigned v) { unsigned o = *p; *p |= v; return o; }

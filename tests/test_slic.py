@@ -1,0 +1,52 @@
+"""SLIC superpixels against the literal restatement of Slic::generate_superpixels in the C oracle.
+Bar: labels identical for every pixel, centres bit-equal (including NaN centres of empty clusters); the labels feed
+interpolate_with_superpixels like main_lc.cpp:201-220."""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+from depth_completion_mt_b200 import api, synth
+from oracle import c_oracle as co
+
+
+def body(lib, to_backend, cases):
+    for k, (rows, cols, step, nc) in enumerate(cases):
+        lab = synth.lab_image(k, rows, cols)
+        if k == 1:  # flat image: every distance ties on colour, exercises "lowest centre index wins"
+            lab[:] = 77
+        labels, centers = api.generate_superpixels(to_backend(lab), step, nc, return_centers=True, lib=lib)
+        labels, centers = (a if isinstance(a, np.ndarray) else a.cpu().numpy() for a in (labels, centers))
+        ref_l, ref_c = co.slic(lab, step, nc)
+        assert centers.shape == ref_c.shape == (lib.dcmt_slic_center_count(rows, cols, int(step)), 5)
+        assert np.array_equal(labels, ref_l), f"case {k}: {(labels != ref_l).sum()} of {labels.size} labels differ"
+        assert np.array_equal(centers.view(np.uint64), ref_c.view(np.uint64)) or np.array_equal(np.isnan(centers), np.isnan(ref_c)) and \
+            np.array_equal(centers[~np.isnan(centers)], ref_c[~np.isnan(ref_c)]), f"case {k}: centres differ"
+    # the labels drive the guided completion (main_lc.cpp:201-220)
+    rows, cols = 96, 160
+    lab = synth.lab_image(9, rows, cols)
+    labels = api.generate_superpixels(to_backend(lab), 12.7, 40, lib=lib)
+    ln = labels if isinstance(labels, np.ndarray) else labels.cpu().numpy()
+    kc = lib.dcmt_slic_center_count(rows, cols, 12)
+    sparse = synth.sparse_depth(9, rows, cols, 0.08)
+    out = api.interpolate_with_superpixels(labels, to_backend(sparse), "gaussian", 1, n_clusters=kc, lib=lib)
+    on = out if isinstance(out, np.ndarray) else out.cpu().numpy()
+    ref = co.interpolate_with_superpixels(sparse, co.slic(lab, 12, 40)[0], kc)
+    assert np.array_equal(ln, co.slic(lab, 12, 40)[0])
+    assert np.array_equal(on.view(np.uint32), ref.view(np.uint32))
+    # argument errors
+    with pytest.raises(Exception):
+        api.generate_superpixels(to_backend(lab), 3, 40, lib=lib)
+
+
+def test_emu_slic(emu_lib):
+    body(emu_lib, lambda a: a, [(64, 96, 10, 40), (50, 70, 9, 30), (120, 200, 18, 50)])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["host", "device"])
+def test_gpu_slic(gpu_lib, mode):
+    import torch
+
+    body(gpu_lib, (lambda a: a) if mode == "host" else (lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()),
+         [(64, 96, 10, 40), (50, 70, 9, 30), (352, 1216, 18, 50), (375, 1242, 68, 40)])
