@@ -417,3 +417,31 @@ def generate_superpixels(lab_image, step, nc: int, *, iterations: int = 10, retu
     centers = np.empty((max(k, 1), 5), np.float64)
     lib.check(lib.dcmt_slic_u8c3_host(_np_ptr(lab), rows, cols, step, int(nc), int(iterations), _np_ptr(labels), _np_ptr(centers)))
     return (labels, centers[:k]) if return_centers else labels
+
+
+# ---------------------------------------------------------------------------------------------- raw Mat files (8f #4)
+_CV_DEPTH = {0: np.uint8, 1: np.int8, 2: np.uint16, 3: np.int16, 4: np.int32, 5: np.float32, 6: np.float64}
+
+
+def read_M(filename):
+    """read_M (src/DC_lidar_only/utils.cpp:15-41): the raw cv::Mat dump `int rows, cols, depth, type, channels, nbytes`
+    followed by the payload.  Returns a numpy array (rows, cols[, channels]); feed uint16 / float32 depth planes
+    straight to img_completion."""
+    with open(filename, "rb") as fh:
+        rows, cols, depth, mtype, channels, nbytes = np.frombuffer(fh.read(24), np.int32)
+        data = fh.read(int(nbytes))
+    dt = _CV_DEPTH[int(mtype) & 7]
+    ch = (int(mtype) >> 3) + 1
+    a = np.frombuffer(data, dt).reshape((int(rows), int(cols), ch) if ch > 1 else (int(rows), int(cols)))
+    return a.copy()
+
+
+def write_M(filename, mat):
+    """write_M (utils.cpp:43-58): the inverse of read_M."""
+    a = np.ascontiguousarray(mat)
+    depth = {v: k for k, v in _CV_DEPTH.items()}[a.dtype.type]
+    ch = a.shape[2] if a.ndim == 3 else 1
+    hdr = np.array([a.shape[0], a.shape[1], depth, depth + ((ch - 1) << 3), ch, a.nbytes], np.int32)
+    with open(filename, "wb") as fh:
+        fh.write(hdr.tobytes())
+        fh.write(a.tobytes())

@@ -58,16 +58,31 @@ __global__ void k_slic_bin_count(const double* __restrict__ centers, int n, int 
     atomicAdd(count + bin_of(y, step, by) * bx + bin_of(x, step, bx), 1);
 }
 
-__global__ void k_slic_bin_scan(int* __restrict__ count, int* __restrict__ fill, int nbins) {  // one thread: nbins is a few thousand at most
-    if (blockIdx.x || threadIdx.x) return;
-    int acc = 0;
-    for (int b = 0; b < nbins; ++b) {
+// exclusive scan of the bin counts by one block: thread t owns `chunk` consecutive bins, the per-thread totals are
+// scanned in shared memory (Hillis-Steele), then every thread writes the offsets of its bins
+constexpr int kScanThreads = 1024;
+__global__ void __launch_bounds__(kScanThreads) k_slic_bin_scan(int* __restrict__ count, int* __restrict__ fill, int nbins) {
+    __shared__ int part[kScanThreads];
+    const int chunk = (nbins + kScanThreads - 1) / kScanThreads;
+    const int b0 = threadIdx.x * chunk, b1 = min(b0 + chunk, nbins);
+    int total = 0;
+    for (int b = b0; b < b1; ++b) total += count[b];
+    part[threadIdx.x] = total;
+    __syncthreads();
+    for (int d = 1; d < kScanThreads; d <<= 1) {
+        const int v = threadIdx.x >= d ? part[threadIdx.x - d] : 0;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    int acc = part[threadIdx.x] - total;  // exclusive prefix of this thread's chunk
+    for (int b = b0; b < b1; ++b) {
         const int c = count[b];
         count[b] = acc;
         fill[b] = 0;
         acc += c;
     }
-    count[nbins] = acc;
+    if (threadIdx.x == kScanThreads - 1) count[nbins] = part[kScanThreads - 1];
 }
 
 __global__ void k_slic_bin_fill(const double* __restrict__ centers, int n, int step, int bx, int by, const int* __restrict__ offset,
@@ -172,7 +187,7 @@ cudaError_t slic_run(const uint8_t* lab, int rows, int cols, int step, int nc, i
     for (int it = 0; it < iterations; ++it) {
         DCMT_LAUNCH(k_slic_clear_counts, dim3((nbins + 1 + 255) / 256), dim3(256), 0, st, w.bin_count, nbins + 1);
         DCMT_LAUNCH(k_slic_bin_count, dim3(cb), dim3(128), 0, st, w.centers, n_centers, step, w.bins_x, w.bins_y, w.bin_count, w.sums);
-        DCMT_LAUNCH(k_slic_bin_scan, dim3(1), dim3(32), 0, st, w.bin_count, w.bin_fill, nbins);
+        DCMT_LAUNCH(k_slic_bin_scan, dim3(1), dim3(kScanThreads), 0, st, w.bin_count, w.bin_fill, nbins);
         DCMT_LAUNCH(k_slic_bin_fill, dim3(cb), dim3(128), 0, st, w.centers, n_centers, step, w.bins_x, w.bins_y, w.bin_count, w.bin_fill, w.bin_items);
         DCMT_LAUNCH(k_slic_assign, dim3((cols + 255) / 256, rows), dim3(256), 0, st, lab, rows, cols, step, nc, w.bins_x, w.bins_y, w.centers,
                     w.bin_count, w.bin_items, labels, w.sums);

@@ -94,3 +94,18 @@ def test_python_api_rejects_wrong_types(emu_lib):
     s = np.zeros((6, 6), np.float32)
     s[2, 3] = 5.0
     assert np.array_equal(api.img_completion(s, False, "whatever", lib=emu_lib), api.img_completion(s, False, "none", lib=emu_lib))
+
+
+def test_raw_mat_file_roundtrip(tmp_path):
+    """utils.cpp:15-58: `int rows, cols, depth, type, channels, nbytes` + payload (CV_32FC1 = type 5, CV_16UC1 = 2, CV_8UC3 = 16)."""
+    import numpy as np
+
+    from depth_completion_mt_b200 import api, synth
+
+    for a, want_type in ((synth.sparse_depth(1, 20, 30), 5), (synth.sparse_depth_q8(1, 20, 30), 2), (synth.lab_image(1, 12, 16), 16)):
+        f = str(tmp_path / "m.bin")
+        api.write_M(f, a)
+        hdr = np.fromfile(f, np.int32, 6)
+        assert list(hdr[:2]) == [a.shape[0], a.shape[1]] and hdr[3] == want_type and hdr[5] == a.nbytes
+        b = api.read_M(f)
+        assert b.dtype == a.dtype and np.array_equal(a, b)
