@@ -12,14 +12,14 @@
 //                                    ballot/popc-compacted horizontal pass over hole words only), median5 by
 //                                    shared sorted columns + a 54-comparator selection network, Gaussian in
 //                                    integer q16, final inversion, float32 store
-//   k_q8_fixup   one CTA per frame, runs only for frames the tiles could not finish (a second fill pass needed)
+//                                    holes that survive the first 31x31 fill (the reference's loop then runs more passes) are
+//                                    resolved in the tile by a warp scanning growing squares of the A5 image in global memory
 // Frames that are not strict q8 are detected (k_q8_classify or in-kernel validation) and go through generic.cu.
 // No tensor cores: nothing here is a contraction.
 #include "fused_q8.cuh"
 
 #include <cstdlib>
 
-#include "median_f32.cuh"
 #include "median_net.cuh"
 
 namespace dcmt {
@@ -645,6 +645,7 @@ __global__ void k_q8_decode(const uint16_t* __restrict__ mid, size_t mid_pitch, 
 // later the median image.
 // ------------------------------------------------------------------------------------------------
 constexpr int TV = 19, TQ = 3;   // rows up/down, quads left/right
+constexpr int kRemCap = 256;     // words still holding a hole after the first fill that are resolved from the list (more: all scan words are visited)
 constexpr int kListCap = 3072;   // hole words kept for the lazy horizontal fill; more than that: all words are processed
 
 struct TailArgs {
@@ -726,6 +727,7 @@ __global__ void __launch_bounds__(QTT, 2) k_q8_tail(TailArgs a, const __grid_con
     uint16_t* Ah = reinterpret_cast<uint16_t*>(A);
     uint16_t* Bh = reinterpret_cast<uint16_t*>(B);
     __shared__ int s_count, s_remaining, s_holes_core, s_left_core;
+    __shared__ uint16_t s_rem_list[kRemCap];  // words of the scan region that still hold a hole after the first fill
     __shared__ __align__(8) uint64_t s_bar;  // mbarrier the TMA tile load signals
     const int slot = blockIdx.z;
     if (a.ctr[slot].needs_generic) return;  // not strict q8: the generic pipeline redoes this frame
@@ -845,7 +847,7 @@ __global__ void __launch_bounds__(QTT, 2) k_q8_tail(TailArgs a, const __grid_con
     }
     __syncthreads();
     DCMT_STAMP(a, 4);
-    int holes_core = 0, left_core = 0, left_any = 0;
+    int holes_core = 0, left_core = 0;
     const int n_quads = s_count;
     auto fill_word = [&](int widx) {
         const uint32_t d = A[widx], hm = hole_mask(d);
@@ -858,8 +860,9 @@ __global__ void __launch_bounds__(QTT, 2) k_q8_tail(TailArgs a, const __grid_con
         A[widx] = nd;
         const uint32_t still = hole_mask(nd);
         if (still) {
-            left_any = 1;
             if (core) left_core += __popc(still) >> 4;
+            const int pos = atomicAdd(&s_remaining, 1);
+            if (pos < kRemCap) s_rem_list[pos] = (uint16_t)widx;
         }
     };
     if (n_quads <= kListCap) {
@@ -869,12 +872,66 @@ __global__ void __launch_bounds__(QTT, 2) k_q8_tail(TailArgs a, const __grid_con
     }
     if (holes_core) atomicAdd(&s_holes_core, holes_core);
     if (left_core) atomicAdd(&s_left_core, left_core);
-    if (left_any) s_remaining = 1;
     __syncthreads();
     if (threadIdx.x == 0) {
         if (s_holes_core) atomicAdd(&a.ctr[slot].holes_after_extrapolation, s_holes_core);
         if (s_left_core) atomicAdd(&a.ctr[slot].holes_after_first_fill, s_left_core);
-        if (s_remaining) a.ctr[slot].holes_remaining = 1;  // a second pass is needed: k_q8_fixup redoes the frame
+    }
+    // ---- A7 (:146-166): the reference repeats the 31x31 fill until no hole is left.  A hole that survives the first
+    //      fill has no valid pixel within 15; pass k of the loop gives it the maximum over the (30 k + 1)-square around
+    //      it of the image BEFORE the loop (a fill of fills is a fill with the summed radius, and a pixel is filled by
+    //      the first pass whose square reaches a valid pixel).  Such holes are rare, so each is resolved directly: one
+    //      warp scans growing squares of the A5 image in global memory (intermediate plane + column keys) until it
+    //      meets a valid pixel.  Every tile resolves the holes of its own scan region from the same global data, so
+    //      neighbouring tiles agree without talking to each other.
+    const int n_rem = s_remaining;
+    if (n_rem > 0) {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = QTT / 32;
+        int max_pass = 0;
+        auto resolve_word = [&](int widx) {
+            const uint32_t d = A[widx];
+            if (hole_mask(d) == 0u) return;
+            const int r = fast_div(widx, a.i_vert.magic), w = widx - r * pitchw;
+            uint32_t nd = d;
+#pragma unroll 1
+            for (int half_lane = 0; half_lane < 2; ++half_lane) {
+                if (((d >> (16 * half_lane)) & 0xffffu) != 1u) continue;
+                const int gy = gy0 + r, gx = gx0 + 2 * w + half_lane;
+                uint32_t m = 0u;
+                int k = 1;
+                while (m < E_VALID_MIN) {
+                    ++k;
+                    const int half = 15 * k;
+                    const int r_lo = max(gy - half, 0), r_hi = min(gy + half, rows - 1);
+                    const int c_lo = max(gx - half, 0), c_hi = min(gx + half, cols - 1);
+                    for (int c = c_lo + lane; c <= c_hi; c += 32) {
+                        const uint32_t kf = __ldg(a.col_first + (size_t)slot * a.mid_pitch + c), kl = __ldg(a.col_last + (size_t)slot * a.mid_pitch + c);
+                        if (kf == 0xffffffffu) { m = max(m, E_HUNDRED); continue; }  // empty column: 100 everywhere (:110)
+                        const int first = (int)(kf >> 16), last = (int)(kl >> 16);
+                        if (r_lo <= first) m = max(m, kf & 0xffffu);   // rows <= first hold value(first)
+                        if (r_hi >= last) m = max(m, kl & 0xffffu);    // rows >= last hold value(last)
+                        const uint16_t* col = mid + c;
+                        for (int rr = max(r_lo, first + 1); rr <= min(r_hi, last - 1); ++rr) m = max(m, (uint32_t)col[(size_t)rr * a.mid_pitch]);
+                    }
+#pragma unroll
+                    for (int sft = 16; sft >= 1; sft >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, sft));
+                    if (r_lo == 0 && c_lo == 0 && r_hi == rows - 1 && c_hi == cols - 1) break;  // whole image scanned
+                }
+                max_pass = max(max_pass, k);
+                nd = half_lane ? ((nd & 0x0000ffffu) | (m << 16)) : ((nd & 0xffff0000u) | m);
+            }
+            if (lane == 0) A[widx] = nd;
+        };
+        if (n_rem <= kRemCap) {
+            for (int e = warp; e < n_rem; e += nwarps) resolve_word(s_rem_list[e]);
+        } else {
+            for (int e = warp; e < SH * SQ * 4; e += nwarps) {
+                const int sr = e / (SQ * 4);
+                resolve_word((sr0 + sr) * pitchw + sq0 * 4 + (e - sr * SQ * 4));
+            }
+        }
+        if (lane == 0 && max_pass > 1) atomicMax(&a.ctr[slot].extra_passes, max_pass - 1);
+        __syncthreads();
     }
     DCMT_STAMP(a, 5);
     // ---- BORDER_REPLICATE for the median (:170): copy the nearest image pixel into the cells outside the image
@@ -1033,110 +1090,6 @@ __global__ void __launch_bounds__(QTT, 2) k_q8_tail(TailArgs a, const __grid_con
     DCMT_STAMP(a, 9);
 }
 
-// ------------------------------------------------------------------------------------------------
-// k_q8_fixup: one CTA per slot; returns at once unless the tiles found holes left after the first 31x31 fill
-// (the reference's while loop then runs more than one effective pass, :146-166).  Redoes A5..A10 for the whole
-// frame in float, in global memory (L2 resident).  Rare and slow by design.
-// ------------------------------------------------------------------------------------------------
-struct FixupArgs {
-    const uint16_t* mid;
-    size_t mid_pitch, mid_fstride;
-    const uint32_t* col_first;
-    const uint32_t* col_last;
-    FrameCounters* ctr;
-    float* w1;
-    float* w2;
-    float* out;
-    size_t out_pitch, out_fstride;
-    int rows, cols, blur, max_passes;
-};
-
-__global__ void __launch_bounds__(1024) k_q8_fixup(FixupArgs a) {
-    const int slot = blockIdx.x;
-    if (a.ctr[slot].needs_generic || !a.ctr[slot].holes_remaining) return;
-    const int rows = a.rows, cols = a.cols;
-    const size_t fpix = (size_t)rows * cols;
-    const uint16_t* mid = a.mid + (size_t)slot * a.mid_fstride;
-    float* D = a.w1 + (size_t)slot * fpix;
-    float* T = a.w2 + (size_t)slot * fpix;
-    float* out = a.out + (size_t)slot * a.out_fstride;
-    // decode + A5
-    for (size_t i = threadIdx.x; i < fpix; i += blockDim.x) {
-        const int y = (int)(i / cols), x = (int)(i - (size_t)y * cols);
-        const uint32_t kf = a.col_first[(size_t)slot * a.mid_pitch + x], kl = a.col_last[(size_t)slot * a.mid_pitch + x];
-        const bool empty = kf == 0xffffffffu;
-        const int first = empty ? rows - 1 : (int)(kf >> 16), last = empty ? 0 : (int)(kl >> 16);
-        uint32_t e = mid[(size_t)y * a.mid_pitch + x];
-        if (y <= first) e = empty ? E_HUNDRED : (kf & 0xffffu);
-        else if (y >= last) e = empty ? E_HUNDRED : (kl & 0xffffu);
-        D[i] = (float)(e - 1u) * (1.0f / 256.0f);
-    }
-    __syncthreads();
-    int passes = 0, any = 1;
-    while (any && passes < a.max_passes) {  // A6 + A7
-        for (size_t i = threadIdx.x; i < fpix; i += blockDim.x) {
-            const int y = (int)(i / cols), x = (int)(i - (size_t)y * cols);
-            const int lo = max(x - 15, 0), hi = min(x + 15, cols - 1);
-            const float* row = D + (size_t)y * cols;
-            float m = row[lo];
-            for (int k = lo + 1; k <= hi; ++k) m = fmaxf(m, row[k]);
-            T[i] = m;
-        }
-        __syncthreads();
-        int remaining = 0;
-        for (size_t i = threadIdx.x; i < fpix; i += blockDim.x) {
-            if (!is_hole(D[i])) continue;
-            const int y = (int)(i / cols), x = (int)(i - (size_t)y * cols);
-            const int lo = max(y - 15, 0), hi = min(y + 15, rows - 1);
-            float m = T[(size_t)lo * cols + x];
-            for (int k = lo + 1; k <= hi; ++k) m = fmaxf(m, T[(size_t)k * cols + x]);
-            D[i] = m;
-            if (is_hole(m)) ++remaining;
-        }
-        ++passes;
-        any = __syncthreads_count(remaining > 0);
-    }
-    // A8 median (BORDER_REPLICATE) -> T
-    for (size_t i = threadIdx.x; i < fpix; i += blockDim.x) {
-        const int y = (int)(i / cols), x = (int)(i - (size_t)y * cols);
-        float w[25];
-#pragma unroll
-        for (int dy = 0; dy < 5; ++dy)
-#pragma unroll
-            for (int dx = 0; dx < 5; ++dx)
-                w[dy * 5 + dx] = D[(size_t)clampi(y + dy - 2, 0, rows - 1) * cols + clampi(x + dx - 2, 0, cols - 1)];
-        T[i] = median25(w, 5);
-    }
-    __syncthreads();
-    if (a.blur == 1) {  // A9 Gaussian rows -> D, then columns + mask + A10
-        const float k0 = 0.375f, k1 = 0.25f, k2 = 0.0625f;
-        for (size_t i = threadIdx.x; i < fpix; i += blockDim.x) {
-            const int y = (int)(i / cols), x = (int)(i - (size_t)y * cols);
-            const float* row = T + (size_t)y * cols;
-            D[i] = __fadd_rn(__fadd_rn(__fmul_rn(row[x], k0), __fmul_rn(__fadd_rn(row[reflect101(x - 1, cols)], row[reflect101(x + 1, cols)]), k1)),
-                             __fmul_rn(__fadd_rn(row[reflect101(x - 2, cols)], row[reflect101(x + 2, cols)]), k2));
-        }
-        __syncthreads();
-        for (size_t i = threadIdx.x; i < fpix; i += blockDim.x) {
-            const int y = (int)(i / cols), x = (int)(i - (size_t)y * cols);
-            float d = T[i];
-            if (is_valid(d)) {
-                const float c0 = D[i];
-                const float m1 = D[(size_t)reflect101(y - 1, rows) * cols + x], p1 = D[(size_t)reflect101(y + 1, rows) * cols + x];
-                const float m2 = D[(size_t)reflect101(y - 2, rows) * cols + x], p2 = D[(size_t)reflect101(y + 2, rows) * cols + x];
-                d = __fadd_rn(__fadd_rn(__fmul_rn(c0, k0), __fmul_rn(__fadd_rn(m1, p1), k1)), __fmul_rn(__fadd_rn(m2, p2), k2));
-            }
-            out[(size_t)y * a.out_pitch + x] = invert_valid(d);
-        }
-    } else {
-        for (size_t i = threadIdx.x; i < fpix; i += blockDim.x) {
-            const int y = (int)(i / cols), x = (int)(i - (size_t)y * cols);
-            out[(size_t)y * a.out_pitch + x] = invert_valid(T[i]);
-        }
-    }
-    if (threadIdx.x == 0) a.ctr[slot].extra_passes = passes - 1;
-}
-
 // main.cpp:79 `convertTo(CV_32F, 1.0 / 256.0)` for frames the fused kernels do not serve (generic pipeline input)
 __global__ void k_u16_to_f32(const uint16_t* __restrict__ in, size_t in_pitch, size_t in_fstride, float* __restrict__ out, int rows, int cols) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, f = blockIdx.z;
@@ -1245,9 +1198,6 @@ cudaError_t q8_run_tail(const Q8Plan& p, float* out, size_t out_pitch, size_t ou
                make_items(NP, QTT), p.prof_tail};
     const dim3 grid((p.cols + p.tw - 1) / p.tw, (p.rows + p.th - 1) / p.th, n_frames);
     DCMT_LAUNCH(k_q8_tail, grid, dim3(QTT), q8_tail_smem(p.th, p.tw), st, a, tmap);
-    FixupArgs f{p.mid, (size_t)p.mid_pitch, (size_t)p.mid_pitch * p.rows, p.col_first, p.col_last, p.ctr, p.w1, p.w2, out,
-                out_pitch, out_fstride, p.rows, p.cols, blur, (p.rows > p.cols ? p.rows : p.cols) / 15 + 2};
-    DCMT_LAUNCH(k_q8_fixup, dim3(n_frames), dim3(1024), 0, st, f);
     return cudaGetLastError();
 }
 

@@ -89,8 +89,16 @@ def body_routing(be):
     assert np.abs(out[1] - co.img_completion(b[1], "gaussian")).max() <= 1e-4
 
 
-def body_multipass(be):
-    check(be, multipass_frame(), "multipass 120x64 (fix-up kernel)")
+def body_multipass(be, big=False):
+    # very sparse frames: many holes survive the first 31x31 fill and are resolved by the growing-square search
+    # (list path and, past 256 words per tile, the visit-everything path); up to 4-5 loop passes
+    for seed, (rows, cols, p) in enumerate(((160, 260, 0.004), (97, 171, 0.001), (64, 400, 0.002))):
+        check(be, synth.sparse_depth(70 + seed, rows, cols, p), f"very sparse {rows}x{cols} p={p}")
+        check(be, synth.sparse_depth(70 + seed, rows, cols, p, kitti_like=True), f"very sparse kitti-like {rows}x{cols}", blur="none")
+    if big:
+        check(be, synth.sparse_depth(80, 352, 1216, 0.01), "352x1216 at 1 %")
+        check(be, synth.sparse_depth(81, 352, 1216, 0.003, kitti_like=True), "352x1216 at 0.3 %")
+    check(be, multipass_frame(), "multipass 120x64")
     check(be, multipass_frame(150, 200), "multipass 150x200", blur="none")
     b = np.stack([synth.sparse_depth(9, 120, 64, 0.05), multipass_frame(), synth.sparse_depth(10, 120, 64, 0.05)])
     out, st = be.img_completion(b, "gaussian", return_stats=True)
@@ -240,7 +248,7 @@ def test_gpu_boundary_routing_multipass(gpu_lib):
     be = Backend(gpu_lib, "gpu_device")
     body_boundary_values(be)
     body_routing(be)
-    body_multipass(be)
+    body_multipass(be, big=True)
     body_routing(Backend(gpu_lib, "gpu_host"))
 
 
