@@ -141,7 +141,7 @@ def run_reference(args, quiet=False):
         "gpu_launches": 0,
     }
     if not quiet:
-        print(json.dumps(line), flush=True)
+        emit(line)
     return line
 
 
@@ -239,7 +239,6 @@ def run_ours(args):
 
     from depth_completion_mt_b200 import _lib, api, sharding, synth
 
-    os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: rank 0 prints one JSON line
     rank, local_rank, world = sharding.init_process_group()
     assert torch.cuda.is_available(), "bench.py --impl ours needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
@@ -454,12 +453,31 @@ def run_ours(args):
             line["cpu_baseline"] = ref["cpu_baseline"]
         except Exception as exc:  # never lose the GPU numbers because the CPU leg failed
             line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": None, "kind": "port", "sample": f"failed: {exc!r}"}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         torch.distributed.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The one JSON line of the contract, on the process's real stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
+    # libraries print to fd 1 behind Python's back (NCCL's version banner under torchrun): route fd 1 to stderr for the
+    # whole run and keep the real stdout for the JSON line alone
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     args = parse_args()
     if args.impl == "reference":
         if int(os.environ.get("RANK", "0")) != 0:

@@ -108,6 +108,10 @@ def load() -> Library:
     """The product library.  Raises if libdcmt.so is absent -- there is no CPU fallback."""
     global _default
     if _default is None:
+        alt = os.environ.get("DCMT_LIB")  # A/B builds of the same sources (tools/build_variant.py); still a CUDA library
+        if alt:
+            _default = Library(alt)
+            return _default
         if not os.path.exists(LIB_PATH):
             raise ImportError(
                 f"{LIB_PATH} not found: build it with `python -m depth_completion_mt_b200.build` "

@@ -25,8 +25,14 @@
 namespace dcmt {
 namespace {
 
-constexpr int QT = 512;    // threads per CTA of k_q8_front (2 CTAs per SM)
-constexpr int QTT = 512;   // threads per CTA of k_q8_tail (2 CTAs per SM: their phases overlap)
+#ifndef DCMT_QT
+#define DCMT_QT 512
+#endif
+#ifndef DCMT_QTT
+#define DCMT_QTT 512
+#endif
+constexpr int QT = DCMT_QT;     // threads per CTA of k_q8_front (2 CTAs per SM)
+constexpr int QTT = DCMT_QTT;   // threads per CTA of k_q8_tail (2 CTAs per SM: their phases overlap)
 
 #define SPLAT16(x) ((uint32_t)(x) | ((uint32_t)(x) << 16))
 constexpr uint32_t E_VALID_MIN = 27;   // e >= 27  <=>  depth >= 0.1f  (26/256 = 0.1015625 is the smallest q8 value >= 0.1f)
@@ -1151,10 +1157,24 @@ size_t q8_tail_smem(int th, int tw) {
 }
 
 void q8_choose_tile(int rows, int cols, int* th, int* tw) {
-    // tiles of about 96 x 160 that divide the frame evenly (KITTI 352 x 1216 -> 88 x 152, 4 x 8 tiles)
-    const int ny = (rows + 95) / 96, nx = (cols + 159) / 160;
-    *th = (rows + ny - 1) / ny;
-    *tw = (((cols + nx - 1) / nx) + 7) / 8 * 8;
+    // Tiles of at most 96 x 160 that divide the frame evenly (KITTI 352 x 1216 -> 88 x 152, 4 x 8 tiles).  Among the
+    // splits near that size, take the one with the least halo work whose shared memory lets TWO CTAs of each kernel
+    // share an SM (228 KB per SM, 1 KB reserved per CTA): the phases of the two overlap.
+    const int ny0 = (rows + 95) / 96, nx0 = (cols + 159) / 160;
+    long best_cost = -1;
+    for (int ny = ny0; ny <= ny0 + 3; ++ny)
+        for (int nx = nx0; nx <= nx0 + 3; ++nx) {
+            const int h = (rows + ny - 1) / ny, w = (((cols + nx - 1) / nx) + 7) / 8 * 8;
+            if (h < 1 || w < 8) continue;
+            const bool two = 2 * (q8_tail_smem(h, w) + 2048) <= 233472 && 2 * (q8_front_smem(h, w) + 2048) <= 233472;
+            if (!two) continue;
+            const long cost = (long)(h + 2 * TV) * (w + 16 * TQ) * ny * nx;
+            if (best_cost < 0 || cost < best_cost) { best_cost = cost; *th = h; *tw = w; }
+        }
+    if (best_cost < 0) {  // cannot happen for the bounds above; keep the plain split
+        *th = (rows + ny0 - 1) / ny0;
+        *tw = (((cols + nx0 - 1) / nx0) + 7) / 8 * 8;
+    }
 }
 
 cudaError_t q8_configure() {
