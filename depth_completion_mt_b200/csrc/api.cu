@@ -418,7 +418,14 @@ int host_streams(HostStreams** out) {
 }
 
 int host_chunk_frames(int rows, int cols, int n_frames) {
-    long c = (long)((16u << 20) / ((size_t)rows * cols) + 1);  // ~64 MB of float pixels per chunk
+    // pixels per chunk of the host pipeline (DCMT_HOST_CHUNK_MPX to override): small enough that filling and draining
+    // the three-stage pipeline costs little, large enough for full-rate DMA and a few waves of CTAs
+    static const long env = [] {
+        const char* s = getenv("DCMT_HOST_CHUNK_MPX");
+        return s ? atol(s) : 0L;
+    }();
+    const size_t px = env > 0 ? (size_t)env << 20 : (size_t)16 << 20;
+    long c = (long)(px / ((size_t)rows * cols) + 1);
     if (c > n_frames) c = n_frames;
     if (c > 65535) c = 65535;
     return (int)(c < 1 ? 1 : c);
