@@ -216,6 +216,33 @@ class ClockSampler:
                 "samples": len(used), "samples_in_timed_regions": len(inwin)}
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this rank (and the pinned host buffers it allocates afterwards, first touch) to the CPUs of the NUMA node its
+    GPU hangs off: the e2e leg is bound by host memory and PCIe, and cross-socket traffic halves it on multi-GPU boxes.
+    Returns a short description for the JSON line; never fails the run."""
+    try:
+        import torch
+
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
+        dev = torch.cuda.get_device_properties(local_rank).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return "numa node unknown"
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if not allowed:
+            return f"numa node {node}: no allowed cpus"
+        os.sched_setaffinity(0, allowed)
+        return f"numa node {node}, {len(allowed)} cpus"
+    except Exception as exc:  # noqa: BLE001
+        return f"not bound ({type(exc).__name__})"
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
@@ -243,6 +270,7 @@ def run_ours(args):
     assert torch.cuda.is_available(), "bench.py --impl ours needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else "single rank: not bound"
     lib = _lib.load()
     rows, cols, n = args.rows, args.cols, args.frames
     reps = (n + UNIQUE - 1) // UNIQUE
@@ -439,7 +467,8 @@ def run_ours(args):
     if not args.no_e2e:
         line["e2e"] = {"value": res_e2e["total_frames"] / (res_e2e["max_ms"] / 1e3), "unit": "frames/s",
                        "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                       "api": "dcmt_*_host via depth_completion_mt_b200.api with numpy views of pinned host buffers"}
+                       "api": "dcmt_*_host via depth_completion_mt_b200.api with numpy views of pinned host buffers",
+                       "host_binding_rank0": numa}
         if res_e2e16 is not None:
             line["e2e_u16_input"] = {"value": res_e2e16["total_frames"] / (res_e2e16["max_ms"] / 1e3), "unit": "frames/s",
                                      "h2d_bytes_per_step": int(n * fpix * 2), "d2h_bytes_per_step": int(d2h),
