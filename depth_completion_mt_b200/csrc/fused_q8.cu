@@ -947,7 +947,8 @@ __global__ void __launch_bounds__(QTT, 2) k_q8_tail(TailArgs a, const __grid_con
         const int r_in0 = max(sr0, -gy0), r_in1 = min(sr0 + SH, rows - gy0);          // in-image scan rows [r_in0, r_in1)
         const int c_in0 = max(c_lo, -gx0), c_in1 = min(c_lo + c_n, cols - gx0);        // in-image scan columns
         const int n_rows_out = SH - max(0, r_in1 - r_in0), n_cols_out = c_n - max(0, c_in1 - c_in0);
-        // (1) columns outside, rows inside   (2) rows outside, all columns (after (1): sources are final)
+        // (1) columns outside, rows inside   (2) rows outside, all columns.  Both read in-image cells only (row and
+        //     column clamped at once), so the two loops need no barrier between them.
         for (int it = threadIdx.x; it < max(0, r_in1 - r_in0) * n_cols_out; it += QTT) {
             const int rr = it / n_cols_out, k = it - rr * n_cols_out;
             const int r = r_in0 + rr;
@@ -955,12 +956,11 @@ __global__ void __launch_bounds__(QTT, 2) k_q8_tail(TailArgs a, const __grid_con
             const int cc = clampi(c, c_in0, c_in1 - 1);
             Ah[(size_t)r * pitchw * 2 + c] = Ah[(size_t)r * pitchw * 2 + cc];
         }
-        __syncthreads();
         for (int it = threadIdx.x; it < n_rows_out * c_n; it += QTT) {
             const int k = it / c_n, c = c_lo + (it - k * c_n);
             const int r = k < r_in0 - sr0 ? sr0 + k : r_in1 + (k - (r_in0 - sr0));
             const int cr = clampi(r, r_in0, r_in1 - 1);
-            if (cr >= 0 && cr < RH) Ah[(size_t)r * pitchw * 2 + c] = Ah[(size_t)cr * pitchw * 2 + c];
+            if (cr >= 0 && cr < RH) Ah[(size_t)r * pitchw * 2 + c] = Ah[(size_t)cr * pitchw * 2 + clampi(c, c_in0, c_in1 - 1)];
         }
         __syncthreads();
     }
@@ -1017,7 +1017,8 @@ __global__ void __launch_bounds__(QTT, 2) k_q8_tail(TailArgs a, const __grid_con
     DCMT_STAMP(a, 7);
     float* out = a.out + (size_t)slot * a.out_fstride;
     // ---- BORDER_REFLECT_101 for the Gaussian (:179): mirror the median image into the 2 cells beyond each edge.
-    //      Columns first (rows inside), then whole rows (their sources then include the mirrored columns).
+    //      Columns beyond the edge (rows inside) and whole rows beyond the edge; both read in-image cells only (row and
+    //      column mirrored at once), so no barrier is needed between the two loops.
     if (border && a.blur == 1) {
         const int c_lo = TQ * 8 - 2, c_n = tw + 4, r_lo = TV - 2, r_n = th + 4;
         const int r_in0 = max(r_lo, -gy0), r_in1 = min(r_lo + r_n, rows - gy0);
@@ -1029,12 +1030,14 @@ __global__ void __launch_bounds__(QTT, 2) k_q8_tail(TailArgs a, const __grid_con
             const int c = gx - gx0, cc = reflect101(gx, cols) - gx0;
             if (c >= c_lo && c < c_lo + c_n && cc >= c_in0 && cc < c_in1) Bh[(size_t)r * pitchw * 2 + c] = Bh[(size_t)r * pitchw * 2 + cc];
         }
-        __syncthreads();
         for (int it = threadIdx.x; it < 4 * c_n; it += QTT) {
             const int k = it / c_n, c = c_lo + (it - k * c_n);
             const int gy = k < 2 ? k - 2 : rows + (k - 2);
             const int r = gy - gy0, cr = reflect101(gy, rows) - gy0;
-            if (r >= r_lo && r < r_lo + r_n && cr >= r_in0 && cr < r_in1) Bh[(size_t)r * pitchw * 2 + c] = Bh[(size_t)cr * pitchw * 2 + c];
+            const int gxc = gx0 + c;
+            const int cs = (gxc < 0 || gxc >= cols) ? reflect101(gxc, cols) - gx0 : c;  // source column inside the image
+            if (r >= r_lo && r < r_lo + r_n && cr >= r_in0 && cr < r_in1 && cs >= c_in0 && cs < c_in1)
+                Bh[(size_t)r * pitchw * 2 + c] = Bh[(size_t)cr * pitchw * 2 + cs];
         }
         __syncthreads();
     }
