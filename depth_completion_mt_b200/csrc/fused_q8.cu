@@ -38,7 +38,6 @@ constexpr int QTT = DCMT_QTT;   // threads per CTA of k_q8_tail (2 CTAs per SM: 
 constexpr uint32_t E_VALID_MIN = 27;   // e >= 27  <=>  depth >= 0.1f  (26/256 = 0.1015625 is the smallest q8 value >= 0.1f)
 constexpr uint32_t E_HUNDRED = 25601;  // encoding of 100.0 (empty-column fill, img_completion.cpp:110)
 constexpr uint32_t kAbsMax = 0u;           // identity of max in the encoding (two lanes)
-constexpr uint32_t kAbsMin = 0xffffffffu;  // identity of min
 
 __device__ __forceinline__ uint32_t pmax(uint32_t a, uint32_t b) { return __vmaxu2(a, b); }
 __device__ __forceinline__ uint32_t pmin(uint32_t a, uint32_t b) { return __vminu2(a, b); }
@@ -61,18 +60,6 @@ __device__ __forceinline__ void sts4(uint32_t* p, uint4 v) { *reinterpret_cast<u
 __device__ __forceinline__ uint2 lds2(const uint32_t* p) { return *reinterpret_cast<const uint2*>(p); }
 __device__ __forceinline__ void sts2(uint32_t* p, uint2 v) { *reinterpret_cast<uint2*>(p) = v; }
 __device__ __forceinline__ uint4 splat4(uint32_t v) { return make_uint4(v, v, v, v); }
-
-// Blend the lanes of a quad (8 pixels starting at image column gx) that lie outside [0, cols) with `ident`.
-__device__ __forceinline__ uint4 mask_columns(uint4 v, int gx, int cols, uint32_t ident) {
-    uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int x0 = gx + 2 * j, x1 = x0 + 1;
-        const uint32_t m = ((x0 >= 0 && x0 < cols) ? 0x0000ffffu : 0u) | ((x1 >= 0 && x1 < cols) ? 0xffff0000u : 0u);
-        w[j] = (w[j] & m) | (ident & ~m);
-    }
-    return make_uint4(w[0], w[1], w[2], w[3]);
-}
 
 // Iterates item = threadIdx.x, threadIdx.x + nt, ... over an (nr x nq) grid as (r, q) without a division: the
 // descriptor (row length, per-step increments, magic reciprocal) is computed on the host for every row length a
@@ -208,7 +195,6 @@ __device__ __forceinline__ uint4 blend(uint4 v, uint4 m, uint32_t ident) {
     return make_uint4((v.x & m.x) | (ident & ~m.x), (v.y & m.y) | (ident & ~m.y), (v.z & m.z) | (ident & ~m.z), (v.w & m.w) | (ident & ~m.w));
 }
 __device__ __forceinline__ uint4 and4(uint4 v, uint4 m) { return make_uint4(v.x & m.x, v.y & m.y, v.z & m.z, v.w & m.w); }
-__device__ __forceinline__ uint4 not4(uint4 v) { return make_uint4(~v.x, ~v.y, ~v.z, ~v.w); }
 
 // what a thread needs to walk its quad column: first row, word offset of (r0, q), strides, activity, lane mask
 struct ColThread {
@@ -970,7 +956,7 @@ __global__ void __launch_bounds__(QTT, 2) k_q8_tail(TailArgs a, const __grid_con
     //      PRMTs of the sorted columns, and each output is the 54-comparator selection network of median_net.cuh on
     //      its five sorted columns.
     {
-        const int MH = th + 4, MI = (tw / 2 + 2 + 3) / 4;  // rows core +- 2; items of four words covering core +- 1 word
+        const int MH = th + 4;  // rows core +- 2; items of four words cover core +- 1 word (a.i_med)
         const int mr0 = TV - 2, mw0 = TQ * 4 - 1;
         const PackedOps ops{(uint32_t)a.one};
         for (Items i(a.i_med); i.r < MH; i.next()) {
@@ -1049,7 +1035,7 @@ __global__ void __launch_bounds__(QTT, 2) k_q8_tail(TailArgs a, const __grid_con
     //      k_q8_fixup), so the masked copy (:181-188) always takes the blurred value and the inversion always
     //      applies:  out16 = 6553600 - (g - 256)  with e = q + 1 and weights summing to 256.
     {
-        const int NP = tw / 4, NGR = (th + 3) / 4;
+        const int NGR = (th + 3) / 4;  // items: tw / 4 per row of items (a.i_gauss)
         for (Items i(a.i_gauss); i.r < NGR; i.next()) {
             const int cy0 = i.r * 4, gx = x0 + i.q * 4;
             if (y0 + cy0 >= rows || gx >= cols) continue;
