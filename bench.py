@@ -52,6 +52,8 @@ def parse_args():
     ap.add_argument("--path", default="auto", choices=["auto", "generic", "fused"])
     ap.add_argument("--input", default="f32", choices=["f32", "u16"],
                     help="lidar_only: float32 metres (the reference's cv::Mat, default) or KITTI uint16 = metres * 256 (main.cpp:75-82)")
+    ap.add_argument("--labels", default="grid", choices=["grid", "slic"],
+                    help="guided workload: jittered grid labels (SURVEY 8d) or real SLIC output of synthetic Lab images (step 18, nc 50)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-frames-per-core", type=int, default=4, help="reference arm: frames per host core per step")
@@ -155,7 +157,7 @@ def workload_config(args, frames_per_step_per_gpu):
              "stereo": "DC_stereo_lidar disparity refinement (BASELINE configs[3])"}
     return {"workload": names[args.workload], "rows": args.rows, "cols": args.cols, "valid_density": args.density,
             "frames_per_gpu_per_step": frames_per_step_per_gpu, "global_batch": frames_per_step_per_gpu * max(1, args.gpus),
-            "unique_frames": UNIQUE, "blur": "gaussian", "input": getattr(args, "input", "f32") if args.workload == "lidar_only" else "f32", "parallelism": f"frame-sharded dp{max(1, args.gpus)}, no collective on the hot path",
+            "unique_frames": UNIQUE, "blur": "gaussian", "labels": getattr(args, "labels", "grid") if args.workload == "guided" else None, "input": getattr(args, "input", "f32") if args.workload == "lidar_only" else "f32", "parallelism": f"frame-sharded dp{max(1, args.gpus)}, no collective on the hot path",
             "l2_policy": "inputs larger than L2 (batch >> 126 MB), no flush needed"}
 
 
@@ -288,8 +290,13 @@ def run_ours(args):
         h2d, d2h = n * fpix * (2 if args.input == "u16" else 4), n * fpix * 4
     elif args.workload == "guided":
         uniq = np.stack([synth.sparse_depth(f, rows, cols, args.density) for f in range(UNIQUE)])
-        labs = [synth.superpixel_labels(f, rows, cols) for f in range(UNIQUE)]
-        k = labs[0][1]
+        if args.labels == "slic":
+            k = lib.dcmt_slic_center_count(rows, cols, 18)
+            labs = [(api.generate_superpixels(torch.from_numpy(synth.lab_image(f, rows, cols)).to(dev), 18, 50, lib=lib).cpu().numpy(), k)
+                    for f in range(UNIQUE)]
+        else:
+            labs = [synth.superpixel_labels(f, rows, cols) for f in range(UNIQUE)]
+            k = labs[0][1]
         d_in = torch.from_numpy(uniq).to(dev).repeat(reps, 1, 1)[:n].contiguous()
         d_lab = torch.from_numpy(np.stack([l[0] for l in labs])).to(dev).repeat(reps, 1, 1)[:n].contiguous()
         holder = {}
@@ -362,18 +369,21 @@ def run_ours(args):
             h_in.copy_(d_in)
             h_lab = torch.empty((n, rows, cols), dtype=torch.int32, pin_memory=True)
             h_lab.copy_(d_lab)
-            np_in, np_lab = h_in.numpy(), h_lab.numpy()
+            h_out = torch.empty((n, rows, cols), dtype=torch.float32, pin_memory=True)
+            np_in, np_lab, np_out = h_in.numpy(), h_lab.numpy(), h_out.numpy()
 
             def host_step():
-                holder["h"] = api.interpolate_with_superpixels(np_lab, np_in, "gaussian", 1, n_clusters=k, lib=lib)
+                holder["h"] = api.interpolate_with_superpixels(np_lab, np_in, "gaussian", 1, n_clusters=k, out=np_out, lib=lib)
         else:
             hs = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in (d_ig, d_l, d_r)]
             for a, b in zip(hs, (d_ig, d_l, d_r)):
                 a.copy_(b)
             nps = [a.numpy() for a in hs]
+            h_out = torch.empty((n, rows, cols), dtype=torch.float32, pin_memory=True)
+            np_out = h_out.numpy()
 
             def host_step():
-                holder["h"] = api.stereo_refine(nps[0], nps[1], nps[2], prm, lib=lib)
+                holder["h"] = api.stereo_refine(nps[0], nps[1], nps[2], prm, out=np_out, lib=lib)
         for _ in range(2):
             host_step()
         torch.cuda.synchronize()

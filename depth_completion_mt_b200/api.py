@@ -125,7 +125,8 @@ def img_completion(sparse, extr: bool = False, blur_type="gaussian", *, path: st
 
 
 def interpolate_with_superpixels(labels, sparse, blur_type="gaussian", use_superpixel: int = 1, *, n_clusters=None,
-                                 return_stats: bool = False, stream=None, lib: _lib.Library | None = None):
+                                 path: str = "auto", return_stats: bool = False, out=None, stream=None,
+                                 lib: _lib.Library | None = None):
     """interpolate_with_superpixels(slic, sparse, dense, blur_type, use_superpixel) -- img_completion_lc.cpp:34-203.
 
     ``labels`` stands for ``slic.clusters`` as an int32 [row][col] map (the reference indexes [col][row], :83);
@@ -146,11 +147,16 @@ def interpolate_with_superpixels(labels, sparse, blur_type="gaussian", use_super
             if n_clusters is None:
                 n_clusters = int(lab3.max().item()) + 1
             lab_ptr = lab3.data_ptr()
-        out = torch.empty_like(s3)
+        if out is None:
+            out = torch.empty_like(s3)
+        else:
+            if not (_is_torch(out) and out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and out.numel() == s3.numel()):
+                raise ValueError("out must be a contiguous float32 CUDA tensor of the input's size")
+            out = out.view(s3.shape)
         stats = torch.zeros((n, STATS_STRIDE), dtype=torch.int32, device=s.device) if return_stats else None
         with torch.cuda.device(s.device):
-            lib.check(lib.dcmt_interpolate_with_superpixels_f32(
-                s3.data_ptr(), lab_ptr, int(n_clusters or 0), out.data_ptr(), rows, cols, 0, 0, n, int(use_superpixel),
+            lib.check(lib.dcmt_interpolate_with_superpixels_ex_f32(
+                s3.data_ptr(), lab_ptr, int(n_clusters or 0), out.data_ptr(), rows, cols, 0, 0, n, int(use_superpixel), PATH[path],
                 stats.data_ptr() if return_stats else None, _stream_ptr(stream)))
     else:
         s = _prep_numpy(sparse, np.float32, "sparse")
@@ -164,10 +170,15 @@ def interpolate_with_superpixels(labels, sparse, blur_type="gaussian", use_super
             if n_clusters is None:
                 n_clusters = int(lab3.max()) + 1
             lab_ptr = _np_ptr(lab3)
-        out = np.empty_like(s3)
+        if out is None:
+            out = np.empty_like(s3)
+        else:
+            if not (isinstance(out, np.ndarray) and out.dtype == np.float32 and out.flags.c_contiguous and out.size == s3.size):
+                raise ValueError("out must be a C-contiguous float32 array of the input's size")
+            out = out.reshape(s3.shape)
         stats = np.zeros((n, STATS_STRIDE), np.int32) if return_stats else None
-        lib.check(lib.dcmt_interpolate_with_superpixels_f32_host(
-            _np_ptr(s3), lab_ptr, int(n_clusters or 0), _np_ptr(out), rows, cols, 0, 0, n, int(use_superpixel),
+        lib.check(lib.dcmt_interpolate_with_superpixels_ex_f32_host(
+            _np_ptr(s3), lab_ptr, int(n_clusters or 0), _np_ptr(out), rows, cols, 0, 0, n, int(use_superpixel), PATH[path],
             _np_ptr(stats) if return_stats else None))
     out = out[0] if squeeze else out
     return (out, stats) if return_stats else out
@@ -193,7 +204,7 @@ def stereo_params(official: bool = False, num_iterations: int | None = None, lib
 
 
 def stereo_refine(depth_ig, left_gray, right_gray, params: StereoParams | None = None, *, return_disparity: bool = False,
-                  stream=None, lib: _lib.Library | None = None):
+                  out=None, stream=None, lib: _lib.Library | None = None):
     """main_sl.cpp:1165-1253: gray images + initial dense depth -> refined (and blurred) depth."""
     lib = lib or _lib.load()
     prm = params or stereo_params(lib=lib)
@@ -204,7 +215,7 @@ def stereo_refine(depth_ig, left_gray, right_gray, params: StereoParams | None =
         if l3.shape != d3.shape or r3.shape != d3.shape:
             raise ValueError("depth_ig, left_gray and right_gray shapes differ")
         n, rows, cols = d3.shape
-        out = torch.empty_like(d3)
+        out = torch.empty_like(d3) if out is None else out.view(d3.shape)
         disp = torch.empty_like(d3) if return_disparity else None
         with torch.cuda.device(d3.device):
             lib.check(lib.dcmt_stereo_refine_f32(d3.data_ptr(), l3.data_ptr(), r3.data_ptr(), out.data_ptr(),
@@ -217,7 +228,7 @@ def stereo_refine(depth_ig, left_gray, right_gray, params: StereoParams | None =
         if l3.shape != d3.shape or r3.shape != d3.shape:
             raise ValueError("depth_ig, left_gray and right_gray shapes differ")
         n, rows, cols = d3.shape
-        out = np.empty_like(d3)
+        out = np.empty_like(d3) if out is None else out.reshape(d3.shape)
         disp = np.empty_like(d3) if return_disparity else None
         lib.check(lib.dcmt_stereo_refine_f32_host(_np_ptr(d3), _np_ptr(l3), _np_ptr(r3), _np_ptr(out),
                                                   _np_ptr(disp) if return_disparity else None, rows, cols, n, C.byref(prm)))

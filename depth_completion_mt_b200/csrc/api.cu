@@ -192,11 +192,13 @@ struct CompletionCall {
 
 // the strict-q8 fused path serves plain img_completion with blur none/gaussian on frames of a sane size
 bool fused_applies(const CompletionCall& cc) {
-    if (cc.flags == DCMT_PATH_GENERIC || cc.guided || cc.blur == DCMT_BLUR_BILATERAL) return false;
+    if (cc.flags == DCMT_PATH_GENERIC || cc.blur == DCMT_BLUR_BILATERAL) return false;
+    if (cc.guided && (cc.n_clusters < 0 || cc.n_clusters > 65535)) return false;  // the fused guided front keeps labels as uint16
     if (cc.rows < dcmt::kQ8MinRows || cc.cols < dcmt::kQ8MinCols || cc.rows > dcmt::kQ8MaxRows) return false;
     int th, tw;
     dcmt::q8_choose_tile(cc.rows, cc.cols, &th, &tw);
-    return dcmt::q8_tail_smem(th, tw) <= 200 * 1024 && dcmt::q8_front_smem(th, tw) <= 200 * 1024;
+    return dcmt::q8_tail_smem(th, tw) <= 200 * 1024 && dcmt::q8_front_smem(th, tw) <= 200 * 1024 &&
+           (!cc.guided || dcmt::q8_guided_smem(th, tw) <= 200 * 1024);
 }
 
 size_t completion_ws_bytes(int rows, int cols, int n_frames, bool bilateral, bool fused, bool u16_in = false) {
@@ -255,7 +257,11 @@ int enqueue_completion(const CompletionCall& cc, const float* sparse, const int3
             const int nf = n_frames - f0 < chunk ? n_frames - f0 : chunk;
             ProfEvents pe{};
             API_CUDA(prof_mark(st, 0, &pe), "profiling event");
-            if (in16.p)
+            if (cc.guided)
+                API_CUDA(dcmt::q8_run_guided_front(p, sparse + (size_t)f0 * fstride, nullptr, pitch, fstride, labels + (size_t)f0 * fpix,
+                                                   cc.n_clusters, nf, cc.flags != DCMT_PATH_FUSED, st),
+                         "fused guided front launch");
+            else if (in16.p)
                 API_CUDA(dcmt::q8_run_front(p, nullptr, in16.p + (size_t)f0 * in16.fstride, in16.pitch, in16.fstride, nf, 0, st),
                          "fused front launch");
             else
@@ -388,9 +394,9 @@ int run_completion(const float* sparse, const int32_t* labels, int n_clusters, b
         int e = f;
         while (e < n_frames && h_flags[e]) ++e;
         ar->used = 0;  // the fused work has completed: the arena is free again
-        if ((rc = enqueue_completion(cc, sparse + (size_t)f * g.fstride, nullptr, dense + (size_t)f * g.fstride, g.pitch, g.fstride,
-                                     e - f, stats ? stats + (size_t)f * DCMT_STATS_STRIDE : nullptr, nullptr, nullptr, nullptr, ar,
-                                     st, nullptr)))
+        if ((rc = enqueue_completion(cc, sparse + (size_t)f * g.fstride, guided ? labels + (size_t)f * rows * cols : nullptr,
+                                     dense + (size_t)f * g.fstride, g.pitch, g.fstride, e - f,
+                                     stats ? stats + (size_t)f * DCMT_STATS_STRIDE : nullptr, nullptr, nullptr, nullptr, ar, st, nullptr)))
             return rc;
         f = e;
     }
@@ -509,9 +515,9 @@ int run_completion_host(const float* sparse, const int32_t* labels, int n_cluste
             int e = f;
             while (e < n_frames && h_flags[e]) ++e;
             std::vector<int32_t> keep(h_flags + e, h_flags + n_frames);  // the nested call reuses the pinned buffer
-            rc = run_completion_host(sparse + (size_t)f * g.fstride, nullptr, 0, false, dense + (size_t)f * g.fstride, rows, cols,
-                                     pitch_bytes, frame_stride_bytes, e - f, blur_type, DCMT_PATH_GENERIC,
-                                     stats ? stats + (size_t)f * DCMT_STATS_STRIDE : nullptr);
+            rc = run_completion_host(sparse + (size_t)f * g.fstride, guided ? labels + (size_t)f * fpix : nullptr, n_clusters, guided,
+                                     dense + (size_t)f * g.fstride, rows, cols, pitch_bytes, frame_stride_bytes, e - f, blur_type,
+                                     DCMT_PATH_GENERIC, stats ? stats + (size_t)f * DCMT_STATS_STRIDE : nullptr);
             if (rc) return rc;
             std::copy(keep.begin(), keep.end(), h_flags + e);
             f = e;
@@ -718,20 +724,33 @@ int dcmt_img_completion_u16_host(const uint16_t* sparse_u16, float* dense, int r
                                    out_frame_stride_bytes, n_frames, blur_type, flags, stats);
 }
 
+int dcmt_interpolate_with_superpixels_ex_f32(const float* sparse, const int32_t* labels, int n_clusters, float* dense, int rows,
+                                             int cols, size_t pitch_bytes, size_t frame_stride_bytes, int n_frames, int use_superpixel,
+                                             int flags, int32_t* stats, void* cuda_stream) {
+    // blur is unconditionally Gaussian in the reference (img_completion_lc.cpp:183-192)
+    return run_completion(sparse, labels, n_clusters, use_superpixel != 0, dense, rows, cols, pitch_bytes, frame_stride_bytes,
+                          n_frames, DCMT_BLUR_GAUSSIAN, flags, stats, nullptr, nullptr, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int dcmt_interpolate_with_superpixels_ex_f32_host(const float* sparse, const int32_t* labels, int n_clusters, float* dense, int rows,
+                                                  int cols, size_t pitch_bytes, size_t frame_stride_bytes, int n_frames,
+                                                  int use_superpixel, int flags, int32_t* stats) {
+    return run_completion_host(sparse, labels, n_clusters, use_superpixel != 0, dense, rows, cols, pitch_bytes, frame_stride_bytes,
+                               n_frames, DCMT_BLUR_GAUSSIAN, flags, stats);
+}
+
 int dcmt_interpolate_with_superpixels_f32(const float* sparse, const int32_t* labels, int n_clusters, float* dense,
                                           int rows, int cols, size_t pitch_bytes, size_t frame_stride_bytes, int n_frames,
                                           int use_superpixel, int32_t* stats, void* cuda_stream) {
-    // blur is unconditionally Gaussian in the reference (img_completion_lc.cpp:183-192)
-    return run_completion(sparse, labels, n_clusters, use_superpixel != 0, dense, rows, cols, pitch_bytes,
-                          frame_stride_bytes, n_frames, DCMT_BLUR_GAUSSIAN, DCMT_PATH_GENERIC, stats, nullptr, nullptr,
-                          static_cast<cudaStream_t>(cuda_stream));
+    return dcmt_interpolate_with_superpixels_ex_f32(sparse, labels, n_clusters, dense, rows, cols, pitch_bytes, frame_stride_bytes,
+                                                    n_frames, use_superpixel, DCMT_PATH_AUTO, stats, cuda_stream);
 }
 
 int dcmt_interpolate_with_superpixels_f32_host(const float* sparse, const int32_t* labels, int n_clusters, float* dense,
                                                int rows, int cols, size_t pitch_bytes, size_t frame_stride_bytes,
                                                int n_frames, int use_superpixel, int32_t* stats) {
-    return run_completion_host(sparse, labels, n_clusters, use_superpixel != 0, dense, rows, cols, pitch_bytes,
-                               frame_stride_bytes, n_frames, DCMT_BLUR_GAUSSIAN, DCMT_PATH_GENERIC, stats);
+    return dcmt_interpolate_with_superpixels_ex_f32_host(sparse, labels, n_clusters, dense, rows, cols, pitch_bytes,
+                                                         frame_stride_bytes, n_frames, use_superpixel, DCMT_PATH_AUTO, stats);
 }
 
 int dcmt_img_completion_stages_f32(const float* sparse, float* dense, int rows, int cols, int blur_type, float* stages,

@@ -618,6 +618,252 @@ __global__ void __launch_bounds__(QT, 2) k_q8_front(FrontArgs a) {
     DCMT_STAMP(a, 4);
 }
 
+// ------------------------------------------------------------------------------------------------
+// k_q8_guided_front: the front of interpolate_with_superpixels (src/DC_lidar_camera/img_completion_lc.cpp:34-145) for
+// strict-q8 input.  The reference runs, for every superpixel c, a 2-tap dilate and a 5x5 close on a copy of the image in
+// which every pixel of another superpixel is 0 (:78-103), and keeps the result inside c.  Per output pixel p with label
+// c:
+//     M_c(s)  = label(s) == c ? D(s) : 0                    (absent outside the image)
+//     R1_c(r) = max(M_c(r + (-1,+1)), M_c(r + (+2,+2)))      r inside the image
+//     R2_c(q) = max over r in 5x5(q), r inside the image, of R1_c(r)
+//     out(p)  = min over q in 5x5(p), q inside the image, of R2_c(q);          out(p) = D(p) if p has no valid label.
+// One thread computes one packed word = two horizontally adjacent pixels, each lane with its own label: the 12 x 10
+// footprint is masked row by row (3 ALU ops per word: packed compare, min with 1, select), and because
+//     max over a 5-window of R1 = max(5-window max of the tap-1 row, 5-window max of the tap-2 row three rows further down)
+// every masked row contributes just six sliding 5-wide maxima; the vertical dilation runs over a ring of five such rows,
+// the erosion over the five results.  About 430 lane-operations per pixel; the generic float kernel needs 3 600.
+// Hole-class values are interchangeable (every later stage only asks `< 0.1`), so other-label pixels and holes both
+// encode as 1.  Afterwards the kernel continues like k_q8_front: vertical / horizontal dilate7, hole fill, uint16 store,
+// column keys -- and k_q8_tail finishes the frame.
+// ------------------------------------------------------------------------------------------------
+constexpr int GT = 256;  // threads per CTA (2 CTAs per SM; up to 128 registers per thread)
+
+struct GuidedArgs {
+    FrontArgs f;            // geometry, input, outputs (column maps built for GT threads)
+    const int32_t* labels;  // rows x cols int32 per frame, contiguous
+    int n_clusters;
+};
+
+// lanes of `w` that lie inside the image -> 0xffff, given the image column of the low lane
+__device__ __forceinline__ uint32_t lanes_inside(int gx, int cols) {
+    return ((gx >= 0 && gx < cols) ? 0x0000ffffu : 0u) | ((gx + 1 >= 0 && gx + 1 < cols) ? 0xffff0000u : 0u);
+}
+
+template <bool kBorder>
+__device__ __forceinline__ uint32_t guided_word(const uint32_t* __restrict__ A, const uint32_t* __restrict__ LB, int pitchw, int r, int w,
+                                                uint32_t C, int gy, int gx, int rows, int cols) {
+    // masked footprint rows k = 0 .. 11 <-> image rows gy - 5 + k; positions idx = 0 .. 9 <-> lane-0 columns gx - 3 + idx
+    uint32_t cm[9];  // kBorder: in-image lanes of the R1 columns jj = 0 .. 8 (lane-0 column gx - 4 + jj)
+    if (kBorder) {
+#pragma unroll
+        for (int jj = 0; jj < 9; ++jj) cm[jj] = lanes_inside(gx - 4 + jj, cols);
+    }
+    uint32_t ha[3][5];    // 5-window maxima of the tap-1 rows, waiting three rows for their tap-2 partner
+    uint32_t ring[5][5];  // H rows (horizontal dilation of R1) for the vertical dilation
+    uint32_t out = 0xffffffffu;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) {
+        const uint32_t* pa = A + (r - 5 + k) * pitchw + (w - 2);
+        const uint32_t* pl = LB + (r - 5 + k) * pitchw + (w - 2);
+        uint32_t d[6], l[6];
+#pragma unroll
+        for (int u = 0; u < 6; ++u) { d[u] = pa[u]; l[u] = pl[u]; }
+        // masked value: same label -> the pixel itself; other label -> 0, i.e. a hole (e = 1); outside the image ->
+        // absent (0 stays 0).  ne = 1 per lane whose label differs; cap = 0xffff - 0xfffe * ne (one IMAD, lanes cannot
+        // borrow); masked = min(value, cap).
+        uint32_t m[10];
+#pragma unroll
+        for (int idx = 0; idx < 10; ++idx) {
+            const int j = (idx + 1) >> 1;  // idx odd: aligned word j; idx even: odd pair (word j, word j + 1)
+            const uint32_t dv = (idx & 1) ? d[j] : odd_pair(d[j], d[j + 1]);
+            const uint32_t lv = (idx & 1) ? l[j] : odd_pair(l[j], l[j + 1]);
+            m[idx] = pmin(dv, 0xffffffffu - pmin(lv ^ C, SPLAT16(1)) * 0xfffeu);
+        }
+        uint32_t ta[5], tb[5];  // 5-window maxima of this row as tap-1 row (R1 row k) and as tap-2 row (R1 row k - 3)
+        if (!kBorder) {
+            uint32_t W[6];  // W_s = max(m[s .. s+4]): tap-1 windows are W_0..W_4, tap-2 windows W_1..W_5
+#pragma unroll
+            for (int s = 0; s < 6; ++s) W[s] = pmax3(pmax3(m[s], m[s + 1], m[s + 2]), m[s + 3], m[s + 4]);
+#pragma unroll
+            for (int b = 0; b < 5; ++b) { ta[b] = W[b]; tb[b] = W[b + 1]; }
+        } else {
+            // R1 columns outside the image are excluded: each tap is masked with the in-image lanes of ITS R1 column
+            uint32_t t1[9], t2[9];
+#pragma unroll
+            for (int jj = 0; jj < 9; ++jj) { t1[jj] = m[jj] & cm[jj]; t2[jj] = m[jj + 1] & cm[jj]; }
+#pragma unroll
+            for (int b = 0; b < 5; ++b) {
+                ta[b] = pmax3(pmax3(t1[b], t1[b + 1], t1[b + 2]), t1[b + 3], t1[b + 4]);
+                tb[b] = pmax3(pmax3(t2[b], t2[b + 1], t2[b + 2]), t2[b + 3], t2[b + 4]);
+            }
+        }
+        if (k >= 3) {  // R1 row i = k - 3 (image row gy - 4 + i): tap-1 row k - 3 (waiting in ha), tap-2 row k
+            const int i = k - 3;
+            const int gr = gy - 4 + i;
+            const bool rin = gr >= 0 && gr < rows;  // R1 rows outside the image are excluded
+#pragma unroll
+            for (int b = 0; b < 5; ++b) ring[i % 5][b] = rin ? pmax(ha[k % 3][b], tb[b]) : 0u;
+        }
+        if (k <= 8) {
+#pragma unroll
+            for (int b = 0; b < 5; ++b) ha[k % 3][b] = ta[b];
+        }
+        if (k >= 7) {
+            // H rows i = k-7 .. k-3 are complete: R2 of q row qi = k - 7 (image row gy - 2 + qi), then the erosion over b
+            const int qi = k - 7;
+            const int gq = gy - 2 + qi;
+            if (gq >= 0 && gq < rows) {
+                uint32_t e = 0xffffffffu;
+#pragma unroll
+                for (int b = 0; b < 5; ++b) {
+                    uint32_t r2 = pmax3(pmax3(ring[0][b], ring[1][b], ring[2][b]), ring[3][b], ring[4][b]);
+                    if (kBorder) r2 |= ~lanes_inside(gx - 2 + b, cols);  // q columns outside the image do not take part in the min
+                    e = pmin(e, r2);
+                }
+                out = pmin(out, e);
+            }
+        }
+    }
+    return out;
+}
+
+__global__ void __launch_bounds__(GT, 2) k_q8_guided_front(GuidedArgs g) {
+    DCMT_DYN_SMEM(uint32_t, smem);
+    const FrontArgs& a = g.f;
+    const int th = a.th, tw = a.tw, rows = a.rows, cols = a.cols;
+    Tile t;
+    t.RH = th + FU + FD;
+    t.RQ = tw / 8 + FLQ + FRQ;
+    t.pitchw = t.RQ * 4;
+    const int plane = t.RH * t.pitchw;
+    uint32_t* A = smem + 4;       // encoded image; later the vertical half of dilate7
+    uint32_t* B = A + plane;      // result of the guided stage (the closed image D)
+    uint32_t* LB = B + plane + 4; // labels, two uint16 per word (0xffff = no valid label)
+    const int frame = blockIdx.z;
+    const int y0 = blockIdx.y * th, x0 = blockIdx.x * tw;
+    const int gy0 = y0 - FU, gx0 = x0 - FLQ * 8;
+    t.rlo = max(0, -gy0);
+    t.rhi = min(t.RH, rows - gy0);
+    tile_columns(t, gx0, cols);
+    const ptrdiff_t origin = (ptrdiff_t)frame * (ptrdiff_t)a.in_fstride + ((ptrdiff_t)gy0 * (ptrdiff_t)a.in_pitch + gx0);
+
+    float bad = 0.0f;
+    if (a.in16) front_load<true, false>(a, a.in16 + origin, A, B, t, gx0, bad);
+    else if (a.validate) front_load<false, true>(a, a.in + origin, A, B, t, gx0, bad);
+    else front_load<false, false>(a, a.in + origin, A, B, t, gx0, bad);
+    // labels of the region (cells outside the image are never looked at: their image value is absent)
+    {
+        const int32_t* lab = g.labels + (size_t)frame * rows * cols;
+        const int nk = g.n_clusters;
+        for (int i = threadIdx.x; i < t.RH * t.pitchw; i += GT) {
+            const int r = fast_div(i, a.i_half.magic);  // i_half.nq == pitchw here (see q8_run_guided_front)
+            const int w = i - r * t.pitchw;
+            const int gy = gy0 + r, gx = gx0 + 2 * w;
+            uint32_t lo = 0xffffu, hi = 0xffffu;
+            if (gy >= 0 && gy < rows) {
+                if (gx >= 0 && gx < cols) { const int v = __ldg(lab + (size_t)gy * cols + gx); if (v >= 0 && v < nk) lo = (uint32_t)v; }
+                if (gx + 1 >= 0 && gx + 1 < cols) { const int v = __ldg(lab + (size_t)gy * cols + gx + 1); if (v >= 0 && v < nk) hi = (uint32_t)v; }
+            }
+            LB[i] = lo | (hi << 16);
+        }
+    }
+    if (__syncthreads_or(bad != 0.0f)) {  // not strict q8: this frame is redone by the generic pipeline
+        if (threadIdx.x == 0) a.ctr[frame].needs_generic = 1;
+        return;
+    }
+    // ---- the guided stage on rows core +- 3, pixels core -4 .. +3 (what dilate7 reads); words 2 .. (tw + 10) / 2.
+    //      (Handling words whose two pixels share a label on a cheaper path, with the others compacted into a list, was
+    //      measured: +6 % with real SLIC labels, nothing with jittered ones, and it costs the second CTA per SM.)
+    {
+        const int w_lo = 2, nw = tw / 2 + 4;
+        const int rb = max(FU - 3, t.rlo), re = min(FU + th + 3, t.rhi);
+        // every R1 / q column any item of this tile touches lies inside the image?
+        const bool cols_inside = gx0 + 2 * w_lo - 4 >= 0 && gx0 + 2 * (w_lo + nw - 1) + 1 + 5 < cols;
+        const int n_items = (re - rb) * nw;
+        for (int it = threadIdx.x; it < n_items; it += GT) {
+            const int rr = fast_div(it, a.m_core.magic);  // m_core.nq == nw here
+            const int w = w_lo + (it - rr * nw), r = rb + rr;
+            const int gy = gy0 + r, gx = gx0 + 2 * w;
+            const uint32_t inside = lanes_inside(gx, cols);
+            uint32_t res = 0u;
+            if (inside) {
+                const uint32_t C = LB[r * t.pitchw + w], dw = A[r * t.pitchw + w];
+                // lanes without a valid label keep their own value (:82 only visits pixels of some superpixel)
+                const uint32_t keep = (((C & 0xffffu) == 0xffffu) ? 0x0000ffffu : 0u) | (((C >> 16) == 0xffffu) ? 0xffff0000u : 0u);
+                res = dw;
+                if (keep != 0xffffffffu) {
+                    const uint32_t gw = cols_inside ? guided_word<false>(A, LB, t.pitchw, r, w, C, gy, gx, rows, cols)
+                                                    : guided_word<true>(A, LB, t.pitchw, r, w, C, gy, gx, rows, cols);
+                    res = (dw & keep) | (gw & ~keep);
+                }
+                res &= inside;
+            }
+            B[r * t.pitchw + w] = res;
+        }
+    }
+    __syncthreads();
+    // ---- vertical half of dilate7 (:88-90 of img_completion.cpp, :106-108 here) on the core rows: B -> A
+    {
+        const int rb = max(FU, t.rlo), re = min(FU + th, t.rhi);
+        const int nw = tw / 2 + 4, n_items = (re - rb) * nw;
+        for (int it = threadIdx.x; it < n_items; it += GT) {
+            const int rr = fast_div(it, a.m_core.magic);
+            const int off = (rb + rr) * t.pitchw + 2 + (it - rr * nw);
+            const uint32_t* p = B + off;
+            const int pw = t.pitchw;
+            A[off] = pmax3(pmax3(p[-3 * pw], p[-2 * pw], p[-pw]), pmax3(p[0], p[pw], p[2 * pw]), p[3 * pw]);
+        }
+    }
+    __syncthreads();
+    // ---- horizontal half of dilate7, hole fill, store the core, column keys: as in k_q8_front
+    uint16_t* mid = a.mid + (size_t)frame * a.mid_fstride;
+    {
+        const int cq = tw / 8;
+        const int rend = min(th, rows - y0);
+        for (int it = threadIdx.x; it < rend * cq; it += GT) {
+            const int r = fast_div(it, a.m_pass.magic);  // m_pass.nq == cq here
+            const int q = it - r * cq;
+            const int gx = x0 + q * 8;
+            if (gx >= cols) continue;
+            const int off = ((r + FU) * t.RQ + q + FLQ) * 4;
+            const uint4 tt = h7_max_quad(A + off);
+            uint4 d = lds4(B + off);
+            d.x = fill_holes(d.x, tt.x);
+            d.y = fill_holes(d.y, tt.y);
+            d.z = fill_holes(d.z, tt.z);
+            d.w = fill_holes(d.w, tt.w);
+            sts4(B + off, d);
+            *reinterpret_cast<uint4*>(mid + (size_t)(y0 + r) * a.mid_pitch + gx) = d;
+        }
+    }
+    __syncthreads();
+    const uint16_t* Bh = reinterpret_cast<const uint16_t*>(B);
+    const int hrows = min(th, rows - y0);
+    for (int c2 = threadIdx.x; c2 < 2 * tw; c2 += GT) {
+        const int col = c2 >> 1, from_bottom = c2 & 1;
+        const int gx = x0 + col;
+        if (gx >= cols) continue;
+        const uint16_t* p = Bh + (size_t)FU * t.pitchw * 2 + FLQ * 8 + col;
+        if (!from_bottom) {
+            for (int cy = 0; cy < hrows; ++cy) {
+                const uint32_t e = p[(size_t)cy * t.pitchw * 2];
+                if (e >= E_VALID_MIN) {
+                    atomicMin(a.col_first + (size_t)frame * a.mid_pitch + gx, ((uint32_t)(y0 + cy) << 16) | e);
+                    break;
+                }
+            }
+        } else {
+            for (int cy = hrows - 1; cy >= 0; --cy) {
+                const uint32_t e = p[(size_t)cy * t.pitchw * 2];
+                if (e >= E_VALID_MIN) {
+                    atomicMax(a.col_last + (size_t)frame * a.mid_pitch + gx, ((uint32_t)(y0 + cy) << 16) | e);
+                    break;
+                }
+            }
+        }
+    }
+}
+
 __global__ void k_q8_init_cols(uint32_t* first, uint32_t* last, size_t n) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { first[i] = 0xffffffffu; last[i] = 0u; }
@@ -1171,6 +1417,8 @@ cudaError_t q8_configure() {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_q8_front<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_q8_guided_front, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_q8_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 }
 
@@ -1189,6 +1437,27 @@ cudaError_t q8_run_front(const Q8Plan& p, const float* in, const uint16_t* in16,
     const dim3 grid((p.cols + p.tw - 1) / p.tw, (p.rows + p.th - 1) / p.th, n_frames);
     if (p.cols % 8 != 0) DCMT_LAUNCH(k_q8_front<true>, grid, dim3(QT), q8_front_smem(p.th, p.tw), st, a);
     else DCMT_LAUNCH(k_q8_front<false>, grid, dim3(QT), q8_front_smem(p.th, p.tw), st, a);
+    return cudaGetLastError();
+}
+
+size_t q8_guided_smem(int th, int tw) { return ((size_t)3 * (th + FU + FD) * (tw / 8 + FLQ + FRQ) * 4 + 12) * sizeof(uint32_t); }
+
+cudaError_t q8_run_guided_front(const Q8Plan& p, const float* in, const uint16_t* in16, size_t in_pitch, size_t in_fstride,
+                                const int32_t* labels, int n_clusters, int n_frames, int validate, cudaStream_t st) {
+    const size_t ncol = (size_t)p.mid_pitch * n_frames;
+    DCMT_LAUNCH(k_q8_zero_counters, dim3((n_frames + 127) / 128), dim3(128), 0, st, p.ctr, n_frames);
+    DCMT_LAUNCH(k_q8_init_cols, dim3((unsigned)((ncol + 255) / 256)), dim3(256), 0, st, p.col_first, p.col_last, ncol);
+    const size_t unit = in16 ? 8 : 4;
+    const uintptr_t base = in16 ? reinterpret_cast<uintptr_t>(in16) : reinterpret_cast<uintptr_t>(in);
+    const int RQ = p.tw / 8 + FLQ + FRQ;
+    // column maps / magic reciprocals for GT threads: load by region quads; items of the guided stage and of the vertical
+    // pass by tw / 2 + 4 words (m_core), of the final pass by core quads (m_pass), label plane by region words (i_half)
+    GuidedArgs g{FrontArgs{in, in16, in_pitch, in_fstride, p.mid, (size_t)p.mid_pitch, (size_t)p.mid_pitch * p.rows, p.col_first, p.col_last,
+                           p.ctr, p.rows, p.cols, p.th, p.tw, (int)(in_pitch % unit == 0 && in_fstride % unit == 0 && (base & 15) == 0), validate,
+                           make_colmap(RQ, GT), make_colmap(p.tw / 8, GT), make_colmap(p.tw / 2 + 4, GT), make_items(RQ * 4, GT), nullptr},
+                 labels, n_clusters};
+    const dim3 grid((p.cols + p.tw - 1) / p.tw, (p.rows + p.th - 1) / p.th, n_frames);
+    DCMT_LAUNCH(k_q8_guided_front, grid, dim3(GT), q8_guided_smem(p.th, p.tw), st, g);
     return cudaGetLastError();
 }
 

@@ -33,6 +33,11 @@ cudaError_t q8_configure();
 // flagged for the generic pipeline); uint16 input needs no check.  Pitches in elements of the input type.
 cudaError_t q8_run_front(const Q8Plan& p, const float* in, const uint16_t* in16, size_t in_pitch, size_t in_fstride, int n_frames,
                          int validate, cudaStream_t st);
+// The front of interpolate_with_superpixels (img_completion_lc.cpp:34-145) for strict-q8 input: labels are rows x cols
+// int32 per frame (contiguous), values outside [0, n_clusters) mean "no superpixel"; needs n_clusters <= 65535.
+size_t q8_guided_smem(int th, int tw);
+cudaError_t q8_run_guided_front(const Q8Plan& p, const float* in, const uint16_t* in16, size_t in_pitch, size_t in_fstride,
+                                const int32_t* labels, int n_clusters, int n_frames, int validate, cudaStream_t st);
 // uint16 -> float32 metres (main.cpp:79) into a contiguous buffer, for frames served by the generic pipeline
 cudaError_t q8_convert_u16(const uint16_t* in, size_t in_pitch, size_t in_fstride, float* out, int rows, int cols, int n_frames,
                            cudaStream_t st);

@@ -133,6 +133,18 @@ DCMT_API int dcmt_interpolate_with_superpixels_f32_host(const float *sparse, con
                                                         size_t frame_stride_bytes, int n_frames, int use_superpixel,
                                                         int32_t *stats_or_null);
 
+/* the same with an explicit kernel path (`flags` as for dcmt_img_completion_f32).  The plain entry points above use
+ * DCMT_PATH_AUTO: strict-q8 frames (KITTI depth) run the fused guided front + fused tail, other frames the generic
+ * float pipeline; the fused guided front needs n_clusters <= 65535. */
+DCMT_API int dcmt_interpolate_with_superpixels_ex_f32(const float *sparse, const int32_t *labels, int n_clusters,
+                                                      float *dense, int rows, int cols, size_t pitch_bytes,
+                                                      size_t frame_stride_bytes, int n_frames, int use_superpixel,
+                                                      int flags, int32_t *stats_or_null, void *cuda_stream);
+DCMT_API int dcmt_interpolate_with_superpixels_ex_f32_host(const float *sparse, const int32_t *labels, int n_clusters,
+                                                           float *dense, int rows, int cols, size_t pitch_bytes,
+                                                           size_t frame_stride_bytes, int n_frames, int use_superpixel,
+                                                           int flags, int32_t *stats_or_null);
+
 /* parameters of the stereo refinement; dcmt_stereo_params_default() fills the values hard-coded in
  * main_sl.cpp, dcmt_stereo_params_official() those of main_sl_OFFICIAL.cpp:832-918. */
 typedef struct dcmt_stereo_params {

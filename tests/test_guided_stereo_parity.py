@@ -37,6 +37,37 @@ def body_guided_seeded(be, shapes):
         assert_bit_equal(got, co.interpolate_with_superpixels(s, lab, k // 2, literal=False), "partial cluster range")
 
 
+def body_guided_fused(be, shapes):
+    """strict-q8 frames take the fused guided front (k_q8_guided_front) + the fused tail; any other frame, and
+    path="generic", the float pipeline: same bytes as the oracle either way."""
+    rng = np.random.default_rng(5)
+    for i, (rows, cols, p, step) in enumerate(shapes):
+        s = synth.sparse_depth(170 + i, rows, cols, p, kitti_like=bool(i & 1))
+        lab, k = synth.superpixel_labels(170 + i, rows, cols, step)
+        if i % 3 == 1:  # unassigned pixels and labels beyond n_clusters keep their own value
+            lab = lab.copy()
+            lab[rng.random(lab.shape) < 0.05] = -1
+            lab[rng.random(lab.shape) < 0.02] = k + 7
+        ref_st = {}
+        ref = co.interpolate_with_superpixels(s, lab, k, literal=False, stats=ref_st)
+        got, st = be.interpolate_with_superpixels(lab, s, 1, n_clusters=k, return_stats=True)
+        assert_bit_equal(got, ref, f"fused guided {rows}x{cols} step {step}")
+        assert int(st[0, 3]) == 1 and int(st[0, 0]) == ref_st["loop_passes"], f"{rows}x{cols}: path {st[0, 3]}"
+        got, st = be.interpolate_with_superpixels(lab, s, 1, n_clusters=k, path="generic", return_stats=True)
+        assert_bit_equal(got, ref, f"generic guided {rows}x{cols}")
+        assert int(st[0, 3]) == 0
+    # a non-q8 frame in a batch is redone by the generic pipeline with its own labels
+    rows, cols = 48, 80
+    b = np.stack([synth.sparse_depth(180, rows, cols, 0.06), synth.sparse_depth_float(181, rows, cols, 0.06), synth.sparse_depth(182, rows, cols, 0.06)])
+    labs = np.stack([synth.superpixel_labels(180 + f, rows, cols, 9)[0] for f in range(3)])
+    k = synth.superpixel_labels(180, rows, cols, 9)[1]
+    got, st = be.interpolate_with_superpixels(labs, b, 1, n_clusters=k, return_stats=True)
+    assert [int(v) for v in st[:, 3]] == [1, 0, 1]
+    for f in (0, 2):
+        assert_bit_equal(got[f], co.interpolate_with_superpixels(b[f], labs[f], k, literal=False), f"batch frame {f}")
+    assert np.abs(got[1] - co.interpolate_with_superpixels(b[1], labs[1], k, literal=False)).max() <= GAUSS_TOL
+
+
 def body_stereo_golden(be, golden):
     g = golden["stereo"]
     for name in sorted({k.split("__")[0] for k in g.files}):
@@ -60,6 +91,10 @@ def test_emu_guided_seeded(emu_lib):
     body_guided_seeded(Backend(emu_lib, "emu"), [(40, 70, 0.06, 8)])
 
 
+def test_emu_guided_fused(emu_lib):
+    body_guided_fused(Backend(emu_lib, "emu"), [(40, 70, 0.06, 8), (97, 171, 0.05, 12), (64, 333, 0.03, 18), (130, 96, 0.1, 7), (33, 47, 0.08, 6)])
+
+
 def test_emu_stereo_golden(emu_lib, golden):
     body_stereo_golden(Backend(emu_lib, "emu"), golden)
 
@@ -77,6 +112,13 @@ def test_emu_stereo_batch(emu_lib):
 @pytest.mark.parametrize("mode", ["gpu_host", "gpu_device"])
 def test_gpu_guided_golden(gpu_lib, golden, mode):
     body_guided_golden(Backend(gpu_lib, mode), golden)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["gpu_host", "gpu_device"])
+def test_gpu_guided_fused(gpu_lib, mode):
+    body_guided_fused(Backend(gpu_lib, mode), [(40, 70, 0.06, 8), (97, 171, 0.05, 12), (64, 333, 0.03, 18), (130, 96, 0.1, 7), (33, 47, 0.08, 6),
+                                               (352, 1216, 0.05, 18), (375, 1242, 0.05, 18)])
 
 
 @pytest.mark.gpu
