@@ -1005,6 +1005,7 @@ int dcmt_stereo_refine_f32(const float* depth_ig, const uint8_t* left_gray, cons
     int rc = check_planes(rows, cols, n_frames);
     if (rc) return rc;
     if (prm->num_iterations < 0) return fail(DCMT_E_BADARG, "num_iterations %d", prm->num_iterations);
+    if ((size_t)rows * (size_t)cols > (size_t)1 << 30) return fail(DCMT_E_UNSUPPORTED, "frame larger than 2^30 pixels");
     if (n_frames == 0) return DCMT_OK;
     const size_t bytes = (size_t)rows * cols * n_frames * sizeof(float);
     if (overlaps(depth_ig, bytes, depth_out, bytes)) return fail(DCMT_E_BADARG, "input and output overlap");
@@ -1022,33 +1023,38 @@ int dcmt_stereo_refine_f32_host(const float* depth_ig, const uint8_t* left_gray,
     if (!depth_ig || !left_gray || !right_gray || !depth_out || !prm) return fail(DCMT_E_BADARG, "null pointer");
     int rc = check_planes(rows, cols, n_frames);
     if (rc) return rc;
+    if (prm->num_iterations < 0) return fail(DCMT_E_BADARG, "num_iterations %d", prm->num_iterations);
+    if ((size_t)rows * (size_t)cols > (size_t)1 << 30) return fail(DCMT_E_UNSUPPORTED, "frame larger than 2^30 pixels");
     if (n_frames == 0) return DCMT_OK;
     if ((rc = check_device())) return rc;
-    const size_t n = (size_t)rows * cols * n_frames;
-    float *d_ig = nullptr, *d_out = nullptr, *d_disp = nullptr;
-    uint8_t *d_l = nullptr, *d_r = nullptr;
-    auto cleanup = [&] { cudaFree(d_ig); cudaFree(d_out); cudaFree(d_disp); cudaFree(d_l); cudaFree(d_r); };
-    cudaError_t e;
-    if ((e = cudaMalloc(&d_ig, n * 4)) != cudaSuccess || (e = cudaMalloc(&d_out, n * 4)) != cudaSuccess ||
-        (disp_out && (e = cudaMalloc(&d_disp, n * 4)) != cudaSuccess) || (e = cudaMalloc(&d_l, n)) != cudaSuccess ||
-        (e = cudaMalloc(&d_r, n)) != cudaSuccess) {
-        cleanup();
-        return fail(DCMT_E_NOMEM, "device staging buffers: %s", cudaGetErrorString(e));
+    // chunks of frames flow H2D -> kernel -> D2H round-robin over the three host streams (asynchronous for page-locked buffers)
+    HostStreams* hs = nullptr;
+    if ((rc = host_streams(&hs))) return rc;
+    const size_t fpix = (size_t)rows * cols;
+    const int hc = host_chunk_frames(rows, cols, n_frames);
+    const size_t bytes = 2 * carve_bytes(fpix * hc, sizeof(float)) + (disp_out ? carve_bytes(fpix * hc, sizeof(float)) : 0) +
+                         2 * carve_bytes(fpix * hc, sizeof(uint8_t));
+    int slot = 0;
+    for (int f0 = 0; f0 < n_frames; f0 += hc, slot = (slot + 1) % kHostStreams) {
+        const int nf = n_frames - f0 < hc ? n_frames - f0 : hc;
+        cudaStream_t st = hs->s[slot];
+        Arena* ar = nullptr;
+        if ((rc = arena_acquire(st, bytes, &ar))) return rc;
+        float* d_ig = carve<float>(ar, fpix * hc);
+        float* d_out = carve<float>(ar, fpix * hc);
+        float* d_disp = disp_out ? carve<float>(ar, fpix * hc) : nullptr;
+        uint8_t* d_l = carve<uint8_t>(ar, fpix * hc);
+        uint8_t* d_r = carve<uint8_t>(ar, fpix * hc);
+        const size_t off = (size_t)f0 * fpix, n = fpix * nf;
+        API_CUDA(cudaMemcpyAsync(d_ig, depth_ig + off, n * 4, cudaMemcpyHostToDevice, st), "host to device copy");
+        API_CUDA(cudaMemcpyAsync(d_l, left_gray + off, n, cudaMemcpyHostToDevice, st), "host to device copy");
+        API_CUDA(cudaMemcpyAsync(d_r, right_gray + off, n, cudaMemcpyHostToDevice, st), "host to device copy");
+        if ((rc = dcmt_stereo_refine_f32(d_ig, d_l, d_r, d_out, d_disp, rows, cols, nf, prm, st))) return rc;
+        API_CUDA(cudaMemcpyAsync(depth_out + off, d_out, n * 4, cudaMemcpyDeviceToHost, st), "device to host copy");
+        if (disp_out) API_CUDA(cudaMemcpyAsync(disp_out + off, d_disp, n * 4, cudaMemcpyDeviceToHost, st), "device to host copy");
     }
-    if ((e = cudaMemcpy(d_ig, depth_ig, n * 4, cudaMemcpyHostToDevice)) != cudaSuccess ||
-        (e = cudaMemcpy(d_l, left_gray, n, cudaMemcpyHostToDevice)) != cudaSuccess ||
-        (e = cudaMemcpy(d_r, right_gray, n, cudaMemcpyHostToDevice)) != cudaSuccess) {
-        cleanup();
-        return cuda_fail(e, "host to device copy");
-    }
-    rc = dcmt_stereo_refine_f32(d_ig, d_l, d_r, d_out, d_disp, rows, cols, n_frames, prm, nullptr);
-    if (rc == DCMT_OK) {
-        if ((e = cudaStreamSynchronize(nullptr)) != cudaSuccess) rc = cuda_fail(e, "kernel execution");
-        else if ((e = cudaMemcpy(depth_out, d_out, n * 4, cudaMemcpyDeviceToHost)) != cudaSuccess) rc = cuda_fail(e, "device to host copy");
-        else if (disp_out && (e = cudaMemcpy(disp_out, d_disp, n * 4, cudaMemcpyDeviceToHost)) != cudaSuccess) rc = cuda_fail(e, "device to host copy");
-    }
-    cleanup();
-    return rc;
+    for (int i = 0; i < kHostStreams; ++i) API_CUDA(cudaStreamSynchronize(hs->s[i]), "kernel execution");
+    return DCMT_OK;
 }
 
 int dcmt_measurement_derivatives_f32(const float* value, float* dx, float* dy, int rows, int cols, int n_frames,

@@ -18,7 +18,7 @@ namespace dcmt {
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int TH = 16, TW = 64;  // tile core of the fused kernel
+constexpr int TH = 32, TW = 128;  // tile core of the fused kernel (2-pixel halo for the Gaussian: 16 % extra refinement work)
 
 // dx of calculateMeasuementDerivatives at (r, c): 0 on the 1-px border (:719,:724)
 template <class Plane>
@@ -33,12 +33,6 @@ struct PlaneF32 {
     int cols;
     __device__ __forceinline__ float operator()(int r, int c) const { return __ldg(p + (size_t)r * cols + c); }
 };
-struct PlaneU8 {
-    const uint8_t* p;
-    int cols;
-    __device__ __forceinline__ float operator()(int r, int c) const { return (float)__ldg(p + (size_t)r * cols + c); }
-};
-
 // One optimize_IG pixel: `iters` damped Gauss-Newton steps on the disparity d of pixel (i, j).
 template <class Plane>
 __device__ __forceinline__ float refine_pixel(const Plane& right, float left_val, float d, int i, int j, int rows,
@@ -69,6 +63,44 @@ __device__ __forceinline__ float refine_pixel(const Plane& right, float left_val
         const float b = __fmul_rn(jcr, err);
         const float dd = __fdiv_rn(-b, H);          // :837
         d = __fadd_rn(d, dd);                       // :838
+    }
+    return d;
+}
+
+// refine_pixel for gray uint8 planes (the fused kernel): the same arithmetic with the four neighbouring bytes of the
+// right image row loaded once per iteration.  `.5 * v[c+1] - .5 * v[c-1]` (:742, double in the source) is exact in
+// float for byte values, so the derivative needs no double here.
+__device__ __forceinline__ float refine_pixel_u8(const uint8_t* __restrict__ rrow, bool row_inner, float left_val, float d, int j, int cols,
+                                                 int iters, float damp, float clip) {
+    for (int k = 0; k < iters; ++k) {
+        if (d == 0.0f) break;
+        const float c = __fsub_rn((float)j, d);
+        if (c != c) break;
+        const int c0 = __double2int_rz((double)c + 0.5);
+        if (c0 < 0 || c0 > cols || c0 == 2147483647 || c0 + 1 > cols) continue;
+        const float dc = __fsub_rn(c, (float)c0);
+        const float dc1 = __double2float_rn(__dsub_rn(1.0, (double)dc));
+        float vm1, v0, v1, v2;  // right(i, c0 - 1 .. c0 + 2), 0 where the column does not exist
+        if (c0 >= 1 && c0 + 2 < cols) {
+            vm1 = (float)__ldg(rrow + c0 - 1); v0 = (float)__ldg(rrow + c0); v1 = (float)__ldg(rrow + c0 + 1); v2 = (float)__ldg(rrow + c0 + 2);
+        } else {
+            vm1 = c0 >= 1 ? (float)__ldg(rrow + c0 - 1) : 0.0f;
+            v0 = c0 < cols ? (float)__ldg(rrow + c0) : 0.0f;
+            v1 = c0 + 1 < cols ? (float)__ldg(rrow + c0 + 1) : 0.0f;
+            v2 = c0 + 2 < cols ? (float)__ldg(rrow + c0 + 2) : 0.0f;
+        }
+        // derivative entries are 0 on the 1-pixel image border (:719,:724) and where the column does not exist
+        const float g00 = (row_inner && c0 >= 1 && c0 < cols - 1) ? __fsub_rn(__fmul_rn(0.5f, v1), __fmul_rn(0.5f, vm1)) : 0.0f;
+        const float g01 = (row_inner && c0 + 1 < cols - 1) ? __fsub_rn(__fmul_rn(0.5f, v2), __fmul_rn(0.5f, v0)) : 0.0f;
+        const float value = __fadd_rn(__fmul_rn(v0, dc1), __fmul_rn(v1, dc));
+        const float gx = __fadd_rn(__fmul_rn(g00, dc1), __fmul_rn(g01, dc));
+        float err = __fsub_rn(value, left_val);
+        if (err > clip) err = clip;
+        if (err < -clip) err = -clip;
+        const float jcr = -gx;
+        const float H = __fadd_rn(__fmul_rn(jcr, jcr), damp);
+        const float b = __fmul_rn(jcr, err);
+        d = __fadd_rn(d, __fdiv_rn(-b, H));
     }
     return d;
 }
@@ -146,8 +178,8 @@ __global__ void __launch_bounds__(kThreads) k_stereo_refine(RefineArgs a) {
     const int rows = a.rows, cols = a.cols;
     const size_t fpix = (size_t)rows * cols;
     const float* dig = a.depth_ig + (size_t)frame * fpix;
-    const PlaneU8 left{a.left + (size_t)frame * fpix, cols};
-    const PlaneU8 right{a.right + (size_t)frame * fpix, cols};
+    const uint8_t* left = a.left + (size_t)frame * fpix;
+    const uint8_t* right = a.right + (size_t)frame * fpix;
     const int halo = a.final_gauss ? 2 : 0;
 
     for (int idx = threadIdx.x; idx < PH * PW; idx += kThreads) {
@@ -157,8 +189,9 @@ __global__ void __launch_bounds__(kThreads) k_stereo_refine(RefineArgs a) {
         const bool core = py >= 2 && py < 2 + TH && px >= 2 && px < 2 + TW;
         const bool wanted = py >= 2 - halo && py < 2 + TH + halo && px >= 2 - halo && px < 2 + TW + halo;
         if (wanted && gy >= 0 && gy < rows && gx >= 0 && gx < cols) {
-            float d = initial_disparity(__ldg(dig + (size_t)gy * cols + gx), a.bf);
-            d = refine_pixel(right, left(gy, gx), d, gy, gx, rows, cols, a.iters, a.damp, a.err_clip);
+            const int o = gy * cols + gx;  // frames are < 2^30 pixels
+            float d = initial_disparity(__ldg(dig + o), a.bf);
+            d = refine_pixel_u8(right + gy * cols, gy >= 1 && gy < rows - 1, (float)__ldg(left + o), d, gx, cols, a.iters, a.damp, a.err_clip);
             depth = depth_from_disparity(d, a.bf, a.depth_clip);
             if (core && a.disp_out) a.disp_out[(size_t)frame * fpix + (size_t)gy * cols + gx] = d;
         }
@@ -184,8 +217,13 @@ __global__ void __launch_bounds__(kThreads) k_stereo_refine(RefineArgs a) {
             const float* row = P + py * PW;
             const int b = 2 - x0;
             const float c0 = row[cx + 2];
-            const float m1 = row[reflect101(gx - 1, cols) + b], p1 = row[reflect101(gx + 1, cols) + b];
-            const float m2 = row[reflect101(gx - 2, cols) + b], p2 = row[reflect101(gx + 2, cols) + b];
+            float m1, p1, m2, p2;
+            if (gx >= 2 && gx + 2 < cols) {
+                m1 = row[cx + 1]; p1 = row[cx + 3]; m2 = row[cx]; p2 = row[cx + 4];
+            } else {
+                m1 = row[reflect101(gx - 1, cols) + b]; p1 = row[reflect101(gx + 1, cols) + b];
+                m2 = row[reflect101(gx - 2, cols) + b]; p2 = row[reflect101(gx + 2, cols) + b];
+            }
             g = __fadd_rn(__fadd_rn(__fmul_rn(c0, k0), __fmul_rn(__fadd_rn(m1, p1), k1)), __fmul_rn(__fadd_rn(m2, p2), k2));
         }
         G[idx] = g;
@@ -197,8 +235,13 @@ __global__ void __launch_bounds__(kThreads) k_stereo_refine(RefineArgs a) {
         if (gy >= rows || gx >= cols) continue;
         const int b = 2 - y0;
         const float c0 = G[(cy + 2) * TW + cx];
-        const float m1 = G[(reflect101(gy - 1, rows) + b) * TW + cx], p1 = G[(reflect101(gy + 1, rows) + b) * TW + cx];
-        const float m2 = G[(reflect101(gy - 2, rows) + b) * TW + cx], p2 = G[(reflect101(gy + 2, rows) + b) * TW + cx];
+        float m1, p1, m2, p2;
+        if (gy >= 2 && gy + 2 < rows) {
+            m1 = G[(cy + 1) * TW + cx]; p1 = G[(cy + 3) * TW + cx]; m2 = G[cy * TW + cx]; p2 = G[(cy + 4) * TW + cx];
+        } else {
+            m1 = G[(reflect101(gy - 1, rows) + b) * TW + cx]; p1 = G[(reflect101(gy + 1, rows) + b) * TW + cx];
+            m2 = G[(reflect101(gy - 2, rows) + b) * TW + cx]; p2 = G[(reflect101(gy + 2, rows) + b) * TW + cx];
+        }
         out[(size_t)gy * cols + gx] =
             __fadd_rn(__fadd_rn(__fmul_rn(c0, k0), __fmul_rn(__fadd_rn(m1, p1), k1)), __fmul_rn(__fadd_rn(m2, p2), k2));
     }
