@@ -811,6 +811,7 @@ int dcmt_slic_u8c3(const uint8_t* lab, int rows, int cols, int step, int nc, int
     if (rc) return rc;
     if (nc == 0 || iterations < 0) return fail(DCMT_E_BADARG, "nc %d, iterations %d", nc, iterations);
     if (step < 4) return fail(DCMT_E_UNSUPPORTED, "step %d: find_local_minimum (slic.cpp:72-99) reads outside the image below 4", step);
+    if (rows >= 1 << 24 || cols >= 1 << 24) return fail(DCMT_E_UNSUPPORTED, "SLIC frames are limited to 2^24 rows / columns");
     if ((size_t)rows * (size_t)cols > (size_t)1 << 30) return fail(DCMT_E_UNSUPPORTED, "frame larger than 2^30 pixels");
     if ((rc = check_device())) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);

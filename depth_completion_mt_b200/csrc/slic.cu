@@ -48,21 +48,31 @@ __device__ __forceinline__ int bin_of(double v, int step, int nb) {
     return b < 0 ? 0 : (b >= nb ? nb - 1 : b);
 }
 
-__global__ void k_slic_bin_count(const double* __restrict__ centers, int n, int step, int bx, int by, int* __restrict__ count,
-                                 unsigned long long* __restrict__ sums) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= n) return;
-    for (int k = 0; k < 6; ++k) sums[(size_t)c * 6 + k] = 0ull;
-    const double x = centers[(size_t)c * 5 + 3], y = centers[(size_t)c * 5 + 4];
-    if (x != x || y != y) return;  // NaN centre (empty cluster): covers nothing
-    atomicAdd(count + bin_of(y, step, by) * bx + bin_of(x, step, bx), 1);
-}
-
-// exclusive scan of the bin counts by one block: thread t owns `chunk` consecutive bins, the per-thread totals are
-// scanned in shared memory (Hillis-Steele), then every thread writes the offsets of its bins
 constexpr int kScanThreads = 1024;
-__global__ void __launch_bounds__(kScanThreads) k_slic_bin_scan(int* __restrict__ count, int* __restrict__ fill, int nbins) {
+
+// Everything between two assignments in ONE launch of one block (the centre and bin counts are a few thousand at most):
+// centre update from the sums of the previous iteration (:166-172), reset of the sums, binning of the centres on the
+// step-sized grid (count, exclusive scan, fill).  Five tiny dependent launches per iteration were 40 % of the run time.
+__global__ void __launch_bounds__(kScanThreads) k_slic_prepare(double* __restrict__ centers, unsigned long long* __restrict__ sums, int n,
+                                                              int step, int bx, int by, int* __restrict__ count, int* __restrict__ fill,
+                                                              int* __restrict__ items, int do_update) {
     __shared__ int part[kScanThreads];
+    const int nbins = bx * by;
+    for (int c = threadIdx.x; c < n; c += kScanThreads) {
+        if (do_update) {
+            const double cnt = (double)sums[(size_t)c * 6 + 5];
+            for (int k = 0; k < 5; ++k) centers[(size_t)c * 5 + k] = __ddiv_rn((double)sums[(size_t)c * 6 + k], cnt);
+        }
+        for (int k = 0; k < 6; ++k) sums[(size_t)c * 6 + k] = 0ull;
+    }
+    for (int b = threadIdx.x; b <= nbins; b += kScanThreads) count[b] = 0;
+    __syncthreads();
+    for (int c = threadIdx.x; c < n; c += kScanThreads) {
+        const double x = centers[(size_t)c * 5 + 3], y = centers[(size_t)c * 5 + 4];
+        if (x != x || y != y) continue;  // NaN centre (empty cluster): covers nothing
+        atomicAdd(count + bin_of(y, step, by) * bx + bin_of(x, step, bx), 1);
+    }
+    __syncthreads();
     const int chunk = (nbins + kScanThreads - 1) / kScanThreads;
     const int b0 = threadIdx.x * chunk, b1 = min(b0 + chunk, nbins);
     int total = 0;
@@ -75,7 +85,7 @@ __global__ void __launch_bounds__(kScanThreads) k_slic_bin_scan(int* __restrict_
         part[threadIdx.x] += v;
         __syncthreads();
     }
-    int acc = part[threadIdx.x] - total;  // exclusive prefix of this thread's chunk
+    int acc = part[threadIdx.x] - total;
     for (int b = b0; b < b1; ++b) {
         const int c = count[b];
         count[b] = acc;
@@ -83,21 +93,13 @@ __global__ void __launch_bounds__(kScanThreads) k_slic_bin_scan(int* __restrict_
         acc += c;
     }
     if (threadIdx.x == kScanThreads - 1) count[nbins] = part[kScanThreads - 1];
-}
-
-__global__ void k_slic_bin_fill(const double* __restrict__ centers, int n, int step, int bx, int by, const int* __restrict__ offset,
-                                int* __restrict__ fill, int* __restrict__ items) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= n) return;
-    const double x = centers[(size_t)c * 5 + 3], y = centers[(size_t)c * 5 + 4];
-    if (x != x || y != y) return;
-    const int b = bin_of(y, step, by) * bx + bin_of(x, step, bx);
-    items[offset[b] + atomicAdd(fill + b, 1)] = c;
-}
-
-__global__ void k_slic_clear_counts(int* __restrict__ count, int n) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) count[i] = 0;
+    __syncthreads();
+    for (int c = threadIdx.x; c < n; c += kScanThreads) {
+        const double x = centers[(size_t)c * 5 + 3], y = centers[(size_t)c * 5 + 4];
+        if (x != x || y != y) continue;
+        const int b = bin_of(y, step, by) * bx + bin_of(x, step, bx);
+        items[count[b] + atomicAdd(fill + b, 1)] = c;
+    }
 }
 
 // assignment (:121-139) + accumulation of the new centres (:148-163), one thread per pixel
@@ -105,43 +107,133 @@ __global__ void __launch_bounds__(256) k_slic_assign(const uint8_t* __restrict__
                                                      const double* __restrict__ centers, const int* __restrict__ offset,
                                                      const int* __restrict__ items, int32_t* __restrict__ labels,
                                                      unsigned long long* __restrict__ sums) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-    if (x >= cols) return;
-    const uint8_t* p = lab + ((size_t)y * cols + x) * 3;
-    const double L = p[0], A = p[1], B = p[2];
-    const int pbx = x / step < bx ? x / step : bx - 1, pby = y / step < by ? y / step : by - 1;
-    double best = (double)FLT_MAX;  // :117
-    int best_c = -1;
-    for (int gy = max(pby - 1, 0); gy <= min(pby + 1, by - 1); ++gy)
-        for (int gx = max(pbx - 1, 0); gx <= min(pbx + 1, bx - 1); ++gx) {
-            const int b = gy * bx + gx;
+    // a block is a 16 x 16 pixel tile: the centres that can cover any of its pixels sit in the bins around it; they are
+    // staged in shared memory once (the per-pixel loops below would otherwise chase offset -> item -> centre through
+    // global memory: the kernel was bound by that latency, 18 % issue-active)
+    constexpr int kCap = 96;
+    __shared__ double s_cent[kCap][5];
+    __shared__ int s_idx[kCap];
+    __shared__ unsigned s_sum[kCap][6];  // per-tile sums of L, a, b, x, y, count for the staged centres
+    __shared__ int s_n;
+    const int tid = threadIdx.y * 16 + threadIdx.x;
+    const int x = blockIdx.x * 16 + threadIdx.x, y = blockIdx.y * 16 + threadIdx.y;
+    if (tid == 0) s_n = 0;
+    for (int i = tid; i < kCap * 6; i += 256) (&s_sum[0][0])[i] = 0u;
+    __syncthreads();
+    {
+        const int bx0 = max((int)(blockIdx.x * 16) / step - 1, 0), bx1 = min((int)(blockIdx.x * 16 + 15) / step + 1, bx - 1);
+        const int by0 = max((int)(blockIdx.y * 16) / step - 1, 0), by1 = min((int)(blockIdx.y * 16 + 15) / step + 1, by - 1);
+        const int nbx = bx1 - bx0 + 1, nb = nbx * (by1 - by0 + 1);
+        for (int i = tid; i < nb; i += 256) {
+            const int b = (by0 + i / nbx) * bx + bx0 + i % nbx;
             for (int k = offset[b]; k < offset[b + 1]; ++k) {
-                const int c = items[k];
-                const double* ce = centers + (size_t)c * 5;
-                const double cx = ce[3], cy = ce[4];
-                // for (int k = cx - step; k < cx + step; k++) (:123): truncation towards zero, then a double comparison
-                if (x < (int)__dsub_rn(cx, (double)step) || !((double)x < __dadd_rn(cx, (double)step))) continue;
-                if (y < (int)__dsub_rn(cy, (double)step) || !((double)y < __dadd_rn(cy, (double)step))) continue;
-                const double dc = __dsqrt_rn(__dadd_rn(__dadd_rn(sq(__dsub_rn(ce[0], L)), sq(__dsub_rn(ce[1], A))), sq(__dsub_rn(ce[2], B))));
-                const double ds = __dsqrt_rn(__dadd_rn(sq(__dsub_rn(cx, (double)x)), sq(__dsub_rn(cy, (double)y))));
-                const double d = __dsqrt_rn(__dadd_rn(sq(__ddiv_rn(dc, (double)nc)), sq(__ddiv_rn(ds, (double)step))));  // ns = step (:105)
-                if (d < best || (d == best && best_c >= 0 && c < best_c)) { best = d; best_c = c; }
+                const int pos = atomicAdd(&s_n, 1);
+                if (pos < kCap) {
+                    const int c = items[k];
+                    s_idx[pos] = c;
+                    for (int q = 0; q < 5; ++q) s_cent[pos][q] = centers[(size_t)c * 5 + q];
+                }
             }
         }
-    int label = labels[(size_t)y * cols + x];
-    if (best_c >= 0) {
-        label = best_c;
-        labels[(size_t)y * cols + x] = label;
     }
-    if (label != -1) {
-        unsigned long long* s = sums + (size_t)label * 6;
-        atomicAdd(s + 0, (unsigned long long)p[0]);
-        atomicAdd(s + 1, (unsigned long long)p[1]);
-        atomicAdd(s + 2, (unsigned long long)p[2]);
-        atomicAdd(s + 3, (unsigned long long)x);
-        atomicAdd(s + 4, (unsigned long long)y);
-        atomicAdd(s + 5, 1ull);
+    __syncthreads();
+    const int n_cand = s_n;
+    const bool staged = n_cand <= kCap;  // otherwise (pathological clustering of centres) fall back to the bins in global memory
+    const bool live = x < cols && y < rows;  // lanes beyond the image stay for the warp collectives
+    const uint8_t* p = lab + ((size_t)(live ? y : 0) * cols + (live ? x : 0)) * 3;
+    const double L = p[0], A = p[1], B = p[2];
+    const int pbx = x / step < bx ? x / step : bx - 1, pby = y / step < by ? y / step : by - 1;
+    // Two stages.  (1) A cheap, monotone stand-in for compute_dist without square roots or divisions,
+    //       D' = Sc / nc^2 + Ss / ns^2  (the reference's distance is sqrt of exactly that, up to ~1e-15 relative rounding),
+    //     finds the winner whenever it beats the runner-up by more than 1e-12 relative: no rounding of the reference's own
+    //     chain (three sqrt, two divisions, three squarings, each within 2^-53) can reverse such a margin.
+    //     (2) Otherwise -- exact ties on symmetric pixels, near ties -- the candidates are re-evaluated with the
+    //     reference's exact operation sequence and its tie rule (strict <, lowest centre index).  Same labels, ~4x less work.
+    const double inv_nc2 = 1.0 / ((double)nc * (double)nc), inv_ns2 = 1.0 / ((double)step * (double)step);
+    double q1 = 1.0e300, q2 = 1.0e300;  // smallest and second smallest D'
+    int best_c = -1, best_i = -1;     // winning centre and its slot in the staged list
+    const int gy_lo = max(pby - 1, 0), gy_hi = min(pby + 1, by - 1), gx_lo = max(pbx - 1, 0), gx_hi = min(pbx + 1, bx - 1);
+    auto covers = [&](double cx, double cy) {
+        // for (int k = cx - step; k < cx + step; k++) (:123): truncation towards zero, then a double comparison
+        return !(x < (int)__dsub_rn(cx, (double)step) || !((double)x < __dadd_rn(cx, (double)step)) ||
+                 y < (int)__dsub_rn(cy, (double)step) || !((double)y < __dadd_rn(cy, (double)step)));
+    };
+    auto cheap = [&](const double* ce, int c, int slot) {
+        const double cx = ce[3], cy = ce[4];
+        if (!covers(cx, cy)) return;
+        const double d0 = ce[0] - L, d1 = ce[1] - A, d2 = ce[2] - B, dx = cx - (double)x, dy = cy - (double)y;
+        const double q = (d0 * d0 + d1 * d1 + d2 * d2) * inv_nc2 + (dx * dx + dy * dy) * inv_ns2;
+        if (q < q1 || (q == q1 && c < best_c)) { q2 = q1; q1 = q; best_c = c; best_i = slot; }
+        else if (q < q2) q2 = q;
+    };
+    if (staged) {
+        for (int i = 0; i < n_cand; ++i) cheap(s_cent[i], s_idx[i], i);
+    } else {
+        for (int gy = gy_lo; gy <= gy_hi; ++gy)
+            for (int gx = gx_lo; gx <= gx_hi; ++gx) {
+                const int b = gy * bx + gx;
+                for (int k = offset[b]; k < offset[b + 1]; ++k) cheap(centers + (size_t)items[k] * 5, items[k], -1);
+            }
     }
+    if (best_c >= 0 && !(q2 > q1 * (1.0 + 1.0e-12))) {
+        // too close to call: the reference's own arithmetic decides
+        double best = (double)FLT_MAX;  // :117
+        best_c = -1;
+        best_i = -1;
+        auto exact = [&](const double* ce, int c, int slot) {
+            const double cx = ce[3], cy = ce[4];
+            if (!covers(cx, cy)) return;
+            const double dc = __dsqrt_rn(__dadd_rn(__dadd_rn(sq(__dsub_rn(ce[0], L)), sq(__dsub_rn(ce[1], A))), sq(__dsub_rn(ce[2], B))));
+            const double ds = __dsqrt_rn(__dadd_rn(sq(__dsub_rn(cx, (double)x)), sq(__dsub_rn(cy, (double)y))));
+            const double d = __dsqrt_rn(__dadd_rn(sq(__ddiv_rn(dc, (double)nc)), sq(__ddiv_rn(ds, (double)step))));  // ns = step (:105)
+            if (d < best || (d == best && best_c >= 0 && c < best_c)) { best = d; best_c = c; best_i = slot; }
+        };
+        if (staged) {
+            for (int i = 0; i < n_cand; ++i) exact(s_cent[i], s_idx[i], i);
+        } else {
+            for (int gy = gy_lo; gy <= gy_hi; ++gy)
+                for (int gx = gx_lo; gx <= gx_hi; ++gx) {
+                    const int b = gy * bx + gx;
+                    for (int k = offset[b]; k < offset[b + 1]; ++k) exact(centers + (size_t)items[k] * 5, items[k], -1);
+                }
+        }
+    }
+    int label = -1;
+    if (live) {
+        label = labels[(size_t)y * cols + x];
+        if (best_c >= 0) {
+            label = best_c;
+            labels[(size_t)y * cols + x] = label;
+        }
+    }
+    // centre sums (integers: exact in any order).  Pixels that were (re)assigned to a staged centre add into the tile's
+    // shared-memory sums, flushed with one global atomic per centre and field at the end -- same-address global atomics
+    // were the bottleneck (357 serialised updates per address and iteration).  Pixels keeping a stale label add directly.
+    if (live && label != -1) {
+        if (best_c >= 0 && best_i >= 0) {
+            atomicAdd(&s_sum[best_i][0], (unsigned)p[0]);
+            atomicAdd(&s_sum[best_i][1], (unsigned)p[1]);
+            atomicAdd(&s_sum[best_i][2], (unsigned)p[2]);
+            atomicAdd(&s_sum[best_i][3], (unsigned)x);
+            atomicAdd(&s_sum[best_i][4], (unsigned)y);
+            atomicAdd(&s_sum[best_i][5], 1u);
+        } else {
+            unsigned long long* sg = sums + (size_t)label * 6;
+            atomicAdd(sg + 0, (unsigned long long)p[0]);
+            atomicAdd(sg + 1, (unsigned long long)p[1]);
+            atomicAdd(sg + 2, (unsigned long long)p[2]);
+            atomicAdd(sg + 3, (unsigned long long)x);
+            atomicAdd(sg + 4, (unsigned long long)y);
+            atomicAdd(sg + 5, 1ull);
+        }
+    }
+    __syncthreads();
+    if (staged)
+        for (int i = tid; i < n_cand * 6; i += 256) {
+            const int slot = i / 6, k = i - slot * 6;
+            const unsigned v = s_sum[slot][k];
+            if (v) atomicAdd(sums + (size_t)s_idx[slot] * 6 + k, (unsigned long long)v);
+        }
 }
 
 __global__ void k_slic_update(const unsigned long long* __restrict__ sums, int n, double* __restrict__ centers) {  // :166-172
@@ -179,20 +271,17 @@ cudaError_t slic_run(const uint8_t* lab, int rows, int cols, int step, int nc, i
     int nx, ny;
     slic_grid(rows, cols, step, &nx, &ny);
     const size_t npx = (size_t)rows * cols;
-    const int nbins = w.bins_x * w.bins_y;
     const unsigned cb = (unsigned)((n_centers + 127) / 128);
     DCMT_LAUNCH(k_slic_fill_labels, dim3((unsigned)((npx + 255) / 256)), dim3(256), 0, st, labels, npx);
     if (n_centers == 0) return cudaGetLastError();
     DCMT_LAUNCH(k_slic_init, dim3(cb), dim3(128), 0, st, lab, rows, cols, step, ny, n_centers, w.centers);
     for (int it = 0; it < iterations; ++it) {
-        DCMT_LAUNCH(k_slic_clear_counts, dim3((nbins + 1 + 255) / 256), dim3(256), 0, st, w.bin_count, nbins + 1);
-        DCMT_LAUNCH(k_slic_bin_count, dim3(cb), dim3(128), 0, st, w.centers, n_centers, step, w.bins_x, w.bins_y, w.bin_count, w.sums);
-        DCMT_LAUNCH(k_slic_bin_scan, dim3(1), dim3(kScanThreads), 0, st, w.bin_count, w.bin_fill, nbins);
-        DCMT_LAUNCH(k_slic_bin_fill, dim3(cb), dim3(128), 0, st, w.centers, n_centers, step, w.bins_x, w.bins_y, w.bin_count, w.bin_fill, w.bin_items);
-        DCMT_LAUNCH(k_slic_assign, dim3((cols + 255) / 256, rows), dim3(256), 0, st, lab, rows, cols, step, nc, w.bins_x, w.bins_y, w.centers,
-                    w.bin_count, w.bin_items, labels, w.sums);
-        DCMT_LAUNCH(k_slic_update, dim3(cb), dim3(128), 0, st, w.sums, n_centers, w.centers);
+        DCMT_LAUNCH(k_slic_prepare, dim3(1), dim3(kScanThreads), 0, st, w.centers, w.sums, n_centers, step, w.bins_x, w.bins_y, w.bin_count,
+                    w.bin_fill, w.bin_items, it > 0 ? 1 : 0);
+        DCMT_LAUNCH(k_slic_assign, dim3((cols + 15) / 16, (rows + 15) / 16), dim3(16, 16), 0, st, lab, rows, cols, step, nc, w.bins_x, w.bins_y,
+                    w.centers, w.bin_count, w.bin_items, labels, w.sums);
     }
+    if (iterations > 0) DCMT_LAUNCH(k_slic_update, dim3(cb), dim3(128), 0, st, w.sums, n_centers, w.centers);
     return cudaGetLastError();
 }
 
