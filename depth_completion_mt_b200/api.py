@@ -401,33 +401,34 @@ def generate_superpixels(lab_image, step, nc: int, *, iterations: int = 10, retu
                          lib: _lib.Library | None = None):
     """Slic::generate_superpixels(lab_image, step, nc), slic.cpp:101-182.
 
-    ``lab_image`` is (rows, cols, 3) uint8 after COLOR_BGR2Lab; ``step`` is truncated to int like the reference's int
-    parameter (main_lc.cpp:197-201 passes a double).  Returns the label map ``Slic::clusters`` as int32 [row][col]
-    (-1 = never assigned) and, optionally, ``Slic::centers`` (K, 5) float64.  ``K = len(centers)`` is the ``n_clusters``
-    argument of interpolate_with_superpixels."""
+    ``lab_image`` is (rows, cols, 3) or a batch (n, rows, cols, 3) uint8 after COLOR_BGR2Lab; ``step`` is truncated to int
+    like the reference's int parameter (main_lc.cpp:197-201 passes a double).  Returns the label map ``Slic::clusters`` as
+    int32 [row][col] (-1 = never assigned) and, optionally, ``Slic::centers`` (K, 5) float64 (with a leading batch
+    dimension for a batch).  ``K = len(centers)`` is the ``n_clusters`` argument of interpolate_with_superpixels."""
     lib = lib or _lib.load()
     step = int(step)
-    if _is_torch(lab_image):
-        lab = _prep_torch(lab_image, torch.uint8, "lab_image")
-        if lab.ndim != 3 or lab.shape[2] != 3:
-            raise ValueError("lab_image must be (rows, cols, 3)")
-        rows, cols = int(lab.shape[0]), int(lab.shape[1])
-        k = lib.dcmt_slic_center_count(rows, cols, step)
-        labels = torch.empty((rows, cols), dtype=torch.int32, device=lab.device)
-        centers = torch.empty((max(k, 1), 5), dtype=torch.float64, device=lab.device)
-        with torch.cuda.device(lab.device):
-            lib.check(lib.dcmt_slic_u8c3(lab.data_ptr(), rows, cols, step, int(nc), int(iterations), labels.data_ptr(), centers.data_ptr(),
-                                         _stream_ptr(stream)))
-        return (labels, centers[:k]) if return_centers else labels
-    lab = _prep_numpy(lab_image, np.uint8, "lab_image")
-    if lab.ndim != 3 or lab.shape[2] != 3:
-        raise ValueError("lab_image must be (rows, cols, 3)")
-    rows, cols = lab.shape[:2]
+    is_t = _is_torch(lab_image)
+    lab = _prep_torch(lab_image, torch.uint8, "lab_image") if is_t else _prep_numpy(lab_image, np.uint8, "lab_image")
+    if lab.ndim not in (3, 4) or lab.shape[-1] != 3:
+        raise ValueError("lab_image must be (rows, cols, 3) or (n, rows, cols, 3)")
+    squeeze = lab.ndim == 3
+    n = 1 if squeeze else int(lab.shape[0])
+    rows, cols = int(lab.shape[-3]), int(lab.shape[-2])
     k = lib.dcmt_slic_center_count(rows, cols, step)
-    labels = np.empty((rows, cols), np.int32)
-    centers = np.empty((max(k, 1), 5), np.float64)
-    lib.check(lib.dcmt_slic_u8c3_host(_np_ptr(lab), rows, cols, step, int(nc), int(iterations), _np_ptr(labels), _np_ptr(centers)))
-    return (labels, centers[:k]) if return_centers else labels
+    if is_t:
+        labels = torch.empty((n, rows, cols), dtype=torch.int32, device=lab.device)
+        centers = torch.empty((n, max(k, 1), 5), dtype=torch.float64, device=lab.device)
+        with torch.cuda.device(lab.device):
+            lib.check(lib.dcmt_slic_u8c3(lab.data_ptr(), rows, cols, n, step, int(nc), int(iterations), labels.data_ptr(),
+                                         centers.data_ptr(), _stream_ptr(stream)))
+    else:
+        labels = np.empty((n, rows, cols), np.int32)
+        centers = np.empty((n, max(k, 1), 5), np.float64)
+        lib.check(lib.dcmt_slic_u8c3_host(_np_ptr(lab), rows, cols, n, step, int(nc), int(iterations), _np_ptr(labels), _np_ptr(centers)))
+    centers = centers[:, :k]
+    if squeeze:
+        labels, centers = labels[0], centers[0]
+    return (labels, centers) if return_centers else labels
 
 
 # ---------------------------------------------------------------------------------------------- raw Mat files (8f #4)

@@ -804,51 +804,56 @@ int dcmt_slic_center_count(int rows, int cols, int step) {
     return dcmt::slic_center_count(rows, cols, step);
 }
 
-int dcmt_slic_u8c3(const uint8_t* lab, int rows, int cols, int step, int nc, int iterations, int32_t* labels, double* centers,
-                   void* cuda_stream) {
+int dcmt_slic_u8c3(const uint8_t* lab, int rows, int cols, int n_frames, int step, int nc, int iterations, int32_t* labels,
+                   double* centers, void* cuda_stream) {
     if (!lab || !labels) return fail(DCMT_E_BADARG, "null pointer");
-    int rc = check_planes(rows, cols, 1);
+    int rc = check_planes(rows, cols, n_frames);
     if (rc) return rc;
     if (nc == 0 || iterations < 0) return fail(DCMT_E_BADARG, "nc %d, iterations %d", nc, iterations);
     if (step < 4) return fail(DCMT_E_UNSUPPORTED, "step %d: find_local_minimum (slic.cpp:72-99) reads outside the image below 4", step);
     if (rows >= 1 << 24 || cols >= 1 << 24) return fail(DCMT_E_UNSUPPORTED, "SLIC frames are limited to 2^24 rows / columns");
     if ((size_t)rows * (size_t)cols > (size_t)1 << 30) return fail(DCMT_E_UNSUPPORTED, "frame larger than 2^30 pixels");
+    if (n_frames > 65535) return fail(DCMT_E_UNSUPPORTED, "at most 65535 frames per call");
+    if (n_frames == 0) return DCMT_OK;
     if ((rc = check_device())) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     const int k = dcmt::slic_center_count(rows, cols, step);
     dcmt::SlicWork w{};
     const size_t nbins = dcmt::slic_bins(rows, cols, step, &w.bins_x, &w.bins_y);
-    const size_t kk = k > 0 ? (size_t)k : 1;
+    const size_t kk = (k > 0 ? (size_t)k : 1) * n_frames, nb = nbins * n_frames;
     Arena* ar = nullptr;
-    if ((rc = arena_acquire(st, carve_bytes(kk * 5, sizeof(double)) + carve_bytes(kk * 6, sizeof(unsigned long long)) +
-                                    carve_bytes(nbins + 1, sizeof(int)) + carve_bytes(nbins, sizeof(int)) + carve_bytes(kk, sizeof(int)),
+    if ((rc = arena_acquire(st, 2 * carve_bytes(kk * 5, sizeof(double)) + carve_bytes(kk * 6, sizeof(unsigned long long)) +
+                                    carve_bytes(nb + n_frames, sizeof(int)) + carve_bytes(nb, sizeof(int)) + carve_bytes(kk, sizeof(int)),
                             &ar)))
         return rc;
     w.centers = carve<double>(ar, kk * 5);
     w.sums = carve<unsigned long long>(ar, kk * 6);
-    w.bin_count = carve<int>(ar, nbins + 1);
-    w.bin_fill = carve<int>(ar, nbins);
+    w.bin_count = carve<int>(ar, nb + n_frames);
+    w.bin_fill = carve<int>(ar, nb);
     w.bin_items = carve<int>(ar, kk);
-    API_CUDA(dcmt::slic_run(lab, rows, cols, step, nc, iterations, labels, k, w, st), "SLIC launch");
+    w.sorted = carve<double>(ar, kk * 5);
+    API_CUDA(dcmt::slic_run(lab, rows, cols, n_frames, step, nc, iterations, labels, k, w, st), "SLIC launch");
     if (centers && k > 0)
-        API_CUDA(cudaMemcpyAsync(centers, w.centers, (size_t)k * 5 * sizeof(double), cudaMemcpyDeviceToDevice, st), "centre copy");
+        API_CUDA(cudaMemcpyAsync(centers, w.centers, (size_t)k * n_frames * 5 * sizeof(double), cudaMemcpyDeviceToDevice, st), "centre copy");
     return DCMT_OK;
 }
 
-int dcmt_slic_u8c3_host(const uint8_t* lab, int rows, int cols, int step, int nc, int iterations, int32_t* labels, double* centers) {
+int dcmt_slic_u8c3_host(const uint8_t* lab, int rows, int cols, int n_frames, int step, int nc, int iterations, int32_t* labels,
+                        double* centers) {
     if (!lab || !labels) return fail(DCMT_E_BADARG, "null pointer");
-    int rc = check_planes(rows, cols, 1);
+    int rc = check_planes(rows, cols, n_frames);
     if (rc) return rc;
+    if (n_frames == 0) return DCMT_OK;
     if ((rc = check_device())) return rc;
-    const size_t n = (size_t)rows * cols;
-    const int k = step >= 1 ? dcmt::slic_center_count(rows, cols, step) : 0;
+    const size_t n = (size_t)rows * cols * n_frames;
+    const size_t k = (size_t)(step >= 1 ? dcmt::slic_center_count(rows, cols, step) : 0) * n_frames;
     uint8_t* d_lab = nullptr;
     int32_t* d_labels = nullptr;
     double* d_centers = nullptr;
     auto cleanup = [&] { cudaFree(d_lab); cudaFree(d_labels); cudaFree(d_centers); };
     cudaError_t e;
     if ((e = cudaMalloc(&d_lab, n * 3)) != cudaSuccess || (e = cudaMalloc(&d_labels, n * 4)) != cudaSuccess ||
-        (e = cudaMalloc(&d_centers, (size_t)(k > 0 ? k : 1) * 5 * sizeof(double))) != cudaSuccess) {
+        (e = cudaMalloc(&d_centers, (k > 0 ? k : 1) * 5 * sizeof(double))) != cudaSuccess) {
         cleanup();
         return fail(DCMT_E_NOMEM, "device staging buffers: %s", cudaGetErrorString(e));
     }
@@ -856,11 +861,11 @@ int dcmt_slic_u8c3_host(const uint8_t* lab, int rows, int cols, int step, int nc
         cleanup();
         return cuda_fail(e, "host to device copy");
     }
-    rc = dcmt_slic_u8c3(d_lab, rows, cols, step, nc, iterations, d_labels, centers ? d_centers : nullptr, nullptr);
+    rc = dcmt_slic_u8c3(d_lab, rows, cols, n_frames, step, nc, iterations, d_labels, centers ? d_centers : nullptr, nullptr);
     if (rc == DCMT_OK) {
         if ((e = cudaStreamSynchronize(nullptr)) != cudaSuccess) rc = cuda_fail(e, "kernel execution");
         else if ((e = cudaMemcpy(labels, d_labels, n * 4, cudaMemcpyDeviceToHost)) != cudaSuccess) rc = cuda_fail(e, "device to host copy");
-        else if (centers && k > 0 && (e = cudaMemcpy(centers, d_centers, (size_t)k * 5 * sizeof(double), cudaMemcpyDeviceToHost)) != cudaSuccess)
+        else if (centers && k > 0 && (e = cudaMemcpy(centers, d_centers, k * 5 * sizeof(double), cudaMemcpyDeviceToHost)) != cudaSuccess)
             rc = cuda_fail(e, "device to host copy");
     }
     cleanup();

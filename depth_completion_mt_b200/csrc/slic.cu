@@ -22,6 +22,8 @@ __device__ __forceinline__ double sq(double x) { return __dmul_rn(x, x); }
 __global__ void k_slic_init(const uint8_t* __restrict__ lab, int rows, int cols, int step, int ny, int n, double* __restrict__ centers) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n) return;
+    lab += (size_t)blockIdx.y * rows * cols * 3;  // frame
+    centers += (size_t)blockIdx.y * n * 5;
     // centres are created column by column: i = step, 2 step, ... (outer), j = step, 2 step, ... (inner)  (:33-34)
     const int ci = c / ny, cj = c - ci * ny;
     const int cx = step + ci * step, cy = step + cj * step;
@@ -55,9 +57,18 @@ constexpr int kScanThreads = 1024;
 // step-sized grid (count, exclusive scan, fill).  Five tiny dependent launches per iteration were 40 % of the run time.
 __global__ void __launch_bounds__(kScanThreads) k_slic_prepare(double* __restrict__ centers, unsigned long long* __restrict__ sums, int n,
                                                               int step, int bx, int by, int* __restrict__ count, int* __restrict__ fill,
-                                                              int* __restrict__ items, int do_update) {
+                                                              int* __restrict__ items, double* __restrict__ sorted, int do_update) {
     __shared__ int part[kScanThreads];
     const int nbins = bx * by;
+    {  // one block per frame
+        const size_t f = blockIdx.x;
+        centers += f * n * 5;
+        sums += f * n * 6;
+        count += f * (nbins + 1);
+        fill += f * nbins;
+        items += f * n;
+        sorted += f * n * 5;
+    }
     for (int c = threadIdx.x; c < n; c += kScanThreads) {
         if (do_update) {
             const double cnt = (double)sums[(size_t)c * 6 + 5];
@@ -65,18 +76,26 @@ __global__ void __launch_bounds__(kScanThreads) k_slic_prepare(double* __restric
         }
         for (int k = 0; k < 6; ++k) sums[(size_t)c * 6 + k] = 0ull;
     }
-    for (int b = threadIdx.x; b <= nbins; b += kScanThreads) count[b] = 0;
+    // bin counts / offsets / fill cursors live in shared memory when the grid of bins fits (it does up to 5120 bins);
+    // only the finished offsets, the items and the bin-ordered centres go to global memory
+    constexpr int kSmemBins = 5120;
+    __shared__ int s_count[kSmemBins + 1];
+    __shared__ int s_fill[kSmemBins];
+    const bool in_smem = nbins <= kSmemBins;
+    int* cnt = in_smem ? s_count : count;
+    int* fil = in_smem ? s_fill : fill;
+    for (int b = threadIdx.x; b <= nbins; b += kScanThreads) cnt[b] = 0;
     __syncthreads();
     for (int c = threadIdx.x; c < n; c += kScanThreads) {
         const double x = centers[(size_t)c * 5 + 3], y = centers[(size_t)c * 5 + 4];
         if (x != x || y != y) continue;  // NaN centre (empty cluster): covers nothing
-        atomicAdd(count + bin_of(y, step, by) * bx + bin_of(x, step, bx), 1);
+        atomicAdd(cnt + bin_of(y, step, by) * bx + bin_of(x, step, bx), 1);
     }
     __syncthreads();
     const int chunk = (nbins + kScanThreads - 1) / kScanThreads;
     const int b0 = threadIdx.x * chunk, b1 = min(b0 + chunk, nbins);
     int total = 0;
-    for (int b = b0; b < b1; ++b) total += count[b];
+    for (int b = b0; b < b1; ++b) total += cnt[b];
     part[threadIdx.x] = total;
     __syncthreads();
     for (int d = 1; d < kScanThreads; d <<= 1) {
@@ -87,34 +106,51 @@ __global__ void __launch_bounds__(kScanThreads) k_slic_prepare(double* __restric
     }
     int acc = part[threadIdx.x] - total;
     for (int b = b0; b < b1; ++b) {
-        const int c = count[b];
-        count[b] = acc;
-        fill[b] = 0;
+        const int c = cnt[b];
+        cnt[b] = acc;
+        fil[b] = 0;
         acc += c;
     }
-    if (threadIdx.x == kScanThreads - 1) count[nbins] = part[kScanThreads - 1];
+    if (threadIdx.x == kScanThreads - 1) cnt[nbins] = part[kScanThreads - 1];
     __syncthreads();
+    if (in_smem)
+        for (int b = threadIdx.x; b <= nbins; b += kScanThreads) count[b] = cnt[b];
     for (int c = threadIdx.x; c < n; c += kScanThreads) {
         const double x = centers[(size_t)c * 5 + 3], y = centers[(size_t)c * 5 + 4];
         if (x != x || y != y) continue;
         const int b = bin_of(y, step, by) * bx + bin_of(x, step, bx);
-        items[count[b] + atomicAdd(fill + b, 1)] = c;
+        const int pos = cnt[b] + atomicAdd(fil + b, 1);
+        items[pos] = c;
+        for (int k = 0; k < 5; ++k) sorted[(size_t)pos * 5 + k] = centers[(size_t)c * 5 + k];  // bin order: the assignment reads them in one hop
     }
 }
 
 // assignment (:121-139) + accumulation of the new centres (:148-163), one thread per pixel
 __global__ void __launch_bounds__(256) k_slic_assign(const uint8_t* __restrict__ lab, int rows, int cols, int step, int nc, int bx, int by,
                                                      const double* __restrict__ centers, const int* __restrict__ offset,
-                                                     const int* __restrict__ items, int32_t* __restrict__ labels,
-                                                     unsigned long long* __restrict__ sums) {
+                                                     const int* __restrict__ items, const double* __restrict__ sorted,
+                                                     int32_t* __restrict__ labels, unsigned long long* __restrict__ sums, int n_centers,
+                                                     double inv_nc2, double inv_ns2) {
     // a block is a 16 x 16 pixel tile: the centres that can cover any of its pixels sit in the bins around it; they are
     // staged in shared memory once (the per-pixel loops below would otherwise chase offset -> item -> centre through
     // global memory: the kernel was bound by that latency, 18 % issue-active)
     constexpr int kCap = 96;
     __shared__ double s_cent[kCap][5];
+    __shared__ double s_hi[kCap][2];  // cx + step, cy + step: the window's open upper ends (:123-124)
+    __shared__ int s_lo[kCap][2];     // (int)(cx - step), (int)(cy - step): its first column / row
     __shared__ int s_idx[kCap];
     __shared__ unsigned s_sum[kCap][6];  // per-tile sums of L, a, b, x, y, count for the staged centres
     __shared__ int s_n;
+    {  // frame
+        const size_t f = blockIdx.z;
+        lab += f * rows * cols * 3;
+        labels += f * rows * cols;
+        centers += f * n_centers * 5;
+        sums += f * n_centers * 6;
+        offset += f * (bx * by + 1);
+        items += f * n_centers;
+        sorted += f * n_centers * 5;
+    }
     const int tid = threadIdx.y * 16 + threadIdx.x;
     const int x = blockIdx.x * 16 + threadIdx.x, y = blockIdx.y * 16 + threadIdx.y;
     if (tid == 0) s_n = 0;
@@ -124,14 +160,23 @@ __global__ void __launch_bounds__(256) k_slic_assign(const uint8_t* __restrict__
         const int bx0 = max((int)(blockIdx.x * 16) / step - 1, 0), bx1 = min((int)(blockIdx.x * 16 + 15) / step + 1, bx - 1);
         const int by0 = max((int)(blockIdx.y * 16) / step - 1, 0), by1 = min((int)(blockIdx.y * 16 + 15) / step + 1, by - 1);
         const int nbx = bx1 - bx0 + 1, nb = nbx * (by1 - by0 + 1);
-        for (int i = tid; i < nb; i += 256) {
+        // 16 threads per bin (at most 16 bins around a 16 x 16 tile for step >= 16; more bins loop): thread j of a bin
+        // copies its j-th centre, so the global loads of all candidates are in flight together
+        for (int i = tid >> 4; i < nb; i += 16) {
             const int b = (by0 + i / nbx) * bx + bx0 + i % nbx;
-            for (int k = offset[b]; k < offset[b + 1]; ++k) {
+            const int o0 = offset[b], o1 = offset[b + 1];
+            for (int k = o0 + (tid & 15); k < o1; k += 16) {
                 const int pos = atomicAdd(&s_n, 1);
                 if (pos < kCap) {
-                    const int c = items[k];
-                    s_idx[pos] = c;
-                    for (int q = 0; q < 5; ++q) s_cent[pos][q] = centers[(size_t)c * 5 + q];
+                    s_idx[pos] = items[k];
+                    double ce[5];
+                    for (int q = 0; q < 5; ++q) ce[q] = sorted[(size_t)k * 5 + q];
+                    for (int q = 0; q < 5; ++q) s_cent[pos][q] = ce[q];
+                    // for (int k = cx - step; k < cx + step; k++) (:123): truncation towards zero, then a double comparison
+                    s_lo[pos][0] = (int)__dsub_rn(ce[3], (double)step);
+                    s_lo[pos][1] = (int)__dsub_rn(ce[4], (double)step);
+                    s_hi[pos][0] = __dadd_rn(ce[3], (double)step);
+                    s_hi[pos][1] = __dadd_rn(ce[4], (double)step);
                 }
             }
         }
@@ -149,7 +194,7 @@ __global__ void __launch_bounds__(256) k_slic_assign(const uint8_t* __restrict__
     //     chain (three sqrt, two divisions, three squarings, each within 2^-53) can reverse such a margin.
     //     (2) Otherwise -- exact ties on symmetric pixels, near ties -- the candidates are re-evaluated with the
     //     reference's exact operation sequence and its tie rule (strict <, lowest centre index).  Same labels, ~4x less work.
-    const double inv_nc2 = 1.0 / ((double)nc * (double)nc), inv_ns2 = 1.0 / ((double)step * (double)step);
+    const double xd = (double)x, yd = (double)y;
     double q1 = 1.0e300, q2 = 1.0e300;  // smallest and second smallest D'
     int best_c = -1, best_i = -1;     // winning centre and its slot in the staged list
     const int gy_lo = max(pby - 1, 0), gy_hi = min(pby + 1, by - 1), gx_lo = max(pbx - 1, 0), gx_hi = min(pbx + 1, bx - 1);
@@ -160,8 +205,8 @@ __global__ void __launch_bounds__(256) k_slic_assign(const uint8_t* __restrict__
     };
     auto cheap = [&](const double* ce, int c, int slot) {
         const double cx = ce[3], cy = ce[4];
-        if (!covers(cx, cy)) return;
-        const double d0 = ce[0] - L, d1 = ce[1] - A, d2 = ce[2] - B, dx = cx - (double)x, dy = cy - (double)y;
+        if (slot >= 0 ? (x < s_lo[slot][0] || !(xd < s_hi[slot][0]) || y < s_lo[slot][1] || !(yd < s_hi[slot][1])) : !covers(cx, cy)) return;
+        const double d0 = ce[0] - L, d1 = ce[1] - A, d2 = ce[2] - B, dx = cx - xd, dy = cy - yd;
         const double q = (d0 * d0 + d1 * d1 + d2 * d2) * inv_nc2 + (dx * dx + dy * dy) * inv_ns2;
         if (q < q1 || (q == q1 && c < best_c)) { q2 = q1; q1 = q; best_c = c; best_i = slot; }
         else if (q < q2) q2 = q;
@@ -182,7 +227,7 @@ __global__ void __launch_bounds__(256) k_slic_assign(const uint8_t* __restrict__
         best_i = -1;
         auto exact = [&](const double* ce, int c, int slot) {
             const double cx = ce[3], cy = ce[4];
-            if (!covers(cx, cy)) return;
+            if (slot >= 0 ? (x < s_lo[slot][0] || !(xd < s_hi[slot][0]) || y < s_lo[slot][1] || !(yd < s_hi[slot][1])) : !covers(cx, cy)) return;
             const double dc = __dsqrt_rn(__dadd_rn(__dadd_rn(sq(__dsub_rn(ce[0], L)), sq(__dsub_rn(ce[1], A))), sq(__dsub_rn(ce[2], B))));
             const double ds = __dsqrt_rn(__dadd_rn(sq(__dsub_rn(cx, (double)x)), sq(__dsub_rn(cy, (double)y))));
             const double d = __dsqrt_rn(__dadd_rn(sq(__ddiv_rn(dc, (double)nc)), sq(__ddiv_rn(ds, (double)step))));  // ns = step (:105)
@@ -209,15 +254,29 @@ __global__ void __launch_bounds__(256) k_slic_assign(const uint8_t* __restrict__
     // centre sums (integers: exact in any order).  Pixels that were (re)assigned to a staged centre add into the tile's
     // shared-memory sums, flushed with one global atomic per centre and field at the end -- same-address global atomics
     // were the bottleneck (357 serialised updates per address and iteration).  Pixels keeping a stale label add directly.
-    if (live && label != -1) {
-        if (best_c >= 0 && best_i >= 0) {
-            atomicAdd(&s_sum[best_i][0], (unsigned)p[0]);
-            atomicAdd(&s_sum[best_i][1], (unsigned)p[1]);
-            atomicAdd(&s_sum[best_i][2], (unsigned)p[2]);
-            atomicAdd(&s_sum[best_i][3], (unsigned)x);
-            atomicAdd(&s_sum[best_i][4], (unsigned)y);
-            atomicAdd(&s_sum[best_i][5], 1u);
-        } else {
+    // a warp is 2 x 16 neighbouring pixels with one to three distinct winners: reduce per winner with the hardware warp
+    // reduction and let one lane add to shared memory (32 lanes hitting one shared-memory address serialise)
+    {
+        const int key = (live && label != -1 && best_c >= 0 && best_i >= 0) ? best_i : -1;
+        unsigned todo = __ballot_sync(0xffffffffu, key >= 0);
+        while (todo) {
+            const int leader = __ffs((int)todo) - 1;
+            const int k0 = __shfl_sync(0xffffffffu, key, leader);
+            const bool mine = key == k0;
+            const unsigned v0 = __reduce_add_sync(0xffffffffu, mine ? (unsigned)p[0] : 0u), v1 = __reduce_add_sync(0xffffffffu, mine ? (unsigned)p[1] : 0u),
+                           v2 = __reduce_add_sync(0xffffffffu, mine ? (unsigned)p[2] : 0u), v3 = __reduce_add_sync(0xffffffffu, mine ? (unsigned)x : 0u),
+                           v4 = __reduce_add_sync(0xffffffffu, mine ? (unsigned)y : 0u), v5 = __reduce_add_sync(0xffffffffu, mine ? 1u : 0u);
+            if ((tid & 31) == leader) {
+                atomicAdd(&s_sum[k0][0], v0);
+                atomicAdd(&s_sum[k0][1], v1);
+                atomicAdd(&s_sum[k0][2], v2);
+                atomicAdd(&s_sum[k0][3], v3);
+                atomicAdd(&s_sum[k0][4], v4);
+                atomicAdd(&s_sum[k0][5], v5);
+            }
+            todo &= ~__ballot_sync(0xffffffffu, mine);
+        }
+        if (live && label != -1 && key < 0) {  // a stale label (no window covers the pixel) or the unstaged fallback
             unsigned long long* sg = sums + (size_t)label * 6;
             atomicAdd(sg + 0, (unsigned long long)p[0]);
             atomicAdd(sg + 1, (unsigned long long)p[1]);
@@ -239,6 +298,8 @@ __global__ void __launch_bounds__(256) k_slic_assign(const uint8_t* __restrict__
 __global__ void k_slic_update(const unsigned long long* __restrict__ sums, int n, double* __restrict__ centers) {  // :166-172
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n) return;
+    sums += (size_t)blockIdx.y * n * 6;  // frame
+    centers += (size_t)blockIdx.y * n * 5;
     const double cnt = (double)sums[(size_t)c * 6 + 5];
     for (int k = 0; k < 5; ++k) centers[(size_t)c * 5 + k] = __ddiv_rn((double)sums[(size_t)c * 6 + k], cnt);
 }
@@ -266,22 +327,23 @@ size_t slic_bins(int rows, int cols, int step, int* bins_x, int* bins_y) {
     return (size_t)*bins_x * *bins_y;
 }
 
-cudaError_t slic_run(const uint8_t* lab, int rows, int cols, int step, int nc, int iterations, int32_t* labels, int n_centers,
-                     const SlicWork& w, cudaStream_t st) {
+cudaError_t slic_run(const uint8_t* lab, int rows, int cols, int n_frames, int step, int nc, int iterations, int32_t* labels,
+                     int n_centers, const SlicWork& w, cudaStream_t st) {
     int nx, ny;
     slic_grid(rows, cols, step, &nx, &ny);
-    const size_t npx = (size_t)rows * cols;
+    const size_t npx = (size_t)rows * cols * n_frames;
     const unsigned cb = (unsigned)((n_centers + 127) / 128);
     DCMT_LAUNCH(k_slic_fill_labels, dim3((unsigned)((npx + 255) / 256)), dim3(256), 0, st, labels, npx);
-    if (n_centers == 0) return cudaGetLastError();
-    DCMT_LAUNCH(k_slic_init, dim3(cb), dim3(128), 0, st, lab, rows, cols, step, ny, n_centers, w.centers);
+    if (n_centers == 0 || n_frames == 0) return cudaGetLastError();
+    DCMT_LAUNCH(k_slic_init, dim3(cb, n_frames), dim3(128), 0, st, lab, rows, cols, step, ny, n_centers, w.centers);
     for (int it = 0; it < iterations; ++it) {
-        DCMT_LAUNCH(k_slic_prepare, dim3(1), dim3(kScanThreads), 0, st, w.centers, w.sums, n_centers, step, w.bins_x, w.bins_y, w.bin_count,
-                    w.bin_fill, w.bin_items, it > 0 ? 1 : 0);
-        DCMT_LAUNCH(k_slic_assign, dim3((cols + 15) / 16, (rows + 15) / 16), dim3(16, 16), 0, st, lab, rows, cols, step, nc, w.bins_x, w.bins_y,
-                    w.centers, w.bin_count, w.bin_items, labels, w.sums);
+        DCMT_LAUNCH(k_slic_prepare, dim3(n_frames), dim3(kScanThreads), 0, st, w.centers, w.sums, n_centers, step, w.bins_x, w.bins_y,
+                    w.bin_count, w.bin_fill, w.bin_items, w.sorted, it > 0 ? 1 : 0);
+        DCMT_LAUNCH(k_slic_assign, dim3((cols + 15) / 16, (rows + 15) / 16, n_frames), dim3(16, 16), 0, st, lab, rows, cols, step, nc,
+                    w.bins_x, w.bins_y, w.centers, w.bin_count, w.bin_items, w.sorted, labels, w.sums, n_centers,
+                    1.0 / ((double)nc * (double)nc), 1.0 / ((double)step * (double)step));
     }
-    if (iterations > 0) DCMT_LAUNCH(k_slic_update, dim3(cb), dim3(128), 0, st, w.sums, n_centers, w.centers);
+    if (iterations > 0) DCMT_LAUNCH(k_slic_update, dim3(cb, n_frames), dim3(128), 0, st, w.sums, n_centers, w.centers);
     return cudaGetLastError();
 }
 

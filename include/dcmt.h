@@ -234,12 +234,13 @@ DCMT_API int dcmt_lidar_project_f32_host(const float *points, int n_points, cons
  * Slic::centers (n_centers x 5 doubles: L, a, b, x, y; NaN for an empty cluster like the reference's 0 / 0).
  * dcmt_slic_center_count gives slic.centers.size() for a shape.  Labels are bit-identical to a scalar build of the
  * reference (same double arithmetic, ties to the lowest centre index, stale labels kept).  Needs step >= 4 (below
- * that the reference itself reads outside the image in find_local_minimum). */
+ * that the reference itself reads outside the image in find_local_minimum).  `n_frames` images (contiguous, each
+ * rows x cols x 3) are segmented side by side: labels n_frames x rows x cols, centers n_frames x n_centers x 5. */
 DCMT_API int dcmt_slic_center_count(int rows, int cols, int step);
-DCMT_API int dcmt_slic_u8c3(const uint8_t *lab, int rows, int cols, int step, int nc, int iterations, int32_t *labels,
-                            double *centers_or_null, void *cuda_stream);
-DCMT_API int dcmt_slic_u8c3_host(const uint8_t *lab, int rows, int cols, int step, int nc, int iterations, int32_t *labels,
-                                 double *centers_or_null);
+DCMT_API int dcmt_slic_u8c3(const uint8_t *lab, int rows, int cols, int n_frames, int step, int nc, int iterations,
+                            int32_t *labels, double *centers_or_null, void *cuda_stream);
+DCMT_API int dcmt_slic_u8c3_host(const uint8_t *lab, int rows, int cols, int n_frames, int step, int nc, int iterations,
+                                 int32_t *labels, double *centers_or_null);
 
 /* debugging aid: runs the generic pipeline on ONE frame and snapshots intermediate images
  * (device memory, n_stages * rows * cols floats, stage order of oracle/dcmt_oracle.c; stages the

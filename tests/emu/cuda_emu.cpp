@@ -23,7 +23,7 @@ long g_launches = 0;
 // block barrier state
 int g_bar_count = 0, g_bar_gen = 0, g_bar_acc = 0, g_bar_result = 0;
 // warp state
-struct Warp { int count = 0, gen = 0, lanes = 32; unsigned slot[32]; unsigned ballot_acc = 0, ballot_res = 0; };
+struct Warp { int count = 0, gen = 0, lanes = 32; unsigned slot[32]; unsigned ballot_acc = 0, ballot_res = 0, sum_acc = 0, sum_res = 0; };
 std::vector<Warp> g_warps;
 
 void yield() { swapcontext(&g_ctx[g_cur], &g_main); }
@@ -104,6 +104,23 @@ unsigned warp_ballot(int pred) {
     }
     const unsigned r = w.ballot_res;
     warp_sync(w);  // nobody overwrites ballot_res before everyone has read it
+    return r;
+}
+
+unsigned warp_reduce_add(unsigned v) {
+    Warp& w = g_warps[g_cur / 32];
+    const int my_gen = w.gen;
+    w.sum_acc += v;
+    if (++w.count >= w.lanes) {
+        w.sum_res = w.sum_acc;
+        w.sum_acc = 0;
+        w.count = 0;
+        ++w.gen;
+    } else {
+        while (w.gen == my_gen) yield();
+    }
+    const unsigned r = w.sum_res;
+    warp_sync(w);  // nobody overwrites sum_res before everyone has read it
     return r;
 }
 

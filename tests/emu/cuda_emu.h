@@ -57,6 +57,7 @@ void block_barrier();
 int block_count(int pred);  // barrier + number of threads with pred != 0
 unsigned warp_exchange(unsigned v, int src_lane_or_neg, int mode, int delta);  // shuffles
 unsigned warp_ballot(int pred);
+unsigned warp_reduce_add(unsigned v);
 void warp_barrier();
 long launches();
 }  // namespace dcmt_emu
@@ -115,6 +116,7 @@ template <class T> static inline T __shfl_sync(unsigned, T v, int lane) { return
 template <class T> static inline T __shfl_down_sync(unsigned, T v, int d) { return emu_shfl(v, 1, d); }
 template <class T> static inline T __shfl_up_sync(unsigned, T v, int d) { return emu_shfl(v, 2, d); }
 template <class T> static inline T __shfl_xor_sync(unsigned, T v, int m) { return emu_shfl(v, 3, m); }
+static inline unsigned __reduce_add_sync(unsigned, unsigned v) { return dcmt_emu::warp_reduce_add(v); }  // full mask only
 static inline unsigned __ballot_sync(unsigned, int p) { return dcmt_emu::warp_ballot(p); }
 static inline int __any_sync(unsigned, int p) { return dcmt_emu::warp_ballot(p) != 0; }
 static inline int __all_sync(unsigned, int p) { return dcmt_emu::warp_ballot(!p) == 0; }

@@ -34,13 +34,21 @@ def body(lib, to_backend, cases):
     ref = co.interpolate_with_superpixels(sparse, co.slic(lab, 12, 40)[0], kc)
     assert np.array_equal(ln, co.slic(lab, 12, 40)[0])
     assert np.array_equal(on.view(np.uint32), ref.view(np.uint32))
+    # a batch of frames runs side by side and gives the per-frame results
+    labs = np.stack([synth.lab_image(20 + f, 64, 96) for f in range(3)])
+    bl, bc = api.generate_superpixels(to_backend(labs), 10, 40, return_centers=True, lib=lib)
+    bl, bc = (a if isinstance(a, np.ndarray) else a.cpu().numpy() for a in (bl, bc))
+    for f in range(3):
+        rl, rc = co.slic(labs[f], 10, 40)
+        assert np.array_equal(bl[f], rl), f"batch frame {f}"
+        assert np.array_equal(bc[f].view(np.uint64), rc.view(np.uint64)), f"batch centres {f}"
     # argument errors
     with pytest.raises(Exception):
         api.generate_superpixels(to_backend(lab), 3, 40, lib=lib)
 
 
 def test_emu_slic(emu_lib):
-    body(emu_lib, lambda a: a, [(64, 96, 10, 40), (50, 70, 9, 30), (120, 200, 18, 50)])
+    body(emu_lib, lambda a: a, [(64, 96, 10, 40), (50, 70, 9, 30), (80, 120, 18, 50)])
 
 
 @pytest.mark.gpu
