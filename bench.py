@@ -54,6 +54,8 @@ def parse_args():
                     help="lidar_only: float32 metres (the reference's cv::Mat, default) or KITTI uint16 = metres * 256 (main.cpp:75-82)")
     ap.add_argument("--labels", default="grid", choices=["grid", "slic"],
                     help="guided workload: jittered grid labels (SURVEY 8d) or real SLIC output of synthetic Lab images (step 18, nc 50)")
+    ap.add_argument("--host-input", default="pinned", choices=["pinned", "wc"],
+                    help="e2e leg, lidar_only: input in torch pinned memory, or in write-combined page-locked memory (dcmt_host_alloc)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-frames-per-core", type=int, default=4, help="reference arm: frames per host core per step")
@@ -279,6 +281,7 @@ def run_ours(args):
     fpix = rows * cols
 
     # ---- synthetic inputs, device resident before timing
+    holder = {}
     if args.workload == "lidar_only":
         uniq16 = np.stack([synth.sparse_depth_q8(f, rows, cols, args.density) for f in range(UNIQUE)])
         d_in16 = torch.from_numpy(uniq16).to(dev).repeat(reps, 1, 1)[:n].contiguous()
@@ -357,10 +360,17 @@ def run_ours(args):
     e2e = None
     if not args.no_e2e:
         if args.workload == "lidar_only":
-            h_in = torch.empty((n, rows, cols), dtype=d_in.dtype, pin_memory=True)
-            h_in.copy_(d_in)
+            if args.host_input == "wc":
+                hb = api.HostBuffer((n, rows, cols), np.uint16 if args.input == "u16" else np.float32, write_combined=True, lib=lib)
+                holder["hb"] = hb
+                hb.array[...] = d_in.cpu().numpy()
+                np_in = hb.array
+            else:
+                h_in = torch.empty((n, rows, cols), dtype=d_in.dtype, pin_memory=True)
+                h_in.copy_(d_in)
+                np_in = h_in.numpy()
             h_out = torch.empty((n, rows, cols), dtype=torch.float32, pin_memory=True)
-            np_in, np_out = h_in.numpy(), h_out.numpy()
+            np_out = h_out.numpy()
 
             def host_step():
                 api.img_completion(np_in, False, "gaussian", path=args.path, out=np_out, lib=lib)

@@ -51,6 +51,8 @@ _SIGNATURES = {
     "dcmt_release_workspaces": (C.c_int, []),
     "dcmt_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "dcmt_launch_count": (C.c_longlong, []),
+    "dcmt_host_alloc": (C.c_int, [C.c_size_t, C.c_int, C.POINTER(C.c_void_p)]),
+    "dcmt_host_free": (C.c_int, [_P]),
     "dcmt_profile_begin": (C.c_int, []),
     "dcmt_profile_end": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "dcmt_img_completion_f32": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int, _P, _P]),

@@ -457,3 +457,29 @@ def write_M(filename, mat):
     with open(filename, "wb") as fh:
         fh.write(hdr.tobytes())
         fh.write(a.tobytes())
+
+
+# ---------------------------------------------------------------------------------------------- page-locked host buffers
+class HostBuffer:
+    """A page-locked host array for the host entry points (``dcmt_host_alloc``): ``.array`` is a numpy view.
+    ``write_combined=True`` suits input buffers the host only writes (do not read them back on the host)."""
+
+    def __init__(self, shape, dtype, write_combined: bool = False, lib: _lib.Library | None = None):
+        self._lib = lib or _lib.load()
+        self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        ptr = C.c_void_p()
+        self._lib.check(self._lib.dcmt_host_alloc(self.nbytes, int(write_combined), C.byref(ptr)))
+        self._ptr = ptr
+        self.array = np.frombuffer((C.c_char * self.nbytes).from_address(ptr.value), dtype=dtype).reshape(shape)
+
+    def close(self):
+        if self._ptr is not None:
+            self.array = None
+            self._lib.dcmt_host_free(self._ptr)
+            self._ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass

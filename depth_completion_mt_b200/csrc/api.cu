@@ -695,6 +695,22 @@ int dcmt_profile_end(double* front_ms, double* tail_ms, long long* chunks) {
     return DCMT_OK;
 }
 
+int dcmt_host_alloc(size_t bytes, int write_combined, void** out) {
+    if (!out || bytes == 0) return fail(DCMT_E_BADARG, "null pointer or zero size");
+    int rc = check_device();
+    if (rc) return rc;
+    void* p = nullptr;
+    cudaError_t e = cudaHostAlloc(&p, bytes, write_combined ? cudaHostAllocWriteCombined : cudaHostAllocDefault);
+    if (e != cudaSuccess) return fail(DCMT_E_NOMEM, "page-locked host buffer of %zu bytes: %s", bytes, cudaGetErrorString(e));
+    *out = p;
+    return DCMT_OK;
+}
+
+int dcmt_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+    return DCMT_OK;
+}
+
 long long dcmt_launch_count(void) { return dcmt::g_launches.load(std::memory_order_relaxed); }
 
 int dcmt_img_completion_f32(const float* sparse, float* dense, int rows, int cols, size_t pitch_bytes,

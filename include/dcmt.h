@@ -92,6 +92,11 @@ DCMT_API long long dcmt_launch_count(void);
  * them and returns the summed milliseconds and the number of chunks.  Not thread-safe with concurrent callers. */
 DCMT_API int dcmt_profile_begin(void);
 DCMT_API int dcmt_profile_end(double *front_ms, double *tail_ms, long long *chunks);
+/* page-locked host buffers for the *_host entry points (their copies are asynchronous and overlap the kernels only
+ * for page-locked memory).  write_combined != 0: for INPUT buffers the host only writes sequentially (faster for the
+ * device to read, very slow for the host to read back). */
+DCMT_API int dcmt_host_alloc(size_t bytes, int write_combined, void **out);
+DCMT_API int dcmt_host_free(void *p);
 /* bytes of device workspace the library caches for a call of this shape */
 DCMT_API size_t dcmt_workspace_bytes(int rows, int cols, int n_frames);
 

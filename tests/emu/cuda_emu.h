@@ -79,6 +79,8 @@ static inline cudaError_t cudaMalloc(void** p, size_t n) { *p = std::malloc(n ? 
 template <class T> static inline cudaError_t cudaMalloc(T** p, size_t n) { return cudaMalloc(reinterpret_cast<void**>(p), n); }
 static inline cudaError_t cudaFree(void* p) { std::free(p); return cudaSuccess; }
 static inline cudaError_t cudaMallocHost(void** p, size_t n) { *p = std::malloc(n ? n : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+enum { cudaHostAllocDefault = 0, cudaHostAllocWriteCombined = 4 };
+static inline cudaError_t cudaHostAlloc(void** p, size_t n, unsigned) { return cudaMallocHost(p, n); }
 static inline cudaError_t cudaFreeHost(void* p) { std::free(p); return cudaSuccess; }
 static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) { std::memcpy(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { std::memcpy(d, s, n); return cudaSuccess; }
