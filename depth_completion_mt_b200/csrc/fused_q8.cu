@@ -31,6 +31,9 @@ namespace {
 #ifndef DCMT_QTT
 #define DCMT_QTT 512
 #endif
+#ifndef DCMT_TAIL_CTAS
+#define DCMT_TAIL_CTAS 2
+#endif
 constexpr int QT = DCMT_QT;     // threads per CTA of k_q8_front (2 CTAs per SM)
 constexpr int QTT = DCMT_QTT;   // threads per CTA of k_q8_tail (2 CTAs per SM: their phases overlap)
 
@@ -955,7 +958,7 @@ __device__ __forceinline__ uint32_t hmax31(const uint32_t* __restrict__ B, int p
     return pmax3(m, __byte_perm(m, m, 0x1032), odd_pair(pmax(b0[-8], b1[-8]), pmax(b0[8], b1[8])));
 }
 
-__global__ void __launch_bounds__(QTT, 2) k_q8_tail(TailArgs a, const __grid_constant__ TensorMap3D tmap) {
+__global__ void __launch_bounds__(QTT, DCMT_TAIL_CTAS) k_q8_tail(TailArgs a, const __grid_constant__ TensorMap3D tmap) {
     DCMT_DYN_SMEM(uint32_t, smem);
     const int th = a.th, tw = a.tw, rows = a.rows, cols = a.cols;
     const int RH = th + 2 * TV, RQ = tw / 8 + 2 * TQ, pitchw = RQ * 4;
@@ -1018,19 +1021,26 @@ __global__ void __launch_bounds__(QTT, 2) k_q8_tail(TailArgs a, const __grid_con
     __syncthreads();
     DCMT_STAMP(a, 1);
     // rows >= last <- value(last), rows <= first <- value(first) (the second write wins); empty column <- 100
-    if (a5_live) {
-        const bool empty = a5_kf == 0xffffffffu;
-        const int first = empty ? rows - 1 : (int)(a5_kf >> 16), last = empty ? 0 : (int)(a5_kl >> 16);
-        uint16_t* p = Ah + a5_c;
-        if (!a5_bottom) {
-            const uint16_t nv = empty ? (uint16_t)E_HUNDRED : (uint16_t)(a5_kf & 0xffffu);
+    auto a5_apply = [&](int item, uint32_t kf, uint32_t kl) {
+        const int c = item >> 1, bottom = item & 1;
+        const bool empty = kf == 0xffffffffu;
+        const int first = empty ? rows - 1 : (int)(kf >> 16), last = empty ? 0 : (int)(kl >> 16);
+        uint16_t* p = Ah + c;
+        if (!bottom) {
+            const uint16_t nv = empty ? (uint16_t)E_HUNDRED : (uint16_t)(kf & 0xffffu);
             const int r1 = min(RH - 1, first - gy0);
             for (int r = max(0, -gy0); r <= r1; ++r) p[(size_t)r * pitchw * 2] = nv;
         } else {
-            const uint16_t mv = empty ? (uint16_t)E_HUNDRED : (uint16_t)(a5_kl & 0xffffu);
+            const uint16_t mv = empty ? (uint16_t)E_HUNDRED : (uint16_t)(kl & 0xffffu);
             const int r1 = min(RH - 1, rows - 1 - gy0);
             for (int r = max(max(0, -gy0), max(last, first + 1) - gy0); r <= r1; ++r) p[(size_t)r * pitchw * 2] = mv;
         }
+    };
+    if (a5_live) a5_apply(a5_item, a5_kf, a5_kl);
+    for (int item = a5_item + QTT; item < 2 * RQ * 8; item += QTT) {  // CTAs with fewer threads than 2 x region columns
+        const int gx = gx0 + (item >> 1);
+        if (gx >= 0 && gx < cols)
+            a5_apply(item, __ldg(a.col_first + (size_t)slot * a.mid_pitch + gx), __ldg(a.col_last + (size_t)slot * a.mid_pitch + gx));
     }
     __syncthreads();
     DCMT_STAMP(a, 2);
@@ -1395,7 +1405,8 @@ void q8_choose_tile(int rows, int cols, int* th, int* tw) {
     // Tiles of at most 96 x 160 that divide the frame evenly (KITTI 352 x 1216 -> 88 x 152, 4 x 8 tiles).  Among the
     // splits near that size, take the one with the least halo work whose shared memory lets TWO CTAs of each kernel
     // share an SM (228 KB per SM, 1 KB reserved per CTA): the phases of the two overlap.
-    const int ny0 = (rows + 95) / 96, nx0 = (cols + 159) / 160;
+    static const int max_h = [] { const char* e = getenv("DCMT_TILE_MAX_H"); return e ? atoi(e) : 96; }();  // experiments
+    const int ny0 = (rows + max_h - 1) / max_h, nx0 = (cols + 159) / 160;
     long best_cost = -1;
     for (int ny = ny0; ny <= ny0 + 3; ++ny)
         for (int nx = nx0; nx <= nx0 + 3; ++nx) {
