@@ -182,3 +182,32 @@ def test_gpu_sweep_sizes(gpu_lib):
         got, gst = be.img_completion(s, "gaussian", return_stats=True)
         assert_bit_equal(got, want, f"{rows}x{cols} p={p}")
         assert int(gst[0, 0]) == st["loop_passes"]
+
+
+@pytest.mark.gpu
+def test_gpu_fused_path_is_graph_capturable(gpu_lib):
+    """DCMT_PATH_FUSED never synchronises or allocates once the workspace exists: a call can be captured into a CUDA graph
+    and replayed on new data (include/dcmt.h, path flags)."""
+    import torch
+
+    from depth_completion_mt_b200 import api, synth
+    from oracle import c_oracle as co
+
+    frames = np.stack([synth.sparse_depth(300 + f, 96, 160, 0.05) for f in range(4)])
+    d_in = torch.from_numpy(frames).cuda()
+    d_out = torch.empty_like(d_in)
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        api.img_completion(d_in, False, "gaussian", path="fused", out=d_out, lib=gpu_lib)  # sizes the workspace of this stream
+        stream.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=stream):
+            api.img_completion(d_in, False, "gaussian", path="fused", out=d_out, lib=gpu_lib)
+    new = np.stack([synth.sparse_depth(310 + f, 96, 160, 0.08) for f in range(4)])
+    d_in.copy_(torch.from_numpy(new))
+    d_out.zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    got = d_out.cpu().numpy()
+    for f in range(4):
+        assert_bit_equal(got[f], co.img_completion(new[f], "gaussian"), f"graph replay frame {f}")
