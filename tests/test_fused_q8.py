@@ -266,3 +266,22 @@ def test_gpu_fused_equals_generic_on_a_large_batch(gpu_lib):
     assert torch.equal(sa[:, :3], sb[:, :3]) and bool((sa[:, 3] == 1).all()) and bool((sb[:, 3] == 0).all())
     for f in (0, 101, 255):
         assert_bit_equal(a[f].cpu().numpy(), co.img_completion(batch[f], "gaussian"), f"frame {f}")
+
+
+@pytest.mark.gpu
+def test_gpu_large_shapes(gpu_lib):
+    """BASELINE configs[4] shapes: 1024x2048 against the oracle, 2048x4096 fused == generic (the oracle needs seconds there)
+    plus one oracle frame; densities 1 % and 20 %."""
+    import torch
+
+    for rows, cols, p in ((1024, 2048, 0.01), (1024, 2048, 0.2)):
+        s = synth.sparse_depth(500, rows, cols, p)
+        out, st = api.img_completion(torch.from_numpy(s).cuda(), False, "gaussian", return_stats=True, lib=gpu_lib)
+        assert int(st[0, 3]) == 1
+        assert_bit_equal(out.cpu().numpy(), co.img_completion(s, "gaussian"), f"{rows}x{cols} p={p}")
+    big = np.stack([synth.sparse_depth(510 + f, 2048, 4096, 0.05, kitti_like=bool(f)) for f in range(2)])
+    dev = torch.from_numpy(big).cuda()
+    a = api.img_completion(dev, False, "gaussian", path="fused", lib=gpu_lib)
+    b = api.img_completion(dev, False, "gaussian", path="generic", lib=gpu_lib)
+    assert torch.equal(a, b)
+    assert_bit_equal(a[0].cpu().numpy(), co.img_completion(big[0], "gaussian"), "2048x4096")
