@@ -208,6 +208,7 @@ size_t completion_ws_bytes(int rows, int cols, int n_frames, bool bilateral, boo
     if (fused) {
         const size_t mid_pitch = ((size_t)cols + 7) / 8 * 8;
         b += carve_bytes((size_t)rows * mid_pitch * chunk, sizeof(uint16_t)) + 2 * carve_bytes(mid_pitch * chunk, sizeof(uint32_t));
+        b += carve_bytes(((size_t)rows / 8 + 1) * ((size_t)cols / 8 + 1) * chunk, sizeof(int));  // tile flags of the guided front (upper bound)
     }
     return b;
 }
@@ -253,13 +254,14 @@ int enqueue_completion(const CompletionCall& cc, const float* sparse, const int3
         p.ctr = ctr;
         p.w1 = w1;
         p.w2 = w2;
+        int* tile_flags = cc.guided ? carve<int>(ar, dcmt::q8_guided_tile_flags(rows, cols, p.th, p.tw, chunk)) : nullptr;
         for (int f0 = 0; f0 < n_frames; f0 += chunk) {
             const int nf = n_frames - f0 < chunk ? n_frames - f0 : chunk;
             ProfEvents pe{};
             API_CUDA(prof_mark(st, 0, &pe), "profiling event");
             if (cc.guided)
                 API_CUDA(dcmt::q8_run_guided_front(p, sparse + (size_t)f0 * fstride, nullptr, pitch, fstride, labels + (size_t)f0 * fpix,
-                                                   cc.n_clusters, nf, cc.flags != DCMT_PATH_FUSED, st),
+                                                   cc.n_clusters, nf, cc.flags != DCMT_PATH_FUSED, tile_flags, st),
                          "fused guided front launch");
             else if (in16.p)
                 API_CUDA(dcmt::q8_run_front(p, nullptr, in16.p + (size_t)f0 * in16.fstride, in16.pitch, in16.fstride, nf, 0, st),

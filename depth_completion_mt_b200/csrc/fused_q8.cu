@@ -639,12 +639,15 @@ __global__ void __launch_bounds__(QT, 2) k_q8_front(FrontArgs a) {
 // encode as 1.  Afterwards the kernel continues like k_q8_front: vertical / horizontal dilate7, hole fill, uint16 store,
 // column keys -- and k_q8_tail finishes the frame.
 // ------------------------------------------------------------------------------------------------
-constexpr int GT = 256;  // threads per CTA (2 CTAs per SM; up to 128 registers per thread)
+constexpr int GTL = 1024;  // per-label kernel: one CTA per SM, 32 warps work on 32 superpixels at a time
+constexpr int GTW = 256;   // word-by-word kernel: two CTAs per SM, up to 128 registers per thread
 
 struct GuidedArgs {
     FrontArgs f;            // geometry, input, outputs (column maps built for GT threads)
     const int32_t* labels;  // rows x cols int32 per frame, contiguous
     int n_clusters;
+    int per_label;          // 1: one warp per superpixel (guided_label_warp); 0: every word on its own (guided_word)
+    int* tile_flags;        // per tile: set by the per-label kernel when the tile is left to the word-by-word kernel
 };
 
 // lanes of `w` that lie inside the image -> 0xffff, given the image column of the low lane
@@ -730,7 +733,97 @@ __device__ __forceinline__ uint32_t guided_word(const uint32_t* __restrict__ A, 
     return out;
 }
 
-__global__ void __launch_bounds__(GT, 2) k_q8_guided_front(GuidedArgs g) {
+// ---- per-superpixel formulation of the guided stage: one warp per label, lanes = word columns, rows slide through
+// registers, horizontal neighbours come from warp shuffles.  For a label c the masked image, its 2-tap dilation, the
+// separable 5x5 dilation and erosion are computed over the bounding box of c inside the tile (plus the footprint halo),
+// i.e. ~(22+11) x (11+5) words instead of 120 masked words for every one of its ~160 output words.
+constexpr int kLabSlots = 512;  // hash table slots for the labels of a tile; more than 3/4 full: the tile falls back to guided_word
+struct LabelTable {
+    unsigned key[kLabSlots];
+    int r0[kLabSlots], r1[kLabSlots], w0[kLabSlots], w1[kLabSlots];
+    int list[kLabSlots];
+    int n, overflow;
+};
+
+__device__ __forceinline__ int label_slot(LabelTable* T, unsigned lab) {
+    unsigned h = (lab * 40503u) & (kLabSlots - 1);
+    for (int probe = 0; probe < kLabSlots; ++probe) {
+        const unsigned old = atomicCAS(&T->key[h], 0xffffffffu, lab);
+        if (old == 0xffffffffu || old == lab) return (int)h;
+        h = (h + 1) & (kLabSlots - 1);
+    }
+    T->overflow = 1;
+    return -1;
+}
+
+__device__ __forceinline__ void label_run(LabelTable* T, unsigned lab, int r, int wa, int wb) {
+    const int s = label_slot(T, lab);
+    if (s < 0) return;
+    atomicMin(&T->r0[s], r);
+    atomicMax(&T->r1[s], r);
+    atomicMin(&T->w0[s], wa);
+    atomicMax(&T->w1[s], wb);
+}
+
+// 5-window of a word given its left and right neighbour words (both packed lanes)
+template <bool kIsMax>
+__device__ __forceinline__ uint32_t h5_word(uint32_t l, uint32_t c, uint32_t r) {
+    return pext3<kIsMax>(pext3<kIsMax>(l, odd_pair(l, c), c), odd_pair(c, r), r);
+}
+
+// All output pixels of label c inside its bounding box [r0, r1] x [w0, w1] (region rows / words), by one warp.
+__device__ __forceinline__ void guided_label_warp(const uint32_t* __restrict__ A, const uint32_t* __restrict__ LB, uint32_t* __restrict__ B,
+                                                  int pitchw, unsigned c, int r0, int r1, int w0, int w1, int gy0, int gx0, int rows,
+                                                  int cols) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t C2 = c * 0x00010001u;
+    uint16_t* Bh = reinterpret_cast<uint16_t*>(B);
+    for (int wc = w0; wc <= w1; wc += 27) {  // column chunks: 27 output words + 2 left / 3 right footprint words = 32 lanes
+        const int nout = min(27, w1 - wc + 1);
+        const int w = wc - 2 + lane;
+        const bool active = lane < nout + 5;
+        const bool writer = lane >= 2 && lane < 2 + nout;
+        const uint32_t colmask = active ? lanes_inside(gx0 + 2 * w, cols) : 0u;
+        uint32_t t1a = 0u, t1b = 0u, t1c = 0u;                    // tap-1 words of the last three masked rows (newest first)
+        uint32_t ra = 0u, rb = 0u, rc = 0u, rd = 0u;              // last four R1 rows (newest first)
+        uint32_t ea = 0xffffffffu, eb = 0xffffffffu, ec = 0xffffffffu, ed = 0xffffffffu;  // last four eroded rows
+        for (int k = r0 - 5; k <= r1 + 6; ++k) {  // masked row k
+            uint32_t m = 0u;
+            if (active) {
+                const uint32_t dv = A[k * pitchw + w], lv = LB[k * pitchw + w];
+                m = pmin(dv, 0xffffffffu - pmin(lv ^ C2, SPLAT16(1)) * 0xfffeu);  // same label: the pixel; other: hole; outside: absent
+            }
+            const uint32_t ms = __shfl_down_sync(0xffffffffu, m, 1);
+            // R1 row i = k - 2: tap 1 = pixels (x+1, x+2) of masked row i - 1 = k - 3, tap 2 = pixels (x+2, x+3) of masked row k
+            const int gi = gy0 + k - 2;
+            const uint32_t r1w = (gi >= 0 && gi < rows) ? (pmax(t1c, ms) & colmask) : 0u;  // R1 outside the image is excluded
+            t1c = t1b; t1b = t1a; t1a = odd_pair(m, ms);
+            // vertical dilation: R1 rows i-4 .. i  ->  row i - 2 = k - 4
+            const uint32_t vd = pmax3(pmax3(rd, rc, rb), ra, r1w);
+            rd = rc; rc = rb; rb = ra; ra = r1w;
+            // horizontal dilation -> R2 at q row k - 4; q outside the image does not take part in the erosion
+            uint32_t h = h5_word<true>(__shfl_up_sync(0xffffffffu, vd, 1), vd, __shfl_down_sync(0xffffffffu, vd, 1));
+            const int gq = gy0 + k - 4;
+            h = (gq >= 0 && gq < rows) ? (h | ~colmask) : 0xffffffffu;
+            // horizontal erosion, then vertical erosion over q rows k-8 .. k-4  ->  output row k - 6
+            const uint32_t e = h5_word<false>(__shfl_up_sync(0xffffffffu, h, 1), h, __shfl_down_sync(0xffffffffu, h, 1));
+            const uint32_t o = pmin3(pmin3(ed, ec, eb), ea, e);
+            ed = ec; ec = eb; eb = ea; ea = e;
+            const int orow = k - 6;
+            if (writer && orow >= r0) {
+                const uint32_t lw = LB[orow * pitchw + w];
+                if ((lw & 0xffffu) == c) Bh[(orow * pitchw + w) * 2] = (uint16_t)(o & 0xffffu);
+                if ((lw >> 16) == c) Bh[(orow * pitchw + w) * 2 + 1] = (uint16_t)(o >> 16);
+            }
+        }
+    }
+}
+
+// kPerLabel: one warp per superpixel, 1024 threads, one CTA per SM; tiles whose labels overflow the table set their flag and
+// leave.  !kPerLabel: every word on its own (guided_word), 256 threads, two CTAs per SM; runs for flagged tiles only
+// unless g.per_label == 0 (A/B switch).
+template <bool kPerLabel, int GT>
+__global__ void __launch_bounds__(GT, kPerLabel ? 1 : 2) k_q8_guided_front(GuidedArgs g) {
     DCMT_DYN_SMEM(uint32_t, smem);
     const FrontArgs& a = g.f;
     const int th = a.th, tw = a.tw, rows = a.rows, cols = a.cols;
@@ -742,7 +835,10 @@ __global__ void __launch_bounds__(GT, 2) k_q8_guided_front(GuidedArgs g) {
     uint32_t* A = smem + 4;       // encoded image; later the vertical half of dilate7
     uint32_t* B = A + plane;      // result of the guided stage (the closed image D)
     uint32_t* LB = B + plane + 4; // labels, two uint16 per word (0xffff = no valid label)
+    LabelTable* T = reinterpret_cast<LabelTable*>(LB + plane + 4);
     const int frame = blockIdx.z;
+    int* tile_flag = g.tile_flags + ((size_t)frame * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    if (!kPerLabel && g.per_label && *tile_flag == 0) return;  // the per-label kernel has done this tile
     const int y0 = blockIdx.y * th, x0 = blockIdx.x * tw;
     const int gy0 = y0 - FU, gx0 = x0 - FLQ * 8;
     t.rlo = max(0, -gy0);
@@ -770,14 +866,67 @@ __global__ void __launch_bounds__(GT, 2) k_q8_guided_front(GuidedArgs g) {
             LB[i] = lo | (hi << 16);
         }
     }
+    if (kPerLabel) {
+        for (int i = threadIdx.x; i < kLabSlots; i += GT) {
+            T->key[i] = 0xffffffffu;
+            T->r0[i] = 0x7fffffff; T->r1[i] = -1; T->w0[i] = 0x7fffffff; T->w1[i] = -1;
+        }
+        if (threadIdx.x == 0) { T->n = 0; T->overflow = 0; }
+    }
     if (__syncthreads_or(bad != 0.0f)) {  // not strict q8: this frame is redone by the generic pipeline
         if (threadIdx.x == 0) a.ctr[frame].needs_generic = 1;
         return;
     }
+    if (kPerLabel) {
+        // ---- which superpixels have pixels in the needed area (rows core +- 3, words 2 .. (tw + 10) / 2), and where: every thread
+        //      walks 8 words of a row and reports runs of one label (a few atomics per run, not per pixel)
+        const int w_lo = 2, nw = tw / 2 + 4, nch = (nw + 7) / 8;
+        const int rb = max(FU - 3, t.rlo), re = min(FU + th + 3, t.rhi);
+        for (int it = threadIdx.x; it < (re - rb) * nch; it += GT) {
+            const int rr = it / nch, ch = it - rr * nch;
+            const int r = rb + rr, wa = w_lo + 8 * ch, wb = min(wa + 8, w_lo + nw);
+            unsigned cur = 0xffffu;
+            int run0 = 0;
+            for (int w = wa; w < wb; ++w) {
+                const uint32_t C = LB[r * t.pitchw + w];
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const unsigned lab = half ? (C >> 16) : (C & 0xffffu);  // 0xffff: no label or outside the image
+                    if (lab != cur) {
+                        if (cur != 0xffffu) label_run(T, cur, r, run0, half ? w : w - 1);
+                        cur = lab;
+                        run0 = w;
+                    }
+                }
+            }
+            if (cur != 0xffffu) label_run(T, cur, r, run0, wb - 1);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < kLabSlots; i += GT)
+            if (T->key[i] != 0xffffffffu) T->list[atomicAdd(&T->n, 1)] = i;
+        // pixels without a label keep their own value; the labelled lanes are written by the label warps below
+        for (int it = threadIdx.x; it < (re - rb) * nw; it += GT) {
+            const int rr = fast_div(it, a.m_core.magic);
+            const int w = w_lo + (it - rr * nw), r = rb + rr;
+            const uint32_t C = LB[r * t.pitchw + w];
+            const uint32_t keep = (((C & 0xffffu) == 0xffffu) ? 0x0000ffffu : 0u) | (((C >> 16) == 0xffffu) ? 0xffff0000u : 0u);
+            B[r * t.pitchw + w] = A[r * t.pitchw + w] & keep & lanes_inside(gx0 + 2 * w, cols);
+        }
+        __syncthreads();
+        if (T->overflow || T->n > kLabSlots * 3 / 4) {  // too many distinct labels for the table: the word-by-word kernel takes the tile
+            if (threadIdx.x == 0) *tile_flag = 1;
+            return;
+        }
+        const int warp = threadIdx.x >> 5;
+        for (int e = warp; e < T->n; e += GT / 32) {
+            const int s_ = T->list[e];
+            guided_label_warp(A, LB, B, t.pitchw, T->key[s_], T->r0[s_], T->r1[s_], T->w0[s_], T->w1[s_], gy0, gx0, rows, cols);
+        }
+    }
     // ---- the guided stage on rows core +- 3, pixels core -4 .. +3 (what dilate7 reads); words 2 .. (tw + 10) / 2.
     //      (Handling words whose two pixels share a label on a cheaper path, with the others compacted into a list, was
     //      measured: +6 % with real SLIC labels, nothing with jittered ones, and it costs the second CTA per SM.)
-    {
+    if (!kPerLabel) {
         const int w_lo = 2, nw = tw / 2 + 4;
         const int rb = max(FU - 3, t.rlo), re = min(FU + th + 3, t.rhi);
         // every R1 / q column any item of this tile touches lies inside the image?
@@ -1428,7 +1577,9 @@ cudaError_t q8_configure() {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_q8_front<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_q8_guided_front, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    e = cudaFuncSetAttribute(k_q8_guided_front<true, GTL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_q8_guided_front<false, GTW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_q8_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 }
@@ -1451,24 +1602,37 @@ cudaError_t q8_run_front(const Q8Plan& p, const float* in, const uint16_t* in16,
     return cudaGetLastError();
 }
 
-size_t q8_guided_smem(int th, int tw) { return ((size_t)3 * (th + FU + FD) * (tw / 8 + FLQ + FRQ) * 4 + 12) * sizeof(uint32_t); }
+size_t q8_guided_smem(int th, int tw) { return ((size_t)3 * (th + FU + FD) * (tw / 8 + FLQ + FRQ) * 4 + 12) * sizeof(uint32_t) + sizeof(LabelTable); }
+
+size_t q8_guided_tile_flags(int rows, int cols, int th, int tw, int n_frames) {
+    return (size_t)((cols + tw - 1) / tw) * ((rows + th - 1) / th) * n_frames;
+}
 
 cudaError_t q8_run_guided_front(const Q8Plan& p, const float* in, const uint16_t* in16, size_t in_pitch, size_t in_fstride,
-                                const int32_t* labels, int n_clusters, int n_frames, int validate, cudaStream_t st) {
+                                const int32_t* labels, int n_clusters, int n_frames, int validate, int* tile_flags, cudaStream_t st) {
     const size_t ncol = (size_t)p.mid_pitch * n_frames;
     DCMT_LAUNCH(k_q8_zero_counters, dim3((n_frames + 127) / 128), dim3(128), 0, st, p.ctr, n_frames);
     DCMT_LAUNCH(k_q8_init_cols, dim3((unsigned)((ncol + 255) / 256)), dim3(256), 0, st, p.col_first, p.col_last, ncol);
     const size_t unit = in16 ? 8 : 4;
     const uintptr_t base = in16 ? reinterpret_cast<uintptr_t>(in16) : reinterpret_cast<uintptr_t>(in);
     const int RQ = p.tw / 8 + FLQ + FRQ;
-    // column maps / magic reciprocals for GT threads: load by region quads; items of the guided stage and of the vertical
-    // pass by tw / 2 + 4 words (m_core), of the final pass by core quads (m_pass), label plane by region words (i_half)
-    GuidedArgs g{FrontArgs{in, in16, in_pitch, in_fstride, p.mid, (size_t)p.mid_pitch, (size_t)p.mid_pitch * p.rows, p.col_first, p.col_last,
-                           p.ctr, p.rows, p.cols, p.th, p.tw, (int)(in_pitch % unit == 0 && in_fstride % unit == 0 && (base & 15) == 0), validate,
-                           make_colmap(RQ, GT), make_colmap(p.tw / 8, GT), make_colmap(p.tw / 2 + 4, GT), make_items(RQ * 4, GT), nullptr},
-                 labels, n_clusters};
+    static const int guided_per_label = [] { const char* e = getenv("DCMT_GUIDED_PER_LABEL"); return e ? atoi(e) : 1; }();
     const dim3 grid((p.cols + p.tw - 1) / p.tw, (p.rows + p.th - 1) / p.th, n_frames);
-    DCMT_LAUNCH(k_q8_guided_front, grid, dim3(GT), q8_guided_smem(p.th, p.tw), st, g);
+    const size_t n_tiles = (size_t)grid.x * grid.y * n_frames;
+    cudaError_t e = cudaMemsetAsync(tile_flags, 0, n_tiles * sizeof(int), st);
+    if (e != cudaSuccess) return e;
+    // column maps / magic reciprocals per thread count: load by region quads; items of the guided stage and of the vertical
+    // pass by tw / 2 + 4 words (m_core), of the final pass by core quads (m_pass), label plane by region words (i_half)
+    auto args = [&](int nt) {
+        return GuidedArgs{FrontArgs{in, in16, in_pitch, in_fstride, p.mid, (size_t)p.mid_pitch, (size_t)p.mid_pitch * p.rows, p.col_first,
+                                    p.col_last, p.ctr, p.rows, p.cols, p.th, p.tw,
+                                    (int)(in_pitch % unit == 0 && in_fstride % unit == 0 && (base & 15) == 0), validate, make_colmap(RQ, nt),
+                                    make_colmap(p.tw / 8, nt), make_colmap(p.tw / 2 + 4, nt), make_items(RQ * 4, nt), nullptr},
+                          labels, n_clusters, guided_per_label, tile_flags};
+    };
+    if (guided_per_label) DCMT_LAUNCH((k_q8_guided_front<true, GTL>), grid, dim3(GTL), q8_guided_smem(p.th, p.tw), st, args(GTL));
+    // tiles the per-label kernel could not take (more distinct labels than its table holds) -- or all of them
+    DCMT_LAUNCH((k_q8_guided_front<false, GTW>), grid, dim3(GTW), q8_guided_smem(p.th, p.tw) - sizeof(LabelTable), st, args(GTW));
     return cudaGetLastError();
 }
 

@@ -37,7 +37,9 @@ cudaError_t q8_run_front(const Q8Plan& p, const float* in, const uint16_t* in16,
 // int32 per frame (contiguous), values outside [0, n_clusters) mean "no superpixel"; needs n_clusters <= 65535.
 size_t q8_guided_smem(int th, int tw);
 cudaError_t q8_run_guided_front(const Q8Plan& p, const float* in, const uint16_t* in16, size_t in_pitch, size_t in_fstride,
-                                const int32_t* labels, int n_clusters, int n_frames, int validate, cudaStream_t st);
+                                const int32_t* labels, int n_clusters, int n_frames, int validate, int* tile_flags, cudaStream_t st);
+// ints of `tile_flags` scratch the guided front needs for n_frames frames
+size_t q8_guided_tile_flags(int rows, int cols, int th, int tw, int n_frames);
 // uint16 -> float32 metres (main.cpp:79) into a contiguous buffer, for frames served by the generic pipeline
 cudaError_t q8_convert_u16(const uint16_t* in, size_t in_pitch, size_t in_fstride, float* out, int rows, int cols, int n_frames,
                            cudaStream_t st);

@@ -163,6 +163,7 @@ static inline unsigned atomicMin(unsigned* p, unsigned v) { unsigned o = *p; *p 
 static inline unsigned atomicMax(unsigned* p, unsigned v) { unsigned o = *p; *p = std::max(o, v); return o; }
 static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; *p += v; return o; }
 static inline unsigned long long atomicMax(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; *p = std::max(o, v); return o; }
+static inline unsigned atomicCAS(unsigned* p, unsigned cmp, unsigned v) { unsigned o = *p; if (o == cmp) *p = v; return o; }
 static inline int atomicOr(int* p, int v) { int o = *p; *p |= v; return o; }
 static inline unsigned atomicOr(unsigned* p, unsigned v) { unsigned o = *p; *p |= v; return o; }
 static inline int atomicExch(int* p, int v) { int o = *p; *p = v; return o; }

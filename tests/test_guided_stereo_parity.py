@@ -56,6 +56,16 @@ def body_guided_fused(be, shapes):
         got, st = be.interpolate_with_superpixels(lab, s, 1, n_clusters=k, path="generic", return_stats=True)
         assert_bit_equal(got, ref, f"generic guided {rows}x{cols}")
         assert int(st[0, 3]) == 0
+    # thousands of tiny superpixels: more labels per tile than the per-label kernel's table holds -> its tiles are left to
+    # the word-by-word kernel
+    rows, cols = 64, 96
+    s = synth.sparse_depth(190, rows, cols, 0.1)
+    yy, xx = np.mgrid[0:rows, 0:cols]
+    lab = ((yy * cols + xx) // 2).astype(np.int32)
+    k = int(lab.max()) + 1
+    got, st = be.interpolate_with_superpixels(lab, s, 1, n_clusters=k, return_stats=True)
+    assert_bit_equal(got, co.interpolate_with_superpixels(s, lab, k, literal=False), "label table overflow")
+    assert int(st[0, 3]) == 1
     # a non-q8 frame in a batch is redone by the generic pipeline with its own labels
     rows, cols = 48, 80
     b = np.stack([synth.sparse_depth(180, rows, cols, 0.06), synth.sparse_depth_float(181, rows, cols, 0.06), synth.sparse_depth(182, rows, cols, 0.06)])
