@@ -771,29 +771,38 @@ __device__ __forceinline__ uint32_t h5_word(uint32_t l, uint32_t c, uint32_t r) 
     return pext3<kIsMax>(pext3<kIsMax>(l, odd_pair(l, c), c), odd_pair(c, r), r);
 }
 
-// All output pixels of label c inside its bounding box [r0, r1] x [w0, w1] (region rows / words), by one warp.
+// All output pixels of label c inside its bounding box [r0, r1] x [w0, w1] (region rows / words), by kW lanes: a whole warp
+// (kW = 32: chunks of 27 output words), or half a warp (kW = 16, boxes up to 11 words wide: two superpixels per warp, the
+// shuffles stay inside the half).  Lanes of a half without work (c == 0xffffffff) just keep step.
+template <int kW>
 __device__ __forceinline__ void guided_label_warp(const uint32_t* __restrict__ A, const uint32_t* __restrict__ LB, uint32_t* __restrict__ B,
-                                                  int pitchw, unsigned c, int r0, int r1, int w0, int w1, int gy0, int gx0, int rows,
-                                                  int cols) {
-    const int lane = threadIdx.x & 31;
+                                                  int pitchw, unsigned c, int r0, int r1, int w0, int w1, int n_rows_max, int gy0, int gx0,
+                                                  int rows, int cols) {
+    const int lane = threadIdx.x & (kW - 1);
+    constexpr int kOut = kW - 5;  // output words per chunk: 2 footprint words on the left, 3 on the right
     const uint32_t C2 = c * 0x00010001u;
+    const bool idle = c == 0xffffffffu;
     uint16_t* Bh = reinterpret_cast<uint16_t*>(B);
-    for (int wc = w0; wc <= w1; wc += 27) {  // column chunks: 27 output words + 2 left / 3 right footprint words = 32 lanes
-        const int nout = min(27, w1 - wc + 1);
+    const int n_chunks = kW == 32 ? (w1 - w0 + kOut) / kOut : 1;  // both halves of a paired warp run one chunk
+    for (int ch = 0; ch < n_chunks; ++ch) {
+        const int wc = w0 + ch * kOut;
+        const int nout = min(kOut, w1 - wc + 1);
         const int w = wc - 2 + lane;
-        const bool active = lane < nout + 5;
-        const bool writer = lane >= 2 && lane < 2 + nout;
+        const bool active = !idle && lane < nout + 5;
+        const bool writer = !idle && lane >= 2 && lane < 2 + nout;
         const uint32_t colmask = active ? lanes_inside(gx0 + 2 * w, cols) : 0u;
         uint32_t t1a = 0u, t1b = 0u, t1c = 0u;                    // tap-1 words of the last three masked rows (newest first)
         uint32_t ra = 0u, rb = 0u, rc = 0u, rd = 0u;              // last four R1 rows (newest first)
         uint32_t ea = 0xffffffffu, eb = 0xffffffffu, ec = 0xffffffffu, ed = 0xffffffffu;  // last four eroded rows
-        for (int k = r0 - 5; k <= r1 + 6; ++k) {  // masked row k
+        for (int j = 0; j < n_rows_max + 12; ++j) {  // masked row k = r0 - 5 + j (the longer box of a pair sets the trip count)
+            const int k = r0 - 5 + j;
+            const bool in_box = k <= r1 + 6;
             uint32_t m = 0u;
-            if (active) {
+            if (active && in_box) {
                 const uint32_t dv = A[k * pitchw + w], lv = LB[k * pitchw + w];
                 m = pmin(dv, 0xffffffffu - pmin(lv ^ C2, SPLAT16(1)) * 0xfffeu);  // same label: the pixel; other: hole; outside: absent
             }
-            const uint32_t ms = __shfl_down_sync(0xffffffffu, m, 1);
+            const uint32_t ms = __shfl_down_sync(0xffffffffu, m, 1, kW);
             // R1 row i = k - 2: tap 1 = pixels (x+1, x+2) of masked row i - 1 = k - 3, tap 2 = pixels (x+2, x+3) of masked row k
             const int gi = gy0 + k - 2;
             const uint32_t r1w = (gi >= 0 && gi < rows) ? (pmax(t1c, ms) & colmask) : 0u;  // R1 outside the image is excluded
@@ -802,15 +811,15 @@ __device__ __forceinline__ void guided_label_warp(const uint32_t* __restrict__ A
             const uint32_t vd = pmax3(pmax3(rd, rc, rb), ra, r1w);
             rd = rc; rc = rb; rb = ra; ra = r1w;
             // horizontal dilation -> R2 at q row k - 4; q outside the image does not take part in the erosion
-            uint32_t h = h5_word<true>(__shfl_up_sync(0xffffffffu, vd, 1), vd, __shfl_down_sync(0xffffffffu, vd, 1));
+            uint32_t h = h5_word<true>(__shfl_up_sync(0xffffffffu, vd, 1, kW), vd, __shfl_down_sync(0xffffffffu, vd, 1, kW));
             const int gq = gy0 + k - 4;
             h = (gq >= 0 && gq < rows) ? (h | ~colmask) : 0xffffffffu;
             // horizontal erosion, then vertical erosion over q rows k-8 .. k-4  ->  output row k - 6
-            const uint32_t e = h5_word<false>(__shfl_up_sync(0xffffffffu, h, 1), h, __shfl_down_sync(0xffffffffu, h, 1));
+            const uint32_t e = h5_word<false>(__shfl_up_sync(0xffffffffu, h, 1, kW), h, __shfl_down_sync(0xffffffffu, h, 1, kW));
             const uint32_t o = pmin3(pmin3(ed, ec, eb), ea, e);
             ed = ec; ec = eb; eb = ea; ea = e;
             const int orow = k - 6;
-            if (writer && orow >= r0) {
+            if (writer && in_box && orow >= r0) {
                 const uint32_t lw = LB[orow * pitchw + w];
                 if ((lw & 0xffffu) == c) Bh[(orow * pitchw + w) * 2] = (uint16_t)(o & 0xffffu);
                 if ((lw >> 16) == c) Bh[(orow * pitchw + w) * 2 + 1] = (uint16_t)(o >> 16);
@@ -917,10 +926,20 @@ __global__ void __launch_bounds__(GT, kPerLabel ? 1 : 2) k_q8_guided_front(Guide
             if (threadIdx.x == 0) *tile_flag = 1;
             return;
         }
-        const int warp = threadIdx.x >> 5;
-        for (int e = warp; e < T->n; e += GT / 32) {
-            const int s_ = T->list[e];
-            guided_label_warp(A, LB, B, t.pitchw, T->key[s_], T->r0[s_], T->r1[s_], T->w0[s_], T->w1[s_], gy0, gx0, rows, cols);
+        // two superpixels per warp where both boxes fit half a warp (11 words: the usual case at step 18), else one
+        const int warp = threadIdx.x >> 5, half = (threadIdx.x >> 4) & 1;
+        for (int e = 2 * warp; e < T->n; e += 2 * (GT / 32)) {
+            const int sa = T->list[e], sb = e + 1 < T->n ? T->list[e + 1] : -1;
+            const int ha = T->r1[sa] - T->r0[sa] + 1, hb = sb >= 0 ? T->r1[sb] - T->r0[sb] + 1 : 0;
+            const bool narrow = T->w1[sa] - T->w0[sa] < 11 && (sb < 0 || T->w1[sb] - T->w0[sb] < 11);
+            if (narrow) {
+                const int s_ = half ? sb : sa;
+                if (s_ >= 0) guided_label_warp<16>(A, LB, B, t.pitchw, T->key[s_], T->r0[s_], T->r1[s_], T->w0[s_], T->w1[s_], max(ha, hb), gy0, gx0, rows, cols);
+                else guided_label_warp<16>(A, LB, B, t.pitchw, 0xffffffffu, 5, 5, 2, 2, max(ha, hb), gy0, gx0, rows, cols);
+            } else {
+                guided_label_warp<32>(A, LB, B, t.pitchw, T->key[sa], T->r0[sa], T->r1[sa], T->w0[sa], T->w1[sa], ha, gy0, gx0, rows, cols);
+                if (sb >= 0) guided_label_warp<32>(A, LB, B, t.pitchw, T->key[sb], T->r0[sb], T->r1[sb], T->w0[sb], T->w1[sb], hb, gy0, gx0, rows, cols);
+            }
         }
     }
     // ---- the guided stage on rows core +- 3, pixels core -4 .. +3 (what dilate7 reads); words 2 .. (tw + 10) / 2.

@@ -72,18 +72,21 @@ static void warp_sync(Warp& w) {
 
 void warp_barrier() { warp_sync(g_warps[g_cur / 32]); }
 
-unsigned warp_exchange(unsigned v, int, int mode, int arg) {
+unsigned warp_exchange(unsigned v, int width, int mode, int arg) {
     Warp& w = g_warps[g_cur / 32];
     const int lane = g_cur % 32;
+    if (width <= 0 || width > 32) width = 32;
+    const int seg = lane / width * width;  // shuffles stay inside segments of `width` lanes
     w.slot[lane] = v;
     warp_sync(w);
     int src = lane;
     switch (mode) {
-        case 0: src = arg & 31; break;
+        case 0: src = seg + (arg & (width - 1)); break;
         case 1: src = lane + arg; break;
         case 2: src = lane - arg; break;
         case 3: src = lane ^ arg; break;
     }
+    if (src < seg || src >= seg + width) src = lane;
     const unsigned r = (src >= 0 && src < w.lanes) ? w.slot[src] : v;
     warp_sync(w);
     return r;

@@ -55,7 +55,7 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()
 void* dyn_smem();
 void block_barrier();
 int block_count(int pred);  // barrier + number of threads with pred != 0
-unsigned warp_exchange(unsigned v, int src_lane_or_neg, int mode, int delta);  // shuffles
+unsigned warp_exchange(unsigned v, int width, int mode, int delta);  // shuffles inside segments of `width` lanes
 unsigned warp_ballot(int pred);
 unsigned warp_reduce_add(unsigned v);
 void warp_barrier();
@@ -108,16 +108,16 @@ static inline int __syncthreads_count(int p) { return dcmt_emu::block_count(p); 
 static inline int __syncthreads_or(int p) { return dcmt_emu::block_count(p) != 0; }
 static inline void __syncwarp(unsigned = 0xffffffffu) { dcmt_emu::warp_barrier(); }
 template <class T> static inline T __ldg(const T* p) { return *p; }
-template <class T> static inline T emu_shfl(T v, int mode, int arg) {
+template <class T> static inline T emu_shfl(T v, int mode, int arg, int width = 32) {
     static_assert(sizeof(T) == 4, "32-bit shuffles only");
     unsigned u; std::memcpy(&u, &v, 4);
-    unsigned r = dcmt_emu::warp_exchange(u, 0, mode, arg);
+    unsigned r = dcmt_emu::warp_exchange(u, width, mode, arg);
     T o; std::memcpy(&o, &r, 4); return o;
 }
-template <class T> static inline T __shfl_sync(unsigned, T v, int lane) { return emu_shfl(v, 0, lane); }
-template <class T> static inline T __shfl_down_sync(unsigned, T v, int d) { return emu_shfl(v, 1, d); }
-template <class T> static inline T __shfl_up_sync(unsigned, T v, int d) { return emu_shfl(v, 2, d); }
-template <class T> static inline T __shfl_xor_sync(unsigned, T v, int m) { return emu_shfl(v, 3, m); }
+template <class T> static inline T __shfl_sync(unsigned, T v, int lane, int width = 32) { return emu_shfl(v, 0, lane, width); }
+template <class T> static inline T __shfl_down_sync(unsigned, T v, int d, int width = 32) { return emu_shfl(v, 1, d, width); }
+template <class T> static inline T __shfl_up_sync(unsigned, T v, int d, int width = 32) { return emu_shfl(v, 2, d, width); }
+template <class T> static inline T __shfl_xor_sync(unsigned, T v, int m, int width = 32) { return emu_shfl(v, 3, m, width); }
 static inline unsigned __reduce_add_sync(unsigned, unsigned v) { return dcmt_emu::warp_reduce_add(v); }  // full mask only
 static inline unsigned __ballot_sync(unsigned, int p) { return dcmt_emu::warp_ballot(p); }
 static inline int __any_sync(unsigned, int p) { return dcmt_emu::warp_ballot(p) != 0; }
