@@ -1,0 +1,178 @@
+"""TEST INFRASTRUCTURE ONLY -- the reference's own code as the checker of the checker.
+
+oracle/_ref/libdcmt_ref.so holds img_completion (src/DC_lidar_only/img_completion.cpp:17-204),
+interpolate_with_superpixels (src/DC_lidar_camera/img_completion_lc.cpp:34-203) and Slic
+(src/DC_lidar_camera/slic.cpp) compiled UNMODIFIED from /root/reference against the stand-in OpenCV header in
+oracle/refshim/ (recipe: oracle/Makefile).  The stand-in implements containers only; the five imgproc calls the
+reference makes are forwarded, through the callbacks registered here, to cv2 -- the same OpenCV 4.13 the
+transliteration (oracle/cv2_oracle.py) uses.  So: control flow, scalar loops and buffer handling are the reference's
+compiled code, the filters are the real library.
+
+It pins the restatements (cv2_oracle.py, dcmt_oracle.c) to the reference itself (tests/test_reference_build.py) and can
+serve as bench.py's CPU arm (`cpu_baseline.kind = "reference"`).  /root/reference exists only in the build container:
+there the library is (re)built on demand; elsewhere the prebuilt file that travelled with the snapshot is used.
+Never imported by the product package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_ref", "libdcmt_ref.so")
+_REF = os.environ.get("DCMT_REFERENCE_DIR", "/root/reference")
+_SHIM = [os.path.join(_HERE, "refshim", n) for n in ("refshim.cpp", "img_completion.h", os.path.join("opencv2", "opencv.hpp"))]
+BLUR = {"none": 0, "gaussian": 1, "bilateral": 2}
+
+_MORPH_CB = C.CFUNCTYPE(C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int)
+_BLUR_CB = C.CFUNCTYPE(C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double)
+_CV_TYPES = {0: np.uint8, 5: np.float32}  # CV_8UC1, CV_32FC1
+
+
+class ReferenceUnavailable(RuntimeError):
+    pass
+
+
+def have_sources() -> bool:
+    return os.path.isfile(os.path.join(_REF, "src", "DC_lidar_only", "img_completion.cpp"))
+
+
+def build(force: bool = False) -> str:
+    """(Re)build oracle/_ref/libdcmt_ref.so where the reference sources exist; otherwise return the prebuilt file."""
+    if have_sources():
+        stale = force or not os.path.exists(_SO) or any(os.path.getmtime(_SO) < os.path.getmtime(p) for p in _SHIM)
+        if stale:
+            subprocess.run(["make", "-C", _HERE, "-B", "_ref/libdcmt_ref.so", f"REF={_REF}"], check=True, capture_output=True)
+    if not os.path.exists(_SO):
+        raise ReferenceUnavailable(f"{_SO} is missing and {_REF} is not present to build it from")
+    return _SO
+
+
+def available() -> bool:
+    try:
+        build()
+        import cv2  # noqa: F401
+        return True
+    except Exception:
+        return False
+
+
+def _view(ptr, rows, cols, cv_type):
+    dt = _CV_TYPES[cv_type]
+    n = rows * cols
+    buf = (C.c_ubyte * (n * np.dtype(dt).itemsize)).from_address(ptr)
+    return np.frombuffer(buf, dtype=dt, count=n).reshape(rows, cols)
+
+
+def _morph(op, src, dst, rows, cols, cv_type, kernel, krows, kcols):
+    try:
+        import cv2
+        s = _view(src, rows, cols, cv_type)
+        k = _view(kernel, krows, kcols, 0)
+        if op == 1:
+            r = cv2.dilate(s, k)
+        elif op == 3:
+            r = cv2.morphologyEx(s, cv2.MORPH_CLOSE, k)
+        else:
+            return 2
+        _view(dst, rows, cols, cv_type)[...] = r
+        return 0
+    except Exception:  # an exception must not cross the C boundary
+        return 1
+
+
+def _blur(kind, src, dst, rows, cols, cv_type, ksize, p0, p1):
+    try:
+        import cv2
+        s = _view(src, rows, cols, cv_type)
+        if kind == 0:
+            r = cv2.medianBlur(s, ksize)
+        elif kind == 1:
+            r = cv2.GaussianBlur(s, (ksize, ksize), p0)
+        elif kind == 2:
+            r = cv2.bilateralFilter(s, ksize, p0, p1)
+        else:
+            return 2
+        _view(dst, rows, cols, cv_type)[...] = r
+        return 0
+    except Exception:
+        return 1
+
+
+_lib = None
+_keep = []  # the ctypes callback objects must outlive the library's use of them
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        import cv2
+        cv2.setNumThreads(1)
+        L = C.CDLL(build())
+        m, b = _MORPH_CB(_morph), _BLUR_CB(_blur)
+        _keep.extend([m, b])
+        L.dcmt_ref_set_callbacks(m, b)
+        _lib = L
+    return _lib
+
+
+def _err():
+    return C.create_string_buffer(256)
+
+
+def img_completion(sparse, blur_type="gaussian"):
+    """The reference's img_completion on one float32 frame.  Raises RuntimeError with the reference's exception text
+    (blur_type="bilateral": OpenCV's in-place assertion, img_completion.cpp:174)."""
+    s = np.ascontiguousarray(sparse, dtype=np.float32)
+    rows, cols = s.shape
+    out = np.empty_like(s)
+    e = _err()
+    rc = lib().dcmt_ref_img_completion(s.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), rows, cols, BLUR[blur_type], e, 256)
+    if rc:
+        raise RuntimeError(e.value.decode(errors="replace"))
+    return out
+
+
+def interpolate_with_superpixels(labels, sparse, blur_type="gaussian", use_superpixel=1, n_clusters=None):
+    """The reference's interpolate_with_superpixels; labels row-major [row][col] (the shim fills Slic::clusters[col][row]),
+    n_clusters = slic.centers.size() (default: max label + 1)."""
+    s = np.ascontiguousarray(sparse, dtype=np.float32)
+    lab = np.ascontiguousarray(labels, dtype=np.int32)
+    rows, cols = s.shape
+    if n_clusters is None:
+        n_clusters = int(lab.max()) + 1 if lab.size else 0
+    out = np.empty_like(s)
+    e = _err()
+    rc = lib().dcmt_ref_interpolate_with_superpixels(s.ctypes.data_as(C.c_void_p), lab.ctypes.data_as(C.c_void_p), int(n_clusters),
+                                                     out.ctypes.data_as(C.c_void_p), rows, cols, BLUR[blur_type], int(use_superpixel), e, 256)
+    if rc:
+        raise RuntimeError(e.value.decode(errors="replace"))
+    return out
+
+
+def generate_superpixels(lab_image, step, nc):
+    """Slic::generate_superpixels on an H x W x 3 uint8 image -> (labels int32 H x W, centers float64 K x 5, counts int32 K)."""
+    img = np.ascontiguousarray(lab_image, dtype=np.uint8)
+    rows, cols, ch = img.shape
+    assert ch == 3
+    cap = (rows // max(int(step), 1) + 2) * (cols // max(int(step), 1) + 2) + 8
+    labels = np.empty((rows, cols), np.int32)
+    centers = np.zeros((cap, 5), np.float64)
+    counts = np.zeros(cap, np.int32)
+    e = _err()
+    n = lib().dcmt_ref_slic(img.ctypes.data_as(C.c_void_p), rows, cols, int(step), int(nc), labels.ctypes.data_as(C.c_void_p),
+                            centers.ctypes.data_as(C.c_void_p), counts.ctypes.data_as(C.c_void_p), cap, e, 256)
+    if n < 0:
+        raise RuntimeError(e.value.decode(errors="replace"))
+    assert n <= cap
+    return labels, centers[:n].copy(), counts[:n].copy()
+
+
+def call_counts():
+    """How many times the reference called (dilate, morphologyEx, medianBlur, GaussianBlur, bilateralFilter) so far."""
+    a = (C.c_longlong * 5)()
+    lib().dcmt_ref_call_counts(a)
+    return tuple(a)
