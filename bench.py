@@ -14,7 +14,8 @@ hot path; NCCL only gathers timings / checksums (depth_completion_mt_b200/shardi
             the timed region
   roofline  algorithmic bytes (8 B/px lidar-only, 12 guided, 10 stereo) / time vs the measured
             HBM copy bandwidth (MEASURED_PEAKS.json)
-  cpu_baseline  the reference CPU path (oracle port: cv2 transliteration, one process per host core)
+  cpu_baseline  the reference CPU path, one process per host core: the reference's own sources (oracle/_ref, kind
+                "reference") when the prebuilt library is present, else the cv2 oracle port
             timed on a bounded sample of the same workload, rank 0 at N=1 only
 `--impl reference` prints the reference-CPU arm alone in the same JSON shape.
 """
@@ -74,7 +75,21 @@ def _ref_worker_init(workload, rows, cols, density):
         have_cv2 = cvo.HAVE_CV2
     except Exception:
         have_cv2 = False
+    ref_ok = False
     if have_cv2:
+        # the reference's own sources compiled from /root/reference in the build container (oracle/_ref/libdcmt_ref.so,
+        # OpenCV calls forwarded to cv2)
+        try:
+            from oracle import ref_oracle as ro
+
+            ref_ok = ro.available()
+        except Exception:
+            ref_ok = False
+    if ref_ok:
+        ro.lib()  # registers the cv2 callbacks, cv2.setNumThreads(1)
+        _W["impl"] = ro
+        _W["kind"] = "ref"
+    elif have_cv2:
         import cv2
 
         cv2.setNumThreads(1)
@@ -107,7 +122,10 @@ def _ref_task(f):
     if _W["workload"] == "lidar_only":
         out = impl.img_completion(args[0], "gaussian")
     elif _W["workload"] == "guided":
-        out = impl.interpolate_with_superpixels(args[0], args[1], args[2])
+        if _W["kind"] == "ref":
+            out = impl.interpolate_with_superpixels(args[1], args[0], n_clusters=args[2])
+        else:
+            out = impl.interpolate_with_superpixels(args[0], args[1], args[2])
     else:
         out = impl.stereo_refine(*args)
     return float(out[0, 0])
@@ -133,14 +151,16 @@ def run_reference(args, quiet=False):
             pool.map(_ref_task, frames, chunksize=chunk)
         dt = time.perf_counter() - t0
     fps = per_step * args.steps / dt
+    is_ref = kind.startswith("reference")
     sample = (f"{per_step} frames/step x {args.steps} steps of the {args.workload} workload "
-              f"({args.rows}x{args.cols}, {args.density:.0%} valid), {kind} oracle port, one single-threaded process per core")
+              f"({args.rows}x{args.cols}, {args.density:.0%} valid), {kind}{'' if is_ref else ' oracle port'}, "
+              "one single-threaded process per core")
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, per_step),
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "reference" if is_ref else "port", "sample": sample},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -150,6 +170,11 @@ def run_reference(args, quiet=False):
 
 
 def _kind():
+    if _W["kind"] == "ref":
+        import cv2
+
+        return ("reference sources compiled from /root/reference (oracle/_ref/libdcmt_ref.so), "
+                "imgproc calls forwarded to cv2 (OpenCV %s)" % cv2.__version__)
     return "cv2 (OpenCV %s)" % _W["impl"].cv2.__version__ if _W["kind"] == "cv2" else "plain-C"
 
 

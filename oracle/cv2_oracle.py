@@ -10,10 +10,12 @@ version, this oracle pins ``opencv-python-headless==4.13.0.92``).  It exists to
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference``
 legs may import it.  The product path (``depth_completion_mt_b200``) never does.
 
-Parity status: the reference ships no golden vectors, no tests and cannot be compiled here
-(no OpenCV C++ headers, ``img_completion.h`` missing from the repo) -> the reference itself is
-"parity unpinned"; this transliteration through the same OpenCV build is the strongest pin
-available.
+Parity status: the reference ships no golden vectors and no tests, and its own build needs
+OpenCV / Eigen / PCL headers that the image lacks (``img_completion.h`` is missing from its
+repo as well).  The pin is therefore the reference's OWN SOURCES compiled against a stand-in
+header (``oracle/refshim``, ``oracle/ref_oracle.py`` -> ``oracle/_ref/libdcmt_ref.so``) with the
+imgproc calls forwarded to this same OpenCV build: ``tests/test_reference_build.py`` requires
+this transliteration, the C restatement and the golden vectors to equal its output bit for bit.
 
 Reference files followed (relative to /root/reference):
   src/DC_lidar_only/img_completion.cpp:17-204          -> img_completion

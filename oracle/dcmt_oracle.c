@@ -11,8 +11,11 @@
  * 4.13.0.92) and are checked, function by function, against that very library through
  * oracle/cv2_oracle.py (tests/test_oracle.py) and against the committed vectors in tests/golden/.
  *
- * Parity status: the reference has no tests / golden vectors and cannot be compiled in the
- * build image, so the pin is "cv2 transliteration == this file == tests/golden" (SURVEY.md 8c).
+ * Parity status: the reference has no tests / golden vectors.  The pin is the reference's own
+ * sources compiled against a stand-in OpenCV / Eigen header with the imgproc calls forwarded to
+ * cv2 (oracle/refshim, oracle/_ref/libdcmt_ref.so): tests/test_reference_build.py requires
+ * "reference build == cv2 transliteration == this file == tests/golden", bit for bit, for
+ * img_completion, interpolate_with_superpixels, the stereo chain, SLIC and the evaluation loops.
  *
  * Who may use it: tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
  * legs -- as the checker, never as the product.  The product (libdcmt.so) does not link it.

@@ -176,3 +176,63 @@ def call_counts():
     a = (C.c_longlong * 5)()
     lib().dcmt_ref_call_counts(a)
     return tuple(a)
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def measurement_derivatives(value):
+    """calculateMeasuementDerivatives (main_sl.cpp:715-745) -> (derivative.x(), derivative.y()) planes."""
+    v = np.ascontiguousarray(value, dtype=np.float32)
+    dx, dy = np.empty_like(v), np.empty_like(v)
+    lib().dcmt_ref_measurement_derivatives(_p(v), _p(dx), _p(dy), *v.shape)
+    return dx, dy
+
+
+def get_initial_disparity(depth):
+    d = np.ascontiguousarray(depth, dtype=np.float32)
+    out = np.empty_like(d)
+    lib().dcmt_ref_get_initial_disparity(_p(d), _p(out), *d.shape)
+    return out
+
+
+def retrieve_optimized_depth(disp):
+    d = np.ascontiguousarray(disp, dtype=np.float32)
+    out = np.empty_like(d)
+    lib().dcmt_ref_retrieve_optimized_depth(_p(d), _p(out), *d.shape)
+    return out
+
+
+def optimize_IG(value_left, value_right, disp):
+    """optimize_IG (main_sl.cpp:804-843) on float value planes; returns the refined disparity (input untouched)."""
+    l = np.ascontiguousarray(value_left, dtype=np.float32)
+    r = np.ascontiguousarray(value_right, dtype=np.float32)
+    d = np.array(disp, dtype=np.float32, order="C", copy=True)
+    lib().dcmt_ref_optimize_IG(_p(l), _p(r), _p(d), *d.shape)
+    return d
+
+
+def stereo_refine(depth_ig, left_gray, right_gray, final_gauss=True, return_disp=False):
+    """The chain of main_sl.cpp:1165-1253 with the constants hard-coded there (4 iterations, damping 500, clips 255 / 100)."""
+    d = np.ascontiguousarray(depth_ig, dtype=np.float32)
+    lg = np.ascontiguousarray(left_gray, dtype=np.uint8)
+    rg = np.ascontiguousarray(right_gray, dtype=np.uint8)
+    out, disp = np.empty_like(d), np.empty_like(d)
+    e = _err()
+    rc = lib().dcmt_ref_stereo_chain(_p(d), _p(lg), _p(rg), _p(out), _p(disp), d.shape[0], d.shape[1], int(bool(final_gauss)), e, 256)
+    if rc:
+        raise RuntimeError(e.value.decode(errors="replace"))
+    return (out, disp) if return_disp else out
+
+
+def evaluate(gt, r, variant):
+    """variant "lidar_only" (main.cpp:16-34) -> mean signed error; "lidar_camera" (main_lc.cpp:85-116) -> (rmse, mae);
+    "stereo_lidar" (main_sl.cpp:1031-1061) -> (mae, rmse).  float32, exactly as the reference accumulates them."""
+    g = np.ascontiguousarray(gt, dtype=np.float32)
+    v = np.ascontiguousarray(r, dtype=np.float32)
+    code = {"lidar_only": 0, "lidar_camera": 1, "stereo_lidar": 2}[variant]
+    out = np.zeros(2, np.float32)
+    rc = lib().dcmt_ref_evaluate(code, _p(g), _p(v), g.shape[0], g.shape[1], _p(out))
+    assert rc == 0
+    return np.float32(out[0]) if code == 0 else (np.float32(out[0]), np.float32(out[1]))

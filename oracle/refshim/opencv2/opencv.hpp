@@ -40,6 +40,7 @@ typedef unsigned char uchar;
 #define CV_8UC1 CV_MAKETYPE(CV_8U, 1)
 #define CV_8UC3 CV_MAKETYPE(CV_8U, 3)
 #define CV_32FC1 CV_MAKETYPE(CV_32F, 1)
+#define CV_32FC(n) CV_MAKETYPE(CV_32F, (n))
 
 namespace cv {
 

@@ -135,3 +135,131 @@ def test_slic_reference_flat_image_has_empty_clusters():
     o_lab, o_cen = co.slic(img, 9, 40)
     assert np.array_equal(r_lab, o_lab)
     assert np.array_equal(r_cen.view(np.uint64), o_cen.view(np.uint64))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# stereo refinement (main_sl.cpp:23-26, 715-885, 1165-1253) and the evaluation loops, from the reference's own lines
+
+
+@pytest.mark.parametrize("shape", [(352, 1216), (64, 100), (9, 12), (3, 3)])
+def test_stereo_chain_reference_vs_restatements(shape):
+    """a3-a9: EntryType matrices, derivatives, initial disparity, 4 GN iterations, depth retrieval: bit for bit; with the
+    final cv::GaussianBlur (float data) within 1e-4 for the C port and bit-equal for the transliteration (same OpenCV)."""
+    dig, left, right = synth.stereo_pair(5, shape[0], shape[1])
+    ref, ref_disp = ro.stereo_refine(dig, left, right, final_gauss=False, return_disp=True)
+    out, disp = co.stereo_refine(dig, left, right, final_gauss=False, return_disp=True)
+    assert_bit_equal(disp, ref_disp, f"{shape} disparity after 4 iterations")
+    assert_bit_equal(out, ref, f"{shape} depth")
+    blurred = ro.stereo_refine(dig, left, right, final_gauss=True)
+    assert np.abs(co.stereo_refine(dig, left, right) - blurred).max() <= 1e-4
+    if min(shape) >= 5:
+        assert_bit_equal(np.asarray(cvo.stereo_refine(dig, left, right)), blurred, f"{shape} transliteration")
+
+
+def test_stereo_functions_one_by_one():
+    dig, left, right = synth.stereo_pair(6, 48, 80)
+    lf, rf = left.astype(np.float32), right.astype(np.float32)
+    for a, b, what in zip(co.measurement_derivatives(rf), ro.measurement_derivatives(rf), ("dx", "dy")):
+        assert_bit_equal(a, b, what)
+    d0 = ro.get_initial_disparity(dig)
+    assert_bit_equal(np.asarray(cvo.get_initial_disparity(dig)), d0, "get_initial_disparity")
+    d4 = ro.optimize_IG(lf, rf, d0)
+    _, disp = co.stereo_refine(dig, left, right, final_gauss=False, return_disp=True)
+    assert_bit_equal(disp, d4, "optimize_IG")
+    assert_bit_equal(np.asarray(cvo.retrieve_optimized_depth(d4)), ro.retrieve_optimized_depth(d4), "retrieve_optimized_depth")
+
+
+def test_stereo_zero_and_far_depths():
+    """depth 0 -> disparity 0 -> never refined, output 0; tiny disparities clip at 100 m (main_sl.cpp:875-878)."""
+    dig, left, right = synth.stereo_pair(8, 40, 64)
+    dig = dig.copy()
+    dig[:5] = 0.0
+    dig[5:8] = 5000.0
+    ref = ro.stereo_refine(dig, left, right, final_gauss=False)
+    assert_bit_equal(co.stereo_refine(dig, left, right, final_gauss=False), ref, "zero / far depths")
+    assert (ref[:5] == 0).all() and (ref[5:8] <= 100.0).all()
+
+
+def test_reference_reproduces_stereo_golden(golden):
+    g = golden["stereo"]
+    for name in sorted({k.split("__")[0] for k in g.files}):
+        dig, left, right = g[name + "__depth_ig"], g[name + "__left"], g[name + "__right"]
+        out, disp = ro.stereo_refine(dig, left, right, final_gauss=False, return_disp=True)
+        assert_bit_equal(out, g[name + "__default_nogauss"], f"{name} depth")
+        assert_bit_equal(disp, g[name + "__disp4"], f"{name} disparity")
+        assert_bit_equal(ro.stereo_refine(dig, left, right), g[name + "__default"], f"{name} with the final Gaussian")
+
+
+@pytest.mark.parametrize("shape", [(37, 53), (352, 1216)])
+def test_evaluation_loops_reference_vs_restatement(shape):
+    """f3: the three float32 raster-order loops (int tolerance 0 / (int)0.1 = 0 / 2)."""
+    rng = np.random.default_rng(11)
+    gt = np.where(rng.random(shape) < 0.3, rng.uniform(0.5, 80, shape), 0).astype(np.float32)
+    dense = (rng.uniform(0.0, 85, shape) * (rng.random(shape) < 0.9)).astype(np.float32)
+    if shape[0] < 100:  # main.cpp:29 prints every pixel pair; keep that one small
+        assert np.float32(co.evaluate(gt, dense, 0, 0)["mean_err"]) == ro.evaluate(gt, dense, "lidar_only")
+    rmse, mae = ro.evaluate(gt, dense, "lidar_camera")
+    o = co.evaluate(gt, dense, 0, 1)
+    assert (np.float32(o["rmse"]), np.float32(o["mae"])) == (rmse, mae)
+    mae2, rmse2 = ro.evaluate(gt, dense, "stereo_lidar")
+    o = co.evaluate(gt, dense, 2, 1)
+    assert (np.float32(o["mae"]), np.float32(o["rmse"])) == (mae2, rmse2)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the product against the reference build directly (B200, through the C ABI)
+
+
+@pytest.mark.gpu
+def test_gpu_img_completion_equals_reference_build(gpu_lib):
+    """Fused strict-q8 kernels (device and host entry points, float32 and KITTI uint16 input) and the generic float32
+    pipeline == the reference's compiled img_completion at 352 x 1216, every bit."""
+    import torch
+
+    from depth_completion_mt_b200 import api
+
+    for frame, density, kitti_like in ((0, 0.05, False), (1, 0.05, True), (2, 0.01, False), (3, 0.2, False)):
+        d16 = synth.sparse_depth_q8(frame, density=density, kitti_like=kitti_like)
+        s = d16.astype(np.float32) / np.float32(256)
+        for bt in ("gaussian", "none"):
+            ref = ro.img_completion(s, bt)
+            assert_bit_equal(api.img_completion(torch.from_numpy(s).cuda(), False, bt, lib=gpu_lib).cpu().numpy(), ref, f"fused {frame} {bt}")
+            assert_bit_equal(api.img_completion(torch.from_numpy(s).cuda(), False, bt, path="generic", lib=gpu_lib).cpu().numpy(), ref, f"generic {frame} {bt}")
+        assert_bit_equal(api.img_completion(s, False, "gaussian", lib=gpu_lib), ro.img_completion(s, "gaussian"), f"host entry point {frame}")
+        assert_bit_equal(api.img_completion(torch.from_numpy(d16).cuda(), False, "gaussian", lib=gpu_lib).cpu().numpy(),
+                         ro.img_completion(s, "gaussian"), f"uint16 input {frame}")
+
+
+@pytest.mark.gpu
+def test_gpu_guided_and_stereo_equal_reference_build(gpu_lib):
+    import torch
+
+    from depth_completion_mt_b200 import api
+
+    rows, cols = 64, 96  # the reference runs three full-frame morphology calls per superpixel: keep it small
+    s = synth.sparse_depth(9, rows, cols, 0.08)
+    lab, k = synth.superpixel_labels(9, rows, cols, step=12)
+    lab = lab.copy()
+    lab[3:6, 40:50] = -1
+    for sp in (1, 0):
+        got = api.interpolate_with_superpixels(torch.from_numpy(lab).cuda(), torch.from_numpy(s).cuda(), "gaussian", sp, n_clusters=k, lib=gpu_lib)
+        assert_bit_equal(got.cpu().numpy(), ro.interpolate_with_superpixels(lab, s, use_superpixel=sp, n_clusters=k), f"guided sp={sp}")
+    dig, left, right = synth.stereo_pair(4)
+    prm = api.stereo_params(final_gauss=0, lib=gpu_lib)
+    got = api.stereo_refine(torch.from_numpy(dig).cuda(), torch.from_numpy(left).cuda(), torch.from_numpy(right).cuda(), prm, lib=gpu_lib)
+    assert_bit_equal(got.cpu().numpy(), ro.stereo_refine(dig, left, right, final_gauss=False), "stereo refinement at 352 x 1216")
+    got = api.stereo_refine(torch.from_numpy(dig).cuda(), torch.from_numpy(left).cuda(), torch.from_numpy(right).cuda(), lib=gpu_lib)
+    assert np.abs(got.cpu().numpy() - ro.stereo_refine(dig, left, right)).max() <= 1e-4  # final float Gaussian (SURVEY 8c tolerance)
+
+
+@pytest.mark.gpu
+def test_gpu_slic_equals_reference_build(gpu_lib):
+    import torch
+
+    from depth_completion_mt_b200 import api
+
+    img = synth.lab_image(1)
+    labels, centers = api.generate_superpixels(torch.from_numpy(img).cuda(), 18, 40, return_centers=True, lib=gpu_lib)
+    r_lab, r_cen, _ = ro.generate_superpixels(img, 18, 40)
+    assert np.array_equal(labels.cpu().numpy(), r_lab)
+    assert np.array_equal(np.ascontiguousarray(centers.cpu().numpy(), dtype=np.float64).view(np.uint64), r_cen.view(np.uint64))
