@@ -26,7 +26,7 @@ namespace dcmt {
 namespace {
 
 #ifndef DCMT_QT
-#define DCMT_QT 512
+#define DCMT_QT 256
 #endif
 #ifndef DCMT_QTT
 #define DCMT_QTT 512
@@ -34,7 +34,10 @@ namespace {
 #ifndef DCMT_TAIL_CTAS
 #define DCMT_TAIL_CTAS 2
 #endif
-constexpr int QT = DCMT_QT;     // threads per CTA of k_q8_front (2 CTAs per SM)
+#ifndef DCMT_FRONT_CTAS
+#define DCMT_FRONT_CTAS 4
+#endif
+constexpr int QT = DCMT_QT;     // threads per CTA of k_q8_front (DCMT_FRONT_CTAS CTAs per SM on tiles of half the tail's height)
 constexpr int QTT = DCMT_QTT;   // threads per CTA of k_q8_tail (2 CTAs per SM: their phases overlap)
 
 #define SPLAT16(x) ((uint32_t)(x) | ((uint32_t)(x) << 16))
@@ -527,7 +530,7 @@ __device__ __forceinline__ void front_load(const FrontArgs& a, const void* in0v,
 }
 
 template <bool kStraddle>
-__global__ void __launch_bounds__(QT, 2) k_q8_front(FrontArgs a) {
+__global__ void __launch_bounds__(QT, DCMT_FRONT_CTAS) k_q8_front(FrontArgs a) {
     DCMT_DYN_SMEM(uint32_t, smem);
     const int th = a.th, tw = a.tw, rows = a.rows, cols = a.cols;
     Tile t;
@@ -1603,8 +1606,21 @@ cudaError_t q8_configure() {
     return cudaFuncSetAttribute(k_q8_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 }
 
-cudaError_t q8_run_front(const Q8Plan& p, const float* in, const uint16_t* in16, size_t in_pitch, size_t in_fstride, int n_frames,
+cudaError_t q8_run_front(const Q8Plan& plan, const float* in, const uint16_t* in16, size_t in_pitch, size_t in_fstride, int n_frames,
                          int validate, cudaStream_t st) {
+    // The front's tiles need not be the tail's (they meet in the global intermediate plane).  k_q8_front is latency bound
+    // (its global loads, seven barriers), so DCMT_FRONT_CTAS CTAs per SM on lower tiles beat two tall ones although the
+    // halo rows weigh more: the tallest even split of the rows whose shared memory fits that many CTAs.
+    // DCMT_FRONT_TILE_H overrides the height bound (experiments).
+    static const int front_h = [] { const char* e = getenv("DCMT_FRONT_TILE_H"); return e ? atoi(e) : 0; }();
+    Q8Plan p = plan;
+    int hmax = front_h > 0 ? front_h : p.th;
+    if (front_h <= 0 && DCMT_FRONT_CTAS > 2)
+        while (hmax > 8 && (size_t)DCMT_FRONT_CTAS * (q8_front_smem(hmax, p.tw) + 1024) > (size_t)228 * 1024) --hmax;
+    if (hmax < p.th) {
+        const int ny = (p.rows + hmax - 1) / hmax;
+        p.th = (p.rows + ny - 1) / ny;
+    }
     const size_t ncol = (size_t)p.mid_pitch * n_frames;
     DCMT_LAUNCH(k_q8_zero_counters, dim3((n_frames + 127) / 128), dim3(128), 0, st, p.ctr, n_frames);
     DCMT_LAUNCH(k_q8_init_cols, dim3((unsigned)((ncol + 255) / 256)), dim3(256), 0, st, p.col_first, p.col_last, ncol);
