@@ -109,11 +109,11 @@ __device__ __forceinline__ uint32_t encode_bits(float v, float& bad) {
     const float ef = valid ? t : 1.0f;
     const float m = ef + 8388608.0f;  // 2^23: the integer lands in the low mantissa bits
     if (kValidate) {
-        // exact test that 256 v is an integer: K = round(256 v) via the 2^23 trick, residual 256 v - K by one FMA
-        // (t itself may round a near-grid value onto the grid, so it cannot be used for this)
-        const float K = fmaf(v, 256.0f, 8388608.0f) - 8388608.0f;
-        const float res = valid ? fmaf(v, 256.0f, -K) : 0.0f;
-        bad = fmaf(res, res, bad);  // stays 0 iff every valid pixel seen so far is on the grid
+        // exact test that 256 v is the integer the encoding kept (t itself may round a near-grid value onto the grid, so
+        // it cannot be used for this): K = 25601 - (m - 2^23); -K = m - (2^23 + 25601) is exact, and ONE FMA gives the
+        // residual 256 v - K, which is zero iff v is on the grid
+        const float res = fmaf(v, 256.0f, m - 8414209.0f);
+        if (valid) bad = fmaf(res, res, bad);  // stays 0 iff every valid pixel seen so far is on the grid
     }
     return __float_as_uint(m);
 }
