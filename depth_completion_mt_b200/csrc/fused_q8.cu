@@ -642,7 +642,13 @@ __global__ void __launch_bounds__(QT, DCMT_FRONT_CTAS) k_q8_front(FrontArgs a) {
 // encode as 1.  Afterwards the kernel continues like k_q8_front: vertical / horizontal dilate7, hole fill, uint16 store,
 // column keys -- and k_q8_tail finishes the frame.
 // ------------------------------------------------------------------------------------------------
-constexpr int GTL = 1024;  // per-label kernel: one CTA per SM, 32 warps work on 32 superpixels at a time
+#ifndef DCMT_GTL
+#define DCMT_GTL 512
+#endif
+#ifndef DCMT_GUIDED_CTAS
+#define DCMT_GUIDED_CTAS 2
+#endif
+constexpr int GTL = DCMT_GTL;  // per-label kernel: DCMT_GUIDED_CTAS CTAs per SM, every warp works on one (or two) superpixels at a time
 constexpr int GTW = 256;   // word-by-word kernel: two CTAs per SM, up to 128 registers per thread
 
 struct GuidedArgs {
@@ -831,11 +837,12 @@ __device__ __forceinline__ void guided_label_warp(const uint32_t* __restrict__ A
     }
 }
 
-// kPerLabel: one warp per superpixel, 1024 threads, one CTA per SM; tiles whose labels overflow the table set their flag and
+// kPerLabel: one warp per superpixel, GTL threads, DCMT_GUIDED_CTAS CTAs per SM (two of 512 on 71-row tiles beat one of 1024 on
+// 88 rows by 10 %: the barriers of one CTA are covered by the other); tiles whose labels overflow the table set their flag and
 // leave.  !kPerLabel: every word on its own (guided_word), 256 threads, two CTAs per SM; runs for flagged tiles only
 // unless g.per_label == 0 (A/B switch).
 template <bool kPerLabel, int GT>
-__global__ void __launch_bounds__(GT, kPerLabel ? 1 : 2) k_q8_guided_front(GuidedArgs g) {
+__global__ void __launch_bounds__(GT, kPerLabel ? DCMT_GUIDED_CTAS : 2) k_q8_guided_front(GuidedArgs g) {
     DCMT_DYN_SMEM(uint32_t, smem);
     const FrontArgs& a = g.f;
     const int th = a.th, tw = a.tw, rows = a.rows, cols = a.cols;
@@ -1639,12 +1646,27 @@ cudaError_t q8_run_front(const Q8Plan& plan, const float* in, const uint16_t* in
 
 size_t q8_guided_smem(int th, int tw) { return ((size_t)3 * (th + FU + FD) * (tw / 8 + FLQ + FRQ) * 4 + 12) * sizeof(uint32_t) + sizeof(LabelTable); }
 
+// tile height of the guided front: the tail's, or -- DCMT_GUIDED_CTAS > 1 -- the tallest even split of the rows whose shared
+// memory lets that many CTAs share an SM (DCMT_GUIDED_TILE_H overrides the bound: experiments)
+static int q8_guided_tile_h(int rows, int th, int tw) {
+    static const int env_h = [] { const char* e = getenv("DCMT_GUIDED_TILE_H"); return e ? atoi(e) : 0; }();
+    int hmax = env_h > 0 ? env_h : th;
+    if (env_h <= 0 && DCMT_GUIDED_CTAS > 1)
+        while (hmax > 8 && (size_t)DCMT_GUIDED_CTAS * (q8_guided_smem(hmax, tw) + 1024) > (size_t)228 * 1024) --hmax;
+    if (hmax >= th) return th;
+    const int ny = (rows + hmax - 1) / hmax;
+    return (rows + ny - 1) / ny;
+}
+
 size_t q8_guided_tile_flags(int rows, int cols, int th, int tw, int n_frames) {
+    th = q8_guided_tile_h(rows, th, tw);
     return (size_t)((cols + tw - 1) / tw) * ((rows + th - 1) / th) * n_frames;
 }
 
-cudaError_t q8_run_guided_front(const Q8Plan& p, const float* in, const uint16_t* in16, size_t in_pitch, size_t in_fstride,
+cudaError_t q8_run_guided_front(const Q8Plan& plan, const float* in, const uint16_t* in16, size_t in_pitch, size_t in_fstride,
                                 const int32_t* labels, int n_clusters, int n_frames, int validate, int* tile_flags, cudaStream_t st) {
+    Q8Plan p = plan;
+    p.th = q8_guided_tile_h(p.rows, p.th, p.tw);  // its own tiles: the kernels meet in the global intermediate plane
     const size_t ncol = (size_t)p.mid_pitch * n_frames;
     DCMT_LAUNCH(k_q8_zero_counters, dim3((n_frames + 127) / 128), dim3(128), 0, st, p.ctr, n_frames);
     DCMT_LAUNCH(k_q8_init_cols, dim3((unsigned)((ncol + 255) / 256)), dim3(256), 0, st, p.col_first, p.col_last, ncol);
