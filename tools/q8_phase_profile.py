@@ -28,7 +28,9 @@ nt = tiles.value * n
 for name, buf, k, labels in (("k_q8_front", fs, 5, ["load+encode", "6 morphology passes", "final pass + store", "column keys"]),
                              ("k_q8_tail", ts, 10, ["load", "A5 extrapolation", "vertical 16-row maxima", "hole scan", "lazy 31-wide fill",
                                                     "replicate border", "median", "reflect border", "gaussian + store"])):
-    a = buf[: nt * 16].view(nt, 16)[:, :k].cpu().numpy().astype(np.float64)
+    a = buf.view(-1, 16)[:, :k].cpu().numpy().astype(np.float64)
+    a = a[a[:, 0] != 0]  # the front runs on its own (lower) tiles: count the CTAs that left stamps
+    nt = len(a)
     d = np.diff(a, axis=1)
     tot = a[:, -1] - a[:, 0]
     print(f"{name}: {nt} CTAs, mean CTA lifetime {tot.mean():.0f} cycles (min {tot.min():.0f}, max {tot.max():.0f})")
