@@ -1619,7 +1619,7 @@ cudaError_t q8_run_front(const Q8Plan& plan, const float* in, const uint16_t* in
     // (its global loads, seven barriers), so DCMT_FRONT_CTAS CTAs per SM on lower tiles beat two tall ones although the
     // halo rows weigh more: the tallest even split of the rows whose shared memory fits that many CTAs.
     // DCMT_FRONT_TILE_H overrides the height bound (experiments).
-    static const int front_h = [] { const char* e = getenv("DCMT_FRONT_TILE_H"); return e ? atoi(e) : 0; }();
+    static const int front_h = [] { const char* e = getenv("DCMT_FRONT_TILE_H"); const int v = e ? atoi(e) : 0; return v > 0 && v < 8 ? 8 : v; }();
     Q8Plan p = plan;
     int hmax = front_h > 0 ? front_h : p.th;
     if (front_h <= 0 && DCMT_FRONT_CTAS > 2)
@@ -1649,7 +1649,7 @@ size_t q8_guided_smem(int th, int tw) { return ((size_t)3 * (th + FU + FD) * (tw
 // tile height of the guided front: the tail's, or -- DCMT_GUIDED_CTAS > 1 -- the tallest even split of the rows whose shared
 // memory lets that many CTAs share an SM (DCMT_GUIDED_TILE_H overrides the bound: experiments)
 static int q8_guided_tile_h(int rows, int th, int tw) {
-    static const int env_h = [] { const char* e = getenv("DCMT_GUIDED_TILE_H"); return e ? atoi(e) : 0; }();
+    static const int env_h = [] { const char* e = getenv("DCMT_GUIDED_TILE_H"); const int v = e ? atoi(e) : 0; return v > 0 && v < 8 ? 8 : v; }();
     int hmax = env_h > 0 ? env_h : th;
     if (env_h <= 0 && DCMT_GUIDED_CTAS > 1)
         while (hmax > 8 && (size_t)DCMT_GUIDED_CTAS * (q8_guided_smem(hmax, tw) + 1024) > (size_t)228 * 1024) --hmax;
