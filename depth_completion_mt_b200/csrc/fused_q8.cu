@@ -873,14 +873,21 @@ __global__ void __launch_bounds__(GT, kPerLabel ? DCMT_GUIDED_CTAS : 2) k_q8_gui
     {
         const int32_t* lab = g.labels + (size_t)frame * rows * cols;
         const int nk = g.n_clusters;
+        const bool lab_vec2 = (cols & 1) == 0 && (reinterpret_cast<uintptr_t>(g.labels) & 7) == 0;  // every word of every frame 8-byte aligned
         for (int i = threadIdx.x; i < t.RH * t.pitchw; i += GT) {
             const int r = fast_div(i, a.i_half.magic);  // i_half.nq == pitchw here (see q8_run_guided_front)
             const int w = i - r * t.pitchw;
             const int gy = gy0 + r, gx = gx0 + 2 * w;
             uint32_t lo = 0xffffu, hi = 0xffffu;
             if (gy >= 0 && gy < rows) {
-                if (gx >= 0 && gx < cols) { const int v = __ldg(lab + (size_t)gy * cols + gx); if (v >= 0 && v < nk) lo = (uint32_t)v; }
-                if (gx + 1 >= 0 && gx + 1 < cols) { const int v = __ldg(lab + (size_t)gy * cols + gx + 1); if (v >= 0 && v < nk) hi = (uint32_t)v; }
+                if (lab_vec2 && gx >= 0 && gx + 1 < cols) {  // both pixels of the word in one 8-byte load (gx is even)
+                    const int2 v = __ldg(reinterpret_cast<const int2*>(lab + (size_t)gy * cols + gx));
+                    if (v.x >= 0 && v.x < nk) lo = (uint32_t)v.x;
+                    if (v.y >= 0 && v.y < nk) hi = (uint32_t)v.y;
+                } else {
+                    if (gx >= 0 && gx < cols) { const int v = __ldg(lab + (size_t)gy * cols + gx); if (v >= 0 && v < nk) lo = (uint32_t)v; }
+                    if (gx + 1 >= 0 && gx + 1 < cols) { const int v = __ldg(lab + (size_t)gy * cols + gx + 1); if (v >= 0 && v < nk) hi = (uint32_t)v; }
+                }
             }
             LB[i] = lo | (hi << 16);
         }

@@ -24,6 +24,7 @@ struct dim3 {
 struct float2 { float x, y; };
 struct alignas(16) float4 { float x, y, z, w; };
 struct uint2 { unsigned x, y; };
+struct int2 { int x, y; };
 struct alignas(16) uint4 { unsigned x, y, z, w; };
 struct ushort2 { unsigned short x, y; };
 struct alignas(8) ushort4 { unsigned short x, y, z, w; };
