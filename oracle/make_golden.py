@@ -6,6 +6,10 @@
 The fixtures are small (a few hundred kB in total) and committed, so that the plain-C oracle and
 the CUDA path stay pinned to OpenCV's arithmetic on machines where cv2 or /root/reference do not
 exist (the GPU box).  Re-running must reproduce the committed files byte for byte.
+
+Where the reference build exists (oracle/_ref/libdcmt_ref.so: the reference's own sources compiled
+from /root/reference, see oracle/ref_oracle.py), every fixture the reference computes is checked
+against ITS output before it is written: the vectors are outputs of the reference itself.
 """
 from __future__ import annotations
 
@@ -16,6 +20,22 @@ import numpy as np
 
 from depth_completion_mt_b200 import synth
 from oracle import cv2_oracle as cvo
+
+try:
+    from oracle import ref_oracle as ro
+
+    HAVE_REF = ro.available()
+except Exception:  # pragma: no cover
+    HAVE_REF = False
+
+
+def pinned(what, arr, ref_fn):
+    """arr as computed by the transliteration; must equal the reference build's own output bit for bit."""
+    if HAVE_REF:
+        ref = np.asarray(ref_fn())
+        assert ref.shape == arr.shape and np.array_equal(ref.view(np.uint32), np.asarray(arr).view(np.uint32)), f"{what}: differs from the reference build"
+    return arr
+
 
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
@@ -57,7 +77,8 @@ def main():
         arrs[name + "__in"] = s
         for bt in ("gaussian", "none", "bilateral"):
             st = {}
-            arrs[f"{name}__{bt}"] = cvo.img_completion(s, bt, st)
+            o = cvo.img_completion(s, bt, st)
+            arrs[f"{name}__{bt}"] = o if bt == "bilateral" else pinned(f"{name} {bt}", o, lambda: ro.img_completion(s, bt))  # the reference's bilateral branch throws
             arrs[f"{name}__passes"] = np.int32(st["loop_passes"])
     np.savez_compressed(os.path.join(OUT, "lidar_only.npz"), **arrs)
 
@@ -87,8 +108,9 @@ def main():
         arrs[name + "__in"] = s
         arrs[name + "__labels"] = lab
         arrs[name + "__k"] = np.int32(k)
-        arrs[name + "__sp1"] = cvo.interpolate_with_superpixels(s, lab, k, use_superpixel=1)
-        arrs[name + "__sp0"] = cvo.interpolate_with_superpixels(s, lab, k, use_superpixel=0)
+        for sp in (1, 0):
+            arrs[name + f"__sp{sp}"] = pinned(f"{name} sp={sp}", cvo.interpolate_with_superpixels(s, lab, k, use_superpixel=sp),
+                                              lambda: ro.interpolate_with_superpixels(lab, s, use_superpixel=sp, n_clusters=k))
     np.savez_compressed(os.path.join(OUT, "guided.npz"), **arrs)
 
     # --- stereo refinement (main_sl.cpp:715-885,1253); numpy float32 restatement + cv2 Gaussian
@@ -98,13 +120,15 @@ def main():
         arrs[name + "__depth_ig"] = dig
         arrs[name + "__left"] = left
         arrs[name + "__right"] = right
-        arrs[name + "__default"] = cvo.stereo_refine(dig, left, right)
-        arrs[name + "__default_nogauss"] = cvo.stereo_refine(dig, left, right, final_gauss=False)
+        arrs[name + "__default"] = pinned(f"{name} stereo", cvo.stereo_refine(dig, left, right), lambda: ro.stereo_refine(dig, left, right))
+        arrs[name + "__default_nogauss"] = pinned(f"{name} stereo, no blur", cvo.stereo_refine(dig, left, right, final_gauss=False),
+                                                  lambda: ro.stereo_refine(dig, left, right, final_gauss=False))
         arrs[name + "__official10"] = cvo.stereo_refine(dig, left, right, num_iterations=10, damp_factor=1370.0,
                                                         err_clip=221.0, depth_clip=80.0, final_gauss=False)
         d0 = cvo.get_initial_disparity(dig)
         arrs[name + "__disp0"] = d0
-        arrs[name + "__disp4"] = cvo.optimize_IG(left.astype(np.float32), right.astype(np.float32), d0)
+        arrs[name + "__disp4"] = pinned(f"{name} optimize_IG", cvo.optimize_IG(left.astype(np.float32), right.astype(np.float32), d0),
+                                        lambda: ro.optimize_IG(left.astype(np.float32), right.astype(np.float32), d0))
         dx, dy = cvo.measurement_derivatives(right.astype(np.float32))
         arrs[name + "__dx_right"] = dx
         arrs[name + "__dy_right"] = dy
@@ -116,12 +140,12 @@ def main():
         for kitti_like in (False, True):
             s = synth.sparse_depth(f, density=0.05, kitti_like=kitti_like)
             for bt in ("gaussian", "none"):
-                o = cvo.img_completion(s, bt)
+                o = pinned(f"352x1216 frame {f} {bt}", cvo.img_completion(s, bt), lambda: ro.img_completion(s, bt))
                 lines.append(f"{f} {int(kitti_like)} {bt} {hashlib.sha256(s.tobytes()).hexdigest()} {hashlib.sha256(o.tobytes()).hexdigest()}")
     with open(os.path.join(OUT, "lidar_only_352x1216.sha256"), "w") as fh:
         fh.write("# frame kitti_like blur sha256(input f32 bytes) sha256(output f32 bytes); synth.sparse_depth(frame, density=0.05)\n")
         fh.write("\n".join(lines) + "\n")
-    print("golden written to", OUT)
+    print("golden written to", OUT, "(checked against the reference build)" if HAVE_REF else "(reference build not available: unchecked)")
 
 
 if __name__ == "__main__":
