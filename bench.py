@@ -59,7 +59,7 @@ def parse_args():
                     help="e2e leg, lidar_only: input in torch pinned memory, or in write-combined page-locked memory (dcmt_host_alloc)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--ref-frames-per-core", type=int, default=4, help="reference arm: frames per host core per step")
+    ap.add_argument("--ref-frames-per-core", type=int, default=16, help="reference arm: frames per host core per step")
     return ap.parse_args()
 
 
