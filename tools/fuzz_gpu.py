@@ -12,13 +12,16 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from depth_completion_mt_b200 import _lib, api, synth  # noqa: E402
 from oracle import c_oracle as co  # noqa: E402
+from oracle import ref_oracle as ro  # noqa: E402
+
+HAVE_REF = ro.available()  # the reference's own compiled sources (prebuilt oracle/_ref travels with the snapshot)
 
 secs = float(sys.argv[1]) if len(sys.argv) > 1 else 60
 seed = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 rng = np.random.default_rng(seed)
 lib = _lib.load()
 t_end = time.time() + secs
-n = ng = 0
+n = ng = nr = ns = 0
 while time.time() < t_end:
     rows = int(rng.integers(32, 420))
     cols = int(rng.integers(32, 1400))
@@ -46,6 +49,19 @@ while time.time() < t_end:
         print(f"MISMATCH lidar rows={rows} cols={cols} p={p} kitti={kitti} blur={blur} u16={u16} host={host} seed={fseed} diff={(got != want).sum()}", flush=True)
         sys.exit(1)
     n += 1
+    if HAVE_REF and rows * cols < 150_000:  # ... and to the reference build itself
+        if not np.array_equal(got.view(np.uint32), ro.img_completion(s, blur).view(np.uint32)):
+            print(f"MISMATCH vs reference build rows={rows} cols={cols} p={p} blur={blur} seed={fseed}", flush=True)
+            sys.exit(1)
+        nr += 1
+    if rng.random() < 0.15:  # stereo refinement (bit-exact without the final float Gaussian)
+        dig, left, right = synth.stereo_pair(fseed % 1000, rows, cols)
+        prm = api.stereo_params(final_gauss=0, lib=lib)
+        gots = api.stereo_refine(torch.from_numpy(dig).cuda(), torch.from_numpy(left).cuda(), torch.from_numpy(right).cuda(), prm, lib=lib).cpu().numpy()
+        if not np.array_equal(gots.view(np.uint32), co.stereo_refine(dig, left, right, final_gauss=False).view(np.uint32)):
+            print(f"MISMATCH stereo rows={rows} cols={cols} seed={fseed}", flush=True)
+            sys.exit(1)
+        ns += 1
     if rng.random() < 0.35 and rows * cols < 200_000:  # guided: the oracle's closed form is slower
         step = int(rng.choice([6, 9, 12, 18, 25]))
         lab, k = synth.superpixel_labels(fseed % 1000, rows, cols, step=step)
@@ -59,4 +75,4 @@ while time.time() < t_end:
             print(f"MISMATCH guided rows={rows} cols={cols} p={p} step={step} k={kk} seed={fseed} diff={(gotg != wantg).sum()}", flush=True)
             sys.exit(1)
         ng += 1
-print(f"fuzz ok: {n} lidar-only and {ng} guided random frames, seed {seed}")
+print(f"fuzz ok: {n} lidar-only ({nr} of them also against the reference build), {ng} guided and {ns} stereo random frames, seed {seed}")
