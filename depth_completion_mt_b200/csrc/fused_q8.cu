@@ -21,6 +21,7 @@
 #include <cstdlib>
 
 #include "median_net.cuh"
+#include "median_rows.cuh"
 
 namespace dcmt {
 namespace {
@@ -36,6 +37,9 @@ namespace {
 #endif
 #ifndef DCMT_FRONT_CTAS
 #define DCMT_FRONT_CTAS 4
+#endif
+#ifndef DCMT_MEDIAN_ROWS
+#define DCMT_MEDIAN_ROWS 1  // 1: shared-work median over runs of rows (median_rows.cuh); 0: independent selection networks
 #endif
 constexpr int QT = DCMT_QT;     // threads per CTA of k_q8_front (DCMT_FRONT_CTAS CTAs per SM on tiles of half the tail's height)
 constexpr int QTT = DCMT_QTT;   // threads per CTA of k_q8_tail (2 CTAs per SM: their phases overlap)
@@ -1086,6 +1090,8 @@ struct TailArgs {
     int one;          // the constant 1, opaque to the compiler (see other_of_pair)
     int use_tma;      // tile load by one TMA box copy (else 16-byte cp.async per thread)
     ItemsDesc i_load, i_vert, i_scan, i_scanw, i_med, i_gauss;  // row lengths RQ, pitchw, SQ, 4 SQ, MI, NP
+    ItemsDesc i_medr;  // row length tw / 2 + 2: one item = one word column x med_len rows (shared-work median)
+    int med_len, med_segs;
     long long* prof;  // optional: 16 clock64() stamps per CTA (debugging aid)
 };
 
@@ -1141,6 +1147,40 @@ __device__ __forceinline__ uint32_t hmax31(const uint32_t* __restrict__ B, int p
     // m.lo / m.hi hold the maxima over the even / odd columns of words w-7 .. w+7; both output lanes need both
     // (lane swap), plus column 2w-15 for the low lane only and column 2w+16 for the high lane only
     return pmax3(m, __byte_perm(m, m, 0x1032), odd_pair(pmax(b0[-8], b1[-8]), pmax(b0[8], b1[8])));
+}
+
+
+// ---- A8 median 5x5 (:170), shared-work form (tools/median_rows_scheme.py).  One item = one packed word column x a run
+// of rows.  Per image row the five pixels of the window (both lanes: W[w-1], the odd pair, W[w], the odd pair, W[w+1])
+// are sorted once: S[y], used by the five outputs whose window holds row y.  Going down the rows two at a time,
+//     PP[q]    = merge(S[q], S[q+1])                         used by four outputs
+//     QQ[q]    = ranks 7..12 of merge(PP[q], PP[q+2])        the only elements of rows q..q+3 that can be the median
+//     out[q+1] = rank 5 of (QQ[q], S[q-1]),   out[q+2] = rank 5 of (QQ[q], S[q+4])
+// i.e. 9 + 13/2 + 24/2 comparators + 8 min/max per output word instead of 13.5 + 54.  The sorted rows and pair merges
+// rotate through registers with periods 3 and 2, so six steps are written out and nothing is ever moved.
+struct MedianRun {
+    uint32_t P[2][10];  // PP[q], PP[q+2] alternate
+    uint32_t O[3][5];   // S of the odd rows q-1, q+1, q+3
+    uint32_t E[5];      // S[q+2], later S[q+4]
+};
+__device__ __forceinline__ void sort_row5(const uint32_t* __restrict__ p, uint32_t (&s)[5], uint32_t one) {
+    const uint32_t c0 = p[0], c2 = p[1], c4 = p[2];
+    s[0] = c0; s[1] = odd_pair(c0, c2); s[2] = c2; s[3] = odd_pair(c2, c4); s[4] = c4;
+    sort5(s, one);
+}
+// K = step number mod 6.  p points at word w-1 of row q+3; o at word w of row q+1.
+template <int K>
+__device__ __forceinline__ void median_step(MedianRun& m, const PackedOps& ops, const uint32_t* __restrict__ p, uint32_t* __restrict__ o, int pitchw,
+                                            bool two) {
+    constexpr int pa = K & 1, pb = pa ^ 1, om = K % 3, on = (K + 2) % 3;
+    uint32_t qq[6];
+    // S[q-1] (slot om) is needed until the first output is out; S[q+3] goes to slot on != om
+    sort_row5(p, m.O[on], ops.one);
+    merge_5_5(ops, m.E, m.O[on], m.P[pb]);
+    merge_10_10_ranks_7_12(ops, m.P[pa], m.P[pb], qq);
+    o[0] = rank5_of_6_5(ops, qq, m.O[om]);
+    sort_row5(p + pitchw, m.E, ops.one);
+    if (two) o[pitchw] = rank5_of_6_5(ops, qq, m.E);
 }
 
 __global__ void __launch_bounds__(QTT, DCMT_TAIL_CTAS) k_q8_tail(TailArgs a, const __grid_constant__ TensorMap3D tmap) {
@@ -1392,6 +1432,38 @@ __global__ void __launch_bounds__(QTT, DCMT_TAIL_CTAS) k_q8_tail(TailArgs a, con
         __syncthreads();
     }
     DCMT_STAMP(a, 6);
+#if DCMT_MEDIAN_ROWS
+    // ---- A8 median 5x5 (:170): shared-work form, see median_step
+    {
+        const int MH = th + 4;  // rows core +- 2, words core +- 1 (a.i_medr)
+        const int mr0 = TV - 2, mw0 = TQ * 4 - 1;
+        const PackedOps ops{(uint32_t)a.one};
+        for (Items i(a.i_medr); i.r < a.med_segs; i.next()) {
+            int r = mr0 + i.r * a.med_len;  // first output row of the run
+            const int rend = min(r + a.med_len, mr0 + MH);
+            const uint32_t* p = A + (r - 2) * pitchw + (mw0 + i.q - 1);
+            uint32_t* o = B + r * pitchw + (mw0 + i.q);
+            MedianRun m;
+            // q = r - 1:  S[q-1] -> O[0], S[q] and S[q+1] -> PP[q] = P[0] (S[q+1] kept in O[1]), S[q+2] -> E
+            uint32_t s0[5];
+            sort_row5(p, m.O[0], ops.one);
+            sort_row5(p + pitchw, s0, ops.one);
+            sort_row5(p + 2 * pitchw, m.O[1], ops.one);
+            merge_5_5(ops, s0, m.O[1], m.P[0]);
+            sort_row5(p + 3 * pitchw, m.E, ops.one);
+            p += 4 * pitchw;
+#pragma unroll 1
+            for (;;) {
+#define DCMT_MEDIAN_STEP(K)                                            \
+    median_step<K>(m, ops, p, o, pitchw, r + 1 < rend);                \
+    r += 2; p += 2 * pitchw; o += 2 * pitchw;                          \
+    if (r >= rend) break;
+                DCMT_MEDIAN_STEP(0) DCMT_MEDIAN_STEP(1) DCMT_MEDIAN_STEP(2) DCMT_MEDIAN_STEP(3) DCMT_MEDIAN_STEP(4) DCMT_MEDIAN_STEP(5)
+#undef DCMT_MEDIAN_STEP
+            }
+        }
+    }
+#else
     // ---- A8 median 5x5 (:170): one item = four output words of one row.  The six word columns it touches are sorted
     //      once (9 compare-exchanges each, both lanes at once), the odd-aligned pixel pairs between them come from
     //      PRMTs of the sorted columns, and each output is the 54-comparator selection network of median_net.cuh on
@@ -1440,6 +1512,7 @@ __global__ void __launch_bounds__(QTT, DCMT_TAIL_CTAS) k_q8_tail(TailArgs a, con
             q[3] = res[3];
         }
     }
+#endif
     __syncthreads();
     DCMT_STAMP(a, 7);
     float* out = a.out + (size_t)slot * a.out_fstride;
@@ -1703,6 +1776,13 @@ cudaError_t q8_run_guided_front(const Q8Plan& plan, const float* in, const uint1
 cudaError_t q8_run_tail(const Q8Plan& p, float* out, size_t out_pitch, size_t out_fstride, int n_frames, int blur, cudaStream_t st) {
     const int vec2 = out_pitch % 4 == 0 && out_fstride % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
     const int RQ = p.tw / 8 + 2 * TQ, RH = p.th + 2 * TV, SQ = p.tw / 8 + 2, MI = (p.tw / 2 + 2 + 3) / 4, NP = p.tw / 4;
+    // shared-work median: word columns x runs of an even number of rows (at least 8: a run starts with four extra row sorts),
+    // as many runs as the threads of a CTA can take in one round
+    const int NW = p.tw / 2 + 2, MH = p.th + 4;
+    const int max_segs = QTT / NW > 0 ? QTT / NW : 1;
+    int med_len = 2 * ((MH + 2 * max_segs - 1) / (2 * max_segs));
+    if (med_len < 8) med_len = 8;
+    const int med_segs = (MH + med_len - 1) / med_len;
     // tile load by TMA: a 3-D map (columns, rows, slots) of the intermediate plane whose column extent is the true
     // image width, so that the padding columns of the plane read as absent like everything else outside the image
     TensorMap3D tmap{};
@@ -1712,7 +1792,7 @@ cudaError_t q8_run_tail(const Q8Plan& p, float* out, size_t out_pitch, size_t ou
     TailArgs a{p.mid, (size_t)p.mid_pitch, (size_t)p.mid_pitch * p.rows, p.col_first, p.col_last, p.ctr, out, out_pitch,
                out_fstride, p.rows, p.cols, p.th, p.tw, blur, vec2, 1, use_tma,
                make_items(RQ, QTT), make_items(RQ * 4, QTT), make_items(SQ, QTT), make_items(SQ * 4, QTT), make_items(MI, QTT),
-               make_items(NP, QTT), p.prof_tail};
+               make_items(NP, QTT), make_items(NW, QTT), med_len, med_segs, p.prof_tail};
     const dim3 grid((p.cols + p.tw - 1) / p.tw, (p.rows + p.th - 1) / p.th, n_frames);
     DCMT_LAUNCH(k_q8_tail, grid, dim3(QTT), q8_tail_smem(p.th, p.tw), st, a, tmap);
     return cudaGetLastError();
