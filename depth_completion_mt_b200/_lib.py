@@ -45,6 +45,7 @@ class DcmtError(RuntimeError):
 _P = C.c_void_p
 _SIGNATURES = {
     "dcmt_version": (C.c_int, []),
+    "dcmt_build_info": (C.c_char_p, []),
     "dcmt_last_error": (C.c_char_p, []),
     "dcmt_status_string": (C.c_char_p, [C.c_int]),
     "dcmt_device_count": (C.c_int, []),
@@ -78,6 +79,19 @@ _SIGNATURES = {
     "dcmt_slic_center_count": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "dcmt_slic_u8c3": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "dcmt_slic_u8c3_host": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "dcmt_img_completion_f32_host_multi": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int]),
+    "dcmt_img_completion_u16_host_multi": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int]),
+    "dcmt_interpolate_with_superpixels_f32_host_multi": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int]),
+    "dcmt_debug_host_copy_f32": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, C.c_int]),
+    "dcmt_debug_host_copy_u16": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, C.c_int]),
+    "dcmt_entries_measurement_derivatives": (C.c_int, [_P, C.c_int, C.c_int, C.c_size_t, C.c_size_t, _P]),
+    "dcmt_entries_measurement_derivatives_host": (C.c_int, [_P, C.c_int, C.c_int, C.c_size_t, C.c_size_t]),
+    "dcmt_entries_optimize_ig": (C.c_int, [_P, C.c_size_t, _P, C.c_size_t, C.c_size_t, _P, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, _P]),
+    "dcmt_entries_optimize_ig_host": (C.c_int, [_P, C.c_size_t, _P, C.c_size_t, C.c_size_t, _P, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float]),
+    "dcmt_get_initial_disparity_mat_f32": (C.c_int, [_P, C.c_size_t, _P, C.c_size_t, C.c_int, C.c_int, C.c_float, C.c_float, _P]),
+    "dcmt_get_initial_disparity_mat_f32_host": (C.c_int, [_P, C.c_size_t, _P, C.c_size_t, C.c_int, C.c_int, C.c_float, C.c_float]),
+    "dcmt_retrieve_optimized_depth_mat_f32": (C.c_int, [_P, C.c_size_t, _P, C.c_size_t, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, _P]),
+    "dcmt_retrieve_optimized_depth_mat_f32_host": (C.c_int, [_P, C.c_size_t, _P, C.c_size_t, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float]),
     "dcmt_debug_q8_phase_cycles": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, C.POINTER(C.c_int), _P]),
     "dcmt_img_completion_stages_f32": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, C.c_int, C.POINTER(C.c_uint32), _P]),
 }
@@ -108,17 +122,26 @@ def bind(path: str) -> Library:
 _default: Library | None = None
 
 
+def _product(path: str) -> Library:
+    lib = Library(path)
+    info = lib.dcmt_build_info().decode()
+    if not info.startswith("cuda"):  # e.g. the CPU emulator build of tests/emu: test infrastructure, never the product
+        raise ImportError(f"{path} is not a CUDA build of libdcmt ({info!r}); depth_completion_mt_b200 has no CPU fallback.")
+    return lib
+
+
 def load() -> Library:
-    """The product library.  Raises if libdcmt.so is absent -- there is no CPU fallback."""
+    """The product library.  Raises if libdcmt.so is absent -- there is no CPU fallback.  ``load().path`` names the file
+    that was bound (bench.py prints it)."""
     global _default
     if _default is None:
-        alt = os.environ.get("DCMT_LIB")  # A/B builds of the same sources (tools/build_variant.py); still a CUDA library
+        alt = os.environ.get("DCMT_LIB")  # A/B builds of the same sources (tools/build_variant.py); must be a CUDA build
         if alt:
-            _default = Library(alt)
+            _default = _product(alt)
             return _default
         if not os.path.exists(LIB_PATH):
             raise ImportError(
                 f"{LIB_PATH} not found: build it with `python -m depth_completion_mt_b200.build` "
                 "(nvcc, sm_100a). depth_completion_mt_b200 has no CPU fallback.")
-        _default = Library(LIB_PATH)
+        _default = _product(LIB_PATH)
     return _default

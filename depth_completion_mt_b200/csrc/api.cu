@@ -52,6 +52,7 @@ int cuda_fail(cudaError_t e, const char* what) {
 struct Arena {
     char* base = nullptr;
     size_t cap = 0, used = 0;
+    bool overflow = false;  // a carve() went past cap since the last acquire: the caller must not launch anything
 };
 std::mutex g_mu;
 std::map<std::pair<int, cudaStream_t>, Arena> g_arenas;
@@ -76,16 +77,26 @@ int arena_acquire(cudaStream_t st, size_t bytes, Arena** out) {
         a.cap = bytes;
     }
     a.used = 0;
+    a.overflow = false;
     *out = &a;
     return DCMT_OK;
 }
 
+// Bounds-checked: a request past the end of the arena sets `overflow` and returns the arena base (valid memory that
+// must not be used); every caller checks arena_ok() before launching.
 template <class T>
 T* carve(Arena* a, size_t count) {
     const size_t bytes = (count * sizeof(T) + 255) & ~size_t(255);
+    if (a->used + bytes > a->cap) {
+        a->overflow = true;
+        return reinterpret_cast<T*>(a->base);
+    }
     T* p = reinterpret_cast<T*>(a->base + a->used);
     a->used += bytes;
     return p;
+}
+int arena_ok(const Arena* a) {
+    return a->overflow ? fail(DCMT_E_NOMEM, "internal: workspace arena of %zu bytes is too small for this call", a->cap) : DCMT_OK;
 }
 size_t carve_bytes(size_t count, size_t elem) { return (count * elem + 255) & ~size_t(255); }
 
@@ -255,6 +266,7 @@ int enqueue_completion(const CompletionCall& cc, const float* sparse, const int3
         p.w1 = w1;
         p.w2 = w2;
         int* tile_flags = cc.guided ? carve<int>(ar, dcmt::q8_guided_tile_flags(rows, cols, p.th, p.tw, chunk)) : nullptr;
+        if (int rc = arena_ok(ar)) return rc;
         for (int f0 = 0; f0 < n_frames; f0 += chunk) {
             const int nf = n_frames - f0 < chunk ? n_frames - f0 : chunk;
             ProfEvents pe{};
@@ -285,6 +297,7 @@ int enqueue_completion(const CompletionCall& cc, const float* sparse, const int3
         return DCMT_OK;
     }
     float* conv = in16.p ? carve<float>(ar, fpix * chunk) : nullptr;
+    if (int rc = arena_ok(ar)) return rc;
     for (int f0 = 0; f0 < n_frames; f0 += chunk) {
         const int nf = n_frames - f0 < chunk ? n_frames - f0 : chunk;
         dcmt::GenericChunk c{};
@@ -323,20 +336,26 @@ int enqueue_completion(const CompletionCall& cc, const float* sparse, const int3
     return DCMT_OK;
 }
 
-// pinned host scratch for the redo flags (one per device, grow-only)
+// pinned host scratch for the redo flags, one per (device, stream) like the arenas (grow-only): calls on different
+// streams never share a buffer; calls on the SAME stream are ordered by the caller, and a buffer is only replaced
+// after that stream has drained (the previous call's read-back may still be in flight otherwise).  The host-pointer
+// entry points use the key (device, nullptr-stream of the host pipeline) under their per-device mutex.
 struct PinnedFlags {
     int32_t* p = nullptr;
     size_t cap = 0;
 };
-std::map<int, PinnedFlags> g_pinned;
+std::map<std::pair<int, cudaStream_t>, PinnedFlags> g_pinned;
 
-int pinned_flags(size_t n, int32_t** out) {
+int pinned_flags(cudaStream_t key, size_t n, int32_t** out) {
     int dev = 0;
     API_CUDA(cudaGetDevice(&dev), "cudaGetDevice");
     std::lock_guard<std::mutex> lk(g_mu);
-    PinnedFlags& pf = g_pinned[dev];
+    PinnedFlags& pf = g_pinned[{dev, key}];
     if (pf.cap < n) {
-        if (pf.p) cudaFreeHost(pf.p);
+        if (pf.p) {
+            API_CUDA(cudaStreamSynchronize(key), "cudaStreamSynchronize");
+            cudaFreeHost(pf.p);
+        }
         pf.p = nullptr;
         pf.cap = 0;
         void* q = nullptr;
@@ -387,7 +406,7 @@ int run_completion(const float* sparse, const int32_t* labels, int n_clusters, b
     if (!used || flags != DCMT_PATH_AUTO) return DCMT_OK;  // DCMT_PATH_FUSED: fully asynchronous, stats[3] = -1 marks bad frames
     // DCMT_PATH_AUTO: one readback of the per-frame "not strict q8" flags, then the generic pipeline for those frames
     int32_t* h_flags = nullptr;
-    if ((rc = pinned_flags((size_t)n_frames, &h_flags))) return rc;
+    if ((rc = pinned_flags(st, (size_t)n_frames, &h_flags))) return rc;
     API_CUDA(cudaMemcpyAsync(h_flags, d_flags, (size_t)n_frames * sizeof(int32_t), cudaMemcpyDeviceToHost, st), "flag readback");
     API_CUDA(cudaStreamSynchronize(st), "kernel execution");
     cc.flags = DCMT_PATH_GENERIC;
@@ -395,7 +414,9 @@ int run_completion(const float* sparse, const int32_t* labels, int n_clusters, b
         if (!h_flags[f]) { ++f; continue; }
         int e = f;
         while (e < n_frames && h_flags[e]) ++e;
-        ar->used = 0;  // the fused work has completed: the arena is free again
+        // the fused work has completed (stream synchronised above): the arena is free again, but it was sized for the
+        // fused plan -- the generic pipeline of this run may need more (two float planes per frame of its chunk)
+        if ((rc = arena_acquire(st, completion_ws_bytes(rows, cols, e - f, bilateral, false), &ar))) return rc;
         if ((rc = enqueue_completion(cc, sparse + (size_t)f * g.fstride, guided ? labels + (size_t)f * rows * cols : nullptr,
                                      dense + (size_t)f * g.fstride, g.pitch, g.fstride, e - f,
                                      stats ? stats + (size_t)f * DCMT_STATS_STRIDE : nullptr, nullptr, nullptr, nullptr, ar, st, nullptr)))
@@ -406,13 +427,23 @@ int run_completion(const float* sparse, const int32_t* labels, int n_clusters, b
 }
 
 // ---- host-pointer driver: chunks of frames flow H2D -> kernels -> D2H round-robin over three internal
-// streams, so the copies of one chunk overlap the kernels of another.  Copies are asynchronous when the
+// streams per device, so the copies of one chunk overlap the kernels of another.  Copies are asynchronous when the
 // caller's buffers are page-locked (e.g. torch pinned memory); pageable buffers work, just slower.
+//
+// The same driver serves one device (the *_host entry points: the current device) and several (the *_host_multi entry
+// points): the frames of the call are split into one contiguous block per device and the chunks of the blocks are
+// enqueued round-robin by the calling thread -- every copy and launch is asynchronous, so one thread keeps all
+// devices busy; there is no exchange between devices (frames are independent).
+//
+// Thread safety: the internal streams, their arenas and the pinned flag buffer are per device, so the host-pointer
+// entry points take a per-device mutex for the duration of the call (several devices: in ascending device order).
+// Two threads driving two different devices run concurrently; two threads on the same device take turns.
 constexpr int kHostStreams = 3;
 struct HostStreams {
     cudaStream_t s[kHostStreams];
 };
 std::map<int, HostStreams> g_host_streams;
+std::map<int, std::mutex> g_host_mu;  // guarded by g_mu for insertion; std::map never moves its nodes
 
 int host_streams(HostStreams** out) {
     int dev = 0;
@@ -442,88 +473,248 @@ int host_chunk_frames(int rows, int cols, int n_frames) {
     return (int)(c < 1 ? 1 : c);
 }
 
+// One device of a host-pointer call.
+struct Lane {
+    int dev = 0;
+    HostStreams* hs = nullptr;
+    int f_begin = 0, f_end = 0;  // frames of the call served by this device
+    int next = 0, slot = 0;      // next frame to enqueue, stream slot of the next chunk
+    int32_t* h_flags = nullptr;  // pinned, one per frame of the lane (fused AUTO path)
+};
+
+// Scope of a host-pointer call: resolves the device list, takes the per-device mutexes, and on the way out -- success
+// or error -- drains every internal stream of every device it touched (so no copy into the caller's buffers is still
+// in flight after the function has returned) and restores the caller's current device.
+class HostCall {
+   public:
+    ~HostCall() {
+        drain();
+        if (restore_ >= 0) cudaSetDevice(restore_);
+        for (auto it = locks_.rbegin(); it != locks_.rend(); ++it) (*it)->unlock();
+    }
+    // devices == nullptr: n_devices <= 0 -> the current device; otherwise the first n_devices visible devices
+    int open(const int* devices, int n_devices, bool all_if_null) {
+        int rc = check_device();
+        if (rc) return rc;
+        int count = 0, cur = 0;
+        API_CUDA(cudaGetDeviceCount(&count), "cudaGetDeviceCount");
+        API_CUDA(cudaGetDevice(&cur), "cudaGetDevice");
+        restore_ = cur;
+        std::vector<int> ids;
+        if (devices) {
+            if (n_devices < 1) return fail(DCMT_E_BADARG, "n_devices must be >= 1 with an explicit device list (got %d)", n_devices);
+            ids.assign(devices, devices + n_devices);
+        } else if (all_if_null) {
+            const int n = n_devices > 0 ? n_devices : count;
+            if (n > count) return fail(DCMT_E_BADARG, "%d devices requested, %d visible", n, count);
+            for (int d = 0; d < n; ++d) ids.push_back(d);
+        } else {
+            ids.push_back(cur);
+        }
+        std::vector<int> sorted = ids;
+        std::sort(sorted.begin(), sorted.end());
+        for (size_t i = 0; i < sorted.size(); ++i) {
+            if (sorted[i] < 0 || sorted[i] >= count) return fail(DCMT_E_BADARG, "device %d out of range (%d visible)", sorted[i], count);
+            if (i && sorted[i] == sorted[i - 1]) return fail(DCMT_E_BADARG, "device %d listed twice", sorted[i]);
+        }
+        for (int d : sorted) {  // ascending order: two calls with overlapping device sets cannot deadlock
+            std::mutex* m;
+            {
+                std::lock_guard<std::mutex> lk(g_mu);
+                m = &g_host_mu[d];
+            }
+            m->lock();
+            locks_.push_back(m);
+        }
+        lanes.resize(ids.size());
+        for (size_t i = 0; i < ids.size(); ++i) {
+            lanes[i].dev = ids[i];
+            API_CUDA(cudaSetDevice(ids[i]), "cudaSetDevice");
+            if ((rc = host_streams(&lanes[i].hs))) return rc;
+        }
+        return DCMT_OK;
+    }
+    // contiguous blocks of frames, sizes differing by at most one
+    void split(int n_frames) {
+        const int n = (int)lanes.size();
+        for (int i = 0; i < n; ++i) {
+            lanes[i].f_begin = (int)((long long)n_frames * i / n);
+            lanes[i].f_end = (int)((long long)n_frames * (i + 1) / n);
+            lanes[i].next = lanes[i].f_begin;
+        }
+    }
+    int use(Lane& l) {
+        API_CUDA(cudaSetDevice(l.dev), "cudaSetDevice");
+        drained_ = false;  // the caller is about to enqueue on this lane
+        return DCMT_OK;
+    }
+    // waits for all enqueued work; the first error wins
+    int finish() {
+        cudaError_t first = cudaSuccess;
+        for (Lane& l : lanes) {
+            if (!l.hs) continue;
+            cudaSetDevice(l.dev);
+            for (int i = 0; i < kHostStreams; ++i) {
+                const cudaError_t e = cudaStreamSynchronize(l.hs->s[i]);
+                if (e != cudaSuccess && first == cudaSuccess) first = e;
+            }
+        }
+        drained_ = true;
+        return first == cudaSuccess ? DCMT_OK : cuda_fail(first, "kernel execution");
+    }
+    std::vector<Lane> lanes;
+
+   private:
+    void drain() {
+        if (drained_) return;
+        for (Lane& l : lanes) {
+            if (!l.hs) continue;
+            cudaSetDevice(l.dev);
+            for (int i = 0; i < kHostStreams; ++i) cudaStreamSynchronize(l.hs->s[i]);
+        }
+        drained_ = true;
+    }
+    std::vector<std::mutex*> locks_;
+    int restore_ = -1;
+    bool drained_ = false;
+};
+
+int copy_frames_h2d(void* d, size_t d_pitch_bytes, const void* h, size_t h_pitch_bytes, size_t h_fstride_bytes, size_t row_bytes, int rows,
+                    int nf, cudaStream_t st) {
+    if (d_pitch_bytes == row_bytes && h_pitch_bytes == row_bytes && h_fstride_bytes == row_bytes * rows) {
+        API_CUDA(cudaMemcpyAsync(d, h, row_bytes * rows * nf, cudaMemcpyHostToDevice, st), "host to device copy");
+    } else if (h_fstride_bytes == h_pitch_bytes * (size_t)rows) {  // frames back to back: one 2-D copy for the whole chunk
+        API_CUDA(cudaMemcpy2DAsync(d, d_pitch_bytes, h, h_pitch_bytes, row_bytes, (size_t)rows * nf, cudaMemcpyHostToDevice, st),
+                 "host to device copy");
+    } else {
+        for (int f = 0; f < nf; ++f)
+            API_CUDA(cudaMemcpy2DAsync(static_cast<char*>(d) + (size_t)f * rows * d_pitch_bytes, d_pitch_bytes,
+                                       static_cast<const char*>(h) + (size_t)f * h_fstride_bytes, h_pitch_bytes, row_bytes, rows,
+                                       cudaMemcpyHostToDevice, st),
+                     "host to device copy");
+    }
+    return DCMT_OK;
+}
+
+int copy_frames_d2h(void* h, size_t h_pitch_bytes, size_t h_fstride_bytes, const void* d, size_t row_bytes, int rows, int nf, cudaStream_t st) {
+    if (h_pitch_bytes == row_bytes && h_fstride_bytes == row_bytes * rows) {
+        API_CUDA(cudaMemcpyAsync(h, d, row_bytes * rows * nf, cudaMemcpyDeviceToHost, st), "device to host copy");
+    } else if (h_fstride_bytes == h_pitch_bytes * (size_t)rows) {
+        API_CUDA(cudaMemcpy2DAsync(h, h_pitch_bytes, d, row_bytes, row_bytes, (size_t)rows * nf, cudaMemcpyDeviceToHost, st), "device to host copy");
+    } else {
+        for (int f = 0; f < nf; ++f)
+            API_CUDA(cudaMemcpy2DAsync(static_cast<char*>(h) + (size_t)f * h_fstride_bytes, h_pitch_bytes,
+                                       static_cast<const char*>(d) + (size_t)f * rows * row_bytes, row_bytes, row_bytes, rows,
+                                       cudaMemcpyDeviceToHost, st),
+                     "device to host copy");
+    }
+    return DCMT_OK;
+}
+
+// copy_only: the same buffers, chunking and streams with the kernels left out (the input is echoed to the output) --
+// the ceiling the host <-> device links put on the end-to-end rate (dcmt_debug_host_copy_*).
 int run_completion_host(const float* sparse, const int32_t* labels, int n_clusters, bool guided, float* dense, int rows,
                         int cols, size_t pitch_bytes, size_t frame_stride_bytes, int n_frames, int blur_type, int flags,
-                        int32_t* stats) {
+                        int32_t* stats, const int* devices = nullptr, int n_devices = 0, bool multi = false, bool copy_only = false) {
     Geometry g;
     int rc = validate_completion(sparse, labels, guided, dense, rows, cols, pitch_bytes, frame_stride_bytes, n_frames,
                                  blur_type, flags, &g);
     if (rc) return rc;
     if (n_frames == 0) return DCMT_OK;
-    if ((rc = check_device())) return rc;
-    API_CUDA(dcmt::generic_configure(), "kernel attribute setup");
-    API_CUDA(dcmt::q8_configure(), "kernel attribute setup");
-    HostStreams* hs = nullptr;
-    if ((rc = host_streams(&hs))) return rc;
+    HostCall call;
+    if ((rc = call.open(devices, n_devices, multi))) return rc;
+    call.split(n_frames);
     const size_t fpix = (size_t)rows * cols;
-    const int hc = host_chunk_frames(rows, cols, n_frames);
     const bool bilateral = blur_type == DCMT_BLUR_BILATERAL;
     const size_t row_bytes = (size_t)cols * sizeof(float);
-    const bool dense_rows = g.pitch == (size_t)cols;
     const CompletionCall cc{labels, n_clusters, guided, rows, cols, blur_type, flags};
-    const bool fused = fused_applies(cc);
+    const bool fused = fused_applies(cc) && !copy_only;
+    int longest = 0;
+    for (Lane& l : call.lanes) longest = std::max(longest, l.f_end - l.f_begin);
+    const int hc = host_chunk_frames(rows, cols, longest);
     const size_t bytes = 2 * carve_bytes(fpix * hc, sizeof(float)) + (guided ? carve_bytes(fpix * hc, sizeof(int32_t)) : 0) +
                          carve_bytes((size_t)hc * DCMT_STATS_STRIDE, sizeof(int32_t)) + carve_bytes((size_t)hc, sizeof(int32_t)) +
                          completion_ws_bytes(rows, cols, hc, bilateral, fused);
-    int32_t* h_flags = nullptr;
-    if (fused && (rc = pinned_flags((size_t)n_frames, &h_flags))) return rc;
-    int slot = 0;
-    for (int f0 = 0; f0 < n_frames; f0 += hc, slot = (slot + 1) % kHostStreams) {
-        const int nf = n_frames - f0 < hc ? n_frames - f0 : hc;
-        cudaStream_t st = hs->s[slot];
+    for (Lane& l : call.lanes) {
+        if (l.f_end == l.f_begin) continue;
+        if ((rc = call.use(l))) return rc;
+        API_CUDA(dcmt::generic_configure(), "kernel attribute setup");
+        API_CUDA(dcmt::q8_configure(), "kernel attribute setup");
+        if (fused && (rc = pinned_flags(nullptr, (size_t)(l.f_end - l.f_begin), &l.h_flags))) return rc;
+    }
+    // one chunk [f0, f0 + nf) of lane l on its next stream: H2D, kernels, D2H
+    auto do_chunk = [&](Lane& l, int f0, int nf, const CompletionCall& c2, bool fused2, int hc2, size_t bytes2) -> int {
+        int rc2;
+        cudaStream_t st = l.hs->s[l.slot];
+        l.slot = (l.slot + 1) % kHostStreams;
         Arena* ar = nullptr;
-        if ((rc = arena_acquire(st, bytes, &ar))) return rc;  // stream order protects reuse by the chunk 3 steps later
-        float* d_in = carve<float>(ar, fpix * hc);
-        float* d_out = carve<float>(ar, fpix * hc);
-        int32_t* d_lab = guided ? carve<int32_t>(ar, fpix * hc) : nullptr;
-        int32_t* d_stats = carve<int32_t>(ar, (size_t)hc * DCMT_STATS_STRIDE);
-        int32_t* d_flags = carve<int32_t>(ar, (size_t)hc);
-        const float* h_in = sparse + (size_t)f0 * g.fstride;
-        float* h_out = dense + (size_t)f0 * g.fstride;
-        if (dense_rows && g.fstride == fpix) {
-            API_CUDA(cudaMemcpyAsync(d_in, h_in, fpix * nf * sizeof(float), cudaMemcpyHostToDevice, st), "host to device copy");
-        } else {
-            for (int f = 0; f < nf; ++f)
-                API_CUDA(cudaMemcpy2DAsync(d_in + (size_t)f * fpix, row_bytes, h_in + (size_t)f * g.fstride,
-                                           g.pitch * sizeof(float), row_bytes, rows, cudaMemcpyHostToDevice, st),
-                         "host to device copy");
-        }
+        if ((rc2 = arena_acquire(st, bytes2, &ar))) return rc2;  // stream order protects reuse by the chunk 3 steps later
+        float* d_in = carve<float>(ar, fpix * hc2);
+        float* d_out = carve<float>(ar, fpix * hc2);
+        int32_t* d_lab = guided ? carve<int32_t>(ar, fpix * hc2) : nullptr;
+        int32_t* d_stats = carve<int32_t>(ar, (size_t)hc2 * DCMT_STATS_STRIDE);
+        int32_t* d_flags = carve<int32_t>(ar, (size_t)hc2);
+        if ((rc2 = arena_ok(ar))) return rc2;
+        if ((rc2 = copy_frames_h2d(d_in, row_bytes, sparse + (size_t)f0 * g.fstride, g.pitch * sizeof(float), g.fstride * sizeof(float),
+                                   row_bytes, rows, nf, st)))
+            return rc2;
         if (guided)
             API_CUDA(cudaMemcpyAsync(d_lab, labels + (size_t)f0 * fpix, fpix * nf * sizeof(int32_t), cudaMemcpyHostToDevice, st),
                      "host to device copy");
-        if ((rc = enqueue_completion(cc, d_in, d_lab, d_out, cols, fpix, nf, stats ? d_stats : nullptr, fused ? d_flags : nullptr,
-                                     nullptr, nullptr, ar, st, nullptr)))
-            return rc;
-        if (fused)
-            API_CUDA(cudaMemcpyAsync(h_flags + f0, d_flags, (size_t)nf * sizeof(int32_t), cudaMemcpyDeviceToHost, st), "flag readback");
-        if (dense_rows && g.fstride == fpix) {
-            API_CUDA(cudaMemcpyAsync(h_out, d_out, fpix * nf * sizeof(float), cudaMemcpyDeviceToHost, st), "device to host copy");
-        } else {
-            for (int f = 0; f < nf; ++f)
-                API_CUDA(cudaMemcpy2DAsync(h_out + (size_t)f * g.fstride, g.pitch * sizeof(float), d_out + (size_t)f * fpix,
-                                           row_bytes, row_bytes, rows, cudaMemcpyDeviceToHost, st),
-                         "device to host copy");
+        if (copy_only) {
+            d_out = d_in;
+        } else if ((rc2 = enqueue_completion(c2, d_in, d_lab, d_out, cols, fpix, nf, stats ? d_stats : nullptr, fused2 ? d_flags : nullptr,
+                                             nullptr, nullptr, ar, st, nullptr))) {
+            return rc2;
         }
-        if (stats)
+        if (fused2)
+            API_CUDA(cudaMemcpyAsync(l.h_flags + (f0 - l.f_begin), d_flags, (size_t)nf * sizeof(int32_t), cudaMemcpyDeviceToHost, st),
+                     "flag readback");
+        if ((rc2 = copy_frames_d2h(dense + (size_t)f0 * g.fstride, g.pitch * sizeof(float), g.fstride * sizeof(float), d_out, row_bytes, rows,
+                                   nf, st)))
+            return rc2;
+        if (stats && !copy_only)
             API_CUDA(cudaMemcpyAsync(stats + (size_t)f0 * DCMT_STATS_STRIDE, d_stats, (size_t)nf * DCMT_STATS_STRIDE * sizeof(int32_t),
                                      cudaMemcpyDeviceToHost, st),
                      "device to host copy");
-    }
-    for (int i = 0; i < kHostStreams; ++i) API_CUDA(cudaStreamSynchronize(hs->s[i]), "kernel execution");
-    if (fused && flags == DCMT_PATH_AUTO) {
-        // frames that turned out not to be strict q8 go through the generic pipeline (runs of consecutive frames)
-        for (int f = 0; f < n_frames;) {
-            if (!h_flags[f]) { ++f; continue; }
-            int e = f;
-            while (e < n_frames && h_flags[e]) ++e;
-            std::vector<int32_t> keep(h_flags + e, h_flags + n_frames);  // the nested call reuses the pinned buffer
-            rc = run_completion_host(sparse + (size_t)f * g.fstride, guided ? labels + (size_t)f * fpix : nullptr, n_clusters, guided,
-                                     dense + (size_t)f * g.fstride, rows, cols, pitch_bytes, frame_stride_bytes, e - f, blur_type,
-                                     DCMT_PATH_GENERIC, stats ? stats + (size_t)f * DCMT_STATS_STRIDE : nullptr);
-            if (rc) return rc;
-            std::copy(keep.begin(), keep.end(), h_flags + e);
-            f = e;
+        return DCMT_OK;
+    };
+    for (bool more = true; more;) {
+        more = false;
+        for (Lane& l : call.lanes) {
+            if (l.next >= l.f_end) continue;
+            more = true;
+            if ((rc = call.use(l))) return rc;
+            const int f0 = l.next, nf = std::min(hc, l.f_end - f0);
+            l.next += nf;
+            if ((rc = do_chunk(l, f0, nf, cc, fused, hc, bytes))) return rc;
         }
+    }
+    if ((rc = call.finish())) return rc;
+    if (fused && flags == DCMT_PATH_AUTO) {
+        // frames that turned out not to be strict q8 go through the generic pipeline (runs of consecutive frames) on the
+        // device that served them, through the same chunk pipeline
+        CompletionCall cg = cc;
+        cg.flags = DCMT_PATH_GENERIC;
+        bool any = false;
+        for (Lane& l : call.lanes) {
+            const int n_lane = l.f_end - l.f_begin;
+            for (int i = 0; i < n_lane;) {
+                if (!l.h_flags[i]) { ++i; continue; }
+                int e = i;
+                while (e < n_lane && l.h_flags[e]) ++e;
+                if ((rc = call.use(l))) return rc;
+                const int hc2 = host_chunk_frames(rows, cols, e - i);
+                const size_t bytes2 = 2 * carve_bytes(fpix * hc2, sizeof(float)) + (guided ? carve_bytes(fpix * hc2, sizeof(int32_t)) : 0) +
+                                      carve_bytes((size_t)hc2 * DCMT_STATS_STRIDE, sizeof(int32_t)) + carve_bytes((size_t)hc2, sizeof(int32_t)) +
+                                      completion_ws_bytes(rows, cols, hc2, bilateral, false);
+                for (int f = l.f_begin + i; f < l.f_begin + e; f += hc2)
+                    if ((rc = do_chunk(l, f, std::min(hc2, l.f_begin + e - f), cg, false, hc2, bytes2))) return rc;
+                any = true;
+                i = e;
+            }
+        }
+        if (any && (rc = call.finish())) return rc;
     }
     return DCMT_OK;
 }
@@ -564,66 +755,67 @@ int run_completion_u16(const uint16_t* sparse, float* dense, int rows, int cols,
 
 int run_completion_u16_host(const uint16_t* sparse, float* dense, int rows, int cols, size_t in_pitch_bytes,
                             size_t in_frame_stride_bytes, size_t out_pitch_bytes, size_t out_frame_stride_bytes, int n_frames,
-                            int blur_type, int flags, int32_t* stats) {
+                            int blur_type, int flags, int32_t* stats, const int* devices = nullptr, int n_devices = 0, bool multi = false,
+                            bool copy_only = false) {
     Geometry gi, go;
     int rc = validate_completion_u16(sparse, dense, rows, cols, in_pitch_bytes, in_frame_stride_bytes, out_pitch_bytes,
                                      out_frame_stride_bytes, n_frames, blur_type, flags, &gi, &go);
     if (rc) return rc;
     if (n_frames == 0) return DCMT_OK;
-    if ((rc = check_device())) return rc;
-    API_CUDA(dcmt::generic_configure(), "kernel attribute setup");
-    API_CUDA(dcmt::q8_configure(), "kernel attribute setup");
-    HostStreams* hs = nullptr;
-    if ((rc = host_streams(&hs))) return rc;
+    HostCall call;
+    if ((rc = call.open(devices, n_devices, multi))) return rc;
+    call.split(n_frames);
     const size_t fpix = (size_t)rows * cols;
     const size_t in_pitch = ((size_t)cols + 7) / 8 * 8;  // device rows 16-byte aligned: vector loads in k_q8_front
-    const int hc = host_chunk_frames(rows, cols, n_frames);
+    int longest = 0;
+    for (Lane& l : call.lanes) longest = std::max(longest, l.f_end - l.f_begin);
+    const int hc = host_chunk_frames(rows, cols, longest);
     CompletionCall cc{nullptr, 0, false, rows, cols, blur_type, flags == DCMT_PATH_GENERIC ? DCMT_PATH_GENERIC : DCMT_PATH_FUSED};
     const bool fused = fused_applies(cc);
     const size_t bytes = carve_bytes((size_t)rows * in_pitch * hc, sizeof(uint16_t)) + carve_bytes(fpix * hc, sizeof(float)) +
                          carve_bytes((size_t)hc * DCMT_STATS_STRIDE, sizeof(int32_t)) +
                          completion_ws_bytes(rows, cols, hc, blur_type == DCMT_BLUR_BILATERAL, fused, true);
-    int slot = 0;
-    for (int f0 = 0; f0 < n_frames; f0 += hc, slot = (slot + 1) % kHostStreams) {
-        const int nf = n_frames - f0 < hc ? n_frames - f0 : hc;
-        cudaStream_t st = hs->s[slot];
-        Arena* ar = nullptr;
-        if ((rc = arena_acquire(st, bytes, &ar))) return rc;
-        uint16_t* d_in = carve<uint16_t>(ar, (size_t)rows * in_pitch * hc);
-        float* d_out = carve<float>(ar, fpix * hc);
-        int32_t* d_stats = carve<int32_t>(ar, (size_t)hc * DCMT_STATS_STRIDE);
-        const uint16_t* h_in = sparse + (size_t)f0 * gi.fstride;
-        float* h_out = dense + (size_t)f0 * go.fstride;
-        if (in_pitch == (size_t)cols && gi.pitch == (size_t)cols && gi.fstride == fpix) {
-            API_CUDA(cudaMemcpyAsync(d_in, h_in, fpix * nf * sizeof(uint16_t), cudaMemcpyHostToDevice, st), "host to device copy");
-        } else if (gi.fstride == gi.pitch * (size_t)rows) {  // frames back to back: one 2-D copy for the whole chunk
-            API_CUDA(cudaMemcpy2DAsync(d_in, in_pitch * sizeof(uint16_t), h_in, gi.pitch * sizeof(uint16_t),
-                                       (size_t)cols * sizeof(uint16_t), (size_t)rows * nf, cudaMemcpyHostToDevice, st),
-                     "host to device copy");
-        } else {
-            for (int f = 0; f < nf; ++f)
-                API_CUDA(cudaMemcpy2DAsync(d_in + (size_t)f * rows * in_pitch, in_pitch * sizeof(uint16_t), h_in + (size_t)f * gi.fstride,
-                                           gi.pitch * sizeof(uint16_t), (size_t)cols * sizeof(uint16_t), rows, cudaMemcpyHostToDevice, st),
-                         "host to device copy");
-        }
-        if ((rc = enqueue_completion(cc, nullptr, nullptr, d_out, cols, fpix, nf, stats ? d_stats : nullptr, nullptr, nullptr, nullptr,
-                                     ar, st, nullptr, U16Input{d_in, in_pitch, (size_t)rows * in_pitch})))
-            return rc;
-        if (go.pitch == (size_t)cols && go.fstride == fpix) {
-            API_CUDA(cudaMemcpyAsync(h_out, d_out, fpix * nf * sizeof(float), cudaMemcpyDeviceToHost, st), "device to host copy");
-        } else {
-            for (int f = 0; f < nf; ++f)
-                API_CUDA(cudaMemcpy2DAsync(h_out + (size_t)f * go.fstride, go.pitch * sizeof(float), d_out + (size_t)f * fpix,
-                                           (size_t)cols * sizeof(float), (size_t)cols * sizeof(float), rows, cudaMemcpyDeviceToHost, st),
+    for (Lane& l : call.lanes) {
+        if (l.f_end == l.f_begin) continue;
+        if ((rc = call.use(l))) return rc;
+        API_CUDA(dcmt::generic_configure(), "kernel attribute setup");
+        API_CUDA(dcmt::q8_configure(), "kernel attribute setup");
+    }
+    for (bool more = true; more;) {
+        more = false;
+        for (Lane& l : call.lanes) {
+            if (l.next >= l.f_end) continue;
+            more = true;
+            if ((rc = call.use(l))) return rc;
+            const int f0 = l.next, nf = std::min(hc, l.f_end - f0);
+            l.next += nf;
+            cudaStream_t st = l.hs->s[l.slot];
+            l.slot = (l.slot + 1) % kHostStreams;
+            Arena* ar = nullptr;
+            if ((rc = arena_acquire(st, bytes, &ar))) return rc;
+            uint16_t* d_in = carve<uint16_t>(ar, (size_t)rows * in_pitch * hc);
+            float* d_out = carve<float>(ar, fpix * hc);
+            int32_t* d_stats = carve<int32_t>(ar, (size_t)hc * DCMT_STATS_STRIDE);
+            if ((rc = arena_ok(ar))) return rc;
+            if ((rc = copy_frames_h2d(d_in, in_pitch * sizeof(uint16_t), sparse + (size_t)f0 * gi.fstride, gi.pitch * sizeof(uint16_t),
+                                      gi.fstride * sizeof(uint16_t), (size_t)cols * sizeof(uint16_t), rows, nf, st)))
+                return rc;
+            if (copy_only) {
+                API_CUDA(cudaMemsetAsync(d_out, 0, fpix * nf * sizeof(float), st), "memset");
+            } else if ((rc = enqueue_completion(cc, nullptr, nullptr, d_out, cols, fpix, nf, stats ? d_stats : nullptr, nullptr, nullptr,
+                                                nullptr, ar, st, nullptr, U16Input{d_in, in_pitch, (size_t)rows * in_pitch}))) {
+                return rc;
+            }
+            if ((rc = copy_frames_d2h(dense + (size_t)f0 * go.fstride, go.pitch * sizeof(float), go.fstride * sizeof(float), d_out,
+                                      (size_t)cols * sizeof(float), rows, nf, st)))
+                return rc;
+            if (stats && !copy_only)
+                API_CUDA(cudaMemcpyAsync(stats + (size_t)f0 * DCMT_STATS_STRIDE, d_stats, (size_t)nf * DCMT_STATS_STRIDE * sizeof(int32_t),
+                                         cudaMemcpyDeviceToHost, st),
                          "device to host copy");
         }
-        if (stats)
-            API_CUDA(cudaMemcpyAsync(stats + (size_t)f0 * DCMT_STATS_STRIDE, d_stats, (size_t)nf * DCMT_STATS_STRIDE * sizeof(int32_t),
-                                     cudaMemcpyDeviceToHost, st),
-                     "device to host copy");
     }
-    for (int i = 0; i < kHostStreams; ++i) API_CUDA(cudaStreamSynchronize(hs->s[i]), "kernel execution");
-    return DCMT_OK;
+    return call.finish();
 }
 
 }  // namespace
@@ -633,6 +825,13 @@ extern "C" {
 static int check_planes(int rows, int cols, int n_frames);
 
 int dcmt_version(void) { return DCMT_VERSION; }
+const char* dcmt_build_info(void) {
+#ifdef DCMT_EMU
+    return "emulator (tests only)";
+#else
+    return "cuda sm_100a";
+#endif
+}
 const char* dcmt_last_error(void) { return g_err; }
 
 const char* dcmt_status_string(int status) {
@@ -742,6 +941,37 @@ int dcmt_img_completion_u16_host(const uint16_t* sparse_u16, float* dense, int r
                                    out_frame_stride_bytes, n_frames, blur_type, flags, stats);
 }
 
+int dcmt_img_completion_f32_host_multi(const float* sparse, float* dense, int rows, int cols, size_t pitch_bytes,
+                                       size_t frame_stride_bytes, int n_frames, int blur_type, int flags, int32_t* stats,
+                                       const int* devices, int n_devices) {
+    return run_completion_host(sparse, nullptr, 0, false, dense, rows, cols, pitch_bytes, frame_stride_bytes, n_frames,
+                               blur_type, flags, stats, devices, n_devices, true);
+}
+
+int dcmt_img_completion_u16_host_multi(const uint16_t* sparse_u16, float* dense, int rows, int cols, size_t in_pitch_bytes,
+                                       size_t in_frame_stride_bytes, size_t out_pitch_bytes, size_t out_frame_stride_bytes,
+                                       int n_frames, int blur_type, int flags, int32_t* stats, const int* devices, int n_devices) {
+    return run_completion_u16_host(sparse_u16, dense, rows, cols, in_pitch_bytes, in_frame_stride_bytes, out_pitch_bytes,
+                                   out_frame_stride_bytes, n_frames, blur_type, flags, stats, devices, n_devices, true);
+}
+
+int dcmt_interpolate_with_superpixels_f32_host_multi(const float* sparse, const int32_t* labels, int n_clusters, float* dense, int rows,
+                                                     int cols, size_t pitch_bytes, size_t frame_stride_bytes, int n_frames,
+                                                     int use_superpixel, int flags, int32_t* stats, const int* devices, int n_devices) {
+    return run_completion_host(sparse, labels, n_clusters, use_superpixel != 0, dense, rows, cols, pitch_bytes, frame_stride_bytes,
+                               n_frames, DCMT_BLUR_GAUSSIAN, flags, stats, devices, n_devices, true);
+}
+
+int dcmt_debug_host_copy_f32(const float* in, float* out, int rows, int cols, int n_frames, const int* devices, int n_devices) {
+    return run_completion_host(in, nullptr, 0, false, out, rows, cols, 0, 0, n_frames, DCMT_BLUR_NONE, DCMT_PATH_AUTO, nullptr, devices,
+                               n_devices, devices != nullptr || n_devices != 0, true);
+}
+
+int dcmt_debug_host_copy_u16(const uint16_t* in, float* out, int rows, int cols, int n_frames, const int* devices, int n_devices) {
+    return run_completion_u16_host(in, out, rows, cols, 0, 0, 0, 0, n_frames, DCMT_BLUR_NONE, DCMT_PATH_AUTO, nullptr, devices, n_devices,
+                                   devices != nullptr || n_devices != 0, true);
+}
+
 int dcmt_interpolate_with_superpixels_ex_f32(const float* sparse, const int32_t* labels, int n_clusters, float* dense, int rows,
                                              int cols, size_t pitch_bytes, size_t frame_stride_bytes, int n_frames, int use_superpixel,
                                              int flags, int32_t* stats, void* cuda_stream) {
@@ -809,6 +1039,7 @@ int dcmt_debug_q8_phase_cycles(const float* sparse, float* dense, int rows, int 
     p.mid = carve<uint16_t>(ar, (size_t)rows * mid_pitch * n_frames);
     p.col_first = carve<uint32_t>(ar, mid_pitch * n_frames);
     p.col_last = carve<uint32_t>(ar, mid_pitch * n_frames);
+    if ((rc = arena_ok(ar))) return rc;
     p.prof_front = front_stamps;
     p.prof_tail = tail_stamps;
     if (tiles_per_frame) *tiles_per_frame = ((cols + p.tw - 1) / p.tw) * ((rows + p.th - 1) / p.th);
@@ -850,6 +1081,7 @@ int dcmt_slic_u8c3(const uint8_t* lab, int rows, int cols, int n_frames, int ste
     w.bin_fill = carve<int>(ar, nb);
     w.bin_items = carve<int>(ar, kk);
     w.sorted = carve<double>(ar, kk * 5);
+    if ((rc = arena_ok(ar))) return rc;
     API_CUDA(dcmt::slic_run(lab, rows, cols, n_frames, step, nc, iterations, labels, k, w, st), "SLIC launch");
     if (centers && k > 0)
         API_CUDA(cudaMemcpyAsync(centers, w.centers, (size_t)k * n_frames * 5 * sizeof(double), cudaMemcpyDeviceToDevice, st), "centre copy");
@@ -862,32 +1094,28 @@ int dcmt_slic_u8c3_host(const uint8_t* lab, int rows, int cols, int n_frames, in
     int rc = check_planes(rows, cols, n_frames);
     if (rc) return rc;
     if (n_frames == 0) return DCMT_OK;
-    if ((rc = check_device())) return rc;
+    HostCall call;
+    if ((rc = call.open(nullptr, 0, false))) return rc;
+    // staging buffers come from the arena of an internal stream (no cudaMalloc per call), copies are asynchronous on it
+    cudaStream_t st = call.lanes[0].hs->s[0];
     const size_t n = (size_t)rows * cols * n_frames;
     const size_t k = (size_t)(step >= 1 ? dcmt::slic_center_count(rows, cols, step) : 0) * n_frames;
-    uint8_t* d_lab = nullptr;
-    int32_t* d_labels = nullptr;
-    double* d_centers = nullptr;
-    auto cleanup = [&] { cudaFree(d_lab); cudaFree(d_labels); cudaFree(d_centers); };
-    cudaError_t e;
-    if ((e = cudaMalloc(&d_lab, n * 3)) != cudaSuccess || (e = cudaMalloc(&d_labels, n * 4)) != cudaSuccess ||
-        (e = cudaMalloc(&d_centers, (k > 0 ? k : 1) * 5 * sizeof(double))) != cudaSuccess) {
-        cleanup();
-        return fail(DCMT_E_NOMEM, "device staging buffers: %s", cudaGetErrorString(e));
+    Arena* stage = nullptr;
+    {
+        // a second arena key on the same device: the SLIC work arena is keyed by `st`, the staging one by the next stream
+        cudaStream_t st2 = call.lanes[0].hs->s[1];
+        if ((rc = arena_acquire(st2, carve_bytes(n * 3, 1) + carve_bytes(n, 4) + carve_bytes((k > 0 ? k : 1) * 5, sizeof(double)), &stage))) return rc;
     }
-    if ((e = cudaMemcpy(d_lab, lab, n * 3, cudaMemcpyHostToDevice)) != cudaSuccess) {
-        cleanup();
-        return cuda_fail(e, "host to device copy");
-    }
-    rc = dcmt_slic_u8c3(d_lab, rows, cols, n_frames, step, nc, iterations, d_labels, centers ? d_centers : nullptr, nullptr);
-    if (rc == DCMT_OK) {
-        if ((e = cudaStreamSynchronize(nullptr)) != cudaSuccess) rc = cuda_fail(e, "kernel execution");
-        else if ((e = cudaMemcpy(labels, d_labels, n * 4, cudaMemcpyDeviceToHost)) != cudaSuccess) rc = cuda_fail(e, "device to host copy");
-        else if (centers && k > 0 && (e = cudaMemcpy(centers, d_centers, k * 5 * sizeof(double), cudaMemcpyDeviceToHost)) != cudaSuccess)
-            rc = cuda_fail(e, "device to host copy");
-    }
-    cleanup();
-    return rc;
+    uint8_t* d_lab = carve<uint8_t>(stage, n * 3);
+    int32_t* d_labels = carve<int32_t>(stage, n);
+    double* d_centers = carve<double>(stage, (k > 0 ? k : 1) * 5);
+    if ((rc = arena_ok(stage))) return rc;
+    call.use(call.lanes[0]);
+    API_CUDA(cudaMemcpyAsync(d_lab, lab, n * 3, cudaMemcpyHostToDevice, st), "host to device copy");
+    if ((rc = dcmt_slic_u8c3(d_lab, rows, cols, n_frames, step, nc, iterations, d_labels, centers ? d_centers : nullptr, st))) return rc;
+    API_CUDA(cudaMemcpyAsync(labels, d_labels, n * 4, cudaMemcpyDeviceToHost, st), "device to host copy");
+    if (centers && k > 0) API_CUDA(cudaMemcpyAsync(centers, d_centers, k * 5 * sizeof(double), cudaMemcpyDeviceToHost, st), "device to host copy");
+    return call.finish();
 }
 
 int dcmt_lidar_project_f32(const float* points, int n_points, const float* T_host, const float* P_host, int rows, int cols,
@@ -904,6 +1132,7 @@ int dcmt_lidar_project_f32(const float* points, int n_points, const float* T_hos
     const size_t nk = dcmt::project_key_count(rows, cols);
     if ((rc = arena_acquire(st, carve_bytes(nk, sizeof(unsigned long long)) + carve_bytes(8, sizeof(unsigned)), &ar))) return rc;
     dcmt::ProjectWork w{carve<unsigned long long>(ar, nk), carve<unsigned>(ar, 8)};
+    if ((rc = arena_ok(ar))) return rc;
     API_CUDA(dcmt::project_run(points, n_points, T_host, P_host, rows, cols, projected, normalized, norm_a, norm_b, n_projected, w, st),
              "projection launch");
     return DCMT_OK;
@@ -915,30 +1144,25 @@ int dcmt_lidar_project_f32_host(const float* points, int n_points, const float* 
     if (n_points < 0) return fail(DCMT_E_BADARG, "n_points must be >= 0 (got %d)", n_points);
     int rc = check_planes(rows, cols, 1);
     if (rc) return rc;
-    if ((rc = check_device())) return rc;
+    HostCall call;
+    if ((rc = call.open(nullptr, 0, false))) return rc;
+    cudaStream_t st = call.lanes[0].hs->s[0], st2 = call.lanes[0].hs->s[1];
     const size_t n = (size_t)rows * cols;
-    float *d_pts = nullptr, *d_proj = nullptr, *d_norm = nullptr;
-    int32_t* d_cnt = nullptr;
-    auto cleanup = [&] { cudaFree(d_pts); cudaFree(d_proj); cudaFree(d_norm); cudaFree(d_cnt); };
-    cudaError_t e;
-    if ((e = cudaMalloc(&d_pts, (size_t)(n_points > 0 ? n_points : 1) * 16)) != cudaSuccess || (e = cudaMalloc(&d_proj, n * 4)) != cudaSuccess ||
-        (e = cudaMalloc(&d_norm, n * 4)) != cudaSuccess || (e = cudaMalloc(&d_cnt, 4)) != cudaSuccess) {
-        cleanup();
-        return fail(DCMT_E_NOMEM, "device staging buffers: %s", cudaGetErrorString(e));
-    }
-    if (n_points > 0 && (e = cudaMemcpy(d_pts, points, (size_t)n_points * 16, cudaMemcpyHostToDevice)) != cudaSuccess) {
-        cleanup();
-        return cuda_fail(e, "host to device copy");
-    }
-    rc = dcmt_lidar_project_f32(d_pts, n_points, T_host, P_host, rows, cols, d_proj, d_norm, norm_a, norm_b, d_cnt, nullptr);
-    if (rc == DCMT_OK) {
-        if ((e = cudaStreamSynchronize(nullptr)) != cudaSuccess) rc = cuda_fail(e, "kernel execution");
-        else if (projected && (e = cudaMemcpy(projected, d_proj, n * 4, cudaMemcpyDeviceToHost)) != cudaSuccess) rc = cuda_fail(e, "device to host copy");
-        else if (normalized && (e = cudaMemcpy(normalized, d_norm, n * 4, cudaMemcpyDeviceToHost)) != cudaSuccess) rc = cuda_fail(e, "device to host copy");
-        else if (n_projected && (e = cudaMemcpy(n_projected, d_cnt, 4, cudaMemcpyDeviceToHost)) != cudaSuccess) rc = cuda_fail(e, "device to host copy");
-    }
-    cleanup();
-    return rc;
+    Arena* stage = nullptr;
+    if ((rc = arena_acquire(st2, carve_bytes((size_t)(n_points > 0 ? n_points : 1) * 4, 4) + 2 * carve_bytes(n, 4) + carve_bytes(1, 4), &stage)))
+        return rc;
+    float* d_pts = carve<float>(stage, (size_t)(n_points > 0 ? n_points : 1) * 4);
+    float* d_proj = carve<float>(stage, n);
+    float* d_norm = carve<float>(stage, n);
+    int32_t* d_cnt = carve<int32_t>(stage, 1);
+    if ((rc = arena_ok(stage))) return rc;
+    call.use(call.lanes[0]);
+    if (n_points > 0) API_CUDA(cudaMemcpyAsync(d_pts, points, (size_t)n_points * 16, cudaMemcpyHostToDevice, st), "host to device copy");
+    if ((rc = dcmt_lidar_project_f32(d_pts, n_points, T_host, P_host, rows, cols, d_proj, d_norm, norm_a, norm_b, d_cnt, st))) return rc;
+    if (projected) API_CUDA(cudaMemcpyAsync(projected, d_proj, n * 4, cudaMemcpyDeviceToHost, st), "device to host copy");
+    if (normalized) API_CUDA(cudaMemcpyAsync(normalized, d_norm, n * 4, cudaMemcpyDeviceToHost, st), "device to host copy");
+    if (n_projected) API_CUDA(cudaMemcpyAsync(n_projected, d_cnt, 4, cudaMemcpyDeviceToHost, st), "device to host copy");
+    return call.finish();
 }
 
 static_assert(sizeof(dcmt_eval_result) == sizeof(dcmt::EvalResult), "dcmt_eval_result and dcmt::EvalResult must match");
@@ -956,6 +1180,7 @@ int dcmt_evaluate_f32(const float* gt, const float* dense, int rows, int cols, s
     Arena* ar = nullptr;
     if ((rc = arena_acquire(st, carve_bytes(dcmt::eval_partial_doubles(n_frames), sizeof(double)), &ar))) return rc;
     double* partials = carve<double>(ar, dcmt::eval_partial_doubles(n_frames));
+    if ((rc = arena_ok(ar))) return rc;
     API_CUDA(dcmt::eval_run(gt, dense, rows, cols, g.pitch, g.fstride, n_frames, tolerance, mode, partials,
                             reinterpret_cast<dcmt::EvalResult*>(results), st),
              "evaluation launch");
@@ -970,29 +1195,21 @@ int dcmt_evaluate_f32_host(const float* gt, const float* dense, int rows, int co
     int rc = check_geometry(rows, cols, pitch_bytes, frame_stride_bytes, n_frames, &g);
     if (rc) return rc;
     if (n_frames == 0) return DCMT_OK;
-    if ((rc = check_device())) return rc;
-    float *d_gt = nullptr, *d_r = nullptr;
-    dcmt_eval_result* d_res = nullptr;
-    auto cleanup = [&] { cudaFree(d_gt); cudaFree(d_r); cudaFree(d_res); };
-    cudaError_t e;
-    if ((e = cudaMalloc(&d_gt, g.span_bytes)) != cudaSuccess || (e = cudaMalloc(&d_r, g.span_bytes)) != cudaSuccess ||
-        (e = cudaMalloc(&d_res, (size_t)n_frames * sizeof(dcmt_eval_result))) != cudaSuccess) {
-        cleanup();
-        return fail(DCMT_E_NOMEM, "device staging buffers: %s", cudaGetErrorString(e));
-    }
-    if ((e = cudaMemcpy(d_gt, gt, g.span_bytes, cudaMemcpyHostToDevice)) != cudaSuccess ||
-        (e = cudaMemcpy(d_r, dense, g.span_bytes, cudaMemcpyHostToDevice)) != cudaSuccess) {
-        cleanup();
-        return cuda_fail(e, "host to device copy");
-    }
-    rc = dcmt_evaluate_f32(d_gt, d_r, rows, cols, pitch_bytes, frame_stride_bytes, n_frames, tolerance, mode, d_res, nullptr);
-    if (rc == DCMT_OK) {
-        if ((e = cudaStreamSynchronize(nullptr)) != cudaSuccess) rc = cuda_fail(e, "kernel execution");
-        else if ((e = cudaMemcpy(results, d_res, (size_t)n_frames * sizeof(dcmt_eval_result), cudaMemcpyDeviceToHost)) != cudaSuccess)
-            rc = cuda_fail(e, "device to host copy");
-    }
-    cleanup();
-    return rc;
+    HostCall call;
+    if ((rc = call.open(nullptr, 0, false))) return rc;
+    cudaStream_t st = call.lanes[0].hs->s[0], st2 = call.lanes[0].hs->s[1];
+    Arena* stage = nullptr;
+    if ((rc = arena_acquire(st2, 2 * carve_bytes(g.span_bytes, 1) + carve_bytes((size_t)n_frames, sizeof(dcmt_eval_result)), &stage))) return rc;
+    float* d_gt = reinterpret_cast<float*>(carve<char>(stage, g.span_bytes));
+    float* d_r = reinterpret_cast<float*>(carve<char>(stage, g.span_bytes));
+    dcmt_eval_result* d_res = carve<dcmt_eval_result>(stage, (size_t)n_frames);
+    if ((rc = arena_ok(stage))) return rc;
+    call.use(call.lanes[0]);
+    API_CUDA(cudaMemcpyAsync(d_gt, gt, g.span_bytes, cudaMemcpyHostToDevice, st), "host to device copy");
+    API_CUDA(cudaMemcpyAsync(d_r, dense, g.span_bytes, cudaMemcpyHostToDevice, st), "host to device copy");
+    if ((rc = dcmt_evaluate_f32(d_gt, d_r, rows, cols, pitch_bytes, frame_stride_bytes, n_frames, tolerance, mode, d_res, st))) return rc;
+    API_CUDA(cudaMemcpyAsync(results, d_res, (size_t)n_frames * sizeof(dcmt_eval_result), cudaMemcpyDeviceToHost, st), "device to host copy");
+    return call.finish();
 }
 
 void dcmt_stereo_params_default(dcmt_stereo_params* p) {
@@ -1050,10 +1267,11 @@ int dcmt_stereo_refine_f32_host(const float* depth_ig, const uint8_t* left_gray,
     if (prm->num_iterations < 0) return fail(DCMT_E_BADARG, "num_iterations %d", prm->num_iterations);
     if ((size_t)rows * (size_t)cols > (size_t)1 << 30) return fail(DCMT_E_UNSUPPORTED, "frame larger than 2^30 pixels");
     if (n_frames == 0) return DCMT_OK;
-    if ((rc = check_device())) return rc;
     // chunks of frames flow H2D -> kernel -> D2H round-robin over the three host streams (asynchronous for page-locked buffers)
-    HostStreams* hs = nullptr;
-    if ((rc = host_streams(&hs))) return rc;
+    HostCall call;
+    if ((rc = call.open(nullptr, 0, false))) return rc;
+    HostStreams* hs = call.lanes[0].hs;
+    call.use(call.lanes[0]);
     const size_t fpix = (size_t)rows * cols;
     const int hc = host_chunk_frames(rows, cols, n_frames);
     const size_t bytes = 2 * carve_bytes(fpix * hc, sizeof(float)) + (disp_out ? carve_bytes(fpix * hc, sizeof(float)) : 0) +
@@ -1069,6 +1287,7 @@ int dcmt_stereo_refine_f32_host(const float* depth_ig, const uint8_t* left_gray,
         float* d_disp = disp_out ? carve<float>(ar, fpix * hc) : nullptr;
         uint8_t* d_l = carve<uint8_t>(ar, fpix * hc);
         uint8_t* d_r = carve<uint8_t>(ar, fpix * hc);
+        if ((rc = arena_ok(ar))) return rc;
         const size_t off = (size_t)f0 * fpix, n = fpix * nf;
         API_CUDA(cudaMemcpyAsync(d_ig, depth_ig + off, n * 4, cudaMemcpyHostToDevice, st), "host to device copy");
         API_CUDA(cudaMemcpyAsync(d_l, left_gray + off, n, cudaMemcpyHostToDevice, st), "host to device copy");
@@ -1077,8 +1296,7 @@ int dcmt_stereo_refine_f32_host(const float* depth_ig, const uint8_t* left_gray,
         API_CUDA(cudaMemcpyAsync(depth_out + off, d_out, n * 4, cudaMemcpyDeviceToHost, st), "device to host copy");
         if (disp_out) API_CUDA(cudaMemcpyAsync(disp_out + off, d_disp, n * 4, cudaMemcpyDeviceToHost, st), "device to host copy");
     }
-    for (int i = 0; i < kHostStreams; ++i) API_CUDA(cudaStreamSynchronize(hs->s[i]), "kernel execution");
-    return DCMT_OK;
+    return call.finish();
 }
 
 int dcmt_measurement_derivatives_f32(const float* value, float* dx, float* dy, int rows, int cols, int n_frames,
@@ -1125,6 +1343,156 @@ int dcmt_retrieve_optimized_depth_f32(const float* disp, float* depth, int rows,
     API_CUDA(dcmt::stereo_retrieve_depth(disp, depth, rows, cols, n_frames, baseline, focal, depth_clip, static_cast<cudaStream_t>(cuda_stream)),
              "retrieve depth launch");
     return DCMT_OK;
+}
+
+// ---- (a3) the reference's own containers: EntryType matrices and pitched CV_32FC1 matrices with in-place semantics ----
+static int check_entries(const void* e, int rows, int cols, size_t row_step, size_t elem_stride) {
+    if (!e) return fail(DCMT_E_BADARG, "null pointer");
+    int rc = check_planes(rows, cols, 1);
+    if (rc) return rc;
+    if (rows > 65535) return fail(DCMT_E_UNSUPPORTED, "at most 65535 rows");
+    if (elem_stride < 12 || elem_stride % 4 != 0) return fail(DCMT_E_BADARG, "elem_stride_bytes %zu: EntryType is three floats", elem_stride);
+    if (row_step % 4 != 0 || row_step < (size_t)cols * elem_stride) return fail(DCMT_E_BADARG, "row_step_bytes %zu invalid for %d entries of %zu bytes", row_step, cols, elem_stride);
+    if (reinterpret_cast<uintptr_t>(e) % 4 != 0) return fail(DCMT_E_BADARG, "entries must be 4-byte aligned");
+    return DCMT_OK;
+}
+static int check_mat_f32(const float* p, int rows, int cols, size_t* pitch_bytes) {
+    if (!p) return fail(DCMT_E_BADARG, "null pointer");
+    if (*pitch_bytes == 0) *pitch_bytes = (size_t)cols * sizeof(float);
+    if (*pitch_bytes % sizeof(float) != 0 || *pitch_bytes < (size_t)cols * sizeof(float)) return fail(DCMT_E_BADARG, "pitch_bytes %zu invalid", *pitch_bytes);
+    return DCMT_OK;
+}
+
+int dcmt_entries_measurement_derivatives(void* entries, int rows, int cols, size_t row_step_bytes, size_t elem_stride_bytes, void* cuda_stream) {
+    int rc = check_entries(entries, rows, cols, row_step_bytes, elem_stride_bytes);
+    if (rc) return rc;
+    if ((rc = check_device())) return rc;
+    API_CUDA(dcmt::stereo_entries_derivatives(entries, row_step_bytes, elem_stride_bytes, rows, cols, static_cast<cudaStream_t>(cuda_stream)),
+             "measurement derivatives launch");
+    return DCMT_OK;
+}
+
+int dcmt_entries_optimize_ig(const void* entries_left, size_t left_row_step_bytes, const void* entries_right, size_t right_row_step_bytes,
+                             size_t elem_stride_bytes, float* disp, size_t disp_pitch_bytes, int rows, int cols, int num_iterations,
+                             float damp_factor, float err_clip, void* cuda_stream) {
+    int rc = check_entries(entries_left, rows, cols, left_row_step_bytes, elem_stride_bytes);
+    if (rc) return rc;
+    if ((rc = check_entries(entries_right, rows, cols, right_row_step_bytes, elem_stride_bytes))) return rc;
+    if ((rc = check_mat_f32(disp, rows, cols, &disp_pitch_bytes))) return rc;
+    if (num_iterations < 0) return fail(DCMT_E_BADARG, "num_iterations %d", num_iterations);
+    if ((rc = check_device())) return rc;
+    API_CUDA(dcmt::stereo_entries_optimize_ig(entries_left, left_row_step_bytes, entries_right, right_row_step_bytes, elem_stride_bytes, disp,
+                                              disp_pitch_bytes / sizeof(float), rows, cols, num_iterations, damp_factor, err_clip,
+                                              static_cast<cudaStream_t>(cuda_stream)),
+             "optimize_IG launch");
+    return DCMT_OK;
+}
+
+int dcmt_get_initial_disparity_mat_f32(const float* depth, size_t depth_pitch_bytes, float* disp, size_t disp_pitch_bytes, int rows, int cols,
+                                       float baseline, float focal, void* cuda_stream) {
+    int rc = check_planes(rows, cols, 1);
+    if (rc) return rc;
+    if (rows > 65535) return fail(DCMT_E_UNSUPPORTED, "at most 65535 rows");
+    if ((rc = check_mat_f32(depth, rows, cols, &depth_pitch_bytes)) || (rc = check_mat_f32(disp, rows, cols, &disp_pitch_bytes))) return rc;
+    if ((rc = check_device())) return rc;
+    API_CUDA(dcmt::stereo_initial_disparity_mat(depth, depth_pitch_bytes / sizeof(float), disp, disp_pitch_bytes / sizeof(float), rows, cols,
+                                                baseline, focal, static_cast<cudaStream_t>(cuda_stream)),
+             "initial disparity launch");
+    return DCMT_OK;
+}
+
+int dcmt_retrieve_optimized_depth_mat_f32(const float* disp, size_t disp_pitch_bytes, float* depth, size_t depth_pitch_bytes, int rows, int cols,
+                                          float baseline, float focal, float depth_clip, void* cuda_stream) {
+    int rc = check_planes(rows, cols, 1);
+    if (rc) return rc;
+    if (rows > 65535) return fail(DCMT_E_UNSUPPORTED, "at most 65535 rows");
+    if ((rc = check_mat_f32(disp, rows, cols, &disp_pitch_bytes)) || (rc = check_mat_f32(depth, rows, cols, &depth_pitch_bytes))) return rc;
+    if ((rc = check_device())) return rc;
+    API_CUDA(dcmt::stereo_retrieve_depth_mat(disp, disp_pitch_bytes / sizeof(float), depth, depth_pitch_bytes / sizeof(float), rows, cols,
+                                             baseline, focal, depth_clip, static_cast<cudaStream_t>(cuda_stream)),
+             "retrieve depth launch");
+    return DCMT_OK;
+}
+
+// host variants: the used part of every row goes to the device (cols * elem_stride bytes of a row_step-byte row), the
+// kernels run on the packed copy, and what the reference function modifies comes back
+int dcmt_entries_measurement_derivatives_host(void* entries, int rows, int cols, size_t row_step_bytes, size_t elem_stride_bytes) {
+    int rc = check_entries(entries, rows, cols, row_step_bytes, elem_stride_bytes);
+    if (rc) return rc;
+    HostCall call;
+    if ((rc = call.open(nullptr, 0, false))) return rc;
+    cudaStream_t st = call.lanes[0].hs->s[0];
+    const size_t used = (size_t)cols * elem_stride_bytes;
+    Arena* ar = nullptr;
+    if ((rc = arena_acquire(st, carve_bytes(used * rows, 1), &ar))) return rc;
+    char* d = carve<char>(ar, used * rows);
+    if ((rc = arena_ok(ar))) return rc;
+    call.use(call.lanes[0]);
+    API_CUDA(cudaMemcpy2DAsync(d, used, entries, row_step_bytes, used, rows, cudaMemcpyHostToDevice, st), "host to device copy");
+    if ((rc = dcmt_entries_measurement_derivatives(d, rows, cols, used, elem_stride_bytes, st))) return rc;
+    API_CUDA(cudaMemcpy2DAsync(entries, row_step_bytes, d, used, used, rows, cudaMemcpyDeviceToHost, st), "device to host copy");
+    return call.finish();
+}
+
+int dcmt_entries_optimize_ig_host(const void* entries_left, size_t left_row_step_bytes, const void* entries_right,
+                                  size_t right_row_step_bytes, size_t elem_stride_bytes, float* disp, size_t disp_pitch_bytes, int rows,
+                                  int cols, int num_iterations, float damp_factor, float err_clip) {
+    int rc = check_entries(entries_left, rows, cols, left_row_step_bytes, elem_stride_bytes);
+    if (rc) return rc;
+    if ((rc = check_entries(entries_right, rows, cols, right_row_step_bytes, elem_stride_bytes))) return rc;
+    if ((rc = check_mat_f32(disp, rows, cols, &disp_pitch_bytes))) return rc;
+    HostCall call;
+    if ((rc = call.open(nullptr, 0, false))) return rc;
+    cudaStream_t st = call.lanes[0].hs->s[0];
+    const size_t used = (size_t)cols * elem_stride_bytes, drow = (size_t)cols * sizeof(float);
+    Arena* ar = nullptr;
+    if ((rc = arena_acquire(st, 2 * carve_bytes(used * rows, 1) + carve_bytes(drow * rows, 1), &ar))) return rc;
+    char* dl = carve<char>(ar, used * rows);
+    char* dr = carve<char>(ar, used * rows);
+    float* dd = reinterpret_cast<float*>(carve<char>(ar, drow * rows));
+    if ((rc = arena_ok(ar))) return rc;
+    call.use(call.lanes[0]);
+    API_CUDA(cudaMemcpy2DAsync(dl, used, entries_left, left_row_step_bytes, used, rows, cudaMemcpyHostToDevice, st), "host to device copy");
+    API_CUDA(cudaMemcpy2DAsync(dr, used, entries_right, right_row_step_bytes, used, rows, cudaMemcpyHostToDevice, st), "host to device copy");
+    API_CUDA(cudaMemcpy2DAsync(dd, drow, disp, disp_pitch_bytes, drow, rows, cudaMemcpyHostToDevice, st), "host to device copy");
+    if ((rc = dcmt_entries_optimize_ig(dl, used, dr, used, elem_stride_bytes, dd, drow, rows, cols, num_iterations, damp_factor, err_clip, st)))
+        return rc;
+    API_CUDA(cudaMemcpy2DAsync(disp, disp_pitch_bytes, dd, drow, drow, rows, cudaMemcpyDeviceToHost, st), "device to host copy");
+    return call.finish();
+}
+
+static int mat_pair_host(const float* in, size_t in_pitch, float* out, size_t out_pitch, int rows, int cols, int which, float baseline,
+                         float focal, float clip) {
+    int rc = check_planes(rows, cols, 1);
+    if (rc) return rc;
+    if ((rc = check_mat_f32(in, rows, cols, &in_pitch)) || (rc = check_mat_f32(out, rows, cols, &out_pitch))) return rc;
+    HostCall call;
+    if ((rc = call.open(nullptr, 0, false))) return rc;
+    cudaStream_t st = call.lanes[0].hs->s[0];
+    const size_t drow = (size_t)cols * sizeof(float);
+    Arena* ar = nullptr;
+    if ((rc = arena_acquire(st, 2 * carve_bytes(drow * rows, 1), &ar))) return rc;
+    float* di = reinterpret_cast<float*>(carve<char>(ar, drow * rows));
+    float* dout = reinterpret_cast<float*>(carve<char>(ar, drow * rows));
+    if ((rc = arena_ok(ar))) return rc;
+    call.use(call.lanes[0]);
+    API_CUDA(cudaMemcpy2DAsync(di, drow, in, in_pitch, drow, rows, cudaMemcpyHostToDevice, st), "host to device copy");
+    API_CUDA(cudaMemcpy2DAsync(dout, drow, out, out_pitch, drow, rows, cudaMemcpyHostToDevice, st), "host to device copy");  // untouched pixels keep their value
+    rc = which == 0 ? dcmt_get_initial_disparity_mat_f32(di, drow, dout, drow, rows, cols, baseline, focal, st)
+                    : dcmt_retrieve_optimized_depth_mat_f32(di, drow, dout, drow, rows, cols, baseline, focal, clip, st);
+    if (rc) return rc;
+    API_CUDA(cudaMemcpy2DAsync(out, out_pitch, dout, drow, drow, rows, cudaMemcpyDeviceToHost, st), "device to host copy");
+    return call.finish();
+}
+
+int dcmt_get_initial_disparity_mat_f32_host(const float* depth, size_t depth_pitch_bytes, float* disp, size_t disp_pitch_bytes, int rows,
+                                            int cols, float baseline, float focal) {
+    return mat_pair_host(depth, depth_pitch_bytes, disp, disp_pitch_bytes, rows, cols, 0, baseline, focal, 0.0f);
+}
+
+int dcmt_retrieve_optimized_depth_mat_f32_host(const float* disp, size_t disp_pitch_bytes, float* depth, size_t depth_pitch_bytes, int rows,
+                                               int cols, float baseline, float focal, float depth_clip) {
+    return mat_pair_host(disp, disp_pitch_bytes, depth, depth_pitch_bytes, rows, cols, 1, baseline, focal, depth_clip);
 }
 
 }  // extern "C"

@@ -1104,9 +1104,19 @@ __device__ __forceinline__ uint32_t other_of_pair(uint32_t a, uint32_t b, uint32
     return a * one + (b * one - lo);
 }
 
+#ifndef DCMT_OTH_NUM
+#define DCMT_OTH_NUM 0  // of every DCMT_OTH_DEN compare-exchanges of the merge networks, this many take their maximum on the ALU pipe
+#endif
+#ifndef DCMT_OTH_DEN
+#define DCMT_OTH_DEN 1
+#endif
 struct PackedOps {
     uint32_t one;
     __device__ __forceinline__ uint32_t other(uint32_t a, uint32_t b, uint32_t lo) const { return other_of_pair(a, b, lo, one); }
+    template <int I>
+    __device__ __forceinline__ uint32_t oth(uint32_t a, uint32_t b, uint32_t lo) const {
+        return (I % DCMT_OTH_DEN) < DCMT_OTH_NUM ? pmax(a, b) : other_of_pair(a, b, lo, one);
+    }
     static __device__ __forceinline__ uint32_t mn(uint32_t a, uint32_t b) { return pmin(a, b); }
     static __device__ __forceinline__ uint32_t mx(uint32_t a, uint32_t b) { return pmax(a, b); }
     static __device__ __forceinline__ uint32_t mn3(uint32_t a, uint32_t b, uint32_t c) { return pmin3(a, b, c); }
@@ -1301,21 +1311,55 @@ __global__ void __launch_bounds__(QTT, DCMT_TAIL_CTAS) k_q8_tail(TailArgs a, con
     {
         const int n = SH * SQ;
         Items i(a.i_scan);
-        for (int base = 0; base < n; base += QTT, i.next()) {
-            bool cand = false;
-            int qidx = 0;
-            if (base + (int)threadIdx.x < n) {
-                qidx = (sr0 + i.r) * RQ + sq0 + i.q;
-                const uint4 v = lds4(A + qidx * 4);
-                // some lane <= 1 (a hole, or absent outside the image)?
-                cand = pmin(pmin(pmin(v.x, v.y), pmin(v.z, v.w)), SPLAT16(2)) != SPLAT16(2);
+        constexpr int kScanRounds = 6;
+        if (n <= kScanRounds * QTT) {
+            // all rounds of a warp first (independent loads and ballots), then ONE reservation per warp in the list
+            uint32_t qv[kScanRounds];
+            unsigned bal[kScanRounds];
+            int total = 0;
+#pragma unroll
+            for (int k = 0; k < kScanRounds; ++k) {
+                bool cand = false;
+                qv[k] = 0u;
+                if (k * QTT + (int)threadIdx.x < n) {
+                    const int qidx = (sr0 + i.r) * RQ + sq0 + i.q;
+                    const uint4 v = lds4(A + qidx * 4);
+                    // some lane <= 1 (a hole, or absent outside the image)?
+                    cand = pmin(pmin(pmin(v.x, v.y), pmin(v.z, v.w)), SPLAT16(2)) != SPLAT16(2);
+                    qv[k] = (uint32_t)qidx | (cand ? 0x80000000u : 0u);
+                }
+                bal[k] = __ballot_sync(0xffffffffu, cand);
+                total += __popc(bal[k]);
+                i.next();
             }
-            const unsigned bal = __ballot_sync(0xffffffffu, cand);
-            if (bal == 0u) continue;
-            int pos = 0;
-            if ((threadIdx.x & 31) == 0) pos = atomicAdd(&s_count, __popc(bal));
-            pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(bal & ((1u << (threadIdx.x & 31)) - 1u));
-            if (cand && pos < kListCap) list[pos] = (uint16_t)qidx;
+            if (total) {
+                int pos = 0;
+                if ((threadIdx.x & 31) == 0) pos = atomicAdd(&s_count, total);
+                pos = __shfl_sync(0xffffffffu, pos, 0);
+                const unsigned below = (1u << (threadIdx.x & 31)) - 1u;
+#pragma unroll
+                for (int k = 0; k < kScanRounds; ++k) {
+                    const int at = pos + __popc(bal[k] & below);
+                    if ((qv[k] & 0x80000000u) && at < kListCap) list[at] = (uint16_t)(qv[k] & 0xffffu);
+                    pos += __popc(bal[k]);
+                }
+            }
+        } else {
+            for (int base = 0; base < n; base += QTT, i.next()) {
+                bool cand = false;
+                int qidx = 0;
+                if (base + (int)threadIdx.x < n) {
+                    qidx = (sr0 + i.r) * RQ + sq0 + i.q;
+                    const uint4 v = lds4(A + qidx * 4);
+                    cand = pmin(pmin(pmin(v.x, v.y), pmin(v.z, v.w)), SPLAT16(2)) != SPLAT16(2);
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, cand);
+                if (bal == 0u) continue;
+                int pos = 0;
+                if ((threadIdx.x & 31) == 0) pos = atomicAdd(&s_count, __popc(bal));
+                pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(bal & ((1u << (threadIdx.x & 31)) - 1u));
+                if (cand && pos < kListCap) list[pos] = (uint16_t)qidx;
+            }
         }
     }
     __syncthreads();

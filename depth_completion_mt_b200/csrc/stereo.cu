@@ -33,9 +33,18 @@ struct PlaneF32 {
     int cols;
     __device__ __forceinline__ float operator()(int r, int c) const { return __ldg(p + (size_t)r * cols + c); }
 };
-// One optimize_IG pixel: `iters` damped Gauss-Newton steps on the disparity d of pixel (i, j).
+// dx entries recomputed from the value plane: what calculateMeasuementDerivatives stored at (r, c)
 template <class Plane>
-__device__ __forceinline__ float refine_pixel(const Plane& right, float left_val, float d, int i, int j, int rows,
+struct GradFromValues {
+    const Plane& v;
+    int rows, cols;
+    __device__ __forceinline__ float operator()(int r, int c) const { return deriv_x(v, r, c, rows, cols); }
+};
+
+// One optimize_IG pixel: `iters` damped Gauss-Newton steps on the disparity d of pixel (i, j).  `grad(r, c)` is the
+// derivative.x() entry of the right image (recomputed from the values, or read from the caller's EntryType matrix).
+template <class Plane, class Grad>
+__device__ __forceinline__ float refine_pixel(const Plane& right, const Grad& grad, float left_val, float d, int i, int j, int rows,
                                               int cols, int iters, float damp, float clip) {
     for (int k = 0; k < iters; ++k) {
         if (d == 0.0f) break;                       // :817 `disparity != 0` (never changes once 0)
@@ -50,8 +59,8 @@ __device__ __forceinline__ float refine_pixel(const Plane& right, float left_val
         const float dc1 = __double2float_rn(__dsub_rn(1.0, (double)dc));  // :789 `1. - dc` in double
         const float p00 = c0 < cols ? right(i, c0) : 0.0f;
         const float p01 = c1 < cols ? right(i, c1) : 0.0f;
-        const float g00 = c0 < cols ? deriv_x(right, i, c0, rows, cols) : 0.0f;
-        const float g01 = c1 < cols ? deriv_x(right, i, c1, rows, cols) : 0.0f;
+        const float g00 = c0 < cols ? grad(i, c0) : 0.0f;
+        const float g01 = c1 < cols ? grad(i, c1) : 0.0f;
         // :794-797 with dr == 0, dr1 == 1: the second-row term contributes an exact zero
         const float value = __fadd_rn(__fmul_rn(p00, dc1), __fmul_rn(p01, dc));
         const float gx = __fadd_rn(__fmul_rn(g00, dc1), __fmul_rn(g01, dc));
@@ -154,7 +163,62 @@ __global__ void __launch_bounds__(kThreads) k_optimize_ig(const float* __restric
     const size_t f = t / fpix, o = t - f * fpix;
     const int i = (int)(o / cols), j = (int)(o - (size_t)i * cols);
     const PlaneF32 right{vr + f * fpix, cols};
-    disp[t] = refine_pixel(right, vl[t], disp[t], i, j, rows, cols, iters, damp, clip);
+    disp[t] = refine_pixel(right, GradFromValues<PlaneF32>{right, rows, cols}, vl[t], disp[t], i, j, rows, cols, iters, damp, clip);
+}
+
+// ---- the reference's own containers (a3): EntryType {float value; Eigen::Vector2f derivative;} (main_sl.cpp:23-26) stored
+// in a cv::Mat of type CV_32FC(sizeof(EntryType)) (:1165,:1169).  at<EntryType>(r, c) addresses
+// data + r * step + c * sizeof(EntryType): 12-byte elements packed at the start of rows that are four times too wide.
+struct EntriesView {
+    char* base;
+    size_t row_step, elem_stride;  // bytes
+    __device__ __forceinline__ float* at(int r, int c) const { return reinterpret_cast<float*>(base + (size_t)r * row_step + (size_t)c * elem_stride); }
+};
+struct EntryValues {
+    EntriesView e;
+    __device__ __forceinline__ float operator()(int r, int c) const { return e.at(r, c)[0]; }
+};
+struct EntryDx {
+    EntriesView e;
+    __device__ __forceinline__ float operator()(int r, int c) const { return e.at(r, c)[1]; }
+};
+
+// calculateMeasuementDerivatives on an EntryType matrix, in place (:715-745): interior entries get (dx, dy), the
+// one-pixel border keeps whatever the caller stored there
+__global__ void __launch_bounds__(kThreads) k_entries_derivatives(EntriesView e, int rows, int cols) {
+    const int c = blockIdx.x * kThreads + threadIdx.x, r = blockIdx.y;
+    if (r < 1 || r >= rows - 1 || c < 1 || c >= cols - 1) return;
+    float* o = e.at(r, c);
+    o[1] = __double2float_rn(__dsub_rn(0.5 * (double)e.at(r, c + 1)[0], 0.5 * (double)e.at(r, c - 1)[0]));
+    o[2] = __double2float_rn(__dsub_rn(0.5 * (double)e.at(r + 1, c)[0], 0.5 * (double)e.at(r - 1, c)[0]));
+}
+
+// optimize_IG on EntryType matrices (:804-843): value of the left entry, value and STORED derivative.x() of the right one
+__global__ void __launch_bounds__(kThreads) k_entries_optimize_ig(EntriesView left, EntriesView right, float* __restrict__ disp,
+                                                                  size_t disp_pitch, int rows, int cols, int iters, float damp,
+                                                                  float clip) {
+    const int j = blockIdx.x * kThreads + threadIdx.x, i = blockIdx.y;
+    if (j >= cols) return;
+    float* d = disp + (size_t)i * disp_pitch + j;
+    *d = refine_pixel(EntryValues{right}, EntryDx{right}, left.at(i, j)[0], *d, i, j, rows, cols, iters, damp, clip);
+}
+
+// get_initial_disparity / retrieve_optimized_depth with the reference's in-place semantics: pixels that fail the test
+// (depth > 0, disparity > 0) keep what the output matrix held (:852, :871)
+__global__ void __launch_bounds__(kThreads) k_initial_disparity_mat(const float* __restrict__ depth, size_t depth_pitch,
+                                                                    float* __restrict__ disp, size_t disp_pitch, int cols, float bf) {
+    const int j = blockIdx.x * kThreads + threadIdx.x, i = blockIdx.y;
+    if (j >= cols) return;
+    const float z = depth[(size_t)i * depth_pitch + j];
+    if (z > 0.0f) disp[(size_t)i * disp_pitch + j] = __fdiv_rn(bf, z);
+}
+__global__ void __launch_bounds__(kThreads) k_retrieve_depth_mat(const float* __restrict__ disp, size_t disp_pitch,
+                                                                 float* __restrict__ depth, size_t depth_pitch, int cols, float bf,
+                                                                 float clip) {
+    const int j = blockIdx.x * kThreads + threadIdx.x, i = blockIdx.y;
+    if (j >= cols) return;
+    const float d = disp[(size_t)i * disp_pitch + j];
+    if (d > 0.0f) depth[(size_t)i * depth_pitch + j] = depth_from_disparity(d, bf, clip);
 }
 
 struct RefineArgs {
@@ -283,6 +347,39 @@ cudaError_t stereo_retrieve_depth(const float* disp, float* depth, int rows, int
     if (total == 0) return cudaSuccess;
     volatile float bf = baseline * focal;
     DCMT_LAUNCH(k_retrieve_depth, dim3(blocks_for(total)), dim3(kThreads), 0, st, disp, depth, total, (float)bf, clip);
+    return cudaGetLastError();
+}
+
+cudaError_t stereo_entries_derivatives(void* entries, size_t row_step, size_t elem_stride, int rows, int cols, cudaStream_t st) {
+    if (rows < 3 || cols < 3) return cudaSuccess;  // no interior
+    DCMT_LAUNCH(k_entries_derivatives, dim3((cols + kThreads - 1) / kThreads, rows), dim3(kThreads), 0, st,
+                EntriesView{static_cast<char*>(entries), row_step, elem_stride}, rows, cols);
+    return cudaGetLastError();
+}
+
+cudaError_t stereo_entries_optimize_ig(const void* left, size_t left_row_step, const void* right, size_t right_row_step, size_t elem_stride,
+                                       float* disp, size_t disp_pitch, int rows, int cols, int iters, float damp, float clip,
+                                       cudaStream_t st) {
+    DCMT_LAUNCH(k_entries_optimize_ig, dim3((cols + kThreads - 1) / kThreads, rows), dim3(kThreads), 0, st,
+                EntriesView{static_cast<char*>(const_cast<void*>(left)), left_row_step, elem_stride},
+                EntriesView{static_cast<char*>(const_cast<void*>(right)), right_row_step, elem_stride}, disp, disp_pitch, rows, cols, iters, damp,
+                clip);
+    return cudaGetLastError();
+}
+
+cudaError_t stereo_initial_disparity_mat(const float* depth, size_t depth_pitch, float* disp, size_t disp_pitch, int rows, int cols,
+                                         float baseline, float focal, cudaStream_t st) {
+    volatile float bf = baseline * focal;
+    DCMT_LAUNCH(k_initial_disparity_mat, dim3((cols + kThreads - 1) / kThreads, rows), dim3(kThreads), 0, st, depth, depth_pitch, disp,
+                disp_pitch, cols, (float)bf);
+    return cudaGetLastError();
+}
+
+cudaError_t stereo_retrieve_depth_mat(const float* disp, size_t disp_pitch, float* depth, size_t depth_pitch, int rows, int cols,
+                                      float baseline, float focal, float clip, cudaStream_t st) {
+    volatile float bf = baseline * focal;
+    DCMT_LAUNCH(k_retrieve_depth_mat, dim3((cols + kThreads - 1) / kThreads, rows), dim3(kThreads), 0, st, disp, disp_pitch, depth,
+                depth_pitch, cols, (float)bf, clip);
     return cudaGetLastError();
 }
 

@@ -22,6 +22,12 @@
  *     `frame_stride_bytes` between consecutive frames of a batch (0 = rows*pitch);
  *   - input and output must not alias; the library keeps a cached per-(device,stream) workspace,
  *     nothing else is retained after return;
+ *   - threading: dcmt_last_error() is thread-local.  Un-suffixed (device-pointer) entry points may be called from
+ *     several threads as long as calls that share a (device, stream) pair are ordered by the caller, as CUDA itself
+ *     requires (the workspace and the read-back buffer of DCMT_PATH_AUTO are cached per pair).  `*_host` entry points
+ *     share three internal streams per device and take a per-device mutex for the duration of the call: threads on
+ *     different devices run concurrently, threads on the same device take turns.  On every return path, including
+ *     errors, a `*_host` call has drained its streams: no copy into the caller's buffers is in flight afterwards;
  *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
  *     DCMT_E_CUDA.
  */
@@ -41,7 +47,7 @@ extern "C" {
 #define DCMT_API __attribute__((visibility("default")))
 #endif
 
-#define DCMT_VERSION 100 /* 0.1.0 */
+#define DCMT_VERSION 200 /* 0.2.0 */
 
 enum {
     DCMT_OK = 0,
@@ -78,6 +84,9 @@ enum {
 #define DCMT_STATS_STRIDE 4
 
 DCMT_API int dcmt_version(void);
+/* "cuda sm_100a" for the product library; the test-only CPU emulator build of the same sources says so here, and the
+ * Python package refuses to load anything that does not start with "cuda" */
+DCMT_API const char *dcmt_build_info(void);
 DCMT_API const char *dcmt_last_error(void);
 DCMT_API const char *dcmt_status_string(int status);
 /* number of visible CUDA devices, or a negative DCMT_E_CUDA */
@@ -123,6 +132,34 @@ DCMT_API int dcmt_img_completion_u16_host(const uint16_t *sparse_u16, float *den
                                           size_t in_pitch_bytes, size_t in_frame_stride_bytes, size_t out_pitch_bytes,
                                           size_t out_frame_stride_bytes, int n_frames, int blur_type, int flags,
                                           int32_t *stats_or_null);
+
+/* (e) the host-pointer entry points over several GPUs of one box: north_star's "batches are partitioned frame-wise
+ * across the 8 B200s" for a C++ caller of the library (one process, one thread).  The frames of the call are split into
+ * one contiguous block per device; chunks of the blocks flow H2D -> kernels -> D2H on three streams per device, all
+ * enqueued by the calling thread; there is no exchange between devices.  `devices` lists CUDA device ordinals
+ * (n_devices >= 1, no repeats); devices == NULL uses the first n_devices visible devices, or all of them when
+ * n_devices <= 0.  Page-locked host buffers (dcmt_host_alloc) are needed for the copies to overlap.  The caller's
+ * current device is restored on return.  Results are identical to the single-device call. */
+DCMT_API int dcmt_img_completion_f32_host_multi(const float *sparse, float *dense, int rows, int cols, size_t pitch_bytes,
+                                                size_t frame_stride_bytes, int n_frames, int blur_type, int flags,
+                                                int32_t *stats_or_null, const int *devices_or_null, int n_devices);
+DCMT_API int dcmt_img_completion_u16_host_multi(const uint16_t *sparse_u16, float *dense, int rows, int cols,
+                                                size_t in_pitch_bytes, size_t in_frame_stride_bytes, size_t out_pitch_bytes,
+                                                size_t out_frame_stride_bytes, int n_frames, int blur_type, int flags,
+                                                int32_t *stats_or_null, const int *devices_or_null, int n_devices);
+DCMT_API int dcmt_interpolate_with_superpixels_f32_host_multi(const float *sparse, const int32_t *labels, int n_clusters,
+                                                              float *dense, int rows, int cols, size_t pitch_bytes,
+                                                              size_t frame_stride_bytes, int n_frames, int use_superpixel,
+                                                              int flags, int32_t *stats_or_null, const int *devices_or_null,
+                                                              int n_devices);
+/* measurement aid: the host pipeline of the calls above with the kernels left out -- the same buffers, chunking and
+ * streams; the float32 variant echoes the input to the output, the uint16 variant returns zeros.  Its rate is the
+ * ceiling the host <-> device links put on the end-to-end rate (bench.py: e2e.copy_ceiling).  devices == NULL and
+ * n_devices == 0: the current device. */
+DCMT_API int dcmt_debug_host_copy_f32(const float *in, float *out, int rows, int cols, int n_frames,
+                                      const int *devices_or_null, int n_devices);
+DCMT_API int dcmt_debug_host_copy_u16(const uint16_t *in, float *out, int rows, int cols, int n_frames,
+                                      const int *devices_or_null, int n_devices);
 
 /* (a2) replaces interpolate_with_superpixels(Slic&, const cv::Mat&, cv::Mat&, const std::string&, int)
  * -- src/DC_lidar_camera/img_completion_lc.cpp:34-203.  `labels` is the Slic::clusters label map as
@@ -190,6 +227,46 @@ DCMT_API int dcmt_optimize_ig_f32(const float *value_left, const float *value_ri
 /* (a8) retrieve_optimized_depth, main_sl.cpp:863-885 (output pre-zeroed as at :1244) */
 DCMT_API int dcmt_retrieve_optimized_depth_f32(const float *disp, float *depth, int rows, int cols, int n_frames,
                                                float baseline, float focal, float depth_clip, void *cuda_stream);
+
+/* (a3) the same four functions on the reference's OWN containers, so that its call sites (main_sl.cpp:1192-1246) need no
+ * change of data layout:
+ *   - EntryType matrices (main_sl.cpp:23-26: struct { float value; Eigen::Vector2f derivative; }, 12 bytes) as
+ *     cv::Mat(rows, cols, CV_32FC(sizeof(EntryType))) (:1165,:1169): element (r, c) lives at
+ *     data + r * row_step_bytes + c * elem_stride_bytes with elem_stride_bytes = 12 and row_step_bytes = Mat::step
+ *     (= cols * 48 there: at<EntryType>() packs the 12-byte entries at the start of rows four times too wide);
+ *   - CV_32FC1 matrices with a pitch, written IN PLACE the way the reference loops do: get_initial_disparity only
+ *     writes where depth > 0 (:852), retrieve_optimized_depth only where disparity > 0 (:871); other pixels keep
+ *     what the output held;
+ *   - calculateMeasuementDerivatives writes derivative (x, y) of the interior entries and leaves the one-pixel border
+ *     as the caller initialised it (:717-721); optimize_IG reads value and the STORED derivative.x() of the right
+ *     matrix (:747-801) and value of the left one, and updates the disparity in place; reads at column index == cols
+ *     (undefined in the reference) are 0.
+ * Device-pointer variants enqueue on `cuda_stream`; `*_host` variants copy the used part of the rows in and the
+ * modified data back.  rows <= 65535. */
+DCMT_API int dcmt_entries_measurement_derivatives(void *entries, int rows, int cols, size_t row_step_bytes,
+                                                  size_t elem_stride_bytes, void *cuda_stream);
+DCMT_API int dcmt_entries_measurement_derivatives_host(void *entries, int rows, int cols, size_t row_step_bytes,
+                                                       size_t elem_stride_bytes);
+DCMT_API int dcmt_entries_optimize_ig(const void *entries_left, size_t left_row_step_bytes, const void *entries_right,
+                                      size_t right_row_step_bytes, size_t elem_stride_bytes, float *disp,
+                                      size_t disp_pitch_bytes, int rows, int cols, int num_iterations, float damp_factor,
+                                      float err_clip, void *cuda_stream);
+DCMT_API int dcmt_entries_optimize_ig_host(const void *entries_left, size_t left_row_step_bytes, const void *entries_right,
+                                           size_t right_row_step_bytes, size_t elem_stride_bytes, float *disp,
+                                           size_t disp_pitch_bytes, int rows, int cols, int num_iterations,
+                                           float damp_factor, float err_clip);
+DCMT_API int dcmt_get_initial_disparity_mat_f32(const float *depth, size_t depth_pitch_bytes, float *disp,
+                                                size_t disp_pitch_bytes, int rows, int cols, float baseline, float focal,
+                                                void *cuda_stream);
+DCMT_API int dcmt_get_initial_disparity_mat_f32_host(const float *depth, size_t depth_pitch_bytes, float *disp,
+                                                     size_t disp_pitch_bytes, int rows, int cols, float baseline,
+                                                     float focal);
+DCMT_API int dcmt_retrieve_optimized_depth_mat_f32(const float *disp, size_t disp_pitch_bytes, float *depth,
+                                                   size_t depth_pitch_bytes, int rows, int cols, float baseline,
+                                                   float focal, float depth_clip, void *cuda_stream);
+DCMT_API int dcmt_retrieve_optimized_depth_mat_f32_host(const float *disp, size_t disp_pitch_bytes, float *depth,
+                                                        size_t depth_pitch_bytes, int rows, int cols, float baseline,
+                                                        float focal, float depth_clip);
 
 /* (8f #3) evaluation reductions: replace evaluate_performance (src/DC_lidar_only/main.cpp:16-34, mode
  * DCMT_EVAL_GT_VALID: pixels with gt > tolerance, result mean_err = sum(gt - r) / count, which that program calls

@@ -2,17 +2,26 @@
 // (`#include "img_completion.h"`: src/DC_lidar_only/img_completion.cpp:15, main.cpp:1, utils.cpp:3), implemented
 // on top of the C ABI of libdcmt.so (include/dcmt.h).
 //
-// With OpenCV available (the reference's own build), define nothing and the reference signatures are provided on
-// cv::Mat, so that main.cpp / main_lc.cpp / main_sl.cpp link against libdcmt.so instead of compiling
-// img_completion.cpp / img_completion_lc.cpp:
+// With OpenCV available (the reference's own build) the reference's signatures are defined on cv::Mat, so that
+// main.cpp / main_lc.cpp / main_sl.cpp link against libdcmt.so instead of compiling img_completion.cpp /
+// img_completion_lc.cpp and the function bodies of main_sl.cpp:715-885:
 //
-//     void img_completion(const cv::Mat&, cv::Mat&, const bool& extr, const std::string& blur_type);      (img_completion.cpp:17)
-//     void interpolate_with_superpixels(Slic&, const cv::Mat&, cv::Mat&, const std::string&, int);        (img_completion_lc.cpp:34)
-//     void calculateMeasuementDerivatives / get_initial_disparity / optimize_IG / retrieve_optimized_depth (main_sl.cpp:715-885)
+//     void img_completion(const cv::Mat&, cv::Mat&, const bool& extr, const std::string& blur_type);      img_completion.cpp:17
+//     void interpolate_with_superpixels(Slic&, const cv::Mat&, cv::Mat&, const std::string&, int);        img_completion_lc.cpp:34
+//     void calculateMeasuementDerivatives(cv::Mat& img);                                                  main_sl.cpp:715
+//     bool calculateObservationDerivatives(const cv::Mat&, const Eigen::Vector2f, float&, Eigen::Vector2f&);        :747
+//     void optimize_IG(cv::Mat& left, cv::Mat& right, cv::Mat& disparity);                                          :804
+//     void get_initial_disparity(cv::Mat& initial_guess, cv::Mat& disparity);                                      :846
+//     void retrieve_optimized_depth(cv::Mat& disparity, cv::Mat& depth);                                            :863
+//     void evaluate_performance / evaluate_performances                      main.cpp:16, main_lc.cpp:85, main_sl.cpp:1031
 //
-// Without OpenCV (this repository's CI) the same functions are available on dcmt::MatView, a plain
-// {rows, cols, step, data} view with cv::Mat's CV_32FC1 memory layout, so the shim itself can be compiled and
-// tested.  Errors of the C ABI become std::runtime_error (the reference functions return void).
+// The stereo functions take the reference's own containers: EntryType matrices (struct { float value;
+// Eigen::Vector2f derivative; }, main_sl.cpp:23-26) stored as cv::Mat(rows, cols, CV_32FC(sizeof(EntryType))) (:1165).
+// EntryType itself stays the caller's (main_sl.cpp defines it); this header only relies on its 12-byte layout.
+//
+// Without OpenCV (this repository's CI) the same functions exist on dcmt::MatView, a plain {rows, cols, step, data}
+// view with cv::Mat's memory layout, so the shim can be compiled and tested anywhere.  Errors of the C ABI become
+// std::runtime_error (the reference functions return void).
 #ifndef DCMT_IMG_COMPLETION_H_
 #define DCMT_IMG_COMPLETION_H_
 
@@ -33,12 +42,15 @@
 
 namespace dcmt {
 
-// cv::Mat-compatible view of a single-channel image: element (r, c) lives at data + r * step + c * sizeof(T)
+// cv::Mat-compatible view of an image: element (r, c) lives at data + r * step + c * sizeof(T)
 struct MatView {
     int rows = 0, cols = 0;
     size_t step = 0;  // bytes between rows (cv::Mat::step)
     void* data = nullptr;
 };
+
+// bytes of one EntryType (main_sl.cpp:23-26): float value + Eigen::Vector2f derivative
+constexpr size_t kEntryBytes = 12;
 
 inline void check(int status) {
     if (status != DCMT_OK) throw std::runtime_error(std::string("dcmt: ") + dcmt_status_string(status) + ": " + dcmt_last_error());
@@ -49,18 +61,25 @@ inline int blur_code(const std::string& blur_type) {
     return blur_type == "bilateral" ? DCMT_BLUR_BILATERAL : blur_type == "gaussian" ? DCMT_BLUR_GAUSSIAN : DCMT_BLUR_NONE;
 }
 
-// img_completion.cpp:17-204.  `dense` must already describe a rows x cols float buffer (cv::Mat overload allocates it,
-// like the reference's clone()).  `extr` is ignored, as in the reference (:103).
+inline void need_same_layout(const MatView& a, const MatView& b, const char* what) {
+    if (a.rows != b.rows || a.cols != b.cols || !a.data || !b.data) throw std::invalid_argument(std::string("dcmt: ") + what + ": views must be allocated with one shape");
+    // the completion ABI takes ONE pitch for input and output (dcmt_img_completion_f32): views with different steps would
+    // be written with the wrong row pitch.  The cv::Mat overloads below always pass continuous matrices.
+    if (a.step != b.step) throw std::invalid_argument(std::string("dcmt: ") + what + ": input and output views must share one step");
+}
+
+// img_completion.cpp:17-204.  `dense` must describe a rows x cols float buffer with the step of `sparse` (the cv::Mat
+// overload allocates it, like the reference's clone()).  `extr` is ignored, as in the reference (:103).
 inline void img_completion(const MatView& sparse, MatView& dense, const bool& /*extr*/, const std::string& blur_type,
                            int path = DCMT_PATH_AUTO) {
-    if (dense.rows != sparse.rows || dense.cols != sparse.cols || !dense.data) throw std::invalid_argument("dcmt: dense view not allocated");
+    need_same_layout(sparse, dense, "img_completion");
     check(dcmt_img_completion_f32_host(static_cast<const float*>(sparse.data), static_cast<float*>(dense.data), sparse.rows,
                                        sparse.cols, sparse.step, 0, 1, blur_code(blur_type), path, nullptr));
-    // stride of input and output must agree in the ABI; MatViews with different steps are handled by the cv::Mat overload
 }
 
 // main.cpp:75-93 in one call: the uint16 payload of a KITTI depth PNG (CV_16UC1 view, metres * 256) -> dense float32 metres;
-// stands for image_r.convertTo(projected_depths, CV_32F, 1.0 / 256.0) (:79) followed by img_completion (:93)
+// stands for image_r.convertTo(projected_depths, CV_32F, 1.0 / 256.0) (:79) followed by img_completion (:93).  Input and
+// output have their own steps here.
 inline void img_completion_u16(const MatView& sparse_u16, MatView& dense, const std::string& blur_type, int path = DCMT_PATH_AUTO) {
     if (dense.rows != sparse_u16.rows || dense.cols != sparse_u16.cols || !dense.data) throw std::invalid_argument("dcmt: dense view not allocated");
     check(dcmt_img_completion_u16_host(static_cast<const uint16_t*>(sparse_u16.data), static_cast<float*>(dense.data), sparse_u16.rows,
@@ -111,16 +130,77 @@ inline int project_lidar(const float* points, int n_points, const float* T_row_m
 inline void interpolate_with_superpixels(const std::vector<std::vector<int>>& clusters_col_major, size_t n_centers,
                                          const MatView& sparse, MatView& dense, const std::string& /*blur_type*/,
                                          int use_superpixel) {
-    if (dense.rows != sparse.rows || dense.cols != sparse.cols || !dense.data) throw std::invalid_argument("dcmt: dense view not allocated");
+    need_same_layout(sparse, dense, "interpolate_with_superpixels");
     std::vector<int32_t> labels;
     if (use_superpixel) {
+        if (clusters_col_major.size() < (size_t)sparse.cols) throw std::invalid_argument("dcmt: Slic::clusters has fewer columns than the image");
         labels.resize((size_t)sparse.rows * sparse.cols);
-        for (int j = 0; j < sparse.cols; ++j)
+        for (int j = 0; j < sparse.cols; ++j) {
+            if (clusters_col_major[j].size() < (size_t)sparse.rows) throw std::invalid_argument("dcmt: Slic::clusters has fewer rows than the image");
             for (int i = 0; i < sparse.rows; ++i) labels[(size_t)i * sparse.cols + j] = clusters_col_major[j][i];
+        }
     }
     check(dcmt_interpolate_with_superpixels_f32_host(static_cast<const float*>(sparse.data), use_superpixel ? labels.data() : nullptr,
                                                      (int)n_centers, static_cast<float*>(dense.data), sparse.rows, sparse.cols,
                                                      sparse.step, 0, 1, use_superpixel, nullptr));
+}
+
+// ---- the stereo functions on EntryType matrices (views whose rows hold `cols` entries of kEntryBytes at the start) ----
+// main_sl.cpp:715-745
+inline void calculateMeasuementDerivatives(MatView& entries) {
+    check(dcmt_entries_measurement_derivatives_host(entries.data, entries.rows, entries.cols, entries.step, kEntryBytes));
+}
+// main_sl.cpp:846-861 (in place: pixels with depth <= 0 keep what `disparity_IG` held)
+inline void get_initial_disparity(const MatView& initial_guess, MatView& disparity_IG, float baseline = 0.54f, float focal = 9.597910e+02f) {
+    if (initial_guess.rows != disparity_IG.rows || initial_guess.cols != disparity_IG.cols) throw std::invalid_argument("dcmt: get_initial_disparity needs same-shaped Mats");
+    check(dcmt_get_initial_disparity_mat_f32_host(static_cast<const float*>(initial_guess.data), initial_guess.step,
+                                                  static_cast<float*>(disparity_IG.data), disparity_IG.step, disparity_IG.rows,
+                                                  disparity_IG.cols, baseline, focal));
+}
+// main_sl.cpp:804-843 (main_sl_OFFICIAL.cpp:832-876: num_iterations from the caller, damp 1370, clip 221)
+inline void optimize_IG(const MatView& entries_left, const MatView& entries_right, MatView& disparity_map_IG, int num_iterations = 4,
+                        float damp_factor = 500.0f, float err_clip = 255.0f) {
+    if (entries_left.rows != entries_right.rows || entries_left.cols != entries_right.cols || entries_left.rows != disparity_map_IG.rows ||
+        entries_left.cols != disparity_map_IG.cols)
+        throw std::invalid_argument("dcmt: optimize_IG needs same-shaped Mats");
+    check(dcmt_entries_optimize_ig_host(entries_left.data, entries_left.step, entries_right.data, entries_right.step, kEntryBytes,
+                                        static_cast<float*>(disparity_map_IG.data), disparity_map_IG.step, disparity_map_IG.rows,
+                                        disparity_map_IG.cols, num_iterations, damp_factor, err_clip));
+}
+// main_sl.cpp:863-885 (in place: pixels with disparity <= 0 keep what `optimized_depth` held; OFFICIAL clips at 80)
+inline void retrieve_optimized_depth(const MatView& disparity_refined, MatView& optimized_depth, float depth_clip = 100.0f,
+                                     float baseline = 0.54f, float focal = 9.597910e+02f) {
+    if (disparity_refined.rows != optimized_depth.rows || disparity_refined.cols != optimized_depth.cols) throw std::invalid_argument("dcmt: retrieve_optimized_depth needs same-shaped Mats");
+    check(dcmt_retrieve_optimized_depth_mat_f32_host(static_cast<const float*>(disparity_refined.data), disparity_refined.step,
+                                                     static_cast<float*>(optimized_depth.data), optimized_depth.step, optimized_depth.rows,
+                                                     optimized_depth.cols, baseline, focal, depth_clip));
+}
+// main_sl.cpp:747-801: one bilinear sample of an EntryType matrix at (row r, column c) = (img_point[0], img_point[1]).
+// This is the per-sample accessor optimize_IG calls once per pixel and iteration in the reference; the library runs it
+// inside its optimize_IG kernel, and callers that probe single points get this host-side sampler of their own (host)
+// matrix.  Same arithmetic in the same order; entries the reference reads at index == rows / == cols (undefined
+// behaviour there: its bounds tests use `>`) read as 0 here, like in the kernels.
+inline bool sample_entries(const MatView& target, float r, float c, float& value, float& dx, float& dy) {
+    const int rows = target.rows, cols = target.cols;
+    const int r0 = (int)(r + 0.5), c0 = (int)(c + 0.5);
+    if (r0 < 0 || r0 > rows || c0 < 0 || c0 > cols) return false;
+    const int r1 = r0 + 1, c1 = c0 + 1;
+    if (r1 < 0 || r1 > rows || c1 < 0 || c1 > cols) return false;
+    auto entry = [&](int rr, int cc, int k) -> float {
+        if (rr >= rows || cc >= cols) return 0.0f;
+        float v;
+        std::memcpy(&v, static_cast<const char*>(target.data) + (size_t)rr * target.step + (size_t)cc * kEntryBytes + 4 * (size_t)k, 4);
+        return v;
+    };
+    const float dr = r - (float)r0, dc = c - (float)c0;
+    const float dr1 = (float)(1. - dr), dc1 = (float)(1. - dc);
+    float out[3];
+    for (int k = 0; k < 3; ++k)
+        out[k] = (entry(r0, c0, k) * dc1 + entry(r0, c1, k) * dc) * dr1 + (entry(r1, c0, k) * dc1 + entry(r1, c1, k) * dc) * dr;
+    value = out[0];
+    dx = out[1];
+    dy = out[2];
+    return true;
 }
 
 // main_sl.cpp:1165-1253 in one call: gray images (CV_8UC1 views) + initial dense depth -> refined depth
@@ -145,22 +225,25 @@ inline void stereo_refine(const MatView& depth_ig, const MatView& left_gray, con
 
 namespace dcmt {
 inline MatView view_of(const cv::Mat& m) { return MatView{m.rows, m.cols, (size_t)m.step, m.data}; }
+inline cv::Mat continuous(const cv::Mat& m) { return m.isContinuous() ? m : m.clone(); }
 }  // namespace dcmt
 
-// img_completion.cpp:17-20.  A CV_16UC1 Mat (the KITTI PNG as read by cv::imread(..., IMREAD_ANYDEPTH), main.cpp:75) is
-// accepted as well and stands for convertTo(CV_32F, 1.0 / 256.0) + img_completion.
+// img_completion.cpp:17-20.  The reference replaces the header of `dense_r_img` by a fresh matrix (`= sparse.clone()`,
+// :27); so does this: the result is computed into a new continuous Mat and assigned, whatever `dense_r_img` was (an
+// ROI, a non-continuous or differently typed matrix).  A CV_16UC1 input (the KITTI PNG as read by
+// cv::imread(..., IMREAD_ANYDEPTH), main.cpp:75) is accepted as well and stands for convertTo(CV_32F, 1.0 / 256.0) +
+// img_completion.
 inline void img_completion(const cv::Mat& sparse_r_img, cv::Mat& dense_r_img, const bool& extr, const std::string& blur_type) {
+    cv::Mat out(sparse_r_img.rows, sparse_r_img.cols, CV_32FC1);
+    dcmt::MatView d = dcmt::view_of(out);
     if (sparse_r_img.type() == CV_16UC1) {
-        dense_r_img.create(sparse_r_img.rows, sparse_r_img.cols, CV_32FC1);
-        dcmt::MatView s16 = dcmt::view_of(sparse_r_img), d16 = dcmt::view_of(dense_r_img);
-        dcmt::img_completion_u16(s16, d16, blur_type);
-        return;
+        dcmt::img_completion_u16(dcmt::view_of(sparse_r_img), d, blur_type);
+    } else {
+        CV_Assert(sparse_r_img.type() == CV_32FC1);
+        const cv::Mat in = dcmt::continuous(sparse_r_img);
+        dcmt::img_completion(dcmt::view_of(in), d, extr, blur_type);
     }
-    CV_Assert(sparse_r_img.type() == CV_32FC1);
-    cv::Mat in = sparse_r_img.isContinuous() ? sparse_r_img : sparse_r_img.clone();
-    dense_r_img.create(in.rows, in.cols, CV_32FC1);  // the reference's `dense = sparse.clone()` (:27)
-    dcmt::MatView s = dcmt::view_of(in), d = dcmt::view_of(dense_r_img);
-    dcmt::img_completion(s, d, extr, blur_type);
+    dense_r_img = out;
 }
 
 // img_completion_lc.cpp:34-38.  Slic is the reference's class (slic.h:30-71): public `clusters` ([col][row]) and `centers`.
@@ -168,35 +251,76 @@ template <class SlicT>
 inline void interpolate_with_superpixels(SlicT& slic, const cv::Mat& sparse_r_img, cv::Mat& dense_r_img, const std::string& blur_type,
                                          int use_superpixel) {
     CV_Assert(sparse_r_img.type() == CV_32FC1);
-    cv::Mat in = sparse_r_img.isContinuous() ? sparse_r_img : sparse_r_img.clone();
-    dense_r_img.create(in.rows, in.cols, CV_32FC1);
-    dcmt::MatView s = dcmt::view_of(in), d = dcmt::view_of(dense_r_img);
-    dcmt::interpolate_with_superpixels(slic.clusters, slic.centers.size(), s, d, blur_type, use_superpixel);
+    const cv::Mat in = dcmt::continuous(sparse_r_img);
+    cv::Mat out(in.rows, in.cols, CV_32FC1);
+    dcmt::MatView d = dcmt::view_of(out);
+    dcmt::interpolate_with_superpixels(slic.clusters, slic.centers.size(), dcmt::view_of(in), d, blur_type, use_superpixel);
+    dense_r_img = out;
+}
+
+// main_sl.cpp:715.  `img` is an EntryType matrix: cv::Mat(rows, cols, CV_32FC(sizeof(EntryType))) (:1165, :1169)
+inline void calculateMeasuementDerivatives(cv::Mat& img) {
+    CV_Assert(img.elemSize() >= dcmt::kEntryBytes);
+    dcmt::MatView v = dcmt::view_of(img);
+    dcmt::calculateMeasuementDerivatives(v);
+}
+// main_sl.cpp:846
+inline void get_initial_disparity(cv::Mat& initial_guess, cv::Mat& disparity_IG) {
+    CV_Assert(initial_guess.type() == CV_32FC1 && disparity_IG.type() == CV_32FC1);
+    dcmt::MatView d = dcmt::view_of(disparity_IG);
+    dcmt::get_initial_disparity(dcmt::view_of(initial_guess), d);
+}
+// main_sl.cpp:804
+inline void optimize_IG(cv::Mat& entryMatrix_left, cv::Mat& entryMatrix_right, cv::Mat& disparity_map_IG) {
+    CV_Assert(entryMatrix_left.elemSize() >= dcmt::kEntryBytes && entryMatrix_right.elemSize() >= dcmt::kEntryBytes &&
+              disparity_map_IG.type() == CV_32FC1);
+    dcmt::MatView d = dcmt::view_of(disparity_map_IG);
+    dcmt::optimize_IG(dcmt::view_of(entryMatrix_left), dcmt::view_of(entryMatrix_right), d);
+}
+// main_sl_OFFICIAL.cpp:832: the caller supplies the iteration count; damp 1370 (:836), error clip 221 (:848-855)
+inline void optimize_IG(cv::Mat& entryMatrix_left, cv::Mat& entryMatrix_right, cv::Mat& disparity_map_IG, int& num_iterations) {
+    dcmt::MatView d = dcmt::view_of(disparity_map_IG);
+    dcmt::optimize_IG(dcmt::view_of(entryMatrix_left), dcmt::view_of(entryMatrix_right), d, num_iterations, 1370.0f, 221.0f);
+}
+// main_sl.cpp:863
+inline void retrieve_optimized_depth(cv::Mat& disparity_refined, cv::Mat& optimized_depth) {
+    CV_Assert(disparity_refined.type() == CV_32FC1 && optimized_depth.type() == CV_32FC1);
+    dcmt::MatView d = dcmt::view_of(optimized_depth);
+    dcmt::retrieve_optimized_depth(dcmt::view_of(disparity_refined), d);
+}
+// main_sl.cpp:747.  Vec2 is Eigen::Vector2f (anything with operator[] / operator() on two floats); img_point = (row, column)
+template <class Vec2>
+inline bool calculateObservationDerivatives(const cv::Mat& target_img, const Vec2 img_point, float& value, Vec2& derivative) {
+    float dx = 0.0f, dy = 0.0f;
+    if (!dcmt::sample_entries(dcmt::view_of(target_img), img_point[0], img_point[1], value, dx, dy)) return false;
+    derivative[0] = dx;
+    derivative[1] = dy;
+    return true;
 }
 
 // main_sl.cpp:1165-1253: the sequence entry fill -> calculateMeasuementDerivatives -> get_initial_disparity ->
-// optimize_IG -> retrieve_optimized_depth -> GaussianBlur on the caller's Mats (gray CV_8UC1, depth CV_32FC1)
+// optimize_IG -> retrieve_optimized_depth -> GaussianBlur in ONE fused kernel, on the caller's gray / depth Mats
 inline void stereo_refine(const cv::Mat& dense_range_img, const cv::Mat& left_gray, const cv::Mat& right_gray, cv::Mat& optimized_depth,
                           const dcmt_stereo_params* params = nullptr) {
     CV_Assert(dense_range_img.type() == CV_32FC1 && left_gray.type() == CV_8UC1 && right_gray.type() == CV_8UC1);
-    cv::Mat ig = dense_range_img.isContinuous() ? dense_range_img : dense_range_img.clone();
-    cv::Mat l = left_gray.isContinuous() ? left_gray : left_gray.clone(), r = right_gray.isContinuous() ? right_gray : right_gray.clone();
-    optimized_depth.create(ig.rows, ig.cols, CV_32FC1);
-    dcmt::MatView vi = dcmt::view_of(ig), vl = dcmt::view_of(l), vr = dcmt::view_of(r), vo = dcmt::view_of(optimized_depth);
-    dcmt::stereo_refine(vi, vl, vr, vo, params);
+    const cv::Mat ig = dcmt::continuous(dense_range_img), l = dcmt::continuous(left_gray), r = dcmt::continuous(right_gray);
+    cv::Mat out(ig.rows, ig.cols, CV_32FC1);
+    dcmt::MatView vo = dcmt::view_of(out);
+    dcmt::stereo_refine(dcmt::view_of(ig), dcmt::view_of(l), dcmt::view_of(r), vo, params);
+    optimized_depth = out;
 }
 
 // the evaluation functions of main.cpp:16 / main_lc.cpp:85 / main_sl.cpp:1031 (CV_32FC1 Mats)
 inline void evaluate_performance(const cv::Mat& GT_img, const cv::Mat& r_img, float& mse) {
-    cv::Mat g = GT_img.isContinuous() ? GT_img : GT_img.clone(), r = r_img.isContinuous() ? r_img : r_img.clone();
+    const cv::Mat g = dcmt::continuous(GT_img), r = dcmt::continuous(r_img);
     dcmt::evaluate_performance(dcmt::view_of(g), dcmt::view_of(r), mse);
 }
 inline void evaluate_performance(const cv::Mat& GT_img, const cv::Mat& r_img, float& mse, float& mae) {
-    cv::Mat g = GT_img.isContinuous() ? GT_img : GT_img.clone(), r = r_img.isContinuous() ? r_img : r_img.clone();
+    const cv::Mat g = dcmt::continuous(GT_img), r = dcmt::continuous(r_img);
     dcmt::evaluate_performance(dcmt::view_of(g), dcmt::view_of(r), mse, mae);
 }
 inline void evaluate_performances(cv::Mat& GT_img, cv::Mat& r_img, float& mae, float& rmse) {
-    cv::Mat g = GT_img.isContinuous() ? GT_img : GT_img.clone(), r = r_img.isContinuous() ? r_img : r_img.clone();
+    const cv::Mat g = dcmt::continuous(GT_img), r = dcmt::continuous(r_img);
     dcmt::evaluate_performances(dcmt::view_of(g), dcmt::view_of(r), mae, rmse);
 }
 #endif  // DCMT_HAVE_OPENCV

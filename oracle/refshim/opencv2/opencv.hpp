@@ -34,13 +34,17 @@
 typedef unsigned char uchar;
 
 #define CV_8U 0
+#define CV_16U 2
 #define CV_32F 5
 #define CV_CN_SHIFT 3
 #define CV_MAKETYPE(depth, cn) ((depth) + (((cn)-1) << CV_CN_SHIFT))
 #define CV_8UC1 CV_MAKETYPE(CV_8U, 1)
 #define CV_8UC3 CV_MAKETYPE(CV_8U, 3)
+#define CV_16UC1 CV_MAKETYPE(CV_16U, 1)
 #define CV_32FC1 CV_MAKETYPE(CV_32F, 1)
 #define CV_32FC(n) CV_MAKETYPE(CV_32F, (n))
+
+#define CV_Assert(expr) do { if (!(expr)) throw cv::Exception("refshim: assertion failed: " #expr); } while (0)
 
 namespace cv {
 
@@ -81,7 +85,7 @@ struct Vec3b {
 
 inline int elem_size_of_type(int type) {
     const int depth = type & ((1 << CV_CN_SHIFT) - 1), cn = (type >> CV_CN_SHIFT) + 1;
-    const int bytes = depth == CV_8U ? 1 : depth == CV_32F ? 4 : 0;
+    const int bytes = depth == CV_8U ? 1 : depth == CV_16U ? 2 : depth == CV_32F ? 4 : 0;
     if (!bytes) throw Exception("refshim: Mat depth not supported by the stand-in header");
     return bytes * cn;
 }
@@ -109,6 +113,11 @@ public:
     }
     int type() const { return type_; }
     bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
+    bool isContinuous() const { return step == (size_t)cols * elemSize() || rows <= 1; }
+    void copyTo(Mat& dst) const {  // unmasked: (re)allocates like OpenCV, then copies row by row
+        dst.create(rows, cols, type_);
+        for (int r = 0; r < rows; ++r) std::memcpy(dst.data + (size_t)r * dst.step, data + (size_t)r * step, (size_t)cols * elemSize());
+    }
     size_t elemSize() const { return (size_t)elem_size_of_type(type_); }
     Mat clone() const {
         Mat m;

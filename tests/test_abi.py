@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol(product_lib):
     exported = set(re.findall(r"\bT (dcmt_\w+)", out))
     assert set(declared_symbols()) <= exported
     assert not [s for s in exported if "oracle" in s], "the product must not link the oracle"
-    assert product_lib.dcmt_version() == 100
+    assert product_lib.dcmt_version() == 200
 
 
 def test_product_is_sm100a_cuda_and_does_not_link_oracle(product_lib):

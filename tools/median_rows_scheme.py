@@ -144,8 +144,12 @@ def emit_fn(name, doc, net, n_in, outs, in_expr, n_out, sig):
     no = sum(1 for o in ops if o[1] == "other")
     lines = [f"// {doc}", f"// {len(net)} comparators -> {n2} two-input + {n3} three-input min/max ops + {no} `other` ops.",
              "template <class Ops, class T>", f"__device__ __forceinline__ void {name}({sig}) {{"]
+    k_other = 0
     for nm, kind, args in ops:
         fn = kind + ("3" if len(args) == 3 and kind != "other" else "")
+        if kind == "other":  # numbered: Ops decides per index which pipe computes the maximum (oth<I>)
+            fn = f"template oth<{k_other}>"
+            k_other += 1
         lines.append(f"    const T {nm} = ops.{fn}({', '.join(args)});")
     for r in range(n_out):
         lines.append(f"    o[{r}] = {res[r]};")
@@ -157,7 +161,9 @@ def emit():
     lines = [
         "// median_rows.cuh -- GENERATED by tools/median_rows_scheme.py (networks found by tools/select_network.py); do not edit.",
         "// Building blocks of the shared-work 5x5 median (cv::medianBlur(5), img_completion.cpp:170): merge of two sorted",
-        "// fives, and ranks 7..12 of the merge of two sorted tens.  Ops: mn, mx, mn3, mx3, other(a, b, lo) as in median_net.cuh.",
+        "// fives, and ranks 7..12 of the merge of two sorted tens.  Ops: mn, mx, mn3, mx3 as in median_net.cuh, and oth<I>(a, b, lo) =",
+        "// the element of {a, b} that is not lo = mn(a, b); I numbers the compare-exchanges of a network so that Ops can split",
+        "// them between the min/max pipe (mx) and the multiply-add pipe (a + b - lo).",
         "#pragma once", "", "namespace dcmt {", ""]
     lines += emit_fn("merge_5_5", "o = merge(a, b), all ascending", MERGE55, 10, MERGE55_OUT,
                      [f"a[{k}]" for k in range(5)] + [f"b[{k}]" for k in range(5)], 10,
