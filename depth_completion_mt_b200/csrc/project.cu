@@ -3,9 +3,11 @@
 // projection) -> perspective division -> bounds test on the float coordinates -> (int) truncation -> scatter of the
 // depth, LAST point in file order wins (:515) -> cv::normalize(NORM_MINMAX, 0, 80) (:521).
 //
-// All arithmetic is float32 in the order of the source: the transform is written out term by term (:485-487), the
-// Eigen product P * p.homogeneous() (:500) accumulates its four terms left to right; explicit __fmul_rn / __fadd_rn /
-// __fdiv_rn keep the compiler from contracting them into FMAs.  "Last writer wins" is made deterministic with a 64-bit
+// All arithmetic is float32 in the order of the source: the transform is written out term by term (:485-487); the
+// Eigen product P * p.homogeneous() (:500) is evaluated the way Eigen >= 3.3 evaluates it (Geometry/Homogeneous.h:
+// dst = P.leftCols<3>() * p, then dst += P.col(3); the three-term sum of the small fixed-size product is the balanced
+// tree a0 + (a1 + a2) of redux_novec_unroller) -- Eigen 3.2 summed left to right; the reference pins no version.
+// Explicit __fmul_rn / __fadd_rn / __fdiv_rn keep the compiler from contracting anything into FMAs.  "Last writer wins" is made deterministic with a 64-bit
 // atomicMax on (point index + 1) << 32 | depth bits per pixel.  cv::normalize is restated from OpenCV 4.x
 // (scale = float((b - a) / (max - min)), shift = float(a) - float(min * scale), dst = src * scale + shift).
 #include "project.cuh"
@@ -28,6 +30,10 @@ __device__ __forceinline__ float row_dot(const float* m, float x, float y, float
     return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[0], x), __fmul_rn(m[1], y)), __fmul_rn(m[2], z)), m[3]);
 }
 
+__device__ __forceinline__ float row_dot_eigen(const float* m, float x, float y, float z) {  // (m0 x + (m1 y + m2 z)) + m3
+    return __fadd_rn(__fadd_rn(__fmul_rn(m[0], x), __fadd_rn(__fmul_rn(m[1], y), __fmul_rn(m[2], z))), m[3]);
+}
+
 __global__ void __launch_bounds__(256) k_project_scatter(const float4* __restrict__ pts, int n, Mats m, int rows, int cols,
                                                          unsigned long long* __restrict__ keys, unsigned* __restrict__ minmax) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -36,7 +42,7 @@ __global__ void __launch_bounds__(256) k_project_scatter(const float4* __restric
         const float4 p = __ldg(pts + i);
         const float tx = row_dot(m.T, p.x, p.y, p.z), ty = row_dot(m.T + 4, p.x, p.y, p.z), tz = row_dot(m.T + 8, p.x, p.y, p.z);
         if (tz > 0.0f) {  // :488
-            const float X = row_dot(m.P, tx, ty, tz), Y = row_dot(m.P + 4, tx, ty, tz), Z = row_dot(m.P + 8, tx, ty, tz);
+            const float X = row_dot_eigen(m.P, tx, ty, tz), Y = row_dot_eigen(m.P + 4, tx, ty, tz), Z = row_dot_eigen(m.P + 8, tx, ty, tz);
             const float u = __fdiv_rn(X, Z), v = __fdiv_rn(Y, Z);  // :501-502
             if (u >= 0.0f && u < (float)cols && v >= 0.0f && v < (float)rows) {  // :505-506 (NaN fails every comparison)
                 const int iu = (int)u, iv = (int)v;  // :510-511

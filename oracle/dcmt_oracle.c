@@ -541,11 +541,17 @@ DCMT_ORACLE_API void dcmt_oracle_evaluate(const float *gt, const float *r, int r
 
 /* ---------------------------------------------------------------- LiDAR projection
  * Literal restatement of src/DC_stereo_lidar/main_sl.cpp:478-523: transform (:485-487, term by term), z > 0 filter
- * (:488), Eigen P * p.homogeneous() (:500; four terms accumulated left to right), division (:501-502), bounds test on
+ * (:488), Eigen P * p.homogeneous() (:500; evaluated like Eigen >= 3.3: (a0 + (a1 + a2)) + P.col(3), see refshim/Eigen/Dense), division (:501-502), bounds test on
  * the float coordinates (:505-506), (int) truncation (:510-511), last writer wins (:515); then cv::normalize
  * (NORM_MINMAX, a, b; OpenCV 4.x norm.cpp: float scale, float shift, dst = src * scale + shift).  T: 4x4 row-major,
  * P: 3x4 row-major.  Returns the number of projected points (:508). */
 static float row_dot4(const float *m, float x, float y, float z) { return m[0] * x + m[1] * y + m[2] * z + m[3]; }
+static float row_dot4_eigen(const float *m, float x, float y, float z) {
+    const float a0 = m[0] * x, a1 = m[1] * y, a2 = m[2] * z;
+    float d = a0 + (a1 + a2);
+    d += m[3];
+    return d;
+}
 DCMT_ORACLE_API int dcmt_oracle_lidar_project(const float *pts, int n, const float *T, const float *P, int rows, int cols,
                                               float *projected, float *normalized, float a, float b) {
     int count = 0;
@@ -554,7 +560,7 @@ DCMT_ORACLE_API int dcmt_oracle_lidar_project(const float *pts, int n, const flo
         const float x = pts[4 * i], y = pts[4 * i + 1], z = pts[4 * i + 2];
         const float tx = row_dot4(T, x, y, z), ty = row_dot4(T + 4, x, y, z), tz = row_dot4(T + 8, x, y, z);
         if (!(tz > 0)) continue;
-        const float X = row_dot4(P, tx, ty, tz), Y = row_dot4(P + 4, tx, ty, tz), Z = row_dot4(P + 8, tx, ty, tz);
+        const float X = row_dot4_eigen(P, tx, ty, tz), Y = row_dot4_eigen(P + 4, tx, ty, tz), Z = row_dot4_eigen(P + 8, tx, ty, tz);
         const float u = X / Z, v = Y / Z;
         if (u >= 0 && u < cols && v >= 0 && v < rows) {
             count++;

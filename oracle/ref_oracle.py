@@ -24,7 +24,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_ref", "libdcmt_ref.so")
 _REF = os.environ.get("DCMT_REFERENCE_DIR", "/root/reference")
-_SHIM = [os.path.join(_HERE, "refshim", n) for n in ("refshim.cpp", "img_completion.h", os.path.join("opencv2", "opencv.hpp"))]
+_SHIM = [os.path.join(_HERE, "refshim", n) for n in ("refshim.cpp", "refshim_ranges.cpp", "refshim_front.cpp", "extract_ranges.sh",
+                                                     "img_completion.h", os.path.join("opencv2", "opencv.hpp"), os.path.join("Eigen", "Dense"))]
 BLUR = {"none": 0, "gaussian": 1, "bilateral": 2}
 
 _MORPH_CB = C.CFUNCTYPE(C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int)
@@ -94,6 +95,8 @@ def _blur(kind, src, dst, rows, cols, cv_type, ksize, p0, p1):
             r = cv2.GaussianBlur(s, (ksize, ksize), p0)
         elif kind == 2:
             r = cv2.bilateralFilter(s, ksize, p0, p1)
+        elif kind == 3:  # cv::normalize(src, dst, alpha, beta, NORM_MINMAX) (main_sl.cpp:523)
+            r = cv2.normalize(s, None, p0, p1, cv2.NORM_MINMAX)
         else:
             return 2
         _view(dst, rows, cols, cv_type)[...] = r
@@ -236,3 +239,36 @@ def evaluate(gt, r, variant):
     rc = lib().dcmt_ref_evaluate(code, _p(g), _p(v), g.shape[0], g.shape[1], _p(out))
     assert rc == 0
     return np.float32(out[0]) if code == 0 else (np.float32(out[0]), np.float32(out[1]))
+
+
+def lidar_project(points, T, P, rows, cols):
+    """The projection loops + cv::normalize(0, 80) of withSuperPixels (main_sl.cpp:474-523), compiled from the reference's
+    own lines (refshim_front.cpp).  points: n x 4 float32; T 4x4, P 3x4.  Returns (projected, normalized, n_projected)."""
+    pts = np.ascontiguousarray(points, dtype=np.float32).reshape(-1, 4)
+    t = np.ascontiguousarray(T, dtype=np.float32).reshape(16)
+    p = np.ascontiguousarray(P, dtype=np.float32).reshape(12)
+    proj = np.empty((rows, cols), np.float32)
+    nrm = np.empty((rows, cols), np.float32)
+    n = C.c_int(0)
+    e = _err()
+    rc = lib().dcmt_ref_lidar_project(_p(pts), len(pts), _p(t), _p(p), rows, cols, _p(proj), _p(nrm), C.byref(n), e, 256)
+    if rc:
+        raise RuntimeError(e.value.decode(errors="replace"))
+    return proj, nrm, n.value
+
+
+def write_M(path, mat):
+    """write_M (utils.cpp:39-58) of a CV_32FC1 matrix."""
+    m = np.ascontiguousarray(mat, dtype=np.float32)
+    lib().dcmt_ref_write_M(str(path).encode(), _p(m), *m.shape)
+
+
+def read_M(path):
+    """read_M (utils.cpp:15-37): the CV_32FC1 matrix of a .bin file, or None."""
+    rows, cols, typ = C.c_int(0), C.c_int(0), C.c_int(0)
+    cap = os.path.getsize(path) // 4
+    out = np.empty(max(cap, 1), np.float32)
+    n = lib().dcmt_ref_read_M(str(path).encode(), C.byref(rows), C.byref(cols), C.byref(typ), _p(out), int(cap))
+    if n == 0 or typ.value != 5:
+        return None
+    return out[:n].reshape(rows.value, cols.value).copy()

@@ -90,11 +90,19 @@ inline int elem_size_of_type(int type) {
     return bytes * cn;
 }
 
+// cv::MatStep as far as the reference uses it: converts to size_t, and step[0] is the row step (utils.cpp:54)
+struct MatStep {
+    size_t p;
+    MatStep(size_t v = 0) : p(v) {}
+    operator size_t() const { return p; }
+    size_t operator[](int) const { return p; }
+};
+
 class Mat {
 public:
     int rows, cols;
     uchar* data;
-    size_t step;  // bytes per row
+    MatStep step;  // bytes per row
 
     Mat() : rows(0), cols(0), data(nullptr), step(0), type_(0) {}
     Mat(int r, int c, int type) : Mat() { create(r, c, type); }
@@ -112,6 +120,8 @@ public:
         Mat m(r, c, type); std::memset(m.data, 1, (size_t)r * m.step); return m;
     }
     int type() const { return type_; }
+    int depth() const { return type_ & ((1 << CV_CN_SHIFT) - 1); }
+    int channels() const { return (type_ >> CV_CN_SHIFT) + 1; }
     bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
     bool isContinuous() const { return step == (size_t)cols * elemSize() || rows <= 1; }
     void copyTo(Mat& dst) const {  // unmasked: (re)allocates like OpenCV, then copies row by row
@@ -149,6 +159,7 @@ private:
 };
 
 enum MorphTypes { MORPH_ERODE = 0, MORPH_DILATE = 1, MORPH_OPEN = 2, MORPH_CLOSE = 3 };
+enum NormTypes { NORM_MINMAX = 32 };
 
 // imgproc entry points the reference calls; defined in oracle/refshim/refshim.cpp (forwarded to cv2)
 void dilate(const Mat& src, Mat& dst, const Mat& kernel);
@@ -156,7 +167,9 @@ void morphologyEx(const Mat& src, Mat& dst, int op, const Mat& kernel);
 void medianBlur(const Mat& src, Mat& dst, int ksize);
 void GaussianBlur(const Mat& src, Mat& dst, Size ksize, double sigmaX);
 void bilateralFilter(const Mat& src, Mat& dst, int d, double sigmaColor, double sigmaSpace);
-// drawing (slic.cpp:330, display only, not on the path)
+// core: cv::normalize(src, dst, alpha, beta, NORM_MINMAX) (main_sl.cpp:523), forwarded to cv2 like the filters
+void normalize(const Mat& src, Mat& dst, double alpha, double beta, int norm_type);
+// drawing (slic.cpp:330, main_sl.cpp:515: display only, not on the path)
 inline void circle(Mat&, Point, int, const Scalar&, int) {}
 
 }  // namespace cv

@@ -25,7 +25,7 @@ extern "C" {
 // src / dst: dense row-major rows x cols planes of the given OpenCV type; dst never aliases src (the shim copies)
 typedef int (*ref_morph_cb)(int op /*1 dilate, 3 close*/, const void* src, void* dst, int rows, int cols, int type,
                             const unsigned char* kernel, int krows, int kcols);
-typedef int (*ref_blur_cb)(int kind /*0 median, 1 gaussian, 2 bilateral*/, const void* src, void* dst, int rows, int cols,
+typedef int (*ref_blur_cb)(int kind /*0 median, 1 gaussian, 2 bilateral, 3 normalize(p0, p1, NORM_MINMAX)*/, const void* src, void* dst, int rows, int cols,
                            int type, int ksize, double p0, double p1);
 }
 
@@ -77,6 +77,10 @@ void GaussianBlur(const Mat& src, Mat& dst, Size ksize, double sigmaX) {
     ++g_calls[3];
     if (ksize.width != ksize.height) throw Exception("refshim: square Gaussian kernels only");
     run_blur(1, src, dst, ksize.width, sigmaX, 0.0);
+}
+void normalize(const Mat& src, Mat& dst, double alpha, double beta, int norm_type) {
+    if (norm_type != NORM_MINMAX) throw Exception("refshim: NORM_MINMAX only");
+    run_blur(3, src, dst, 0, alpha, beta);
 }
 void bilateralFilter(const Mat& src, Mat& dst, int d, double sigmaColor, double sigmaSpace) {
     ++g_calls[4];

@@ -263,3 +263,46 @@ def test_gpu_slic_equals_reference_build(gpu_lib):
     r_lab, r_cen, _ = ro.generate_superpixels(img, 18, 40)
     assert np.array_equal(labels.cpu().numpy(), r_lab)
     assert np.array_equal(np.ascontiguousarray(centers.cpu().numpy(), dtype=np.float64).view(np.uint64), r_cen.view(np.uint64))
+
+
+# ---- the callers either side of the path, pinned to the reference's own lines ----------------------
+T_KITTI, P_KITTI = synth.KITTI_T_VELO_TO_CAM, synth.KITTI_P_RECT_02
+
+
+@pytest.mark.parametrize("rows,cols,n", [(352, 1216, 120000), (375, 1242, 60000), (64, 200, 20000), (48, 160, 30000)])
+def test_projection_loop_reference_vs_restatement(rows, cols, n):
+    """main_sl.cpp:474-523 compiled from the reference (two PCL types and the Eigen product are stand-ins, see
+    refshim_front.cpp / refshim/Eigen/Dense) == the C restatement the GPU kernel is tested against, bit for bit:
+    projected depth image, its cv::normalize(0, 80) and the count of projected points."""
+    pts = synth.velodyne_cloud({1216: 0, 1242: 5, 200: 0, 160: 1}[cols], n)
+    if cols == 160:  # many points per pixel: last writer in file order wins
+        pts = np.concatenate([pts, pts[::-1] * np.float32(1.0001), pts[: n // 2]])
+    rp, rn, rc = ro.lidar_project(pts, T_KITTI, P_KITTI, rows, cols)
+    cp, cn, cc = co.lidar_project(pts, T_KITTI, P_KITTI, rows, cols)
+    assert rc == cc and (rc > 1000 or cols < 1000)
+    assert_bit_equal(cp, rp, "projected_depths")
+    assert_bit_equal(cn, rn, "normalized_depths")
+
+
+def test_projection_loop_degenerate_clouds():
+    behind = synth.velodyne_cloud(3, 2000)
+    behind[:, 0] = -np.abs(behind[:, 0]) - 1.0
+    for pts in (np.zeros((0, 4), np.float32), behind):
+        rp, rn, rc = ro.lidar_project(pts, T_KITTI, P_KITTI, 40, 60)
+        cp, cn, cc = co.lidar_project(pts, T_KITTI, P_KITTI, 40, 60)
+        assert rc == cc == 0
+        assert_bit_equal(cp, rp, "projected_depths (empty)")
+        assert_bit_equal(cn, rn, "normalized_depths (empty)")
+
+
+def test_raw_mat_format_reference_vs_package(tmp_path):
+    """utils.cpp:15-58 (read_M / write_M, compiled from the reference) and depth_completion_mt_b200.api.read_M / write_M
+    produce and accept the same bytes."""
+    from depth_completion_mt_b200 import api
+
+    m = synth.sparse_depth(4, 37, 53, 0.3)
+    ro.write_M(tmp_path / "ref.bin", m)
+    api.write_M(tmp_path / "pkg.bin", m)
+    assert open(tmp_path / "ref.bin", "rb").read() == open(tmp_path / "pkg.bin", "rb").read()
+    assert_bit_equal(api.read_M(tmp_path / "ref.bin"), m, "package reads the reference's file")
+    assert_bit_equal(ro.read_M(tmp_path / "pkg.bin"), m, "the reference reads the package's file")
