@@ -58,6 +58,7 @@ def parse_args():
     ap.add_argument("--host-input", default="pinned", choices=["pinned", "wc"],
                     help="e2e leg, lidar_only: input in torch pinned memory, or in write-combined page-locked memory (dcmt_host_alloc)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--host-multi", action="store_true", help="single process: also time dcmt_img_completion_u16_host_multi over all visible GPUs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-frames-per-core", type=int, default=16, help="reference arm: frames per host core per step")
     return ap.parse_args()
@@ -131,8 +132,21 @@ def _ref_task(f):
     return float(out[0, 0])
 
 
+def _single_frame_ms(runs):
+    """BASELINE configs[0]: one frame, one thread (cv2.setNumThreads(1) in the worker), median of `runs` calls."""
+    _ref_task(0)
+    ts = []
+    for _ in range(runs):
+        t0 = time.perf_counter()
+        _ref_task(0)
+        ts.append(1e3 * (time.perf_counter() - t0))
+    return statistics.median(ts)
+
+
 def run_reference(args, quiet=False):
-    """Reference CPU arm: oracle port of the reference's own CPU implementation on all host cores."""
+    """Reference CPU arm: the reference's own CPU implementation (oracle/_ref, else the oracle port) on all host cores.
+    `config` is the GPU arm's (same workload, same frames per step); each timed step is a BOUNDED SAMPLE of that step
+    (cpu_baseline.sample says how many frames), and the rate is what is compared."""
     import multiprocessing as mp
 
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
@@ -142,6 +156,7 @@ def run_reference(args, quiet=False):
     ctx = mp.get_context("fork")
     with ctx.Pool(cores, initializer=_ref_worker_init, initargs=(args.workload, args.rows, args.cols, args.density)) as pool:
         kind = pool.apply(_kind)
+        single_ms = pool.apply(_single_frame_ms, (20 if args.workload != "guided" else 3,))
         frames = list(range(per_step))
         chunk = max(1, per_step // (cores * 2))
         for _ in range(max(1, args.warmup)):
@@ -152,15 +167,18 @@ def run_reference(args, quiet=False):
         dt = time.perf_counter() - t0
     fps = per_step * args.steps / dt
     is_ref = kind.startswith("reference")
-    sample = (f"{per_step} frames/step x {args.steps} steps of the {args.workload} workload "
+    sample = (f"{per_step} frames per timed step (a bounded sample of the {args.frames}-frame step of `config`) x {args.steps} steps of the {args.workload} workload "
               f"({args.rows}x{args.cols}, {args.density:.0%} valid), {kind}{'' if is_ref else ' oracle port'}, "
               "one single-threaded process per core")
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, per_step),
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "reference" if is_ref else "port", "sample": sample},
+        "config": workload_config(args, args.frames),
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "reference" if is_ref else "port", "sample": sample,
+                         "sample_frames_per_step": per_step, "single_thread_ms": single_ms,
+                         "single_thread_note": "one frame, one thread, median of 20 calls (BASELINE configs[0]); the imgproc calls go "
+                                               "through Python / cv2 callbacks (7 per frame), a native OpenCV build would be somewhat faster"},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -281,7 +299,8 @@ def measured_peak():
 
 
 def ncu_traffic(workload):
-    """dram bytes per frame from the committed ncu capture, if one exists (profiles/traffic.json)."""
+    """record of the committed ncu capture of this workload, if one exists (profiles/traffic.json): DRAM bytes and warp
+    instructions per frame, and the launch configuration they were captured at (the bench's own chunk size)."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
             return json.load(fh).get(workload)
@@ -381,24 +400,79 @@ def run_ours(args):
                 continue
             golden_ok &= hashlib.sha256(out_t[int(p[0])].cpu().numpy().tobytes()).hexdigest() == p[4]
 
-    # ---- end to end through the host entry point: pinned host buffers, H2D + D2H inside the timed region
-    e2e = None
+    # ---- end to end through the host entry points: pinned host buffers, H2D + D2H inside the timed region; next to
+    #      every leg the COPY-ONLY ceiling: the same buffers, chunking and streams with the kernels left out
+    def timed_host(fn):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        barrier()
+        t0w = time.time()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            fn()
+        torch.cuda.synchronize()
+        ms = 1e3 * (time.perf_counter() - t0)
+        t1w = time.time()
+        barrier()
+        if sampler:
+            sampler.mark(t0w, t1w)
+        return ms
+
+    import ctypes as C
+
+    e2e_ms = e2e16_ms = ceil_ms = ceil16_ms = multi_ms = None
+    latency = None
     if not args.no_e2e:
         if args.workload == "lidar_only":
             if args.host_input == "wc":
-                hb = api.HostBuffer((n, rows, cols), np.uint16 if args.input == "u16" else np.float32, write_combined=True, lib=lib)
+                hb = api.HostBuffer((n, rows, cols), np.float32, write_combined=True, lib=lib)
                 holder["hb"] = hb
-                hb.array[...] = d_in.cpu().numpy()
+                hb.array[...] = (d_in16.to(torch.float32) / 256.0).cpu().numpy()
                 np_in = hb.array
             else:
-                h_in = torch.empty((n, rows, cols), dtype=d_in.dtype, pin_memory=True)
-                h_in.copy_(d_in)
+                h_in = torch.empty((n, rows, cols), dtype=torch.float32, pin_memory=True)
+                h_in.copy_(d_in16.to(torch.float32) / 256.0)
                 np_in = h_in.numpy()
+            h_in16 = torch.empty((n, rows, cols), dtype=torch.uint16, pin_memory=True)
+            h_in16.copy_(d_in16)
+            np_in16 = h_in16.numpy()
             h_out = torch.empty((n, rows, cols), dtype=torch.float32, pin_memory=True)
             np_out = h_out.numpy()
+            e2e_ms = timed_host(lambda: api.img_completion(np_in, False, "gaussian", path=args.path, out=np_out, lib=lib))
+            assert bool(torch.equal(h_out[:UNIQUE].to(dev), out_t[:UNIQUE])), "host path and device path disagree"
+            # the same frames as the KITTI uint16 payload (dcmt_img_completion_u16_host, main.cpp:75-93): half the H2D bytes
+            h_out.zero_()
+            e2e16_ms = timed_host(lambda: api.img_completion(np_in16, False, "gaussian", out=np_out, lib=lib))
+            assert bool(torch.equal(h_out[:UNIQUE].to(dev), out_t[:UNIQUE])), "uint16 host path and device path disagree"
+            ceil_ms = timed_host(lambda: lib.check(lib.dcmt_debug_host_copy_f32(np_in.ctypes.data, np_out.ctypes.data, rows, cols, n, None, 0)))
+            ceil16_ms = timed_host(lambda: lib.check(lib.dcmt_debug_host_copy_u16(np_in16.ctypes.data, np_out.ctypes.data, rows, cols, n, None, 0)))
+            # one process, all visible GPUs: the multi-device host entry point (only where this rank sees several devices)
+            if world == 1 and torch.cuda.device_count() > 1 and args.host_multi:
+                h_out.zero_()
+                multi_ms = timed_host(lambda: api.img_completion(np_in16, False, "gaussian", out=np_out, devices="all", lib=lib))
+                assert bool(torch.equal(h_out[:UNIQUE].to(dev), out_t[:UNIQUE])), "multi-device host path and device path disagree"
+            # single-frame latency (BASELINE configs[0], main.cpp:93 is called with ONE frame): median of 30 calls
+            def med(fn, k=30):
+                fn()
+                ts = []
+                for _ in range(k):
+                    t0 = time.perf_counter()
+                    fn()
+                    ts.append(1e3 * (time.perf_counter() - t0))
+                return statistics.median(ts)
+            one_in, one_in16, one_out = np_in[:1], np_in16[:1], np_out[:1]
+            d_one, d_one_out = d_in[:1].contiguous(), torch.empty((1, rows, cols), dtype=torch.float32, device=dev)
 
-            def host_step():
-                api.img_completion(np_in, False, "gaussian", path=args.path, out=np_out, lib=lib)
+            def dev_one(path):
+                api.img_completion(d_one, False, "gaussian", path=path, out=d_one_out, lib=lib)
+                torch.cuda.synchronize()
+            latency = {"unit": "ms", "calls": 30, "frames_per_call": 1,
+                       "f32_host": med(lambda: api.img_completion(one_in, False, "gaussian", out=one_out, lib=lib)),
+                       "u16_host": med(lambda: api.img_completion(one_in16, False, "gaussian", out=one_out, lib=lib)),
+                       "device_auto": med(lambda: dev_one("auto")), "device_fused": med(lambda: dev_one("fused")),
+                       "note": "one 352x1216 frame per call, median wall time incl. the synchronisation; *_host: pinned host buffers in "
+                               "and out (dcmt_img_completion_f32_host / _u16_host); device_*: resident input, kernels + sync only"}
         elif args.workload == "guided":
             h_in = torch.empty((n, rows, cols), dtype=torch.float32, pin_memory=True)
             h_in.copy_(d_in)
@@ -409,6 +483,7 @@ def run_ours(args):
 
             def host_step():
                 holder["h"] = api.interpolate_with_superpixels(np_lab, np_in, "gaussian", 1, n_clusters=k, out=np_out, lib=lib)
+            e2e_ms = timed_host(host_step)
         else:
             hs = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in (d_ig, d_l, d_r)]
             for a, b in zip(hs, (d_ig, d_l, d_r)):
@@ -419,53 +494,11 @@ def run_ours(args):
 
             def host_step():
                 holder["h"] = api.stereo_refine(nps[0], nps[1], nps[2], prm, out=np_out, lib=lib)
-        for _ in range(2):
-            host_step()
-        torch.cuda.synchronize()
-        barrier()
-        t0w = time.time()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            host_step()
-        torch.cuda.synchronize()
-        e2e_ms = 1e3 * (time.perf_counter() - t0)
-        t1w = time.time()
-        barrier()
-        if sampler:
-            sampler.mark(t0w, t1w)
-        if args.workload == "lidar_only":
-            assert bool(torch.equal(h_out[:UNIQUE].to(dev), out_t[:UNIQUE])), "host path and device path disagree"
-        # the same frames as the KITTI uint16 payload (dcmt_img_completion_u16_host): half the host-to-device bytes
-        e2e16_ms = None
-        if args.workload == "lidar_only" and args.input == "f32":
-            h_in16 = torch.empty((n, rows, cols), dtype=torch.uint16, pin_memory=True)
-            h_in16.copy_(d_in16)
-            np_in16 = h_in16.numpy()
-            h_out.zero_()
-            for _ in range(2):
-                api.img_completion(np_in16, False, "gaussian", out=np_out, lib=lib)
-            torch.cuda.synchronize()
-            barrier()
-            t0w = time.time()
-            t0 = time.perf_counter()
-            for _ in range(args.steps):
-                api.img_completion(np_in16, False, "gaussian", out=np_out, lib=lib)
-            torch.cuda.synchronize()
-            e2e16_ms = 1e3 * (time.perf_counter() - t0)
-            t1w = time.time()
-            barrier()
-            if sampler:
-                sampler.mark(t0w, t1w)
-            assert bool(torch.equal(h_out[:UNIQUE].to(dev), out_t[:UNIQUE])), "uint16 host path and device path disagree"
-    else:
-        e2e_ms = 0.0
-        e2e16_ms = None
+            e2e_ms = timed_host(host_step)
 
     # ---- per-kernel split of the fused path (CUDA events around each kernel, a few extra untimed steps)
     kernels = None
     if args.workload == "lidar_only":
-        import ctypes as C
-
         lib.check(lib.dcmt_profile_begin())
         for _ in range(3):
             step()
@@ -481,10 +514,16 @@ def run_ours(args):
                 "k_q8_tail": {"ms_per_step": tm.value / 3, "alg_bytes_per_px": 6, "achieved_GBps": 6 * px / (tm.value * 1e6),
                               "frac": 6 * px / (tm.value * 1e6) / peak_, "note": "uint16 intermediate in, float32 out; dominant kernel"},
                 "chunks_per_step": ch.value // 3,
+                "how": "CUDA events around each kernel over 3 extra steps AFTER the timed region (dcmt_profile_begin / _end)",
             }
     res = sharding.gather_validation(elapsed_ms, n * args.steps, sums, device=dev)
-    res_e2e = sharding.gather_validation(e2e_ms, n * args.steps, sums, device=dev)
-    res_e2e16 = sharding.gather_validation(e2e16_ms, n * args.steps, sums, device=dev) if e2e16_ms is not None else None
+    def gathered_fps(ms):
+        if ms is None:
+            return None
+        g = sharding.gather_validation(ms, n * args.steps, sums, device=dev)
+        return g["total_frames"] / (g["max_ms"] / 1e3)
+
+    fps_e2e, fps_e2e16, fps_ceil, fps_ceil16 = (gathered_fps(m) for m in (e2e_ms, e2e16_ms, ceil_ms, ceil16_ms))
     clocks = sampler.stop() if sampler else None
     if rank != 0:
         if world > 1:
@@ -497,27 +536,55 @@ def run_ours(args):
     bytes_per_frame = bpp * fpix
     peak, peak_src = measured_peak()
     achieved = fps * bytes_per_frame / 1e9 / world  # per GPU
-    traffic = ncu_traffic(args.workload)
+    traffic_rec = ncu_traffic(args.workload) or {}
+    traffic = traffic_rec.get("dram_bytes_per_frame") if isinstance(traffic_rec, dict) else traffic_rec
+    # the bound the kernels actually run against, next to the HBM one: warp instructions per frame (committed ncu counters)
+    # over the issue rate of the chip (4 schedulers x SMs x SM clock)
+    issue = None
+    wi = traffic_rec.get("warp_instructions_per_frame") if isinstance(traffic_rec, dict) else None
+    if wi and clocks and clocks.get("sm_mhz"):
+        sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+        rate = 4.0 * sms * clocks["sm_mhz"] * 1e6
+        per_frame = float(sum(wi.values()))
+        issue = {"warp_instructions_per_frame": wi, "issue_rate_per_s": rate, "floor_us_per_frame": 1e6 * per_frame / rate,
+                 "achieved_us_per_frame": 1e6 * world / fps, "frac": (per_frame / rate) / (world / fps),
+                 "source": traffic_rec.get("source"),
+                 "note": "time the counted instructions would take if every scheduler issued every cycle / measured time per frame"}
     line = {
         "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": res["max_ms"] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": workload_config(args, n),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                     "peak_source": peak_src, "kernels": kernels,
+                     "traffic_unit": "DRAM bytes per frame (read + write, front + tail)", "traffic_capture": traffic_rec.get("capture") if isinstance(traffic_rec, dict) else None,
+                     "algorithmic_bytes_per_frame": bytes_per_frame, "peak_source": peak_src, "kernels": kernels, "issue": issue,
                      "note": f"whole hot path, {bpp} algorithmic B/px x {fpix} px x frames / CUDA-event time, per GPU"},
-        "gpu_launches": int(launches), "clocks": clocks,
+        "gpu_launches": int(launches), "clocks": clocks, "lib": {"path": lib.path, "build": lib.dcmt_build_info().decode(), "version": lib.dcmt_version()},
         "validation": {"ranks": world, "checksums_equal_across_ranks": all(bool(torch.equal(c, res["checksums"][0])) for c in res["checksums"]),
                        "replicas_equal": bool(replicas_equal), "golden_sha256_match": golden_ok, "ms_per_rank": res["ms_per_rank"]},
     }
     if not args.no_e2e:
-        line["e2e"] = {"value": res_e2e["total_frames"] / (res_e2e["max_ms"] / 1e3), "unit": "frames/s",
-                       "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                       "api": "dcmt_*_host via depth_completion_mt_b200.api with numpy views of pinned host buffers",
-                       "host_binding_rank0": numa}
-        if res_e2e16 is not None:
-            line["e2e_u16_input"] = {"value": res_e2e16["total_frames"] / (res_e2e16["max_ms"] / 1e3), "unit": "frames/s",
-                                     "h2d_bytes_per_step": int(n * fpix * 2), "d2h_bytes_per_step": int(d2h),
-                                     "api": "dcmt_img_completion_u16_host: KITTI uint16 payload in (main.cpp:75-82), float32 out"}
+        api_note = "dcmt_*_host via depth_completion_mt_b200.api with numpy views of pinned host buffers"
+        if args.workload == "lidar_only":
+            # headline: the reference program's own input format -- the uint16 payload of the KITTI depth PNG (main.cpp:75-82);
+            # the call stands for convertTo(CV_32F, 1/256) + img_completion (main.cpp:79,93)
+            line["e2e"] = {"value": fps_e2e16, "unit": "frames/s", "h2d_bytes_per_step": int(n * fpix * 2), "d2h_bytes_per_step": int(d2h),
+                           "input": "uint16 KITTI depth payload (main.cpp:75-82), float32 out",
+                           "api": "dcmt_img_completion_u16_host; " + api_note, "copy_ceiling": fps_ceil16,
+                           "frac_of_copy_ceiling": fps_e2e16 / fps_ceil16 if fps_ceil16 else None,
+                           "copy_ceiling_note": "dcmt_debug_host_copy_u16: the same pinned buffers, chunks and streams, kernels left out",
+                           "host_binding_rank0": numa}
+            line["e2e_f32_input"] = {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": int(n * fpix * 4), "d2h_bytes_per_step": int(d2h),
+                                     "input": "float32 metres (the cv::Mat img_completion takes, img_completion.cpp:17)",
+                                     "api": "dcmt_img_completion_f32_host", "copy_ceiling": fps_ceil,
+                                     "frac_of_copy_ceiling": fps_e2e / fps_ceil if fps_ceil else None}
+            if multi_ms is not None:
+                line["e2e_host_multi"] = {"value": n * args.steps / (multi_ms / 1e3), "unit": "frames/s", "devices": torch.cuda.device_count(),
+                                          "api": "dcmt_img_completion_u16_host_multi: one process, one thread, all visible GPUs"}
+            if latency:
+                line["latency"] = latency
+        else:
+            line["e2e"] = {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "api": api_note,
+                           "host_binding_rank0": numa}
     if world == 1 and not args.no_cpu_baseline:
         try:
             cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "3", "--warmup", "1", "--workload", args.workload,
@@ -525,6 +592,8 @@ def run_ours(args):
             r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
             ref = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
             line["cpu_baseline"] = ref["cpu_baseline"]
+            if line.get("latency") and ref["cpu_baseline"].get("single_thread_ms"):
+                line["latency"]["reference_single_thread_ms"] = ref["cpu_baseline"]["single_thread_ms"]
         except Exception as exc:  # never lose the GPU numbers because the CPU leg failed
             line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": None, "kind": "port", "sample": f"failed: {exc!r}"}
     emit(line)

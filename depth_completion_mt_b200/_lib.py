@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libdcmt.so")
 
 DCMT_OK, DCMT_E_BADARG, DCMT_E_UNSUPPORTED, DCMT_E_CUDA, DCMT_E_NOMEM = 0, -1, -2, -3, -4
 BLUR = {"none": 0, "gaussian": 1, "bilateral": 2}
-PATH = {"auto": 0, "generic": 1, "fused": 2}
+PATH = {"auto": 0, "generic": 1, "fused": 2, "rank": 3}
 STATS_STRIDE = 4
 N_STAGES = 10
 

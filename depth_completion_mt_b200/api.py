@@ -71,19 +71,35 @@ def _np_ptr(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
+def _device_list(devices):
+    """devices=None -> (NULL, 0); "all" -> (NULL, -1) = every visible device; a sequence of ordinals -> (int[], n)."""
+    if devices is None:
+        return None, None, 0
+    if isinstance(devices, str):
+        if devices != "all":
+            raise ValueError("devices must be None, 'all' or a sequence of CUDA device ordinals")
+        return None, None, -1
+    arr = (C.c_int * len(devices))(*[int(d) for d in devices])
+    return arr, arr, len(devices)
+
+
 def img_completion(sparse, extr: bool = False, blur_type="gaussian", *, path: str = "auto", return_stats: bool = False,
-                   out=None, stream=None, lib: _lib.Library | None = None):
+                   out=None, stream=None, devices=None, lib: _lib.Library | None = None):
     """img_completion(sparse_r_img, dense_r_img, extr, blur_type) -- img_completion.cpp:17-204.
 
     ``extr`` is accepted and ignored exactly like the reference (:103 ``int densify = true``).
     ``sparse`` is float32 metres, or uint16 = metres * 256 -- the payload of a KITTI depth PNG, in which case the call
     also stands for the ``convertTo(CV_32F, 1.0 / 256.0)`` of main.cpp:79 in front of it (``dcmt_img_completion_u16``).
     Returns ``dense`` (and an int32 (n, 4) stats array when ``return_stats``).  ``out`` optionally supplies the
-    output buffer (same type/shape as ``sparse``, contiguous) so that steady-state callers allocate nothing."""
+    output buffer (same type/shape as ``sparse``, contiguous) so that steady-state callers allocate nothing.
+    ``devices`` (host arrays only): "all" or a list of CUDA device ordinals -- the frames of the batch are partitioned
+    over those GPUs inside the one call (``dcmt_img_completion_*_host_multi``)."""
     del extr
     lib = lib or _lib.load()
     blur = _blur_code(blur_type)
     if _is_torch(sparse):
+        if devices is not None:
+            raise ValueError("devices= applies to host (numpy) input; a CUDA tensor already lives on one device")
         u16 = sparse.dtype == torch.uint16
         s = _prep_torch(sparse, torch.uint16 if u16 else torch.float32, "sparse")
         s3, squeeze = _batch3(s, "sparse")
@@ -116,10 +132,18 @@ def img_completion(sparse, extr: bool = False, blur_type="gaussian", *, path: st
             out = out.reshape(s3.shape)
         stats = np.zeros((n, STATS_STRIDE), np.int32) if return_stats else None
         st_ptr = _np_ptr(stats) if return_stats else None
-        if u16:
+        keep, dev_ptr, n_dev = _device_list(devices)
+        if devices is not None and u16:
+            lib.check(lib.dcmt_img_completion_u16_host_multi(_np_ptr(s3), _np_ptr(out), rows, cols, 0, 0, 0, 0, n, blur, PATH[path], st_ptr,
+                                                             dev_ptr, n_dev))
+        elif devices is not None:
+            lib.check(lib.dcmt_img_completion_f32_host_multi(_np_ptr(s3), _np_ptr(out), rows, cols, 0, 0, n, blur, PATH[path], st_ptr,
+                                                             dev_ptr, n_dev))
+        elif u16:
             lib.check(lib.dcmt_img_completion_u16_host(_np_ptr(s3), _np_ptr(out), rows, cols, 0, 0, 0, 0, n, blur, PATH[path], st_ptr))
         else:
             lib.check(lib.dcmt_img_completion_f32_host(_np_ptr(s3), _np_ptr(out), rows, cols, 0, 0, n, blur, PATH[path], st_ptr))
+        del keep
     out = out[0] if squeeze else out
     return (out, stats) if return_stats else out
 

@@ -16,6 +16,7 @@
 #include "fused_q8.cuh"
 #include "generic.cuh"
 #include "project.cuh"
+#include "rank_f32.cuh"
 #include "slic.cuh"
 #include "stereo.cuh"
 
@@ -212,9 +213,14 @@ bool fused_applies(const CompletionCall& cc) {
            (!cc.guided || dcmt::q8_guided_smem(th, tw) <= 200 * 1024);
 }
 
-size_t completion_ws_bytes(int rows, int cols, int n_frames, bool bilateral, bool fused, bool u16_in = false) {
+size_t completion_ws_bytes(int rows, int cols, int n_frames, bool bilateral, bool fused, bool u16_in = false, bool rank = false) {
     const int chunk = fused ? fused_chunk_frames(rows, cols, n_frames) : generic_chunk_frames(rows, cols, n_frames);
     size_t b = generic_ws_bytes(rows, cols, chunk, bilateral);
+    if (fused && rank) {  // dictionary, its sizes, the code plane (rank_f32.cu)
+        const size_t code_pitch = ((size_t)cols + 7) / 8 * 8;
+        b += carve_bytes((size_t)dcmt::kRankMaxValid * chunk, sizeof(float)) + carve_bytes((size_t)chunk, sizeof(int)) +
+             carve_bytes((size_t)rows * code_pitch * chunk, sizeof(uint16_t));
+    }
     if (u16_in && !fused) b += carve_bytes((size_t)rows * cols * chunk, sizeof(float));
     if (fused) {
         const size_t mid_pitch = ((size_t)cols + 7) / 8 * 8;
@@ -266,12 +272,35 @@ int enqueue_completion(const CompletionCall& cc, const float* sparse, const int3
         p.w1 = w1;
         p.w2 = w2;
         int* tile_flags = cc.guided ? carve<int>(ar, dcmt::q8_guided_tile_flags(rows, cols, p.th, p.tw, chunk)) : nullptr;
+        // DCMT_PATH_RANK: float32 frames through the per-frame dictionary (rank_f32.cu) in front of the same kernels
+        const bool rank = cc.flags == DCMT_PATH_RANK && !in16.p;
+        float* lut = rank ? carve<float>(ar, (size_t)dcmt::kRankMaxValid * chunk) : nullptr;
+        int* lut_count = rank ? carve<int>(ar, (size_t)chunk) : nullptr;
+        uint16_t* codes = rank ? carve<uint16_t>(ar, (size_t)rows * p.mid_pitch * chunk) : nullptr;
         if (int rc = arena_ok(ar)) return rc;
+        if (rank) {
+            API_CUDA(dcmt::rank_configure(), "kernel attribute setup");
+            p.codes_in = 1;
+            p.counters_ready = 1;
+            p.lut = lut;
+        }
         for (int f0 = 0; f0 < n_frames; f0 += chunk) {
             const int nf = n_frames - f0 < chunk ? n_frames - f0 : chunk;
             ProfEvents pe{};
             API_CUDA(prof_mark(st, 0, &pe), "profiling event");
-            if (cc.guided)
+            if (rank) {
+                API_CUDA(dcmt::q8_zero_counters(p, nf, st), "counter setup launch");
+                API_CUDA(dcmt::rank_build(sparse + (size_t)f0 * fstride, pitch, fstride, rows, cols, nf, lut, lut_count, codes,
+                                          (size_t)p.mid_pitch, ctr, st),
+                         "dictionary launch");
+                if (cc.guided)
+                    API_CUDA(dcmt::q8_run_guided_front(p, nullptr, codes, (size_t)p.mid_pitch, (size_t)p.mid_pitch * rows,
+                                                       labels + (size_t)f0 * fpix, cc.n_clusters, nf, 0, tile_flags, st),
+                             "fused guided front launch");
+                else
+                    API_CUDA(dcmt::q8_run_front(p, nullptr, codes, (size_t)p.mid_pitch, (size_t)p.mid_pitch * rows, nf, 0, st),
+                             "fused front launch");
+            } else if (cc.guided)
                 API_CUDA(dcmt::q8_run_guided_front(p, sparse + (size_t)f0 * fstride, nullptr, pitch, fstride, labels + (size_t)f0 * fpix,
                                                    cc.n_clusters, nf, cc.flags != DCMT_PATH_FUSED, tile_flags, st),
                          "fused guided front launch");
@@ -373,7 +402,7 @@ int validate_completion(const float* sparse, const int32_t* labels, bool guided,
     if (!sparse || !dense) return fail(DCMT_E_BADARG, "null image pointer");
     if (guided && !labels) return fail(DCMT_E_BADARG, "null label pointer");
     if (blur_type < DCMT_BLUR_NONE || blur_type > DCMT_BLUR_BILATERAL) return fail(DCMT_E_BADARG, "blur_type %d", blur_type);
-    if (flags < DCMT_PATH_AUTO || flags > DCMT_PATH_FUSED) return fail(DCMT_E_BADARG, "flags %d", flags);
+    if (flags < DCMT_PATH_AUTO || flags > DCMT_PATH_RANK) return fail(DCMT_E_BADARG, "flags %d", flags);
     int rc = check_geometry(rows, cols, pitch_bytes, frame_stride_bytes, n_frames, g);
     if (rc) return rc;
     if (n_frames && overlaps(sparse, g->span_bytes, dense, g->span_bytes)) return fail(DCMT_E_BADARG, "input and output overlap");
@@ -397,31 +426,46 @@ int run_completion(const float* sparse, const int32_t* labels, int n_clusters, b
     const bool bilateral = blur_type == DCMT_BLUR_BILATERAL;
     Arena* ar = nullptr;
     const size_t flag_bytes = fused ? carve_bytes((size_t)n_frames, sizeof(int32_t)) : 0;
-    if ((rc = arena_acquire(st, completion_ws_bytes(rows, cols, n_frames, bilateral, fused) + flag_bytes, &ar))) return rc;
+    if ((rc = arena_acquire(st, completion_ws_bytes(rows, cols, n_frames, bilateral, fused, false, flags == DCMT_PATH_RANK) + flag_bytes, &ar)))
+        return rc;
     int32_t* d_flags = fused ? carve<int32_t>(ar, (size_t)n_frames) : nullptr;
     bool used = false;
     if ((rc = enqueue_completion(cc, sparse, labels, dense, g.pitch, g.fstride, n_frames, stats, d_flags, stages, stage_mask, ar,
                                  st, &used)))
         return rc;
-    if (!used || flags != DCMT_PATH_AUTO) return DCMT_OK;  // DCMT_PATH_FUSED: fully asynchronous, stats[3] = -1 marks bad frames
-    // DCMT_PATH_AUTO: one readback of the per-frame "not strict q8" flags, then the generic pipeline for those frames
+    if (!used || flags == DCMT_PATH_FUSED || flags == DCMT_PATH_GENERIC) return DCMT_OK;  // DCMT_PATH_FUSED: fully asynchronous, stats[3] = -1 marks bad frames
+    // DCMT_PATH_AUTO / DCMT_PATH_RANK: read the per-frame "not served" flags back (one synchronisation per pass) and redo
+    // those frames one level down: strict-q8 kernels -> dictionary (rank_f32.cu) -> generic pipeline
     int32_t* h_flags = nullptr;
     if ((rc = pinned_flags(st, (size_t)n_frames, &h_flags))) return rc;
     API_CUDA(cudaMemcpyAsync(h_flags, d_flags, (size_t)n_frames * sizeof(int32_t), cudaMemcpyDeviceToHost, st), "flag readback");
     API_CUDA(cudaStreamSynchronize(st), "kernel execution");
-    cc.flags = DCMT_PATH_GENERIC;
-    for (int f = 0; f < n_frames;) {
-        if (!h_flags[f]) { ++f; continue; }
-        int e = f;
-        while (e < n_frames && h_flags[e]) ++e;
-        // the fused work has completed (stream synchronised above): the arena is free again, but it was sized for the
-        // fused plan -- the generic pipeline of this run may need more (two float planes per frame of its chunk)
-        if ((rc = arena_acquire(st, completion_ws_bytes(rows, cols, e - f, bilateral, false), &ar))) return rc;
-        if ((rc = enqueue_completion(cc, sparse + (size_t)f * g.fstride, guided ? labels + (size_t)f * rows * cols : nullptr,
-                                     dense + (size_t)f * g.fstride, g.pitch, g.fstride, e - f,
-                                     stats ? stats + (size_t)f * DCMT_STATS_STRIDE : nullptr, nullptr, nullptr, nullptr, ar, st, nullptr)))
-            return rc;
-        f = e;
+    for (int level = flags == DCMT_PATH_AUTO ? DCMT_PATH_RANK : DCMT_PATH_GENERIC;; level = DCMT_PATH_GENERIC) {
+        cc.flags = level;
+        const bool want_flags = level == DCMT_PATH_RANK;
+        bool any = false;
+        for (int f = 0; f < n_frames;) {
+            if (!h_flags[f]) { ++f; continue; }
+            int e = f;
+            while (e < n_frames && h_flags[e]) ++e;
+            // the previous pass has completed (stream synchronised): the arena is free again, but it was sized for that
+            // pass -- this one may need more (the generic pipeline: two float planes per frame of its chunk)
+            const size_t fb = want_flags ? carve_bytes((size_t)(e - f), sizeof(int32_t)) : 0;
+            if ((rc = arena_acquire(st, completion_ws_bytes(rows, cols, e - f, bilateral, want_flags, false, want_flags) + fb, &ar))) return rc;
+            int32_t* run_flags = want_flags ? carve<int32_t>(ar, (size_t)(e - f)) : nullptr;
+            if ((rc = enqueue_completion(cc, sparse + (size_t)f * g.fstride, guided ? labels + (size_t)f * rows * cols : nullptr,
+                                         dense + (size_t)f * g.fstride, g.pitch, g.fstride, e - f,
+                                         stats ? stats + (size_t)f * DCMT_STATS_STRIDE : nullptr, run_flags, nullptr, nullptr, ar, st, nullptr)))
+                return rc;
+            if (want_flags) {
+                // arenas are reused by the next run of this pass in stream order; the flags leave through the pinned buffer first
+                API_CUDA(cudaMemcpyAsync(h_flags + f, run_flags, (size_t)(e - f) * sizeof(int32_t), cudaMemcpyDeviceToHost, st), "flag readback");
+                API_CUDA(cudaStreamSynchronize(st), "kernel execution");
+            }
+            any = true;
+            f = e;
+        }
+        if (level == DCMT_PATH_GENERIC || !any) break;
     }
     return DCMT_OK;
 }
@@ -634,7 +678,7 @@ int run_completion_host(const float* sparse, const int32_t* labels, int n_cluste
     const int hc = host_chunk_frames(rows, cols, longest);
     const size_t bytes = 2 * carve_bytes(fpix * hc, sizeof(float)) + (guided ? carve_bytes(fpix * hc, sizeof(int32_t)) : 0) +
                          carve_bytes((size_t)hc * DCMT_STATS_STRIDE, sizeof(int32_t)) + carve_bytes((size_t)hc, sizeof(int32_t)) +
-                         completion_ws_bytes(rows, cols, hc, bilateral, fused);
+                         completion_ws_bytes(rows, cols, hc, bilateral, fused, false, flags == DCMT_PATH_RANK);
     for (Lane& l : call.lanes) {
         if (l.f_end == l.f_begin) continue;
         if ((rc = call.use(l))) return rc;
@@ -691,30 +735,41 @@ int run_completion_host(const float* sparse, const int32_t* labels, int n_cluste
         }
     }
     if ((rc = call.finish())) return rc;
-    if (fused && flags == DCMT_PATH_AUTO) {
-        // frames that turned out not to be strict q8 go through the generic pipeline (runs of consecutive frames) on the
-        // device that served them, through the same chunk pipeline
-        CompletionCall cg = cc;
-        cg.flags = DCMT_PATH_GENERIC;
-        bool any = false;
-        for (Lane& l : call.lanes) {
-            const int n_lane = l.f_end - l.f_begin;
-            for (int i = 0; i < n_lane;) {
-                if (!l.h_flags[i]) { ++i; continue; }
-                int e = i;
-                while (e < n_lane && l.h_flags[e]) ++e;
-                if ((rc = call.use(l))) return rc;
-                const int hc2 = host_chunk_frames(rows, cols, e - i);
+    if (fused && (flags == DCMT_PATH_AUTO || flags == DCMT_PATH_RANK)) {
+        // frames the pass did not serve (not strict q8; dictionary too small) are redone one level down -- strict-q8
+        // kernels -> dictionary (rank_f32.cu) -> generic pipeline -- in runs of consecutive frames, on the device that
+        // served them, through the same chunk pipeline
+        for (int level = flags == DCMT_PATH_AUTO ? DCMT_PATH_RANK : DCMT_PATH_GENERIC;; level = DCMT_PATH_GENERIC) {
+            CompletionCall cg = cc;
+            cg.flags = level;
+            const bool lf = level == DCMT_PATH_RANK;
+            bool any = false;
+            // the runs are fixed before anything is enqueued: the rank pass overwrites the flags it reads
+            struct Run { Lane* l; int f, e; };
+            std::vector<Run> runs;
+            for (Lane& l : call.lanes) {
+                const int n_lane = l.f_end - l.f_begin;
+                for (int i = 0; i < n_lane;) {
+                    if (!l.h_flags[i]) { ++i; continue; }
+                    int e = i;
+                    while (e < n_lane && l.h_flags[e]) ++e;
+                    runs.push_back(Run{&l, l.f_begin + i, l.f_begin + e});
+                    i = e;
+                }
+            }
+            for (const Run& r : runs) {
+                if ((rc = call.use(*r.l))) return rc;
+                const int hc2 = host_chunk_frames(rows, cols, r.e - r.f);
                 const size_t bytes2 = 2 * carve_bytes(fpix * hc2, sizeof(float)) + (guided ? carve_bytes(fpix * hc2, sizeof(int32_t)) : 0) +
                                       carve_bytes((size_t)hc2 * DCMT_STATS_STRIDE, sizeof(int32_t)) + carve_bytes((size_t)hc2, sizeof(int32_t)) +
-                                      completion_ws_bytes(rows, cols, hc2, bilateral, false);
-                for (int f = l.f_begin + i; f < l.f_begin + e; f += hc2)
-                    if ((rc = do_chunk(l, f, std::min(hc2, l.f_begin + e - f), cg, false, hc2, bytes2))) return rc;
+                                      completion_ws_bytes(rows, cols, hc2, bilateral, lf, false, lf);
+                for (int f = r.f; f < r.e; f += hc2)
+                    if ((rc = do_chunk(*r.l, f, std::min(hc2, r.e - f), cg, lf, hc2, bytes2))) return rc;
                 any = true;
-                i = e;
             }
+            if (any && (rc = call.finish())) return rc;
+            if (level == DCMT_PATH_GENERIC || !any) break;
         }
-        if (any && (rc = call.finish())) return rc;
     }
     return DCMT_OK;
 }
@@ -725,7 +780,7 @@ int validate_completion_u16(const uint16_t* sparse, float* dense, int rows, int 
                             int blur_type, int flags, Geometry* gi, Geometry* go) {
     if (!sparse || !dense) return fail(DCMT_E_BADARG, "null image pointer");
     if (blur_type < DCMT_BLUR_NONE || blur_type > DCMT_BLUR_BILATERAL) return fail(DCMT_E_BADARG, "blur_type %d", blur_type);
-    if (flags < DCMT_PATH_AUTO || flags > DCMT_PATH_FUSED) return fail(DCMT_E_BADARG, "flags %d", flags);
+    if (flags < DCMT_PATH_AUTO || flags > DCMT_PATH_RANK) return fail(DCMT_E_BADARG, "flags %d", flags);
     int rc = check_geometry(rows, cols, in_pitch_bytes, in_frame_stride_bytes, n_frames, gi, sizeof(uint16_t));
     if (rc) return rc;
     if ((rc = check_geometry(rows, cols, out_pitch_bytes, out_frame_stride_bytes, n_frames, go, sizeof(float)))) return rc;

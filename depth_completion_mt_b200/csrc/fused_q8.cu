@@ -22,6 +22,7 @@
 
 #include "median_net.cuh"
 #include "median_rows.cuh"
+#include "rank_f32.cuh"
 
 namespace dcmt {
 namespace {
@@ -149,6 +150,7 @@ struct FrontArgs {
     ColMap m_load, m_pass, m_core;  // region (RQ quads), computed quads (RQ - 1), core quads (tw / 8)
     ItemsDesc i_half;               // half-quad columns of the computed quads: 2 (RQ - 1) per row of items
     long long* prof;              // optional: 16 clock64() stamps per CTA (debugging aid)
+    int codes;                    // in16 holds CODES (the dictionary encoding of rank_f32.cu: already e), not KITTI uint16
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -458,7 +460,7 @@ __device__ __forceinline__ uint32_t encode_u16_pair(uint32_t w) {
 // pass 0: load, validate, invert, encode (:55-67) into plane A; cells outside the image are zeroed in BOTH planes.
 // Sweeps go in batches of three so that up to six 16-byte global loads per thread are in flight before the first
 // one is consumed.  kIn16: KITTI uint16 input (one 16-byte load per quad, no validation needed).
-template <bool kIn16, bool kValidate>
+template <bool kIn16, bool kValidate, bool kCodes = false>
 __device__ __forceinline__ void front_load(const FrontArgs& a, const void* in0v, uint32_t* A, uint32_t* B, const Tile& t, int gx0,
                                            float& bad) {
     // in0 points at region cell (0, 0) of the frame (possibly outside the buffer: only in-image cells are read)
@@ -508,7 +510,9 @@ __device__ __forceinline__ void front_load(const FrontArgs& a, const void* in0v,
             }
             uint4 o;
             if (vec) {
-                if (kIn16) {
+                if (kCodes) {
+                    o = h[u];
+                } else if (kIn16) {
                     o = make_uint4(encode_u16_pair(h[u].x), encode_u16_pair(h[u].y), encode_u16_pair(h[u].z), encode_u16_pair(h[u].w));
                 } else {
                     o.x = encode_pair<kValidate>(f0[u].x, f0[u].y, bad);
@@ -522,7 +526,8 @@ __device__ __forceinline__ void front_load(const FrontArgs& a, const void* in0v,
                 for (int j = 0; j < 8; ++j) {
                     e[j] = 0u;
                     if (gx + j < a.cols) {
-                        if (kIn16) e[j] = encode_u16_pair((uint32_t)__ldg(in0h + (rr[u] * pitch + q * 8 + j))) & 0xffffu;
+                        if (kCodes) e[j] = (uint32_t)__ldg(in0h + (rr[u] * pitch + q * 8 + j));
+                        else if (kIn16) e[j] = encode_u16_pair((uint32_t)__ldg(in0h + (rr[u] * pitch + q * 8 + j))) & 0xffffu;
                         else e[j] = encode_bits<kValidate>(__ldg(in0 + (rr[u] * pitch + q * 8 + j)), bad) & 0xffffu;
                     }
                 }
@@ -557,7 +562,8 @@ __global__ void __launch_bounds__(QT, DCMT_FRONT_CTAS) k_q8_front(FrontArgs a) {
 
     DCMT_STAMP(a, 0);
     float bad = 0.0f;
-    if (a.in16) front_load<true, false>(a, a.in16 + origin, A, B, t, gx0, bad);  // uint16 input is q8 by construction
+    if (a.in16 && a.codes) front_load<true, false, true>(a, a.in16 + origin, A, B, t, gx0, bad);  // dictionary codes (rank_f32.cu)
+    else if (a.in16) front_load<true, false>(a, a.in16 + origin, A, B, t, gx0, bad);  // uint16 input is q8 by construction
     else if (a.validate) front_load<false, true>(a, a.in + origin, A, B, t, gx0, bad);
     else front_load<false, false>(a, a.in + origin, A, B, t, gx0, bad);
     if (__syncthreads_or(bad != 0.0f)) {  // not strict q8: this frame is redone by the generic pipeline
@@ -870,7 +876,8 @@ __global__ void __launch_bounds__(GT, kPerLabel ? DCMT_GUIDED_CTAS : 2) k_q8_gui
     const ptrdiff_t origin = (ptrdiff_t)frame * (ptrdiff_t)a.in_fstride + ((ptrdiff_t)gy0 * (ptrdiff_t)a.in_pitch + gx0);
 
     float bad = 0.0f;
-    if (a.in16) front_load<true, false>(a, a.in16 + origin, A, B, t, gx0, bad);
+    if (a.in16 && a.codes) front_load<true, false, true>(a, a.in16 + origin, A, B, t, gx0, bad);
+    else if (a.in16) front_load<true, false>(a, a.in16 + origin, A, B, t, gx0, bad);
     else if (a.validate) front_load<false, true>(a, a.in + origin, A, B, t, gx0, bad);
     else front_load<false, false>(a, a.in + origin, A, B, t, gx0, bad);
     // labels of the region (cells outside the image are never looked at: their image value is absent)
@@ -1092,6 +1099,8 @@ struct TailArgs {
     ItemsDesc i_load, i_vert, i_scan, i_scanw, i_med, i_gauss;  // row lengths RQ, pitchw, SQ, 4 SQ, MI, NP
     ItemsDesc i_medr;  // row length tw / 2 + 2: one item = one word column x med_len rows (shared-work median)
     int med_len, med_segs;
+    uint32_t e_hundred;  // code of the constant 100.0: E_HUNDRED (strict q8), kRankHundred (dictionary codes)
+    const float* lut;    // dictionary of the frames (kRank): lut[slot * kRankMaxValid + code - kRankFirstCode]
     long long* prof;  // optional: 16 clock64() stamps per CTA (debugging aid)
 };
 
@@ -1193,6 +1202,7 @@ __device__ __forceinline__ void median_step(MedianRun& m, const PackedOps& ops, 
     if (two) o[pitchw] = rank5_of_6_5(ops, qq, m.E);
 }
 
+template <bool kRank>
 __global__ void __launch_bounds__(QTT, DCMT_TAIL_CTAS) k_q8_tail(TailArgs a, const __grid_constant__ TensorMap3D tmap) {
     DCMT_DYN_SMEM(uint32_t, smem);
     const int th = a.th, tw = a.tw, rows = a.rows, cols = a.cols;
@@ -1262,11 +1272,11 @@ __global__ void __launch_bounds__(QTT, DCMT_TAIL_CTAS) k_q8_tail(TailArgs a, con
         const int first = empty ? rows - 1 : (int)(kf >> 16), last = empty ? 0 : (int)(kl >> 16);
         uint16_t* p = Ah + c;
         if (!bottom) {
-            const uint16_t nv = empty ? (uint16_t)E_HUNDRED : (uint16_t)(kf & 0xffffu);
+            const uint16_t nv = empty ? (uint16_t)a.e_hundred : (uint16_t)(kf & 0xffffu);
             const int r1 = min(RH - 1, first - gy0);
             for (int r = max(0, -gy0); r <= r1; ++r) p[(size_t)r * pitchw * 2] = nv;
         } else {
-            const uint16_t mv = empty ? (uint16_t)E_HUNDRED : (uint16_t)(kl & 0xffffu);
+            const uint16_t mv = empty ? (uint16_t)a.e_hundred : (uint16_t)(kl & 0xffffu);
             const int r1 = min(RH - 1, rows - 1 - gy0);
             for (int r = max(max(0, -gy0), max(last, first + 1) - gy0); r <= r1; ++r) p[(size_t)r * pitchw * 2] = mv;
         }
@@ -1423,7 +1433,7 @@ __global__ void __launch_bounds__(QTT, DCMT_TAIL_CTAS) k_q8_tail(TailArgs a, con
                     const int c_lo = max(gx - half, 0), c_hi = min(gx + half, cols - 1);
                     for (int c = c_lo + lane; c <= c_hi; c += 32) {
                         const uint32_t kf = __ldg(a.col_first + (size_t)slot * a.mid_pitch + c), kl = __ldg(a.col_last + (size_t)slot * a.mid_pitch + c);
-                        if (kf == 0xffffffffu) { m = max(m, E_HUNDRED); continue; }  // empty column: 100 everywhere (:110)
+                        if (kf == 0xffffffffu) { m = max(m, a.e_hundred); continue; }  // empty column: 100 everywhere (:110)
                         const int first = (int)(kf >> 16), last = (int)(kl >> 16);
                         if (r_lo <= first) m = max(m, kf & 0xffffu);   // rows <= first hold value(first)
                         if (r_hi >= last) m = max(m, kl & 0xffffu);    // rows >= last hold value(last)
@@ -1586,6 +1596,66 @@ __global__ void __launch_bounds__(QTT, DCMT_TAIL_CTAS) k_q8_tail(TailArgs a, con
         __syncthreads();
     }
     DCMT_STAMP(a, 8);
+    if (kRank) {
+        // ---- A9 + A10 on dictionary codes: decode with the frame's LUT (the inverted float each code stands for; kRankHundred
+        //      = 100.0), 5x5 Gaussian in float32 -- the separable symmetric form OpenCV's float path uses, kernel
+        //      [.0625 .25 .375 .25 .0625], rows then columns (:176-179) -- masked copy (:181-188: every pixel is valid here),
+        //      final inversion (:191-202).  One item = 4 pixels x 4 rows, as below.
+        const float* lut = a.lut + (size_t)slot * kRankMaxValid;
+        const uint32_t eh = a.e_hundred;
+        auto dec = [&](uint32_t e) -> float { return e == eh ? kMaxDepth : __ldg(lut + ((int)e - kRankFirstCode)); };
+        auto inv_out = [&](float d) -> float { return d >= 0.1f ? __fsub_rn(kMaxDepth, d) : d; };
+        const int NGR = (th + 3) / 4;
+        for (Items i(a.i_gauss); i.r < NGR; i.next()) {
+            const int cy0 = i.r * 4, gx = x0 + i.q * 4;
+            if (y0 + cy0 >= rows || gx >= cols) continue;
+            const uint32_t* p = B + (TV + cy0) * pitchw + TQ * 4 + 2 * i.q;
+            float* o = out + (size_t)(y0 + cy0) * a.out_pitch + gx;
+            float f[4][4];
+            if (a.blur == 1) {
+                float h[8][4];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {  // input rows cy0-2 .. cy0+5, pixels gx-2 .. gx+5
+                    const uint32_t* q = p + (k - 2) * pitchw;
+                    const uint32_t wa = q[-1], wb = q[0], wc = q[1], wd = q[2];
+                    const float x0f = dec(wa & 0xffffu), x1f = dec(wa >> 16), x2f = dec(wb & 0xffffu), x3f = dec(wb >> 16),
+                                x4f = dec(wc & 0xffffu), x5f = dec(wc >> 16), x6f = dec(wd & 0xffffu), x7f = dec(wd >> 16);
+                    const float xs[8] = {x0f, x1f, x2f, x3f, x4f, x5f, x6f, x7f};
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        h[k][c] = __fadd_rn(__fadd_rn(__fmul_rn(xs[c + 2], 0.375f), __fmul_rn(__fadd_rn(xs[c + 1], xs[c + 3]), 0.25f)),
+                                            __fmul_rn(__fadd_rn(xs[c], xs[c + 4]), 0.0625f));
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        f[j][c] = inv_out(__fadd_rn(__fadd_rn(__fmul_rn(h[j + 2][c], 0.375f), __fmul_rn(__fadd_rn(h[j + 1][c], h[j + 3][c]), 0.25f)),
+                                                    __fmul_rn(__fadd_rn(h[j][c], h[j + 4][c]), 0.0625f)));
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t w0 = p[j * pitchw], w1 = p[j * pitchw + 1];
+                    f[j][0] = inv_out(dec(w0 & 0xffffu));
+                    f[j][1] = inv_out(dec(w0 >> 16));
+                    f[j][2] = inv_out(dec(w1 & 0xffffu));
+                    f[j][3] = inv_out(dec(w1 >> 16));
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (cy0 + j >= th || y0 + cy0 + j >= rows) break;
+                float* oj = o + (size_t)j * a.out_pitch;
+                if (gx + 4 <= cols && a.vec_ok) {
+                    *reinterpret_cast<float4*>(oj) = make_float4(f[j][0], f[j][1], f[j][2], f[j][3]);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        if (gx + c < cols) oj[c] = f[j][c];
+                }
+            }
+        }
+    } else {
     // ---- A9 + A10: 5x5 Gaussian [1 4 6 4 1]^2 / 256 in integer q16 (:176-189), final inversion (:191-202), float32
     //      store.  One item = 4 pixels (two words) x 4 rows: the horizontal [1 4 6 4 1] sums of the 8 rows it touches
     //      come straight from the packed words with 16-bit x 8-bit dot products (IDP.2A), the vertical combination
@@ -1640,6 +1710,7 @@ __global__ void __launch_bounds__(QTT, DCMT_TAIL_CTAS) k_q8_tail(TailArgs a, con
             }
         }
     }
+    }
     DCMT_STAMP(a, 9);
 }
 
@@ -1654,14 +1725,14 @@ __global__ void k_q8_zero_counters(FrameCounters* c, int n) {
     if (i < n) { c[i] = FrameCounters{}; c[i].path = 1; }
 }
 
-__global__ void k_q8_write_stats(const FrameCounters* __restrict__ c, int32_t* __restrict__ stats, int32_t* __restrict__ flags, int n) {
+__global__ void k_q8_write_stats(const FrameCounters* __restrict__ c, int32_t* __restrict__ stats, int32_t* __restrict__ flags, int n, int path_code) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     if (stats) {
         stats[4 * i + 0] = c[i].extra_passes + 1;
         stats[4 * i + 1] = c[i].holes_after_first_fill;
         stats[4 * i + 2] = c[i].holes_after_extrapolation;
-        stats[4 * i + 3] = c[i].needs_generic ? -1 : 1;
+        stats[4 * i + 3] = c[i].needs_generic ? -1 : path_code;
     }
     if (flags) flags[i] = c[i].needs_generic;
 }
@@ -1734,7 +1805,9 @@ cudaError_t q8_configure() {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_q8_guided_front<false, GTW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_q8_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    e = cudaFuncSetAttribute(k_q8_tail<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_q8_tail<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 }
 
 cudaError_t q8_run_front(const Q8Plan& plan, const float* in, const uint16_t* in16, size_t in_pitch, size_t in_fstride, int n_frames,
@@ -1753,7 +1826,7 @@ cudaError_t q8_run_front(const Q8Plan& plan, const float* in, const uint16_t* in
         p.th = (p.rows + ny - 1) / ny;
     }
     const size_t ncol = (size_t)p.mid_pitch * n_frames;
-    DCMT_LAUNCH(k_q8_zero_counters, dim3((n_frames + 127) / 128), dim3(128), 0, st, p.ctr, n_frames);
+    if (!p.counters_ready) DCMT_LAUNCH(k_q8_zero_counters, dim3((n_frames + 127) / 128), dim3(128), 0, st, p.ctr, n_frames);
     DCMT_LAUNCH(k_q8_init_cols, dim3((unsigned)((ncol + 255) / 256)), dim3(256), 0, st, p.col_first, p.col_last, ncol);
     // 16-byte vector loads need 16-byte aligned rows: 4 floats or 8 uint16 per unit
     const size_t unit = in16 ? 8 : 4;
@@ -1762,6 +1835,7 @@ cudaError_t q8_run_front(const Q8Plan& plan, const float* in, const uint16_t* in
                 p.ctr, p.rows, p.cols, p.th, p.tw, (int)(in_pitch % unit == 0 && in_fstride % unit == 0 && (base & 15) == 0), validate,
                 make_colmap(p.tw / 8 + FLQ + FRQ, QT), make_colmap(p.tw / 8 + FLQ + FRQ - 1, QT), make_colmap(p.tw / 8, QT),
                 make_items(2 * (p.tw / 8 + FLQ + FRQ - 1), QT), p.prof_front};
+    a.codes = p.codes_in;
     const dim3 grid((p.cols + p.tw - 1) / p.tw, (p.rows + p.th - 1) / p.th, n_frames);
     if (p.cols % 8 != 0) DCMT_LAUNCH(k_q8_front<true>, grid, dim3(QT), q8_front_smem(p.th, p.tw), st, a);
     else DCMT_LAUNCH(k_q8_front<false>, grid, dim3(QT), q8_front_smem(p.th, p.tw), st, a);
@@ -1792,7 +1866,7 @@ cudaError_t q8_run_guided_front(const Q8Plan& plan, const float* in, const uint1
     Q8Plan p = plan;
     p.th = q8_guided_tile_h(p.rows, p.th, p.tw);  // its own tiles: the kernels meet in the global intermediate plane
     const size_t ncol = (size_t)p.mid_pitch * n_frames;
-    DCMT_LAUNCH(k_q8_zero_counters, dim3((n_frames + 127) / 128), dim3(128), 0, st, p.ctr, n_frames);
+    if (!p.counters_ready) DCMT_LAUNCH(k_q8_zero_counters, dim3((n_frames + 127) / 128), dim3(128), 0, st, p.ctr, n_frames);
     DCMT_LAUNCH(k_q8_init_cols, dim3((unsigned)((ncol + 255) / 256)), dim3(256), 0, st, p.col_first, p.col_last, ncol);
     const size_t unit = in16 ? 8 : 4;
     const uintptr_t base = in16 ? reinterpret_cast<uintptr_t>(in16) : reinterpret_cast<uintptr_t>(in);
@@ -1805,11 +1879,13 @@ cudaError_t q8_run_guided_front(const Q8Plan& plan, const float* in, const uint1
     // column maps / magic reciprocals per thread count: load by region quads; items of the guided stage and of the vertical
     // pass by tw / 2 + 4 words (m_core), of the final pass by core quads (m_pass), label plane by region words (i_half)
     auto args = [&](int nt) {
-        return GuidedArgs{FrontArgs{in, in16, in_pitch, in_fstride, p.mid, (size_t)p.mid_pitch, (size_t)p.mid_pitch * p.rows, p.col_first,
+        GuidedArgs g = GuidedArgs{FrontArgs{in, in16, in_pitch, in_fstride, p.mid, (size_t)p.mid_pitch, (size_t)p.mid_pitch * p.rows, p.col_first,
                                     p.col_last, p.ctr, p.rows, p.cols, p.th, p.tw,
                                     (int)(in_pitch % unit == 0 && in_fstride % unit == 0 && (base & 15) == 0), validate, make_colmap(RQ, nt),
                                     make_colmap(p.tw / 8, nt), make_colmap(p.tw / 2 + 4, nt), make_items(RQ * 4, nt), nullptr},
                           labels, n_clusters, guided_per_label, tile_flags};
+        g.f.codes = p.codes_in;
+        return g;
     };
     if (guided_per_label) DCMT_LAUNCH((k_q8_guided_front<true, GTL>), grid, dim3(GTL), q8_guided_smem(p.th, p.tw), st, args(GTL));
     // tiles the per-label kernel could not take (more distinct labels than its table holds) -- or all of them
@@ -1836,14 +1912,20 @@ cudaError_t q8_run_tail(const Q8Plan& p, float* out, size_t out_pitch, size_t ou
     TailArgs a{p.mid, (size_t)p.mid_pitch, (size_t)p.mid_pitch * p.rows, p.col_first, p.col_last, p.ctr, out, out_pitch,
                out_fstride, p.rows, p.cols, p.th, p.tw, blur, vec2, 1, use_tma,
                make_items(RQ, QTT), make_items(RQ * 4, QTT), make_items(SQ, QTT), make_items(SQ * 4, QTT), make_items(MI, QTT),
-               make_items(NP, QTT), make_items(NW, QTT), med_len, med_segs, p.prof_tail};
+               make_items(NP, QTT), make_items(NW, QTT), med_len, med_segs, p.lut ? kRankHundred : E_HUNDRED, p.lut, p.prof_tail};
     const dim3 grid((p.cols + p.tw - 1) / p.tw, (p.rows + p.th - 1) / p.th, n_frames);
-    DCMT_LAUNCH(k_q8_tail, grid, dim3(QTT), q8_tail_smem(p.th, p.tw), st, a, tmap);
+    if (p.lut) DCMT_LAUNCH(k_q8_tail<true>, grid, dim3(QTT), q8_tail_smem(p.th, p.tw), st, a, tmap);
+    else DCMT_LAUNCH(k_q8_tail<false>, grid, dim3(QTT), q8_tail_smem(p.th, p.tw), st, a, tmap);
+    return cudaGetLastError();
+}
+
+cudaError_t q8_zero_counters(const Q8Plan& p, int n_frames, cudaStream_t st) {
+    DCMT_LAUNCH(k_q8_zero_counters, dim3((n_frames + 127) / 128), dim3(128), 0, st, p.ctr, n_frames);
     return cudaGetLastError();
 }
 
 cudaError_t q8_write_stats(const Q8Plan& p, int32_t* stats, int32_t* flags, int n_frames, cudaStream_t st) {
-    DCMT_LAUNCH(k_q8_write_stats, dim3((n_frames + 127) / 128), dim3(128), 0, st, p.ctr, stats, flags, n_frames);
+    DCMT_LAUNCH(k_q8_write_stats, dim3((n_frames + 127) / 128), dim3(128), 0, st, p.ctr, stats, flags, n_frames, p.lut ? 2 : 1);
     return cudaGetLastError();
 }
 

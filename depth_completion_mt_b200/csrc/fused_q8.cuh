@@ -19,6 +19,12 @@ struct Q8Plan {
     float* w2;
     long long* prof_front;  // optional debugging aid: 16 clock64() stamps per CTA of k_q8_front / k_q8_tail
     long long* prof_tail;
+    // float32 frames through the dictionary of rank_f32.cu: the front reads CODES from its uint16 input, the tail decodes
+    // with `lut` (max_frames x kRankMaxValid floats) and blurs in float32; counters were zeroed (and possibly flagged)
+    // before the front runs
+    int codes_in;
+    int counters_ready;
+    const float* lut;
 };
 
 // fused path applies to frames of at least this size (smaller ones use the generic pipeline)
@@ -46,6 +52,8 @@ cudaError_t q8_convert_u16(const uint16_t* in, size_t in_pitch, size_t in_fstrid
 // A5..A10: plan.mid -> out (float32), blur in {none, gaussian}; then the fix-up kernel
 cudaError_t q8_run_tail(const Q8Plan& p, float* out, size_t out_pitch, size_t out_fstride, int n_frames, int blur,
                         cudaStream_t st);
+// zero the per-frame counters (what q8_run_front does itself unless plan.counters_ready)
+cudaError_t q8_zero_counters(const Q8Plan& p, int n_frames, cudaStream_t st);
 // counters -> stats[4*n] (optional) and flags[n] (1 = frame must be redone by the generic pipeline)
 cudaError_t q8_write_stats(const Q8Plan& p, int32_t* stats, int32_t* flags, int n_frames, cudaStream_t st);
 // test aid: decode a uint16 plane (inverted space) into float

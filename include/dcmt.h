@@ -72,7 +72,15 @@ enum {
     /* fused kernels without validation, fully asynchronous (CUDA-graph capturable): the CALLER guarantees strict q8
      * input (e.g. KITTI uint16 PNG / 256, main.cpp:75-82); other input gives undefined output.  Shapes / blur
      * types the fused kernels do not serve (bilateral, frames under 32x32) still use the generic pipeline. */
-    DCMT_PATH_FUSED = 2
+    DCMT_PATH_FUSED = 2,
+    /* float32 frames that are NOT strict q8 -- e.g. the cv::normalize'd depth the stereo program completes
+     * (main_sl.cpp:522-540) -- on the same fused kernels: the inverted values of a frame's valid pixels are sorted into a
+     * per-frame dictionary and replaced by their ranks (every stage between the inversion and the blur only selects among
+     * its inputs, so any monotone code gives the same selections), and the tail decodes before the float32 Gaussian.
+     * Bit-identical to the reference with blur none, within 1e-4 with the Gaussian.  Frames with more than 32768 valid
+     * pixels or a NaN are redone by the generic pipeline (one read-back, like DCMT_PATH_AUTO).  DCMT_PATH_AUTO tries the
+     * strict-q8 kernels first, then this, then the generic pipeline. */
+    DCMT_PATH_RANK = 3
 };
 
 /* per-frame statistics, DCMT_STATS_STRIDE int32 per frame (device memory for the async entry
@@ -80,7 +88,7 @@ enum {
  *   [0] passes the reference's `while` loop executes (img_completion.cpp:146-166), >= 1
  *   [1] holes counted by the first loop pass (= holes left after the first 31x31 fill)
  *   [2] holes counted by the first 31x31 fill (= holes left after column extrapolation)
- *   [3] path that produced the frame: 0 generic, 1 fused strict-q8 */
+ *   [3] path that produced the frame: 0 generic, 1 fused strict-q8, 2 fused through the float32 dictionary (DCMT_PATH_RANK) */
 #define DCMT_STATS_STRIDE 4
 
 DCMT_API int dcmt_version(void);
