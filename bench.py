@@ -34,7 +34,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-BYTES_PER_PX = {"lidar_only": 8, "guided": 12, "stereo": 10}
+BYTES_PER_PX = {"lidar_only": 8, "guided": 12, "stereo": 10, "stereo_chain": 14}  # SURVEY.md 8d (stereo_chain: a2 + a4-a9, 14 B/px)
 METRIC = "frames/sec @1216x352 sparse depth"
 UNIQUE = 64
 
@@ -50,9 +50,10 @@ def parse_args():
     ap.add_argument("--rows", type=int, default=352)
     ap.add_argument("--cols", type=int, default=1216)
     ap.add_argument("--density", type=float, default=0.05)
-    ap.add_argument("--path", default="auto", choices=["auto", "generic", "fused"])
-    ap.add_argument("--input", default="f32", choices=["f32", "u16"],
-                    help="lidar_only: float32 metres (the reference's cv::Mat, default) or KITTI uint16 = metres * 256 (main.cpp:75-82)")
+    ap.add_argument("--path", default="auto", choices=["auto", "generic", "fused", "rank"])
+    ap.add_argument("--input", default="f32", choices=["f32", "u16", "float"],
+                    help="lidar_only / guided: float32 metres on the KITTI q8 grid (the reference's cv::Mat, default), KITTI uint16 = metres * 256 "
+                         "(main.cpp:75-82), or `float`: arbitrary float32 depths (what DC_stereo_lidar completes after cv::normalize; use --path rank)")
     ap.add_argument("--labels", default="grid", choices=["grid", "slic"],
                     help="guided workload: jittered grid labels (SURVEY 8d) or real SLIC output of synthetic Lab images (step 18, nc 50)")
     ap.add_argument("--host-input", default="pinned", choices=["pinned", "wc"],
@@ -113,6 +114,10 @@ def _ref_inputs(f):
         elif _W["workload"] == "guided":
             lab, k = synth.superpixel_labels(f, rows, cols)
             c[f] = (synth.sparse_depth(f, rows, cols, _W["density"]), lab, k)
+        elif _W["workload"] == "stereo_chain":
+            lab, k = synth.superpixel_labels(f, rows, cols, 65)
+            _, left, right = synth.stereo_pair(f, rows, cols)
+            c[f] = (synth.velodyne_cloud(f, 120000), lab, k, left, right)
         else:
             c[f] = synth.stereo_pair(f, rows, cols)
     return c[f]
@@ -127,6 +132,18 @@ def _ref_task(f):
             out = impl.interpolate_with_superpixels(args[1], args[0], n_clusters=args[2])
         else:
             out = impl.interpolate_with_superpixels(args[0], args[1], args[2])
+    elif _W["workload"] == "stereo_chain":
+        synth = _W["synth"]
+        pts, lab, k, left, right = args
+        if _W["kind"] == "ref":
+            nrm = impl.lidar_project(pts, synth.KITTI_T_VELO_TO_CAM, synth.KITTI_P_RECT_02, _W["rows"], _W["cols"])[1]
+            dense = impl.interpolate_with_superpixels(lab, nrm, n_clusters=k)
+        else:
+            from oracle import c_oracle as co
+
+            nrm = co.lidar_project(pts, synth.KITTI_T_VELO_TO_CAM, synth.KITTI_P_RECT_02, _W["rows"], _W["cols"])[1]
+            dense = impl.interpolate_with_superpixels(nrm, lab, k)
+        out = impl.stereo_refine(dense, left, right)
     else:
         out = impl.stereo_refine(*args)
     return float(out[0, 0])
@@ -153,6 +170,8 @@ def run_reference(args, quiet=False):
     per_step = max(1, args.ref_frames_per_core) * cores
     if args.workload == "guided":
         per_step = cores  # ~2 s per frame per core
+    if args.workload == "stereo_chain":
+        per_step = 2 * cores  # ~100 superpixels: about 0.25 s per frame per core
     ctx = mp.get_context("fork")
     with ctx.Pool(cores, initializer=_ref_worker_init, initargs=(args.workload, args.rows, args.cols, args.density)) as pool:
         kind = pool.apply(_kind)
@@ -199,7 +218,9 @@ def _kind():
 def workload_config(args, frames_per_step_per_gpu):
     names = {"lidar_only": "DC_lidar_only img_completion, fused dilate/erode/fill/blur (BASELINE configs[1])",
              "guided": "DC_lidar_camera interpolate_with_superpixels (BASELINE configs[2])",
-             "stereo": "DC_stereo_lidar disparity refinement (BASELINE configs[3])"}
+             "stereo": "DC_stereo_lidar disparity refinement (BASELINE configs[3])",
+             "stereo_chain": "DC_stereo_lidar chain: LiDAR projection + cv::normalize -> interpolate_with_superpixels on the normalised floats -> "
+                             "disparity refinement (main_sl.cpp:478-540,1162-1253; BASELINE configs[3])"}
     return {"workload": names[args.workload], "rows": args.rows, "cols": args.cols, "valid_density": args.density,
             "frames_per_gpu_per_step": frames_per_step_per_gpu, "global_batch": frames_per_step_per_gpu * max(1, args.gpus),
             "unique_frames": UNIQUE, "blur": "gaussian", "labels": getattr(args, "labels", "grid") if args.workload == "guided" else None, "input": getattr(args, "input", "f32") if args.workload == "lidar_only" else "f32", "parallelism": f"frame-sharded dp{max(1, args.gpus)}, no collective on the hot path",
@@ -327,16 +348,21 @@ def run_ours(args):
     # ---- synthetic inputs, device resident before timing
     holder = {}
     if args.workload == "lidar_only":
-        uniq16 = np.stack([synth.sparse_depth_q8(f, rows, cols, args.density) for f in range(UNIQUE)])
-        d_in16 = torch.from_numpy(uniq16).to(dev).repeat(reps, 1, 1)[:n].contiguous()
-        d_in = d_in16 if args.input == "u16" else (d_in16.to(torch.float32) / 256.0).contiguous()  # exact: convertTo(CV_32F, 1/256)
+        if args.input == "float":
+            d_in16 = None
+            uniqf = np.stack([synth.sparse_depth_float(f, rows, cols, args.density) for f in range(UNIQUE)])
+            d_in = torch.from_numpy(uniqf).to(dev).repeat(reps, 1, 1)[:n].contiguous()
+        else:
+            uniq16 = np.stack([synth.sparse_depth_q8(f, rows, cols, args.density) for f in range(UNIQUE)])
+            d_in16 = torch.from_numpy(uniq16).to(dev).repeat(reps, 1, 1)[:n].contiguous()
+            d_in = d_in16 if args.input == "u16" else (d_in16.to(torch.float32) / 256.0).contiguous()  # exact: convertTo(CV_32F, 1/256)
         d_out = torch.empty((n, rows, cols), dtype=torch.float32, device=dev)
 
         def step():
             api.img_completion(d_in, False, "gaussian", path=args.path, out=d_out, lib=lib)
         h2d, d2h = n * fpix * (2 if args.input == "u16" else 4), n * fpix * 4
     elif args.workload == "guided":
-        uniq = np.stack([synth.sparse_depth(f, rows, cols, args.density) for f in range(UNIQUE)])
+        uniq = np.stack([(synth.sparse_depth_float if args.input == "float" else synth.sparse_depth)(f, rows, cols, args.density) for f in range(UNIQUE)])
         if args.labels == "slic":
             k = lib.dcmt_slic_center_count(rows, cols, 18)
             labs = [(api.generate_superpixels(torch.from_numpy(synth.lab_image(f, rows, cols)).to(dev), 18, 50, lib=lib).cpu().numpy(), k)
@@ -349,8 +375,36 @@ def run_ours(args):
         holder = {}
 
         def step():
-            holder["out"] = api.interpolate_with_superpixels(d_lab, d_in, "gaussian", 1, n_clusters=k, lib=lib)
+            holder["out"] = api.interpolate_with_superpixels(d_lab, d_in, "gaussian", 1, n_clusters=k, path=args.path, lib=lib)
         h2d, d2h = n * fpix * 8, n * fpix * 4
+    elif args.workload == "stereo_chain":
+        # what the stereo program really runs per frame (main_sl.cpp:1150 withSuperPixels, :1162-1253): Velodyne cloud ->
+        # projected depth image -> cv::normalize(0, 80) -> superpixel-guided completion of the normalised FLOATS (dictionary
+        # path of the fused kernels) -> disparity refinement against the gray pair.  Labels are an input here (SLIC of the
+        # left image is the f1 row, measured on its own).
+        npts = 120000
+        uniq_n = min(UNIQUE, n)
+        clouds = np.stack([synth.velodyne_cloud(f, npts) for f in range(uniq_n)])
+        reps_c = (n + uniq_n - 1) // uniq_n
+        d_pts = torch.from_numpy(clouds).to(dev).repeat(reps_c, 1, 1)[:n].contiguous()
+        labs = [synth.superpixel_labels(f, rows, cols, 65) for f in range(uniq_n)]  # ~100 superpixels, main_sl.cpp:443
+        k = labs[0][1]
+        d_lab = torch.from_numpy(np.stack([l[0] for l in labs])).to(dev).repeat(reps_c, 1, 1)[:n].contiguous()
+        trip = [synth.stereo_pair(f, rows, cols) for f in range(uniq_n)]
+        d_l, d_r = (torch.from_numpy(np.stack([t[i] for t in trip])).to(dev).repeat(reps_c, 1, 1)[:n].contiguous() for i in (1, 2))
+        prm = api.stereo_params(lib=lib)
+        holder = {}
+        CH = 128  # clouds per projection call: bounds the 8-byte key plane per cloud (3.4 MB at 352x1216)
+
+        def step():
+            outs = []
+            for c0 in range(0, n, CH):
+                _, nrm, _ = api.lidar_project_batch(d_pts[c0:c0 + CH], None, synth.KITTI_T_VELO_TO_CAM, synth.KITTI_P_RECT_02, rows, cols, lib=lib)
+                dense = api.interpolate_with_superpixels(d_lab[c0:c0 + CH], nrm, "gaussian", 1, n_clusters=k, path="rank", lib=lib)
+                outs.append(api.stereo_refine(dense, d_l[c0:c0 + CH], d_r[c0:c0 + CH], prm, lib=lib))
+            holder["out"] = torch.cat(outs) if len(outs) > 1 else outs[0]
+        h2d, d2h = n * (npts * 16 + fpix * 6), n * fpix * 4
+        args.no_e2e = True  # the chain has no single host entry point: its stages are the three calls above
     else:
         trip = [synth.stereo_pair(f, rows, cols) for f in range(UNIQUE)]
         d_ig, d_l, d_r = (torch.from_numpy(np.stack([t[i] for t in trip])).to(dev).repeat(reps, 1, 1)[:n].contiguous() for i in range(3))
@@ -392,7 +446,7 @@ def run_ours(args):
     replicas_equal = all(bool(torch.equal(out_t[UNIQUE * k_:UNIQUE * (k_ + 1)], out_t[:UNIQUE][: max(0, min(UNIQUE, n - UNIQUE * k_))]))
                          for k_ in range(1, reps) if n - UNIQUE * k_ > 0)
     golden_ok = None
-    if args.workload == "lidar_only" and (rows, cols, args.density) == (352, 1216, 0.05):
+    if args.workload == "lidar_only" and args.input != "float" and (rows, cols, args.density) == (352, 1216, 0.05):
         golden_ok = True
         for l in open(os.path.join(ROOT, "tests", "golden", "lidar_only_352x1216.sha256")):
             p = l.split()
@@ -424,7 +478,14 @@ def run_ours(args):
     e2e_ms = e2e16_ms = ceil_ms = ceil16_ms = multi_ms = None
     latency = None
     if not args.no_e2e:
-        if args.workload == "lidar_only":
+        if args.workload == "lidar_only" and args.input == "float":
+            h_in = torch.empty((n, rows, cols), dtype=torch.float32, pin_memory=True)
+            h_in.copy_(d_in)
+            h_out = torch.empty((n, rows, cols), dtype=torch.float32, pin_memory=True)
+            np_in, np_out = h_in.numpy(), h_out.numpy()
+            e2e_ms = timed_host(lambda: api.img_completion(np_in, False, "gaussian", path=args.path, out=np_out, lib=lib))
+            ceil_ms = timed_host(lambda: lib.check(lib.dcmt_debug_host_copy_f32(np_in.ctypes.data, np_out.ctypes.data, rows, cols, n, None, 0)))
+        elif args.workload == "lidar_only":
             if args.host_input == "wc":
                 hb = api.HostBuffer((n, rows, cols), np.float32, write_combined=True, lib=lib)
                 holder["hb"] = hb
@@ -482,7 +543,7 @@ def run_ours(args):
             np_in, np_lab, np_out = h_in.numpy(), h_lab.numpy(), h_out.numpy()
 
             def host_step():
-                holder["h"] = api.interpolate_with_superpixels(np_lab, np_in, "gaussian", 1, n_clusters=k, out=np_out, lib=lib)
+                holder["h"] = api.interpolate_with_superpixels(np_lab, np_in, "gaussian", 1, n_clusters=k, path=args.path, out=np_out, lib=lib)
             e2e_ms = timed_host(host_step)
         else:
             hs = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in (d_ig, d_l, d_r)]
@@ -498,7 +559,7 @@ def run_ours(args):
 
     # ---- per-kernel split of the fused path (CUDA events around each kernel, a few extra untimed steps)
     kernels = None
-    if args.workload == "lidar_only":
+    if args.workload == "lidar_only" and args.input != "float":
         lib.check(lib.dcmt_profile_begin())
         for _ in range(3):
             step()
@@ -564,7 +625,7 @@ def run_ours(args):
     }
     if not args.no_e2e:
         api_note = "dcmt_*_host via depth_completion_mt_b200.api with numpy views of pinned host buffers"
-        if args.workload == "lidar_only":
+        if args.workload == "lidar_only" and args.input != "float":
             # headline: the reference program's own input format -- the uint16 payload of the KITTI depth PNG (main.cpp:75-82);
             # the call stands for convertTo(CV_32F, 1/256) + img_completion (main.cpp:79,93)
             line["e2e"] = {"value": fps_e2e16, "unit": "frames/s", "h2d_bytes_per_step": int(n * fpix * 2), "d2h_bytes_per_step": int(d2h),
@@ -584,7 +645,7 @@ def run_ours(args):
                 line["latency"] = latency
         else:
             line["e2e"] = {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "api": api_note,
-                           "host_binding_rank0": numa}
+                           "copy_ceiling": fps_ceil, "host_binding_rank0": numa}
     if world == 1 and not args.no_cpu_baseline:
         try:
             cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "3", "--warmup", "1", "--workload", args.workload,

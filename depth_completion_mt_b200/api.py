@@ -420,6 +420,28 @@ def lidar_project(points, T, P, rows: int, cols: int, norm=(0.0, 80.0), *, retur
     return (proj, nrm, int(cnt[0])) if return_count else (proj, nrm)
 
 
+def lidar_project_batch(points, counts, T, P, rows: int, cols: int, norm=(0.0, 80.0), *, stream=None, lib: _lib.Library | None = None):
+    """main_sl.cpp:478-523 for a batch of clouds in four launches.  ``points``: CUDA tensor (n_clouds, max_points, 4) float32;
+    ``counts``: CUDA int32 (n_clouds,) points per cloud, or None (max_points each).  Returns (projected, normalized, n_projected):
+    (n_clouds, rows, cols) float32 twice and (n_clouds,) int32."""
+    lib = lib or _lib.load()
+    Tm = np.ascontiguousarray(np.asarray(T, np.float32).reshape(4, 4))
+    Pm = np.ascontiguousarray(np.asarray(P, np.float32).reshape(3, 4))
+    pts = _prep_torch(points, torch.float32, "points")
+    if pts.ndim != 3 or pts.shape[2] != 4:
+        raise ValueError("points must be (n_clouds, max_points, 4)")
+    nc, mp = int(pts.shape[0]), int(pts.shape[1])
+    cn = _prep_torch(counts, torch.int32, "counts") if counts is not None else None
+    proj = torch.empty((nc, rows, cols), dtype=torch.float32, device=pts.device)
+    nrm = torch.empty_like(proj)
+    cnt = torch.zeros(nc, dtype=torch.int32, device=pts.device)
+    with torch.cuda.device(pts.device):
+        lib.check(lib.dcmt_lidar_project_batch_f32(pts.data_ptr() if pts.numel() else None, cn.data_ptr() if cn is not None else None, mp, mp, nc,
+                                                   _np_ptr(Tm), _np_ptr(Pm), rows, cols, proj.data_ptr(), nrm.data_ptr(), float(norm[0]),
+                                                   float(norm[1]), cnt.data_ptr(), _stream_ptr(stream)))
+    return proj, nrm, cnt
+
+
 # ---------------------------------------------------------------------------------------------- SLIC (8f #1)
 def generate_superpixels(lab_image, step, nc: int, *, iterations: int = 10, return_centers: bool = False, stream=None,
                          lib: _lib.Library | None = None):

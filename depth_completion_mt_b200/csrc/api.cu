@@ -1193,6 +1193,31 @@ int dcmt_lidar_project_f32(const float* points, int n_points, const float* T_hos
     return DCMT_OK;
 }
 
+int dcmt_lidar_project_batch_f32(const float* points, const int32_t* n_points_dev_or_null, int max_points, size_t cloud_stride_points,
+                                 int n_clouds, const float* T_host, const float* P_host, int rows, int cols, float* projected,
+                                 float* normalized, float norm_a, float norm_b, int32_t* n_projected, void* cuda_stream) {
+    if ((!points && max_points > 0) || !T_host || !P_host) return fail(DCMT_E_BADARG, "null pointer");
+    if (max_points < 0 || n_clouds < 0) return fail(DCMT_E_BADARG, "max_points %d, n_clouds %d", max_points, n_clouds);
+    if (n_clouds > 65535) return fail(DCMT_E_UNSUPPORTED, "at most 65535 clouds per call");
+    if (n_clouds > 1 && cloud_stride_points < (size_t)max_points) return fail(DCMT_E_BADARG, "cloud_stride_points %zu < max_points %d", cloud_stride_points, max_points);
+    int rc = check_planes(rows, cols, 1);
+    if (rc) return rc;
+    if ((size_t)rows * (size_t)cols > (size_t)1 << 30) return fail(DCMT_E_UNSUPPORTED, "frame larger than 2^30 pixels");
+    if (points && (reinterpret_cast<uintptr_t>(points) & 15)) return fail(DCMT_E_BADARG, "points must be 16-byte aligned");
+    if (n_clouds == 0) return DCMT_OK;
+    if ((rc = check_device())) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    Arena* ar = nullptr;
+    const size_t nk = dcmt::project_key_count(rows, cols) * n_clouds;
+    if ((rc = arena_acquire(st, carve_bytes(nk, sizeof(unsigned long long)) + carve_bytes(8 * (size_t)n_clouds, sizeof(unsigned)), &ar))) return rc;
+    dcmt::ProjectWork w{carve<unsigned long long>(ar, nk), carve<unsigned>(ar, 8 * (size_t)n_clouds)};
+    if ((rc = arena_ok(ar))) return rc;
+    API_CUDA(dcmt::project_run_batch(points, max_points, n_points_dev_or_null, cloud_stride_points, n_clouds, T_host, P_host, rows, cols,
+                                     projected, normalized, norm_a, norm_b, n_projected, w, st),
+             "projection launch");
+    return DCMT_OK;
+}
+
 int dcmt_lidar_project_f32_host(const float* points, int n_points, const float* T_host, const float* P_host, int rows, int cols,
                                 float* projected, float* normalized, float norm_a, float norm_b, int32_t* n_projected) {
     if ((!points && n_points > 0) || !T_host || !P_host) return fail(DCMT_E_BADARG, "null pointer");

@@ -1600,58 +1600,76 @@ __global__ void __launch_bounds__(QTT, DCMT_TAIL_CTAS) k_q8_tail(TailArgs a, con
         // ---- A9 + A10 on dictionary codes: decode with the frame's LUT (the inverted float each code stands for; kRankHundred
         //      = 100.0), 5x5 Gaussian in float32 -- the separable symmetric form OpenCV's float path uses, kernel
         //      [.0625 .25 .375 .25 .0625], rows then columns (:176-179) -- masked copy (:181-188: every pixel is valid here),
-        //      final inversion (:191-202).  One item = 4 pixels x 4 rows, as below.
+        //      final inversion (:191-202).  Every pixel is decoded ONCE (a gather from the LUT in global memory) into a float
+        //      plane that takes the place of plane A, dead since the median; it holds half the tile's rows at a time.
         const float* lut = a.lut + (size_t)slot * kRankMaxValid;
         const uint32_t eh = a.e_hundred;
-        auto dec = [&](uint32_t e) -> float { return e == eh ? kMaxDepth : __ldg(lut + ((int)e - kRankFirstCode)); };
+        // (cells of the tile that lie outside the image hold 0 / stale codes and only feed outputs that are never stored: the
+        // index is clamped so that they read inside the dictionary)
+        auto dec = [&](uint32_t e) -> float { return e == eh ? kMaxDepth : __ldg(lut + min(max((int)e - kRankFirstCode, 0), kRankMaxValid - 1)); };
         auto inv_out = [&](float d) -> float { return d >= 0.1f ? __fsub_rn(kMaxDepth, d) : d; };
-        const int NGR = (th + 3) / 4;
-        for (Items i(a.i_gauss); i.r < NGR; i.next()) {
-            const int cy0 = i.r * 4, gx = x0 + i.q * 4;
-            if (y0 + cy0 >= rows || gx >= cols) continue;
-            const uint32_t* p = B + (TV + cy0) * pitchw + TQ * 4 + 2 * i.q;
-            float* o = out + (size_t)(y0 + cy0) * a.out_pitch + gx;
-            float f[4][4];
+        float* F = reinterpret_cast<float*>(A);  // (rows of the half + 4) x (tw + 4) floats
+        const int FW = tw + 4, NGR = (th + 3) / 4, NP = tw / 4;
+        const int gsplit = (NGR + 1) / 2;  // item rows [0, gsplit) first, then [gsplit, NGR)
+        for (int half = 0; half < 2; ++half) {
+            const int g0 = half ? gsplit : 0, g1 = half ? NGR : gsplit;
+            if (g0 >= g1) break;
+            const int fr0 = 4 * g0 - 2, fr_n = 4 * (g1 - g0) + 4;  // core rows fr0 .. fr0 + fr_n - 1 (relative to the core)
             if (a.blur == 1) {
-                float h[8][4];
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {  // input rows cy0-2 .. cy0+5, pixels gx-2 .. gx+5
-                    const uint32_t* q = p + (k - 2) * pitchw;
-                    const uint32_t wa = q[-1], wb = q[0], wc = q[1], wd = q[2];
-                    const float x0f = dec(wa & 0xffffu), x1f = dec(wa >> 16), x2f = dec(wb & 0xffffu), x3f = dec(wb >> 16),
-                                x4f = dec(wc & 0xffffu), x5f = dec(wc >> 16), x6f = dec(wd & 0xffffu), x7f = dec(wd >> 16);
-                    const float xs[8] = {x0f, x1f, x2f, x3f, x4f, x5f, x6f, x7f};
-#pragma unroll
-                    for (int c = 0; c < 4; ++c)
-                        h[k][c] = __fadd_rn(__fadd_rn(__fmul_rn(xs[c + 2], 0.375f), __fmul_rn(__fadd_rn(xs[c + 1], xs[c + 3]), 0.25f)),
-                                            __fmul_rn(__fadd_rn(xs[c], xs[c + 4]), 0.0625f));
+                if (half) __syncthreads();  // the first half's readers are done with F
+                for (int it = threadIdx.x; it < fr_n * (FW / 2); it += QTT) {
+                    const int rr = it / (FW / 2), wq = it - rr * (FW / 2);
+                    const uint32_t w = B[(TV + fr0 + rr) * pitchw + TQ * 4 - 1 + wq];  // pixels core column 2 wq - 2, 2 wq - 1
+                    *reinterpret_cast<float2*>(F + rr * FW + 2 * wq) = make_float2(dec(w & 0xffffu), dec(w >> 16));
                 }
+                __syncthreads();
+            }
+            for (int it = threadIdx.x; it < (g1 - g0) * NP; it += QTT) {
+                const int gr = it / NP, ip = it - gr * NP;
+                const int cy0 = (g0 + gr) * 4, gx = x0 + ip * 4;
+                if (y0 + cy0 >= rows || gx >= cols) continue;
+                float* o = out + (size_t)(y0 + cy0) * a.out_pitch + gx;
+                float f[4][4];
+                if (a.blur == 1) {
+                    float h[8][4];
+                    const float* fp = F + (cy0 - 2 - fr0) * FW + ip * 4;  // row cy0 - 2, pixel gx - 2
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
+                    for (int k = 0; k < 8; ++k) {  // input rows cy0-2 .. cy0+5, pixels gx-2 .. gx+5
+                        const float4 xa = *reinterpret_cast<const float4*>(fp + k * FW), xb = *reinterpret_cast<const float4*>(fp + k * FW + 4);
+                        const float xs[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
 #pragma unroll
-                    for (int c = 0; c < 4; ++c)
-                        f[j][c] = inv_out(__fadd_rn(__fadd_rn(__fmul_rn(h[j + 2][c], 0.375f), __fmul_rn(__fadd_rn(h[j + 1][c], h[j + 3][c]), 0.25f)),
-                                                    __fmul_rn(__fadd_rn(h[j][c], h[j + 4][c]), 0.0625f)));
-            } else {
+                        for (int c = 0; c < 4; ++c)
+                            h[k][c] = __fadd_rn(__fadd_rn(__fmul_rn(xs[c + 2], 0.375f), __fmul_rn(__fadd_rn(xs[c + 1], xs[c + 3]), 0.25f)),
+                                                __fmul_rn(__fadd_rn(xs[c], xs[c + 4]), 0.0625f));
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            f[j][c] = inv_out(__fadd_rn(__fadd_rn(__fmul_rn(h[j + 2][c], 0.375f), __fmul_rn(__fadd_rn(h[j + 1][c], h[j + 3][c]), 0.25f)),
+                                                        __fmul_rn(__fadd_rn(h[j][c], h[j + 4][c]), 0.0625f)));
+                } else {
+                    const uint32_t* p = B + (TV + cy0) * pitchw + TQ * 4 + 2 * ip;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t w0 = p[j * pitchw], w1 = p[j * pitchw + 1];
+                        f[j][0] = inv_out(dec(w0 & 0xffffu));
+                        f[j][1] = inv_out(dec(w0 >> 16));
+                        f[j][2] = inv_out(dec(w1 & 0xffffu));
+                        f[j][3] = inv_out(dec(w1 >> 16));
+                    }
+                }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const uint32_t w0 = p[j * pitchw], w1 = p[j * pitchw + 1];
-                    f[j][0] = inv_out(dec(w0 & 0xffffu));
-                    f[j][1] = inv_out(dec(w0 >> 16));
-                    f[j][2] = inv_out(dec(w1 & 0xffffu));
-                    f[j][3] = inv_out(dec(w1 >> 16));
-                }
-            }
+                    if (cy0 + j >= th || y0 + cy0 + j >= rows) break;
+                    float* oj = o + (size_t)j * a.out_pitch;
+                    if (gx + 4 <= cols && a.vec_ok) {
+                        *reinterpret_cast<float4*>(oj) = make_float4(f[j][0], f[j][1], f[j][2], f[j][3]);
+                    } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (cy0 + j >= th || y0 + cy0 + j >= rows) break;
-                float* oj = o + (size_t)j * a.out_pitch;
-                if (gx + 4 <= cols && a.vec_ok) {
-                    *reinterpret_cast<float4*>(oj) = make_float4(f[j][0], f[j][1], f[j][2], f[j][3]);
-                } else {
-#pragma unroll
-                    for (int c = 0; c < 4; ++c)
-                        if (gx + c < cols) oj[c] = f[j][c];
+                        for (int c = 0; c < 4; ++c)
+                            if (gx + c < cols) oj[c] = f[j][c];
+                    }
                 }
             }
         }

@@ -20,8 +20,12 @@ struct Mats {
     float P[12];
 };
 
+// Every kernel below serves a BATCH of clouds: blockIdx.y is the cloud; its keys, min / max words, points and images
+// sit at cloud * (their per-cloud size).
 __global__ void k_project_clear(unsigned long long* __restrict__ keys, size_t n, unsigned* __restrict__ minmax) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    keys += (size_t)blockIdx.y * n;
+    minmax += (size_t)blockIdx.y * 8;
     if (i < n) keys[i] = 0ull;
     if (i == 0) { minmax[2] = 0u; minmax[3] = 0xffffffffu; minmax[4] = 0u; }
 }
@@ -34,9 +38,14 @@ __device__ __forceinline__ float row_dot_eigen(const float* m, float x, float y,
     return __fadd_rn(__fadd_rn(__fmul_rn(m[0], x), __fadd_rn(__fmul_rn(m[1], y), __fmul_rn(m[2], z))), m[3]);
 }
 
-__global__ void __launch_bounds__(256) k_project_scatter(const float4* __restrict__ pts, int n, Mats m, int rows, int cols,
+__global__ void __launch_bounds__(256) k_project_scatter(const float4* __restrict__ pts, int n, const int32_t* __restrict__ counts,
+                                                         size_t cloud_stride, Mats m, int rows, int cols,
                                                          unsigned long long* __restrict__ keys, unsigned* __restrict__ minmax) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (counts) n = counts[blockIdx.y];
+    pts += (size_t)blockIdx.y * cloud_stride;
+    keys += (size_t)blockIdx.y * rows * cols;
+    minmax += (size_t)blockIdx.y * 8;
     int landed = 0;
     if (i < n) {
         const float4 p = __ldg(pts + i);
@@ -66,6 +75,9 @@ __device__ __forceinline__ float unorder_bits(unsigned o) { return __uint_as_flo
 __global__ void __launch_bounds__(256) k_project_gather(const unsigned long long* __restrict__ keys, size_t n, float* __restrict__ projected,
                                                         unsigned* __restrict__ minmax) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    keys += (size_t)blockIdx.y * n;
+    minmax += (size_t)blockIdx.y * 8;
+    if (projected) projected += (size_t)blockIdx.y * n;
     unsigned lo = 0xffffffffu, hi = 0u;
     if (i < n) {
         const unsigned long long k = keys[i];
@@ -87,8 +99,11 @@ __global__ void __launch_bounds__(256) k_project_gather(const unsigned long long
 __global__ void __launch_bounds__(256) k_project_normalize(const unsigned long long* __restrict__ keys, size_t n, const unsigned* __restrict__ minmax,
                                                            float a, float b, float* __restrict__ normalized, int32_t* __restrict__ n_projected) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0 && n_projected) *n_projected = (int32_t)minmax[2];
+    keys += (size_t)blockIdx.y * n;
+    minmax += (size_t)blockIdx.y * 8;
+    if (i == 0 && n_projected) n_projected[blockIdx.y] = (int32_t)minmax[2];
     if (i >= n || !normalized) return;
+    normalized += (size_t)blockIdx.y * n;
     // cv::normalize, NORM_MINMAX, dtype CV_32F (OpenCV 4.x modules/core/src/norm.cpp)
     const double smin = (double)unorder_bits(minmax[3]), smax = (double)unorder_bits(minmax[4]);
     const double dmin = a < b ? (double)a : (double)b, dmax = a < b ? (double)b : (double)a;
@@ -104,19 +119,28 @@ __global__ void __launch_bounds__(256) k_project_normalize(const unsigned long l
 
 size_t project_key_count(int rows, int cols) { return (size_t)rows * cols; }
 
-cudaError_t project_run(const float* points, int n_points, const float* T, const float* P, int rows, int cols, float* projected,
-                        float* normalized, float norm_a, float norm_b, int32_t* n_projected, const ProjectWork& w, cudaStream_t st) {
+cudaError_t project_run_batch(const float* points, int n_points, const int32_t* counts_dev, size_t cloud_stride_points, int n_clouds,
+                              const float* T, const float* P, int rows, int cols, float* projected, float* normalized, float norm_a,
+                              float norm_b, int32_t* n_projected, const ProjectWork& w, cudaStream_t st) {
+    if (n_clouds == 0) return cudaSuccess;
     Mats m;
     for (int k = 0; k < 12; ++k) { m.T[k] = T[k]; m.P[k] = P[k]; }
     const size_t n = (size_t)rows * cols;
     const unsigned nb = (unsigned)((n + 255) / 256);
-    DCMT_LAUNCH(k_project_clear, dim3(nb), dim3(256), 0, st, w.keys, n, w.minmax);
+    // four launches for the whole batch: clear, scatter (64-bit atomicMax, last point in file order wins), gather + min / max,
+    // normalize.  (A single cloud used to cost the same four launches: 58 us each, launch bound.)
+    DCMT_LAUNCH(k_project_clear, dim3(nb, n_clouds), dim3(256), 0, st, w.keys, n, w.minmax);
     if (n_points > 0)
-        DCMT_LAUNCH(k_project_scatter, dim3((n_points + 255) / 256), dim3(256), 0, st, reinterpret_cast<const float4*>(points), n_points, m, rows,
-                    cols, w.keys, w.minmax);
-    DCMT_LAUNCH(k_project_gather, dim3(nb), dim3(256), 0, st, w.keys, n, projected, w.minmax);
-    DCMT_LAUNCH(k_project_normalize, dim3(nb), dim3(256), 0, st, w.keys, n, w.minmax, norm_a, norm_b, normalized, n_projected);
+        DCMT_LAUNCH(k_project_scatter, dim3((n_points + 255) / 256, n_clouds), dim3(256), 0, st, reinterpret_cast<const float4*>(points),
+                    n_points, counts_dev, cloud_stride_points, m, rows, cols, w.keys, w.minmax);
+    DCMT_LAUNCH(k_project_gather, dim3(nb, n_clouds), dim3(256), 0, st, w.keys, n, projected, w.minmax);
+    DCMT_LAUNCH(k_project_normalize, dim3(nb, n_clouds), dim3(256), 0, st, w.keys, n, w.minmax, norm_a, norm_b, normalized, n_projected);
     return cudaGetLastError();
+}
+
+cudaError_t project_run(const float* points, int n_points, const float* T, const float* P, int rows, int cols, float* projected,
+                        float* normalized, float norm_a, float norm_b, int32_t* n_projected, const ProjectWork& w, cudaStream_t st) {
+    return project_run_batch(points, n_points, nullptr, 0, 1, T, P, rows, cols, projected, normalized, norm_a, norm_b, n_projected, w, st);
 }
 
 }  // namespace dcmt

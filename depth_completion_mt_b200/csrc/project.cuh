@@ -14,4 +14,11 @@ size_t project_key_count(int rows, int cols);
 cudaError_t project_run(const float* points, int n_points, const float* T, const float* P, int rows, int cols, float* projected,
                         float* normalized, float norm_a, float norm_b, int32_t* n_projected, const ProjectWork& w, cudaStream_t st);
 
+// The same for n_clouds clouds in four launches: cloud c holds counts_dev[c] points (device array; null: n_points each) at
+// points + c * cloud_stride_points * 4 floats, n_points bounds every count; the work arrays hold n_clouds x (keys, 8 min / max
+// words); images and n_projected are n_clouds planes / ints.
+cudaError_t project_run_batch(const float* points, int n_points, const int32_t* counts_dev, size_t cloud_stride_points, int n_clouds,
+                              const float* T, const float* P, int rows, int cols, float* projected, float* normalized, float norm_a,
+                              float norm_b, int32_t* n_projected, const ProjectWork& w, cudaStream_t st);
+
 }  // namespace dcmt

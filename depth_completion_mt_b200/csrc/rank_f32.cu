@@ -7,8 +7,8 @@
 // are first replaced by their RANKS among the frame's inverted values (any strictly monotone code gives the same
 // selections), and the codes are turned back into the floats they stand for before the Gaussian:
 //
-//   k_rank_sort    one CTA per frame: the inverted values 100 - v of the valid pixels (v >= 0.1f and 100 - v >= 0.1f)
-//                  are gathered in shared memory and sorted (bitonic network); the sorted list is the frame's
+//   k_rank_compact the inverted values 100 - v of the valid pixels (v >= 0.1f and 100 - v >= 0.1f) are gathered per frame
+//   k_rank_sort    one CTA per frame sorts them in shared memory (bitonic network); the sorted list is the frame's
 //                  dictionary LUT[0 .. count)
 //   k_rank_encode  every pixel -> code: 1 for a hole (the encoding of fused_q8.cu), 27 + lower_bound(LUT, 100 - v) for a
 //                  valid pixel (equal values share a code); the code plane is the uint16 input of k_q8_front
@@ -31,68 +31,80 @@ __device__ __forceinline__ bool rank_valid(float v, float& inv) {
     return v >= 0.1f && inv >= 0.1f;
 }
 
-__global__ void __launch_bounds__(kSortThreads, 1) k_rank_sort(const float* __restrict__ in, size_t in_pitch, size_t in_fstride, int rows,
-                                                               int cols, float* __restrict__ lut, int* __restrict__ lut_count,
-                                                               FrameCounters* __restrict__ ctr) {
-    DCMT_DYN_SMEM(uint32_t, keys);  // kRankMaxValid keys
-    __shared__ int s_warp_sum[kSortThreads / 32];
-    __shared__ int s_total, s_bad;
-    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const float* src = in + (size_t)f * in_fstride;
-    const int n = rows * cols;
-    if (tid == 0) s_bad = 0;
-    // pass 1: valid pixels per thread (pixels tid, tid + T, ...), then an exclusive scan over the CTA
-    int mine = 0, bad = 0;
-    for (int i = tid; i < n; i += kSortThreads) {
-        const int r = i / cols, c = i - r * cols;
-        const float v = __ldg(src + (size_t)r * in_pitch + c);
-        float inv;
-        mine += rank_valid(v, inv) ? 1 : 0;
-        bad |= (v != v) ? 1 : 0;  // NaN: outside the domain parity is defined on -> generic pipeline
+// Gather the keys of a frame's valid pixels (bit patterns of the inverted values: positive floats order like their bits)
+// into lut[frame][0 .. count), in arbitrary order, with every SM: one thread per 8 pixels of a row, one reservation per
+// warp.  count keeps counting past the capacity (the sort kernel flags such frames); a NaN flags the frame at once.
+__global__ void __launch_bounds__(256) k_rank_compact(const float* __restrict__ in, size_t in_pitch, size_t in_fstride, int rows, int cols,
+                                                      int vec_ok, float* __restrict__ lut, int* __restrict__ lut_count,
+                                                      FrameCounters* __restrict__ ctr) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y, f = blockIdx.z, lane = threadIdx.x & 31;
+    float iv[8];
+    uint32_t m = 0u;  // bit j: pixel j of the octet is valid
+    bool nan = false;
+    if (q * 8 < cols) {
+        const float* src = in + (size_t)f * in_fstride + (size_t)r * in_pitch + q * 8;
+        float v[8];
+        if (vec_ok && q * 8 + 8 <= cols) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = q * 8 + j < cols ? __ldg(src + j) : 0.0f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            nan |= v[j] != v[j];
+            if (rank_valid(v[j], iv[j])) m |= 1u << j;
+        }
     }
-    int incl = mine;
+    const int n = __popc(m);
+    if (__any_sync(0xffffffffu, nan) && lane == 0) ctr[f].needs_generic = 1;  // outside the domain parity is defined on
+    // offsets: inclusive scan inside the warp, warp totals through shared memory, ONE atomic reservation per block (the
+    // blocks of a frame run side by side: a reservation per warp serialised 1 700 atomics per frame on one address)
+    __shared__ int s_warp[8], s_base;
+    const int warp = threadIdx.x >> 5;
+    int incl = n;
 #pragma unroll
     for (int s = 1; s < 32; s <<= 1) {
         const int t = __shfl_up_sync(0xffffffffu, incl, s);
         if (lane >= s) incl += t;
     }
-    if (lane == 31) s_warp_sum[warp] = incl;
-    if (bad) s_bad = 1;
+    if (lane == 31) s_warp[warp] = incl;
     __syncthreads();
-    if (warp == 0) {
-        int w = s_warp_sum[lane];
-        int winc = w;
+    if (threadIdx.x == 0) {
+        int tot = 0;
 #pragma unroll
-        for (int s = 1; s < 32; s <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, winc, s);
-            if (lane >= s) winc += t;
-        }
-        s_warp_sum[lane] = winc - w;  // exclusive
-        if (lane == 31) s_total = winc;
+        for (int w = 0; w < 8; ++w) { const int c = s_warp[w]; s_warp[w] = tot; tot += c; }
+        s_base = tot ? atomicAdd(lut_count + f, tot) : 0;
     }
     __syncthreads();
-    const int total = s_total;
-    if (total > kRankMaxValid || s_bad) {  // the dictionary does not fit / NaN: this frame goes to the generic pipeline
-        if (tid == 0) {
-            ctr[f].needs_generic = 1;
-            lut_count[f] = 0;
+    int base = s_base + s_warp[warp] + incl - n;
+    float* o = lut + (size_t)f * kRankMaxValid;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        if ((m >> j) & 1u) {
+            if (base < kRankMaxValid) o[base] = iv[j];  // the float itself: positive floats order like their bit patterns
+            ++base;
         }
+}
+
+// One CTA per frame: the gathered keys are sorted in shared memory (bitonic network) and written back -- the frame's
+// dictionary.  Frames whose keys do not fit (or that were flagged for a NaN) are left to the generic pipeline.
+__global__ void __launch_bounds__(kSortThreads, 1) k_rank_sort(float* __restrict__ lut, const int* __restrict__ lut_count,
+                                                               FrameCounters* __restrict__ ctr) {
+    DCMT_DYN_SMEM(uint32_t, keys);  // kRankMaxValid keys
+    const int f = blockIdx.x, tid = threadIdx.x;
+    const int total = lut_count[f];
+    if (total > kRankMaxValid) {
+        if (tid == 0) ctr[f].needs_generic = 1;
         return;
     }
-    // pass 2: the keys (bit patterns of positive floats order like the floats), at thread-private offsets
-    int at = s_warp_sum[warp] + incl - mine;
-    for (int i = tid; i < n; i += kSortThreads) {
-        const int r = i / cols, c = i - r * cols;
-        const float v = __ldg(src + (size_t)r * in_pitch + c);
-        float inv;
-        if (rank_valid(v, inv)) keys[at++] = __float_as_uint(inv);
-    }
-    int P = 1;
+    if (ctr[f].needs_generic) return;
+    float* o = lut + (size_t)f * kRankMaxValid;
+    int P = 2;
     while (P < total) P <<= 1;
-    if (P < 2) P = 2;
-    for (int i = total + tid; i < P; i += kSortThreads) keys[i] = 0xffffffffu;
+    for (int i = tid; i < P; i += kSortThreads) keys[i] = i < total ? __float_as_uint(o[i]) : 0xffffffffu;
     __syncthreads();
-    // bitonic sort, ascending
     for (int k = 2; k <= P; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
             for (int t = tid; t < (P >> 1); t += kSortThreads) {
@@ -105,41 +117,81 @@ __global__ void __launch_bounds__(kSortThreads, 1) k_rank_sort(const float* __re
             __syncthreads();
         }
     }
-    float* o = lut + (size_t)f * kRankMaxValid;
     for (int i = tid; i < total; i += kSortThreads) o[i] = __uint_as_float(keys[i]);
-    if (tid == 0) lut_count[f] = total;
 }
 
-// one thread per 8 pixels of a row (one 16-byte store of codes)
+// One thread per 8 pixels of a row (one 16-byte store of codes).  The valid pixels of a warp's 256 pixels (about 13 at 5 %)
+// are queued in shared memory and searched one per lane -- every lane runs at most a few binary searches, all lanes at
+// once, instead of every lane walking its eight pixels in turn while the others wait.
 __global__ void __launch_bounds__(256) k_rank_encode(const float* __restrict__ in, size_t in_pitch, size_t in_fstride, int rows, int cols,
-                                                     const float* __restrict__ lut, const int* __restrict__ lut_count,
+                                                     int vec_ok, const float* __restrict__ lut, const int* __restrict__ lut_count,
                                                      uint16_t* __restrict__ codes, size_t code_pitch) {
-    const int q = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y, f = blockIdx.z;
-    if (q * 8 >= cols) return;
-    const int count = lut_count[f];
+    __shared__ float s_val[8][256];                     // queue of the warp: inverted values of its valid pixels ...
+    __shared__ uint16_t s_slot[8][256];                 // ... and which of its 256 pixels each one is
+    __shared__ __align__(16) uint16_t s_code[8][256];   // codes of the warp's 256 pixels: [lane * 8 + j]
+    const int q = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y, f = blockIdx.z, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int count = min(lut_count[f], kRankMaxValid);  // (frames past the capacity are flagged and redone: any code will do)
     const float* d = lut + (size_t)f * kRankMaxValid;
-    const float* src = in + (size_t)f * in_fstride + (size_t)r * in_pitch + q * 8;
-    uint32_t e[8];
+    float iv[8];
+    uint32_t m = 0u, inside = 0u;
+    if (q * 8 < cols) {
+        const float* src = in + (size_t)f * in_fstride + (size_t)r * in_pitch + q * 8;
+        float v[8];
+        if (vec_ok && q * 8 + 8 <= cols) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+            inside = 0xffu;
+        } else {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        e[j] = 0u;  // beyond the last column: the padding of the code plane, never read as image
-        if (q * 8 + j < cols) {
-            float inv;
-            if (rank_valid(__ldg(src + j), inv)) {
-                int lo = 0, hi = count;  // first index with d[index] >= inv
-                while (lo < hi) {
-                    const int mid = (lo + hi) >> 1;
-                    if (__ldg(d + mid) < inv) lo = mid + 1;
-                    else hi = mid;
-                }
-                e[j] = (uint32_t)(kRankFirstCode + lo);
-            } else {
-                e[j] = 1u;
+            for (int j = 0; j < 8; ++j) {
+                v[j] = q * 8 + j < cols ? __ldg(src + j) : 0.0f;
+                inside |= q * 8 + j < cols ? 1u << j : 0u;
             }
         }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (rank_valid(v[j], iv[j])) m |= 1u << j;
+        m &= inside;
     }
-    uint16_t* o = codes + ((size_t)f * rows + r) * code_pitch + q * 8;
-    *reinterpret_cast<uint4*>(o) = make_uint4(e[0] | (e[1] << 16), e[2] | (e[3] << 16), e[4] | (e[5] << 16), e[6] | (e[7] << 16));
+    // holes: 1, beyond the last column: 0 (padding of the code plane, never read as image); valid ones are overwritten below
+    uint16_t* sc = s_code[warp];
+    float* sv = s_val[warp];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sc[lane * 8 + j] = (uint16_t)((inside >> j) & 1u);
+    // queue: (value, slot) of every valid pixel of the warp
+    const int n = __popc(m);
+    int incl = n;
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, s);
+        if (lane >= s) incl += t;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    uint16_t* ss = s_slot[warp];
+    int at = incl - n;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        if ((m >> j) & 1u) {
+            sv[at] = iv[j];
+            ss[at] = (uint16_t)(lane * 8 + j);
+            ++at;
+        }
+    __syncwarp();
+    for (int k = lane; k < total; k += 32) {
+        const float inv = sv[k];
+        int lo = 0, hi = count;  // first index with d[index] >= inv
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (__ldg(d + mid) < inv) lo = mid + 1;
+            else hi = mid;
+        }
+        sc[ss[k]] = (uint16_t)(kRankFirstCode + lo);
+    }
+    __syncwarp();
+    if (q * 8 < cols) {
+        uint16_t* o = codes + ((size_t)f * rows + r) * code_pitch + q * 8;
+        *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(sc + lane * 8);
+    }
 }
 
 }  // namespace
@@ -151,10 +203,14 @@ cudaError_t rank_configure() {
 cudaError_t rank_build(const float* in, size_t in_pitch, size_t in_fstride, int rows, int cols, int n_frames, float* lut, int* lut_count,
                        uint16_t* codes, size_t code_pitch, FrameCounters* ctr, cudaStream_t st) {
     if (n_frames == 0) return cudaSuccess;
-    DCMT_LAUNCH(k_rank_sort, dim3(n_frames), dim3(kSortThreads), kRankMaxValid * sizeof(uint32_t), st, in, in_pitch, in_fstride, rows, cols,
+    cudaError_t e = cudaMemsetAsync(lut_count, 0, (size_t)n_frames * sizeof(int), st);
+    if (e != cudaSuccess) return e;
+    const int vec_ok = in_pitch % 4 == 0 && in_fstride % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0;
+    DCMT_LAUNCH(k_rank_compact, dim3(((cols + 7) / 8 + 255) / 256, rows, n_frames), dim3(256), 0, st, in, in_pitch, in_fstride, rows, cols, vec_ok,
                 lut, lut_count, ctr);
+    DCMT_LAUNCH(k_rank_sort, dim3(n_frames), dim3(kSortThreads), kRankMaxValid * sizeof(uint32_t), st, lut, lut_count, ctr);
     DCMT_LAUNCH(k_rank_encode, dim3(((cols + 7) / 8 + 255) / 256, rows, n_frames), dim3(256), 0, st, in, in_pitch, in_fstride, rows, cols,
-                lut, lut_count, codes, code_pitch);
+                vec_ok, lut, lut_count, codes, code_pitch);
     return cudaGetLastError();
 }
 

@@ -310,6 +310,13 @@ DCMT_API int dcmt_evaluate_f32_host(const float *gt, const float *dense, int row
 DCMT_API int dcmt_lidar_project_f32(const float *points, int n_points, const float *T_host, const float *P_host, int rows,
                                     int cols, float *projected_or_null, float *normalized_or_null, float norm_a,
                                     float norm_b, int32_t *n_projected_or_null, void *cuda_stream);
+/* the same for a batch of clouds in four launches (one cloud alone is launch bound): cloud c holds n_points_dev[c] points
+ * (DEVICE array of n_clouds int32; NULL: max_points each) at points + c * cloud_stride_points * 4 floats; max_points bounds
+ * every count.  Outputs are n_clouds planes (n_projected: n_clouds int32); one T and P for the whole batch. */
+DCMT_API int dcmt_lidar_project_batch_f32(const float *points, const int32_t *n_points_dev_or_null, int max_points,
+                                          size_t cloud_stride_points, int n_clouds, const float *T_host, const float *P_host,
+                                          int rows, int cols, float *projected_or_null, float *normalized_or_null, float norm_a,
+                                          float norm_b, int32_t *n_projected_or_null, void *cuda_stream);
 DCMT_API int dcmt_lidar_project_f32_host(const float *points, int n_points, const float *T_host, const float *P_host,
                                          int rows, int cols, float *projected_or_null, float *normalized_or_null,
                                          float norm_a, float norm_b, int32_t *n_projected_or_null);

@@ -54,13 +54,13 @@ def body_boundary_values(be):
     check(be, s, "negative / tiny / sub-threshold values are holes", want_path=1)
     s2 = s.copy()
     s2[7, 9] = np.float32(12.3)  # a valid pixel that is not a multiple of 1/256: generic pipeline
-    check(be, s2, "one non-q8 valid pixel", want_path=0)
+    check(be, s2, "one non-q8 valid pixel", want_path=2)  # the float32 dictionary (DCMT_PATH_RANK) serves it
     # slivers next to the thresholds where a non-q8 value is valid for the reference: must be caught, not mapped to a hole
     for v in (0.1, np.nextafter(np.float32(0.1015625), np.float32(0)), 99.899, 99.8999, np.nextafter(np.float32(99.9), np.float32(0)),
               np.nextafter(np.float32(36.00390625), np.float32(0)), np.nextafter(np.float32(12.5), np.float32(100))):
         s3 = base.astype(np.float32) / np.float32(256)
         s3[11, 13] = np.float32(v)
-        check(be, s3, f"sliver value {v!r}", want_path=0)
+        check(be, s3, f"sliver value {v!r}", want_path=2)
     # ... and just outside them the pixel is a hole for the reference too (either path is fine, the bytes must match)
     for v in (0.0999, 99.9, 99.95, 100.0, 250.0):
         s3 = base.astype(np.float32) / np.float32(256)
@@ -72,7 +72,9 @@ def body_routing(be):
     s = synth.sparse_depth(6, 64, 96, 0.05)
     check(be, s, "forced generic", path="generic", want_path=0)
     f = synth.sparse_depth_float(6, 64, 96, 0.05)
-    check(be, f, "float frame via auto", want_path=0)
+    check(be, f, "float frame via auto", want_path=2)
+    check(be, f, "float frame, dictionary path asked for", path="rank", want_path=2)
+    check(be, f, "float frame, blur none: bit-exact", blur="none", want_path=2)
     # DCMT_PATH_FUSED trusts the caller (no validation, no synchronisation): only meaningful for strict q8 frames
     check(be, s, "forced fused", path="fused", want_path=1)
     # bilateral and tiny frames are served by the generic pipeline whatever the flag says
@@ -83,7 +85,7 @@ def body_routing(be):
     # mixed batch: only the non-q8 frame is redone
     b = np.stack([synth.sparse_depth(7, 64, 96, 0.05), f, synth.sparse_depth(8, 64, 96, 0.02)])
     out, st = be.img_completion(b, "gaussian", return_stats=True)
-    assert [int(v) for v in st[:, 3]] == [1, 0, 1]
+    assert [int(v) for v in st[:, 3]] == [1, 2, 1]
     for i in (0, 2):
         assert_bit_equal(out[i], co.img_completion(b[i], "gaussian"), f"mixed batch frame {i}")
     assert np.abs(out[1] - co.img_completion(b[1], "gaussian")).max() <= 1e-4
@@ -285,3 +287,57 @@ def test_gpu_large_shapes(gpu_lib):
     b = api.img_completion(dev, False, "gaussian", path="generic", lib=gpu_lib)
     assert torch.equal(a, b)
     assert_bit_equal(a[0].cpu().numpy(), co.img_completion(big[0], "gaussian"), "2048x4096")
+
+
+def body_rank(be, shapes, big=False):
+    """DCMT_PATH_RANK (rank_f32.cu): float32 frames that are not strict q8 -- what the stereo program completes after
+    cv::normalize (main_sl.cpp:522-540) -- run on the fused kernels through a per-frame order-preserving dictionary.
+    Blur none: bit-exact for any finite input (every stage only selects); Gaussian: float32, tolerance 1e-4."""
+    for i, (rows, cols, p) in enumerate(shapes):
+        f = synth.sparse_depth_float(400 + i, rows, cols, p)
+        if i % 3 == 1:  # negatives, sub-threshold, > 99.9 (inverts to a hole), exactly 100, duplicates
+            rng = np.random.default_rng(i)
+            f = f.copy()
+            f[rng.integers(0, rows, 20), rng.integers(0, cols, 20)] = np.float32(-2.5)
+            f[rng.integers(0, rows, 20), rng.integers(0, cols, 20)] = np.float32(0.0999)
+            f[rng.integers(0, rows, 20), rng.integers(0, cols, 20)] = np.float32(99.95)
+            f[rng.integers(0, rows, 20), rng.integers(0, cols, 20)] = np.float32(100.0)
+            f[rng.integers(0, rows, 40), rng.integers(0, cols, 40)] = np.float32(17.123)
+        for path in ("rank", "auto"):
+            out, st = be.img_completion(f, "none", path=path, return_stats=True)
+            ref_st = {}
+            assert_bit_equal(out, co.img_completion(f, "none", ref_st), f"rank {rows}x{cols} p={p} none {path}")
+            assert int(st[0, 3]) == 2 and int(st[0, 0]) == ref_st["loop_passes"] and int(st[0, 2]) == ref_st["holes_after_extrapolation"]
+            out = be.img_completion(f, "gaussian", path=path)
+            assert np.abs(out - co.img_completion(f, "gaussian")).max() <= 1e-4, f"rank {rows}x{cols} gaussian {path}"
+    # a frame with more valid pixels than the dictionary holds (32768) goes to the generic pipeline; so does a NaN
+    rows, cols = (352, 1216) if big else (200, 400)
+    dense = synth.sparse_depth_float(420, rows, cols, 0.5)
+    assert (dense >= 0.1).sum() > 32768
+    out, st = be.img_completion(dense, "none", path="rank", return_stats=True)
+    assert int(st[0, 3]) == 0
+    assert_bit_equal(out, co.img_completion(dense, "none"), "dictionary overflow -> generic")
+    b = np.stack([synth.sparse_depth_float(421, 64, 96, 0.05), synth.sparse_depth(422, 64, 96, 0.05), synth.sparse_depth_float(423, 64, 96, 0.05)])
+    out, st = be.img_completion(b, "none", return_stats=True)
+    assert [int(v) for v in st[:, 3]] == [2, 1, 2]
+    for i in range(3):
+        assert_bit_equal(out[i], co.img_completion(b[i], "none"), f"mixed batch frame {i}")
+    # the normalised projection of a LiDAR cloud (main_sl.cpp:522-540): the input the stereo program really feeds
+    pts = synth.velodyne_cloud(7, 60000 if big else 30000)
+    r2, c2 = (352, 1216) if big else (200, 700)
+    nrm = co.lidar_project(pts, synth.KITTI_T_VELO_TO_CAM, synth.KITTI_P_RECT_02, r2, c2)[1]
+    out, st = be.img_completion(nrm, "none", return_stats=True)
+    assert (nrm >= 0.1).sum() > 300 and int(st[0, 3]) == 2
+    assert_bit_equal(out, co.img_completion(nrm, "none"), "normalised projection, blur none")
+    assert np.abs(be.img_completion(nrm, "gaussian") - co.img_completion(nrm, "gaussian")).max() <= 1e-4
+
+
+def test_emu_rank(emu_lib):
+    body_rank(Backend(emu_lib, "emu"), [(64, 96, 0.05), (97, 171, 0.05), (120, 200, 0.01), (80, 136, 0.3), (50, 333, 0.002)])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["gpu_host", "gpu_device"])
+def test_gpu_rank(gpu_lib, mode):
+    body_rank(Backend(gpu_lib, mode), [(352, 1216, 0.05), (375, 1242, 0.05), (352, 1216, 0.01), (97, 171, 0.05), (512, 1760, 0.02),
+                                       (1024, 2048, 0.005)], big=True)

@@ -66,16 +66,23 @@ def body_guided_fused(be, shapes):
     got, st = be.interpolate_with_superpixels(lab, s, 1, n_clusters=k, return_stats=True)
     assert_bit_equal(got, co.interpolate_with_superpixels(s, lab, k, literal=False), "label table overflow")
     assert int(st[0, 3]) == 1
-    # a non-q8 frame in a batch is redone by the generic pipeline with its own labels
+    # a non-q8 frame in a batch is redone through the float32 dictionary (DCMT_PATH_RANK) with its own labels
     rows, cols = 48, 80
     b = np.stack([synth.sparse_depth(180, rows, cols, 0.06), synth.sparse_depth_float(181, rows, cols, 0.06), synth.sparse_depth(182, rows, cols, 0.06)])
     labs = np.stack([synth.superpixel_labels(180 + f, rows, cols, 9)[0] for f in range(3)])
     k = synth.superpixel_labels(180, rows, cols, 9)[1]
     got, st = be.interpolate_with_superpixels(labs, b, 1, n_clusters=k, return_stats=True)
-    assert [int(v) for v in st[:, 3]] == [1, 0, 1]
+    assert [int(v) for v in st[:, 3]] == [1, 2, 1]
     for f in (0, 2):
         assert_bit_equal(got[f], co.interpolate_with_superpixels(b[f], labs[f], k, literal=False), f"batch frame {f}")
     assert np.abs(got[1] - co.interpolate_with_superpixels(b[1], labs[1], k, literal=False)).max() <= GAUSS_TOL
+    # guided completion of float frames at the shapes given (the only form DC_stereo_lidar feeds it, main_sl.cpp:540)
+    for i, (rows, cols, p, step) in enumerate(shapes[:3]):
+        f = synth.sparse_depth_float(500 + i, rows, cols, p)
+        lab, k = synth.superpixel_labels(500 + i, rows, cols, step)
+        got, st = be.interpolate_with_superpixels(lab, f, 1, n_clusters=k, return_stats=True)
+        assert int(st[0, 3]) == 2, f"float guided {rows}x{cols}: path {st[0, 3]}"
+        assert np.abs(got - co.interpolate_with_superpixels(f, lab, k, literal=False)).max() <= GAUSS_TOL, f"float guided {rows}x{cols}"
 
 
 def body_stereo_golden(be, golden):

@@ -62,3 +62,24 @@ def test_gpu_project(gpu_lib, mode):
 
     body(gpu_lib, (lambda a: a) if mode == "host" else (lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()),
          [(64, 200, 20000), (48, 160, 30000), (352, 1216, 120000), (375, 1242, 120000)])
+
+
+@pytest.mark.gpu
+def test_gpu_project_batch(gpu_lib):
+    """dcmt_lidar_project_batch_f32: clouds of different sizes in one call == the literal loop per cloud"""
+    import torch
+
+    rows, cols = 352, 1216
+    sizes = [120000, 60000, 0, 99999, 1]
+    clouds = [synth.velodyne_cloud(k, n) if n else np.zeros((0, 4), np.float32) for k, n in enumerate(sizes)]
+    mp = max(sizes)
+    buf = np.zeros((len(sizes), mp, 4), np.float32)
+    for k, c in enumerate(clouds):
+        buf[k, : len(c)] = c
+    proj, nrm, cnt = api.lidar_project_batch(torch.from_numpy(buf).cuda(), torch.tensor(sizes, dtype=torch.int32).cuda(), T, P, rows, cols,
+                                             lib=gpu_lib)
+    for k, c in enumerate(clouds):
+        rp, rn, rc = co.lidar_project(c, T, P, rows, cols)
+        assert int(cnt[k]) == rc
+        assert_bit_equal(proj[k].cpu().numpy(), rp, f"cloud {k} projected")
+        assert_bit_equal(nrm[k].cpu().numpy(), rn, f"cloud {k} normalized")

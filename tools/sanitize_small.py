@@ -18,6 +18,12 @@ for k, (rows, cols, p) in enumerate(((97, 171, 0.05), (100, 321, 0.004), (64, 96
     d16 = synth.sparse_depth_q8(k, rows, cols, p)
     out = api.img_completion(torch.from_numpy(d16).cuda(), False, "none", lib=lib).cpu().numpy()
     assert np.array_equal(out.view(np.uint32), co.img_completion(d16.astype(np.float32) / np.float32(256), "none").view(np.uint32))
+# the float32 dictionary path (rank_f32.cu + k_q8_tail<true>), incl. a tile that overhangs the image on both sides
+for k, (rows, cols, p) in enumerate(((97, 171, 0.05), (64, 96, 0.1), (193, 40, 0.05))):
+    f = synth.sparse_depth_float(40 + k, rows, cols, p)
+    for blur in ("none", "gaussian"):
+        out = api.img_completion(torch.from_numpy(f).cuda(), False, blur, path="rank", lib=lib).cpu().numpy()
+        assert np.abs(out - co.img_completion(f, blur)).max() <= 1e-4, (rows, cols, blur)
 lab = synth.lab_image(0, 64, 96)
 labels = api.generate_superpixels(torch.from_numpy(lab).cuda(), 10, 40, lib=lib)
 assert np.array_equal(labels.cpu().numpy(), co.slic(lab, 10, 40)[0])
