@@ -1920,6 +1920,8 @@ cudaError_t q8_run_tail(const Q8Plan& p, float* out, size_t out_pitch, size_t ou
     const int max_segs = QTT / NW > 0 ? QTT / NW : 1;
     int med_len = 2 * ((MH + 2 * max_segs - 1) / (2 * max_segs));
     if (med_len < 8) med_len = 8;
+    static const int env_len = [] { const char* e = getenv("DCMT_MED_LEN"); return e ? atoi(e) : 0; }();  // experiments
+    if (env_len >= 2) med_len = env_len & ~1;
     const int med_segs = (MH + med_len - 1) / med_len;
     // tile load by TMA: a 3-D map (columns, rows, slots) of the intermediate plane whose column extent is the true
     // image width, so that the padding columns of the plane read as absent like everything else outside the image

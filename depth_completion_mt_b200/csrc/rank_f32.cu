@@ -105,14 +105,45 @@ __global__ void __launch_bounds__(kSortThreads, 1) k_rank_sort(float* __restrict
     while (P < total) P <<= 1;
     for (int i = tid; i < P; i += kSortThreads) keys[i] = i < total ? __float_as_uint(o[i]) : 0xffffffffu;
     __syncthreads();
-    for (int k = 2; k <= P; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = tid; t < (P >> 1); t += kSortThreads) {
-                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));  // the lower index of pair t at distance j
-                const int p = i | j;
-                const uint32_t a = keys[i], b = keys[p];
-                const bool up = (i & k) == 0;
-                if ((a > b) == up) { keys[i] = b; keys[p] = a; }
+    // bitonic sort, ascending, four keys per access: a stage at distance j >= 4 exchanges QUADS (two 16-byte loads, four
+    // min / max pairs, two 16-byte stores: the direction is uniform over a quad because k >= 8 there); the stages at
+    // distances 2 and 1 of every k run on one quad in registers.  91 + 15 passes over shared memory instead of 120 scalar ones.
+    if (P < 4) {  // at most two keys (P is 2): one compare-exchange
+        if (tid == 0 && keys[0] > keys[1]) { const uint32_t t = keys[0]; keys[0] = keys[1]; keys[1] = t; }
+        __syncthreads();
+    } else {
+        uint4* kq = reinterpret_cast<uint4*>(keys);
+        const int nq = P >> 2;
+        auto cx = [](uint32_t& a, uint32_t& b, bool up) {
+            const uint32_t lo = min(a, b), hi = max(a, b);
+            a = up ? lo : hi;
+            b = up ? hi : lo;
+        };
+        for (int k = 2; k <= P; k <<= 1) {
+            for (int j = k >> 1; j >= 4; j >>= 1) {
+                const int jq = j >> 2;  // distance in quads
+                for (int t = tid; t < (nq >> 1); t += kSortThreads) {
+                    const int iq = ((t & ~(jq - 1)) << 1) | (t & (jq - 1));  // the lower quad of pair t
+                    uint4 a = kq[iq], b = kq[iq | jq];
+                    const bool up = ((iq << 2) & k) == 0;
+                    cx(a.x, b.x, up); cx(a.y, b.y, up); cx(a.z, b.z, up); cx(a.w, b.w, up);
+                    kq[iq] = a;
+                    kq[iq | jq] = b;
+                }
+                __syncthreads();
+            }
+            for (int q = tid; q < nq; q += kSortThreads) {
+                uint4 v = kq[q];
+                const int i = q << 2;
+                if (k == 2) {  // pairs (0,1) ascending, (2,3) descending
+                    cx(v.x, v.y, true);
+                    cx(v.z, v.w, false);
+                } else {
+                    const bool up = (i & k) == 0;  // k == 4: (i & 4); larger k: uniform over the quad as well
+                    cx(v.x, v.z, up); cx(v.y, v.w, up);
+                    cx(v.x, v.y, up); cx(v.z, v.w, up);
+                }
+                kq[q] = v;
             }
             __syncthreads();
         }
@@ -121,21 +152,25 @@ __global__ void __launch_bounds__(kSortThreads, 1) k_rank_sort(float* __restrict
 }
 
 // One thread per 8 pixels of a row (one 16-byte store of codes).  The valid pixels of a warp's 256 pixels (about 13 at 5 %)
-// are queued in shared memory and searched one per lane -- every lane runs at most a few binary searches, all lanes at
-// once, instead of every lane walking its eight pixels in turn while the others wait.
+// are queued in shared memory and searched one per lane: the searches are chains of dependent loads from the dictionary,
+// so what counts is how many run side by side -- not every lane walking its own eight pixels in turn.  The kernel keeps
+// its shared memory small (8 KB per block) on purpose: the 86 KB dictionary of the frame the SM is working on then stays
+// in L1 (a 32 KB-per-block variant that pushed it out to L2 was 50 % slower).
+constexpr int kEncOct = 1;  // octets per thread
 __global__ void __launch_bounds__(256) k_rank_encode(const float* __restrict__ in, size_t in_pitch, size_t in_fstride, int rows, int cols,
                                                      int vec_ok, const float* __restrict__ lut, const int* __restrict__ lut_count,
                                                      uint16_t* __restrict__ codes, size_t code_pitch) {
-    __shared__ float s_val[8][256];                     // queue of the warp: inverted values of its valid pixels ...
-    __shared__ uint16_t s_slot[8][256];                 // ... and which of its 256 pixels each one is
-    __shared__ __align__(16) uint16_t s_code[8][256];   // codes of the warp's 256 pixels: [lane * 8 + j]
+    __shared__ uint16_t s_slot[8][256];                 // queue of the warp: which of its 256 pixels are valid
+    __shared__ __align__(16) uint16_t s_code[8][256];   // codes of the warp's pixels: [lane * 8 + j]
     const int q = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y, f = blockIdx.z, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int count = min(lut_count[f], kRankMaxValid);  // (frames past the capacity are flagged and redone: any code will do)
     const float* d = lut + (size_t)f * kRankMaxValid;
-    float iv[8];
+    const float* row = in + (size_t)f * in_fstride + (size_t)r * in_pitch;
+    uint16_t* sc = s_code[warp];
+    uint16_t* ss = s_slot[warp];
     uint32_t m = 0u, inside = 0u;
     if (q * 8 < cols) {
-        const float* src = in + (size_t)f * in_fstride + (size_t)r * in_pitch + q * 8;
+        const float* src = row + q * 8;
         float v[8];
         if (vec_ok && q * 8 + 8 <= cols) {
             const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src) + 1);
@@ -149,16 +184,15 @@ __global__ void __launch_bounds__(256) k_rank_encode(const float* __restrict__ i
             }
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-            if (rank_valid(v[j], iv[j])) m |= 1u << j;
+        for (int j = 0; j < 8; ++j) {
+            float inv;
+            if (rank_valid(v[j], inv)) m |= 1u << j;
+        }
         m &= inside;
     }
     // holes: 1, beyond the last column: 0 (padding of the code plane, never read as image); valid ones are overwritten below
-    uint16_t* sc = s_code[warp];
-    float* sv = s_val[warp];
 #pragma unroll
     for (int j = 0; j < 8; ++j) sc[lane * 8 + j] = (uint16_t)((inside >> j) & 1u);
-    // queue: (value, slot) of every valid pixel of the warp
     const int n = __popc(m);
     int incl = n;
 #pragma unroll
@@ -167,29 +201,26 @@ __global__ void __launch_bounds__(256) k_rank_encode(const float* __restrict__ i
         if (lane >= s) incl += t;
     }
     const int total = __shfl_sync(0xffffffffu, incl, 31);
-    uint16_t* ss = s_slot[warp];
     int at = incl - n;
 #pragma unroll
     for (int j = 0; j < 8; ++j)
-        if ((m >> j) & 1u) {
-            sv[at] = iv[j];
-            ss[at] = (uint16_t)(lane * 8 + j);
-            ++at;
-        }
+        if ((m >> j) & 1u) ss[at++] = (uint16_t)(lane * 8 + j);
     __syncwarp();
+    const int px0 = (q - lane) * 8;  // first pixel of the warp in the row
     for (int k = lane; k < total; k += 32) {
-        const float inv = sv[k];
+        const int slot = ss[k];
+        const float inv = __fsub_rn(kMaxDepth, __ldg(row + px0 + slot));  // the pixel again (L1): cheaper than queueing the value
         int lo = 0, hi = count;  // first index with d[index] >= inv
         while (lo < hi) {
             const int mid = (lo + hi) >> 1;
             if (__ldg(d + mid) < inv) lo = mid + 1;
             else hi = mid;
         }
-        sc[ss[k]] = (uint16_t)(kRankFirstCode + lo);
+        sc[slot] = (uint16_t)(kRankFirstCode + lo);
     }
     __syncwarp();
     if (q * 8 < cols) {
-        uint16_t* o = codes + ((size_t)f * rows + r) * code_pitch + q * 8;
+        uint16_t* o = codes + ((size_t)f * rows + r) * code_pitch + (size_t)q * 8;
         *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(sc + lane * 8);
     }
 }
@@ -209,7 +240,7 @@ cudaError_t rank_build(const float* in, size_t in_pitch, size_t in_fstride, int 
     DCMT_LAUNCH(k_rank_compact, dim3(((cols + 7) / 8 + 255) / 256, rows, n_frames), dim3(256), 0, st, in, in_pitch, in_fstride, rows, cols, vec_ok,
                 lut, lut_count, ctr);
     DCMT_LAUNCH(k_rank_sort, dim3(n_frames), dim3(kSortThreads), kRankMaxValid * sizeof(uint32_t), st, lut, lut_count, ctr);
-    DCMT_LAUNCH(k_rank_encode, dim3(((cols + 7) / 8 + 255) / 256, rows, n_frames), dim3(256), 0, st, in, in_pitch, in_fstride, rows, cols,
+    DCMT_LAUNCH(k_rank_encode, dim3(((cols + 7) / 8 + 256 * kEncOct - 1) / (256 * kEncOct), rows, n_frames), dim3(256), 0, st, in, in_pitch, in_fstride, rows, cols,
                 vec_ok, lut, lut_count, codes, code_pitch);
     return cudaGetLastError();
 }

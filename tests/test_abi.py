@@ -109,3 +109,71 @@ def test_raw_mat_file_roundtrip(tmp_path):
         assert list(hdr[:2]) == [a.shape[0], a.shape[1]] and hdr[3] == want_type and hdr[5] == a.nbytes
         b = api.read_M(f)
         assert b.dtype == a.dtype and np.array_equal(a, b)
+
+
+# ---- the multi-device host entry points (SURVEY 8e for a C-ABI caller): one call, frames split over the listed GPUs ---------
+@pytest.mark.gpu
+def test_host_multi_entry_points(gpu_lib):
+    """dcmt_img_completion_{f32,u16}_host_multi: same bytes as the single-device call, for an explicit device list, for
+    `all visible devices`, with more devices than frames, and with a non-q8 frame in the batch (redo on the device that
+    served it).  Runs on one GPU (the list [0]); uses every GPU of the box when there are several."""
+    import torch
+
+    from depth_completion_mt_b200 import api, synth
+    from oracle import c_oracle as co
+
+    n_dev = torch.cuda.device_count()
+    rows, cols = 97, 171
+    d16 = np.stack([synth.sparse_depth_q8(600 + f, rows, cols, 0.05) for f in range(7)])
+    s = d16.astype(np.float32) / np.float32(256)
+    s[3] = synth.sparse_depth_float(603, rows, cols, 0.05)  # not strict q8: dictionary path, on whichever device got frame 3
+    want = np.stack([co.img_completion(f, "none") for f in s])
+    want16 = np.stack([co.img_completion(f.astype(np.float32) / np.float32(256), "none") for f in d16])
+    for devices in ([0], "all", list(range(n_dev))[::-1]):
+        got, st = api.img_completion(s, False, "none", devices=devices, return_stats=True, lib=gpu_lib)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), f"f32 multi {devices}"
+        assert [int(v) for v in st[:, 3]] == [1, 1, 1, 2, 1, 1, 1]
+        got = api.img_completion(d16, False, "none", devices=devices, lib=gpu_lib)
+        assert np.array_equal(got.view(np.uint32), want16.view(np.uint32)), f"u16 multi {devices}"
+    assert torch.cuda.current_device() == 0  # the caller's device is restored
+    # argument errors: an ordinal out of range, a repeated ordinal
+    import ctypes as C
+
+    out = np.empty_like(s)
+    for bad in ([n_dev], [0, 0]):
+        arr = (C.c_int * len(bad))(*bad)
+        rc = gpu_lib.dcmt_img_completion_f32_host_multi(s.ctypes.data, out.ctypes.data, rows, cols, 0, 0, len(s), 0, 0, None, arr, len(bad))
+        assert rc == _lib.DCMT_E_BADARG, bad
+    # the copy-only ceiling leg echoes the input
+    echo = np.zeros_like(s)
+    gpu_lib.check(gpu_lib.dcmt_debug_host_copy_f32(s.ctypes.data, echo.ctypes.data, rows, cols, len(s), None, 0))
+    assert np.array_equal(echo, s)
+
+
+def test_host_multi_rejects_bad_device_lists_without_gpu(product_lib):
+    """argument validation happens before any device work"""
+    import ctypes as C
+
+    s = np.zeros((2, 8, 8), np.float32)
+    out = np.empty_like(s)
+    rc = product_lib.dcmt_img_completion_f32_host_multi(s.ctypes.data, out.ctypes.data, 8, 8, 0, 0, 2, 0, 0, None, (C.c_int * 1)(0), 0)
+    assert rc in (_lib.DCMT_E_BADARG, _lib.DCMT_E_CUDA)
+
+
+def test_host_multi_on_emulator(emu_lib):
+    """the lane / redo logic of the multi-device host driver (one emulated device): same bytes as the plain host call,
+    incl. a frame that falls through strict q8 -> dictionary and one that falls through to the generic pipeline"""
+    from depth_completion_mt_b200 import api, synth
+    from oracle import c_oracle as co
+
+    rows, cols = 64, 96
+    s = np.stack([synth.sparse_depth(700 + f, rows, cols, 0.05) for f in range(4)])
+    s[1] = synth.sparse_depth_float(701, rows, cols, 0.05)
+    s[2] = synth.sparse_depth_float(702, rows, cols, 0.05)
+    s[2, 5, 5] = np.nan  # outside the parity domain: must still be routed to the generic pipeline, not crash
+    got, st = api.img_completion(s, False, "none", devices=[0], return_stats=True, lib=emu_lib)
+    assert [int(v) for v in st[:, 3]] == [1, 2, 0, 1]
+    for f in (0, 1, 3):
+        assert np.array_equal(got[f].view(np.uint32), co.img_completion(s[f], "none").view(np.uint32)), f
+    plain = api.img_completion(s, False, "none", lib=emu_lib)
+    assert np.array_equal(got.view(np.uint32), plain.view(np.uint32))
