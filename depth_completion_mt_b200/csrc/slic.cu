@@ -136,8 +136,11 @@ __global__ void __launch_bounds__(256) k_slic_assign(const uint8_t* __restrict__
     // global memory: the kernel was bound by that latency, 18 % issue-active)
     constexpr int kCap = 96;
     __shared__ double s_cent[kCap][5];
-    __shared__ double s_hi[kCap][2];  // cx + step, cy + step: the window's open upper ends (:123-124)
-    __shared__ int s_lo[kCap][2];     // (int)(cx - step), (int)(cy - step): its first column / row
+    // the window of a centre (:123-124: `for (int k = cx - step; k < cx + step; k++)`, truncation towards zero, then a double
+    // comparison) as integers: first column / row lo = (int)(c - step), and -- for integer k -- k < c + step <=> k < ceil(c + step);
+    // stored as {lo_x, ceil_x - lo_x, lo_y, ceil_y - lo_y} so that a pixel tests (unsigned)(x - lo) < width: one 16-byte load,
+    // two subtractions, two compares per candidate instead of four double compares
+    __shared__ int4 s_win[kCap];
     __shared__ int s_idx[kCap];
     __shared__ unsigned s_sum[kCap][6];  // per-tile sums of L, a, b, x, y, count for the staged centres
     __shared__ int s_n;
@@ -172,11 +175,9 @@ __global__ void __launch_bounds__(256) k_slic_assign(const uint8_t* __restrict__
                     double ce[5];
                     for (int q = 0; q < 5; ++q) ce[q] = sorted[(size_t)k * 5 + q];
                     for (int q = 0; q < 5; ++q) s_cent[pos][q] = ce[q];
-                    // for (int k = cx - step; k < cx + step; k++) (:123): truncation towards zero, then a double comparison
-                    s_lo[pos][0] = (int)__dsub_rn(ce[3], (double)step);
-                    s_lo[pos][1] = (int)__dsub_rn(ce[4], (double)step);
-                    s_hi[pos][0] = __dadd_rn(ce[3], (double)step);
-                    s_hi[pos][1] = __dadd_rn(ce[4], (double)step);
+                    const int lox = (int)__dsub_rn(ce[3], (double)step), loy = (int)__dsub_rn(ce[4], (double)step);
+                    const int hix = (int)ceil(__dadd_rn(ce[3], (double)step)), hiy = (int)ceil(__dadd_rn(ce[4], (double)step));
+                    s_win[pos] = make_int4(lox, hix - lox, loy, hiy - loy);
                 }
             }
         }
@@ -205,7 +206,12 @@ __global__ void __launch_bounds__(256) k_slic_assign(const uint8_t* __restrict__
     };
     auto cheap = [&](const double* ce, int c, int slot) {
         const double cx = ce[3], cy = ce[4];
-        if (slot >= 0 ? (x < s_lo[slot][0] || !(xd < s_hi[slot][0]) || y < s_lo[slot][1] || !(yd < s_hi[slot][1])) : !covers(cx, cy)) return;
+        if (slot >= 0) {
+            const int4 w = s_win[slot];
+            if ((unsigned)(x - w.x) >= (unsigned)w.y || (unsigned)(y - w.z) >= (unsigned)w.w) return;
+        } else if (!covers(cx, cy)) {
+            return;
+        }
         const double d0 = ce[0] - L, d1 = ce[1] - A, d2 = ce[2] - B, dx = cx - xd, dy = cy - yd;
         const double q = (d0 * d0 + d1 * d1 + d2 * d2) * inv_nc2 + (dx * dx + dy * dy) * inv_ns2;
         if (q < q1 || (q == q1 && c < best_c)) { q2 = q1; q1 = q; best_c = c; best_i = slot; }
@@ -227,7 +233,12 @@ __global__ void __launch_bounds__(256) k_slic_assign(const uint8_t* __restrict__
         best_i = -1;
         auto exact = [&](const double* ce, int c, int slot) {
             const double cx = ce[3], cy = ce[4];
-            if (slot >= 0 ? (x < s_lo[slot][0] || !(xd < s_hi[slot][0]) || y < s_lo[slot][1] || !(yd < s_hi[slot][1])) : !covers(cx, cy)) return;
+            if (slot >= 0) {
+                const int4 w = s_win[slot];
+                if ((unsigned)(x - w.x) >= (unsigned)w.y || (unsigned)(y - w.z) >= (unsigned)w.w) return;
+            } else if (!covers(cx, cy)) {
+                return;
+            }
             const double dc = __dsqrt_rn(__dadd_rn(__dadd_rn(sq(__dsub_rn(ce[0], L)), sq(__dsub_rn(ce[1], A))), sq(__dsub_rn(ce[2], B))));
             const double ds = __dsqrt_rn(__dadd_rn(sq(__dsub_rn(cx, (double)x)), sq(__dsub_rn(cy, (double)y))));
             const double d = __dsqrt_rn(__dadd_rn(sq(__ddiv_rn(dc, (double)nc)), sq(__ddiv_rn(ds, (double)step))));  // ns = step (:105)

@@ -26,6 +26,8 @@ struct alignas(16) float4 { float x, y, z, w; };
 struct uint2 { unsigned x, y; };
 struct int2 { int x, y; };
 struct alignas(16) uint4 { unsigned x, y, z, w; };
+struct alignas(16) int4 { int x, y, z, w; };
+static inline int4 make_int4(int a, int b, int c, int d) { return int4{a, b, c, d}; }
 struct ushort2 { unsigned short x, y; };
 struct alignas(8) ushort4 { unsigned short x, y, z, w; };
 static inline float4 make_float4(float a, float b, float c, float d) { return float4{a, b, c, d}; }
