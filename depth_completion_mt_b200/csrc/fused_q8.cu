@@ -1097,6 +1097,7 @@ struct TailArgs {
     int one;          // the constant 1, opaque to the compiler (see other_of_pair)
     int use_tma;      // tile load by one TMA box copy (else 16-byte cp.async per thread)
     ItemsDesc i_load, i_vert, i_scan, i_scanw, i_med, i_gauss;  // row lengths RQ, pitchw, SQ, 4 SQ, MI, NP
+    ItemsDesc i_vert2; // row length pitchw / 2: pairs of word columns (vertical maxima)
     ItemsDesc i_medr;  // row length tw / 2 + 2: one item = one word column x med_len rows (shared-work median)
     int med_len, med_segs;
     uint32_t e_hundred;  // code of the constant 100.0: E_HUNDRED (strict q8), kRankHundred (dictionary codes)
@@ -1294,20 +1295,28 @@ __global__ void __launch_bounds__(QTT, DCMT_TAIL_CTAS) k_q8_tail(TailArgs a, con
     //      running prefix maximum of the next 15 rows completes every window.  No intermediate planes, one barrier.
     {
         const int NB = (TV + th + 4 + 15) / 16;  // vertical maxima are needed for rows [0, TV + th + 4)
-        for (Items i(a.i_vert); i.r < NB; i.next()) {
+        // one item = TWO adjacent word columns x one block (8-byte accesses): the phase is bound by shared-memory
+        // instructions and latency, and 50 x 8 items fit the CTA's threads in one round where 100 x 8 took two
+        for (Items i(a.i_vert2); i.r < NB; i.next()) {
             const int r0 = 16 * i.r;
-            const uint32_t* p = A + r0 * pitchw + i.q;
-            uint32_t* o = B + r0 * pitchw + i.q;
-            uint32_t sfx[16];
-            sfx[15] = p[15 * pitchw];
+            const uint32_t* p = A + r0 * pitchw + 2 * i.q;
+            uint32_t* o = B + r0 * pitchw + 2 * i.q;
+            uint2 sfx[16];
+            sfx[15] = lds2(p + 15 * pitchw);
 #pragma unroll
-            for (int k = 14; k >= 0; --k) sfx[k] = pmax(p[k * pitchw], sfx[k + 1]);
-            o[0] = sfx[0];
-            uint32_t m = 0u;
+            for (int k = 14; k >= 0; --k) {
+                const uint2 v = lds2(p + k * pitchw);
+                sfx[k] = make_uint2(pmax(v.x, sfx[k + 1].x), pmax(v.y, sfx[k + 1].y));
+            }
+            sts2(o, sfx[0]);
+            uint2 m = make_uint2(0u, 0u);
 #pragma unroll
             for (int j = 1; j < 16; ++j) {
-                if (r0 + 15 + j < RH) m = pmax(m, p[(15 + j) * pitchw]);  // rows past the region are absent
-                o[j * pitchw] = pmax(sfx[j], m);
+                if (r0 + 15 + j < RH) {  // rows past the region are absent
+                    const uint2 v = lds2(p + (15 + j) * pitchw);
+                    m = make_uint2(pmax(m.x, v.x), pmax(m.y, v.y));
+                }
+                sts2(o + j * pitchw, make_uint2(pmax(sfx[j].x, m.x), pmax(sfx[j].y, m.y)));
             }
         }
     }
@@ -1932,7 +1941,7 @@ cudaError_t q8_run_tail(const Q8Plan& p, float* out, size_t out_pitch, size_t ou
     TailArgs a{p.mid, (size_t)p.mid_pitch, (size_t)p.mid_pitch * p.rows, p.col_first, p.col_last, p.ctr, out, out_pitch,
                out_fstride, p.rows, p.cols, p.th, p.tw, blur, vec2, 1, use_tma,
                make_items(RQ, QTT), make_items(RQ * 4, QTT), make_items(SQ, QTT), make_items(SQ * 4, QTT), make_items(MI, QTT),
-               make_items(NP, QTT), make_items(NW, QTT), med_len, med_segs, p.lut ? kRankHundred : E_HUNDRED, p.lut, p.prof_tail};
+               make_items(NP, QTT), make_items(RQ * 2, QTT), make_items(NW, QTT), med_len, med_segs, p.lut ? kRankHundred : E_HUNDRED, p.lut, p.prof_tail};
     const dim3 grid((p.cols + p.tw - 1) / p.tw, (p.rows + p.th - 1) / p.th, n_frames);
     if (p.lut) DCMT_LAUNCH(k_q8_tail<true>, grid, dim3(QTT), q8_tail_smem(p.th, p.tw), st, a, tmap);
     else DCMT_LAUNCH(k_q8_tail<false>, grid, dim3(QTT), q8_tail_smem(p.th, p.tw), st, a, tmap);
