@@ -306,6 +306,166 @@ __global__ void __launch_bounds__(256) k_slic_assign(const uint8_t* __restrict__
         }
 }
 
+// ---- assignment over BANDS of rows with the whole frame's centres in shared memory ---------------------------------------
+// k_slic_assign stages the candidate centres of every 16 x 16 tile from global memory (offset -> item -> centre, dependent
+// loads) between two barriers: at 1 200 centres per frame it ran at 40 % issue-active, stalled on those loads.  A frame's
+// centres are small (K x 5 doubles = 48 KB at KITTI size): here a CTA copies ALL of them -- in bin order, with their integer
+// windows and the bin offsets -- into shared memory once and then streams the pixels of a band of rows through them; a pixel
+// reads the 3 x 3 bins around it straight from shared memory.  Same arithmetic, same tie rule, same labels and sums.
+constexpr int kBandThreads = 512;
+
+struct BandSmem {  // layout of the dynamic shared memory for K centres and NB bins
+    size_t off_cent, off_win, off_sum, off_idx, off_bin, total;
+};
+static inline BandSmem band_smem(int K, int NB) {
+    BandSmem b;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { const size_t at = o; o = (o + bytes + 15) & ~size_t(15); return at; };  // 16-byte aligned parts
+    b.off_cent = take((size_t)K * 5 * sizeof(double));
+    b.off_win = take((size_t)K * sizeof(int4));
+    b.off_sum = take((size_t)K * 6 * sizeof(unsigned));
+    b.off_idx = take((size_t)K * sizeof(int));
+    b.off_bin = take((size_t)(NB + 1) * sizeof(int));
+    b.total = o;
+    return b;
+}
+
+__global__ void __launch_bounds__(kBandThreads) k_slic_assign_band(const uint8_t* __restrict__ lab, int rows, int cols, int step, int nc,
+                                                                    int bx, int by, uint32_t step_magic, int band_rows,
+                                                                    const int* __restrict__ offset, const int* __restrict__ items,
+                                                                    const double* __restrict__ sorted, int32_t* __restrict__ labels,
+                                                                    unsigned long long* __restrict__ sums, int n_centers, double inv_nc2,
+                                                                    double inv_ns2, BandSmem lay) {
+    DCMT_DYN_SMEM(unsigned char, smem);
+    double* s_cent = reinterpret_cast<double*>(smem + lay.off_cent);   // [k][5], bin order
+    int4* s_win = reinterpret_cast<int4*>(smem + lay.off_win);         // {lo_x, width_x, lo_y, width_y}
+    unsigned* s_sum = reinterpret_cast<unsigned*>(smem + lay.off_sum);  // [k][6]
+    int* s_idx = reinterpret_cast<int*>(smem + lay.off_idx);            // original centre index (tie rule, labels)
+    int* s_bin = reinterpret_cast<int*>(smem + lay.off_bin);            // exclusive offsets, nbins + 1
+    const int nbins = bx * by;
+    {  // frame
+        const size_t f = blockIdx.y;
+        lab += f * rows * cols * 3;
+        labels += f * rows * cols;
+        sums += f * n_centers * 6;
+        offset += f * (nbins + 1);
+        items += f * n_centers;
+        sorted += f * n_centers * 5;
+    }
+    const int tid = threadIdx.x;
+    for (int b = tid; b <= nbins; b += kBandThreads) s_bin[b] = offset[b];
+    __syncthreads();
+    const int n_binned = s_bin[nbins];  // centres that are not NaN
+    for (int i = tid; i < n_binned * 5; i += kBandThreads) s_cent[i] = sorted[i];
+    for (int i = tid; i < n_binned * 6; i += kBandThreads) s_sum[i] = 0u;
+    for (int k = tid; k < n_binned; k += kBandThreads) {
+        s_idx[k] = items[k];
+        const double cx = sorted[(size_t)k * 5 + 3], cy = sorted[(size_t)k * 5 + 4];
+        // for (int k = cx - step; k < cx + step; k++) (:123): truncation towards zero, then a double comparison; for integer k,
+        // k < c + step <=> k < ceil(c + step)
+        const int lox = (int)__dsub_rn(cx, (double)step), loy = (int)__dsub_rn(cy, (double)step);
+        const int hix = (int)ceil(__dadd_rn(cx, (double)step)), hiy = (int)ceil(__dadd_rn(cy, (double)step));
+        s_win[k] = make_int4(lox, hix - lox, loy, hiy - loy);
+    }
+    __syncthreads();
+    const int y_begin = blockIdx.x * band_rows, y_end = min(rows, y_begin + band_rows);
+    const int n_px = (y_end - y_begin) * cols;
+    const int lane = tid & 31;
+    // whole warps walk the band (32 consecutive pixels of the row-major order), so that the warp collectives below are uniform
+    // pixel tid, tid + 512, ... of the band in row-major order, walked without a division per pixel
+    const int step_y = kBandThreads / cols, step_x = kBandThreads - step_y * cols;
+    int wy = tid / cols, wx = tid - wy * cols;
+    for (int base = (tid & ~31); base < n_px; base += kBandThreads) {
+        const bool live = base + lane < n_px;
+        const int x = live ? wx : 0, y = y_begin + (live ? wy : 0);
+        wx += step_x;
+        wy += step_y;
+        if (wx >= cols) { wx -= cols; ++wy; }
+        const uint8_t* p = lab + ((size_t)y * cols + x) * 3;
+        const double L = p[0], A = p[1], B = p[2];
+        const int pbx = min(fast_div(x, step_magic), bx - 1), pby = min(fast_div(y, step_magic), by - 1);
+        const int gy_lo = max(pby - 1, 0), gy_hi = min(pby + 1, by - 1), gx_lo = max(pbx - 1, 0), gx_hi = min(pbx + 1, bx - 1);
+        const double xd = (double)x, yd = (double)y;
+        // stage 1: the square-root- and division-free stand-in for compute_dist (see k_slic_assign); stage 2 for near ties
+        double q1 = 1.0e300, q2 = 1.0e300;
+        int best_c = -1, best_k = -1;
+        if (live) {
+            for (int gy = gy_lo; gy <= gy_hi; ++gy) {
+                const int k0 = s_bin[gy * bx + gx_lo], k1 = s_bin[gy * bx + gx_hi + 1];  // bins of a row are contiguous
+                for (int k = k0; k < k1; ++k) {
+                    const int4 w = s_win[k];
+                    if ((unsigned)(x - w.x) >= (unsigned)w.y || (unsigned)(y - w.z) >= (unsigned)w.w) continue;
+                    const double* ce = s_cent + (size_t)k * 5;
+                    const double d0 = ce[0] - L, d1 = ce[1] - A, d2 = ce[2] - B, dx = ce[3] - xd, dy = ce[4] - yd;
+                    const double q = (d0 * d0 + d1 * d1 + d2 * d2) * inv_nc2 + (dx * dx + dy * dy) * inv_ns2;
+                    const int c = s_idx[k];
+                    if (q < q1 || (q == q1 && c < best_c)) { q2 = q1; q1 = q; best_c = c; best_k = k; }
+                    else if (q < q2) q2 = q;
+                }
+            }
+            if (best_c >= 0 && !(q2 > q1 * (1.0 + 1.0e-12))) {
+                // too close to call: the reference's own arithmetic decides (compute_dist :61-69, strict <, lowest index)
+                double best = (double)FLT_MAX;  // :117
+                best_c = -1;
+                best_k = -1;
+                for (int gy = gy_lo; gy <= gy_hi; ++gy) {
+                    const int k0 = s_bin[gy * bx + gx_lo], k1 = s_bin[gy * bx + gx_hi + 1];
+                    for (int k = k0; k < k1; ++k) {
+                        const int4 w = s_win[k];
+                        if ((unsigned)(x - w.x) >= (unsigned)w.y || (unsigned)(y - w.z) >= (unsigned)w.w) continue;
+                        const double* ce = s_cent + (size_t)k * 5;
+                        const double dc = __dsqrt_rn(__dadd_rn(__dadd_rn(sq(__dsub_rn(ce[0], L)), sq(__dsub_rn(ce[1], A))), sq(__dsub_rn(ce[2], B))));
+                        const double ds = __dsqrt_rn(__dadd_rn(sq(__dsub_rn(ce[3], (double)x)), sq(__dsub_rn(ce[4], (double)y))));
+                        const double d = __dsqrt_rn(__dadd_rn(sq(__ddiv_rn(dc, (double)nc)), sq(__ddiv_rn(ds, (double)step))));  // ns = step (:105)
+                        const int c = s_idx[k];
+                        if (d < best || (d == best && best_c >= 0 && c < best_c)) { best = d; best_c = c; best_k = k; }
+                    }
+                }
+            }
+        }
+        int label = -1;
+        if (live) {
+            label = labels[(size_t)y * cols + x];
+            if (best_c >= 0) {
+                label = best_c;
+                labels[(size_t)y * cols + x] = label;
+            }
+        }
+        // centre sums (integers: exact in any order): per distinct winner of the warp one hardware reduction and one lane adding
+        // into the CTA's shared-memory sums; pixels that keep a stale label (no window covers them) add to global memory directly
+        const int key = (live && best_c >= 0) ? best_k : -1;
+        unsigned todo = __ballot_sync(0xffffffffu, key >= 0);
+        while (todo) {
+            const int leader = __ffs((int)todo) - 1;
+            const int kk = __shfl_sync(0xffffffffu, key, leader);
+            const bool mine = key == kk;
+            const unsigned v0 = __reduce_add_sync(0xffffffffu, mine ? (unsigned)p[0] : 0u), v1 = __reduce_add_sync(0xffffffffu, mine ? (unsigned)p[1] : 0u),
+                           v2 = __reduce_add_sync(0xffffffffu, mine ? (unsigned)p[2] : 0u), v3 = __reduce_add_sync(0xffffffffu, mine ? (unsigned)x : 0u),
+                           v4 = __reduce_add_sync(0xffffffffu, mine ? (unsigned)y : 0u), v5 = __reduce_add_sync(0xffffffffu, mine ? 1u : 0u);
+            if (lane == leader) {
+                unsigned* sg = s_sum + (size_t)kk * 6;
+                atomicAdd(sg + 0, v0); atomicAdd(sg + 1, v1); atomicAdd(sg + 2, v2);
+                atomicAdd(sg + 3, v3); atomicAdd(sg + 4, v4); atomicAdd(sg + 5, v5);
+            }
+            todo &= ~__ballot_sync(0xffffffffu, mine);
+        }
+        if (live && label != -1 && key < 0) {
+            unsigned long long* sg = sums + (size_t)label * 6;
+            atomicAdd(sg + 0, (unsigned long long)p[0]);
+            atomicAdd(sg + 1, (unsigned long long)p[1]);
+            atomicAdd(sg + 2, (unsigned long long)p[2]);
+            atomicAdd(sg + 3, (unsigned long long)x);
+            atomicAdd(sg + 4, (unsigned long long)y);
+            atomicAdd(sg + 5, 1ull);
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < n_binned * 6; i += kBandThreads) {
+        const unsigned v = s_sum[i];
+        if (v) atomicAdd(sums + (size_t)s_idx[i / 6] * 6 + (i % 6), (unsigned long long)v);
+    }
+}
+
 __global__ void k_slic_update(const unsigned long long* __restrict__ sums, int n, double* __restrict__ centers) {  // :166-172
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n) return;
@@ -347,12 +507,34 @@ cudaError_t slic_run(const uint8_t* lab, int rows, int cols, int n_frames, int s
     DCMT_LAUNCH(k_slic_fill_labels, dim3((unsigned)((npx + 255) / 256)), dim3(256), 0, st, labels, npx);
     if (n_centers == 0 || n_frames == 0) return cudaGetLastError();
     DCMT_LAUNCH(k_slic_init, dim3(cb, n_frames), dim3(128), 0, st, lab, rows, cols, step, ny, n_centers, w.centers);
+    // assignment kernel: bands of rows with the frame's centres in shared memory when they fit (two CTAs per SM), else tiles
+    const BandSmem lay = band_smem(n_centers, w.bins_x * w.bins_y);
+    const bool bands_fit = lay.total <= (size_t)110 * 1024;
+    int n_bands = 1, band_rows = rows;
+    if (bands_fit) {
+        // enough CTAs to fill the chip twice, but bands of at least 32 rows (every CTA copies the whole frame's centres)
+        n_bands = (2 * 148 + n_frames - 1) / n_frames;
+        if (n_bands > rows / 32) n_bands = rows / 32;
+        if (n_bands < 1) n_bands = 1;
+        band_rows = (rows + n_bands - 1) / n_bands;
+        // a CTA sums coordinates in 32 bits: band pixels x largest coordinate must stay below 2^32
+        while (band_rows > 1 && (unsigned long long)band_rows * cols * (rows > cols ? rows : cols) >= (1ull << 32)) band_rows = (band_rows + 1) / 2;
+        n_bands = (rows + band_rows - 1) / band_rows;
+        cudaError_t e = cudaFuncSetAttribute(k_slic_assign_band, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+        if (e != cudaSuccess) return e;
+    }
+    const uint32_t step_magic = (uint32_t)((1ull << 32) / (unsigned)step) + 1u;
     for (int it = 0; it < iterations; ++it) {
         DCMT_LAUNCH(k_slic_prepare, dim3(n_frames), dim3(kScanThreads), 0, st, w.centers, w.sums, n_centers, step, w.bins_x, w.bins_y,
                     w.bin_count, w.bin_fill, w.bin_items, w.sorted, it > 0 ? 1 : 0);
-        DCMT_LAUNCH(k_slic_assign, dim3((cols + 15) / 16, (rows + 15) / 16, n_frames), dim3(16, 16), 0, st, lab, rows, cols, step, nc,
-                    w.bins_x, w.bins_y, w.centers, w.bin_count, w.bin_items, w.sorted, labels, w.sums, n_centers,
-                    1.0 / ((double)nc * (double)nc), 1.0 / ((double)step * (double)step));
+        if (bands_fit)
+            DCMT_LAUNCH(k_slic_assign_band, dim3(n_bands, n_frames), dim3(kBandThreads), lay.total, st, lab, rows, cols, step, nc, w.bins_x,
+                        w.bins_y, step_magic, band_rows, w.bin_count, w.bin_items, w.sorted, labels, w.sums, n_centers,
+                        1.0 / ((double)nc * (double)nc), 1.0 / ((double)step * (double)step), lay);
+        else
+            DCMT_LAUNCH(k_slic_assign, dim3((cols + 15) / 16, (rows + 15) / 16, n_frames), dim3(16, 16), 0, st, lab, rows, cols, step, nc,
+                        w.bins_x, w.bins_y, w.centers, w.bin_count, w.bin_items, w.sorted, labels, w.sums, n_centers,
+                        1.0 / ((double)nc * (double)nc), 1.0 / ((double)step * (double)step));
     }
     if (iterations > 0) DCMT_LAUNCH(k_slic_update, dim3(cb, n_frames), dim3(128), 0, st, w.sums, n_centers, w.centers);
     return cudaGetLastError();

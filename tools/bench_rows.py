@@ -67,7 +67,14 @@ def main():
     pn = pts.cpu().numpy()
     cms = cpu_time(lambda: co.lidar_project(pn, synth.KITTI_T_VELO_TO_CAM, synth.KITTI_P_RECT_02, rows, cols))
     out.append({"row": "8f#2 LiDAR projection + normalize (main_sl.cpp:478-523)", "points": 120000, "ms": ms, "clouds_per_s": 1e3 / ms,
-                "cpu_oracle_ms_per_cloud": cms, "note": "5 small kernels per cloud: launch-latency bound at this size"})
+                "cpu_oracle_ms_per_cloud": cms, "note": "4 small kernels per cloud: launch-latency bound at this size"})
+    # ---- projection, batched: 128 clouds per call in the same four launches
+    nb = 128
+    clouds = torch.from_numpy(np.stack([synth.velodyne_cloud(f % 8, 120000) for f in range(nb)])).cuda()
+    ms = gpu_time(lambda: api.lidar_project_batch(clouds, None, synth.KITTI_T_VELO_TO_CAM, synth.KITTI_P_RECT_02, rows, cols, lib=lib), max(3, a.reps // 2))
+    out.append({"row": "8f#2 LiDAR projection + normalize, batch of 128 clouds (dcmt_lidar_project_batch_f32)", "points": 120000, "ms": ms,
+                "clouds_per_s": nb * 1e3 / ms})
+    del clouds
     # ---- SLIC: one frame, step 18, 10 iterations
     lab = torch.from_numpy(synth.lab_image(0, rows, cols)).cuda()
     ms = gpu_time(lambda: api.generate_superpixels(lab, 18, 50, lib=lib), a.reps)
@@ -89,6 +96,14 @@ def main():
     ms = gpu_time(chain, max(3, a.reps // 4))
     out.append({"row": "DC_lidar_camera chain: SLIC -> interpolate_with_superpixels -> evaluate_performance (main_lc.cpp:184-225)", "ms": ms,
                 "frames_per_s": 1e3 / ms})
+    sparse64 = torch.from_numpy(np.stack([synth.sparse_depth(f, rows, cols, 0.05) for f in range(8)])).cuda().repeat(8, 1, 1).contiguous()
+
+    def chain64():
+        labels = api.generate_superpixels(labs, 18, 50, lib=lib)
+        d = api.interpolate_with_superpixels(labels, sparse64, "gaussian", 1, n_clusters=k, lib=lib)
+        return api.evaluate(sparse64, d, "lidar_camera", lib=lib)
+    ms = gpu_time(chain64, 3)
+    out.append({"row": "DC_lidar_camera chain, batch of 64 frames", "ms": ms, "frames_per_s": 64e3 / ms})
     for o in out:
         print(json.dumps(o), flush=True)
 
