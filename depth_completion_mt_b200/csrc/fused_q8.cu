@@ -1083,7 +1083,7 @@ __global__ void k_q8_decode(const uint16_t* __restrict__ mid, size_t mid_pitch, 
 // ------------------------------------------------------------------------------------------------
 constexpr int TV = 19, TQ = 3;   // rows up/down, quads left/right
 constexpr int kRemCap = 256;     // words still holding a hole after the first fill that are resolved from the list (more: all scan words are visited)
-constexpr int kListCap = 3072;   // hole WORDS kept for the lazy horizontal fill; more than that: all words are processed
+constexpr int kListCap = 3072;   // hole quads kept for the lazy horizontal fill; more than that: all words are processed
 
 struct TailArgs {
     const uint16_t* mid;
@@ -1332,61 +1332,59 @@ __global__ void __launch_bounds__(QTT, DCMT_TAIL_CTAS) k_q8_tail(TailArgs a, con
         Items i(a.i_scan);
         constexpr int kScanRounds = 6;
         if (n <= kScanRounds * QTT) {
-            // All rounds of a warp first (independent loads), then ONE reservation per warp in the list.  The list holds
-            // WORDS (a quad with a hole usually has it in one or two of its four words): the fill below then runs with every
-            // lane on a word that needs it.  qv: quad index | 4-bit mask of its hole words << 16.
+            // all rounds of a warp first (independent loads and ballots), then ONE reservation per warp in the list
             uint32_t qv[kScanRounds];
-            int mine = 0;
+            unsigned bal[kScanRounds];
+            int total = 0;
 #pragma unroll
             for (int k = 0; k < kScanRounds; ++k) {
+                bool cand = false;
                 qv[k] = 0u;
                 if (k * QTT + (int)threadIdx.x < n) {
                     const int qidx = (sr0 + i.r) * RQ + sq0 + i.q;
                     const uint4 v = lds4(A + qidx * 4);
                     // some lane <= 1 (a hole, or absent outside the image)?
-                    if (pmin(pmin(pmin(v.x, v.y), pmin(v.z, v.w)), SPLAT16(2)) != SPLAT16(2)) {
-                        const uint32_t m4 = (hole_mask(v.x) ? 1u : 0u) | (hole_mask(v.y) ? 2u : 0u) | (hole_mask(v.z) ? 4u : 0u) | (hole_mask(v.w) ? 8u : 0u);
-                        qv[k] = (uint32_t)qidx | (m4 << 16);
-                        mine += __popc(m4);
-                    }
+                    cand = pmin(pmin(pmin(v.x, v.y), pmin(v.z, v.w)), SPLAT16(2)) != SPLAT16(2);
+                    qv[k] = (uint32_t)qidx | (cand ? 0x80000000u : 0u);
                 }
+                bal[k] = __ballot_sync(0xffffffffu, cand);
+                total += __popc(bal[k]);
                 i.next();
             }
-            const int lane = threadIdx.x & 31;
-            int incl = mine;
-#pragma unroll
-            for (int sft = 1; sft < 32; sft <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, incl, sft);
-                if (lane >= sft) incl += t;
-            }
-            const int total = __shfl_sync(0xffffffffu, incl, 31);
             if (total) {
                 int pos = 0;
-                if (lane == 0) pos = atomicAdd(&s_count, total);
-                pos = __shfl_sync(0xffffffffu, pos, 0) + incl - mine;
-                if (mine) {
+                if ((threadIdx.x & 31) == 0) pos = atomicAdd(&s_count, total);
+                pos = __shfl_sync(0xffffffffu, pos, 0);
+                const unsigned below = (1u << (threadIdx.x & 31)) - 1u;
 #pragma unroll
-                    for (int k = 0; k < kScanRounds; ++k) {
-                        uint32_t m4 = qv[k] >> 16;
-                        const uint32_t w0 = (qv[k] & 0xffffu) * 4u;
-                        while (m4) {
-                            const int j = __ffs((int)m4) - 1;
-                            m4 &= m4 - 1u;
-                            if (pos < kListCap) list[pos] = (uint16_t)(w0 + j);
-                            ++pos;
-                        }
-                    }
+                for (int k = 0; k < kScanRounds; ++k) {
+                    const int at = pos + __popc(bal[k] & below);
+                    if ((qv[k] & 0x80000000u) && at < kListCap) list[at] = (uint16_t)(qv[k] & 0xffffu);
+                    pos += __popc(bal[k]);
                 }
             }
         } else {
-            // (tiles with more scan quads than kScanRounds rounds cover: every word of the scan region is visited below)
-            if (threadIdx.x == 0) s_count = kListCap + 1;
+            for (int base = 0; base < n; base += QTT, i.next()) {
+                bool cand = false;
+                int qidx = 0;
+                if (base + (int)threadIdx.x < n) {
+                    qidx = (sr0 + i.r) * RQ + sq0 + i.q;
+                    const uint4 v = lds4(A + qidx * 4);
+                    cand = pmin(pmin(pmin(v.x, v.y), pmin(v.z, v.w)), SPLAT16(2)) != SPLAT16(2);
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, cand);
+                if (bal == 0u) continue;
+                int pos = 0;
+                if ((threadIdx.x & 31) == 0) pos = atomicAdd(&s_count, __popc(bal));
+                pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(bal & ((1u << (threadIdx.x & 31)) - 1u));
+                if (cand && pos < kListCap) list[pos] = (uint16_t)qidx;
+            }
         }
     }
     __syncthreads();
     DCMT_STAMP(a, 4);
     int holes_core = 0, left_core = 0;
-    const int n_words = s_count;
+    const int n_quads = s_count;
     auto fill_word = [&](int widx) {
         const uint32_t d = A[widx], hm = hole_mask(d);
         if (hm == 0u) return;
@@ -1403,9 +1401,9 @@ __global__ void __launch_bounds__(QTT, DCMT_TAIL_CTAS) k_q8_tail(TailArgs a, con
             if (pos < kRemCap) s_rem_list[pos] = (uint16_t)widx;
         }
     };
-    if (n_words <= kListCap) {
-        for (int k = threadIdx.x; k < n_words; k += QTT) fill_word(list[k]);
-    } else {  // more hole words than the list holds (or a tile too large for the scan rounds): every scan word is visited
+    if (n_quads <= kListCap) {
+        for (int k = threadIdx.x; k < 4 * n_quads; k += QTT) fill_word(list[k >> 2] * 4 + (k & 3));
+    } else {  // cannot happen for tiles up to 96 x 160 (2184 scan quads); kept for larger tiles
         for (Items i(a.i_scanw); i.r < SH; i.next()) fill_word((sr0 + i.r) * pitchw + sq0 * 4 + i.q);
     }
     if (holes_core) atomicAdd(&s_holes_core, holes_core);

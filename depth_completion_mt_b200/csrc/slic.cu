@@ -13,6 +13,8 @@
 // create_connectivity (:186-260) writes only its local `new_clusters`, never `clusters`: nothing to do.
 #include "slic.cuh"
 
+#include <cstdlib>
+
 namespace dcmt {
 namespace {
 
@@ -509,7 +511,10 @@ cudaError_t slic_run(const uint8_t* lab, int rows, int cols, int n_frames, int s
     DCMT_LAUNCH(k_slic_init, dim3(cb, n_frames), dim3(128), 0, st, lab, rows, cols, step, ny, n_centers, w.centers);
     // assignment kernel: bands of rows with the frame's centres in shared memory when they fit (two CTAs per SM), else tiles
     const BandSmem lay = band_smem(n_centers, w.bins_x * w.bins_y);
-    const bool bands_fit = lay.total <= (size_t)110 * 1024;
+    // measured on the B200 (step 18, 1 200 centres): bands win for batches (3.7 k frames/s against 3.0 k at 256 frames) and lose for a
+    // handful of frames (a band is a long serial walk: 11 CTAs cannot fill the chip), so small batches keep the tile kernel
+    static const int band_min = [] { const char* e = getenv("DCMT_SLIC_BAND_MIN_FRAMES"); return e ? atoi(e) : 32; }();
+    const bool bands_fit = lay.total <= (size_t)110 * 1024 && n_frames >= band_min;
     int n_bands = 1, band_rows = rows;
     if (bands_fit) {
         // enough CTAs to fill the chip twice, but bands of at least 32 rows (every CTA copies the whole frame's centres)
