@@ -21,7 +21,7 @@ seed = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 rng = np.random.default_rng(seed)
 lib = _lib.load()
 t_end = time.time() + secs
-n = ng = nr = ns = 0
+n = ng = nr = ns = nf = 0
 while time.time() < t_end:
     rows = int(rng.integers(32, 420))
     cols = int(rng.integers(32, 1400))
@@ -54,6 +54,26 @@ while time.time() < t_end:
             print(f"MISMATCH vs reference build rows={rows} cols={cols} p={p} blur={blur} seed={fseed}", flush=True)
             sys.exit(1)
         nr += 1
+    if rng.random() < 0.4:  # arbitrary float frames: the per-frame dictionary path of the fused kernels, bit-exact with blur none
+        hi = float(rng.choice([5.0, 50.0, 90.0, 99.95, 140.0]))
+        f = synth.sparse_depth_float(fseed, rows, cols, min(p, 0.07), hi=hi)
+        if rng.random() < 0.3:
+            ys, xs = rng.integers(0, rows, 30), rng.integers(0, cols, 30)
+            f[ys, xs] = rng.choice(np.array([-3.0, 0.0999, 0.1, 99.9, 99.95, 100.0, 17.123, 1e-30], np.float32), 30)
+        srcf = f if host else torch.from_numpy(f).cuda()
+        gotf, stf = api.img_completion(srcf, False, "none", return_stats=True, lib=lib)
+        if not host:
+            gotf, stf = gotf.cpu().numpy(), stf.cpu().numpy()
+        nvalid = int(((f >= np.float32(0.1)) & ((np.float32(100) - f) >= np.float32(0.1))).sum())
+        if int(stf[0, 3]) != (2 if nvalid <= 32768 else 0) or not np.array_equal(gotf.view(np.uint32), co.img_completion(f, "none").view(np.uint32)):
+            print(f"MISMATCH float rows={rows} cols={cols} p={p} hi={hi} host={host} seed={fseed} path={stf[0, 3]}", flush=True)
+            sys.exit(1)
+        gotf = api.img_completion(srcf, False, "gaussian", lib=lib)
+        gotf = gotf if host else gotf.cpu().numpy()
+        if np.abs(gotf - co.img_completion(f, "gaussian")).max() > 1e-4:
+            print(f"MISMATCH float gaussian rows={rows} cols={cols} p={p} hi={hi} seed={fseed}", flush=True)
+            sys.exit(1)
+        nf += 1
     if rng.random() < 0.15:  # stereo refinement (bit-exact without the final float Gaussian)
         dig, left, right = synth.stereo_pair(fseed % 1000, rows, cols)
         prm = api.stereo_params(final_gauss=0, lib=lib)
@@ -75,4 +95,4 @@ while time.time() < t_end:
             print(f"MISMATCH guided rows={rows} cols={cols} p={p} step={step} k={kk} seed={fseed} diff={(gotg != wantg).sum()}", flush=True)
             sys.exit(1)
         ng += 1
-print(f"fuzz ok: {n} lidar-only ({nr} of them also against the reference build), {ng} guided and {ns} stereo random frames, seed {seed}")
+print(f"fuzz ok: {n} lidar-only ({nr} of them also against the reference build), {nf} float (dictionary path), {ng} guided and {ns} stereo random frames, seed {seed}")
