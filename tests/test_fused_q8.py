@@ -208,6 +208,17 @@ def test_emu_reverse_block_and_thread_order():
         "        assert np.array_equal(out.view(np.uint32), co.img_completion(s, blur).view(np.uint32)), (r, c, blur)\n"
         "    g = api.img_completion(s, False, 'gaussian', path='generic', lib=lib)\n"
         "    assert np.array_equal(g.view(np.uint32), co.img_completion(s, 'gaussian').view(np.uint32)), (r, c, 'generic')\n"
+        "for (r, c, p) in ((97, 171, 0.05), (64, 200, 0.01)):\n"
+        "    f = synth.sparse_depth_float(44, r, c, p)\n"
+        "    out = api.img_completion(f, False, 'none', path='rank', lib=lib)\n"
+        "    assert np.array_equal(out.view(np.uint32), co.img_completion(f, 'none').view(np.uint32)), (r, c, 'rank')\n"
+        "    assert np.abs(api.img_completion(f, False, 'gaussian', lib=lib) - co.img_completion(f, 'gaussian')).max() <= 1e-4\n"
+        "import os\n"
+        "os.environ['DCMT_SLIC_BAND_MIN_FRAMES'] = '1'\n"
+        "lab = np.stack([synth.lab_image(k, 64, 96) for k in range(2)])\n"
+        "labels = api.generate_superpixels(lab, 10, 40, lib=lib)\n"
+        "for k in range(2):\n"
+        "    assert np.array_equal(labels[k], co.slic(lab[k], 10, 40)[0]), 'band SLIC'\n"
         "print('REVERSE_OK')\n" % ROOT
     )
     env = dict(os.environ, DCMT_EMU_ORDER="reverse")

@@ -10,7 +10,7 @@ from depth_completion_mt_b200 import api, synth
 from oracle import c_oracle as co
 
 
-def body(lib, to_backend, cases):
+def body(lib, to_backend, cases, big_batch=None):
     for k, (rows, cols, step, nc) in enumerate(cases):
         lab = synth.lab_image(k, rows, cols)
         if k == 1:  # flat image: every distance ties on colour, exercises "lowest centre index wins"
@@ -42,6 +42,17 @@ def body(lib, to_backend, cases):
         rl, rc = co.slic(labs[f], 10, 40)
         assert np.array_equal(bl[f], rl), f"batch frame {f}"
         assert np.array_equal(bc[f].view(np.uint64), rc.view(np.uint64)), f"batch centres {f}"
+    # batches of 32 frames and more take the band kernel (the frame's centres in shared memory, k_slic_assign_band): same
+    # labels and centres, incl. a flat frame (all ties) and an odd number of centres
+    shapes = big_batch or (36, 52, 8)
+    labs = np.stack([synth.lab_image(40 + f, shapes[0], shapes[1]) for f in range(4)] * 8)
+    labs[5] = 77
+    bl, bc = api.generate_superpixels(to_backend(labs), shapes[2], 40, return_centers=True, lib=lib)
+    bl, bc = (a if isinstance(a, np.ndarray) else a.cpu().numpy() for a in (bl, bc))
+    for f in (0, 1, 2, 3, 5, 31):
+        rl, rc = co.slic(labs[f], shapes[2], 40)
+        assert np.array_equal(bl[f], rl), f"band batch frame {f}: {(bl[f] != rl).sum()} labels differ"
+        assert np.array_equal(np.isnan(bc[f]), np.isnan(rc)) and np.array_equal(bc[f][~np.isnan(rc)], rc[~np.isnan(rc)]), f"band batch centres {f}"
     # argument errors
     with pytest.raises(Exception):
         api.generate_superpixels(to_backend(lab), 3, 40, lib=lib)
@@ -57,4 +68,4 @@ def test_gpu_slic(gpu_lib, mode):
     import torch
 
     body(gpu_lib, (lambda a: a) if mode == "host" else (lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()),
-         [(64, 96, 10, 40), (50, 70, 9, 30), (352, 1216, 18, 50), (375, 1242, 68, 40)])
+         [(64, 96, 10, 40), (50, 70, 9, 30), (352, 1216, 18, 50), (375, 1242, 68, 40)], big_batch=(352, 1216, 18))
