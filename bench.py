@@ -500,14 +500,21 @@ def run_ours(args):
             np_in16 = h_in16.numpy()
             h_out = torch.empty((n, rows, cols), dtype=torch.float32, pin_memory=True)
             np_out = h_out.numpy()
+            # the copy-only ceiling is measured before AND after each end-to-end leg and the faster of the two is reported: the
+            # host side of a shared box drifts by 10-20 % within a run, and a ceiling must not be taken in a slower moment than
+            # the thing it bounds
+            copy_f32 = lambda: lib.check(lib.dcmt_debug_host_copy_f32(np_in.ctypes.data, np_out.ctypes.data, rows, cols, n, None, 0))
+            copy_u16 = lambda: lib.check(lib.dcmt_debug_host_copy_u16(np_in16.ctypes.data, np_out.ctypes.data, rows, cols, n, None, 0))
+            ceil_ms = timed_host(copy_f32)
             e2e_ms = timed_host(lambda: api.img_completion(np_in, False, "gaussian", path=args.path, out=np_out, lib=lib))
             assert bool(torch.equal(h_out[:UNIQUE].to(dev), out_t[:UNIQUE])), "host path and device path disagree"
+            ceil_ms = min(ceil_ms, timed_host(copy_f32))
             # the same frames as the KITTI uint16 payload (dcmt_img_completion_u16_host, main.cpp:75-93): half the H2D bytes
+            ceil16_ms = timed_host(copy_u16)
             h_out.zero_()
             e2e16_ms = timed_host(lambda: api.img_completion(np_in16, False, "gaussian", out=np_out, lib=lib))
             assert bool(torch.equal(h_out[:UNIQUE].to(dev), out_t[:UNIQUE])), "uint16 host path and device path disagree"
-            ceil_ms = timed_host(lambda: lib.check(lib.dcmt_debug_host_copy_f32(np_in.ctypes.data, np_out.ctypes.data, rows, cols, n, None, 0)))
-            ceil16_ms = timed_host(lambda: lib.check(lib.dcmt_debug_host_copy_u16(np_in16.ctypes.data, np_out.ctypes.data, rows, cols, n, None, 0)))
+            ceil16_ms = min(ceil16_ms, timed_host(copy_u16))
             # one process, all visible GPUs: the multi-device host entry point (only where this rank sees several devices)
             if world == 1 and torch.cuda.device_count() > 1 and args.host_multi:
                 h_out.zero_()
@@ -632,7 +639,7 @@ def run_ours(args):
                            "input": "uint16 KITTI depth payload (main.cpp:75-82), float32 out",
                            "api": "dcmt_img_completion_u16_host; " + api_note, "copy_ceiling": fps_ceil16,
                            "frac_of_copy_ceiling": fps_e2e16 / fps_ceil16 if fps_ceil16 else None,
-                           "copy_ceiling_note": "dcmt_debug_host_copy_u16: the same pinned buffers, chunks and streams, kernels left out",
+                           "copy_ceiling_note": "dcmt_debug_host_copy_u16: the same pinned buffers, chunks and streams, kernels left out; the faster of a run before and a run after the e2e leg",
                            "host_binding_rank0": numa}
             line["e2e_f32_input"] = {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": int(n * fpix * 4), "d2h_bytes_per_step": int(d2h),
                                      "input": "float32 metres (the cv::Mat img_completion takes, img_completion.cpp:17)",
