@@ -72,27 +72,41 @@ __device__ __forceinline__ unsigned order_bits(float f) {  // monotone map float
 }
 __device__ __forceinline__ float unorder_bits(unsigned o) { return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o); }
 
+// four pixels per thread, one reduction per 1024-pixel block, and only a block whose values can change the image minimum /
+// maximum touches the shared words: a reservation per warp made 13 000 requests per cloud to ONE address in L2 -- 17 us of
+// a 20 us cloud, atomics or plain reads alike
+constexpr int kGatherPx = 4;
 __global__ void __launch_bounds__(256) k_project_gather(const unsigned long long* __restrict__ keys, size_t n, float* __restrict__ projected,
                                                         unsigned* __restrict__ minmax) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ unsigned s_lo[8], s_hi[8];
+    const size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * kGatherPx;
     keys += (size_t)blockIdx.y * n;
     minmax += (size_t)blockIdx.y * 8;
     if (projected) projected += (size_t)blockIdx.y * n;
     unsigned lo = 0xffffffffu, hi = 0u;
-    if (i < n) {
-        const unsigned long long k = keys[i];
-        const float d = k ? __uint_as_float((unsigned)(k & 0xffffffffull)) : 0.0f;
-        if (projected) projected[i] = d;
-        lo = hi = order_bits(d);
+#pragma unroll
+    for (int j = 0; j < kGatherPx; ++j) {
+        const size_t i = i0 + j;
+        if (i < n) {
+            const unsigned long long k = keys[i];
+            const float d = k ? __uint_as_float((unsigned)(k & 0xffffffffull)) : 0.0f;
+            if (projected) projected[i] = d;
+            const unsigned o = order_bits(d);
+            lo = min(lo, o);
+            hi = max(hi, o);
+        }
     }
 #pragma unroll
     for (int s = 16; s >= 1; s >>= 1) {
         lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, s));
         hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, s));
     }
-    // one warp in 13 000 changes the image minimum / maximum: read first (monotone values: a stale read only costs an
-    // atomic), so that the same-address atomics do not serialise the whole image (they were 17 us of a 20 us cloud)
-    if ((threadIdx.x & 31) == 0) {
+    if ((threadIdx.x & 31) == 0) { s_lo[threadIdx.x >> 5] = lo; s_hi[threadIdx.x >> 5] = hi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int w = 1; w < 8; ++w) { lo = min(lo, s_lo[w]); hi = max(hi, s_hi[w]); }
+        // monotone values: a stale read only costs an atomic
         if (lo != 0xffffffffu && lo < *reinterpret_cast<volatile unsigned*>(minmax + 3)) atomicMin(minmax + 3, lo);
         if (hi > *reinterpret_cast<volatile unsigned*>(minmax + 4)) atomicMax(minmax + 4, hi);
     }
@@ -135,7 +149,8 @@ cudaError_t project_run_batch(const float* points, int n_points, const int32_t* 
     if (n_points > 0)
         DCMT_LAUNCH(k_project_scatter, dim3((n_points + 255) / 256, n_clouds), dim3(256), 0, st, reinterpret_cast<const float4*>(points),
                     n_points, counts_dev, cloud_stride_points, m, rows, cols, w.keys, w.minmax);
-    DCMT_LAUNCH(k_project_gather, dim3(nb, n_clouds), dim3(256), 0, st, w.keys, n, projected, w.minmax);
+    DCMT_LAUNCH(k_project_gather, dim3((unsigned)((n + 256 * kGatherPx - 1) / (256 * kGatherPx)), n_clouds), dim3(256), 0, st, w.keys, n, projected,
+                w.minmax);
     DCMT_LAUNCH(k_project_normalize, dim3(nb, n_clouds), dim3(256), 0, st, w.keys, n, w.minmax, norm_a, norm_b, normalized, n_projected);
     return cudaGetLastError();
 }
