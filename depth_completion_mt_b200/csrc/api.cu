@@ -918,7 +918,7 @@ int dcmt_release_workspaces(void) {
 
 size_t dcmt_workspace_bytes(int rows, int cols, int n_frames) {
     if (rows < 1 || cols < 1 || n_frames < 1) return 0;
-    return completion_ws_bytes(rows, cols, n_frames, true, true);
+    return completion_ws_bytes(rows, cols, n_frames, true, true, true, true);  // upper bound over the paths a call may take
 }
 
 int dcmt_profile_begin(void) {
