@@ -420,6 +420,26 @@ def lidar_project(points, T, P, rows: int, cols: int, norm=(0.0, 80.0), *, retur
     return (proj, nrm, int(cnt[0])) if return_count else (proj, nrm)
 
 
+def bgr2gray(bgr, *, stream=None, lib: _lib.Library | None = None):
+    """cv::cvtColor(img, gray, COLOR_BGR2GRAY) (main_sl.cpp:1167,1171): (rows, cols, 3) or (n, rows, cols, 3) uint8 -> gray uint8."""
+    lib = lib or _lib.load()
+    is_t = _is_torch(bgr)
+    x = _prep_torch(bgr, torch.uint8, "bgr") if is_t else _prep_numpy(bgr, np.uint8, "bgr")
+    if x.ndim not in (3, 4) or x.shape[-1] != 3:
+        raise ValueError("bgr must be (rows, cols, 3) or (n, rows, cols, 3)")
+    squeeze = x.ndim == 3
+    x4 = x[None] if squeeze else x
+    n, rows, cols = int(x4.shape[0]), int(x4.shape[1]), int(x4.shape[2])
+    if is_t:
+        out = torch.empty((n, rows, cols), dtype=torch.uint8, device=x.device)
+        with torch.cuda.device(x.device):
+            lib.check(lib.dcmt_bgr2gray_u8(x4.data_ptr(), out.data_ptr(), rows, cols, 0, 0, n, _stream_ptr(stream)))
+    else:
+        out = np.empty((n, rows, cols), np.uint8)
+        lib.check(lib.dcmt_bgr2gray_u8_host(_np_ptr(x4), _np_ptr(out), rows, cols, 0, 0, n))
+    return out[0] if squeeze else out
+
+
 def lidar_project_batch(points, counts, T, P, rows: int, cols: int, norm=(0.0, 80.0), *, stream=None, lib: _lib.Library | None = None):
     """main_sl.cpp:478-523 for a batch of clouds in four launches.  ``points``: CUDA tensor (n_clouds, max_points, 4) float32;
     ``counts``: CUDA int32 (n_clouds,) points per cloud, or None (max_points each).  Returns (projected, normalized, n_projected):

@@ -1425,6 +1425,50 @@ int dcmt_retrieve_optimized_depth_f32(const float* disp, float* depth, int rows,
     return DCMT_OK;
 }
 
+// ---- cv::cvtColor(COLOR_BGR2GRAY) in front of the EntryType fill (main_sl.cpp:1167,1171) ----
+static int check_gray(const uint8_t* bgr, uint8_t* gray, int rows, int cols, size_t* bgr_pitch, size_t* gray_pitch, int n_frames) {
+    if (!bgr || !gray) return fail(DCMT_E_BADARG, "null pointer");
+    int rc = check_planes(rows, cols, n_frames);
+    if (rc) return rc;
+    if (rows > 65535 || n_frames > 65535) return fail(DCMT_E_UNSUPPORTED, "at most 65535 rows / frames");
+    if (*bgr_pitch == 0) *bgr_pitch = (size_t)cols * 3;
+    if (*gray_pitch == 0) *gray_pitch = (size_t)cols;
+    if (*bgr_pitch < (size_t)cols * 3 || *gray_pitch < (size_t)cols) return fail(DCMT_E_BADARG, "pitch too small");
+    return DCMT_OK;
+}
+
+int dcmt_bgr2gray_u8(const uint8_t* bgr, uint8_t* gray, int rows, int cols, size_t bgr_pitch_bytes, size_t gray_pitch_bytes, int n_frames,
+                     void* cuda_stream) {
+    int rc = check_gray(bgr, gray, rows, cols, &bgr_pitch_bytes, &gray_pitch_bytes, n_frames);
+    if (rc) return rc;
+    if (n_frames == 0) return DCMT_OK;
+    if ((rc = check_device())) return rc;
+    API_CUDA(dcmt::stereo_bgr2gray(bgr, bgr_pitch_bytes, bgr_pitch_bytes * rows, gray, gray_pitch_bytes, gray_pitch_bytes * rows, rows, cols,
+                                   n_frames, static_cast<cudaStream_t>(cuda_stream)),
+             "BGR2GRAY launch");
+    return DCMT_OK;
+}
+
+int dcmt_bgr2gray_u8_host(const uint8_t* bgr, uint8_t* gray, int rows, int cols, size_t bgr_pitch_bytes, size_t gray_pitch_bytes, int n_frames) {
+    int rc = check_gray(bgr, gray, rows, cols, &bgr_pitch_bytes, &gray_pitch_bytes, n_frames);
+    if (rc) return rc;
+    if (n_frames == 0) return DCMT_OK;
+    HostCall call;
+    if ((rc = call.open(nullptr, 0, false))) return rc;
+    cudaStream_t st = call.lanes[0].hs->s[0];
+    const size_t in_row = (size_t)cols * 3, frames_rows = (size_t)rows * n_frames;
+    Arena* ar = nullptr;
+    if ((rc = arena_acquire(st, carve_bytes(in_row * frames_rows, 1) + carve_bytes((size_t)cols * frames_rows, 1), &ar))) return rc;
+    uint8_t* d_in = carve<uint8_t>(ar, in_row * frames_rows);
+    uint8_t* d_out = carve<uint8_t>(ar, (size_t)cols * frames_rows);
+    if ((rc = arena_ok(ar))) return rc;
+    call.use(call.lanes[0]);
+    API_CUDA(cudaMemcpy2DAsync(d_in, in_row, bgr, bgr_pitch_bytes, in_row, frames_rows, cudaMemcpyHostToDevice, st), "host to device copy");
+    if ((rc = dcmt_bgr2gray_u8(d_in, d_out, rows, cols, 0, 0, n_frames, st))) return rc;
+    API_CUDA(cudaMemcpy2DAsync(gray, gray_pitch_bytes, d_out, cols, cols, frames_rows, cudaMemcpyDeviceToHost, st), "device to host copy");
+    return call.finish();
+}
+
 // ---- (a3) the reference's own containers: EntryType matrices and pitched CV_32FC1 matrices with in-place semantics ----
 static int check_entries(const void* e, int rows, int cols, size_t row_step, size_t elem_stride) {
     if (!e) return fail(DCMT_E_BADARG, "null pointer");

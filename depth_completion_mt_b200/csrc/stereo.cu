@@ -311,6 +311,29 @@ __global__ void __launch_bounds__(kThreads) k_stereo_refine(RefineArgs a) {
     }
 }
 
+// cv::cvtColor(COLOR_BGR2GRAY) on CV_8UC3 (main_sl.cpp:1167,1171): OpenCV's 8-bit path is fixed point with 15-bit
+// coefficients, gray = (3735 B + 19235 G + 9798 R + 16384) >> 15 (bit-equal to cv2 4.13 for every (B, G, R), tests/test_stereo_gray.py).
+// One thread per 4 pixels: 12 input bytes (three aligned 32-bit loads where the row allows), one 32-bit store.
+__global__ void __launch_bounds__(kThreads) k_bgr2gray(const uint8_t* __restrict__ bgr, size_t bgr_pitch, size_t bgr_fstride,
+                                                       uint8_t* __restrict__ gray, size_t gray_pitch, size_t gray_fstride, int cols) {
+    const int q = blockIdx.x * kThreads + threadIdx.x, r = blockIdx.y;
+    if (q * 4 >= cols) return;
+    const uint8_t* src = bgr + (size_t)blockIdx.z * bgr_fstride + (size_t)r * bgr_pitch + (size_t)q * 12;
+    uint8_t* dst = gray + (size_t)blockIdx.z * gray_fstride + (size_t)r * gray_pitch + (size_t)q * 4;
+    auto g = [](unsigned b, unsigned gg, unsigned rr) { return (3735u * b + 19235u * gg + 9798u * rr + 16384u) >> 15; };
+    if (q * 4 + 4 <= cols && (reinterpret_cast<uintptr_t>(src) & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 3) == 0) {
+        const uint32_t w0 = __ldg(reinterpret_cast<const uint32_t*>(src)), w1 = __ldg(reinterpret_cast<const uint32_t*>(src) + 1),
+                       w2 = __ldg(reinterpret_cast<const uint32_t*>(src) + 2);
+        const unsigned g0 = g(w0 & 255u, (w0 >> 8) & 255u, (w0 >> 16) & 255u);
+        const unsigned g1 = g(w0 >> 24, w1 & 255u, (w1 >> 8) & 255u);
+        const unsigned g2 = g((w1 >> 16) & 255u, w1 >> 24, w2 & 255u);
+        const unsigned g3 = g((w2 >> 8) & 255u, (w2 >> 16) & 255u, w2 >> 24);
+        *reinterpret_cast<uint32_t*>(dst) = g0 | (g1 << 8) | (g2 << 16) | (g3 << 24);
+    } else {
+        for (int j = 0; j < 4 && q * 4 + j < cols; ++j) dst[j] = (uint8_t)g(src[3 * j], src[3 * j + 1], src[3 * j + 2]);
+    }
+}
+
 inline unsigned blocks_for(long long total) { return (unsigned)((total + kThreads - 1) / kThreads); }
 
 }  // namespace
@@ -347,6 +370,14 @@ cudaError_t stereo_retrieve_depth(const float* disp, float* depth, int rows, int
     if (total == 0) return cudaSuccess;
     volatile float bf = baseline * focal;
     DCMT_LAUNCH(k_retrieve_depth, dim3(blocks_for(total)), dim3(kThreads), 0, st, disp, depth, total, (float)bf, clip);
+    return cudaGetLastError();
+}
+
+cudaError_t stereo_bgr2gray(const uint8_t* bgr, size_t bgr_pitch, size_t bgr_fstride, uint8_t* gray, size_t gray_pitch, size_t gray_fstride,
+                            int rows, int cols, int n_frames, cudaStream_t st) {
+    if (n_frames == 0) return cudaSuccess;
+    DCMT_LAUNCH(k_bgr2gray, dim3(((cols + 3) / 4 + kThreads - 1) / kThreads, rows, n_frames), dim3(kThreads), 0, st, bgr, bgr_pitch, bgr_fstride,
+                gray, gray_pitch, gray_fstride, cols);
     return cudaGetLastError();
 }
 

@@ -21,6 +21,9 @@ cudaError_t stereo_initial_disparity_mat(const float* depth, size_t depth_pitch,
                                          float baseline, float focal, cudaStream_t st);
 cudaError_t stereo_retrieve_depth_mat(const float* disp, size_t disp_pitch, float* depth, size_t depth_pitch, int rows, int cols,
                                       float baseline, float focal, float clip, cudaStream_t st);
+// cv::cvtColor(COLOR_BGR2GRAY), CV_8UC3 -> CV_8UC1 (main_sl.cpp:1167,1171); pitches / frame strides in bytes
+cudaError_t stereo_bgr2gray(const uint8_t* bgr, size_t bgr_pitch, size_t bgr_fstride, uint8_t* gray, size_t gray_pitch, size_t gray_fstride,
+                            int rows, int cols, int n_frames, cudaStream_t st);
 cudaError_t stereo_refine(const float* depth_ig, const uint8_t* left, const uint8_t* right, float* depth_out,
                           float* disp_out, int rows, int cols, int n_frames, float baseline, float focal, float damp,
                           float err_clip, float depth_clip, int iters, int final_gauss, cudaStream_t st);

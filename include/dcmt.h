@@ -236,6 +236,14 @@ DCMT_API int dcmt_optimize_ig_f32(const float *value_left, const float *value_ri
 DCMT_API int dcmt_retrieve_optimized_depth_f32(const float *disp, float *depth, int rows, int cols, int n_frames,
                                                float baseline, float focal, float depth_clip, void *cuda_stream);
 
+/* cv::cvtColor(COLOR_BGR2GRAY) on CV_8UC3 images (main_sl.cpp:1167,1171), the step in front of the EntryType fill:
+ * OpenCV's 8-bit path is fixed point, gray = (3735 B + 19235 G + 9798 R + 16384) >> 15 -- bit-equal to OpenCV 4.13.
+ * n_frames images follow each other at rows * pitch; pitches in bytes (0 = dense: cols * 3 / cols). */
+DCMT_API int dcmt_bgr2gray_u8(const uint8_t *bgr, uint8_t *gray, int rows, int cols, size_t bgr_pitch_bytes,
+                              size_t gray_pitch_bytes, int n_frames, void *cuda_stream);
+DCMT_API int dcmt_bgr2gray_u8_host(const uint8_t *bgr, uint8_t *gray, int rows, int cols, size_t bgr_pitch_bytes,
+                                   size_t gray_pitch_bytes, int n_frames);
+
 /* (a3) the same four functions on the reference's OWN containers, so that its call sites (main_sl.cpp:1192-1246) need no
  * change of data layout:
  *   - EntryType matrices (main_sl.cpp:23-26: struct { float value; Eigen::Vector2f derivative; }, 12 bytes) as

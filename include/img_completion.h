@@ -203,6 +203,12 @@ inline bool sample_entries(const MatView& target, float r, float c, float& value
     return true;
 }
 
+// cv::cvtColor(img, gray, cv::COLOR_BGR2GRAY) (main_sl.cpp:1167,1171) on CV_8UC3 / CV_8UC1 views
+inline void bgr2gray(const MatView& bgr, MatView& gray) {
+    if (bgr.rows != gray.rows || bgr.cols != gray.cols || !bgr.data || !gray.data) throw std::invalid_argument("dcmt: bgr2gray needs same-shaped Mats");
+    check(dcmt_bgr2gray_u8_host(static_cast<const uint8_t*>(bgr.data), static_cast<uint8_t*>(gray.data), bgr.rows, bgr.cols, bgr.step, gray.step, 1));
+}
+
 // main_sl.cpp:1165-1253 in one call: gray images (CV_8UC1 views) + initial dense depth -> refined depth
 inline void stereo_refine(const MatView& depth_ig, const MatView& left_gray, const MatView& right_gray, MatView& depth_out,
                           const dcmt_stereo_params* params = nullptr) {
@@ -299,11 +305,21 @@ inline bool calculateObservationDerivatives(const cv::Mat& target_img, const Vec
 }
 
 // main_sl.cpp:1165-1253: the sequence entry fill -> calculateMeasuementDerivatives -> get_initial_disparity ->
-// optimize_IG -> retrieve_optimized_depth -> GaussianBlur in ONE fused kernel, on the caller's gray / depth Mats
+// optimize_IG -> retrieve_optimized_depth -> GaussianBlur in ONE fused kernel, on the caller's gray (CV_8UC1) or colour
+// (CV_8UC3, BGR) images and depth Mat
 inline void stereo_refine(const cv::Mat& dense_range_img, const cv::Mat& left_gray, const cv::Mat& right_gray, cv::Mat& optimized_depth,
                           const dcmt_stereo_params* params = nullptr) {
-    CV_Assert(dense_range_img.type() == CV_32FC1 && left_gray.type() == CV_8UC1 && right_gray.type() == CV_8UC1);
-    const cv::Mat ig = dcmt::continuous(dense_range_img), l = dcmt::continuous(left_gray), r = dcmt::continuous(right_gray);
+    CV_Assert(dense_range_img.type() == CV_32FC1 && left_gray.type() == right_gray.type() && (left_gray.type() == CV_8UC1 || left_gray.type() == CV_8UC3));
+    const cv::Mat ig = dcmt::continuous(dense_range_img);
+    cv::Mat l = dcmt::continuous(left_gray), r = dcmt::continuous(right_gray);
+    if (l.type() == CV_8UC3) {  // the colour images as read: cv::cvtColor(COLOR_BGR2GRAY) (main_sl.cpp:1167,1171) on the device as well
+        cv::Mat lg(l.rows, l.cols, CV_8UC1), rg(r.rows, r.cols, CV_8UC1);
+        dcmt::MatView vlg = dcmt::view_of(lg), vrg = dcmt::view_of(rg);
+        dcmt::bgr2gray(dcmt::view_of(l), vlg);
+        dcmt::bgr2gray(dcmt::view_of(r), vrg);
+        l = lg;
+        r = rg;
+    }
     cv::Mat out(ig.rows, ig.cols, CV_32FC1);
     dcmt::MatView vo = dcmt::view_of(out);
     dcmt::stereo_refine(dcmt::view_of(ig), dcmt::view_of(l), dcmt::view_of(r), vo, params);
