@@ -1844,7 +1844,11 @@ cudaError_t q8_run_front(const Q8Plan& plan, const float* in, const uint16_t* in
     // halo rows weigh more: the tallest even split of the rows whose shared memory fits that many CTAs.
     // DCMT_FRONT_TILE_H overrides the height bound (experiments).
     static const int front_h = [] { const char* e = getenv("DCMT_FRONT_TILE_H"); const int v = e ? atoi(e) : 0; return v > 0 && v < 8 ? 8 : v; }();
+    // DCMT_FRONT_TILE_W: another tile width for the front (experiments; a multiple of 8 whose region keeps more than 8 rows per
+    // sweep of the CTA's threads, the bound col_pass relies on)
+    static const int front_w = [] { const char* e = getenv("DCMT_FRONT_TILE_W"); return e ? atoi(e) / 8 * 8 : 0; }();
     Q8Plan p = plan;
+    if (front_w >= 8 && (front_w / 8 + FLQ + FRQ) * 9 <= QT) p.tw = front_w;
     int hmax = front_h > 0 ? front_h : p.th;
     if (front_h <= 0 && DCMT_FRONT_CTAS > 2)
         while (hmax > 8 && (size_t)DCMT_FRONT_CTAS * (q8_front_smem(hmax, p.tw) + 1024) > (size_t)228 * 1024) --hmax;

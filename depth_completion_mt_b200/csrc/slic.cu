@@ -310,14 +310,34 @@ __global__ void __launch_bounds__(256) k_slic_assign(const uint8_t* __restrict__
 
 // ---- assignment over BANDS of rows with the whole frame's centres in shared memory ---------------------------------------
 // k_slic_assign stages the candidate centres of every 16 x 16 tile from global memory (offset -> item -> centre, dependent
-// loads) between two barriers: at 1 200 centres per frame it ran at 40 % issue-active, stalled on those loads.  A frame's
-// centres are small (K x 5 doubles = 48 KB at KITTI size): here a CTA copies ALL of them -- in bin order, with their integer
-// windows and the bin offsets -- into shared memory once and then streams the pixels of a band of rows through them; a pixel
-// reads the 3 x 3 bins around it straight from shared memory.  Same arithmetic, same tie rule, same labels and sums.
-constexpr int kBandThreads = 512;
+// loads) between two barriers, and every pixel walks its own 3 x 3 bins in double precision: ~900 instructions per pixel and
+// iteration, 40 % issue-active.  Here a CTA copies ALL centres of its frame -- in bin order, with their integer windows, a
+// float copy and the bin offsets -- into shared memory once (K x 108 bytes: 130 KB at KITTI size) and streams a band of rows
+// through them, one warp per 32 consecutive pixels of a row:
+//   * the warp first finds, one candidate per lane, the centres whose window meets its row segment at all (about 7 of the 14
+//     in the bins around it) and then walks THAT list together: the centre is the same for all lanes (broadcast loads);
+//   * the walk runs in float.  Its result is taken only where the winner beats the runner-up by more than the error bound of
+//     the float evaluation (e_abs, kRel below); the other pixels -- exact ties on symmetric pixels, near ties -- are decided
+//     by the double-precision two-stage procedure of k_slic_assign (slic_resolve), i.e. by the reference's own arithmetic;
+//   * the sums of the new centres are reduced per group of equal winners with one __match_any_sync and four REDUX.
+// Same candidates (the window test is the exact integer one), same winner, same sums: labels and centres stay bit-identical.
+//
+// Error bound of the float stage.  With eps = 2^-24, colours in [0, 255], |c - p| < step + 1 for the coordinates of a covering
+// centre and M = max(rows, cols): a colour difference is off by at most 2^-15 (conversion of the centre + rounding of the
+// subtraction), its square by 2^-15 * 511; a coordinate difference by 2^-23 M, its square by 2^-22 M (step + 2).  So
+//   |q_float - q| <= E + 1e-6 q,   E = 0.0468 / nc^2 + 2^-21 M (step + 2) / step^2
+// (six roundings at most on the way of any term through the sum of positive terms: 3.6e-7 relative), and
+//   q1_float + 2.5 E < q2_float (1 - 4e-6)   =>   q1 < q2 by far more than the 1e-12 the double stage itself asks for.
+#ifndef DCMT_SLIC_BAND_THREADS
+#define DCMT_SLIC_BAND_THREADS 768  // 80 registers, no spills; 1024 threads would cap them at 64 and spill inside the walk
+#endif
+constexpr int kBandThreads = DCMT_SLIC_BAND_THREADS;
+#ifndef __CUDACC__
+#define __noinline__ __attribute__((noinline))
+#endif
 
 struct BandSmem {  // layout of the dynamic shared memory for K centres and NB bins
-    size_t off_cent, off_win, off_sum, off_idx, off_bin, total;
+    size_t off_cent, off_win, off_f4, off_f2, off_sum, off_bin, total;
 };
 static inline BandSmem band_smem(int K, int NB) {
     BandSmem b;
@@ -325,11 +345,65 @@ static inline BandSmem band_smem(int K, int NB) {
     auto take = [&](size_t bytes) { const size_t at = o; o = (o + bytes + 15) & ~size_t(15); return at; };  // 16-byte aligned parts
     b.off_cent = take((size_t)K * 5 * sizeof(double));
     b.off_win = take((size_t)K * sizeof(int4));
+    b.off_f4 = take((size_t)K * sizeof(float4));
+    b.off_f2 = take((size_t)K * sizeof(float2));
     b.off_sum = take((size_t)K * 6 * sizeof(unsigned));
-    b.off_idx = take((size_t)K * sizeof(int));
     b.off_bin = take((size_t)(NB + 1) * sizeof(int));
     b.total = o;
     return b;
+}
+
+struct BandView {  // what slic_resolve needs of the CTA's shared memory
+    const double* cent;  // [k][5], bin order
+    const int4* win;     // {lo_x, width_x, lo_y, width_y}
+    const float2* f2;    // {centre y as float, original centre index (bits)}
+    const int* bin;      // exclusive offsets, nbins + 1
+    int bx, by, nc, step;
+    double inv_nc2, inv_ns2;
+};
+
+// The winner of one pixel by the reference's arithmetic: stage 1, the square-root- and division-free stand-in for compute_dist
+// in double (see k_slic_assign); stage 2, compute_dist itself (:61-69, strict <, lowest centre index) when stage 1 is within
+// 1e-12.  Returns the winner's slot in the bin-ordered list.  Rare (pixels the float walk could not call): kept out of line.
+__device__ __noinline__ int slic_resolve(const BandView& v, int x, int y, unsigned pix) {
+    const double L = pix & 255u, A = (pix >> 8) & 255u, B = pix >> 16;
+    const int pbx = min(x / v.step, v.bx - 1), pby = min(y / v.step, v.by - 1);
+    const int gy_lo = max(pby - 1, 0), gy_hi = min(pby + 1, v.by - 1), gx_lo = max(pbx - 1, 0), gx_hi = min(pbx + 1, v.bx - 1);
+    const double xd = (double)x, yd = (double)y;
+    double q1 = 1.0e300, q2 = 1.0e300;
+    int best_c = -1, best_k = -1;
+    for (int gy = gy_lo; gy <= gy_hi; ++gy) {
+        const int k0 = v.bin[gy * v.bx + gx_lo], k1 = v.bin[gy * v.bx + gx_hi + 1];  // bins of a row are contiguous
+        for (int k = k0; k < k1; ++k) {
+            const int4 w = v.win[k];
+            if ((unsigned)(x - w.x) >= (unsigned)w.y || (unsigned)(y - w.z) >= (unsigned)w.w) continue;
+            const double* ce = v.cent + (size_t)k * 5;
+            const double d0 = ce[0] - L, d1 = ce[1] - A, d2 = ce[2] - B, dx = ce[3] - xd, dy = ce[4] - yd;
+            const double q = (d0 * d0 + d1 * d1 + d2 * d2) * v.inv_nc2 + (dx * dx + dy * dy) * v.inv_ns2;
+            const int c = __float_as_int(v.f2[k].y);
+            if (q < q1 || (q == q1 && c < best_c)) { q2 = q1; q1 = q; best_c = c; best_k = k; }
+            else if (q < q2) q2 = q;
+        }
+    }
+    if (best_c >= 0 && !(q2 > q1 * (1.0 + 1.0e-12))) {
+        double best = (double)FLT_MAX;  // :117
+        best_c = -1;
+        best_k = -1;
+        for (int gy = gy_lo; gy <= gy_hi; ++gy) {
+            const int k0 = v.bin[gy * v.bx + gx_lo], k1 = v.bin[gy * v.bx + gx_hi + 1];
+            for (int k = k0; k < k1; ++k) {
+                const int4 w = v.win[k];
+                if ((unsigned)(x - w.x) >= (unsigned)w.y || (unsigned)(y - w.z) >= (unsigned)w.w) continue;
+                const double* ce = v.cent + (size_t)k * 5;
+                const double dc = __dsqrt_rn(__dadd_rn(__dadd_rn(sq(__dsub_rn(ce[0], L)), sq(__dsub_rn(ce[1], A))), sq(__dsub_rn(ce[2], B))));
+                const double ds = __dsqrt_rn(__dadd_rn(sq(__dsub_rn(ce[3], xd)), sq(__dsub_rn(ce[4], yd))));
+                const double d = __dsqrt_rn(__dadd_rn(sq(__ddiv_rn(dc, (double)v.nc)), sq(__ddiv_rn(ds, (double)v.step))));  // ns = step (:105)
+                const int c = __float_as_int(v.f2[k].y);
+                if (d < best || (d == best && best_c >= 0 && c < best_c)) { best = d; best_c = c; best_k = k; }
+            }
+        }
+    }
+    return best_k;
 }
 
 __global__ void __launch_bounds__(kBandThreads) k_slic_assign_band(const uint8_t* __restrict__ lab, int rows, int cols, int step, int nc,
@@ -337,13 +411,14 @@ __global__ void __launch_bounds__(kBandThreads) k_slic_assign_band(const uint8_t
                                                                     const int* __restrict__ offset, const int* __restrict__ items,
                                                                     const double* __restrict__ sorted, int32_t* __restrict__ labels,
                                                                     unsigned long long* __restrict__ sums, int n_centers, double inv_nc2,
-                                                                    double inv_ns2, BandSmem lay) {
+                                                                    double inv_ns2, float e_abs, BandSmem lay) {
     DCMT_DYN_SMEM(unsigned char, smem);
-    double* s_cent = reinterpret_cast<double*>(smem + lay.off_cent);   // [k][5], bin order
-    int4* s_win = reinterpret_cast<int4*>(smem + lay.off_win);         // {lo_x, width_x, lo_y, width_y}
+    double* s_cent = reinterpret_cast<double*>(smem + lay.off_cent);
+    int4* s_win = reinterpret_cast<int4*>(smem + lay.off_win);
+    float4* s_f4 = reinterpret_cast<float4*>(smem + lay.off_f4);        // {L, a, b, x} of the centre as floats
+    float2* s_f2 = reinterpret_cast<float2*>(smem + lay.off_f2);        // {y as float, original centre index}
     unsigned* s_sum = reinterpret_cast<unsigned*>(smem + lay.off_sum);  // [k][6]
-    int* s_idx = reinterpret_cast<int*>(smem + lay.off_idx);            // original centre index (tie rule, labels)
-    int* s_bin = reinterpret_cast<int*>(smem + lay.off_bin);            // exclusive offsets, nbins + 1
+    int* s_bin = reinterpret_cast<int*>(smem + lay.off_bin);
     const int nbins = bx * by;
     {  // frame
         const size_t f = blockIdx.y;
@@ -358,113 +433,117 @@ __global__ void __launch_bounds__(kBandThreads) k_slic_assign_band(const uint8_t
     for (int b = tid; b <= nbins; b += kBandThreads) s_bin[b] = offset[b];
     __syncthreads();
     const int n_binned = s_bin[nbins];  // centres that are not NaN
-    for (int i = tid; i < n_binned * 5; i += kBandThreads) s_cent[i] = sorted[i];
     for (int i = tid; i < n_binned * 6; i += kBandThreads) s_sum[i] = 0u;
     for (int k = tid; k < n_binned; k += kBandThreads) {
-        s_idx[k] = items[k];
-        const double cx = sorted[(size_t)k * 5 + 3], cy = sorted[(size_t)k * 5 + 4];
+        double ce[5];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) ce[q] = sorted[(size_t)k * 5 + q];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) s_cent[(size_t)k * 5 + q] = ce[q];
         // for (int k = cx - step; k < cx + step; k++) (:123): truncation towards zero, then a double comparison; for integer k,
         // k < c + step <=> k < ceil(c + step)
-        const int lox = (int)__dsub_rn(cx, (double)step), loy = (int)__dsub_rn(cy, (double)step);
-        const int hix = (int)ceil(__dadd_rn(cx, (double)step)), hiy = (int)ceil(__dadd_rn(cy, (double)step));
+        const int lox = (int)__dsub_rn(ce[3], (double)step), loy = (int)__dsub_rn(ce[4], (double)step);
+        const int hix = (int)ceil(__dadd_rn(ce[3], (double)step)), hiy = (int)ceil(__dadd_rn(ce[4], (double)step));
         s_win[k] = make_int4(lox, hix - lox, loy, hiy - loy);
+        s_f4[k] = make_float4((float)ce[0], (float)ce[1], (float)ce[2], (float)ce[3]);
+        s_f2[k] = make_float2((float)ce[4], __int_as_float(items[k]));
     }
     __syncthreads();
+    BandView view;
+    view.cent = s_cent; view.win = s_win; view.f2 = s_f2; view.bin = s_bin;
+    view.bx = bx; view.by = by; view.nc = nc; view.step = step; view.inv_nc2 = inv_nc2; view.inv_ns2 = inv_ns2;
     const int y_begin = blockIdx.x * band_rows, y_end = min(rows, y_begin + band_rows);
-    const int n_px = (y_end - y_begin) * cols;
-    const int lane = tid & 31;
-    // whole warps walk the band (32 consecutive pixels of the row-major order), so that the warp collectives below are uniform
-    // pixel tid, tid + 512, ... of the band in row-major order, walked without a division per pixel
-    const int step_y = kBandThreads / cols, step_x = kBandThreads - step_y * cols;
-    int wy = tid / cols, wx = tid - wy * cols;
-    for (int base = (tid & ~31); base < n_px; base += kBandThreads) {
-        const bool live = base + lane < n_px;
-        const int x = live ? wx : 0, y = y_begin + (live ? wy : 0);
-        wx += step_x;
-        wy += step_y;
-        if (wx >= cols) { wx -= cols; ++wy; }
-        const uint8_t* p = lab + ((size_t)y * cols + x) * 3;
-        const double L = p[0], A = p[1], B = p[2];
-        const int pbx = min(fast_div(x, step_magic), bx - 1), pby = min(fast_div(y, step_magic), by - 1);
-        const int gy_lo = max(pby - 1, 0), gy_hi = min(pby + 1, by - 1), gx_lo = max(pbx - 1, 0), gx_hi = min(pbx + 1, bx - 1);
-        const double xd = (double)x, yd = (double)y;
-        // stage 1: the square-root- and division-free stand-in for compute_dist (see k_slic_assign); stage 2 for near ties
-        double q1 = 1.0e300, q2 = 1.0e300;
-        int best_c = -1, best_k = -1;
-        if (live) {
-            for (int gy = gy_lo; gy <= gy_hi; ++gy) {
-                const int k0 = s_bin[gy * bx + gx_lo], k1 = s_bin[gy * bx + gx_hi + 1];  // bins of a row are contiguous
-                for (int k = k0; k < k1; ++k) {
+    const int lane = tid & 31, warp = tid >> 5;
+    constexpr int kWarps = kBandThreads / 32;
+    // one item = 32 consecutive pixels of one row; warp w takes items w, w + kWarps, ... (walked without a division per item)
+    const int segs = (cols + 31) >> 5, n_items = (y_end - y_begin) * segs;
+    const int d_row = kWarps / segs, d_seg = kWarps - d_row * segs;
+    int ry = warp / segs, sg = warp - ry * segs;
+    const float inc = (float)inv_nc2, ins = (float)inv_ns2;
+    const float kInf = __int_as_float(0x7f800000), kRel = 1.0f - 4.0e-6f;
+    auto load_px = [&](int r, int s) -> unsigned {  // L | a << 8 | b << 16 of the lane's pixel, 0 beyond the row
+        const int px = s * 32 + lane;
+        if (px >= cols) return 0u;
+        const uint8_t* p = lab + ((size_t)(y_begin + r) * cols + px) * 3;
+        return (unsigned)p[0] | ((unsigned)p[1] << 8) | ((unsigned)p[2] << 16);
+    };
+    unsigned pix = warp < n_items ? load_px(ry, sg) : 0u;
+    for (int item = warp; item < n_items; item += kWarps) {
+        const int y = y_begin + ry, x0 = sg * 32, x = x0 + lane;
+        const bool live = x < cols;
+        // the next item's pixel is on its way while this one is worked on (the loads were a quarter of all stall samples)
+        ry += d_row;
+        sg += d_seg;
+        if (sg >= segs) { sg -= segs; ++ry; }
+        const unsigned pix_next = item + kWarps < n_items ? load_px(ry, sg) : 0u;
+        const float L = (float)(pix & 255u), A = (float)((pix >> 8) & 255u), B = (float)(pix >> 16), xf = (float)x, yf = (float)y;
+        // bins that can hold a centre covering any pixel of the segment
+        const int pby = min(fast_div(y, step_magic), by - 1);
+        const int gy_lo = max(pby - 1, 0), gy_hi = min(pby + 1, by - 1);
+        const int gx_lo = max(min(fast_div(x0, step_magic), bx - 1) - 1, 0), gx_hi = min(min(fast_div(x0 + 31, step_magic), bx - 1) + 1, bx - 1);
+        float q1 = kInf, q2 = kInf;  // smallest and second smallest float distance over the covering centres
+        int best = -1;               // slot of the smallest
+        for (int gy = gy_lo; gy <= gy_hi; ++gy) {
+            const int k0 = s_bin[gy * bx + gx_lo], k1 = s_bin[gy * bx + gx_hi + 1];  // bins of a row are contiguous
+            for (int kb = k0; kb < k1; kb += 32) {
+                bool meets = false;
+                if (kb + lane < k1) {
+                    const int4 w = s_win[kb + lane];
+                    meets = (unsigned)(y - w.z) < (unsigned)w.w && w.x < x0 + 32 && w.x + w.y > x0;
+                }
+                unsigned todo = __ballot_sync(0xffffffffu, meets);
+                while (todo) {
+                    const int k = kb + __ffs((int)todo) - 1;  // the same centre for every lane
+                    todo &= todo - 1;
                     const int4 w = s_win[k];
-                    if ((unsigned)(x - w.x) >= (unsigned)w.y || (unsigned)(y - w.z) >= (unsigned)w.w) continue;
-                    const double* ce = s_cent + (size_t)k * 5;
-                    const double d0 = ce[0] - L, d1 = ce[1] - A, d2 = ce[2] - B, dx = ce[3] - xd, dy = ce[4] - yd;
-                    const double q = (d0 * d0 + d1 * d1 + d2 * d2) * inv_nc2 + (dx * dx + dy * dy) * inv_ns2;
-                    const int c = s_idx[k];
-                    if (q < q1 || (q == q1 && c < best_c)) { q2 = q1; q1 = q; best_c = c; best_k = k; }
-                    else if (q < q2) q2 = q;
-                }
-            }
-            if (best_c >= 0 && !(q2 > q1 * (1.0 + 1.0e-12))) {
-                // too close to call: the reference's own arithmetic decides (compute_dist :61-69, strict <, lowest index)
-                double best = (double)FLT_MAX;  // :117
-                best_c = -1;
-                best_k = -1;
-                for (int gy = gy_lo; gy <= gy_hi; ++gy) {
-                    const int k0 = s_bin[gy * bx + gx_lo], k1 = s_bin[gy * bx + gx_hi + 1];
-                    for (int k = k0; k < k1; ++k) {
-                        const int4 w = s_win[k];
-                        if ((unsigned)(x - w.x) >= (unsigned)w.y || (unsigned)(y - w.z) >= (unsigned)w.w) continue;
-                        const double* ce = s_cent + (size_t)k * 5;
-                        const double dc = __dsqrt_rn(__dadd_rn(__dadd_rn(sq(__dsub_rn(ce[0], L)), sq(__dsub_rn(ce[1], A))), sq(__dsub_rn(ce[2], B))));
-                        const double ds = __dsqrt_rn(__dadd_rn(sq(__dsub_rn(ce[3], (double)x)), sq(__dsub_rn(ce[4], (double)y))));
-                        const double d = __dsqrt_rn(__dadd_rn(sq(__ddiv_rn(dc, (double)nc)), sq(__ddiv_rn(ds, (double)step))));  // ns = step (:105)
-                        const int c = s_idx[k];
-                        if (d < best || (d == best && best_c >= 0 && c < best_c)) { best = d; best_c = c; best_k = k; }
-                    }
+                    const float4 c = s_f4[k];
+                    const float cy = s_f2[k].x;
+                    const float d0 = c.x - L, d1 = c.y - A, d2 = c.z - B, dx = c.w - xf, dy = cy - yf;
+                    float q = (d0 * d0 + d1 * d1 + d2 * d2) * inc + (dx * dx + dy * dy) * ins;
+                    if ((unsigned)(x - w.x) >= (unsigned)w.y) q = kInf;  // the window does not reach this lane's column
+                    q2 = fminf(q2, fmaxf(q1, q));
+                    if (q < q1) best = k;
+                    q1 = fminf(q1, q);
                 }
             }
         }
-        int label = -1;
-        if (live) {
-            label = labels[(size_t)y * cols + x];
-            if (best_c >= 0) {
-                label = best_c;
-                labels[(size_t)y * cols + x] = label;
+        int key = -1;
+        if (live && best >= 0) {
+            if (!(q1 + e_abs < q2 * kRel)) best = slic_resolve(view, x, y, pix);  // too close for floats
+            key = best;
+        }
+        if (key >= 0) labels[(size_t)y * cols + x] = __float_as_int(s_f2[key].y);
+        // centre sums (integers: exact in any order): lanes with the same winner reduce among themselves, the lowest adds into the
+        // CTA's shared-memory sums; pixels that keep a stale label (no window covers them) add to global memory directly
+        {
+            const unsigned peers = __match_any_sync(0xffffffffu, (unsigned)key);
+            const unsigned v0 = __reduce_add_sync(peers, pix & 255u), v1 = __reduce_add_sync(peers, (pix >> 8) & 255u),
+                           v2 = __reduce_add_sync(peers, pix >> 16), v3 = __reduce_add_sync(peers, (unsigned)x);
+            if (key >= 0 && lane == __ffs((int)peers) - 1) {
+                const unsigned n = (unsigned)__popc(peers);
+                unsigned* sg6 = s_sum + (size_t)key * 6;
+                atomicAdd(sg6 + 0, v0); atomicAdd(sg6 + 1, v1); atomicAdd(sg6 + 2, v2);
+                atomicAdd(sg6 + 3, v3); atomicAdd(sg6 + 4, n * (unsigned)y); atomicAdd(sg6 + 5, n);
             }
         }
-        // centre sums (integers: exact in any order): per distinct winner of the warp one hardware reduction and one lane adding
-        // into the CTA's shared-memory sums; pixels that keep a stale label (no window covers them) add to global memory directly
-        const int key = (live && best_c >= 0) ? best_k : -1;
-        unsigned todo = __ballot_sync(0xffffffffu, key >= 0);
-        while (todo) {
-            const int leader = __ffs((int)todo) - 1;
-            const int kk = __shfl_sync(0xffffffffu, key, leader);
-            const bool mine = key == kk;
-            const unsigned v0 = __reduce_add_sync(0xffffffffu, mine ? (unsigned)p[0] : 0u), v1 = __reduce_add_sync(0xffffffffu, mine ? (unsigned)p[1] : 0u),
-                           v2 = __reduce_add_sync(0xffffffffu, mine ? (unsigned)p[2] : 0u), v3 = __reduce_add_sync(0xffffffffu, mine ? (unsigned)x : 0u),
-                           v4 = __reduce_add_sync(0xffffffffu, mine ? (unsigned)y : 0u), v5 = __reduce_add_sync(0xffffffffu, mine ? 1u : 0u);
-            if (lane == leader) {
-                unsigned* sg = s_sum + (size_t)kk * 6;
-                atomicAdd(sg + 0, v0); atomicAdd(sg + 1, v1); atomicAdd(sg + 2, v2);
-                atomicAdd(sg + 3, v3); atomicAdd(sg + 4, v4); atomicAdd(sg + 5, v5);
+        if (live && key < 0) {
+            const int label = labels[(size_t)y * cols + x];
+            if (label != -1) {
+                unsigned long long* sg6 = sums + (size_t)label * 6;
+                atomicAdd(sg6 + 0, (unsigned long long)(pix & 255u));
+                atomicAdd(sg6 + 1, (unsigned long long)((pix >> 8) & 255u));
+                atomicAdd(sg6 + 2, (unsigned long long)(pix >> 16));
+                atomicAdd(sg6 + 3, (unsigned long long)x);
+                atomicAdd(sg6 + 4, (unsigned long long)y);
+                atomicAdd(sg6 + 5, 1ull);
             }
-            todo &= ~__ballot_sync(0xffffffffu, mine);
         }
-        if (live && label != -1 && key < 0) {
-            unsigned long long* sg = sums + (size_t)label * 6;
-            atomicAdd(sg + 0, (unsigned long long)p[0]);
-            atomicAdd(sg + 1, (unsigned long long)p[1]);
-            atomicAdd(sg + 2, (unsigned long long)p[2]);
-            atomicAdd(sg + 3, (unsigned long long)x);
-            atomicAdd(sg + 4, (unsigned long long)y);
-            atomicAdd(sg + 5, 1ull);
-        }
+        pix = pix_next;
     }
     __syncthreads();
     for (int i = tid; i < n_binned * 6; i += kBandThreads) {
         const unsigned v = s_sum[i];
-        if (v) atomicAdd(sums + (size_t)s_idx[i / 6] * 6 + (i % 6), (unsigned long long)v);
+        if (v) atomicAdd(sums + (size_t)__float_as_int(s_f2[i / 6].y) * 6 + (i % 6), (unsigned long long)v);
     }
 }
 
@@ -509,24 +588,29 @@ cudaError_t slic_run(const uint8_t* lab, int rows, int cols, int n_frames, int s
     DCMT_LAUNCH(k_slic_fill_labels, dim3((unsigned)((npx + 255) / 256)), dim3(256), 0, st, labels, npx);
     if (n_centers == 0 || n_frames == 0) return cudaGetLastError();
     DCMT_LAUNCH(k_slic_init, dim3(cb, n_frames), dim3(128), 0, st, lab, rows, cols, step, ny, n_centers, w.centers);
-    // assignment kernel: bands of rows with the frame's centres in shared memory when they fit (two CTAs per SM), else tiles
+    // assignment kernel: bands of rows with the frame's centres in shared memory when they fit (one CTA of 768 threads per SM),
+    // else 16 x 16 tiles.  DCMT_SLIC_BAND_MIN_FRAMES: batch size from which the band kernel is used (experiments).
     const BandSmem lay = band_smem(n_centers, w.bins_x * w.bins_y);
-    // measured on the B200 (step 18, 1 200 centres): bands win for batches (3.7 k frames/s against 3.0 k at 256 frames) and lose for a
-    // handful of frames (a band is a long serial walk: 11 CTAs cannot fill the chip), so small batches keep the tile kernel
-    static const int band_min = [] { const char* e = getenv("DCMT_SLIC_BAND_MIN_FRAMES"); return e ? atoi(e) : 32; }();
-    const bool bands_fit = lay.total <= (size_t)110 * 1024 && n_frames >= band_min;
+    static const int band_min = [] { const char* e = getenv("DCMT_SLIC_BAND_MIN_FRAMES"); return e ? atoi(e) : 1; }();
+    constexpr size_t kBandSmemMax = 200 * 1024;
+    const bool bands_fit = lay.total <= kBandSmemMax && n_frames >= band_min;
     int n_bands = 1, band_rows = rows;
+    float e_abs = 0.f;
     if (bands_fit) {
-        // enough CTAs to fill the chip twice, but bands of at least 32 rows (every CTA copies the whole frame's centres)
-        n_bands = (2 * 148 + n_frames - 1) / n_frames;
-        if (n_bands > rows / 32) n_bands = rows / 32;
+        // about four CTAs per SM over the run, but bands of at least 4 rows (every CTA copies the whole frame's centres)
+        n_bands = (4 * 148 + n_frames - 1) / n_frames;
+        if (n_bands > rows / 4) n_bands = rows / 4;
         if (n_bands < 1) n_bands = 1;
         band_rows = (rows + n_bands - 1) / n_bands;
         // a CTA sums coordinates in 32 bits: band pixels x largest coordinate must stay below 2^32
         while (band_rows > 1 && (unsigned long long)band_rows * cols * (rows > cols ? rows : cols) >= (1ull << 32)) band_rows = (band_rows + 1) / 2;
         n_bands = (rows + band_rows - 1) / band_rows;
-        cudaError_t e = cudaFuncSetAttribute(k_slic_assign_band, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(k_slic_assign_band, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBandSmemMax);
         if (e != cudaSuccess) return e;
+        // 2.5 E of the float stage (see k_slic_assign_band), rounded up
+        const double M = rows > cols ? rows : cols;
+        const double E = 0.0468 / ((double)nc * (double)nc) + M * ((double)step + 2.0) / ((double)step * (double)step) / 2097152.0;
+        e_abs = (float)(2.5 * E * 1.001);
     }
     const uint32_t step_magic = (uint32_t)((1ull << 32) / (unsigned)step) + 1u;
     for (int it = 0; it < iterations; ++it) {
@@ -535,7 +619,7 @@ cudaError_t slic_run(const uint8_t* lab, int rows, int cols, int n_frames, int s
         if (bands_fit)
             DCMT_LAUNCH(k_slic_assign_band, dim3(n_bands, n_frames), dim3(kBandThreads), lay.total, st, lab, rows, cols, step, nc, w.bins_x,
                         w.bins_y, step_magic, band_rows, w.bin_count, w.bin_items, w.sorted, labels, w.sums, n_centers,
-                        1.0 / ((double)nc * (double)nc), 1.0 / ((double)step * (double)step), lay);
+                        1.0 / ((double)nc * (double)nc), 1.0 / ((double)step * (double)step), e_abs, lay);
         else
             DCMT_LAUNCH(k_slic_assign, dim3((cols + 15) / 16, (rows + 15) / 16, n_frames), dim3(16, 16), 0, st, lab, rows, cols, step, nc,
                         w.bins_x, w.bins_y, w.centers, w.bin_count, w.bin_items, w.sorted, labels, w.sums, n_centers,

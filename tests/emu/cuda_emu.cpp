@@ -127,6 +127,16 @@ unsigned warp_reduce_add(unsigned v) {
     return r;
 }
 
+int warp_gather(unsigned v, unsigned* out) {  // every lane's value, in lane order; returns the number of lanes of the warp
+    Warp& w = g_warps[g_cur / 32];
+    w.slot[g_cur % 32] = v;
+    warp_sync(w);
+    const int n = w.lanes;
+    for (int i = 0; i < n; ++i) out[i] = w.slot[i];
+    warp_sync(w);  // nobody overwrites a slot before everyone has read it
+    return n;
+}
+
 void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()>& body) {
     ++g_launches;
     if (smem_bytes > kSmem) std::abort();

@@ -61,6 +61,7 @@ int block_count(int pred);  // barrier + number of threads with pred != 0
 unsigned warp_exchange(unsigned v, int width, int mode, int delta);  // shuffles inside segments of `width` lanes
 unsigned warp_ballot(int pred);
 unsigned warp_reduce_add(unsigned v);
+int warp_gather(unsigned v, unsigned* out);  // all lanes' values; number of lanes in the warp
 void warp_barrier();
 long launches();
 }  // namespace dcmt_emu
@@ -122,7 +123,21 @@ template <class T> static inline T __shfl_sync(unsigned, T v, int lane, int widt
 template <class T> static inline T __shfl_down_sync(unsigned, T v, int d, int width = 32) { return emu_shfl(v, 1, d, width); }
 template <class T> static inline T __shfl_up_sync(unsigned, T v, int d, int width = 32) { return emu_shfl(v, 2, d, width); }
 template <class T> static inline T __shfl_xor_sync(unsigned, T v, int m, int width = 32) { return emu_shfl(v, 3, m, width); }
-static inline unsigned __reduce_add_sync(unsigned, unsigned v) { return dcmt_emu::warp_reduce_add(v); }  // full mask only
+// every lane of the warp makes the call, each with the mask of its own group (the __match_any_sync idiom)
+static inline unsigned __reduce_add_sync(unsigned mask, unsigned v) {
+    unsigned a[32], r = 0;
+    const int n = dcmt_emu::warp_gather(v, a);
+    for (int i = 0; i < n; ++i)
+        if (mask >> i & 1u) r += a[i];
+    return r;
+}
+static inline unsigned __match_any_sync(unsigned, unsigned v) {
+    unsigned a[32], r = 0;
+    const int n = dcmt_emu::warp_gather(v, a);
+    for (int i = 0; i < n; ++i)
+        if (a[i] == v) r |= 1u << i;
+    return r;
+}
 static inline unsigned __ballot_sync(unsigned, int p) { return dcmt_emu::warp_ballot(p); }
 static inline int __any_sync(unsigned, int p) { return dcmt_emu::warp_ballot(p) != 0; }
 static inline int __all_sync(unsigned, int p) { return dcmt_emu::warp_ballot(!p) == 0; }

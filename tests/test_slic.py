@@ -42,8 +42,8 @@ def body(lib, to_backend, cases, big_batch=None):
         rl, rc = co.slic(labs[f], 10, 40)
         assert np.array_equal(bl[f], rl), f"batch frame {f}"
         assert np.array_equal(bc[f].view(np.uint64), rc.view(np.uint64)), f"batch centres {f}"
-    # batches of 32 frames and more take the band kernel (the frame's centres in shared memory, k_slic_assign_band): same
-    # labels and centres, incl. a flat frame (all ties) and an odd number of centres
+    # a larger batch (bands of whole frames in k_slic_assign_band): same labels and centres, incl. a flat frame (all ties: every
+    # pixel goes through slic_resolve) and an odd number of centres
     shapes = big_batch or (36, 52, 8)
     labs = np.stack([synth.lab_image(40 + f, shapes[0], shapes[1]) for f in range(4)] * 8)
     labs[5] = 77
@@ -62,6 +62,22 @@ def test_emu_slic(emu_lib):
     body(emu_lib, lambda a: a, [(64, 96, 10, 40), (50, 70, 9, 30), (80, 120, 18, 50)])
 
 
+def check_tile_kernel(lib, to_backend, rows, cols, step):
+    """More centres than the band kernel's shared memory holds (K x 108 bytes > 200 KB): the 16 x 16 tile kernel runs."""
+    k = lib.dcmt_slic_center_count(rows, cols, step)
+    assert k * 108 > 200 * 1024
+    lab = synth.lab_image(61, rows, cols)
+    labels, centers = api.generate_superpixels(to_backend(lab), step, 40, return_centers=True, lib=lib)
+    labels, centers = (a if isinstance(a, np.ndarray) else a.cpu().numpy() for a in (labels, centers))
+    ref_l, ref_c = co.slic(lab, step, 40)
+    assert np.array_equal(labels, ref_l), f"{(labels != ref_l).sum()} of {labels.size} labels differ"
+    assert np.array_equal(np.isnan(centers), np.isnan(ref_c)) and np.array_equal(centers[~np.isnan(ref_c)], ref_c[~np.isnan(ref_c)])
+
+
+def test_emu_slic_tile_kernel(emu_lib):
+    check_tile_kernel(emu_lib, lambda a: a, 140, 232, 4)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("mode", ["host", "device"])
 def test_gpu_slic(gpu_lib, mode):
@@ -69,3 +85,10 @@ def test_gpu_slic(gpu_lib, mode):
 
     body(gpu_lib, (lambda a: a) if mode == "host" else (lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()),
          [(64, 96, 10, 40), (50, 70, 9, 30), (352, 1216, 18, 50), (375, 1242, 68, 40)], big_batch=(352, 1216, 18))
+
+
+@pytest.mark.gpu
+def test_gpu_slic_tile_kernel(gpu_lib):
+    import torch
+
+    check_tile_kernel(gpu_lib, lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda(), 352, 1216, 10)
