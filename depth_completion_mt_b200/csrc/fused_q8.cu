@@ -1841,21 +1841,39 @@ cudaError_t q8_run_front(const Q8Plan& plan, const float* in, const uint16_t* in
                          int validate, cudaStream_t st) {
     // The front's tiles need not be the tail's (they meet in the global intermediate plane).  k_q8_front is latency bound
     // (its global loads, seven barriers), so DCMT_FRONT_CTAS CTAs per SM on lower tiles beat two tall ones although the
-    // halo rows weigh more: the tallest even split of the rows whose shared memory fits that many CTAs.
-    // DCMT_FRONT_TILE_H overrides the height bound (experiments).
+    // halo rows weigh more: the tallest even split of the rows whose shared memory fits that many CTAs.  Its width: the
+    // kernel is bound by shared-memory bandwidth, and a quarter of its wavefronts were bank conflicts of warps that straddle
+    // two rows of the region (rows of 21 quads, 42 half-quads: the second row starts on the banks the first one ends on).
+    // A tile width of 8 (8 m - 2) pixels makes those rows 16 m half-quads long -- whole 128-byte wavefronts -- which is
+    // worth 6 - 7 % at equal work (measured at 1216 x 352: 112-pixel tiles 1.387 ms against 1.480 ms for the tail's 152): such
+    // widths compete with the tail's on (region quads x region rows), with that bonus.
+    // DCMT_FRONT_TILE_H / DCMT_FRONT_TILE_W override the height bound / the width (experiments).
     static const int front_h = [] { const char* e = getenv("DCMT_FRONT_TILE_H"); const int v = e ? atoi(e) : 0; return v > 0 && v < 8 ? 8 : v; }();
-    // DCMT_FRONT_TILE_W: another tile width for the front (experiments; a multiple of 8 whose region keeps more than 8 rows per
-    // sweep of the CTA's threads, the bound col_pass relies on)
-    static const int front_w = [] { const char* e = getenv("DCMT_FRONT_TILE_W"); return e ? atoi(e) / 8 * 8 : 0; }();
+    static const int front_w = [] { const char* e = getenv("DCMT_FRONT_TILE_W"); return e ? atoi(e) / 8 * 8 : -1; }();
     Q8Plan p = plan;
-    if (front_w >= 8 && (front_w / 8 + FLQ + FRQ) * 9 <= QT) p.tw = front_w;
-    int hmax = front_h > 0 ? front_h : p.th;
-    if (front_h <= 0 && DCMT_FRONT_CTAS > 2)
-        while (hmax > 8 && (size_t)DCMT_FRONT_CTAS * (q8_front_smem(hmax, p.tw) + 1024) > (size_t)228 * 1024) --hmax;
-    if (hmax < p.th) {
+    auto height_for = [&](int tw) {
+        int hmax = front_h > 0 ? front_h : plan.th;
+        if (front_h <= 0 && DCMT_FRONT_CTAS > 2)
+            while (hmax > 8 && (size_t)DCMT_FRONT_CTAS * (q8_front_smem(hmax, tw) + 1024) > (size_t)228 * 1024) --hmax;
+        if (hmax >= plan.th) return plan.th;
         const int ny = (p.rows + hmax - 1) / hmax;
-        p.th = (p.rows + ny - 1) / ny;
+        return (p.rows + ny - 1) / ny;
+    };
+    auto width_ok = [&](int tw) { return tw >= 8 && (tw / 8 + FLQ + FRQ) * 9 <= QT; };  // more than 8 rows per sweep: col_pass relies on it
+    if (front_w >= 0) {
+        if (width_ok(front_w)) p.tw = front_w;
+    } else {
+        double best = -1.0;
+        const int widths[4] = {plan.tw, 48, 112, 176};
+        for (int tw : widths) {
+            if (!width_ok(tw)) continue;
+            const int th = height_for(tw), nx = (p.cols + tw - 1) / tw, ny = (p.rows + th - 1) / th;
+            const double work = (double)nx * (tw / 8 + FLQ + FRQ) * ny * (th + FU + FD);
+            const double cost = work * ((tw / 8 + FLQ + FRQ - 1) % 8 == 0 ? 0.93 : 1.0);
+            if (best < 0 || cost < best) { best = cost; p.tw = tw; }
+        }
     }
+    p.th = height_for(p.tw);
     const size_t ncol = (size_t)p.mid_pitch * n_frames;
     if (!p.counters_ready) DCMT_LAUNCH(k_q8_zero_counters, dim3((n_frames + 127) / 128), dim3(128), 0, st, p.ctr, n_frames);
     DCMT_LAUNCH(k_q8_init_cols, dim3((unsigned)((ncol + 255) / 256)), dim3(256), 0, st, p.col_first, p.col_last, ncol);

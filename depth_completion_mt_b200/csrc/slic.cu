@@ -312,14 +312,16 @@ __global__ void __launch_bounds__(256) k_slic_assign(const uint8_t* __restrict__
 // k_slic_assign stages the candidate centres of every 16 x 16 tile from global memory (offset -> item -> centre, dependent
 // loads) between two barriers, and every pixel walks its own 3 x 3 bins in double precision: ~900 instructions per pixel and
 // iteration, 40 % issue-active.  Here a CTA copies ALL centres of its frame -- in bin order, with their integer windows, a
-// float copy and the bin offsets -- into shared memory once (K x 108 bytes: 130 KB at KITTI size) and streams a band of rows
-// through them, one warp per 32 consecutive pixels of a row:
-//   * the warp first finds, one candidate per lane, the centres whose window meets its row segment at all (about 7 of the 14
-//     in the bins around it) and then walks THAT list together: the centre is the same for all lanes (broadcast loads);
+// float record and the bin offsets -- into shared memory once (K x 112 bytes: 140 KB at KITTI size) and streams a band of rows
+// through them.  A warp owns a strip 32 pixels wide and walks down its rows:
+//   * the centres whose window meets the strip's columns at all are found once per row of bins (one candidate per lane, kept
+//     in a register); per image row one compare + ballot gives the ~7 that also cover the row, and the warp walks THAT list
+//     together: the centre is the same for all lanes (broadcast loads), two centres per trip;
 //   * the walk runs in float.  Its result is taken only where the winner beats the runner-up by more than the error bound of
 //     the float evaluation (e_abs, kRel below); the other pixels -- exact ties on symmetric pixels, near ties -- are decided
 //     by the double-precision two-stage procedure of k_slic_assign (slic_resolve), i.e. by the reference's own arithmetic;
-//   * the sums of the new centres are reduced per group of equal winners with one __match_any_sync and four REDUX.
+//   * going down a strip a lane keeps its winner for about `step` rows: the sums of the new centres are run-length
+//     accumulated in registers and added to the CTA's shared-memory sums when the winner changes.
 // Same candidates (the window test is the exact integer one), same winner, same sums: labels and centres stay bit-identical.
 //
 // Error bound of the float stage.  With eps = 2^-24, colours in [0, 255], |c - p| < step + 1 for the coordinates of a covering
@@ -329,7 +331,7 @@ __global__ void __launch_bounds__(256) k_slic_assign(const uint8_t* __restrict__
 // (six roundings at most on the way of any term through the sum of positive terms: 3.6e-7 relative), and
 //   q1_float + 2.5 E < q2_float (1 - 4e-6)   =>   q1 < q2 by far more than the 1e-12 the double stage itself asks for.
 #ifndef DCMT_SLIC_BAND_THREADS
-#define DCMT_SLIC_BAND_THREADS 768  // 80 registers, no spills; 1024 threads would cap them at 64 and spill inside the walk
+#define DCMT_SLIC_BAND_THREADS 768
 #endif
 constexpr int kBandThreads = DCMT_SLIC_BAND_THREADS;
 #ifndef __CUDACC__
@@ -337,7 +339,7 @@ constexpr int kBandThreads = DCMT_SLIC_BAND_THREADS;
 #endif
 
 struct BandSmem {  // layout of the dynamic shared memory for K centres and NB bins
-    size_t off_cent, off_win, off_f4, off_f2, off_sum, off_bin, total;
+    size_t off_cent, off_win, off_rec, off_sum, off_bin, total;
 };
 static inline BandSmem band_smem(int K, int NB) {
     BandSmem b;
@@ -345,8 +347,7 @@ static inline BandSmem band_smem(int K, int NB) {
     auto take = [&](size_t bytes) { const size_t at = o; o = (o + bytes + 15) & ~size_t(15); return at; };  // 16-byte aligned parts
     b.off_cent = take((size_t)K * 5 * sizeof(double));
     b.off_win = take((size_t)K * sizeof(int4));
-    b.off_f4 = take((size_t)K * sizeof(float4));
-    b.off_f2 = take((size_t)K * sizeof(float2));
+    b.off_rec = take((size_t)K * 2 * sizeof(float4));
     b.off_sum = take((size_t)K * 6 * sizeof(unsigned));
     b.off_bin = take((size_t)(NB + 1) * sizeof(int));
     b.total = o;
@@ -356,7 +357,7 @@ static inline BandSmem band_smem(int K, int NB) {
 struct BandView {  // what slic_resolve needs of the CTA's shared memory
     const double* cent;  // [k][5], bin order
     const int4* win;     // {lo_x, width_x, lo_y, width_y}
-    const float2* f2;    // {centre y as float, original centre index (bits)}
+    const float4* rec;   // [k][2]: {L, a, b, x} and {y, lo_x, width_x, original centre index (the last three as integer bits)}
     const int* bin;      // exclusive offsets, nbins + 1
     int bx, by, nc, step;
     double inv_nc2, inv_ns2;
@@ -364,7 +365,8 @@ struct BandView {  // what slic_resolve needs of the CTA's shared memory
 
 // The winner of one pixel by the reference's arithmetic: stage 1, the square-root- and division-free stand-in for compute_dist
 // in double (see k_slic_assign); stage 2, compute_dist itself (:61-69, strict <, lowest centre index) when stage 1 is within
-// 1e-12.  Returns the winner's slot in the bin-ordered list.  Rare (pixels the float walk could not call): kept out of line.
+// 1e-12.  Returns the winner's slot in the bin-ordered list (-1: no window covers the pixel).  Rare (pixels the float walk
+// could not call): kept out of line.
 __device__ __noinline__ int slic_resolve(const BandView& v, int x, int y, unsigned pix) {
     const double L = pix & 255u, A = (pix >> 8) & 255u, B = pix >> 16;
     const int pbx = min(x / v.step, v.bx - 1), pby = min(y / v.step, v.by - 1);
@@ -380,7 +382,7 @@ __device__ __noinline__ int slic_resolve(const BandView& v, int x, int y, unsign
             const double* ce = v.cent + (size_t)k * 5;
             const double d0 = ce[0] - L, d1 = ce[1] - A, d2 = ce[2] - B, dx = ce[3] - xd, dy = ce[4] - yd;
             const double q = (d0 * d0 + d1 * d1 + d2 * d2) * v.inv_nc2 + (dx * dx + dy * dy) * v.inv_ns2;
-            const int c = __float_as_int(v.f2[k].y);
+            const int c = __float_as_int(v.rec[2 * k + 1].w);
             if (q < q1 || (q == q1 && c < best_c)) { q2 = q1; q1 = q; best_c = c; best_k = k; }
             else if (q < q2) q2 = q;
         }
@@ -398,7 +400,7 @@ __device__ __noinline__ int slic_resolve(const BandView& v, int x, int y, unsign
                 const double dc = __dsqrt_rn(__dadd_rn(__dadd_rn(sq(__dsub_rn(ce[0], L)), sq(__dsub_rn(ce[1], A))), sq(__dsub_rn(ce[2], B))));
                 const double ds = __dsqrt_rn(__dadd_rn(sq(__dsub_rn(ce[3], xd)), sq(__dsub_rn(ce[4], yd))));
                 const double d = __dsqrt_rn(__dadd_rn(sq(__ddiv_rn(dc, (double)v.nc)), sq(__ddiv_rn(ds, (double)v.step))));  // ns = step (:105)
-                const int c = __float_as_int(v.f2[k].y);
+                const int c = __float_as_int(v.rec[2 * k + 1].w);
                 if (d < best || (d == best && best_c >= 0 && c < best_c)) { best = d; best_c = c; best_k = k; }
             }
         }
@@ -415,8 +417,7 @@ __global__ void __launch_bounds__(kBandThreads) k_slic_assign_band(const uint8_t
     DCMT_DYN_SMEM(unsigned char, smem);
     double* s_cent = reinterpret_cast<double*>(smem + lay.off_cent);
     int4* s_win = reinterpret_cast<int4*>(smem + lay.off_win);
-    float4* s_f4 = reinterpret_cast<float4*>(smem + lay.off_f4);        // {L, a, b, x} of the centre as floats
-    float2* s_f2 = reinterpret_cast<float2*>(smem + lay.off_f2);        // {y as float, original centre index}
+    float4* s_rec = reinterpret_cast<float4*>(smem + lay.off_rec);
     unsigned* s_sum = reinterpret_cast<unsigned*>(smem + lay.off_sum);  // [k][6]
     int* s_bin = reinterpret_cast<int*>(smem + lay.off_bin);
     const int nbins = bx * by;
@@ -445,20 +446,22 @@ __global__ void __launch_bounds__(kBandThreads) k_slic_assign_band(const uint8_t
         const int lox = (int)__dsub_rn(ce[3], (double)step), loy = (int)__dsub_rn(ce[4], (double)step);
         const int hix = (int)ceil(__dadd_rn(ce[3], (double)step)), hiy = (int)ceil(__dadd_rn(ce[4], (double)step));
         s_win[k] = make_int4(lox, hix - lox, loy, hiy - loy);
-        s_f4[k] = make_float4((float)ce[0], (float)ce[1], (float)ce[2], (float)ce[3]);
-        s_f2[k] = make_float2((float)ce[4], __int_as_float(items[k]));
+        s_rec[2 * k] = make_float4((float)ce[0], (float)ce[1], (float)ce[2], (float)ce[3]);
+        s_rec[2 * k + 1] = make_float4((float)ce[4], __int_as_float(lox), __int_as_float(hix - lox), __int_as_float(items[k]));
     }
     __syncthreads();
     BandView view;
-    view.cent = s_cent; view.win = s_win; view.f2 = s_f2; view.bin = s_bin;
+    view.cent = s_cent; view.win = s_win; view.rec = s_rec; view.bin = s_bin;
     view.bx = bx; view.by = by; view.nc = nc; view.step = step; view.inv_nc2 = inv_nc2; view.inv_ns2 = inv_ns2;
-    const int y_begin = blockIdx.x * band_rows, y_end = min(rows, y_begin + band_rows);
+    const int y_begin = blockIdx.x * band_rows, n_rows = min(rows, y_begin + band_rows) - y_begin;
     const int lane = tid & 31, warp = tid >> 5;
     constexpr int kWarps = kBandThreads / 32;
-    // one item = 32 consecutive pixels of one row; warp w takes items w, w + kWarps, ... (walked without a division per item)
-    const int segs = (cols + 31) >> 5, n_items = (y_end - y_begin) * segs;
-    const int d_row = kWarps / segs, d_seg = kWarps - d_row * segs;
-    int ry = warp / segs, sg = warp - ry * segs;
+    // one item = 32 consecutive pixels of one row; the items of the band in strip-major order (down the first strip of 32 columns,
+    // then down the next), a contiguous run of them per warp
+    const int n_strips = (cols + 31) >> 5, n_items = n_rows * n_strips, per_warp = (n_items + kWarps - 1) / kWarps;
+    int item = warp * per_warp;
+    const int item_end = min(item + per_warp, n_items);
+    int strip = item / max(n_rows, 1), row = item - strip * n_rows;
     const float inc = (float)inv_nc2, ins = (float)inv_ns2;
     const float kInf = __int_as_float(0x7f800000), kRel = 1.0f - 4.0e-6f;
     auto load_px = [&](int r, int s) -> unsigned {  // L | a << 8 | b << 16 of the lane's pixel, 0 beyond the row
@@ -467,83 +470,117 @@ __global__ void __launch_bounds__(kBandThreads) k_slic_assign_band(const uint8_t
         const uint8_t* p = lab + ((size_t)(y_begin + r) * cols + px) * 3;
         return (unsigned)p[0] | ((unsigned)p[1] << 8) | ((unsigned)p[2] << 16);
     };
-    unsigned pix = warp < n_items ? load_px(ry, sg) : 0u;
-    for (int item = warp; item < n_items; item += kWarps) {
-        const int y = y_begin + ry, x0 = sg * 32, x = x0 + lane;
+    unsigned pix = item < item_end ? load_px(row, strip) : 0u;
+    // the lane's candidate: a centre of the bins around (strip, row of bins) whose window meets the strip's columns
+    int cand_k = -1, cand_lo = 0, cand_h = 0, cand_pby = -2, cand_strip = -1;
+    bool cand_overflow = false;  // more than 32 centres in those bins (pathological clustering): every pixel asks slic_resolve
+    // run of consecutive rows of the strip with the same winner: its sums wait in registers.  The rows of a run are consecutive and
+    // its column is the lane's, so the coordinate sums follow from the count: n x, and n y_after - n (n + 1) / 2 for the n rows
+    // that end just before row y_after.
+    int run_key = -1;
+    unsigned run_L = 0, run_a = 0, run_b = 0, run_n = 0;
+    auto flush_run = [&](int xv, int y_after) {
+        if (run_key >= 0) {
+            unsigned* sg = s_sum + (size_t)run_key * 6;
+            atomicAdd(sg + 0, run_L); atomicAdd(sg + 1, run_a); atomicAdd(sg + 2, run_b);
+            atomicAdd(sg + 3, run_n * (unsigned)xv); atomicAdd(sg + 4, run_n * (unsigned)y_after - run_n * (run_n + 1u) / 2u); atomicAdd(sg + 5, run_n);
+        }
+        run_L = run_a = run_b = run_n = 0u;
+        run_key = -1;
+    };
+    for (; item < item_end; ++item) {
+        const int y = y_begin + row, x0 = strip * 32, x = x0 + lane;
         const bool live = x < cols;
+        const int cur_strip = strip;
         // the next item's pixel is on its way while this one is worked on (the loads were a quarter of all stall samples)
-        ry += d_row;
-        sg += d_seg;
-        if (sg >= segs) { sg -= segs; ++ry; }
-        const unsigned pix_next = item + kWarps < n_items ? load_px(ry, sg) : 0u;
-        const float L = (float)(pix & 255u), A = (float)((pix >> 8) & 255u), B = (float)(pix >> 16), xf = (float)x, yf = (float)y;
-        // bins that can hold a centre covering any pixel of the segment
+        if (++row == n_rows) { row = 0; ++strip; }
+        const unsigned pix_next = item + 1 < item_end ? load_px(row, strip) : 0u;
         const int pby = min(fast_div(y, step_magic), by - 1);
-        const int gy_lo = max(pby - 1, 0), gy_hi = min(pby + 1, by - 1);
-        const int gx_lo = max(min(fast_div(x0, step_magic), bx - 1) - 1, 0), gx_hi = min(min(fast_div(x0 + 31, step_magic), bx - 1) + 1, bx - 1);
+        if (pby != cand_pby || cur_strip != cand_strip) {  // warp-uniform: every `step` rows
+            if (cur_strip != cand_strip && cand_strip >= 0) flush_run(x - 32, y_begin + n_rows);  // the runs of the strip above end
+            cand_pby = pby;
+            cand_strip = cur_strip;
+            const int gy_lo = max(pby - 1, 0), gy_hi = min(pby + 1, by - 1);
+            const int gx_lo = max(min(fast_div(x0, step_magic), bx - 1) - 1, 0), gx_hi = min(min(fast_div(x0 + 31, step_magic), bx - 1) + 1, bx - 1);
+            int k = -1, before = 0;
+            for (int gy = gy_lo; gy <= gy_hi; ++gy) {
+                const int k0 = s_bin[gy * bx + gx_lo], k1 = s_bin[gy * bx + gx_hi + 1];  // bins of a row are contiguous
+                if (lane >= before && lane < before + (k1 - k0)) k = k0 + (lane - before);
+                before += k1 - k0;
+            }
+            cand_overflow = before > 32;
+            cand_k = -1;
+            if (k >= 0) {
+                const int4 w = s_win[k];
+                if (w.x < x0 + 32 && w.x + w.y > x0) { cand_k = k; cand_lo = w.z; cand_h = w.w; }
+            }
+        }
+        const float L = (float)(pix & 255u), A = (float)((pix >> 8) & 255u), B = (float)(pix >> 16), xf = (float)x, yf = (float)y;
         float q1 = kInf, q2 = kInf;  // smallest and second smallest float distance over the covering centres
         int best = -1;               // slot of the smallest
-        for (int gy = gy_lo; gy <= gy_hi; ++gy) {
-            const int k0 = s_bin[gy * bx + gx_lo], k1 = s_bin[gy * bx + gx_hi + 1];  // bins of a row are contiguous
-            for (int kb = k0; kb < k1; kb += 32) {
-                bool meets = false;
-                if (kb + lane < k1) {
-                    const int4 w = s_win[kb + lane];
-                    meets = (unsigned)(y - w.z) < (unsigned)w.w && w.x < x0 + 32 && w.x + w.y > x0;
-                }
-                unsigned todo = __ballot_sync(0xffffffffu, meets);
-                while (todo) {
-                    const int k = kb + __ffs((int)todo) - 1;  // the same centre for every lane
-                    todo &= todo - 1;
-                    const int4 w = s_win[k];
-                    const float4 c = s_f4[k];
-                    const float cy = s_f2[k].x;
-                    const float d0 = c.x - L, d1 = c.y - A, d2 = c.z - B, dx = c.w - xf, dy = cy - yf;
-                    float q = (d0 * d0 + d1 * d1 + d2 * d2) * inc + (dx * dx + dy * dy) * ins;
-                    if ((unsigned)(x - w.x) >= (unsigned)w.y) q = kInf;  // the window does not reach this lane's column
-                    q2 = fminf(q2, fmaxf(q1, q));
-                    if (q < q1) best = k;
-                    q1 = fminf(q1, q);
-                }
+        unsigned todo = __ballot_sync(0xffffffffu, cand_k >= 0 && (unsigned)(y - cand_lo) < (unsigned)cand_h);
+        while (todo) {  // two centres per trip (the second may be missing), the same two for every lane
+            const int j0 = __ffs((int)todo) - 1;
+            todo &= todo - 1;
+            const bool two = todo != 0u;
+            const int j1 = two ? __ffs((int)todo) - 1 : j0;
+            todo &= todo - 1;
+            const int ka = __shfl_sync(0xffffffffu, cand_k, j0), kb = __shfl_sync(0xffffffffu, cand_k, j1);
+            const float4 a0 = s_rec[2 * ka], a1 = s_rec[2 * ka + 1], b0 = s_rec[2 * kb], b1 = s_rec[2 * kb + 1];
+            float qa, qb;
+            {
+                const float d0 = a0.x - L, d1 = a0.y - A, d2 = a0.z - B, dx = a0.w - xf, dy = a1.x - yf;
+                qa = (d0 * d0 + d1 * d1 + d2 * d2) * inc + (dx * dx + dy * dy) * ins;
+                if ((unsigned)(x - __float_as_int(a1.y)) >= (unsigned)__float_as_int(a1.z)) qa = kInf;  // the window misses this column
             }
+            {
+                const float d0 = b0.x - L, d1 = b0.y - A, d2 = b0.z - B, dx = b0.w - xf, dy = b1.x - yf;
+                qb = (d0 * d0 + d1 * d1 + d2 * d2) * inc + (dx * dx + dy * dy) * ins;
+                if (!two || (unsigned)(x - __float_as_int(b1.y)) >= (unsigned)__float_as_int(b1.z)) qb = kInf;
+            }
+            q2 = fminf(q2, fmaxf(q1, qa));
+            if (qa < q1) best = ka;
+            q1 = fminf(q1, qa);
+            q2 = fminf(q2, fmaxf(q1, qb));
+            if (qb < q1) best = kb;
+            q1 = fminf(q1, qb);
         }
         int key = -1;
-        if (live && best >= 0) {
-            if (!(q1 + e_abs < q2 * kRel)) best = slic_resolve(view, x, y, pix);  // too close for floats
-            key = best;
+        if (live) {
+            if (cand_overflow) key = slic_resolve(view, x, y, pix);
+            else if (best >= 0) key = (q1 + e_abs < q2 * kRel) ? best : slic_resolve(view, x, y, pix);  // too close for floats
         }
-        if (key >= 0) labels[(size_t)y * cols + x] = __float_as_int(s_f2[key].y);
-        // centre sums (integers: exact in any order): lanes with the same winner reduce among themselves, the lowest adds into the
-        // CTA's shared-memory sums; pixels that keep a stale label (no window covers them) add to global memory directly
-        {
-            const unsigned peers = __match_any_sync(0xffffffffu, (unsigned)key);
-            const unsigned v0 = __reduce_add_sync(peers, pix & 255u), v1 = __reduce_add_sync(peers, (pix >> 8) & 255u),
-                           v2 = __reduce_add_sync(peers, pix >> 16), v3 = __reduce_add_sync(peers, (unsigned)x);
-            if (key >= 0 && lane == __ffs((int)peers) - 1) {
-                const unsigned n = (unsigned)__popc(peers);
-                unsigned* sg6 = s_sum + (size_t)key * 6;
-                atomicAdd(sg6 + 0, v0); atomicAdd(sg6 + 1, v1); atomicAdd(sg6 + 2, v2);
-                atomicAdd(sg6 + 3, v3); atomicAdd(sg6 + 4, n * (unsigned)y); atomicAdd(sg6 + 5, n);
-            }
+        if (key >= 0) labels[(size_t)y * cols + x] = __float_as_int(s_rec[2 * key + 1].w);
+        // centre sums (integers: exact in any order)
+        if (key != run_key) {
+            flush_run(x, y);
+            run_key = key;
         }
-        if (live && key < 0) {
+        if (key >= 0) {
+            run_L += pix & 255u; run_a += (pix >> 8) & 255u; run_b += pix >> 16;
+            run_n += 1u;
+        } else if (live) {  // no window covers the pixel: it keeps its label and counts for that centre (global memory directly)
             const int label = labels[(size_t)y * cols + x];
             if (label != -1) {
-                unsigned long long* sg6 = sums + (size_t)label * 6;
-                atomicAdd(sg6 + 0, (unsigned long long)(pix & 255u));
-                atomicAdd(sg6 + 1, (unsigned long long)((pix >> 8) & 255u));
-                atomicAdd(sg6 + 2, (unsigned long long)(pix >> 16));
-                atomicAdd(sg6 + 3, (unsigned long long)x);
-                atomicAdd(sg6 + 4, (unsigned long long)y);
-                atomicAdd(sg6 + 5, 1ull);
+                unsigned long long* sg = sums + (size_t)label * 6;
+                atomicAdd(sg + 0, (unsigned long long)(pix & 255u));
+                atomicAdd(sg + 1, (unsigned long long)((pix >> 8) & 255u));
+                atomicAdd(sg + 2, (unsigned long long)(pix >> 16));
+                atomicAdd(sg + 3, (unsigned long long)x);
+                atomicAdd(sg + 4, (unsigned long long)y);
+                atomicAdd(sg + 5, 1ull);
             }
         }
         pix = pix_next;
     }
+    if (cand_strip >= 0) {  // the warp had items: its last one was row (item_end - 1) % n_rows of strip cand_strip
+        const int last_row = (item_end - 1) - cand_strip * n_rows;
+        flush_run(cand_strip * 32 + lane, y_begin + last_row + 1);
+    }
     __syncthreads();
     for (int i = tid; i < n_binned * 6; i += kBandThreads) {
         const unsigned v = s_sum[i];
-        if (v) atomicAdd(sums + (size_t)__float_as_int(s_f2[i / 6].y) * 6 + (i % 6), (unsigned long long)v);
+        if (v) atomicAdd(sums + (size_t)__float_as_int(s_rec[2 * (i / 6) + 1].w) * 6 + (i % 6), (unsigned long long)v);
     }
 }
 
@@ -589,18 +626,25 @@ cudaError_t slic_run(const uint8_t* lab, int rows, int cols, int n_frames, int s
     if (n_centers == 0 || n_frames == 0) return cudaGetLastError();
     DCMT_LAUNCH(k_slic_init, dim3(cb, n_frames), dim3(128), 0, st, lab, rows, cols, step, ny, n_centers, w.centers);
     // assignment kernel: bands of rows with the frame's centres in shared memory when they fit (one CTA of 768 threads per SM),
-    // else 16 x 16 tiles.  DCMT_SLIC_BAND_MIN_FRAMES: batch size from which the band kernel is used (experiments).
+    // else 16 x 16 tiles.  Measured on the B200 (step 18, 1 254 centres), frames/s for batches of 1 / 2 / 8 / 64 / 256 frames:
+    // bands 2.1 k / 4.1 k / 9.2 k / 12.7 k / 14.1 k, tiles 2.5 k / 3.4 k / 4.9 k / 3.0 k / 3.0 k -- a single frame keeps the tiles
+    // (a band CTA copies all centres first).  DCMT_SLIC_BAND_MIN_FRAMES: batch size from which the band kernel is used.
     const BandSmem lay = band_smem(n_centers, w.bins_x * w.bins_y);
-    static const int band_min = [] { const char* e = getenv("DCMT_SLIC_BAND_MIN_FRAMES"); return e ? atoi(e) : 1; }();
+    static const int band_min = [] { const char* e = getenv("DCMT_SLIC_BAND_MIN_FRAMES"); return e ? atoi(e) : 2; }();
     constexpr size_t kBandSmemMax = 200 * 1024;
     const bool bands_fit = lay.total <= kBandSmemMax && n_frames >= band_min;
     int n_bands = 1, band_rows = rows;
     float e_abs = 0.f;
     if (bands_fit) {
-        // about four CTAs per SM over the run, but bands of at least 4 rows (every CTA copies the whole frame's centres)
-        n_bands = (4 * 148 + n_frames - 1) / n_frames;
-        if (n_bands > rows / 4) n_bands = rows / 4;
-        if (n_bands < 1) n_bands = 1;
+        // one CTA per SM at a time: the number of bands per frame (of at least 4 rows: every CTA copies the whole frame's centres) that
+        // fills the last wave of CTAs best, slightly preferring fewer bands
+        const int max_bands = rows / 4 < 1 ? 1 : (rows / 4 > 64 ? 64 : rows / 4);
+        double best_score = -1.0;
+        for (int nb = 1; nb <= max_bands; ++nb) {
+            const double ctas = (double)nb * n_frames, waves = (double)((nb * (long)n_frames + 147) / 148);
+            const double score = ctas / (waves * 148.0) - 0.002 * nb;
+            if (score > best_score) { best_score = score; n_bands = nb; }
+        }
         band_rows = (rows + n_bands - 1) / n_bands;
         // a CTA sums coordinates in 32 bits: band pixels x largest coordinate must stay below 2^32
         while (band_rows > 1 && (unsigned long long)band_rows * cols * (rows > cols ? rows : cols) >= (1ull << 32)) band_rows = (band_rows + 1) / 2;
