@@ -312,14 +312,15 @@ __global__ void __launch_bounds__(256) k_slic_assign(const uint8_t* __restrict__
 // k_slic_assign stages the candidate centres of every 16 x 16 tile from global memory (offset -> item -> centre, dependent
 // loads) between two barriers, and every pixel walks its own 3 x 3 bins in double precision: ~900 instructions per pixel and
 // iteration, 40 % issue-active.  Here a CTA copies ALL centres of its frame -- in bin order, with their integer windows, a
-// float record and the bin offsets -- into shared memory once (K x 112 bytes: 140 KB at KITTI size) and streams a band of rows
+// float record and the bin offsets -- into shared memory once (K x 72 bytes: 90 KB at KITTI size, two CTAs per SM) and streams a band of rows
 // through them.  A warp owns a strip 32 pixels wide and walks down its rows:
 //   * the centres whose window meets the strip's columns at all are found once per row of bins (one candidate per lane, kept
 //     in a register); per image row one compare + ballot gives the ~7 that also cover the row, and the warp walks THAT list
 //     together: the centre is the same for all lanes (broadcast loads), two centres per trip;
 //   * the walk runs in float.  Its result is taken only where the winner beats the runner-up by more than the error bound of
 //     the float evaluation (e_abs, kRel below); the other pixels -- exact ties on symmetric pixels, near ties -- are decided
-//     by the double-precision two-stage procedure of k_slic_assign (slic_resolve), i.e. by the reference's own arithmetic;
+//     by the double-precision two-stage procedure of k_slic_assign (slic_resolve), i.e. by the reference's own arithmetic --
+//     after the walk, from a short list in shared memory (a call inside the walk cost it its registers: spills, stalled loads);
 //   * going down a strip a lane keeps its winner for about `step` rows: the sums of the new centres are run-length
 //     accumulated in registers and added to the CTA's shared-memory sums when the winner changes.
 // Same candidates (the window test is the exact integer one), same winner, same sums: labels and centres stay bit-identical.
@@ -331,25 +332,41 @@ __global__ void __launch_bounds__(256) k_slic_assign(const uint8_t* __restrict__
 // (six roundings at most on the way of any term through the sum of positive terms: 3.6e-7 relative), and
 //   q1_float + 2.5 E < q2_float (1 - 4e-6)   =>   q1 < q2 by far more than the 1e-12 the double stage itself asks for.
 #ifndef DCMT_SLIC_BAND_THREADS
-#define DCMT_SLIC_BAND_THREADS 768
+#define DCMT_SLIC_BAND_THREADS 384
 #endif
 constexpr int kBandThreads = DCMT_SLIC_BAND_THREADS;
+#ifndef DCMT_SLIC_CENT_SMEM
+#define DCMT_SLIC_CENT_SMEM 0  // 1: the centres in double precision in shared memory as well (slic_resolve reads them; + 40 bytes per centre)
+#endif
 #ifndef __CUDACC__
 #define __noinline__ __attribute__((noinline))
 #endif
 
+#ifndef DCMT_SLIC_PREFETCH_ROWS
+#define DCMT_SLIC_PREFETCH_ROWS 4
+#endif
+constexpr int kBandPrefetchRows = DCMT_SLIC_PREFETCH_ROWS;  // 0: no L2 prefetch
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+#if !defined(DCMT_EMU)
+    if (kBandPrefetchRows > 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
+constexpr int kBandQueue = 1024;  // deferred pixels a CTA lists (more: it walks its band again)
 struct BandSmem {  // layout of the dynamic shared memory for K centres and NB bins
-    size_t off_cent, off_win, off_rec, off_sum, off_bin, total;
+    size_t off_cent, off_win, off_rec, off_sum, off_bin, off_queue, total;
 };
 static inline BandSmem band_smem(int K, int NB) {
     BandSmem b;
     size_t o = 0;
     auto take = [&](size_t bytes) { const size_t at = o; o = (o + bytes + 15) & ~size_t(15); return at; };  // 16-byte aligned parts
-    b.off_cent = take((size_t)K * 5 * sizeof(double));
+    b.off_cent = take(DCMT_SLIC_CENT_SMEM ? (size_t)K * 5 * sizeof(double) : 0);
     b.off_win = take((size_t)K * sizeof(int4));
     b.off_rec = take((size_t)K * 2 * sizeof(float4));
     b.off_sum = take((size_t)K * 6 * sizeof(unsigned));
-    b.off_bin = take((size_t)(NB + 1) * sizeof(int));
+    b.off_bin = take((size_t)(NB + 2) * sizeof(int));  // + the CTA's count of deferred pixels
+    b.off_queue = take((size_t)kBandQueue * sizeof(int));
     b.total = o;
     return b;
 }
@@ -413,13 +430,16 @@ __global__ void __launch_bounds__(kBandThreads) k_slic_assign_band(const uint8_t
                                                                     const int* __restrict__ offset, const int* __restrict__ items,
                                                                     const double* __restrict__ sorted, int32_t* __restrict__ labels,
                                                                     unsigned long long* __restrict__ sums, int n_centers, double inv_nc2,
-                                                                    double inv_ns2, float e_abs, BandSmem lay) {
+                                                                    double inv_ns2, float e_abs, int cand_max, BandSmem lay) {
     DCMT_DYN_SMEM(unsigned char, smem);
     double* s_cent = reinterpret_cast<double*>(smem + lay.off_cent);
     int4* s_win = reinterpret_cast<int4*>(smem + lay.off_win);
     float4* s_rec = reinterpret_cast<float4*>(smem + lay.off_rec);
     unsigned* s_sum = reinterpret_cast<unsigned*>(smem + lay.off_sum);  // [k][6]
     int* s_bin = reinterpret_cast<int*>(smem + lay.off_bin);
+    int* s_deferred = s_bin + (bx * by + 1);  // pixels of this CTA left to slic_resolve ...
+    int* s_queue = reinterpret_cast<int*>(smem + lay.off_queue);  // ... and the offsets of the first kBandQueue of them
+    constexpr int kDeferred = 0x40000000;   // marker in `labels`: kDeferred | (old label + 1); labels themselves stay far below
     const int nbins = bx * by;
     {  // frame
         const size_t f = blockIdx.y;
@@ -431,16 +451,29 @@ __global__ void __launch_bounds__(kBandThreads) k_slic_assign_band(const uint8_t
         sorted += f * n_centers * 5;
     }
     const int tid = threadIdx.x;
+    if (tid == 0) *s_deferred = 0;
     for (int b = tid; b <= nbins; b += kBandThreads) s_bin[b] = offset[b];
     __syncthreads();
     const int n_binned = s_bin[nbins];  // centres that are not NaN
     for (int i = tid; i < n_binned * 6; i += kBandThreads) s_sum[i] = 0u;
+    auto add_stale = [&](int label, unsigned px, int x, int y) {  // a pixel that keeps its label counts for that centre: global memory directly
+        if (label == -1) return;
+        unsigned long long* sg = sums + (size_t)label * 6;
+        atomicAdd(sg + 0, (unsigned long long)(px & 255u));
+        atomicAdd(sg + 1, (unsigned long long)((px >> 8) & 255u));
+        atomicAdd(sg + 2, (unsigned long long)(px >> 16));
+        atomicAdd(sg + 3, (unsigned long long)x);
+        atomicAdd(sg + 4, (unsigned long long)y);
+        atomicAdd(sg + 5, 1ull);
+    };
     for (int k = tid; k < n_binned; k += kBandThreads) {
         double ce[5];
 #pragma unroll
         for (int q = 0; q < 5; ++q) ce[q] = sorted[(size_t)k * 5 + q];
+        if (DCMT_SLIC_CENT_SMEM) {
 #pragma unroll
-        for (int q = 0; q < 5; ++q) s_cent[(size_t)k * 5 + q] = ce[q];
+            for (int q = 0; q < 5; ++q) s_cent[(size_t)k * 5 + q] = ce[q];
+        }
         // for (int k = cx - step; k < cx + step; k++) (:123): truncation towards zero, then a double comparison; for integer k,
         // k < c + step <=> k < ceil(c + step)
         const int lox = (int)__dsub_rn(ce[3], (double)step), loy = (int)__dsub_rn(ce[4], (double)step);
@@ -450,9 +483,6 @@ __global__ void __launch_bounds__(kBandThreads) k_slic_assign_band(const uint8_t
         s_rec[2 * k + 1] = make_float4((float)ce[4], __int_as_float(lox), __int_as_float(hix - lox), __int_as_float(items[k]));
     }
     __syncthreads();
-    BandView view;
-    view.cent = s_cent; view.win = s_win; view.rec = s_rec; view.bin = s_bin;
-    view.bx = bx; view.by = by; view.nc = nc; view.step = step; view.inv_nc2 = inv_nc2; view.inv_ns2 = inv_ns2;
     const int y_begin = blockIdx.x * band_rows, n_rows = min(rows, y_begin + band_rows) - y_begin;
     const int lane = tid & 31, warp = tid >> 5;
     constexpr int kWarps = kBandThreads / 32;
@@ -464,42 +494,42 @@ __global__ void __launch_bounds__(kBandThreads) k_slic_assign_band(const uint8_t
     int strip = item / max(n_rows, 1), row = item - strip * n_rows;
     const float inc = (float)inv_nc2, ins = (float)inv_ns2;
     const float kInf = __int_as_float(0x7f800000), kRel = 1.0f - 4.0e-6f;
-    auto load_px = [&](int r, int s) -> unsigned {  // L | a << 8 | b << 16 of the lane's pixel, 0 beyond the row
-        const int px = s * 32 + lane;
-        if (px >= cols) return 0u;
-        const uint8_t* p = lab + ((size_t)(y_begin + r) * cols + px) * 3;
-        return (unsigned)p[0] | ((unsigned)p[1] << 8) | ((unsigned)p[2] << 16);
-    };
-    unsigned pix = item < item_end ? load_px(row, strip) : 0u;
-    // the lane's candidate: a centre of the bins around (strip, row of bins) whose window meets the strip's columns
-    int cand_k = -1, cand_lo = 0, cand_h = 0, cand_pby = -2, cand_strip = -1;
-    bool cand_overflow = false;  // more than 32 centres in those bins (pathological clustering): every pixel asks slic_resolve
-    // run of consecutive rows of the strip with the same winner: its sums wait in registers.  The rows of a run are consecutive and
-    // its column is the lane's, so the coordinate sums follow from the count: n x, and n y_after - n (n + 1) / 2 for the n rows
-    // that end just before row y_after.
+    // offset of the lane's pixel in the frame (the host keeps rows x cols x 3 below 2^31 for this kernel): + cols per row of the strip
+    auto px_offset = [&](int r, int s) { return (y_begin + r) * cols + s * 32 + lane; };
+    int off = px_offset(row, strip);
+    unsigned pix = 0u;  // L | a << 8 | b << 16 of the lane's pixel, 0 beyond the row
+    if (item < item_end && strip * 32 + lane < cols) {
+        const uint8_t* p = lab + (size_t)off * 3;
+        pix = (unsigned)p[0] | ((unsigned)p[1] << 8) | ((unsigned)p[2] << 16);
+    }
+    // the lane's candidate: a centre of the bins around (strip, row of bins) whose window meets the strip's columns (its slot; -1: none;
+    // -2: more than 32 centres in those bins -- pathological clustering -- every pixel asks slic_resolve), the rows of its window as
+    // lo << 12 | height, and the item at which the warp leaves the row of bins or the strip and looks again
+    int cand = -1, cand_rows = 0, rebuild_at = item;
+    // run of consecutive rows of the strip with the same winner: its sums wait in registers, two 16-bit fields per register (a run is
+    // cut at 255 rows: 255 x 255 < 2^16).  The rows of a run are consecutive and its column is the lane's, so the coordinate sums
+    // follow from the count: n x, and n y_after - n (n + 1) / 2 for the n rows that end just before row y_after.
     int run_key = -1;
-    unsigned run_L = 0, run_a = 0, run_b = 0, run_n = 0;
+    unsigned run_La = 0u, run_bn = 0u;  // L | a << 16,  b | n << 16
     auto flush_run = [&](int xv, int y_after) {
         if (run_key >= 0) {
             unsigned* sg = s_sum + (size_t)run_key * 6;
-            atomicAdd(sg + 0, run_L); atomicAdd(sg + 1, run_a); atomicAdd(sg + 2, run_b);
-            atomicAdd(sg + 3, run_n * (unsigned)xv); atomicAdd(sg + 4, run_n * (unsigned)y_after - run_n * (run_n + 1u) / 2u); atomicAdd(sg + 5, run_n);
+            const unsigned n = run_bn >> 16;
+            atomicAdd(sg + 0, run_La & 0xffffu); atomicAdd(sg + 1, run_La >> 16); atomicAdd(sg + 2, run_bn & 0xffffu);
+            atomicAdd(sg + 3, n * (unsigned)xv); atomicAdd(sg + 4, n * (unsigned)y_after - n * (n + 1u) / 2u); atomicAdd(sg + 5, n);
         }
-        run_L = run_a = run_b = run_n = 0u;
+        run_La = run_bn = 0u;
         run_key = -1;
     };
     for (; item < item_end; ++item) {
         const int y = y_begin + row, x0 = strip * 32, x = x0 + lane;
         const bool live = x < cols;
-        const int cur_strip = strip;
-        // the next item's pixel is on its way while this one is worked on (the loads were a quarter of all stall samples)
-        if (++row == n_rows) { row = 0; ++strip; }
-        const unsigned pix_next = item + 1 < item_end ? load_px(row, strip) : 0u;
-        const int pby = min(fast_div(y, step_magic), by - 1);
-        if (pby != cand_pby || cur_strip != cand_strip) {  // warp-uniform: every `step` rows
-            if (cur_strip != cand_strip && cand_strip >= 0) flush_run(x - 32, y_begin + n_rows);  // the runs of the strip above end
-            cand_pby = pby;
-            cand_strip = cur_strip;
+        const int cur_off = off;
+        if (item == rebuild_at) {  // warp-uniform: every `step` rows
+            if (row == 0) flush_run(x - 32, y_begin + n_rows);  // the runs of the strip before end with it
+            const int pby = min(fast_div(y, step_magic), by - 1);
+            const int rows_in_cell = pby < by - 1 ? (pby + 1) * step - y : n_rows;
+            rebuild_at = item + min(rows_in_cell, n_rows - row);
             const int gy_lo = max(pby - 1, 0), gy_hi = min(pby + 1, by - 1);
             const int gx_lo = max(min(fast_div(x0, step_magic), bx - 1) - 1, 0), gx_hi = min(min(fast_div(x0 + 31, step_magic), bx - 1) + 1, bx - 1);
             int k = -1, before = 0;
@@ -508,25 +538,36 @@ __global__ void __launch_bounds__(kBandThreads) k_slic_assign_band(const uint8_t
                 if (lane >= before && lane < before + (k1 - k0)) k = k0 + (lane - before);
                 before += k1 - k0;
             }
-            cand_overflow = before > 32;
-            cand_k = -1;
+            cand = -1;
             if (k >= 0) {
                 const int4 w = s_win[k];
-                if (w.x < x0 + 32 && w.x + w.y > x0) { cand_k = k; cand_lo = w.z; cand_h = w.w; }
+                if (w.x < x0 + 32 && w.x + w.y > x0) { cand = k; cand_rows = (w.z << 12) | w.w; }
             }
+            if (before > cand_max) cand = -2;  // 32, the lanes of a warp (less in tests of this path)
         }
-        const float L = (float)(pix & 255u), A = (float)((pix >> 8) & 255u), B = (float)(pix >> 16), xf = (float)x, yf = (float)y;
+        // the next item's pixel is on its way while this one is worked on: three byte loads now, put together at the bottom of the
+        // loop (warps issue in order: an instruction that needs the bytes would wait here for them)
+        if (++row == n_rows) { row = 0; ++strip; off = px_offset(0, strip); } else off += cols;
+        unsigned next_L = 0u, next_a = 0u, next_b = 0u;
+        if (item + 1 < item_end && strip * 32 + lane < cols) {
+            const uint8_t* p = lab + (size_t)off * 3;
+            next_L = p[0]; next_a = p[1]; next_b = p[2];
+            // ... and the rows after it on their way into L2 (one item of work did not cover the latency of these loads from DRAM)
+            if (row + kBandPrefetchRows < n_rows) prefetch_l2(p + (size_t)kBandPrefetchRows * cols * 3);
+        }
+        const float xf = (float)x, yf = (float)y;
         float q1 = kInf, q2 = kInf;  // smallest and second smallest float distance over the covering centres
         int best = -1;               // slot of the smallest
-        unsigned todo = __ballot_sync(0xffffffffu, cand_k >= 0 && (unsigned)(y - cand_lo) < (unsigned)cand_h);
+        unsigned todo = __ballot_sync(0xffffffffu, cand >= 0 && (unsigned)(y - (cand_rows >> 12)) < (unsigned)(cand_rows & 4095));
         while (todo) {  // two centres per trip (the second may be missing), the same two for every lane
             const int j0 = __ffs((int)todo) - 1;
             todo &= todo - 1;
             const bool two = todo != 0u;
             const int j1 = two ? __ffs((int)todo) - 1 : j0;
             todo &= todo - 1;
-            const int ka = __shfl_sync(0xffffffffu, cand_k, j0), kb = __shfl_sync(0xffffffffu, cand_k, j1);
+            const int ka = __shfl_sync(0xffffffffu, cand, j0), kb = __shfl_sync(0xffffffffu, cand, j1);
             const float4 a0 = s_rec[2 * ka], a1 = s_rec[2 * ka + 1], b0 = s_rec[2 * kb], b1 = s_rec[2 * kb + 1];
+            const float L = (float)(pix & 255u), A = (float)((pix >> 8) & 255u), B = (float)(pix >> 16);  // here: three registers less across the loop
             float qa, qb;
             {
                 const float d0 = a0.x - L, d1 = a0.y - A, d2 = a0.z - B, dx = a0.w - xf, dy = a1.x - yf;
@@ -546,36 +587,77 @@ __global__ void __launch_bounds__(kBandThreads) k_slic_assign_band(const uint8_t
             q1 = fminf(q1, qb);
         }
         int key = -1;
+        bool deferred = false;  // too close for floats (or no candidate list): decided after the walk, by slic_resolve
         if (live) {
-            if (cand_overflow) key = slic_resolve(view, x, y, pix);
-            else if (best >= 0) key = (q1 + e_abs < q2 * kRel) ? best : slic_resolve(view, x, y, pix);  // too close for floats
+            if (cand == -2) deferred = true;
+            else if (best >= 0) {
+                if (q1 + e_abs < q2 * kRel) key = best;
+                else deferred = true;
+            }
         }
-        if (key >= 0) labels[(size_t)y * cols + x] = __float_as_int(s_rec[2 * key + 1].w);
+        if (key >= 0) labels[cur_off] = __float_as_int(s_rec[2 * key + 1].w);
+        if (deferred) {  // rare: leave a marker that keeps the old label (it stands if no window covers the pixel after all)
+            labels[cur_off] = kDeferred | (labels[cur_off] + 1);
+            const int slot = atomicAdd(s_deferred, 1);
+            if (slot < kBandQueue) s_queue[slot] = cur_off;
+        }
         // centre sums (integers: exact in any order)
-        if (key != run_key) {
+        if (key != run_key || run_bn >= (255u << 16)) {
             flush_run(x, y);
             run_key = key;
         }
         if (key >= 0) {
-            run_L += pix & 255u; run_a += (pix >> 8) & 255u; run_b += pix >> 16;
-            run_n += 1u;
-        } else if (live) {  // no window covers the pixel: it keeps its label and counts for that centre (global memory directly)
-            const int label = labels[(size_t)y * cols + x];
-            if (label != -1) {
-                unsigned long long* sg = sums + (size_t)label * 6;
-                atomicAdd(sg + 0, (unsigned long long)(pix & 255u));
-                atomicAdd(sg + 1, (unsigned long long)((pix >> 8) & 255u));
-                atomicAdd(sg + 2, (unsigned long long)(pix >> 16));
-                atomicAdd(sg + 3, (unsigned long long)x);
-                atomicAdd(sg + 4, (unsigned long long)y);
-                atomicAdd(sg + 5, 1ull);
+            run_La += __byte_perm(pix, 0u, 0x4140);  // L | a << 16
+            run_bn += (pix >> 16) + 0x10000u;         // b | 1 << 16
+        } else if (live && !deferred) {  // no window covers the pixel: it keeps its label and counts for that centre
+            add_stale(labels[cur_off], pix, x, y);
+        }
+        pix = next_L | (next_a << 8) | (next_b << 16);
+    }
+    if (item_end > warp * per_warp) {  // the warp had items: its last one tells where its open runs end
+        const int last = item_end - 1, last_strip = last / n_rows;
+        flush_run(last_strip * 32 + lane, y_begin + (last - last_strip * n_rows) + 1);
+    }
+    __syncthreads();
+    const int n_deferred = *s_deferred;
+    if (n_deferred > 0) {
+        // the marked pixels by the reference's arithmetic: from the queue, one per thread; when it overflowed (flat images: every pixel
+        // ties), in a second walk over the same items (every lane meets the pixels it marked itself)
+        BandView view;
+        view.cent = DCMT_SLIC_CENT_SMEM ? s_cent : sorted; view.win = s_win; view.rec = s_rec; view.bin = s_bin;
+        view.bx = bx; view.by = by; view.nc = nc; view.step = step; view.inv_nc2 = inv_nc2; view.inv_ns2 = inv_ns2;
+        auto decide = [&](int o, int x, int y) {
+            const int marker = labels[o];
+            if (marker < kDeferred) return;
+            const uint8_t* p = lab + (size_t)o * 3;
+            const unsigned px = (unsigned)p[0] | ((unsigned)p[1] << 8) | ((unsigned)p[2] << 16);
+            const int key = slic_resolve(view, x, y, px);
+            if (key >= 0) {
+                labels[o] = __float_as_int(s_rec[2 * key + 1].w);
+                unsigned* sg = s_sum + (size_t)key * 6;
+                atomicAdd(sg + 0, px & 255u); atomicAdd(sg + 1, (px >> 8) & 255u); atomicAdd(sg + 2, px >> 16);
+                atomicAdd(sg + 3, (unsigned)x); atomicAdd(sg + 4, (unsigned)y); atomicAdd(sg + 5, 1u);
+            } else {
+                const int old_label = (marker & (kDeferred - 1)) - 1;
+                labels[o] = old_label;
+                add_stale(old_label, px, x, y);
+            }
+        };
+        if (n_deferred <= kBandQueue) {
+            for (int i = tid; i < n_deferred; i += kBandThreads) {
+                const int o = s_queue[i], y = o / cols;
+                decide(o, o - y * cols, y);
+            }
+        } else {
+            item = warp * per_warp;
+            strip = item / max(n_rows, 1);
+            row = item - strip * n_rows;
+            for (; item < item_end; ++item) {
+                const int x = strip * 32 + lane, y = y_begin + row, o = px_offset(row, strip);
+                if (++row == n_rows) { row = 0; ++strip; }
+                if (x < cols) decide(o, x, y);
             }
         }
-        pix = pix_next;
-    }
-    if (cand_strip >= 0) {  // the warp had items: its last one was row (item_end - 1) % n_rows of strip cand_strip
-        const int last_row = (item_end - 1) - cand_strip * n_rows;
-        flush_run(cand_strip * 32 + lane, y_begin + last_row + 1);
     }
     __syncthreads();
     for (int i = tid; i < n_binned * 6; i += kBandThreads) {
@@ -625,24 +707,27 @@ cudaError_t slic_run(const uint8_t* lab, int rows, int cols, int n_frames, int s
     DCMT_LAUNCH(k_slic_fill_labels, dim3((unsigned)((npx + 255) / 256)), dim3(256), 0, st, labels, npx);
     if (n_centers == 0 || n_frames == 0) return cudaGetLastError();
     DCMT_LAUNCH(k_slic_init, dim3(cb, n_frames), dim3(128), 0, st, lab, rows, cols, step, ny, n_centers, w.centers);
-    // assignment kernel: bands of rows with the frame's centres in shared memory when they fit (one CTA of 768 threads per SM),
+    // assignment kernel: bands of rows with the frame's centres in shared memory when they fit (K x 72 bytes: two CTAs per SM at KITTI size),
     // else 16 x 16 tiles.  Measured on the B200 (step 18, 1 254 centres), frames/s for batches of 1 / 2 / 8 / 64 / 256 frames:
     // bands 2.1 k / 4.1 k / 9.2 k / 12.7 k / 14.1 k, tiles 2.5 k / 3.4 k / 4.9 k / 3.0 k / 3.0 k -- a single frame keeps the tiles
     // (a band CTA copies all centres first).  DCMT_SLIC_BAND_MIN_FRAMES: batch size from which the band kernel is used.
     const BandSmem lay = band_smem(n_centers, w.bins_x * w.bins_y);
     static const int band_min = [] { const char* e = getenv("DCMT_SLIC_BAND_MIN_FRAMES"); return e ? atoi(e) : 2; }();
+    // DCMT_SLIC_CAND_MAX (tests): fewer than 32 candidates per warp before the walk gives up and every pixel asks slic_resolve
+    static const int cand_max = [] { const char* e = getenv("DCMT_SLIC_CAND_MAX"); const int v = e ? atoi(e) : 32; return v < 0 ? 0 : (v > 32 ? 32 : v); }();
     constexpr size_t kBandSmemMax = 200 * 1024;
-    const bool bands_fit = lay.total <= kBandSmemMax && n_frames >= band_min;
+    const bool bands_fit = lay.total <= kBandSmemMax && n_frames >= band_min && (long long)rows * cols * 3 < (1ll << 31) && step <= 2000;
     int n_bands = 1, band_rows = rows;
     float e_abs = 0.f;
     if (bands_fit) {
-        // one CTA per SM at a time: the number of bands per frame (of at least 4 rows: every CTA copies the whole frame's centres) that
+        // one or two CTAs per SM at a time: the number of bands per frame (of at least 4 rows: every CTA copies the whole frame's centres) that
         // fills the last wave of CTAs best, slightly preferring fewer bands
         const int max_bands = rows / 4 < 1 ? 1 : (rows / 4 > 64 ? 64 : rows / 4);
+        const long per_sm = (233472 / (lay.total + 1024) >= 2 && 2 * kBandThreads <= 2048) ? 2 : 1, wave = 148 * per_sm;  // resident CTAs
         double best_score = -1.0;
         for (int nb = 1; nb <= max_bands; ++nb) {
-            const double ctas = (double)nb * n_frames, waves = (double)((nb * (long)n_frames + 147) / 148);
-            const double score = ctas / (waves * 148.0) - 0.002 * nb;
+            const double ctas = (double)nb * n_frames, waves = (double)((nb * (long)n_frames + wave - 1) / wave);
+            const double score = ctas / (waves * wave) - 0.002 * nb;
             if (score > best_score) { best_score = score; n_bands = nb; }
         }
         band_rows = (rows + n_bands - 1) / n_bands;
@@ -663,7 +748,7 @@ cudaError_t slic_run(const uint8_t* lab, int rows, int cols, int n_frames, int s
         if (bands_fit)
             DCMT_LAUNCH(k_slic_assign_band, dim3(n_bands, n_frames), dim3(kBandThreads), lay.total, st, lab, rows, cols, step, nc, w.bins_x,
                         w.bins_y, step_magic, band_rows, w.bin_count, w.bin_items, w.sorted, labels, w.sums, n_centers,
-                        1.0 / ((double)nc * (double)nc), 1.0 / ((double)step * (double)step), e_abs, lay);
+                        1.0 / ((double)nc * (double)nc), 1.0 / ((double)step * (double)step), e_abs, cand_max, lay);
         else
             DCMT_LAUNCH(k_slic_assign, dim3((cols + 15) / 16, (rows + 15) / 16, n_frames), dim3(16, 16), 0, st, lab, rows, cols, step, nc,
                         w.bins_x, w.bins_y, w.centers, w.bin_count, w.bin_items, w.sorted, labels, w.sums, n_centers,

@@ -63,9 +63,9 @@ def test_emu_slic(emu_lib):
 
 
 def check_tile_kernel(lib, to_backend, rows, cols, step):
-    """More centres than the band kernel's shared memory holds (K x 108 bytes > 200 KB): the 16 x 16 tile kernel runs."""
+    """More centres than the band kernel's shared memory holds (K x 72 bytes > 200 KB): the 16 x 16 tile kernel runs."""
     k = lib.dcmt_slic_center_count(rows, cols, step)
-    assert k * 108 > 200 * 1024
+    assert k * 72 > 200 * 1024
     lab = synth.lab_image(61, rows, cols)
     labels, centers = api.generate_superpixels(to_backend(lab), step, 40, return_centers=True, lib=lib)
     labels, centers = (a if isinstance(a, np.ndarray) else a.cpu().numpy() for a in (labels, centers))
@@ -74,8 +74,40 @@ def check_tile_kernel(lib, to_backend, rows, cols, step):
     assert np.array_equal(np.isnan(centers), np.isnan(ref_c)) and np.array_equal(centers[~np.isnan(ref_c)], ref_c[~np.isnan(ref_c)])
 
 
+def test_emu_slic_band_kernel_without_candidate_list():
+    """More centres around a strip than a warp has lanes make the band kernel hand every pixel of those rows to slic_resolve (old
+    labels kept under the marker, incl. pixels no window covers).  DCMT_SLIC_CAND_MAX lowers that limit so that ordinary frames take
+    the path -- 0: all rows, 6: some rows; a single frame through the band kernel as well (separate process: read once)."""
+    import os
+    import subprocess
+    import sys
+
+    from tests.conftest import ROOT
+
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "import numpy as np\n"
+        "from depth_completion_mt_b200 import _lib, api, synth\n"
+        "from oracle import c_oracle as co\n"
+        "from tests.emu import build_emu\n"
+        "lib = _lib.bind(build_emu.build())\n"
+        "lab = np.stack([synth.lab_image(70 + k, 50, 88) for k in range(2)])\n"
+        "lab[1, :, 40:] = 9\n"
+        "labels, centers = api.generate_superpixels(lab, 9, 30, return_centers=True, lib=lib)\n"
+        "for k in range(2):\n"
+        "    rl, rc = co.slic(lab[k], 9, 30)\n"
+        "    assert np.array_equal(labels[k], rl), (k, int((labels[k] != rl).sum()))\n"
+        "    assert np.array_equal(np.isnan(centers[k]), np.isnan(rc)) and np.array_equal(centers[k][~np.isnan(rc)], rc[~np.isnan(rc)]), k\n"
+        "print('CAND_OK')\n" % ROOT
+    )
+    for cand_max in ("0", "6"):
+        env = dict(os.environ, DCMT_SLIC_CAND_MAX=cand_max, DCMT_SLIC_BAND_MIN_FRAMES="1")
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900, env=env)
+        assert r.returncode == 0 and "CAND_OK" in r.stdout, r.stdout + r.stderr
+
+
 def test_emu_slic_tile_kernel(emu_lib):
-    check_tile_kernel(emu_lib, lambda a: a, 140, 232, 4)
+    check_tile_kernel(emu_lib, lambda a: a, 180, 280, 4)
 
 
 @pytest.mark.gpu
