@@ -1913,6 +1913,9 @@ size_t q8_guided_tile_flags(int rows, int cols, int th, int tw, int n_frames) {
 cudaError_t q8_run_guided_front(const Q8Plan& plan, const float* in, const uint16_t* in16, size_t in_pitch, size_t in_fstride,
                                 const int32_t* labels, int n_clusters, int n_frames, int validate, int* tile_flags, cudaStream_t st) {
     Q8Plan p = plan;
+    // DCMT_GUIDED_TILE_W: another tile width for the guided front (experiments; same bound as the plain front's)
+    static const int guided_w = [] { const char* e = getenv("DCMT_GUIDED_TILE_W"); return e ? atoi(e) / 8 * 8 : 0; }();
+    if (guided_w >= 8 && (guided_w / 8 + FLQ + FRQ) * 9 <= (GTL < GTW ? GTL : GTW)) p.tw = guided_w;
     p.th = q8_guided_tile_h(p.rows, p.th, p.tw);  // its own tiles: the kernels meet in the global intermediate plane
     const size_t ncol = (size_t)p.mid_pitch * n_frames;
     if (!p.counters_ready) DCMT_LAUNCH(k_q8_zero_counters, dim3((n_frames + 127) / 128), dim3(128), 0, st, p.ctr, n_frames);

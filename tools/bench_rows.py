@@ -85,6 +85,10 @@ def main():
     labs = torch.from_numpy(np.stack([synth.lab_image(f, rows, cols) for f in range(8)])).cuda().repeat(8, 1, 1, 1).contiguous()
     ms = gpu_time(lambda: api.generate_superpixels(labs, 18, 50, lib=lib), max(3, a.reps // 4))
     out.append({"row": "8f#1 Slic::generate_superpixels, batch of 64 frames", "step": 18, "iterations": 10, "ms": ms, "frames_per_s": 64e3 / ms})
+    labs256 = labs.repeat(4, 1, 1, 1).contiguous()
+    ms = gpu_time(lambda: api.generate_superpixels(labs256, 18, 50, lib=lib), 3)
+    out.append({"row": "8f#1 Slic::generate_superpixels, batch of 256 frames", "step": 18, "iterations": 10, "ms": ms, "frames_per_s": 256e3 / ms})
+    del labs256
     # ---- the DC_lidar_camera chain on device: SLIC -> guided completion -> evaluation, one frame (main_lc.cpp:184-225)
     sparse = torch.from_numpy(synth.sparse_depth(0, rows, cols, 0.05)).cuda()
     k = lib.dcmt_slic_center_count(rows, cols, 18)
