@@ -19,15 +19,15 @@ def k(v):
 
 
 rows = [
-    ("lidar_only (configs[1]), float32 q8 in; full line of the one-GPU session", [("r02_final_bench.json", 1)]),
-    ("lidar_only (configs[1]), N = 1 / 2 / 4 / 8 on ONE 8-GPU box, final kernels", [("r02_lidar_1gpu.json", 1), ("r02_lidar_2gpu.json", 2), ("r02_lidar_4gpu.json", 4), ("r02_lidar_8gpu.json", 8)]),
+    ("lidar_only (configs[1]), float32 q8 in; full line of the closing one-GPU session", [("r02_final_bench.json", 1)]),
+    ("lidar_only (configs[1]), N = 1 / 2 / 4 / 8 on ONE 8-GPU box (before the front's own tile width: + 2.5 % since)", [("r02_lidar_1gpu.json", 1), ("r02_lidar_2gpu.json", 2), ("r02_lidar_4gpu.json", 4), ("r02_lidar_8gpu.json", 8)]),
     ("lidar_only, uint16 in (device resident)", [("r02_final_bench_u16_input.json", 1)]),
     ("lidar_only, arbitrary float in (dictionary path)", [("r02_final_bench_float_rank.json", 1), ("r02_float_8gpu.json", 8)]),
     ("guided (configs[2])", [("r02_final_bench_guided.json", 1), ("r02_guided_8gpu.json", 8)]),
     ("guided, arbitrary float in", [("r02_final_bench_guided_float_rank.json", 1)]),
     ("stereo refinement (configs[3], a4-a9)", [("r02_final_bench_stereo.json", 1), ("r02_stereo_8gpu.json", 8)]),
-    ("stereo chain (configs[3]: projection -> guided float -> refinement), one-GPU session (before the projection gather fix)", [("r02_final_bench_stereo_chain.json", 1)]),
-    ("stereo chain, N = 1 / 8 on ONE 8-GPU box, final kernels", [("r02_chain_1gpu_same_box.json", 1), ("r02_chain_8gpu.json", 8)]),
+    ("stereo chain (configs[3]: projection -> guided float -> refinement), closing one-GPU session", [("r02_final_bench_stereo_chain.json", 1)]),
+    ("stereo chain, N = 1 / 8 on ONE 8-GPU box", [("r02_chain_1gpu_same_box.json", 1), ("r02_chain_8gpu.json", 8)]),
     ("sweep 352x1216 @ 1 %", [("r02_sweep_352x1216_p01_8gpu.json", 8)]),
     ("sweep 2048x4096 @ 1 %", [("r02_sweep_2048x4096_p01_8gpu.json", 8)]),
     ("sweep 2048x4096 @ 20 %", [("r02_sweep_2048x4096_p20_8gpu.json", 8)]),
