@@ -20,6 +20,7 @@ def k(v):
 
 rows = [
     ("lidar_only (configs[1]), float32 q8 in; full line of the closing one-GPU session", [("r02_final_bench.json", 1)]),
+    ("lidar_only (configs[1]), N = 1 / 8 on ONE 8-GPU box, closing kernels", [("r02_lidar_1gpu_closing.json", 1), ("r02_lidar_8gpu_closing.json", 8)]),
     ("lidar_only (configs[1]), N = 1 / 2 / 4 / 8 on ONE 8-GPU box (before the front's own tile width: + 2.5 % since)", [("r02_lidar_1gpu.json", 1), ("r02_lidar_2gpu.json", 2), ("r02_lidar_4gpu.json", 4), ("r02_lidar_8gpu.json", 8)]),
     ("lidar_only, uint16 in (device resident)", [("r02_final_bench_u16_input.json", 1)]),
     ("lidar_only, arbitrary float in (dictionary path)", [("r02_final_bench_float_rank.json", 1), ("r02_float_8gpu.json", 8)]),
