@@ -34,7 +34,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-BYTES_PER_PX = {"lidar_only": 8, "guided": 12, "stereo": 10, "stereo_chain": 14}  # SURVEY.md 8d (stereo_chain: a2 + a4-a9, 14 B/px)
+# SURVEY.md 8d (stereo_chain: a2 + a4-a9, 14 B/px; lidar_camera_chain: Lab image 3 + sparse 4 + dense 4 B/px, the labels stay on the device)
+BYTES_PER_PX = {"lidar_only": 8, "guided": 12, "stereo": 10, "stereo_chain": 14, "lidar_camera_chain": 11}
 METRIC = "frames/sec @1216x352 sparse depth"
 UNIQUE = 64
 
@@ -118,6 +119,8 @@ def _ref_inputs(f):
             lab, k = synth.superpixel_labels(f, rows, cols, 65)
             _, left, right = synth.stereo_pair(f, rows, cols)
             c[f] = (synth.velodyne_cloud(f, 120000), lab, k, left, right)
+        elif _W["workload"] == "lidar_camera_chain":
+            c[f] = (synth.sparse_depth(f, rows, cols, _W["density"]), synth.lab_image(f, rows, cols))
         else:
             c[f] = synth.stereo_pair(f, rows, cols)
     return c[f]
@@ -132,6 +135,15 @@ def _ref_task(f):
             out = impl.interpolate_with_superpixels(args[1], args[0], n_clusters=args[2])
         else:
             out = impl.interpolate_with_superpixels(args[0], args[1], args[2])
+    elif _W["workload"] == "lidar_camera_chain":
+        from oracle import c_oracle as co
+
+        if _W["kind"] == "ref":
+            labels, centers = impl.generate_superpixels(args[1], 18, 50)[:2]
+            out = impl.interpolate_with_superpixels(labels, args[0], n_clusters=len(centers))
+        else:
+            labels, centers = co.slic(args[1], 18, 50)
+            out = impl.interpolate_with_superpixels(args[0], labels, len(centers))
     elif _W["workload"] == "stereo_chain":
         synth = _W["synth"]
         pts, lab, k, left, right = args
@@ -168,14 +180,14 @@ def run_reference(args, quiet=False):
 
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     per_step = max(1, args.ref_frames_per_core) * cores
-    if args.workload == "guided":
+    if args.workload in ("guided", "lidar_camera_chain"):
         per_step = cores  # ~2 s per frame per core
     if args.workload == "stereo_chain":
         per_step = 2 * cores  # ~100 superpixels: about 0.25 s per frame per core
     ctx = mp.get_context("fork")
     with ctx.Pool(cores, initializer=_ref_worker_init, initargs=(args.workload, args.rows, args.cols, args.density)) as pool:
         kind = pool.apply(_kind)
-        single_ms = pool.apply(_single_frame_ms, (20 if args.workload != "guided" else 3,))
+        single_ms = pool.apply(_single_frame_ms, (20 if args.workload not in ("guided", "lidar_camera_chain") else 3,))
         frames = list(range(per_step))
         chunk = max(1, per_step // (cores * 2))
         for _ in range(max(1, args.warmup)):
@@ -219,6 +231,8 @@ def workload_config(args, frames_per_step_per_gpu):
     names = {"lidar_only": "DC_lidar_only img_completion, fused dilate/erode/fill/blur (BASELINE configs[1])",
              "guided": "DC_lidar_camera interpolate_with_superpixels (BASELINE configs[2])",
              "stereo": "DC_stereo_lidar disparity refinement (BASELINE configs[3])",
+             "lidar_camera_chain": "DC_lidar_camera chain: Slic::generate_superpixels (step 18, nc 50, 10 iterations) on the Lab image -> "
+                                   "interpolate_with_superpixels (main_lc.cpp:184-220; BASELINE configs[2])",
              "stereo_chain": "DC_stereo_lidar chain: LiDAR projection + cv::normalize -> interpolate_with_superpixels on the normalised floats -> "
                              "disparity refinement (main_sl.cpp:478-540,1162-1253; BASELINE configs[3])"}
     return {"workload": names[args.workload], "rows": args.rows, "cols": args.cols, "valid_density": args.density,
@@ -377,6 +391,24 @@ def run_ours(args):
         def step():
             holder["out"] = api.interpolate_with_superpixels(d_lab, d_in, "gaussian", 1, n_clusters=k, path=args.path, lib=lib)
         h2d, d2h = n * fpix * 8, n * fpix * 4
+    elif args.workload == "lidar_camera_chain":
+        # what the camera program runs per frame (main_lc.cpp:184-220): Lab image -> SLIC superpixels -> guided completion of the
+        # sparse depth with those labels; the labels never leave the device
+        uniq = np.stack([synth.sparse_depth(f, rows, cols, args.density) for f in range(UNIQUE)])
+        d_in = torch.from_numpy(uniq).to(dev).repeat(reps, 1, 1)[:n].contiguous()
+        d_labimg = torch.from_numpy(np.stack([synth.lab_image(f, rows, cols) for f in range(UNIQUE)])).to(dev).repeat(reps, 1, 1, 1)[:n].contiguous()
+        k = lib.dcmt_slic_center_count(rows, cols, 18)
+        holder = {}
+        CH = 256  # frames per SLIC call: bounds its per-frame work buffers
+
+        def step():
+            outs = []
+            for c0 in range(0, n, CH):
+                labels = api.generate_superpixels(d_labimg[c0:c0 + CH], 18, 50, lib=lib)
+                outs.append(api.interpolate_with_superpixels(labels, d_in[c0:c0 + CH], "gaussian", 1, n_clusters=k, path=args.path, lib=lib))
+            holder["out"] = torch.cat(outs) if len(outs) > 1 else outs[0]
+        h2d, d2h = n * fpix * 7, n * fpix * 4
+        args.no_e2e = True  # the chain has no single host entry point: its stages are the two calls above
     elif args.workload == "stereo_chain":
         # what the stereo program really runs per frame (main_sl.cpp:1150 withSuperPixels, :1162-1253): Velodyne cloud ->
         # projected depth image -> cv::normalize(0, 80) -> superpixel-guided completion of the normalised FLOATS (dictionary

@@ -26,6 +26,7 @@ rows = [
     ("lidar_only, arbitrary float in (dictionary path)", [("r02_final_bench_float_rank.json", 1), ("r02_float_8gpu.json", 8)]),
     ("guided (configs[2])", [("r02_final_bench_guided.json", 1), ("r02_guided_8gpu.json", 8)]),
     ("guided, arbitrary float in", [("r02_final_bench_guided_float_rank.json", 1)]),
+    ("DC_lidar_camera chain (configs[2]: SLIC on the Lab image -> guided completion)", [("r02_final_bench_lidar_camera_chain.json", 1)]),
     ("stereo refinement (configs[3], a4-a9)", [("r02_final_bench_stereo.json", 1), ("r02_stereo_8gpu.json", 8)]),
     ("stereo chain (configs[3]: projection -> guided float -> refinement), closing one-GPU session", [("r02_final_bench_stereo_chain.json", 1)]),
     ("stereo chain, N = 1 / 8 on ONE 8-GPU box", [("r02_chain_1gpu_same_box.json", 1), ("r02_chain_8gpu.json", 8)]),
