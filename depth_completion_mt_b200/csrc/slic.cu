@@ -335,6 +335,9 @@ __global__ void __launch_bounds__(256) k_slic_assign(const uint8_t* __restrict__
 #define DCMT_SLIC_BAND_THREADS 384
 #endif
 constexpr int kBandThreads = DCMT_SLIC_BAND_THREADS;
+#ifndef DCMT_SLIC_BAND_CTAS
+#define DCMT_SLIC_BAND_CTAS 2  // CTAs per SM the register allocation aims at
+#endif
 #ifndef DCMT_SLIC_CENT_SMEM
 #define DCMT_SLIC_CENT_SMEM 0  // 1: the centres in double precision in shared memory as well (slic_resolve reads them; + 40 bytes per centre)
 #endif
@@ -425,7 +428,7 @@ __device__ __noinline__ int slic_resolve(const BandView& v, int x, int y, unsign
     return best_k;
 }
 
-__global__ void __launch_bounds__(kBandThreads) k_slic_assign_band(const uint8_t* __restrict__ lab, int rows, int cols, int step, int nc,
+__global__ void __launch_bounds__(kBandThreads, DCMT_SLIC_BAND_CTAS) k_slic_assign_band(const uint8_t* __restrict__ lab, int rows, int cols, int step, int nc,
                                                                     int bx, int by, uint32_t step_magic, int band_rows,
                                                                     const int* __restrict__ offset, const int* __restrict__ items,
                                                                     const double* __restrict__ sorted, int32_t* __restrict__ labels,
