@@ -74,6 +74,28 @@ def check_tile_kernel(lib, to_backend, rows, cols, step):
     assert np.array_equal(np.isnan(centers), np.isnan(ref_c)) and np.array_equal(centers[~np.isnan(ref_c)], ref_c[~np.isnan(ref_c)])
 
 
+@pytest.mark.parametrize("rows,cols,step,nc,frames", [
+    (37, 70, 7, 20, 2),     # partial last strip (70 = 2 x 32 + 6), bands of a few rows
+    (12, 200, 5, 40, 3),    # low and wide: more bands than bins in y
+    (64, 33, 9, 10, 2),     # one pixel in the second strip
+    (90, 130, 31, 60, 2),   # step about as large as a strip: few, wide windows
+    (41, 97, 4, 5, 2),      # smallest step, colour dominates (nc small): many near ties on a noisy image
+    (6, 40, 4, 30, 2),      # a single row of centres
+])
+def test_emu_slic_band_kernel_shapes(emu_lib, rows, cols, step, nc, frames):
+    """The band kernel (batches) at shapes that stress its item walk: partial strips, bands of very few rows, steps from 4 to
+    strip width.  One frame of each batch is flat (every pixel deferred to slic_resolve), one has a flat half (long runs)."""
+    labs = np.stack([synth.lab_image(90 + f, rows, cols) for f in range(frames)])
+    labs[0, :, cols // 2:] = 40
+    if frames > 2:
+        labs[2] = 200
+    bl, bc = api.generate_superpixels(labs, step, nc, return_centers=True, lib=emu_lib)
+    for f in range(frames):
+        rl, rc = co.slic(labs[f], step, nc)
+        assert np.array_equal(bl[f], rl), f"frame {f}: {(bl[f] != rl).sum()} of {rl.size} labels differ"
+        assert np.array_equal(np.isnan(bc[f]), np.isnan(rc)) and np.array_equal(bc[f][~np.isnan(rc)], rc[~np.isnan(rc)]), f"centres {f}"
+
+
 def test_emu_slic_band_kernel_without_candidate_list():
     """More centres around a strip than a warp has lanes make the band kernel hand every pixel of those rows to slic_resolve (old
     labels kept under the marker, incl. pixels no window covers).  DCMT_SLIC_CAND_MAX lowers that limit so that ordinary frames take
