@@ -85,11 +85,16 @@ def check_tile_kernel(lib, to_backend, rows, cols, step):
 def test_emu_slic_band_kernel_shapes(emu_lib, rows, cols, step, nc, frames):
     """The band kernel (batches) at shapes that stress its item walk: partial strips, bands of very few rows, steps from 4 to
     strip width.  One frame of each batch is flat (every pixel deferred to slic_resolve), one has a flat half (long runs)."""
+    check_band_shapes(emu_lib, lambda a: a, rows, cols, step, nc, frames)
+
+
+def check_band_shapes(lib, to_backend, rows, cols, step, nc, frames):
     labs = np.stack([synth.lab_image(90 + f, rows, cols) for f in range(frames)])
     labs[0, :, cols // 2:] = 40
     if frames > 2:
         labs[2] = 200
-    bl, bc = api.generate_superpixels(labs, step, nc, return_centers=True, lib=emu_lib)
+    bl, bc = api.generate_superpixels(to_backend(labs), step, nc, return_centers=True, lib=lib)
+    bl, bc = (a if isinstance(a, np.ndarray) else a.cpu().numpy() for a in (bl, bc))
     for f in range(frames):
         rl, rc = co.slic(labs[f], step, nc)
         assert np.array_equal(bl[f], rl), f"frame {f}: {(bl[f] != rl).sum()} of {rl.size} labels differ"
@@ -146,3 +151,14 @@ def test_gpu_slic_tile_kernel(gpu_lib):
     import torch
 
     check_tile_kernel(gpu_lib, lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda(), 352, 1216, 10)
+
+
+@pytest.mark.gpu
+def test_gpu_slic_band_kernel_shapes(gpu_lib):
+    """The emulator's stress shapes on the device, plus KITTI raw size (1242 = 38 x 32 + 26 columns, 375 rows) in a small batch."""
+    import torch
+
+    to_dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    for case in [(37, 70, 7, 20, 2), (12, 200, 5, 40, 3), (64, 33, 9, 10, 2), (90, 130, 31, 60, 2), (41, 97, 4, 5, 2), (6, 40, 4, 30, 2),
+                 (375, 1242, 18, 50, 3)]:
+        check_band_shapes(gpu_lib, to_dev, *case)
