@@ -1063,9 +1063,12 @@ __global__ void __launch_bounds__(GT, kPerLabel ? DCMT_GUIDED_CTAS : 2) k_q8_gui
     }
 }
 
-__global__ void k_q8_init_cols(uint32_t* first, uint32_t* last, size_t n) {
+// set-up of a front launch in one kernel: the per-column keys and -- unless the caller did it (ctr == nullptr) -- the per-frame counters
+// (n >= n_frames: a frame has at least one column)
+__global__ void k_q8_init_cols(uint32_t* first, uint32_t* last, size_t n, FrameCounters* ctr, int n_frames) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { first[i] = 0xffffffffu; last[i] = 0u; }
+    if (ctr && i < (size_t)n_frames) { ctr[i] = FrameCounters{}; ctr[i].path = 1; }
 }
 
 // debugging / test aid: decode a uint16 plane back to float metres in inverted space
@@ -1875,8 +1878,8 @@ cudaError_t q8_run_front(const Q8Plan& plan, const float* in, const uint16_t* in
     }
     p.th = height_for(p.tw);
     const size_t ncol = (size_t)p.mid_pitch * n_frames;
-    if (!p.counters_ready) DCMT_LAUNCH(k_q8_zero_counters, dim3((n_frames + 127) / 128), dim3(128), 0, st, p.ctr, n_frames);
-    DCMT_LAUNCH(k_q8_init_cols, dim3((unsigned)((ncol + 255) / 256)), dim3(256), 0, st, p.col_first, p.col_last, ncol);
+    DCMT_LAUNCH(k_q8_init_cols, dim3((unsigned)((ncol + 255) / 256)), dim3(256), 0, st, p.col_first, p.col_last, ncol,
+                p.counters_ready ? nullptr : p.ctr, n_frames);
     // 16-byte vector loads need 16-byte aligned rows: 4 floats or 8 uint16 per unit
     const size_t unit = in16 ? 8 : 4;
     const uintptr_t base = in16 ? reinterpret_cast<uintptr_t>(in16) : reinterpret_cast<uintptr_t>(in);
@@ -1918,8 +1921,8 @@ cudaError_t q8_run_guided_front(const Q8Plan& plan, const float* in, const uint1
     if (guided_w >= 8 && (guided_w / 8 + FLQ + FRQ) * 9 <= (GTL < GTW ? GTL : GTW)) p.tw = guided_w;
     p.th = q8_guided_tile_h(p.rows, p.th, p.tw);  // its own tiles: the kernels meet in the global intermediate plane
     const size_t ncol = (size_t)p.mid_pitch * n_frames;
-    if (!p.counters_ready) DCMT_LAUNCH(k_q8_zero_counters, dim3((n_frames + 127) / 128), dim3(128), 0, st, p.ctr, n_frames);
-    DCMT_LAUNCH(k_q8_init_cols, dim3((unsigned)((ncol + 255) / 256)), dim3(256), 0, st, p.col_first, p.col_last, ncol);
+    DCMT_LAUNCH(k_q8_init_cols, dim3((unsigned)((ncol + 255) / 256)), dim3(256), 0, st, p.col_first, p.col_last, ncol,
+                p.counters_ready ? nullptr : p.ctr, n_frames);
     const size_t unit = in16 ? 8 : 4;
     const uintptr_t base = in16 ? reinterpret_cast<uintptr_t>(in16) : reinterpret_cast<uintptr_t>(in);
     const int RQ = p.tw / 8 + FLQ + FRQ;
