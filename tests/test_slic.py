@@ -133,8 +133,34 @@ def test_emu_slic_band_kernel_without_candidate_list():
         assert r.returncode == 0 and "CAND_OK" in r.stdout, r.stdout + r.stderr
 
 
-def test_emu_slic_tile_kernel(emu_lib):
-    check_tile_kernel(emu_lib, lambda a: a, 180, 280, 4)
+def test_emu_slic_tile_kernel_on_a_batch():
+    """Batches take the band kernel unless the frame's centres exceed its shared memory (the GPU test below does that at 352 x 1216,
+    step 10); here DCMT_SLIC_BAND_MIN_FRAMES keeps a small batch on the 16 x 16 tile kernel (separate process: read once)."""
+    import os
+    import subprocess
+    import sys
+
+    from tests.conftest import ROOT
+
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "import numpy as np\n"
+        "from depth_completion_mt_b200 import _lib, api, synth\n"
+        "from oracle import c_oracle as co\n"
+        "from tests.emu import build_emu\n"
+        "lib = _lib.bind(build_emu.build())\n"
+        "lab = np.stack([synth.lab_image(80 + k, 64, 96) for k in range(3)])\n"
+        "lab[2] = 5\n"
+        "labels, centers = api.generate_superpixels(lab, 10, 40, return_centers=True, lib=lib)\n"
+        "for k in range(3):\n"
+        "    rl, rc = co.slic(lab[k], 10, 40)\n"
+        "    assert np.array_equal(labels[k], rl), (k, int((labels[k] != rl).sum()))\n"
+        "    assert np.array_equal(np.isnan(centers[k]), np.isnan(rc)) and np.array_equal(centers[k][~np.isnan(rc)], rc[~np.isnan(rc)]), k\n"
+        "print('TILE_OK')\n" % ROOT
+    )
+    env = dict(os.environ, DCMT_SLIC_BAND_MIN_FRAMES="1000")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900, env=env)
+    assert r.returncode == 0 and "TILE_OK" in r.stdout, r.stdout + r.stderr
 
 
 @pytest.mark.gpu
