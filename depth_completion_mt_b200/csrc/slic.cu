@@ -5,7 +5,9 @@
 // centres whose window covers it (centres are binned on a step-sized grid each iteration; the covering ones lie in the
 // 3 x 3 bins around the pixel) and takes the minimum over (distance, index) -- the same result, all pixels in parallel.
 //   * window test exactly as written: k from (int)(cx - step) while k < cx + step (:123-124), double arithmetic;
-//   * distance exactly as compute_dist (:61-69): doubles, pow(x, 2) = x * x, sqrt, no FMA contraction;
+//   * distance exactly as compute_dist (:61-69) -- doubles, pow(x, 2) = x * x, sqrt, no FMA contraction -- wherever it decides:
+//     cheaper monotone stand-ins (without the square roots in double; in float in the band kernel) pick the winner only when
+//     their margin exceeds their own error bound, everything closer is re-evaluated in the reference's operation sequence;
 //   * pixels no window covers keep their previous label (the reference only resets `distances`, :115-119);
 //   * centre update (:141-171) sums integers (pixel values, coordinates): exact in any order, done with 64-bit
 //     integer atomics, then divided in double; an empty cluster becomes 0 / 0 = NaN and never wins a pixel again.
