@@ -184,6 +184,17 @@ def run_reference(args, quiet=False):
         per_step = cores  # ~2 s per frame per core
     if args.workload == "stereo_chain":
         per_step = 2 * cores  # ~100 superpixels: about 0.25 s per frame per core
+    if not quiet:
+        # --impl reference: load the reference build in THIS process as well (the work runs in forked workers), so that whoever lists
+        # the libraries this process loaded sees which implementation `kind` names.  Not in the GPU arm's cpu_baseline leg: that
+        # process is the product's, its list should show libdcmt.so alone.
+        try:
+            from oracle import cv2_oracle as _cvo, ref_oracle as _ro
+
+            if _cvo.HAVE_CV2 and _ro.available():
+                _ro.lib()
+        except Exception:
+            pass
     ctx = mp.get_context("fork")
     with ctx.Pool(cores, initializer=_ref_worker_init, initargs=(args.workload, args.rows, args.cols, args.density)) as pool:
         kind = pool.apply(_kind)
